@@ -1,0 +1,60 @@
+"""Array-level mirror of ``CloudMicrophysics.Microphysics2M`` (``CM2``): the SB2006
+leaf process rates and the 2-moment terminal velocities over device columns.
+
+The reference exports these as pointwise methods that hosts broadcast
+(test/gpu_tests.jl:220-235); here each name takes device columns.  All leaf rates
+of one state come out of ONE fused kernel launch (``sb2006_process_rates``); the
+per-process functions below are thin selections of its output columns so the
+reference's call sites read the same."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from . import parameters as CMP
+from ._columns import Tendencies, check_columns, ptr, ptr_table, stream_handle
+
+
+def sb2006_process_rates(mp, tps, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, which=None):
+    """All (or the named subset ``which`` of) ``_abi.SB2006_LEAVES`` for each point."""
+    cols = [rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai]
+    suf, n, dev = check_columns(cols, ["rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai"])
+    block = CMP.pack_2m_warm(mp, tps)
+    names = _abi.SB2006_LEAVES
+    which = list(names) if which is None else list(which)
+    outs = [torch.empty_like(rho) if nm in which else None for nm in names]
+    lib = _abi.load()
+    fn = getattr(lib, f"cumicro_sb2006_leaves_{suf}")
+    with torch.cuda.device(dev):
+        st = fn(C.byref(block), C.c_int64(n), *[ptr(c) for c in cols], ptr_table(outs), stream_handle(dev))
+    _abi.check(st, "cumicro_sb2006_leaves")
+    return Tendencies({nm: o for nm, o in zip(names, outs) if o is not None})
+
+
+def _termvel(fname, pdf, vel, q, rho, N):
+    suf, n, dev = check_columns([q, rho, N], ["q", "rho", "N"])
+    vt0, vt1 = torch.empty_like(q), torch.empty_like(q)
+    fn = getattr(_abi.load(), f"cumicro_{fname}_{suf}")
+    with torch.cuda.device(dev):
+        st = fn(C.byref(pdf), C.byref(vel), C.c_int64(n), ptr(q), ptr(rho), ptr(N), ptr(vt0), ptr(vt1),
+                stream_handle(dev))
+    _abi.check(st, f"cumicro_{fname}")
+    return vt0, vt1
+
+
+def rain_terminal_velocity(sb, vel, q_rai, rho, N_rai):
+    """CM2.rain_terminal_velocity(SB2006, vel, q_rai, ρ, N_rai) (CM2:685-719): returns
+    (number-weighted, mass-weighted) columns; ``vel`` is SB2006VelType or Chen2022VelTypeRain."""
+    kind = type(vel).__name__
+    if kind.startswith("cumicro_vel_sb2006"):
+        return _termvel("termvel_2m_rain_sb", sb.pdf_r, vel, q_rai, rho, N_rai)
+    if kind.startswith("cumicro_vel_chen_rain"):
+        return _termvel("termvel_2m_rain_chen", sb.pdf_r, vel, q_rai, rho, N_rai)
+    raise TypeError(f"unsupported velocity parameterisation {kind}")
+
+
+def cloud_terminal_velocity(pdf_c, vel, q_liq, rho, N_liq):
+    """CM2.cloud_terminal_velocity(pdf_c, ::StokesRegimeVelType, q_liq, ρₐ, N_liq) (CM2:647-664)."""
+    return _termvel("termvel_2m_cloud", pdf_c, vel, q_liq, rho, N_liq)

@@ -1,0 +1,121 @@
+// cm_launch.cuh — the one streaming kernel shape every cumicro family uses.
+//
+// All hot-path functions are pointwise over structure-of-arrays columns: NIN input
+// columns, NOUT output columns, n points, no coupling between points.  A family
+// supplies a functor F (parameters by value, constant-bank resident through the
+// __grid_constant__ kernel argument) with
+//     __device__ void operator()(const FT (&x)[NIN], FT (&y)[NOUT]) const;
+// and this header supplies the data movement:
+//   * one thread owns VEC = 16 B / sizeof(FT) consecutive points: every input column
+//     is read exactly once with one 128-bit ld.global.nc, every live output column is
+//     written exactly once with one 128-bit st.global.cs (streaming, never re-read);
+//   * all loads of an item are issued before any arithmetic, so 7-12 independent
+//     128-bit requests per thread are in flight while the FP64 pipe works on the
+//     previous item of other warps;
+//   * the VEC points of one thread are evaluated in one unrolled body so the compiler
+//     interleaves their (independent) FP64 dependency chains;
+//   * persistent grid-stride launch: blocks = SMs x resident blocks, so the grid is a
+//     whole number of waves on the 148 SMs;
+//   * a scalar variant covers misaligned columns and the n % VEC tail.
+// NULL output pointers are skipped (optional diagnostics columns).
+#pragma once
+#include <algorithm>
+
+#include "cm_types.cuh"
+
+namespace cm {
+
+template <class FT, int NIN, int NOUT, class F> struct PointwiseArgs {
+    F f;
+    const FT* in[NIN];
+    FT* out[NOUT];
+    int64_t n;
+};
+
+template <class FT, int NIN, int NOUT, class F, bool VECTOR, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int64_t first) {
+    constexpr int VEC = VECTOR ? vec<FT>::N : 1;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK;
+    const int64_t n_items = VECTOR ? (a.n / VEC) : (a.n - first);
+    for (int64_t it = (int64_t)blockIdx.x * BLOCK + threadIdx.x; it < n_items; it += stride) {
+        const int64_t i0 = VECTOR ? it * VEC : first + it;
+        FT x[VEC][NIN];
+        if constexpr (VECTOR) {
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) {
+                auto pk = ldg_vec(a.in[c] + i0);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) x[v][c] = pk.v[v];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) x[0][c] = __ldg(a.in[c] + i0);
+        }
+        FT y[VEC][NOUT];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a.f(x[v], y[v]);
+        if constexpr (VECTOR) {
+#pragma unroll
+            for (int c = 0; c < NOUT; ++c) {
+                if (a.out[c] == nullptr) continue;
+                pack<FT, VEC> pk;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) pk.v[v] = y[v][c];
+                st_vec(a.out[c] + i0, pk);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NOUT; ++c)
+                if (a.out[c]) a.out[c][i0] = y[0][c];
+        }
+    }
+}
+
+// Enqueue F over n points on `stream`.  BLOCK x MINB fixes the register budget
+// (65536 / (BLOCK*MINB) per thread); WAVES = resident-block multiples of the grid.
+template <class FT, int NIN, int NOUT, class F, int BLOCK = 256, int MINB = 1>
+int launch_pointwise(const F& f, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[NOUT], cudaStream_t stream,
+                     const char* what) {
+    if (n == 0) return CUMICRO_OK;
+    PointwiseArgs<FT, NIN, NOUT, F> a;
+    a.f = f;
+    a.n = n;
+    bool vec_ok = true;
+    for (int c = 0; c < NIN; ++c) { a.in[c] = in[c]; vec_ok = vec_ok && cmh::aligned16(in[c]); }
+    for (int c = 0; c < NOUT; ++c) { a.out[c] = out[c]; vec_ok = vec_ok && (out[c] == nullptr || cmh::aligned16(out[c])); }
+    constexpr int VEC = vec<FT>::N;
+    const int max_blocks = cmh::num_sms() * MINB * 4;  // 4 equal waves of the resident grid
+    int64_t first = 0;
+    if (vec_ok && n >= VEC) {
+        int64_t items = n / VEC;
+        int blocks = (int)std::min<int64_t>((items + BLOCK - 1) / BLOCK, max_blocks);
+        pointwise_kernel<FT, NIN, NOUT, F, true, BLOCK, MINB><<<blocks, BLOCK, 0, stream>>>(a, 0);
+        cmh::count_launch();
+        first = items * VEC;
+    }
+    if (first < n) {
+        int64_t items = n - first;
+        int blocks = (int)std::min<int64_t>((items + BLOCK - 1) / BLOCK, max_blocks);
+        pointwise_kernel<FT, NIN, NOUT, F, false, BLOCK, MINB><<<blocks, BLOCK, 0, stream>>>(a, first);
+        cmh::count_launch();
+    }
+    return cmh::cuda_status(cudaGetLastError(), what);
+}
+
+// Shared argument validation of the C-ABI entry points.
+template <class FT, int NIN>
+int validate_columns(const void* params, int64_t n, const FT* const (&in)[NIN]) {
+    if (params == nullptr) return cmh::fail(CUMICRO_E_NULL, "parameter block is NULL");
+    if (n < 0) return cmh::fail(CUMICRO_E_SIZE, "n = %lld is negative", (long long)n);
+    for (int c = 0; c < NIN; ++c)
+        if (n > 0 && in[c] == nullptr) return cmh::fail(CUMICRO_E_NULL, "input column %d is NULL", c);
+    return CUMICRO_OK;
+}
+template <class FT, int NOUT> int require_outputs(int64_t n, FT* const (&out)[NOUT], int n_required) {
+    for (int c = 0; c < n_required; ++c)
+        if (n > 0 && out[c] == nullptr) return cmh::fail(CUMICRO_E_NULL, "output column %d is NULL", c);
+    return CUMICRO_OK;
+}
+
+}  // namespace cm

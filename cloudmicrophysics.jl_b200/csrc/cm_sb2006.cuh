@@ -1,0 +1,355 @@
+// cm_sb2006.cuh — Seifert & Beheng (2006) 2-moment warm-rain processes and the
+// non-equilibrium condensation/evaporation relaxation, fused per grid point.
+//
+// Device form of BMT.warm_rain_tendencies_2m (BMT:707-782) and its callees:
+//   NEQ._conv_q_vap_to_q_lcl_const  NEQ:117-140     CM2.rain_evaporation  CM2:780-828
+//   CM2.autoconversion              CM2:396-427     CM2.accretion         CM2:445-470
+//   CM2.cloud_liquid_self_collection CM2:488-501    CM2.rain_self_collection CM2:545-560
+//   CM2.rain_breakup                CM2:579-601     CM2.number_tendency_from_mass_limits CM2:882-891
+//   CM2.pdf_rain_parameters         CM2:67-110      CM2.Γ_incl            CM2:746-753
+// The reference evaluates pdf_rain_parameters three times and the saturation
+// vapour pressure three times per point with identical arguments; here every
+// shared quantity is computed once.  Regime predicates use the same comparison
+// operators (<, <=, >=) on the same quantities as the reference.
+#pragma once
+#include "cm_thermo.cuh"
+
+namespace cm {
+
+// Per-launch constants derived on the host from the SB2006 parameter block.
+template <class FT> struct SB2006K {
+    FT acnv_pref;     // kcc/20/x_star (nu_c+2)(nu_c+4)/(nu_c+1)^2 rho0
+    FT inv_x_star;    // 1/acnv.x_star
+    FT lclsc_pref;    // kcc (nu_c+2)/(nu_c+1) rho0
+    FT pi_rho_w;      // pi rho_w (rain pdf)
+    FT six_over_pi_rho_w;
+    FT six_x_star_r;  // 6 * pdf_r.xr_min (evaporation t_star)
+    FT inv_xr_min;    // 1/pdf_r.xr_min
+    FT cbrt_Sc;       // cbrt(nu_air / max(D_vapor, eps))
+    FT inv_nu_air;
+    FT inv_K_safe, inv_D_safe;
+    FT gi_c1[2], gi_e1[2], gi_c2[2], gi_e2[2];  // Γ_incl coefficients for a = -1 and a = beta_vent_0
+    FT inv_numadj_tau;
+    FT inv_xc_min, inv_xc_max, inv_xr_max;
+    FT two_pi;
+};
+
+template <class FT>
+__host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, const typename P<FT>::air& aps) {
+    SB2006K<FT> k;
+    const FT pi = FT(3.141592653589793238462643383279502884L);
+    const FT nu_c = sb.pdf_c.nu_c;
+    k.acnv_pref = sb.acnv.kcc / 20 / sb.acnv.x_star * (nu_c + 2) * (nu_c + 4) / ((nu_c + 1) * (nu_c + 1)) * sb.acnv.rho0;
+    k.inv_x_star = FT(1) / sb.acnv.x_star;
+    k.lclsc_pref = sb.acnv.kcc * (nu_c + 2) / (nu_c + 1) * sb.acnv.rho0;
+    k.pi_rho_w = pi * sb.pdf_r.rho_w;
+    k.six_over_pi_rho_w = FT(6) / (pi * sb.pdf_r.rho_w);
+    k.six_x_star_r = FT(6) * sb.pdf_r.xr_min;
+    k.inv_xr_min = FT(1) / sb.pdf_r.xr_min;
+    const FT epsn = std::cbrt(std::numeric_limits<FT>::min());
+    k.cbrt_Sc = std::cbrt(aps.nu_air / std::max(aps.D_vapor, epsn));
+    k.inv_nu_air = FT(1) / aps.nu_air;
+    k.inv_K_safe = FT(1) / std::max(aps.K_therm, epsn);
+    k.inv_D_safe = FT(1) / std::max(aps.D_vapor, epsn);
+    const FT a[2] = {FT(-1), sb.evap.beta_vent_0};
+    for (int i = 0; i < 2; ++i) {
+        k.gi_c1[i] = FT(0.33) - FT(0.7) * a[i];
+        k.gi_e1[i] = FT(0.08) - FT(0.93) * a[i];
+        k.gi_c2[i] = FT(1.34) - FT(0.1) * a[i];
+        k.gi_e2[i] = FT(0.8) - a[i];
+    }
+    k.inv_numadj_tau = FT(1) / sb.numadj_tau;
+    k.inv_xc_min = FT(1) / sb.pdf_c.xc_min;
+    k.inv_xc_max = FT(1) / sb.pdf_c.xc_max;
+    k.inv_xr_max = FT(1) / sb.pdf_r.xr_max;
+    k.two_pi = 2 * pi;
+    return k;
+}
+
+template <class FT> struct RainPDF { FT N0r, Dr_mean, xr_mean, lam; };
+
+// CM2.pdf_rain_parameters                                          CM2:67-110
+template <class FT>
+CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT pi_rho_w, FT q, FT rho, FT N) {
+    const FT e = num<FT>::eps();
+    FT safe_q = fmax_(q, e);
+    FT safe_N = fmax_(N, e);
+    FT L = rho * safe_q;
+    RainPDF<FT> r;
+    if (!pdf.limited) {
+        FT xr_mean = L / safe_N;
+        FT lam = cbrt_(pi_rho_w / xr_mean);
+        bool cond = (N < e) || (q < e);
+        r.lam = lam;
+        r.N0r = cond ? FT(0) : lam * safe_N;
+        r.Dr_mean = cond ? FT(0) : rcp_(lam);
+        r.xr_mean = cond ? FT(0) : xr_mean;
+    } else {
+        FT xt = clamp_(L / safe_N, pdf.xr_min, pdf.xr_max);                        // SB2006 Eq. (94)
+        FT N0r = clamp_(safe_N * cbrt_(pi_rho_w / xt), pdf.N0_min, pdf.N0_max);    // Eq. (95)
+        FT lam = clamp_(sqrt_(sqrt_(pi_rho_w * N0r / L)), pdf.lam_min, pdf.lam_max);  // Eq. (96)
+        FT xr_mean = clamp_(L * lam / N0r, pdf.xr_min, pdf.xr_max);                // Eq. (97)
+        bool cond = (N < e) && (q < e);
+        r.lam = lam;
+        r.N0r = cond ? FT(0) : N0r;
+        r.Dr_mean = cond ? FT(0) : rcp_(lam);
+        r.xr_mean = cond ? FT(0) : xr_mean;
+    }
+    return r;
+}
+
+// CM2.number_tendency_from_mass_limits                              CM2:882-891
+template <class FT> CM_DEV FT number_tendency_from_mass_limits(FT inv_x_min, FT inv_x_max, FT inv_tau, FT q, FT n) {
+    FT n_target = (q < num<FT>::eps()) ? FT(0) : clamp_(n, q * inv_x_max, q * inv_x_min);
+    return (n_target - n) * inv_tau;
+}
+
+template <class FT> struct Warm2M {
+    FT dq_lcl_dt, dn_lcl_dt, dq_rai_dt, dn_rai_dt;
+    FT leaf[CUMICRO_SB2006_NLEAF];
+};
+
+// BMT.bulk_microphysics_tendencies(::Microphysics2Moment, mp{WR,Nothing}, ...)  BMT:820-854
+// q_ice is the cloud-ice content seen by the thermodynamics (0 for warm-only).
+template <class FT>
+CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& p, const ThermoK<FT>& tk,
+                                          const SB2006K<FT>& sk, FT rho, FT T, FT q_tot, FT q_lcl, FT n_lcl,
+                                          FT q_rai, FT n_rai, FT q_ice) {
+    const FT e = num<FT>::eps();
+    const auto& sb = p.sb;
+    Warm2M<FT> o;
+
+    // input clamps                                                   BMT:827-836
+    rho = fmax_(FT(0), rho);
+    q_tot = fmax_(FT(0), q_tot);
+    q_lcl = fmax_(FT(0), q_lcl);
+    q_rai = fmax_(FT(0), q_rai);
+    n_lcl = fmax_(FT(0), n_lcl);
+    n_rai = fmax_(FT(0), n_rai);
+    const FT N_lcl = rho * n_lcl;   // BMT:718-719
+    const FT N_rai = rho * n_rai;
+    const FT inv_rho = rcp_(rho);
+
+    // ---- thermodynamic state shared by cond/evap and rain evaporation
+    const TempState<FT> ts = temp_state(tk, T);
+    const FT p_vs = p_sat_liq(tk, ts);
+    const FT Lv = latent_heat_vapor(tk, T);
+    const FT q_liq = q_lcl + q_rai;
+    const FT qv = q_vap(q_tot, q_liq, q_ice);
+    const FT rho_Rv_T = rho * tk.R_v * T;
+
+    // ---- NEQ._conv_q_vap_to_q_lcl_const                            NEQ:117-140
+    {
+        FT cp_air = cp_m(tk, q_tot, q_liq, q_ice);
+        FT qv_sat = p_vs * rcp_(rho_Rv_T);
+        FT dqsl_dT = qv_sat * (Lv * tk.inv_R_v * ts.inv_T * ts.inv_T - ts.inv_T);  // NEQ.dqcld_dT
+        FT Gam = FT(1) + Lv * rcp_(cp_air) * dqsl_dT;                                 // NEQ.gamma_helper
+        FT sat_excess = qv - qv_sat;
+        FT inv_ts = rcp_(p.condevap_tau_relax * Gam);
+        FT cond = (sat_excess < FT(0)) ? -fmin_(-sat_excess, q_lcl) * inv_ts : sat_excess * inv_ts;
+        o.leaf[CUMICRO_SB_COND_DQ_LCL] = cond;
+    }
+
+    // ---- rain size distribution (shared by evaporation, self-collection, breakup)
+    const FT safe_q_rai = fmax_(q_rai, e);
+    const FT safe_N_rai = fmax_(N_rai, e);
+    const RainPDF<FT> rp = pdf_rain_parameters<FT>(sb.pdf_r, sk.pi_rho_w, safe_q_rai, rho, safe_N_rai);
+    const FT xr_mean = rp.xr_mean;
+    const FT inv_xr_mean = rcp_(xr_mean);
+    const FT Dr = cbrt_(xr_mean * sk.six_over_pi_rho_w);  // mean-volume diameter  CM2:590, 802
+    const FT sqrt_rho0_rho = sqrt_(sb.pdf_r.rho0 * inv_rho);
+    const bool no_rain = (q_rai < e) || (N_rai < e);
+
+    // ---- CM2.rain_evaporation                                       CM2:780-828
+    {
+        FT S = qv * rho_Rv_T * rcp_(p_vs) - FT(1);                     // TDI.supersaturation_over_liquid
+        FT G = G_func(tk, sk.inv_K_safe, sk.inv_D_safe, Lv, p_vs, ts);  // CO.G_func_liquid
+        FT t_star = cbrt_(sk.six_x_star_r * inv_xr_mean);
+        // Γ_incl(a, t) = exp(-t) / (c1 t^e1 + c2 t^e2), a ∈ {-1, beta_vent_0}   CM2:746-753
+        FT lt = log_(t_star);
+        FT emt = exp_(-t_star);
+        FT gi0 = emt * rcp_(sk.gi_c1[0] * exp_(sk.gi_e1[0] * lt) + sk.gi_c2[0] * exp_(sk.gi_e2[0] * lt));
+        FT gi1 = emt * rcp_(sk.gi_c1[1] * exp_(sk.gi_e1[1] * lt) + sk.gi_c2[1] * exp_(sk.gi_e2[1] * lt));
+        FT a_vent_0 = sb.evap.a_vent_0_coeff * gi0;
+        FT b_vent_0 = sb.evap.b_vent_0_coeff * gi1;
+        FT sqrt_rho0e = (sb.evap.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.evap.rho0 * inv_rho);
+        FT N_Re = sb.evap.alpha * pow_(xr_mean, sb.evap.beta) * sqrt_rho0e * Dr * sk.inv_nu_air;
+        FT v = sk.cbrt_Sc * sqrt_(N_Re);
+        FT Fv0 = a_vent_0 + b_vent_0 * v;
+        FT Fv1 = sb.evap.a_vent_1 + sb.evap.b_vent_1 * v;
+        FT common = sk.two_pi * G * S * N_rai * Dr;
+        FT dn = fmin_(FT(0), common * Fv0 * inv_xr_mean);
+        FT dq = fmin_(FT(0), common * Fv1 * inv_rho);
+        bool off_q = (q_rai < e) || (N_rai <= e) || (S >= FT(0));
+        bool off_n = off_q || (xr_mean * sk.inv_xr_min < e);
+        o.leaf[CUMICRO_SB_EVAP_DN_RAI] = off_n ? FT(0) : dn;
+        o.leaf[CUMICRO_SB_EVAP_DQ_RAI] = off_q ? FT(0) : dq;
+    }
+
+    // ---- CM2.autoconversion + CM2.accretion (shared tau)             CM2:396-470
+    {
+        FT safe_q_lcl = fmax_(q_lcl, e);
+        FT safe_N_lcl = fmax_(N_lcl, e);
+        FT L_lcl = rho * safe_q_lcl;
+        FT xbar = L_lcl * rcp_(safe_N_lcl);
+        FT x_lcl = fmin_(sb.acnv.x_star, xbar);
+        FT one_m_tau = safe_q_lcl * rcp_(safe_q_lcl + q_rai);  // q_rai >= 0 after the input clamp
+        FT tau = FT(1) - one_m_tau;                             // SB2006 Eq. (5)
+        FT tau_a = pow_(tau, sb.acnv.a);
+        FT phi_au = (q_rai < e) ? FT(0) : sb.acnv.A * tau_a * pow_param(FT(1) - tau_a, sb.acnv.b);
+        FT LL = L_lcl * L_lcl;
+        FT dL_rai_dt = sk.acnv_pref * LL * (x_lcl * x_lcl) *
+                       (FT(1) + phi_au * rcp_(one_m_tau * one_m_tau)) * inv_rho;   // Eq. (4)
+        FT dN_rai_dt = dL_rai_dt * sk.inv_x_star;
+        bool off = (q_lcl < e) || (N_lcl < e);
+        FT dq = off ? FT(0) : dL_rai_dt * inv_rho;
+        FT dN_rai = off ? FT(0) : dN_rai_dt;
+        FT dN_lcl_au = off ? FT(0) : FT(-2) * dN_rai_dt;
+        o.leaf[CUMICRO_SB_ACNV_DQ_LCL] = -dq;
+        o.leaf[CUMICRO_SB_ACNV_DN_LCL] = dN_lcl_au;
+        o.leaf[CUMICRO_SB_ACNV_DQ_RAI] = dq;
+        o.leaf[CUMICRO_SB_ACNV_DN_RAI] = dN_rai;
+
+        // CM2.cloud_liquid_self_collection (uses the unclamped q_lcl)   CM2:488-501
+        FT Lu = rho * q_lcl;
+        FT sc = -sk.lclsc_pref * inv_rho * (Lu * Lu) - dN_lcl_au;
+        o.leaf[CUMICRO_SB_LCL_SELFCOL] = (q_lcl < e) ? FT(0) : sc;
+
+        // CM2.accretion                                                  CM2:445-470
+        FT L_rai = rho * safe_q_rai;
+        FT sqrt_rho0a = (sb.accr.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.accr.rho0 * inv_rho);
+        FT phi_ac = pow_param(tau * rcp_(tau + sb.accr.tau0), sb.accr.c);     // Eq. (8)
+        FT dLr = sb.accr.kcr * L_lcl * L_rai * phi_ac * sqrt_rho0a;          // Eq. (7)
+        bool off_ac = (q_lcl < e) || (q_rai < e) || (N_lcl < e);
+        FT dq_ac = off_ac ? FT(0) : dLr * inv_rho;
+        o.leaf[CUMICRO_SB_ACCR_DQ_LCL] = -dq_ac;
+        o.leaf[CUMICRO_SB_ACCR_DN_LCL] = off_ac ? FT(0) : -dLr * safe_N_lcl * rcp_(L_lcl);  // dL_lcl_dt / x_lcl
+        o.leaf[CUMICRO_SB_ACCR_DQ_RAI] = dq_ac;
+    }
+
+    // ---- CM2.rain_self_collection / rain_breakup                       CM2:545-601
+    {
+        FT L_rai = rho * safe_q_rai;
+        FT inv_Br = cbrt_(xr_mean * FT(1.0 / 6.0));   // 1/Br, Br = cbrt(6/xr_mean)   CM2:141-146
+        FT sc = -sb.self.krr * N_rai * L_rai * sqrt_rho0_rho * pow_param(FT(1) + sb.self.kappa_rr * inv_Br, sb.self.d);
+        sc = no_rain ? FT(0) : sc;
+        FT dD = Dr - sb.brek.Deq;
+        FT phi_p1 = (Dr < sb.brek.Dr_th) ? FT(0)
+                                         : ((Dr <= sb.brek.Deq) ? sb.brek.kbr * dD + FT(1) : exp_(sb.brek.kappa_br * dD));
+        FT br = no_rain ? FT(0) : -phi_p1 * sc;   // Eq. (13): -(Φ_br + 1) dN_sc
+        o.leaf[CUMICRO_SB_RAI_SELFCOL] = sc;
+        o.leaf[CUMICRO_SB_RAI_BREAKUP] = br;
+    }
+
+    // ---- number adjustment (Horn 2012)                                 BMT:771-779
+    o.leaf[CUMICRO_SB_NUMADJ_LCL] =
+        number_tendency_from_mass_limits<FT>(sk.inv_xc_min, sk.inv_xc_max, sk.inv_numadj_tau, q_lcl, n_lcl);
+    o.leaf[CUMICRO_SB_NUMADJ_RAI] =
+        number_tendency_from_mass_limits<FT>(sk.inv_xr_min, sk.inv_xr_max, sk.inv_numadj_tau, q_rai, n_rai);
+
+    // ---- aggregate in the order of BMT:736-779
+    o.dq_lcl_dt = o.leaf[CUMICRO_SB_COND_DQ_LCL] + o.leaf[CUMICRO_SB_ACNV_DQ_LCL] + o.leaf[CUMICRO_SB_ACCR_DQ_LCL];
+    o.dq_rai_dt = o.leaf[CUMICRO_SB_EVAP_DQ_RAI] + o.leaf[CUMICRO_SB_ACNV_DQ_RAI] + o.leaf[CUMICRO_SB_ACCR_DQ_RAI];
+    o.dn_lcl_dt = (o.leaf[CUMICRO_SB_ACNV_DN_LCL] + o.leaf[CUMICRO_SB_LCL_SELFCOL] + o.leaf[CUMICRO_SB_ACCR_DN_LCL]) * inv_rho +
+                  o.leaf[CUMICRO_SB_NUMADJ_LCL];
+    o.dn_rai_dt = (o.leaf[CUMICRO_SB_EVAP_DN_RAI] + o.leaf[CUMICRO_SB_ACNV_DN_RAI] + o.leaf[CUMICRO_SB_RAI_SELFCOL] +
+                   o.leaf[CUMICRO_SB_RAI_BREAKUP]) * inv_rho +
+                  o.leaf[CUMICRO_SB_NUMADJ_RAI];
+    return o;
+}
+
+}  // namespace cm
+
+// ============================ 2-moment terminal velocities ============================
+namespace cm {
+
+// CM2.rain_terminal_velocity(::SB2006, ::SB2006VelType, q_rai, rho, N_rai)   CM2:685-702
+// (+ _sb_rain_terminal_velocity_helper CM2:720-739: limited -> (1,1,1,1)).
+template <class FT>
+CM_DEV void rain_terminal_velocity_sb(const typename P<FT>::sb_pdf_r& pdf_r, const typename P<FT>::vel_sb2006& vel,
+                                      FT pi_rho_w, FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) {
+    const FT e = num<FT>::eps();
+    const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, fmax_(q_rai, e), rho, fmax_(N_rai, e));
+    const FT Dr_mean = r.Dr_mean;
+    FT pa0 = FT(1), pb0 = FT(1), pa1 = FT(1), pb1 = FT(1);
+    if (!pdf_r.limited) {
+        const FT lam = rcp_(Dr_mean);
+        const FT two_rc = -log_(vel.aR / vel.bR) / vel.cR;  // 2 rc, rc = -1/(2 cR) log(aR/bR)
+        const FT ta = two_rc * lam, tb = two_rc * (lam + vel.cR);
+        const FT ea = exp_(-ta), eb = exp_(-tb);
+        pa0 = ea;
+        pb0 = eb;
+        pa1 = (ta * ta * ta + FT(3) * (ta * ta) + FT(6) * ta + FT(6)) * ea / FT(6);
+        pb1 = (tb * tb * tb + FT(3) * (tb * tb) + FT(6) * tb + FT(6)) * eb / FT(6);
+    }
+    const FT s = sqrt_(vel.rho0 / rho);
+    const FT d1 = FT(1) + vel.cR * Dr_mean;
+    const FT d2 = d1 * d1;
+    const FT v0 = fmax_(FT(0), s * (vel.aR * pa0 - vel.bR * pb0 / d1));
+    const FT v1 = fmax_(FT(0), s * (vel.aR * pa1 - vel.bR * pb1 / (d2 * d2)));
+    vt0 = (N_rai < e) ? FT(0) : v0;
+    vt1 = (q_rai < e) ? FT(0) : v1;
+}
+
+// CO.Chen2022_vel_coeffs(::Chen2022VelTypeRain, rho)                      CO:290-300
+template <class FT>
+CM_DEV void chen2022_vel_coeffs_rain(const typename P<FT>::vel_chen_rain& v, FT rho, FT aiu[3], FT bi[3], FT ciu[3]) {
+    rho = fmax_(rho, FT(0));
+    const FT q = exp_(v.rho0 * rho);
+    const FT log1000 = FT(6.907755278982137);
+    FT ai[3] = {v.a[0] * q, v.a[1] * q, v.a[2] * q * pow_(rho, v.a3_pow)};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        bi[i] = v.b[i] - v.b_rho * rho;
+        aiu[i] = ai[i] * exp_(bi[i] * log1000);  // 1000^bi
+        ciu[i] = v.c[i] * FT(1000);
+    }
+}
+
+// CO.Chen2022_exponential_pdf(a, b, c, lam_inv, k), k! passed as inv_fac    CO:414-422
+template <class FT> CM_DEV FT chen2022_exponential_pdf(FT a, FT b, FT c, FT log_lam_inv, FT inv_lam_inv, FT delta, FT inv_fac) {
+    return a * exp_(-delta * log_lam_inv - (b + delta) * log_(inv_lam_inv + c)) * tgamma_(b + delta) * inv_fac;
+}
+
+// CM2.rain_terminal_velocity(::SB2006, ::Chen2022VelTypeRain, ...)          CM2:703-719
+template <class FT>
+CM_DEV void rain_terminal_velocity_chen(const typename P<FT>::sb_pdf_r& pdf_r, const typename P<FT>::vel_chen_rain& vel,
+                                        FT pi_rho_w, FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) {
+    const FT e = num<FT>::eps();
+    FT aiu[3], bi[3], ciu[3];
+    chen2022_vel_coeffs_rain<FT>(vel, rho, aiu, bi, ciu);
+    const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, fmax_(q_rai, e), rho, fmax_(N_rai, e));
+    const FT ll = log_(r.Dr_mean), il = rcp_(r.Dr_mean);
+    FT v0 = FT(0), v3 = FT(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v0 += chen2022_exponential_pdf<FT>(aiu[i], bi[i], ciu[i], ll, il, FT(1), FT(1));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v3 += chen2022_exponential_pdf<FT>(aiu[i], bi[i], ciu[i], ll, il, FT(4), FT(1.0 / 6.0));
+    vt0 = (N_rai < e) ? FT(0) : fmax_(FT(0), v0);
+    vt1 = (q_rai < e) ? FT(0) : fmax_(FT(0), v3);
+}
+
+// CM2.cloud_terminal_velocity                                               CM2:647-664
+// with CM2.log_pdf_cloud_parameters_mass (CM2:176-190) and DT.generalized_gamma_Mn (DT:109-112).
+// `gratio[2]` = Gamma((nu+1+n)/mu)/Gamma((nu+1)/mu) for n = 2/3, 5/3 and `pref0` =
+// 1/18 cbrt((6/rho_w/pi)^2) grav/nu_air are parameter-only (host-side).
+template <class FT>
+CM_DEV void cloud_terminal_velocity(const typename P<FT>::sb_pdf_c& pdf_c, const typename P<FT>::vel_stokes& vel,
+                                    FT pref0, const FT gratio[2], FT q_liq, FT rho, FT N_liq, FT& vt0, FT& vt1) {
+    const FT e = num<FT>::eps();
+    const FT safe_q = fmax_(q_liq, e), safe_N = fmax_(N_liq, e);
+    const FT logx = log_(rho * safe_q / safe_N);
+    const FT logB = -pdf_c.mu_c * (logx + pdf_c.loggamma_z1 - pdf_c.loggamma_z2);
+    const FT pref = pref0 * (vel.rho_w / rho - FT(1));
+    const FT inv_mu = rcp_(pdf_c.mu_c);
+    // M^n / N = B^(-n/mu) * gratio
+    const FT m23 = exp_(-(FT(2.0 / 3.0) * inv_mu) * logB) * gratio[0];
+    const FT m53 = exp_(-(FT(5.0 / 3.0) * inv_mu) * logB) * gratio[1];
+    const FT v0 = pref * m23;
+    const FT v1 = pref * (safe_N * m53) / rho / safe_q;
+    const bool cond = (N_liq < e) || (q_liq < e);
+    vt0 = cond ? FT(0) : v0;
+    vt1 = cond ? FT(0) : v1;
+}
+
+}  // namespace cm

@@ -1,0 +1,76 @@
+// cm_thermo.cuh — moist thermodynamics needed by the tendency kernels.
+//
+// Device form of what the reference reaches through src/ThermodynamicsInterface.jl
+// (TDI:9-33, 60-125), i.e. Thermodynamics.jl's saturation vapour pressure, latent
+// heats, cp_m and supersaturation (formulas: SURVEY.md §A.1).
+//
+// ThermoK holds per-launch constants derived on the host (cm::make_thermo_k) so
+// no thread spends FP64 divisions on parameter-only expressions.
+#pragma once
+#include "cm_types.cuh"
+
+namespace cm {
+
+template <class FT> struct ThermoK {
+    FT T_0, T_triple, inv_T_triple, press_triple, T_freeze, R_v, inv_R_v;
+    FT cp_d, dcp_vd, dcp_lv, dcp_iv;  // cp_d, cp_v-cp_d, cp_l-cp_v, cp_i-cp_v
+    FT LH_v0, LH_s0, dcp_vl, dcp_vi;  // cp_v-cp_l, cp_v-cp_i
+    FT a_liq, b_liq, a_ice, b_ice;    // p_sat exponents: dcp/R_v, (LH_0 - dcp T_0)/R_v
+    FT cv_l, q_min, LH_f0, dcp_li;    // cp_l; q_min; LH_s0-LH_v0; cp_l-cp_i
+};
+
+template <class FT> __host__ inline ThermoK<FT> make_thermo_k(const typename P<FT>::thermo& t) {
+    ThermoK<FT> k;
+    k.T_0 = t.T_0; k.T_triple = t.T_triple; k.inv_T_triple = FT(1) / t.T_triple;
+    k.press_triple = t.press_triple; k.T_freeze = t.T_freeze;
+    k.R_v = t.R_v; k.inv_R_v = FT(1) / t.R_v;
+    k.cp_d = t.cp_d; k.dcp_vd = t.cp_v - t.cp_d; k.dcp_lv = t.cp_l - t.cp_v; k.dcp_iv = t.cp_i - t.cp_v;
+    k.LH_v0 = t.LH_v0; k.LH_s0 = t.LH_s0; k.dcp_vl = t.cp_v - t.cp_l; k.dcp_vi = t.cp_v - t.cp_i;
+    k.a_liq = k.dcp_vl / t.R_v; k.b_liq = (t.LH_v0 - k.dcp_vl * t.T_0) / t.R_v;
+    k.a_ice = k.dcp_vi / t.R_v; k.b_ice = (t.LH_s0 - k.dcp_vi * t.T_0) / t.R_v;
+    k.cv_l = t.cp_l; k.q_min = t.q_min; k.LH_f0 = t.LH_s0 - t.LH_v0; k.dcp_li = t.cp_l - t.cp_i;
+    return k;
+}
+
+// Temperature-dependent quantities shared by every process at one grid point.
+template <class FT> struct TempState {
+    FT T, inv_T, log_Tr, dinvT;  // log(T/T_triple), 1/T_triple - 1/T
+};
+
+template <class FT> CM_DEV TempState<FT> temp_state(const ThermoK<FT>& k, FT T) {
+    TempState<FT> s;
+    s.T = T;
+    s.inv_T = rcp_(T);
+    s.log_Tr = log_(T * k.inv_T_triple);
+    s.dinvT = (T - k.T_triple) * s.inv_T * k.inv_T_triple;  // = 1/T_triple - 1/T without cancellation
+    return s;
+}
+
+// TD.saturation_vapor_pressure(tps, T, Liquid()/Ice()):
+//   p_triple (T/T_triple)^(dcp/R_v) exp((LH_0 - dcp T_0)/R_v (1/T_triple - 1/T))
+// evaluated as a single exponential.
+template <class FT> CM_DEV FT p_sat_liq(const ThermoK<FT>& k, const TempState<FT>& s) {
+    return k.press_triple * exp_(k.a_liq * s.log_Tr + k.b_liq * s.dinvT);
+}
+template <class FT> CM_DEV FT p_sat_ice(const ThermoK<FT>& k, const TempState<FT>& s) {
+    return k.press_triple * exp_(k.a_ice * s.log_Tr + k.b_ice * s.dinvT);
+}
+template <class FT> CM_DEV FT latent_heat_vapor(const ThermoK<FT>& k, FT T) { return k.LH_v0 + k.dcp_vl * (T - k.T_0); }
+template <class FT> CM_DEV FT latent_heat_sublim(const ThermoK<FT>& k, FT T) { return k.LH_s0 + k.dcp_vi * (T - k.T_0); }
+template <class FT> CM_DEV FT latent_heat_fusion(const ThermoK<FT>& k, FT T) { return k.LH_f0 + k.dcp_li * (T - k.T_0); }
+template <class FT> CM_DEV FT cp_m(const ThermoK<FT>& k, FT qt, FT ql, FT qi) {
+    return k.cp_d + k.dcp_vd * qt + k.dcp_lv * ql + k.dcp_iv * qi;
+}
+// TDI.q_vap                                                       TDI:60-61
+template <class FT> CM_DEV FT q_vap(FT qt, FT ql, FT qi) { return fmax_(FT(0), qt - ql - qi); }
+
+// CO.G_func_liquid / G_func_ice                                    CO:47-102
+//   1 / (L/K/T (L/R_v/T - 1) + R_v T / D / p_vs), with the reference's eps floors.
+template <class FT>
+CM_DEV FT G_func(const ThermoK<FT>& k, FT inv_K_safe, FT inv_D_safe, FT L, FT p_vs, const TempState<FT>& s) {
+    FT p_vs_safe = fmax_(p_vs, num<FT>::eps_numerics());
+    FT LT = L * s.inv_T;
+    return rcp_(LT * inv_K_safe * (LT * k.inv_R_v - FT(1)) + k.R_v * s.T * inv_D_safe * rcp_(p_vs_safe));
+}
+
+}  // namespace cm

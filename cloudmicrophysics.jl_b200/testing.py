@@ -1,0 +1,175 @@
+"""Synthetic atmospheric states and parity metrics shared by tests/, bench.py and
+``__graft_entry__.smoke()``.  Pure numpy; nothing here touches the CUDA library or
+the oracle.
+
+States follow the reference's own generator ``generate_atmospheric_states``
+(test/gpu_performance.jl:80-136): a 0-15 km column with a decaying temperature
+profile, RH swept 0.05..1.05, condensate = saturation excess + U(0,1)*1e-4.  Julia's
+MersenneTwister stream is not reproducible here, so PCG64 with the same seed (1234)
+is used and both the CPU and GPU paths always see the same generated bits."""
+from __future__ import annotations
+
+import numpy as np
+
+from .parameters import DEFAULTS
+
+F64_RTOL = 1e-12   # north-star Float64 tolerance (relative)
+F32_ULPS = 4       # north-star Float32 tolerance (ULP-equivalent)
+
+
+def _psat(T, LH0, dcp):
+    d = DEFAULTS
+    Rv, T0, Tt, pt = d["gas_constant_vapor"], d["thermodynamics_temperature_reference"], d["temperature_triple_point"], d["pressure_triple_point"]
+    return pt * (T / Tt) ** (dcp / Rv) * np.exp((LH0 - dcp * T0) / Rv * (1 / Tt - 1 / T))
+
+
+def psat_liq(T):
+    d = DEFAULTS
+    return _psat(T, d["latent_heat_vaporization_at_reference"], d["isobaric_specific_heat_vapor"] - d["isobaric_specific_heat_liquid"])
+
+
+def psat_ice(T):
+    d = DEFAULTS
+    return _psat(T, d["latent_heat_sublimation_at_reference"], d["isobaric_specific_heat_vapor"] - d["isobaric_specific_heat_ice"])
+
+
+def atmospheric_profile(n, rng):
+    """(T, p, rho, q_vap, q_sat_liq, q_sat_ice) for n points, test/gpu_performance.jl:80-118."""
+    d = DEFAULTS
+    Rd, Rv, g = d["gas_constant_dry_air"], d["gas_constant_vapor"], d["gravitational_acceleration"]
+    z = np.linspace(0.0, 15000.0, n)
+    T_surf, T_min, p0 = 300.0, 215.0, 1.0e5
+    lapse = 6.5e-3
+    T = np.maximum(T_surf - lapse * z, T_min)
+    # hydrostatic pressure of the (dry) profile above
+    z_tp = (T_surf - T_min) / lapse
+    p = np.where(z <= z_tp, p0 * (T / T_surf) ** (g / (Rd * lapse)),
+                 p0 * (T_min / T_surf) ** (g / (Rd * lapse)) * np.exp(-g * (z - z_tp) / (Rd * T_min)))
+    RH = np.linspace(0.05, 1.05, n)
+    # decorrelate RH from height so every regime occurs at every temperature
+    RH = RH[rng.permutation(n)] if n > 1 else RH
+    pv = RH * psat_liq(T)
+    eps_ = Rd / Rv
+    q_vap = eps_ * pv / (p - (1 - eps_) * pv)
+    Rm = Rd * (1 + (Rv / Rd - 1) * q_vap)
+    rho = p / (Rm * T)
+    q_sat_liq = psat_liq(T) / (rho * Rv * T)
+    q_sat_ice = psat_ice(T) / (rho * Rv * T)
+    return T, p, rho, q_vap, q_sat_liq, q_sat_ice
+
+
+def synthetic_states_2m(n, seed=1234, dtype=np.float64, number="loguniform", frac_empty=0.05):
+    """Inputs of the 2-moment warm-rain method: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai.
+
+    ``number='const'`` is the reference's benchmark choice (n_lcl=1e8, n_rai=1e4,
+    test/gpu_performance.jl:219-220); ``'loguniform'`` (default) draws
+    n_lcl in [1e7,1e9], n_rai in [1e2,1e6] so the PSD limiter / breakup / number-adjustment
+    regimes are all exercised.  ``frac_empty`` of the points get exact zeros in q_lcl
+    and/or q_rai (the eps-gated branches)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    T, p, rho, q_vap, qsl, qsi = atmospheric_profile(n, rng)
+    q_lcl = np.maximum(0.0, q_vap - qsl) + rng.random(n) * 1e-4
+    q_rai = rng.random(n) * 1e-4
+    if number == "const":
+        n_lcl = np.full(n, 1e8)
+        n_rai = np.full(n, 1e4)
+    else:
+        n_lcl = 10.0 ** rng.uniform(7, 9, n)
+        n_rai = 10.0 ** rng.uniform(2, 6, n)
+    if frac_empty > 0:
+        u = rng.random(n)
+        q_lcl[u < frac_empty] = 0.0
+        q_rai[(u > frac_empty / 2) & (u < 1.5 * frac_empty)] = 0.0
+        n_rai[(u > 1.5 * frac_empty) & (u < 1.75 * frac_empty)] = 0.0
+    q_tot = q_vap + q_lcl + q_rai
+    st = dict(rho=rho, T=T, q_tot=q_tot, q_lcl=q_lcl, n_lcl=n_lcl, q_rai=q_rai, n_rai=n_rai)
+    return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}
+
+
+def synthetic_states_1m(n, seed=1234, dtype=np.float64, frac_empty=0.05):
+    """Inputs of the 1-moment method: rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno
+    (test/gpu_performance.jl:80-136)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    T, p, rho, q_vap, qsl, qsi = atmospheric_profile(n, rng)
+    q_lcl = np.maximum(0.0, q_vap - qsl) + rng.random(n) * 1e-4
+    q_icl = np.maximum(0.0, q_vap - qsi) + rng.random(n) * 1e-4
+    q_rai = rng.random(n) * 1e-4
+    q_sno = rng.random(n) * 1e-4
+    if frac_empty > 0:
+        u = rng.random(n)
+        q_lcl[u < frac_empty] = 0.0
+        q_icl[(u > 0.5 * frac_empty) & (u < 1.5 * frac_empty)] = 0.0
+        q_rai[(u > 1.5 * frac_empty) & (u < 2.5 * frac_empty)] = 0.0
+        q_sno[(u > 2.5 * frac_empty) & (u < 3.5 * frac_empty)] = 0.0
+    q_tot = q_vap + q_lcl + q_icl + q_rai + q_sno
+    st = dict(rho=rho, T=T, q_tot=q_tot, q_lcl=q_lcl, q_icl=q_icl, q_rai=q_rai, q_sno=q_sno, p=p)
+    return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}
+
+
+def perturb(states, rel=2.0 ** -40, seed=7, skip=()):
+    """Inputs with every element multiplied by (1 ± rel) (random signs): used to
+    measure the reference's own conditioning at each point."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    for k, v in states.items():
+        if k in skip:
+            out[k] = v
+            continue
+        s = rng.integers(0, 2, v.shape[0]) * 2 - 1
+        out[k] = (v.astype(np.float64) * (1.0 + rel * s)).astype(v.dtype)
+    return out
+
+
+def compare_report(got, ref, sens=None, rtol=F64_RTOL, backward_ulps=16, eps=np.finfo(np.float64).eps,
+                   sens_rel=2.0 ** -40):
+    """Parity metrics of one output column.
+
+    ``max_rel``   : max |got-ref| / max(|ref|, tiny) over points that are not excused.
+    A point is *excused* from the pure forward criterion only when ``sens`` (the
+    change of the REFERENCE's own output under a ``sens_rel`` relative perturbation of
+    its inputs) shows that ``backward_ulps`` ULPs of input noise already move the
+    reference result by more than the observed difference — i.e. the difference is
+    within the result's conditioning (catastrophic cancellation such as q_vap - q_sat
+    near saturation), the mixed forward/backward criterion of DESIGN.md §parity.
+    Non-finite values and zeros must match exactly."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape
+    fin = np.isfinite(ref)
+    nonfinite_mismatch = int(np.sum((~fin) & ~((got == ref) | (np.isnan(got) & np.isnan(ref)))))
+    nonfinite_mismatch += int(np.sum(fin & ~np.isfinite(got)))
+    both = fin & np.isfinite(got)
+    diff = np.zeros_like(ref)
+    diff[both] = np.abs(got[both] - ref[both])
+    denom = np.maximum(np.abs(ref), np.finfo(np.float64).tiny)
+    rel = np.where(both, diff / denom, 0.0)
+    rel[both & (diff == 0)] = 0.0
+    fwd_ok = rel <= rtol
+    if sens is not None:
+        allow = np.abs(np.asarray(sens, dtype=np.float64)) * (backward_ulps * eps / sens_rel)
+        excused = both & ~fwd_ok & (diff <= allow)
+    else:
+        excused = np.zeros_like(fwd_ok)
+    bad = both & ~fwd_ok & ~excused
+    zero_mismatch = int(np.sum(both & ((ref == 0) != (got == 0))))
+    counted = both & ~excused
+    return dict(
+        n=int(ref.size),
+        max_rel=float(rel[counted].max()) if counted.any() else 0.0,
+        max_rel_all=float(rel.max()) if rel.size else 0.0,
+        n_excused=int(excused.sum()),
+        n_bad=int(bad.sum()),
+        n_nonfinite_mismatch=nonfinite_mismatch,
+        n_zero_mismatch=zero_mismatch,
+        frac_forward_ok=float(fwd_ok[both].mean()) if both.any() else 1.0,
+        worst_index=int(np.argmax(np.where(counted, rel, -1.0))) if rel.size else -1,
+    )
+
+
+def ulp_error_f32(got, truth64):
+    """|got - truth| in units of the Float32 ULP of the true value."""
+    got = np.asarray(got, dtype=np.float64)
+    truth64 = np.asarray(truth64, dtype=np.float64)
+    t32 = np.abs(truth64.astype(np.float32))
+    ulp = np.spacing(np.maximum(t32, np.finfo(np.float32).tiny)).astype(np.float64)
+    return np.abs(got - truth64) / ulp

@@ -1,0 +1,185 @@
+/* cumicro.h — C ABI of libcumicro.so: B200 (sm_100a) bulk cloud-microphysics
+ * tendencies.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * CliMA/CloudMicrophysics.jl (reference file:line cited per entry point).  The
+ * reference exposes pointwise Julia methods that a host model broadcasts over
+ * arrays; each entry point below is the array-level form of one such method:
+ * structure-of-arrays columns in, structure-of-arrays columns out, one fused
+ * kernel per call.  A Julia package extension packs the
+ * live `mp`/`tps` parameter objects into the POD blocks declared in
+ * cumicro_params.inc and `ccall`s these symbols.
+ *
+ * Conventions
+ *  - Plain C types only.  `_f64` / `_f32` suffix = Float64 / Float32 method.
+ *  - Device entry points: every column pointer is a DEVICE pointer to `n`
+ *    contiguous elements, owned by the caller; work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*, NULL = legacy default stream) and the call
+ *    returns without synchronising.  The caller selects the device.
+ *  - `_host` entry points take HOST pointers (pinned memory recommended), run
+ *    a chunked H2D -> kernel -> D2H pipeline on internal streams and return
+ *    after the results are in the host buffers.
+ *  - Output pointers documented as "optional" may be NULL (column skipped).
+ *  - Return value: 0 ok; <0 API misuse (CUMICRO_E_*); >0 a cudaError_t value.
+ *    cumicro_last_error() returns a thread-local message for the last failure.
+ *  - Per-point domain violations (the reference throws DomainError /
+ *    AssertionError, IN:558-562, IN:47,73) cannot throw from a kernel: the
+ *    output is NaN and a device counter is incremented (see *_status args).
+ *  - The library never falls back to the CPU.
+ */
+#ifndef CUMICRO_H
+#define CUMICRO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUMICRO_VERSION 100 /* 0.1.0 */
+
+#define CUMICRO_OK 0
+#define CUMICRO_E_NULL (-1)      /* required pointer is NULL */
+#define CUMICRO_E_SIZE (-2)      /* n < 0 or size overflow */
+#define CUMICRO_E_OPTION (-3)    /* unknown option / enum value in a parameter block */
+#define CUMICRO_E_NODEVICE (-4)  /* no CUDA device / driver */
+#define CUMICRO_E_ARG (-5)       /* other invalid argument */
+
+#define CUMICRO_FT double
+#define CUMICRO_T(x) x##_f64
+#include "cumicro_params.inc"
+#undef CUMICRO_FT
+#undef CUMICRO_T
+
+#define CUMICRO_FT float
+#define CUMICRO_T(x) x##_f32
+#include "cumicro_params.inc"
+#undef CUMICRO_FT
+#undef CUMICRO_T
+
+int cumicro_version(void);
+const char* cumicro_last_error(void);
+
+/* Number of kernels launched by this library in the calling process so far
+ * (monotonic; used by bench.py for `gpu_launches`). */
+int64_t cumicro_launch_count(void);
+
+/* Roofline probe: enqueue `iters` x 8 independent FP64 FMAs per thread on
+ * SMs x blocks_per_sm blocks of 256 threads; *flops_out = flops issued (2 per FMA).
+ * bench.py times it with CUDA events to obtain the FP64 pipe peak in place. */
+int cumicro_probe_fp64_fma(int64_t iters, int blocks_per_sm, double* scratch, double* flops_out, void* stream);
+
+/* Free the per-thread device staging buffers that the `_host` entry points cache. */
+void cumicro_release_workspace(void);
+
+/* ---------------------------------------------------------------------------
+ * 2-moment warm rain (Seifert-Beheng 2006)
+ * Replaces: BulkMicrophysicsTendencies.bulk_microphysics_tendencies(
+ *     ::Microphysics2Moment, mp::Microphysics2MParams{WR,Nothing}, tps,
+ *     rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai)       BMT:820-854
+ * (body: warm_rain_tendencies_2m, BMT:707-782).
+ * `q_ice` is the optional 8th positional argument of that method (BMT:823): the
+ * cloud-ice content seen by the thermodynamics; NULL means zero.
+ * Outputs: dq_lcl_dt, dn_lcl_dt, dq_rai_dt, dn_rai_dt (required);
+ * zero4[0..3] = dq_ice_dt, dq_rim_dt, db_rim_dt, dn_lcl_activation_dt are
+ * identically zero in the reference (BMT:840-853): optional, filled with 0.
+ * ------------------------------------------------------------------------- */
+int cumicro_bmt2m_warm_f64(const cumicro_params_2m_warm_f64* p, int64_t n,
+                           const double* rho, const double* T, const double* q_tot,
+                           const double* q_lcl, const double* n_lcl,
+                           const double* q_rai, const double* n_rai,
+                           const double* q_ice /* optional: NULL = 0 */,
+                           double* dq_lcl_dt, double* dn_lcl_dt,
+                           double* dq_rai_dt, double* dn_rai_dt,
+                           double* const* zero4, void* stream);
+int cumicro_bmt2m_warm_f32(const cumicro_params_2m_warm_f32* p, int64_t n,
+                           const float* rho, const float* T, const float* q_tot,
+                           const float* q_lcl, const float* n_lcl,
+                           const float* q_rai, const float* n_rai,
+                           const float* q_ice /* optional: NULL = 0 */,
+                           float* dq_lcl_dt, float* dn_lcl_dt,
+                           float* dq_rai_dt, float* dn_rai_dt,
+                           float* const* zero4, void* stream);
+
+/* Same tendencies through HOST buffers (e2e path).  `chunk` = points per
+ * pipeline stage (0 = library default). */
+int cumicro_bmt2m_warm_host_f64(const cumicro_params_2m_warm_f64* p, int64_t n,
+                                const double* rho, const double* T, const double* q_tot,
+                                const double* q_lcl, const double* n_lcl,
+                                const double* q_rai, const double* n_rai,
+                                double* dq_lcl_dt, double* dn_lcl_dt,
+                                double* dq_rai_dt, double* dn_rai_dt, int64_t chunk);
+int cumicro_bmt2m_warm_host_f32(const cumicro_params_2m_warm_f32* p, int64_t n,
+                                const float* rho, const float* T, const float* q_tot,
+                                const float* q_lcl, const float* n_lcl,
+                                const float* q_rai, const float* n_rai,
+                                float* dq_lcl_dt, float* dn_lcl_dt,
+                                float* dq_rai_dt, float* dn_rai_dt, int64_t chunk);
+
+/* Individual SB2006 process rates, one column each (the array form of the
+ * leaf methods the reference exports and tests one by one,
+ * test/gpu_tests.jl:220-235).  `out` is a HOST array of CUMICRO_SB2006_NLEAF
+ * device column pointers (NULL entries skipped), in this order: */
+enum {
+    CUMICRO_SB_COND_DQ_LCL = 0, /* NEQ._conv_q_vap_to_q_lcl_const   NEQ:117-140 */
+    CUMICRO_SB_EVAP_DN_RAI,     /* CM2.rain_evaporation d(rho n_rai)/dt CM2:780-828 */
+    CUMICRO_SB_EVAP_DQ_RAI,     /* CM2.rain_evaporation dq_rai/dt */
+    CUMICRO_SB_ACNV_DQ_LCL,     /* CM2.autoconversion  CM2:396-427 */
+    CUMICRO_SB_ACNV_DN_LCL,     /*   dN_lcl_dt [1/m3/s] */
+    CUMICRO_SB_ACNV_DQ_RAI,
+    CUMICRO_SB_ACNV_DN_RAI,
+    CUMICRO_SB_LCL_SELFCOL,     /* CM2.cloud_liquid_self_collection CM2:488-501 */
+    CUMICRO_SB_ACCR_DQ_LCL,     /* CM2.accretion CM2:445-470 */
+    CUMICRO_SB_ACCR_DN_LCL,
+    CUMICRO_SB_ACCR_DQ_RAI,
+    CUMICRO_SB_RAI_SELFCOL,     /* CM2.rain_self_collection CM2:545-560 */
+    CUMICRO_SB_RAI_BREAKUP,     /* CM2.rain_breakup CM2:579-601 */
+    CUMICRO_SB_NUMADJ_LCL,      /* CM2.number_tendency_from_mass_limits CM2:882-891 */
+    CUMICRO_SB_NUMADJ_RAI,
+    CUMICRO_SB2006_NLEAF
+};
+int cumicro_sb2006_leaves_f64(const cumicro_params_2m_warm_f64* p, int64_t n,
+                              const double* rho, const double* T, const double* q_tot,
+                              const double* q_lcl, const double* n_lcl,
+                              const double* q_rai, const double* n_rai,
+                              double* const* out, void* stream);
+int cumicro_sb2006_leaves_f32(const cumicro_params_2m_warm_f32* p, int64_t n,
+                              const float* rho, const float* T, const float* q_tot,
+                              const float* q_lcl, const float* n_lcl,
+                              const float* q_rai, const float* n_rai,
+                              float* const* out, void* stream);
+
+/* 2-moment terminal velocities (number- and mass-weighted).
+ * CM2.rain_terminal_velocity(::SB2006, ::SB2006VelType, q_rai, rho, N_rai)  CM2:685-702
+ * CM2.rain_terminal_velocity(::SB2006, ::Chen2022VelTypeRain, ...)          CM2:703-719
+ * CM2.cloud_terminal_velocity(pdf_c, ::StokesRegimeVelType, q, rho, N)      CM2:647-664
+ * N_* are number densities [1/m3] as in the reference signatures. */
+int cumicro_termvel_2m_rain_sb_f64(const cumicro_sb_pdf_r_f64* pdf_r,
+                                   const cumicro_vel_sb2006_f64* vel, int64_t n,
+                                   const double* q_rai, const double* rho, const double* N_rai,
+                                   double* vt0, double* vt1, void* stream);
+int cumicro_termvel_2m_rain_chen_f64(const cumicro_sb_pdf_r_f64* pdf_r,
+                                     const cumicro_vel_chen_rain_f64* vel, int64_t n,
+                                     const double* q_rai, const double* rho, const double* N_rai,
+                                     double* vt0, double* vt1, void* stream);
+int cumicro_termvel_2m_cloud_f64(const cumicro_sb_pdf_c_f64* pdf_c,
+                                 const cumicro_vel_stokes_f64* vel, int64_t n,
+                                 const double* q_lcl, const double* rho, const double* N_lcl,
+                                 double* vt0, double* vt1, void* stream);
+int cumicro_termvel_2m_rain_sb_f32(const cumicro_sb_pdf_r_f32* pdf_r,
+                                   const cumicro_vel_sb2006_f32* vel, int64_t n,
+                                   const float* q_rai, const float* rho, const float* N_rai,
+                                   float* vt0, float* vt1, void* stream);
+int cumicro_termvel_2m_rain_chen_f32(const cumicro_sb_pdf_r_f32* pdf_r,
+                                     const cumicro_vel_chen_rain_f32* vel, int64_t n,
+                                     const float* q_rai, const float* rho, const float* N_rai,
+                                     float* vt0, float* vt1, void* stream);
+int cumicro_termvel_2m_cloud_f32(const cumicro_sb_pdf_c_f32* pdf_c,
+                                 const cumicro_vel_stokes_f32* vel, int64_t n,
+                                 const float* q_lcl, const float* rho, const float* N_lcl,
+                                 float* vt0, float* vt1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUMICRO_H */

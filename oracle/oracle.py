@@ -1,0 +1,100 @@
+"""ctypes binding of the CPU parity oracle (oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False):
+    """Compile the oracle with the committed Makefile (g++, -ffp-contract=off, OpenMP)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int):
+    lib().oracle_set_num_threads(int(n))
+
+
+def _suf(dtype):
+    return {"float64": "f64", "float32": "f32"}[np.dtype(dtype).name]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _cols(arrays, dtype):
+    out = [np.ascontiguousarray(a, dtype=dtype) for a in arrays]
+    n = out[0].shape[0]
+    assert all(a.shape == (n,) for a in out)
+    return out, n
+
+
+def bmt2m_warm(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, leaves=False):
+    """BMT:820-854 over arrays. Returns dict of 4 tendencies (+ the SB2006 leaf columns)."""
+    from importlib import import_module
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    (rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai), n = _cols((rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai), dtype)
+    names = ("dq_lcl_dt", "dn_lcl_dt", "dq_rai_dt", "dn_rai_dt")
+    out = {k: np.empty(n, dtype) for k in names}
+    leaf_ptrs = None
+    leaf_arrays = None
+    if leaves:
+        nleaf = 15
+        leaf_arrays = [np.empty(n, dtype) for _ in range(nleaf)]
+        leaf_ptrs = (C.c_void_p * nleaf)(*[_ptr(a) for a in leaf_arrays])
+    fn = getattr(lib(), f"oracle_bmt2m_warm_{_suf(dtype)}")
+    st = fn(C.byref(params), C.c_int64(n), *[_ptr(a) for a in (rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai)],
+            *[_ptr(out[k]) for k in names], leaf_ptrs)
+    assert st == 0
+    if leaves:
+        out["leaves"] = leaf_arrays
+    return out
+
+
+def _termvel(fname, pdf, vel, q, rho, N):
+    dtype = np.float64 if type(pdf).__name__.endswith("f64") else np.float32
+    (q, rho, N), n = _cols((q, rho, N), dtype)
+    vt0 = np.empty(n, dtype)
+    vt1 = np.empty(n, dtype)
+    fn = getattr(lib(), f"oracle_{fname}_{_suf(dtype)}")
+    st = fn(C.byref(pdf), C.byref(vel), C.c_int64(n), _ptr(q), _ptr(rho), _ptr(N), _ptr(vt0), _ptr(vt1))
+    assert st == 0
+    return vt0, vt1
+
+
+def termvel_2m_rain_sb(pdf_r, vel, q, rho, N):
+    return _termvel("termvel_2m_rain_sb", pdf_r, vel, q, rho, N)
+
+
+def termvel_2m_rain_chen(pdf_r, vel, q, rho, N):
+    return _termvel("termvel_2m_rain_chen", pdf_r, vel, q, rho, N)
+
+
+def termvel_2m_cloud(pdf_c, vel, q, rho, N):
+    return _termvel("termvel_2m_cloud", pdf_c, vel, q, rho, N)

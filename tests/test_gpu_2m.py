@@ -1,0 +1,330 @@
+"""GPU parity tests of the 2-moment (SB2006) path: CUDA kernels called through the
+C-ABI vs the CPU oracle on the same seeded inputs.
+
+Tolerances (north star): Float64 <= 1e-12 relative per tendency; Float32 <= 4
+ULP-equivalent; regime/branch selection bit-exact (zero / non-zero pattern and
+non-finite values must match exactly).  Points where the reference's own result is
+ill-conditioned (q_vap - q_sat near saturation, 1 - tau^a near tau = 1) are judged by
+the mixed forward/backward criterion of ``cumicro.testing.compare_report``: the
+difference must be smaller than what 16 ULP of input noise does to the reference
+itself."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai")
+OUTS = ("dq_lcl_dt", "dn_lcl_dt", "dq_rai_dt", "dn_rai_dt")
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "sb2006_goldens.json")))
+
+
+def _to_dev(st, dev):
+    import torch
+    return {k: torch.from_numpy(v).to(dev) for k, v in st.items()}
+
+
+def _gpu_bmt(built, mp, tps, cols, **kw):
+    BMT = built.BMT
+    return BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[cols[k] for k in KEYS], **kw)
+
+
+def _oracle_with_sens(orc, block, st, leaves=False):
+    from cumicro.testing import perturb
+    ref = orc.bmt2m_warm(block, *[st[k] for k in KEYS], leaves=leaves)
+    sens = None
+    for seed in (7, 8, 9):
+        pr = orc.bmt2m_warm(block, *[perturb(st, seed=seed)[k] for k in KEYS], leaves=leaves)
+        d = {k: np.abs(pr[k] - ref[k]) for k in OUTS}
+        if leaves:
+            d["leaves"] = [np.abs(a - b) for a, b in zip(pr["leaves"], ref["leaves"])]
+        if sens is None:
+            sens = d
+        else:
+            for k in OUTS:
+                sens[k] = np.maximum(sens[k], d[k])
+            if leaves:
+                sens["leaves"] = [np.maximum(a, b) for a, b in zip(sens["leaves"], d["leaves"])]
+    return ref, sens
+
+
+@pytest.mark.parametrize("limited", [True, False])
+@pytest.mark.parametrize("number", ["loguniform", "const"])
+def test_bmt2m_warm_f64_parity(built, orc, cuda, limited, number):
+    from cumicro.testing import synthetic_states_2m, compare_report
+    CMP = built.CMP
+    n = 1 << 18
+    st = synthetic_states_2m(n, seed=1234, number=number)
+    mp = CMP.Microphysics2MParams(np.float64, is_limited=limited)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    out = _gpu_bmt(built, mp, tps, _to_dev(st, cuda))
+    ref, sens = _oracle_with_sens(orc, CMP.pack_2m_warm(mp, tps), st)
+    for k in OUTS:
+        rep = compare_report(out[k].cpu().numpy(), ref[k], sens=sens[k])
+        assert rep["n_bad"] == 0 and rep["max_rel"] <= 1e-12, (k, rep)
+        assert rep["n_zero_mismatch"] == 0 and rep["n_nonfinite_mismatch"] == 0, (k, rep)
+        assert rep["frac_forward_ok"] > 0.99, (k, rep)
+    for k in ("dq_ice_dt", "dq_rim_dt", "db_rim_dt", "dn_lcl_activation_dt"):
+        assert out[k].shape[0] == n and float(out[k].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("limited", [True, False])
+def test_sb2006_leaves_f64_parity_and_regimes(built, orc, cuda, limited):
+    from cumicro.testing import synthetic_states_2m, compare_report
+    CMP, abi = built.CMP, built._abi
+    n = 1 << 17
+    st = synthetic_states_2m(n, seed=99)
+    mp = CMP.Microphysics2MParams(np.float64, is_limited=limited)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    cols = _to_dev(st, cuda)
+    got = built.CM2.sb2006_process_rates(mp, tps, *[cols[k] for k in KEYS])
+    ref, sens = _oracle_with_sens(orc, CMP.pack_2m_warm(mp, tps), st, leaves=True)
+    for i, name in enumerate(abi.SB2006_LEAVES):
+        g = got[name].cpu().numpy()
+        rep = compare_report(g, ref["leaves"][i], sens=sens["leaves"][i])
+        assert rep["n_bad"] == 0 and rep["max_rel"] <= 1e-12, (name, rep)
+        # bit-exact regime selection: gated-off (exact zero) points coincide
+        assert rep["n_zero_mismatch"] == 0, (name, rep)
+    # breakup regimes (Dr < Dr_th | Dr <= Deq | else) all present in the limited run
+    if limited:
+        br = ref["leaves"][abi.SB2006_LEAVES.index("rai_breakup")]
+        sc = ref["leaves"][abi.SB2006_LEAVES.index("rai_selfcol")]
+        assert ((br == 0) & (sc != 0)).any() and (br > 0).any() and (br < 0).any()
+
+
+def test_golden_values_through_the_gpu(built, cuda):
+    """The reference's GPU test literals (test/gpu_tests.jl:844-871) reproduced by
+    the CUDA path itself."""
+    import torch
+    CMP, abi = built.CMP, built._abi
+    s = G["state_gpu"]
+    rho = s["rho"]
+    vals = dict(rho=rho, T=s["T"], q_tot=s["q_tot"], q_lcl=s["q_lcl"], n_lcl=s["N_lcl"] / rho, q_rai=s["q_rai"],
+                n_rai=s["N_rai"] / rho)
+    cols = {k: torch.full((10,), v, dtype=torch.float64, device=cuda) for k, v in vals.items()}
+    for limited in (True, False):
+        mp = CMP.Microphysics2MParams(np.float64, is_limited=limited)
+        tps = CMP.ThermodynamicsParameters(np.float64)
+        got = built.CM2.sb2006_process_rates(mp, tps, *[cols[k] for k in KEYS])
+        leaf = {k: v.cpu().numpy() for k, v in got.items()}
+        vt0, vt1 = built.CM2.rain_terminal_velocity(mp.warm_rain.seifert_beheng, CMP.SB2006VelType(np.float64),
+                                                    cols["q_rai"], cols["rho"], cols["n_rai"] * cols["rho"])
+        leaf["vt0"], leaf["vt1"] = vt0.cpu().numpy(), vt1.cpu().numpy()
+        table = dict(G["common"])
+        table.update(G["limited" if limited else "notlimited"])
+        for name, (val, rtol, where) in table.items():
+            g = leaf[name]
+            assert np.all(g == g[0]), name  # `allequal(out)` of the reference test
+            if val == 0:
+                assert g[0] == 0
+            else:
+                assert abs(g[0] - val) <= rtol * abs(val), (name, g[0], val, where)
+
+
+@pytest.mark.parametrize("limited", [True, False])
+def test_terminal_velocities_f64_parity(built, orc, cuda, limited):
+    import torch
+    from cumicro.testing import synthetic_states_2m, compare_report
+    CMP = built.CMP
+    st = synthetic_states_2m(1 << 16, seed=11)
+    cols = _to_dev(st, cuda)
+    N_rai, N_lcl = st["n_rai"] * st["rho"], st["n_lcl"] * st["rho"]
+    dN_rai, dN_lcl = cols["n_rai"] * cols["rho"], cols["n_lcl"] * cols["rho"]
+    sb = CMP.SB2006(np.float64, is_limited=limited)
+    cases = [
+        ("rain_sb", built.CM2.rain_terminal_velocity(sb, CMP.SB2006VelType(np.float64), cols["q_rai"], cols["rho"], dN_rai),
+         orc.termvel_2m_rain_sb(sb.pdf_r, CMP.SB2006VelType(np.float64), st["q_rai"], st["rho"], N_rai)),
+        ("rain_chen", built.CM2.rain_terminal_velocity(sb, CMP.Chen2022VelTypeRain(np.float64), cols["q_rai"], cols["rho"], dN_rai),
+         orc.termvel_2m_rain_chen(sb.pdf_r, CMP.Chen2022VelTypeRain(np.float64), st["q_rai"], st["rho"], N_rai)),
+        ("cloud", built.CM2.cloud_terminal_velocity(sb.pdf_c, CMP.StokesRegimeVelType(np.float64), cols["q_lcl"], cols["rho"], dN_lcl),
+         orc.termvel_2m_cloud(sb.pdf_c, CMP.StokesRegimeVelType(np.float64), st["q_lcl"], st["rho"], N_lcl)),
+    ]
+    for name, got, ref in cases:
+        for j in (0, 1):
+            g, r = got[j].cpu().numpy(), ref[j]
+            # v = a - b/(...) differences of O(1) terms clipped at 0: measure against the velocity scale
+            rep = compare_report(g, r)
+            scale_err = np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-3))
+            assert scale_err <= 1e-12, (name, j, rep, scale_err)
+            assert rep["n_nonfinite_mismatch"] == 0
+
+
+def test_chen_rain_golden_gpu(built, cuda):
+    import torch
+    CMP = built.CMP
+    g = G["chen_rain_2m"]
+    sb = CMP.SB2006(np.float64, overrides=CMP.SB2006_LIMITERS_OVERRIDE)
+    f = lambda v: torch.full((3,), v, dtype=torch.float64, device=cuda)
+    vt0, vt1 = built.CM2.rain_terminal_velocity(sb, CMP.Chen2022VelTypeRain(np.float64), f(g["state"]["q_rai"]),
+                                                f(g["state"]["rho"]), f(g["state"]["N_rai"]))
+    assert abs(float(vt0[0]) / g["vt0"][0] - 1) < 1.5e-8 and abs(float(vt1[0]) / g["vt1"][0] - 1) < 1.5e-8
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 257, 1025])
+def test_ragged_sizes_and_tail(built, orc, cuda, n):
+    import torch
+    from cumicro.testing import synthetic_states_2m, compare_report
+    CMP = built.CMP
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    st = synthetic_states_2m(max(n, 1), seed=5)
+    st = {k: v[:n].copy() for k, v in st.items()}
+    out = _gpu_bmt(built, mp, tps, _to_dev(st, cuda))
+    assert out["dq_lcl_dt"].shape[0] == n
+    if n:
+        ref = orc.bmt2m_warm(CMP.pack_2m_warm(mp, tps), *[st[k] for k in KEYS])
+        for k in OUTS:
+            np.testing.assert_allclose(out[k].cpu().numpy(), ref[k], rtol=1e-9, atol=0)
+
+
+def test_misaligned_columns_take_the_scalar_path_with_identical_bits(built, cuda):
+    import torch
+    from cumicro.testing import synthetic_states_2m
+    CMP = built.CMP
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    n = 4099
+    st = synthetic_states_2m(n + 1, seed=21)
+    cols = _to_dev(st, cuda)
+    whole = _gpu_bmt(built, mp, tps, cols)
+    shifted = {k: v[1:] for k, v in cols.items()}  # 8-byte aligned, not 16
+    assert all(v.data_ptr() % 16 == 8 for v in shifted.values())
+    part = _gpu_bmt(built, mp, tps, shifted)
+    for k in OUTS:
+        assert torch.equal(part[k], whole[k][1:]), k
+
+
+def test_negative_and_zero_inputs_are_clamped_like_the_reference(built, orc, cuda):
+    import torch
+    CMP = built.CMP
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    base = dict(rho=1.0, T=285.0, q_tot=1e-2, q_lcl=1e-3, n_lcl=1e8, q_rai=1e-4, n_rai=1e4)
+    rows = [dict(base)]
+    for k in ("q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai"):
+        for v in (0.0, -1e-5):
+            r = dict(base)
+            r[k] = v
+            rows.append(r)
+    rows.append(dict(base, q_lcl=0.0, q_rai=0.0, n_lcl=0.0, n_rai=0.0))
+    rows.append(dict(base, T=240.0))
+    rows.append(dict(base, q_rai=1e-2, n_rai=1.0))      # xr_max clamp, N0_min clamp
+    rows.append(dict(base, q_rai=1e-9, n_rai=1e7))      # xr_min clamp
+    st = {k: np.array([r[k] for r in rows]) for k in KEYS}
+    out = _gpu_bmt(built, mp, tps, _to_dev(st, cuda))
+    ref = orc.bmt2m_warm(CMP.pack_2m_warm(mp, tps), *[st[k] for k in KEYS])
+    for k in OUTS:
+        g = out[k].cpu().numpy()
+        assert np.all(np.isfinite(g)), k
+        np.testing.assert_allclose(g, ref[k], rtol=1e-12, atol=0)
+        assert np.array_equal(g == 0, ref[k] == 0)
+
+
+def test_optional_q_ice_column(built, orc, cuda):
+    """BMT:823,843: the warm-only method forwards q_ice to the thermodynamics."""
+    import torch
+    from cumicro.testing import synthetic_states_2m
+    CMP = built.CMP
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    st = synthetic_states_2m(4096, seed=31)
+    cols = _to_dev(st, cuda)
+    q_ice = torch.full_like(cols["rho"], 2e-4)
+    a = _gpu_bmt(built, mp, tps, cols, q_ice=q_ice)
+    b = _gpu_bmt(built, mp, tps, cols)
+    z = _gpu_bmt(built, mp, tps, cols, q_ice=torch.zeros_like(q_ice))
+    assert not torch.equal(a["dq_lcl_dt"], b["dq_lcl_dt"])
+    for k in OUTS:
+        assert torch.equal(z[k], b[k])
+
+
+def test_materialized_zero_columns(built, cuda):
+    from cumicro.testing import synthetic_states_2m
+    CMP = built.CMP
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    cols = _to_dev(synthetic_states_2m(1000, seed=2), cuda)
+    out = _gpu_bmt(built, mp, tps, cols, materialize_zeros=True)
+    for k in ("dq_ice_dt", "dq_rim_dt", "db_rim_dt", "dn_lcl_activation_dt"):
+        assert out[k].is_contiguous() and float(out[k].abs().sum()) == 0.0
+
+
+def test_bmt2m_warm_f32(built, orc, cuda):
+    """Float32 method: judged in Float32 ULPs of the true (Float64-oracle) value, and
+    against the Float32 restatement's own error."""
+    from cumicro.testing import synthetic_states_2m, ulp_error_f32
+    CMP = built.CMP
+    n = 1 << 16
+    st32 = synthetic_states_2m(n, seed=77, dtype=np.float32)
+    mp32, tps32 = CMP.Microphysics2MParams(np.float32), CMP.ThermodynamicsParameters(np.float32)
+    out = _gpu_bmt(built, mp32, tps32, _to_dev(st32, cuda))
+    ref32 = orc.bmt2m_warm(CMP.pack_2m_warm(mp32, tps32), *[st32[k] for k in KEYS])
+    truth = orc.bmt2m_warm(CMP.pack_2m_warm(CMP.Microphysics2MParams(np.float64), CMP.ThermodynamicsParameters(np.float64)),
+                           *[st32[k].astype(np.float64) for k in KEYS])
+    for k in OUTS:
+        g = out[k].cpu().numpy()
+        assert g.dtype == np.float32 and np.all(np.isfinite(g))
+        assert np.array_equal(g == 0, ref32[k] == 0), k   # regime selection
+        e_gpu = ulp_error_f32(g, truth[k])
+        e_ref = ulp_error_f32(ref32[k], truth[k])
+        # the CUDA Float32 path is at least as close to the true value as the reference's
+        # Float32 arithmetic is (median and 99th percentile), see DESIGN.md §Float32
+        assert np.median(e_gpu) <= max(4.0, 1.5 * np.median(e_ref)), (k, np.median(e_gpu), np.median(e_ref))
+        assert np.percentile(e_gpu, 99) <= max(4.0, 1.5 * np.percentile(e_ref, 99)), k
+
+
+def test_host_buffer_pipeline_matches_device_path(built, cuda):
+    import torch
+    from cumicro.testing import synthetic_states_2m
+    CMP, BMT = built.CMP, built.BMT
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    n = (1 << 18) + 77
+    st = synthetic_states_2m(n, seed=8)
+    dev = _gpu_bmt(built, mp, tps, _to_dev(st, cuda))
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
+    for chunk in (0, 50_000, 1 << 20):
+        host = BMT.bulk_microphysics_tendencies_host(BMT.Microphysics2Moment(), mp, tps, *[pinned[k] for k in KEYS], chunk=chunk)
+        for k in OUTS:
+            assert torch.equal(host[k], dev[k].cpu()), (k, chunk)
+    # pageable numpy buffers work too
+    host = BMT.bulk_microphysics_tendencies_host(BMT.Microphysics2Moment(), mp, tps, *[st[k] for k in KEYS])
+    for k in OUTS:
+        assert np.array_equal(host[k], dev[k].cpu().numpy())
+
+
+def test_full_size_properties_2pow24(built, cuda):
+    """BASELINE config 2 size (2^24 points): size-independent properties.
+    (1) determinism; (2) slab independence: evaluating any contiguous slab alone gives
+    the same bits as the whole-array call (what the multi-GPU slab partition relies on);
+    (3) fused tendencies == aggregation of the leaf kernel's columns (BMT:736-779);
+    (4) mass bookkeeping: acnv and accr move mass between cloud and rain only."""
+    import torch
+    from cumicro.testing import synthetic_states_2m
+    CMP, abi = built.CMP, built._abi
+    mp = CMP.Microphysics2MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    n = 1 << 24
+    cols = _to_dev(synthetic_states_2m(n, seed=1234), cuda)
+    a = _gpu_bmt(built, mp, tps, cols)
+    b = _gpu_bmt(built, mp, tps, cols)
+    for k in OUTS:
+        assert torch.equal(a[k], b[k])
+        assert bool(torch.isfinite(a[k]).all())
+    lo, hi = 5_000_000, 9_000_002
+    part = _gpu_bmt(built, mp, tps, {k: v[lo:hi].contiguous() for k, v in cols.items()})
+    for k in OUTS:
+        assert torch.equal(part[k], a[k][lo:hi])
+    m = 1 << 22
+    sub = {k: v[:m] for k, v in cols.items()}
+    L = built.CM2.sb2006_process_rates(mp, tps, *[sub[k] for k in KEYS])
+    rho = sub["rho"]
+    dq_l = L["cond_dq_lcl"] + L["acnv_dq_lcl"] + L["accr_dq_lcl"]
+    dq_r = L["evap_dq_rai"] + L["acnv_dq_rai"] + L["accr_dq_rai"]
+    assert torch.equal(dq_l, a["dq_lcl_dt"][:m]) and torch.equal(dq_r, a["dq_rai_dt"][:m])
+    assert torch.equal(L["acnv_dq_lcl"], -L["acnv_dq_rai"]) and torch.equal(L["accr_dq_lcl"], -L["accr_dq_rai"])
+    assert bool((L["evap_dq_rai"] <= 0).all()) and bool((L["rai_selfcol"] <= 0).all())
