@@ -36,6 +36,7 @@ template <class FT, int NIN, int NOUT, class F, bool VECTOR, int BLOCK, int MINB
 __global__ void __launch_bounds__(BLOCK, MINB)
 pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int64_t first) {
     constexpr int VEC = VECTOR ? vec<FT>::N : 1;
+    math_tables_init();  // exp/log tables -> shared memory (cm_math.cuh)
     const int64_t stride = (int64_t)gridDim.x * BLOCK;
     const int64_t n_items = VECTOR ? (a.n / VEC) : (a.n - first);
     for (int64_t it = (int64_t)blockIdx.x * BLOCK + threadIdx.x; it < n_items; it += stride) {

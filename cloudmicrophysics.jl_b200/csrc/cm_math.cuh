@@ -1,82 +1,274 @@
-// cm_math.cuh — device math primitives for the cumicro kernels.
+// cm_math.cuh — math primitives of the cumicro kernels.
 //
-// Everything the physics headers need from "libm" goes through the cm::
-// functions below so the implementation can be tuned in one place.  The FP64
-// kernels are bound by the FP64 pipe, so the special
-// functions here are written to minimise DFMA/DMUL/DADD issue slots while
-// staying far inside the 1e-12 relative parity budget:
-//   * no special-case handling that the call sites cannot reach (arguments are
-//     clamped by the physics code before they get here),
-//   * reciprocal / rsqrt seeds from the MUFU unit (MUFU.RCP64H / RSQ64H),
-//   * pow(x, y) = exp(y * log(x)) with a log accurate to < 1 ulp, which keeps
-//     the relative error of the power below ~|y ln x| * 2.2e-16.
+// The FP64 tendency kernels are bound by the FP64 pipe: B200
+// issues 64 FP64 instructions/clk/SM, DADD/DMUL/DFMA alike, so the figure of merit
+// of every function here is its FP64 *instruction count*.  The CUDA libm versions
+// carry special-case handling and (for pow) double-double arithmetic that the call
+// sites do not need; the versions below are written for the argument ranges the
+// physics produces and stay far inside the 1e-12 relative parity budget:
+//
+//   exp_   : table-driven, 2^(j/64) from shared memory + degree-5 polynomial      ~10 FP64
+//   logp_  : table-driven (128 x (1/c, -log 1/c)) + degree-7 log1p polynomial    ~13 FP64
+//   powp_  : exp_(y * logp_(x)); relative error ~ |y ln x| * 3e-16               ~24 FP64
+//   cbrtp_ : FP32 MUFU (lg2/ex2) seed, one cubic step on x^(-1/3), one correction ~12 FP64
+//   rcp_   : MUFU.RCP64H seed + cubic + Newton step, <= 1 ulp                      ~5 FP64
+// Suffix `p` = positive, normal, finite argument required (garbage, not NaN, outside;
+// call sites select the result away in those cases, exactly where the reference's
+// ifelse does).  + - * / sqrt are IEEE operations, identical to the CPU reference; the
+// code is compiled with -fmad=false, so a fused multiply-add happens exactly where
+// fma() is written and results do not depend on how the compiler schedules the
+// surrounding code (scalar-tail and vector kernels give identical bits).
+//
+// Every function is __host__ __device__ (MUFU seeds are emulated on the host) so
+// tests/test_cm_math.py measures the accuracy against mpmath without a GPU.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+
+#include <cmath>
 #include <cstdint>
+#include <cstring>
+
+#include "cm_math_tables.inc"
 
 namespace cm {
 
 #define CM_DEV __device__ __forceinline__
+#define CM_HD __host__ __device__ __forceinline__
+
+// ---- bit access -------------------------------------------------------------------------
+CM_HD int hi32(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    int64_t u; memcpy(&u, &x, 8); return (int)(u >> 32);
+#endif
+}
+CM_HD int lo32(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    int64_t u; memcpy(&u, &x, 8); return (int)(u & 0xffffffff);
+#endif
+}
+CM_HD double mk64(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+CM_HD double bits2d(unsigned long long u) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
 
 template <class FT> struct num;
 template <> struct num<double> {
-    static CM_DEV double eps() { return 2.220446049250313e-16; }
+    static CM_HD double eps() { return 2.220446049250313e-16; }
     // UT.ϵ_numerics(Float64) = cbrt(floatmin(Float64))            UT:318
-    static CM_DEV double eps_numerics() { return 2.8126442852362996e-103; }
-    static CM_DEV double inf() { return CUDART_INF; }
-    static CM_DEV double pi() { return 3.141592653589793; }
+    static CM_HD double eps_numerics() { return 2.8126442852362996e-103; }
+    static CM_HD double inf() { return bits2d(0x7ff0000000000000ULL); }
+    static CM_HD double pi() { return 3.141592653589793; }
 };
 template <> struct num<float> {
-    static CM_DEV float eps() { return 1.1920929e-07f; }
+    static CM_HD float eps() { return 1.1920929e-07f; }
     // cbrt(floatmin(Float32))
-    static CM_DEV float eps_numerics() { return 2.2737368e-13f; }
-    static CM_DEV float inf() { return CUDART_INF_F; }
-    static CM_DEV float pi() { return 3.1415927f; }
+    static CM_HD float eps_numerics() { return 2.2737368e-13f; }
+    static CM_HD float inf() { return (float)bits2d(0x7ff0000000000000ULL); }
+    static CM_HD float pi() { return 3.1415927f; }
 };
 
-// --- min / max / clamp with the reference's (Julia Base) selection semantics ----
-CM_DEV double fmax_(double a, double b) { return fmax(a, b); }
-CM_DEV float fmax_(float a, float b) { return fmaxf(a, b); }
-CM_DEV double fmin_(double a, double b) { return fmin(a, b); }
-CM_DEV float fmin_(float a, float b) { return fminf(a, b); }
-// Base.clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x))
-template <class FT> CM_DEV FT clamp_(FT x, FT lo, FT hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }
+// ---- lookup tables ------------------------------------------------------------------------
+// Global copies (host + device) and the per-block shared-memory copy the device
+// functions read.  A kernel that uses exp_/logp_/powp_ must call math_tables_init()
+// (all threads of the block) before its first use; cm_launch.cuh does.
+static const unsigned long long cm_exp_tab_host[64] = CM_EXP_TABLE_INIT;
+static const unsigned long long cm_log_tab_host[256] = CM_LOG_TABLE_INIT;
+static __device__ const unsigned long long cm_exp_tab_dev[64] = CM_EXP_TABLE_INIT;
+static __device__ const unsigned long long cm_log_tab_dev[256] = CM_LOG_TABLE_INIT;
+#ifdef __CUDACC__
+static __shared__ unsigned long long cm_sh_exp[64];
+static __shared__ ulonglong2 cm_sh_log[128];
+#endif
 
-// --- elementary functions -----------------------------------------------------------
-CM_DEV double exp_(double x) { return exp(x); }
-CM_DEV float exp_(float x) { return expf(x); }
-CM_DEV double log_(double x) { return log(x); }
-CM_DEV float log_(float x) { return logf(x); }
-CM_DEV double sqrt_(double x) { return sqrt(x); }
-CM_DEV float sqrt_(float x) { return sqrtf(x); }
-CM_DEV double cbrt_(double x) { return cbrt(x); }
-CM_DEV float cbrt_(float x) { return cbrtf(x); }
-CM_DEV double pow_(double x, double y) { return pow(x, y); }
-CM_DEV float pow_(float x, float y) { return powf(x, y); }
-CM_DEV double expm1_(double x) { return expm1(x); }
-CM_DEV float expm1_(float x) { return expm1f(x); }
-CM_DEV double log1p_(double x) { return log1p(x); }
-CM_DEV float log1p_(float x) { return log1pf(x); }
-CM_DEV double tgamma_(double x) { return tgamma(x); }
-CM_DEV float tgamma_(float x) { return tgammaf(x); }
-CM_DEV double lgamma_(double x) { return lgamma(x); }
-CM_DEV float lgamma_(float x) { return lgammaf(x); }
-CM_DEV double erf_(double x) { return erf(x); }
-CM_DEV float erf_(float x) { return erff(x); }
-CM_DEV double rcp_(double x) { return 1.0 / x; }
-CM_DEV float rcp_(float x) { return 1.0f / x; }
+CM_DEV void math_tables_init() {
+#ifdef __CUDA_ARCH__
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) cm_sh_exp[i] = cm_exp_tab_dev[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x)
+        cm_sh_log[i] = make_ulonglong2(cm_log_tab_dev[2 * i], cm_log_tab_dev[2 * i + 1]);
+    __syncthreads();
+#endif
+}
+CM_HD double exp_tab(int j) {
+#ifdef __CUDA_ARCH__
+    return bits2d(cm_sh_exp[j]);
+#else
+    return bits2d(cm_exp_tab_host[j]);
+#endif
+}
+CM_HD void log_tab(int i, double& invc, double& logc) {
+#ifdef __CUDA_ARCH__
+    const ulonglong2 t = cm_sh_log[i];
+    invc = bits2d(t.x);
+    logc = bits2d(t.y);
+#else
+    invc = bits2d(cm_log_tab_host[2 * i]);
+    logc = bits2d(cm_log_tab_host[2 * i + 1]);
+#endif
+}
+
+// ---- min / max / clamp with the reference's (Julia Base) selection semantics --------------
+CM_HD double fmax_(double a, double b) { return fmax(a, b); }
+CM_HD float fmax_(float a, float b) { return fmaxf(a, b); }
+CM_HD double fmin_(double a, double b) { return fmin(a, b); }
+CM_HD float fmin_(float a, float b) { return fminf(a, b); }
+// Base.clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x))
+template <class FT> CM_HD FT clamp_(FT x, FT lo, FT hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }
+CM_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
+CM_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+
+// ---- IEEE operations (bit-identical to the CPU reference) ------------------------------------
+CM_HD double sqrt_(double x) { return sqrt(x); }
+CM_HD float sqrt_(float x) { return sqrtf(x); }
+CM_HD double div_(double a, double b) { return a / b; }
+CM_HD float div_(float a, float b) { return a / b; }
+
+// ---- reciprocal: <= 1 ulp, normal finite x ---------------------------------------------------
+CM_HD double rcp_(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H: ~20 good bits
+#else
+    double r = mk64(hi32(1.0 / x) & 0xfffffc00, 0);  // host emulation of the 20-bit seed
+#endif
+    double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);  // cubic: 60 bits
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+CM_HD float rcp_(float x) { return 1.0f / x; }
+
+// ---- exp: |x| <= 708 (callers' arguments are bounded; see exp_full_ otherwise) ---------------
+// x = (64 e + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^e * T[j] * (1 + expm1(r)).
+CM_HD double exp_(double x) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, 9.23324826168936568e+01, magic);  // 64 / ln 2
+    const int ki = lo32(t);
+    const double kf = t - magic;
+    double r = fma(kf, -1.08304246962491451e-02, x);  // -ln2/64: fl(ln2/64)
+    r = fma(kf, -3.62351064663484306e-19, r);         // -(ln2/64 - fl(ln2/64))
+    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);  // 1/120, 1/24
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = p * r;  // expm1(r)
+    const double T = exp_tab(ki & 63);
+    const double y = fma(T, p, T);
+    return mk64(hi32(y) + ((ki >> 6) << 20), lo32(y));
+}
+// exp with the IEEE limits: 0 below the normal range, +Inf above, NaN propagated.
+CM_HD double exp_full_(double x) {
+    const double y = exp_(fmin(fmax(x, -708.0), 709.0));
+    return (x != x) ? x : ((x < -708.0) ? 0.0 : ((x > 709.0) ? num<double>::inf() : y));
+}
+CM_HD float exp_(float x) { return expf(x); }
+CM_HD float exp_full_(float x) { return expf(x); }
+
+// ---- log: positive, normal, finite x ------------------------------------------------------
+// x = 2^k z, z in [0.6875, 1.375); z = c (1 + r) with 1/c, -log(1/c) tabulated (128 cells).
+CM_HD double logp_(double x) {
+    const int hx = hi32(x);
+    const int tmp = hx - 0x3fe60000;
+    const int i = (tmp >> 13) & 127;
+    const int k = tmp >> 20;  // arithmetic shift: floor
+    const double z = mk64(hx - (k << 20), lo32(x));
+    double invc, logc;
+    log_tab(i, invc, logc);
+    const double r = fma(z, invc, -1.0);
+    const double kd = (double)k;
+    const double w = fma(kd, 6.93147180559945286e-01, logc);  // fl(ln2)
+    double q = fma(r, 1.4285714285714285e-01, -1.6666666666666666e-01);  // 1/7, -1/6
+    q = fma(q, r, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 3.3333333333333331e-01);
+    q = fma(q, r, -0.5);
+    const double r2 = r * r;
+    const double lo = fma(r2, q, kd * 2.31904681384629956e-17);  // + k (ln2 - fl(ln2))
+    return (w + r) + lo;
+}
+CM_HD float logp_(float x) { return logf(x); }
+CM_HD double log_full_(double x) { return log(x); }
+CM_HD float log_full_(float x) { return logf(x); }
+
+// ---- pow: x positive normal, |y ln x| <= 708 ---------------------------------------------
+CM_HD double powp_(double x, double y) { return exp_(y * logp_(x)); }
+CM_HD float powp_(float x, float y) { return powf(x, y); }
+CM_HD double pow_full_(double x, double y) { return pow(x, y); }
+CM_HD float pow_full_(float x, float y) { return powf(x, y); }
+
+// ---- cbrt: positive, normal, finite x -------------------------------------------------------
+CM_HD double cbrtp_(double x) {
+    const int hx = hi32(x);
+    const int e = (hx >> 20) - 1023;               // x = m 2^e, m in [1, 2)
+    const int q = ((e + 3072) * 43691 >> 17) - 1024;  // floor(e / 3) for |e| <= 1100
+    const double a = mk64(hx - ((3 * q) << 20), lo32(x));  // a = x 2^(-3q) in [1, 8)
+    // r0 ~ a^(-1/3) from the FP32 special-function unit (relative error ~ 2^-21)
+#ifdef __CUDA_ARCH__
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((float)a));
+    float rf;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(l * -0.33333334f));
+    double r = (double)rf;
+#else
+    double r = (double)(float)(1.0 / std::cbrt(a)) * (1.0 + 3e-7);
+#endif
+    // one cubically convergent step on r -> a^(-1/3): e = 1 - a r^3, r *= 1 + e/3 + 2 e^2/9
+    double r2 = r * r;
+    const double err = fma(-(a * r), r2, 1.0);
+    const double pe = fma(err, 2.2222222222222221e-01, 3.3333333333333331e-01) * err;
+    r = fma(r, pe, r);
+    r2 = r * r;
+    double y = a * r2;  // a^(1/3), ~2-3 ulp
+    // one Newton correction with the residual computed by fma: y -= (y^3 - a) / (3 y^2)
+    const double d = fma(-(y * y), y, a);
+    y = fma(d, r2 * 3.3333333333333331e-01, y);
+    return mk64(hi32(y) + (q << 20), lo32(y));
+}
+CM_HD float cbrtp_(float x) { return cbrtf(x); }
+CM_HD double cbrt_full_(double x) { return cbrt(x); }
+CM_HD float cbrt_full_(float x) { return cbrtf(x); }
+
+// ---- rarely used special functions: CUDA libm ------------------------------------------------
+CM_HD double expm1_(double x) { return expm1(x); }
+CM_HD float expm1_(float x) { return expm1f(x); }
+CM_HD double log1p_(double x) { return log1p(x); }
+CM_HD float log1p_(float x) { return log1pf(x); }
+CM_HD double tgamma_(double x) { return tgamma(x); }
+CM_HD float tgamma_(float x) { return tgammaf(x); }
+CM_HD double lgamma_(double x) { return lgamma(x); }
+CM_HD float lgamma_(float x) { return lgammaf(x); }
+CM_HD double erf_(double x) { return erf(x); }
+CM_HD float erf_(float x) { return erff(x); }
+CM_HD double erfc_(double x) { return erfc(x); }
+CM_HD float erfc_(float x) { return erfcf(x); }
+CM_HD double tanh_(double x) { return tanh(x); }
+CM_HD float tanh_(float x) { return tanhf(x); }
 
 // x^y for a parameter exponent that is very often a small integer (SB2006's
-// b = 3, c = 4, d = -5): the integer cases are exact products, everything else
-// goes through pow_.  `y` is uniform across the grid, so the branch is free.
-template <class FT> CM_DEV FT pow_param(FT x, FT y) {
+// b = 3, c = 4, d = -5): the integer cases are exact products (what Julia's ^ gives for
+// these literal-valued parameters to within 1 ulp), everything else goes through powp_.
+// `y` is uniform across the grid, so the branch is free.
+template <class FT> CM_HD FT pow_param(FT x, FT y) {
     if (y == FT(2)) return x * x;
     if (y == FT(3)) return x * x * x;
     if (y == FT(4)) { FT x2 = x * x; return x2 * x2; }
     if (y == FT(-5)) { FT x2 = x * x; return FT(1) / (x2 * x2 * x); }
     if (y == FT(1)) return x;
-    return pow_(x, y);
+    return powp_(x, y);
 }
 
 // --- 128-bit vector access ------------------------------------------------------------
@@ -92,6 +284,7 @@ template <> struct vec<float> {
 
 template <class FT, int N> struct pack { FT v[N]; };
 
+#ifdef __CUDACC__
 CM_DEV pack<double, 2> ldg_vec(const double* p) {
     double2 t = __ldg(reinterpret_cast<const double2*>(p));
     pack<double, 2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
@@ -106,5 +299,6 @@ CM_DEV void st_vec(double* p, const pack<double, 2>& r) {
 CM_DEV void st_vec(float* p, const pack<float, 4>& r) {
     __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
 }
+#endif
 
 }  // namespace cm

@@ -28,7 +28,8 @@ template <class FT> struct SB2006K {
     FT cbrt_Sc;       // cbrt(nu_air / max(D_vapor, eps))
     FT inv_nu_air;
     FT inv_K_safe, inv_D_safe;
-    FT gi_c1[2], gi_e1[2], gi_c2[2], gi_e2[2];  // Γ_incl coefficients for a = -1 and a = beta_vent_0
+    FT gi_c1[2], gi_e1[2], gi_c2[2], gi_de[2];  // Γ_incl coefficients for a = -1 and a = beta_vent_0 (de = e2 - e1)
+    FT cbrt_six_over_pi_rho_w, cbrt_six_x_star_r, log_six_x_star_r_third, cbrt_one_sixth;
     FT inv_numadj_tau;
     FT inv_xc_min, inv_xc_max, inv_xr_max;
     FT two_pi;
@@ -56,8 +57,12 @@ __host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, cons
         k.gi_c1[i] = FT(0.33) - FT(0.7) * a[i];
         k.gi_e1[i] = FT(0.08) - FT(0.93) * a[i];
         k.gi_c2[i] = FT(1.34) - FT(0.1) * a[i];
-        k.gi_e2[i] = FT(0.8) - a[i];
+        k.gi_de[i] = (FT(0.8) - a[i]) - k.gi_e1[i];
     }
+    k.cbrt_six_over_pi_rho_w = std::cbrt(k.six_over_pi_rho_w);
+    k.cbrt_six_x_star_r = std::cbrt(k.six_x_star_r);
+    k.log_six_x_star_r_third = std::log(k.six_x_star_r) / 3;
+    k.cbrt_one_sixth = std::cbrt(FT(1) / FT(6));
     k.inv_numadj_tau = FT(1) / sb.numadj_tau;
     k.inv_xc_min = FT(1) / sb.pdf_c.xc_min;
     k.inv_xc_max = FT(1) / sb.pdf_c.xc_max;
@@ -69,27 +74,29 @@ __host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, cons
 template <class FT> struct RainPDF { FT N0r, Dr_mean, xr_mean, lam; };
 
 // CM2.pdf_rain_parameters                                          CM2:67-110
+// (q and N are the caller's already-floored safe values, as at every reference call site.)
 template <class FT>
 CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT pi_rho_w, FT q, FT rho, FT N) {
     const FT e = num<FT>::eps();
-    FT safe_q = fmax_(q, e);
-    FT safe_N = fmax_(N, e);
-    FT L = rho * safe_q;
+    const FT safe_q = fmax_(q, e);
+    const FT safe_N = fmax_(N, e);
+    const FT L = rho * safe_q;
     RainPDF<FT> r;
     if (!pdf.limited) {
-        FT xr_mean = L / safe_N;
-        FT lam = cbrt_(pi_rho_w / xr_mean);
-        bool cond = (N < e) || (q < e);
+        const FT xr_mean = L * rcp_(safe_N);
+        const FT lam = cbrtp_(pi_rho_w * safe_N * rcp_(L));
+        const bool cond = (N < e) || (q < e);
         r.lam = lam;
         r.N0r = cond ? FT(0) : lam * safe_N;
         r.Dr_mean = cond ? FT(0) : rcp_(lam);
         r.xr_mean = cond ? FT(0) : xr_mean;
     } else {
-        FT xt = clamp_(L / safe_N, pdf.xr_min, pdf.xr_max);                        // SB2006 Eq. (94)
-        FT N0r = clamp_(safe_N * cbrt_(pi_rho_w / xt), pdf.N0_min, pdf.N0_max);    // Eq. (95)
-        FT lam = clamp_(sqrt_(sqrt_(pi_rho_w * N0r / L)), pdf.lam_min, pdf.lam_max);  // Eq. (96)
-        FT xr_mean = clamp_(L * lam / N0r, pdf.xr_min, pdf.xr_max);                // Eq. (97)
-        bool cond = (N < e) && (q < e);
+        const FT inv_L = rcp_(L);
+        const FT xt = clamp_(L * rcp_(safe_N), pdf.xr_min, pdf.xr_max);                       // SB2006 Eq. (94)
+        const FT N0r = clamp_(safe_N * cbrtp_(pi_rho_w * rcp_(xt)), pdf.N0_min, pdf.N0_max);  // Eq. (95)
+        const FT lam = clamp_(sqrt_(sqrt_(pi_rho_w * N0r * inv_L)), pdf.lam_min, pdf.lam_max);  // Eq. (96)
+        const FT xr_mean = clamp_(L * lam * rcp_(N0r), pdf.xr_min, pdf.xr_max);                // Eq. (97)
+        const bool cond = (N < e) && (q < e);
         r.lam = lam;
         r.N0r = cond ? FT(0) : N0r;
         r.Dr_mean = cond ? FT(0) : rcp_(lam);
@@ -100,7 +107,7 @@ CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT p
 
 // CM2.number_tendency_from_mass_limits                              CM2:882-891
 template <class FT> CM_DEV FT number_tendency_from_mass_limits(FT inv_x_min, FT inv_x_max, FT inv_tau, FT q, FT n) {
-    FT n_target = (q < num<FT>::eps()) ? FT(0) : clamp_(n, q * inv_x_max, q * inv_x_min);
+    const FT n_target = (q < num<FT>::eps()) ? FT(0) : clamp_(n, q * inv_x_max, q * inv_x_min);
     return (n_target - n) * inv_tau;
 }
 
@@ -111,6 +118,10 @@ template <class FT> struct Warm2M {
 
 // BMT.bulk_microphysics_tendencies(::Microphysics2Moment, mp{WR,Nothing}, ...)  BMT:820-854
 // q_ice is the cloud-ice content seen by the thermodynamics (0 for warm-only).
+//
+// Where the reference subtracts nearly equal numbers (tau = 1 - q_l/(q_l+q_r), and the
+// (1 - tau) it forms from it) the operations are IEEE and in the reference's order, so
+// the rounding pattern is the reference's own.
 template <class FT>
 CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& p, const ThermoK<FT>& tk,
                                           const SB2006K<FT>& sk, FT rho, FT T, FT q_tot, FT q_lcl, FT n_lcl,
@@ -133,20 +144,21 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     // ---- thermodynamic state shared by cond/evap and rain evaporation
     const TempState<FT> ts = temp_state(tk, T);
     const FT p_vs = p_sat_liq(tk, ts);
+    const FT inv_p_vs = rcp_(fmax_(p_vs, num<FT>::eps_numerics()));
     const FT Lv = latent_heat_vapor(tk, T);
     const FT q_liq = q_lcl + q_rai;
     const FT qv = q_vap(q_tot, q_liq, q_ice);
     const FT rho_Rv_T = rho * tk.R_v * T;
+    const FT qv_sat = p_vs * rcp_(rho_Rv_T);
+    const FT sat_excess = qv - qv_sat;
 
     // ---- NEQ._conv_q_vap_to_q_lcl_const                            NEQ:117-140
     {
-        FT cp_air = cp_m(tk, q_tot, q_liq, q_ice);
-        FT qv_sat = p_vs * rcp_(rho_Rv_T);
-        FT dqsl_dT = qv_sat * (Lv * tk.inv_R_v * ts.inv_T * ts.inv_T - ts.inv_T);  // NEQ.dqcld_dT
-        FT Gam = FT(1) + Lv * rcp_(cp_air) * dqsl_dT;                                 // NEQ.gamma_helper
-        FT sat_excess = qv - qv_sat;
-        FT inv_ts = rcp_(p.condevap_tau_relax * Gam);
-        FT cond = (sat_excess < FT(0)) ? -fmin_(-sat_excess, q_lcl) * inv_ts : sat_excess * inv_ts;
+        const FT cp_air = cp_m(tk, q_tot, q_liq, q_ice);
+        const FT dqsl_dT = qv_sat * fma_(Lv * tk.inv_R_v * ts.inv_T, ts.inv_T, -ts.inv_T);  // NEQ.dqcld_dT
+        // 1/(tau Gamma), Gamma = 1 + Lv/cp_air dqsl_dT                                     NEQ.gamma_helper
+        const FT inv_ts = cp_air * rcp_(p.condevap_tau_relax * fma_(Lv, dqsl_dT, cp_air));
+        const FT cond = (sat_excess < FT(0)) ? -fmin_(-sat_excess, q_lcl) * inv_ts : sat_excess * inv_ts;
         o.leaf[CUMICRO_SB_COND_DQ_LCL] = cond;
     }
 
@@ -155,88 +167,92 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     const FT safe_N_rai = fmax_(N_rai, e);
     const RainPDF<FT> rp = pdf_rain_parameters<FT>(sb.pdf_r, sk.pi_rho_w, safe_q_rai, rho, safe_N_rai);
     const FT xr_mean = rp.xr_mean;
-    const FT inv_xr_mean = rcp_(xr_mean);
-    const FT Dr = cbrt_(xr_mean * sk.six_over_pi_rho_w);  // mean-volume diameter  CM2:590, 802
+    // every power of xr_mean below comes from ONE cube root and ONE logarithm
+    const FT cx = cbrtp_(xr_mean);
+    const FT inv_cx = rcp_(cx);
+    const FT inv_xr_mean = inv_cx * inv_cx * inv_cx;
+    const FT Dr = cx * sk.cbrt_six_over_pi_rho_w;  // cbrt(6 xr/(pi rho_w)): mean-volume diameter  CM2:590, 802
     const FT sqrt_rho0_rho = sqrt_(sb.pdf_r.rho0 * inv_rho);
     const bool no_rain = (q_rai < e) || (N_rai < e);
 
     // ---- CM2.rain_evaporation                                       CM2:780-828
     {
-        FT S = qv * rho_Rv_T * rcp_(p_vs) - FT(1);                     // TDI.supersaturation_over_liquid
-        FT G = G_func(tk, sk.inv_K_safe, sk.inv_D_safe, Lv, p_vs, ts);  // CO.G_func_liquid
-        FT t_star = cbrt_(sk.six_x_star_r * inv_xr_mean);
-        // Γ_incl(a, t) = exp(-t) / (c1 t^e1 + c2 t^e2), a ∈ {-1, beta_vent_0}   CM2:746-753
-        FT lt = log_(t_star);
-        FT emt = exp_(-t_star);
-        FT gi0 = emt * rcp_(sk.gi_c1[0] * exp_(sk.gi_e1[0] * lt) + sk.gi_c2[0] * exp_(sk.gi_e2[0] * lt));
-        FT gi1 = emt * rcp_(sk.gi_c1[1] * exp_(sk.gi_e1[1] * lt) + sk.gi_c2[1] * exp_(sk.gi_e2[1] * lt));
-        FT a_vent_0 = sb.evap.a_vent_0_coeff * gi0;
-        FT b_vent_0 = sb.evap.b_vent_0_coeff * gi1;
-        FT sqrt_rho0e = (sb.evap.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.evap.rho0 * inv_rho);
-        FT N_Re = sb.evap.alpha * pow_(xr_mean, sb.evap.beta) * sqrt_rho0e * Dr * sk.inv_nu_air;
-        FT v = sk.cbrt_Sc * sqrt_(N_Re);
-        FT Fv0 = a_vent_0 + b_vent_0 * v;
-        FT Fv1 = sb.evap.a_vent_1 + sb.evap.b_vent_1 * v;
-        FT common = sk.two_pi * G * S * N_rai * Dr;
-        FT dn = fmin_(FT(0), common * Fv0 * inv_xr_mean);
-        FT dq = fmin_(FT(0), common * Fv1 * inv_rho);
-        bool off_q = (q_rai < e) || (N_rai <= e) || (S >= FT(0));
-        bool off_n = off_q || (xr_mean * sk.inv_xr_min < e);
+        const FT S = fma_(qv * rho_Rv_T, inv_p_vs, FT(-1));                  // TDI.supersaturation_over_liquid
+        const FT G = G_func(tk, sk.inv_K_safe, sk.inv_D_safe, Lv, inv_p_vs, ts);  // CO.G_func_liquid
+        const FT lx = logp_(xr_mean);
+        const FT t_star = sk.cbrt_six_x_star_r * inv_cx;           // cbrt(6 x*/xr)
+        const FT lt = fma_(lx, FT(-1.0 / 3.0), sk.log_six_x_star_r_third);  // log(t_star)
+        // Γ_incl(a, t) = exp(-t) / (c1 t^e1 + c2 t^e2) = exp(-t - e1 ln t) / (c1 + c2 t^(e2-e1))   CM2:746-753
+        const FT gi0 = exp_(fma_(-sk.gi_e1[0], lt, -t_star)) * rcp_(fma_(sk.gi_c2[0], exp_(sk.gi_de[0] * lt), sk.gi_c1[0]));
+        const FT gi1 = exp_(fma_(-sk.gi_e1[1], lt, -t_star)) * rcp_(fma_(sk.gi_c2[1], exp_(sk.gi_de[1] * lt), sk.gi_c1[1]));
+        const FT a_vent_0 = sb.evap.a_vent_0_coeff * gi0;
+        const FT b_vent_0 = sb.evap.b_vent_0_coeff * gi1;
+        const FT sqrt_rho0e = (sb.evap.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.evap.rho0 * inv_rho);
+        const FT N_Re = sb.evap.alpha * exp_(sb.evap.beta * lx) * sqrt_rho0e * Dr * sk.inv_nu_air;
+        const FT v = sk.cbrt_Sc * sqrt_(N_Re);
+        const FT Fv0 = fma_(b_vent_0, v, a_vent_0);
+        const FT Fv1 = fma_(sb.evap.b_vent_1, v, sb.evap.a_vent_1);
+        const FT common = sk.two_pi * G * S * N_rai * Dr;
+        const FT dn = fmin_(FT(0), common * Fv0 * inv_xr_mean);
+        const FT dq = fmin_(FT(0), common * Fv1 * inv_rho);
+        const bool off_q = (q_rai < e) || (N_rai <= e) || (S >= FT(0));
+        const bool off_n = off_q || (xr_mean * sk.inv_xr_min < e);
         o.leaf[CUMICRO_SB_EVAP_DN_RAI] = off_n ? FT(0) : dn;
         o.leaf[CUMICRO_SB_EVAP_DQ_RAI] = off_q ? FT(0) : dq;
     }
 
     // ---- CM2.autoconversion + CM2.accretion (shared tau)             CM2:396-470
     {
-        FT safe_q_lcl = fmax_(q_lcl, e);
-        FT safe_N_lcl = fmax_(N_lcl, e);
-        FT L_lcl = rho * safe_q_lcl;
-        FT xbar = L_lcl * rcp_(safe_N_lcl);
-        FT x_lcl = fmin_(sb.acnv.x_star, xbar);
-        FT one_m_tau = safe_q_lcl * rcp_(safe_q_lcl + q_rai);  // q_rai >= 0 after the input clamp
-        FT tau = FT(1) - one_m_tau;                             // SB2006 Eq. (5)
-        FT tau_a = pow_(tau, sb.acnv.a);
-        FT phi_au = (q_rai < e) ? FT(0) : sb.acnv.A * tau_a * pow_param(FT(1) - tau_a, sb.acnv.b);
-        FT LL = L_lcl * L_lcl;
-        FT dL_rai_dt = sk.acnv_pref * LL * (x_lcl * x_lcl) *
-                       (FT(1) + phi_au * rcp_(one_m_tau * one_m_tau)) * inv_rho;   // Eq. (4)
-        FT dN_rai_dt = dL_rai_dt * sk.inv_x_star;
-        bool off = (q_lcl < e) || (N_lcl < e);
-        FT dq = off ? FT(0) : dL_rai_dt * inv_rho;
-        FT dN_rai = off ? FT(0) : dN_rai_dt;
-        FT dN_lcl_au = off ? FT(0) : FT(-2) * dN_rai_dt;
+        const FT safe_q_lcl = fmax_(q_lcl, e);
+        const FT safe_N_lcl = fmax_(N_lcl, e);
+        const FT L_lcl = rho * safe_q_lcl;
+        const FT inv_L_lcl = rcp_(L_lcl);
+        const FT x_lcl = fmin_(sb.acnv.x_star, L_lcl * rcp_(safe_N_lcl));
+        const FT tau = FT(1) - div_(safe_q_lcl, safe_q_lcl + q_rai);          // SB2006 Eq. (5), IEEE, reference order
+        const FT one_m_tau = FT(1) - tau;
+        const FT tau_a = powp_(tau, sb.acnv.a);
+        const FT phi_au = (q_rai < e) ? FT(0) : sb.acnv.A * tau_a * pow_param(FT(1) - tau_a, sb.acnv.b);
+        const FT LL = L_lcl * L_lcl;
+        const FT dL_rai_dt = sk.acnv_pref * LL * (x_lcl * x_lcl) *
+                             fma_(phi_au, rcp_(one_m_tau * one_m_tau), FT(1)) * inv_rho;   // Eq. (4)
+        const FT dN_rai_dt = dL_rai_dt * sk.inv_x_star;
+        const bool off = (q_lcl < e) || (N_lcl < e);
+        const FT dq = off ? FT(0) : dL_rai_dt * inv_rho;
+        const FT dN_rai = off ? FT(0) : dN_rai_dt;
+        const FT dN_lcl_au = off ? FT(0) : FT(-2) * dN_rai_dt;
         o.leaf[CUMICRO_SB_ACNV_DQ_LCL] = -dq;
         o.leaf[CUMICRO_SB_ACNV_DN_LCL] = dN_lcl_au;
         o.leaf[CUMICRO_SB_ACNV_DQ_RAI] = dq;
         o.leaf[CUMICRO_SB_ACNV_DN_RAI] = dN_rai;
 
         // CM2.cloud_liquid_self_collection (uses the unclamped q_lcl)   CM2:488-501
-        FT Lu = rho * q_lcl;
-        FT sc = -sk.lclsc_pref * inv_rho * (Lu * Lu) - dN_lcl_au;
+        const FT Lu = rho * q_lcl;
+        const FT sc = -sk.lclsc_pref * inv_rho * (Lu * Lu) - dN_lcl_au;
         o.leaf[CUMICRO_SB_LCL_SELFCOL] = (q_lcl < e) ? FT(0) : sc;
 
         // CM2.accretion                                                  CM2:445-470
-        FT L_rai = rho * safe_q_rai;
-        FT sqrt_rho0a = (sb.accr.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.accr.rho0 * inv_rho);
-        FT phi_ac = pow_param(tau * rcp_(tau + sb.accr.tau0), sb.accr.c);     // Eq. (8)
-        FT dLr = sb.accr.kcr * L_lcl * L_rai * phi_ac * sqrt_rho0a;          // Eq. (7)
-        bool off_ac = (q_lcl < e) || (q_rai < e) || (N_lcl < e);
-        FT dq_ac = off_ac ? FT(0) : dLr * inv_rho;
+        const FT L_rai = rho * safe_q_rai;
+        // (accretion floors q_rai at eps instead of 0, CM2:452, but is gated off below eps: same tau)
+        const FT sqrt_rho0a = (sb.accr.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.accr.rho0 * inv_rho);
+        const FT phi_ac = pow_param(tau * rcp_(tau + sb.accr.tau0), sb.accr.c);   // Eq. (8)
+        const FT dLr = sb.accr.kcr * L_lcl * L_rai * phi_ac * sqrt_rho0a;             // Eq. (7)
+        const bool off_ac = (q_lcl < e) || (q_rai < e) || (N_lcl < e);
+        const FT dq_ac = off_ac ? FT(0) : dLr * inv_rho;
         o.leaf[CUMICRO_SB_ACCR_DQ_LCL] = -dq_ac;
-        o.leaf[CUMICRO_SB_ACCR_DN_LCL] = off_ac ? FT(0) : -dLr * safe_N_lcl * rcp_(L_lcl);  // dL_lcl_dt / x_lcl
+        o.leaf[CUMICRO_SB_ACCR_DN_LCL] = off_ac ? FT(0) : -dLr * safe_N_lcl * inv_L_lcl;  // dL_lcl_dt / x_lcl
         o.leaf[CUMICRO_SB_ACCR_DQ_RAI] = dq_ac;
     }
 
     // ---- CM2.rain_self_collection / rain_breakup                       CM2:545-601
     {
-        FT L_rai = rho * safe_q_rai;
-        FT inv_Br = cbrt_(xr_mean * FT(1.0 / 6.0));   // 1/Br, Br = cbrt(6/xr_mean)   CM2:141-146
-        FT sc = -sb.self.krr * N_rai * L_rai * sqrt_rho0_rho * pow_param(FT(1) + sb.self.kappa_rr * inv_Br, sb.self.d);
+        const FT L_rai = rho * safe_q_rai;
+        const FT inv_Br = cx * sk.cbrt_one_sixth;   // 1/Br, Br = cbrt(6/xr_mean)   CM2:141-146
+        FT sc = -sb.self.krr * N_rai * L_rai * sqrt_rho0_rho * pow_param(fma_(sb.self.kappa_rr, inv_Br, FT(1)), sb.self.d);
         sc = no_rain ? FT(0) : sc;
-        FT dD = Dr - sb.brek.Deq;
-        FT phi_p1 = (Dr < sb.brek.Dr_th) ? FT(0)
-                                         : ((Dr <= sb.brek.Deq) ? sb.brek.kbr * dD + FT(1) : exp_(sb.brek.kappa_br * dD));
-        FT br = no_rain ? FT(0) : -phi_p1 * sc;   // Eq. (13): -(Φ_br + 1) dN_sc
+        const FT dD = Dr - sb.brek.Deq;
+        const FT phi_p1 = (Dr < sb.brek.Dr_th) ? FT(0)
+                                               : ((Dr <= sb.brek.Deq) ? fma_(sb.brek.kbr, dD, FT(1)) : exp_(sb.brek.kappa_br * dD));
+        const FT br = no_rain ? FT(0) : -phi_p1 * sc;   // Eq. (13): -(Φ_br + 1) dN_sc
         o.leaf[CUMICRO_SB_RAI_SELFCOL] = sc;
         o.leaf[CUMICRO_SB_RAI_BREAKUP] = br;
     }
@@ -250,11 +266,11 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     // ---- aggregate in the order of BMT:736-779
     o.dq_lcl_dt = o.leaf[CUMICRO_SB_COND_DQ_LCL] + o.leaf[CUMICRO_SB_ACNV_DQ_LCL] + o.leaf[CUMICRO_SB_ACCR_DQ_LCL];
     o.dq_rai_dt = o.leaf[CUMICRO_SB_EVAP_DQ_RAI] + o.leaf[CUMICRO_SB_ACNV_DQ_RAI] + o.leaf[CUMICRO_SB_ACCR_DQ_RAI];
-    o.dn_lcl_dt = (o.leaf[CUMICRO_SB_ACNV_DN_LCL] + o.leaf[CUMICRO_SB_LCL_SELFCOL] + o.leaf[CUMICRO_SB_ACCR_DN_LCL]) * inv_rho +
-                  o.leaf[CUMICRO_SB_NUMADJ_LCL];
-    o.dn_rai_dt = (o.leaf[CUMICRO_SB_EVAP_DN_RAI] + o.leaf[CUMICRO_SB_ACNV_DN_RAI] + o.leaf[CUMICRO_SB_RAI_SELFCOL] +
-                   o.leaf[CUMICRO_SB_RAI_BREAKUP]) * inv_rho +
-                  o.leaf[CUMICRO_SB_NUMADJ_RAI];
+    o.dn_lcl_dt = fma_(o.leaf[CUMICRO_SB_ACNV_DN_LCL] + o.leaf[CUMICRO_SB_LCL_SELFCOL] + o.leaf[CUMICRO_SB_ACCR_DN_LCL],
+                       inv_rho, o.leaf[CUMICRO_SB_NUMADJ_LCL]);
+    o.dn_rai_dt = fma_(o.leaf[CUMICRO_SB_EVAP_DN_RAI] + o.leaf[CUMICRO_SB_ACNV_DN_RAI] + o.leaf[CUMICRO_SB_RAI_SELFCOL] +
+                           o.leaf[CUMICRO_SB_RAI_BREAKUP],
+                       inv_rho, o.leaf[CUMICRO_SB_NUMADJ_RAI]);
     return o;
 }
 
@@ -273,10 +289,10 @@ CM_DEV void rain_terminal_velocity_sb(const typename P<FT>::sb_pdf_r& pdf_r, con
     const FT Dr_mean = r.Dr_mean;
     FT pa0 = FT(1), pb0 = FT(1), pa1 = FT(1), pb1 = FT(1);
     if (!pdf_r.limited) {
-        const FT lam = rcp_(Dr_mean);
-        const FT two_rc = -log_(vel.aR / vel.bR) / vel.cR;  // 2 rc, rc = -1/(2 cR) log(aR/bR)
+        const FT lam = FT(1) / Dr_mean;
+        const FT two_rc = -log_full_(vel.aR / vel.bR) / vel.cR;  // 2 rc, rc = -1/(2 cR) log(aR/bR)
         const FT ta = two_rc * lam, tb = two_rc * (lam + vel.cR);
-        const FT ea = exp_(-ta), eb = exp_(-tb);
+        const FT ea = exp_full_(-ta), eb = exp_full_(-tb);
         pa0 = ea;
         pb0 = eb;
         pa1 = (ta * ta * ta + FT(3) * (ta * ta) + FT(6) * ta + FT(6)) * ea / FT(6);
@@ -295,20 +311,20 @@ CM_DEV void rain_terminal_velocity_sb(const typename P<FT>::sb_pdf_r& pdf_r, con
 template <class FT>
 CM_DEV void chen2022_vel_coeffs_rain(const typename P<FT>::vel_chen_rain& v, FT rho, FT aiu[3], FT bi[3], FT ciu[3]) {
     rho = fmax_(rho, FT(0));
-    const FT q = exp_(v.rho0 * rho);
+    const FT q = exp_full_(v.rho0 * rho);
     const FT log1000 = FT(6.907755278982137);
-    FT ai[3] = {v.a[0] * q, v.a[1] * q, v.a[2] * q * pow_(rho, v.a3_pow)};
+    FT ai[3] = {v.a[0] * q, v.a[1] * q, v.a[2] * q * pow_full_(rho, v.a3_pow)};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         bi[i] = v.b[i] - v.b_rho * rho;
-        aiu[i] = ai[i] * exp_(bi[i] * log1000);  // 1000^bi
+        aiu[i] = ai[i] * exp_full_(bi[i] * log1000);  // 1000^bi
         ciu[i] = v.c[i] * FT(1000);
     }
 }
 
 // CO.Chen2022_exponential_pdf(a, b, c, lam_inv, k), k! passed as inv_fac    CO:414-422
 template <class FT> CM_DEV FT chen2022_exponential_pdf(FT a, FT b, FT c, FT log_lam_inv, FT inv_lam_inv, FT delta, FT inv_fac) {
-    return a * exp_(-delta * log_lam_inv - (b + delta) * log_(inv_lam_inv + c)) * tgamma_(b + delta) * inv_fac;
+    return a * exp_full_(-delta * log_lam_inv - (b + delta) * log_full_(inv_lam_inv + c)) * tgamma_(b + delta) * inv_fac;
 }
 
 // CM2.rain_terminal_velocity(::SB2006, ::Chen2022VelTypeRain, ...)          CM2:703-719
@@ -319,7 +335,7 @@ CM_DEV void rain_terminal_velocity_chen(const typename P<FT>::sb_pdf_r& pdf_r, c
     FT aiu[3], bi[3], ciu[3];
     chen2022_vel_coeffs_rain<FT>(vel, rho, aiu, bi, ciu);
     const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, fmax_(q_rai, e), rho, fmax_(N_rai, e));
-    const FT ll = log_(r.Dr_mean), il = rcp_(r.Dr_mean);
+    const FT ll = log_full_(r.Dr_mean), il = FT(1) / r.Dr_mean;
     FT v0 = FT(0), v3 = FT(0);
 #pragma unroll
     for (int i = 0; i < 3; ++i) v0 += chen2022_exponential_pdf<FT>(aiu[i], bi[i], ciu[i], ll, il, FT(1), FT(1));
@@ -338,13 +354,13 @@ CM_DEV void cloud_terminal_velocity(const typename P<FT>::sb_pdf_c& pdf_c, const
                                     FT pref0, const FT gratio[2], FT q_liq, FT rho, FT N_liq, FT& vt0, FT& vt1) {
     const FT e = num<FT>::eps();
     const FT safe_q = fmax_(q_liq, e), safe_N = fmax_(N_liq, e);
-    const FT logx = log_(rho * safe_q / safe_N);
+    const FT logx = log_full_(rho * safe_q / safe_N);
     const FT logB = -pdf_c.mu_c * (logx + pdf_c.loggamma_z1 - pdf_c.loggamma_z2);
     const FT pref = pref0 * (vel.rho_w / rho - FT(1));
-    const FT inv_mu = rcp_(pdf_c.mu_c);
+    const FT inv_mu = FT(1) / pdf_c.mu_c;
     // M^n / N = B^(-n/mu) * gratio
-    const FT m23 = exp_(-(FT(2.0 / 3.0) * inv_mu) * logB) * gratio[0];
-    const FT m53 = exp_(-(FT(5.0 / 3.0) * inv_mu) * logB) * gratio[1];
+    const FT m23 = exp_full_(-(FT(2.0 / 3.0) * inv_mu) * logB) * gratio[0];
+    const FT m53 = exp_full_(-(FT(5.0 / 3.0) * inv_mu) * logB) * gratio[1];
     const FT v0 = pref * m23;
     const FT v1 = pref * (safe_N * m53) / rho / safe_q;
     const bool cond = (N_liq < e) || (q_liq < e);

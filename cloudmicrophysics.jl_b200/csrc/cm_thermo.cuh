@@ -41,36 +41,36 @@ template <class FT> CM_DEV TempState<FT> temp_state(const ThermoK<FT>& k, FT T) 
     TempState<FT> s;
     s.T = T;
     s.inv_T = rcp_(T);
-    s.log_Tr = log_(T * k.inv_T_triple);
+    s.log_Tr = logp_(T * k.inv_T_triple);
     s.dinvT = (T - k.T_triple) * s.inv_T * k.inv_T_triple;  // = 1/T_triple - 1/T without cancellation
     return s;
 }
 
 // TD.saturation_vapor_pressure(tps, T, Liquid()/Ice()):
 //   p_triple (T/T_triple)^(dcp/R_v) exp((LH_0 - dcp T_0)/R_v (1/T_triple - 1/T))
-// evaluated as a single exponential.
+// evaluated as ONE exponential (one exp_ instead of the reference's pow + exp; the
+// exponent is O(10), so the result carries ~1e-15 relative error like the reference's).
 template <class FT> CM_DEV FT p_sat_liq(const ThermoK<FT>& k, const TempState<FT>& s) {
-    return k.press_triple * exp_(k.a_liq * s.log_Tr + k.b_liq * s.dinvT);
+    return k.press_triple * exp_(fma_(k.a_liq, s.log_Tr, k.b_liq * s.dinvT));
 }
 template <class FT> CM_DEV FT p_sat_ice(const ThermoK<FT>& k, const TempState<FT>& s) {
-    return k.press_triple * exp_(k.a_ice * s.log_Tr + k.b_ice * s.dinvT);
+    return k.press_triple * exp_(fma_(k.a_ice, s.log_Tr, k.b_ice * s.dinvT));
 }
-template <class FT> CM_DEV FT latent_heat_vapor(const ThermoK<FT>& k, FT T) { return k.LH_v0 + k.dcp_vl * (T - k.T_0); }
-template <class FT> CM_DEV FT latent_heat_sublim(const ThermoK<FT>& k, FT T) { return k.LH_s0 + k.dcp_vi * (T - k.T_0); }
-template <class FT> CM_DEV FT latent_heat_fusion(const ThermoK<FT>& k, FT T) { return k.LH_f0 + k.dcp_li * (T - k.T_0); }
+template <class FT> CM_DEV FT latent_heat_vapor(const ThermoK<FT>& k, FT T) { return fma_(k.dcp_vl, T - k.T_0, k.LH_v0); }
+template <class FT> CM_DEV FT latent_heat_sublim(const ThermoK<FT>& k, FT T) { return fma_(k.dcp_vi, T - k.T_0, k.LH_s0); }
+template <class FT> CM_DEV FT latent_heat_fusion(const ThermoK<FT>& k, FT T) { return fma_(k.dcp_li, T - k.T_0, k.LH_f0); }
 template <class FT> CM_DEV FT cp_m(const ThermoK<FT>& k, FT qt, FT ql, FT qi) {
-    return k.cp_d + k.dcp_vd * qt + k.dcp_lv * ql + k.dcp_iv * qi;
+    return fma_(k.dcp_iv, qi, fma_(k.dcp_lv, ql, fma_(k.dcp_vd, qt, k.cp_d)));
 }
 // TDI.q_vap                                                       TDI:60-61
 template <class FT> CM_DEV FT q_vap(FT qt, FT ql, FT qi) { return fmax_(FT(0), qt - ql - qi); }
 
 // CO.G_func_liquid / G_func_ice                                    CO:47-102
-//   1 / (L/K/T (L/R_v/T - 1) + R_v T / D / p_vs), with the reference's eps floors.
+//   1 / (L/K/T (L/R_v/T - 1) + R_v T / D / p_vs); inv_p_vs = 1/max(p_vs, eps) from the caller.
 template <class FT>
-CM_DEV FT G_func(const ThermoK<FT>& k, FT inv_K_safe, FT inv_D_safe, FT L, FT p_vs, const TempState<FT>& s) {
-    FT p_vs_safe = fmax_(p_vs, num<FT>::eps_numerics());
-    FT LT = L * s.inv_T;
-    return rcp_(LT * inv_K_safe * (LT * k.inv_R_v - FT(1)) + k.R_v * s.T * inv_D_safe * rcp_(p_vs_safe));
+CM_DEV FT G_func(const ThermoK<FT>& k, FT inv_K_safe, FT inv_D_safe, FT L, FT inv_p_vs, const TempState<FT>& s) {
+    const FT LT = L * s.inv_T;
+    return rcp_(fma_(LT * inv_K_safe, fma_(LT, k.inv_R_v, FT(-1)), k.R_v * s.T * inv_D_safe * inv_p_vs));
 }
 
 }  // namespace cm

@@ -77,6 +77,36 @@ def bmt2m_warm(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, leaves=False):
     return out
 
 
+def bmt2m_warm_bound(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, leaves=False):
+    """First-order rounding-error bounds of the reference algorithm (oracle_tracked.hpp)
+    for the outputs of ``bmt2m_warm`` on the same Float64 inputs."""
+    assert type(params).__name__.endswith("f64")
+    (rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai), n = _cols((rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai), np.float64)
+    names = ("dq_lcl_dt", "dn_lcl_dt", "dq_rai_dt", "dn_rai_dt")
+    out = {k: np.empty(n, np.float64) for k in names}
+    b4 = (C.c_void_p * 4)(*[_ptr(out[k]) for k in names])
+    leaf_ptrs, leaf_arrays = None, None
+    if leaves:
+        leaf_arrays = [np.empty(n, np.float64) for _ in range(15)]
+        leaf_ptrs = (C.c_void_p * 15)(*[_ptr(a) for a in leaf_arrays])
+    st = lib().oracle_bmt2m_warm_bound_f64(C.byref(params), C.c_int64(n),
+                                           *[_ptr(a) for a in (rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai)], b4, leaf_ptrs)
+    assert st == 0
+    if leaves:
+        out["leaves"] = leaf_arrays
+    return out
+
+
+def termvel_bound(fname, pdf, vel, q, rho, N):
+    """Error bounds for ``termvel_2m_{rain_sb,rain_chen,cloud}`` (Float64)."""
+    (q, rho, N), n = _cols((q, rho, N), np.float64)
+    b0, b1 = np.empty(n), np.empty(n)
+    st = getattr(lib(), f"oracle_{fname}_bound_f64")(C.byref(pdf), C.byref(vel), C.c_int64(n), _ptr(q), _ptr(rho),
+                                                     _ptr(N), _ptr(b0), _ptr(b1))
+    assert st == 0
+    return b0, b1
+
+
 def _termvel(fname, pdf, vel, q, rho, N):
     dtype = np.float64 if type(pdf).__name__.endswith("f64") else np.float32
     (q, rho, N), n = _cols((q, rho, N), dtype)

@@ -64,7 +64,7 @@ inline RainPDF<FT> pdf_rain_parameters(const typename PT<FT>::sb_pdf_r& pdf, FT 
     RainPDF<FT> r;
     if (!pdf.limited) {
         FT xr_mean = L / safe_N;
-        FT lam = std::cbrt(pi<FT>() * pdf.rho_w / xr_mean);
+        FT lam = cbrt_(pi<FT>() * pdf.rho_w / xr_mean);
         FT N0r = lam * safe_N;
         FT Dr_mean = 1 / lam;
         bool cond = (N < eN) || (q < eM);
@@ -73,8 +73,8 @@ inline RainPDF<FT> pdf_rain_parameters(const typename PT<FT>::sb_pdf_r& pdf, FT 
         r.xr_mean = cond ? FT(0) : xr_mean;
     } else {
         FT xt = jclamp(L / safe_N, pdf.xr_min, pdf.xr_max);                                 // Eq. (94)
-        FT N0r = jclamp(safe_N * std::cbrt(pi<FT>() * pdf.rho_w / xt), pdf.N0_min, pdf.N0_max);  // (95)
-        FT lam = jclamp(std::sqrt(std::sqrt(pi<FT>() * pdf.rho_w * N0r / L)), pdf.lam_min, pdf.lam_max);  // (96)
+        FT N0r = jclamp(safe_N * cbrt_(pi<FT>() * pdf.rho_w / xt), pdf.N0_min, pdf.N0_max);  // (95)
+        FT lam = jclamp(sqrt_(sqrt_(pi<FT>() * pdf.rho_w * N0r / L)), pdf.lam_min, pdf.lam_max);  // (96)
         FT xr_mean = jclamp(L * lam / N0r, pdf.xr_min, pdf.xr_max);                         // (97)
         FT Dr_mean = 1 / lam;
         bool cond = (N < eN) && (q < eM);
@@ -90,7 +90,7 @@ template <class FT>
 inline void pdf_rain_parameters_mass(const typename PT<FT>::sb_pdf_r& pdf, FT q, FT rho, FT N,
                                      FT& Ar, FT& Br) {
     RainPDF<FT> r = pdf_rain_parameters<FT>(pdf, q, rho, N);
-    Br = std::cbrt(6 / r.xr_mean);
+    Br = cbrt_(6 / r.xr_mean);
     Ar = N * Br / 3;
 }
 
@@ -102,10 +102,10 @@ inline void log_pdf_cloud_parameters_mass(const typename PT<FT>::sb_pdf_c& pdf, 
     FT safe_q = jmax(q, eM);
     FT safe_N = jmax(N, eN);
     FT L = rho * safe_q;
-    FT logx = std::log(L / safe_N);
+    FT logx = log_(L / safe_N);
     FT z1 = (pdf.nu_c + 1) / pdf.mu_c;
     FT lB = -pdf.mu_c * (logx + pdf.loggamma_z1 - pdf.loggamma_z2);
-    FT lA = std::log(pdf.mu_c) + std::log(safe_N) + z1 * lB - pdf.loggamma_z1;
+    FT lA = log_(pdf.mu_c) + log_(safe_N) + z1 * lB - pdf.loggamma_z1;
     bool cond = (N < eN) || (q < eM);
     logA = cond ? -inf<FT>() : lA;
     logB = cond ? inf<FT>() : lB;
@@ -116,8 +116,8 @@ inline void pdf_cloud_parameters_mass(const typename PT<FT>::sb_pdf_c& pdf, FT q
                                       FT& Ac, FT& Bc) {
     FT lA, lB;
     log_pdf_cloud_parameters_mass<FT>(pdf, q, rho, N, lA, lB);
-    Ac = std::exp(lA);
-    Bc = std::exp(lB);
+    Ac = exp_(lA);
+    Bc = exp_(lB);
 }
 
 template <class FT> struct LclRaiRates { FT dq_lcl_dt, dN_lcl_dt, dq_rai_dt, dN_rai_dt; };
@@ -136,7 +136,7 @@ inline LclRaiRates<FT> autoconversion(const typename PT<FT>::sb_acnv& acnv,
     FT x_lcl = jmin(x_star, L_lcl / safe_N_lcl);
     FT safe_q_rai = jmax(FT(0), q_rai);
     FT tau = 1 - safe_q_lcl / (safe_q_lcl + safe_q_rai);  // Eq. (5)
-    FT phi_au = (q_rai < eM) ? FT(0) : A * std::pow(tau, a) * std::pow(1 - std::pow(tau, a), b);
+    FT phi_au = (q_rai < eM) ? FT(0) : A * pow_(tau, a) * pow_(1 - pow_(tau, a), b);
     FT nu1 = nu_c + 1;
     FT dL_rai_dt = kcc / 20 / x_star * (nu_c + 2) * (nu_c + 4) / (nu1 * nu1) * (L_lcl * L_lcl) *
                    (x_lcl * x_lcl) * (1 + phi_au / ((1 - tau) * (1 - tau))) * rho0 / rho;  // Eq. (4)
@@ -164,8 +164,8 @@ inline LclRaiRates<FT> accretion(const typename PT<FT>::sb_accr& accr, FT q_lcl,
     FT L_rai = rho * safe_q_rai;
     FT x_lcl = L_lcl / safe_N_lcl;
     FT tau = 1 - safe_q_lcl / (safe_q_lcl + safe_q_rai);  // Eq. (5)
-    FT phi_ac = std::pow(tau / (tau + accr.tau0), accr.c);  // Eq. (8)
-    FT dL_rai_dt = accr.kcr * L_lcl * L_rai * phi_ac * std::sqrt(accr.rho0 / rho);  // Eq. (7)
+    FT phi_ac = pow_(tau / (tau + accr.tau0), accr.c);  // Eq. (8)
+    FT dL_rai_dt = accr.kcr * L_lcl * L_rai * phi_ac * sqrt_(accr.rho0 / rho);  // Eq. (7)
     FT dL_lcl_dt = -dL_rai_dt;
     FT dN_lcl_dt = dL_lcl_dt / x_lcl;
     bool cond = (q_lcl < eM) || (q_rai < eM) || (N_lcl < eN);
@@ -198,7 +198,7 @@ inline FT rain_self_collection(const typename PT<FT>::sb_pdf_r& pdf, const typen
     FT L_rai = rho * safe_q;
     FT Ar, Br;
     pdf_rain_parameters_mass<FT>(pdf, safe_q, rho, safe_N, Ar, Br);
-    FT v = -self.krr * N_rai * L_rai * std::sqrt(pdf.rho0 / rho) * std::pow(1 + self.kappa_rr / Br, self.d);
+    FT v = -self.krr * N_rai * L_rai * sqrt_(pdf.rho0 / rho) * pow_(1 + self.kappa_rr / Br, self.d);
     bool cond = (q_rai < eM) || (N_rai < eN);
     return cond ? FT(0) : v;
 }
@@ -211,10 +211,10 @@ inline FT rain_breakup(const typename PT<FT>::sb_pdf_r& pdf, const typename PT<F
     FT safe_q = jmax(q_rai, eM);
     FT safe_N = jmax(N_rai, eN);
     RainPDF<FT> r = pdf_rain_parameters<FT>(pdf, safe_q, rho, safe_N);
-    FT Dr = std::cbrt(r.xr_mean * 6 / (pi<FT>() * pdf.rho_w));
+    FT Dr = cbrt_(r.xr_mean * 6 / (pi<FT>() * pdf.rho_w));
     FT dD = Dr - brek.Deq;
     FT phi = (Dr < brek.Dr_th) ? FT(-1)
-                               : ((Dr <= brek.Deq) ? brek.kbr * dD : std::exp(brek.kappa_br * dD) - 1);
+                               : ((Dr <= brek.Deq) ? brek.kbr * dD : exp_(brek.kappa_br * dD) - 1);
     FT v = -(phi + 1) * dN_rai_dt_sc;  // Eq. (13)
     bool cond = (q_rai < eM) || (N_rai < eN);
     return cond ? FT(0) : v;
@@ -222,8 +222,8 @@ inline FT rain_breakup(const typename PT<FT>::sb_pdf_r& pdf, const typename PT<F
 
 // CM2.Γ_incl                                                      CM2:746-753
 template <class FT> inline FT Gamma_incl(FT a, FT x) {
-    return std::exp(-x) / ((FT(0.33) - FT(0.7) * a) * std::pow(x, FT(0.08) - FT(0.93) * a) +
-                           (FT(1.34) - FT(0.1) * a) * std::pow(x, FT(0.8) - a));
+    return exp_(-x) / ((FT(0.33) - FT(0.7) * a) * pow_(x, FT(0.08) - FT(0.93) * a) +
+                           (FT(1.34) - FT(0.1) * a) * pow_(x, FT(0.8) - a));
 }
 
 // CM2.rain_evaporation                                             CM2:780-828
@@ -241,15 +241,15 @@ inline void rain_evaporation(const typename PT<FT>::sb2006& sb, const typename P
     FT safe_N = jmax(N_rai, eN);
     RainPDF<FT> r = pdf_rain_parameters<FT>(sb.pdf_r, safe_q, rho, safe_N);
     FT xr_mean = r.xr_mean;
-    FT Dr = std::cbrt(6 * xr_mean / (pi<FT>() * rho_w));
-    FT t_star = std::cbrt(FT(6) * x_star / xr_mean);
+    FT Dr = cbrt_(6 * xr_mean / (pi<FT>() * rho_w));
+    FT t_star = cbrt_(FT(6) * x_star / xr_mean);
     FT a_vent_0 = evap.a_vent_0_coeff * Gamma_incl<FT>(FT(-1), t_star);
     FT b_vent_0 = evap.b_vent_0_coeff * Gamma_incl<FT>(evap.beta_vent_0, t_star);
     FT a_vent_1 = evap.a_vent_1;
     FT b_vent_1 = evap.b_vent_1;
-    FT N_Re = evap.alpha * std::pow(xr_mean, evap.beta) * std::sqrt(evap.rho0 / rho) * Dr / aps.nu_air;
-    FT cbrt_Sc = std::cbrt(aps.nu_air / jmax(aps.D_vapor, eps_numerics<FT>()));
-    FT sqrt_N_Re = std::sqrt(N_Re);
+    FT N_Re = evap.alpha * pow_(xr_mean, evap.beta) * sqrt_(evap.rho0 / rho) * Dr / aps.nu_air;
+    FT cbrt_Sc = cbrt_(aps.nu_air / jmax(aps.D_vapor, eps_numerics<FT>()));
+    FT sqrt_N_Re = sqrt_(N_Re);
     FT Fv0 = a_vent_0 + b_vent_0 * cbrt_Sc * sqrt_N_Re;
     FT Fv1 = a_vent_1 + b_vent_1 * cbrt_Sc * sqrt_N_Re;
     FT dn = jmin(FT(0), 2 * pi<FT>() * G * S * N_rai * Dr * Fv0 / xr_mean);
@@ -275,7 +275,7 @@ inline void cloud_terminal_velocity(const typename PT<FT>::sb_pdf_c& pdf_c,
     FT Ac, Bc;
     pdf_cloud_parameters_mass<FT>(pdf_c, safe_q, rho, safe_N, Ac, Bc);
     FT t = FT(6) / vel.rho_w / pi<FT>();
-    FT pref = FT(1.0 / 18) * std::cbrt(t * t) * (vel.rho_w / rho - 1) * vel.grav / vel.nu_air;
+    FT pref = FT(1.0 / 18) * cbrt_(t * t) * (vel.rho_w / rho - 1) * vel.grav / vel.nu_air;
     FT v0 = pref * generalized_gamma_Mn<FT>(pdf_c.nu_c, pdf_c.mu_c, Bc, safe_N, FT(2.0 / 3)) / safe_N;
     FT v1 = pref * generalized_gamma_Mn<FT>(pdf_c.nu_c, pdf_c.mu_c, Bc, safe_N, FT(5.0 / 3)) / rho / safe_q;
     bool cond = (N_liq < eN) || (q_liq < eM);
@@ -298,15 +298,15 @@ inline void rain_terminal_velocity_sb(const typename PT<FT>::sb_pdf_r& pdf_r,
         pa0 = pb0 = pa1 = pb1 = FT(1);
     } else {
         FT lam = 1 / Dr_mean;
-        FT rc = -1 / (2 * vel.cR) * std::log(vel.aR / vel.bR);
-        auto G1 = [](FT t) { return std::exp(-t); };
-        auto G4 = [](FT t) { return (t * t * t + 3 * (t * t) + 6 * t + 6) * std::exp(-t); };
+        FT rc = -1 / (2 * vel.cR) * log_(vel.aR / vel.bR);
+        auto G1 = [](FT t) { return exp_(-t); };
+        auto G4 = [](FT t) { return (t * t * t + 3 * (t * t) + 6 * t + 6) * exp_(-t); };
         pa0 = G1(2 * rc * lam);
         pb0 = G1(2 * rc * (lam + vel.cR));
         pa1 = G4(2 * rc * lam) / 6;
         pb1 = G4(2 * rc * (lam + vel.cR)) / 6;
     }
-    FT s = std::sqrt(vel.rho0 / rho);
+    FT s = sqrt_(vel.rho0 / rho);
     FT d1 = 1 + vel.cR * Dr_mean;
     FT d2 = d1 * d1;
     FT v0 = jmax(FT(0), s * (vel.aR * pa0 - vel.bR * pb0 / d1));

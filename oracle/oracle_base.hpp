@@ -22,8 +22,26 @@
 #include <algorithm>
 
 #include "../include/cumicro.h"
+#include "oracle_tracked.hpp"
 
 namespace orc {
+
+// ---- elementary functions: libm for float/double/long double, error-propagating
+// overloads for Tr (oracle_tracked.hpp).  All oracle code calls these unqualified.
+#define ORC_FN1(name) \
+    inline float name##_(float x) { return std::name(x); } \
+    inline double name##_(double x) { return std::name(x); }
+ORC_FN1(exp) ORC_FN1(log) ORC_FN1(log2) ORC_FN1(log10) ORC_FN1(log1p) ORC_FN1(expm1) ORC_FN1(sqrt) ORC_FN1(cbrt)
+ORC_FN1(tgamma) ORC_FN1(lgamma) ORC_FN1(erf) ORC_FN1(erfc) ORC_FN1(tanh) ORC_FN1(atanh) ORC_FN1(fabs)
+#undef ORC_FN1
+inline float pow_(float x, float y) { return std::pow(x, y); }
+inline double pow_(double x, double y) { return std::pow(x, y); }
+inline bool isfinite_(double x) { return std::isfinite(x); }
+inline bool isfinite_(float x) { return std::isfinite(x); }
+inline bool isinf_(double x) { return std::isinf(x); }
+inline bool isinf_(float x) { return std::isinf(x); }
+inline bool isnan_(double x) { return std::isnan(x); }
+inline bool isnan_(float x) { return std::isnan(x); }
 
 template <class FT> struct PT;  // parameter-type selector
 template <> struct PT<double> {
@@ -44,6 +62,7 @@ template <> struct PT<double> {
     using vel_chen_large_ice = cumicro_vel_chen_large_ice_f64;
     using params_2m_warm = cumicro_params_2m_warm_f64;
 };
+template <> struct PT<Tr> : PT<double> {};  // parameters stay plain Float64
 template <> struct PT<float> {
     using thermo = cumicro_thermo_f32;
     using air = cumicro_air_f32;
@@ -69,13 +88,19 @@ template <class FT> inline FT jmin(FT a, FT b) { return (b < a) ? b : a; }
 // Base.clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x))
 template <class FT> inline FT jclamp(FT x, FT lo, FT hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }
 template <class FT> inline FT ifelse(bool c, FT a, FT b) { return c ? a : b; }
+inline Tr jmax(Tr a, Tr b) { return (a < b) ? b : a; }
+inline Tr jmin(Tr a, Tr b) { return (b < a) ? b : a; }
+inline Tr jclamp(Tr x, Tr lo, Tr hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }
+inline Tr ifelse(bool c, Tr a, Tr b) { return c ? a : b; }
 template <class FT> inline FT eps() { return std::numeric_limits<FT>::epsilon(); }
 template <class FT> inline FT inf() { return std::numeric_limits<FT>::infinity(); }
+template <> inline Tr eps<Tr>() { return Tr(std::numeric_limits<double>::epsilon()); }
+template <> inline Tr inf<Tr>() { return Tr(std::numeric_limits<double>::infinity()); }
 template <class FT> inline FT pi() { return FT(3.141592653589793238462643383279502884L); }
 
 // ---- Utilities.jl -----------------------------------------------------------
 // UT.ϵ_numerics(FT) = cbrt(floatmin(FT))                         UT:318
-template <class FT> inline FT eps_numerics() { return std::cbrt(std::numeric_limits<FT>::min()); }
+template <class FT> inline FT eps_numerics() { return cbrt_(std::numeric_limits<FT>::min()); }
 // UT.ϵ_numerics_2M_M / _2M_N / _P3_B = eps(FT)                   UT:325,332,340
 template <class FT> inline FT eps_2M() { return eps<FT>(); }
 // UT.clamp_to_nonneg                                             UT:296
@@ -83,25 +108,22 @@ template <class FT> inline FT clamp_to_nonneg(FT x) { return jmax(FT(0), x); }
 
 // ---- LogExpFunctions.jl (external; restated from its definition) -----------
 // log1pexp(x): Maechler (2012) branches with the package's thresholds.
-inline double log1pexp(double x) {
-    if (x < -36.7368005696771) return std::exp(x);
-    if (x < 18.021826694558577) return std::log1p(std::exp(x));
-    if (x < 33.23111882352963) return x + std::exp(-x);
-    return x;
-}
-inline float log1pexp(float x) {
-    if (x < -15.942385f) return std::exp(x);
-    if (x < 9.011913f) return std::log1p(std::exp(x));
-    if (x < 16.635532f) return x + std::exp(-x);
+template <class FT> struct Log1pExpCut { static constexpr double a = -36.7368005696771, b = 18.021826694558577, c = 33.23111882352963; };
+template <> struct Log1pExpCut<float> { static constexpr double a = -15.942385, b = 9.011913, c = 16.635532; };
+template <class FT> inline FT log1pexp(FT x) {
+    using C = Log1pExpCut<FT>;
+    if (x < FT(C::a)) return exp_(x);
+    if (x < FT(C::b)) return log1p_(exp_(x));
+    if (x < FT(C::c)) return x + exp_(-x);
     return x;
 }
 // log1mexp(x) = x < log(1/2) ? log1p(-exp(x)) : log(-expm1(x))
 template <class FT> inline FT log1mexp(FT x) {
     const FT loghalf = FT(-0.6931471805599453094172321214581765680755L);
-    return (x < loghalf) ? std::log1p(-std::exp(x)) : std::log(-std::expm1(x));
+    return (x < loghalf) ? log1p_(-exp_(x)) : log_(-expm1_(x));
 }
 // cloglog(x) = log(-log1p(-x))
-template <class FT> inline FT cloglog(FT x) { return std::log(-std::log1p(-x)); }
+template <class FT> inline FT cloglog(FT x) { return log_(-log1p_(-x)); }
 
 // ---- Thermodynamics.jl (external) --------------------------
 template <class FT> struct Thermo {
@@ -121,8 +143,8 @@ template <class FT> struct Thermo {
         return p.R_d * (1 + (Rv_over_Rd - 1) * qt - Rv_over_Rd * (ql + qi));
     }
     FT p_sat_calc(FT T, FT LH_0, FT dcp) const {
-        return p.press_triple * std::pow(T / p.T_triple, dcp / p.R_v) *
-               std::exp((LH_0 - dcp * p.T_0) / p.R_v * (1 / p.T_triple - 1 / T));
+        return p.press_triple * pow_(T / p.T_triple, dcp / p.R_v) *
+               exp_((LH_0 - dcp * p.T_0) / p.R_v * (1 / p.T_triple - 1 / T));
     }
     FT p_sat_liq(FT T) const { return p_sat_calc(T, p.LH_v0, p.cp_v - p.cp_l); }
     FT p_sat_ice(FT T) const { return p_sat_calc(T, p.LH_s0, p.cp_v - p.cp_i); }
@@ -170,7 +192,7 @@ template <class FT> inline FT logistic_function(FT x, FT x_0, FT k) {
     FT x_safe = jmax(x, e);
     FT x_0_safe = jmax(x_0, e);
     FT z = k * (x_safe / x_0_safe - x_0_safe / x_safe);
-    FT result = std::exp(-log1pexp(-z));
+    FT result = exp_(-log1pexp(-z));
     return (x < e) ? FT(0) : ((x_0 < e) ? FT(1) : result);
 }
 // CO.logistic_function_integral                                   CO:157-173
@@ -196,8 +218,8 @@ inline double fac(int n) {
 template <class FT> inline FT chen2022_exponential_pdf(FT a, FT b, FT c, FT lam_inv, int k) {
     FT delta = FT(k + 1);
     FT gamma_delta = FT(fac(k));
-    return a * std::exp(-delta * std::log(lam_inv) - (b + delta) * std::log(1 / lam_inv + c)) *
-           std::tgamma(b + delta) / gamma_delta;
+    return a * exp_(-delta * log_(lam_inv) - (b + delta) * log_(1 / lam_inv + c)) *
+           tgamma_(b + delta) / gamma_delta;
 }
 
 // CO.Chen2022_vel_coeffs(::Chen2022VelTypeRain, ρₐ)                CO:290-300
@@ -205,18 +227,18 @@ template <class FT>
 inline void chen2022_vel_coeffs_rain(const typename PT<FT>::vel_chen_rain& v, FT rho,
                                      FT aiu[3], FT bi[3], FT ciu[3]) {
     rho = jmax(rho, FT(0));
-    FT q = std::exp(v.rho0 * rho);
-    FT ai[3] = {v.a[0] * q, v.a[1] * q, v.a[2] * q * std::pow(rho, v.a3_pow)};
+    FT q = exp_(v.rho0 * rho);
+    FT ai[3] = {v.a[0] * q, v.a[1] * q, v.a[2] * q * pow_(rho, v.a3_pow)};
     for (int i = 0; i < 3; ++i) {
         bi[i] = v.b[i] - v.b_rho * rho;
-        aiu[i] = ai[i] * std::pow(FT(1000), bi[i]);
+        aiu[i] = ai[i] * pow_(FT(1000), bi[i]);
         ciu[i] = v.c[i] * 1000;
     }
 }
 
 // DT.generalized_gamma_Mⁿ                                          DT:109-112
 template <class FT> inline FT generalized_gamma_Mn(FT nu, FT mu, FT B, FT N, FT n) {
-    return N * std::pow(B, -n / mu) * std::tgamma((nu + 1 + n) / mu) / std::tgamma((nu + 1) / mu);
+    return N * pow_(B, -n / mu) * tgamma_((nu + 1 + n) / mu) / tgamma_((nu + 1) / mu);
 }
 
 }  // namespace orc

@@ -1,0 +1,12 @@
+// Host-side harness of cm_math.cuh for tests/test_cm_math.py: evaluates the HOST
+// instantiation of the device math (same arithmetic, MUFU seeds emulated).
+#include "../../cloudmicrophysics.jl_b200/csrc/cm_math.cuh"
+
+extern "C" {
+void cmt_exp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::exp_(x[i]); }
+void cmt_exp_full(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::exp_full_(x[i]); }
+void cmt_log(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::logp_(x[i]); }
+void cmt_cbrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::cbrtp_(x[i]); }
+void cmt_rcp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::rcp_(x[i]); }
+void cmt_pow(const double* x, const double* p, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::powp_(x[i], p[i]); }
+}

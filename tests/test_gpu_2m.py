@@ -33,48 +33,33 @@ def _gpu_bmt(built, mp, tps, cols, **kw):
     return BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[cols[k] for k in KEYS], **kw)
 
 
-def _oracle_with_sens(orc, block, st, leaves=False):
-    from cumicro.testing import perturb
+def _oracle_with_bound(orc, block, st, leaves=False):
     ref = orc.bmt2m_warm(block, *[st[k] for k in KEYS], leaves=leaves)
-    sens = None
-    for seed in (7, 8, 9):
-        pr = orc.bmt2m_warm(block, *[perturb(st, seed=seed)[k] for k in KEYS], leaves=leaves)
-        d = {k: np.abs(pr[k] - ref[k]) for k in OUTS}
-        if leaves:
-            d["leaves"] = [np.abs(a - b) for a, b in zip(pr["leaves"], ref["leaves"])]
-        if sens is None:
-            sens = d
-        else:
-            for k in OUTS:
-                sens[k] = np.maximum(sens[k], d[k])
-            if leaves:
-                sens["leaves"] = [np.maximum(a, b) for a, b in zip(sens["leaves"], d["leaves"])]
-    return ref, sens
+    bound = orc.bmt2m_warm_bound(block, *[st[k] for k in KEYS], leaves=leaves)
+    return ref, bound
 
 
 @pytest.mark.parametrize("limited", [True, False])
 @pytest.mark.parametrize("number", ["loguniform", "const"])
 def test_bmt2m_warm_f64_parity(built, orc, cuda, limited, number):
-    from cumicro.testing import synthetic_states_2m, compare_report
+    from cumicro.testing import synthetic_states_2m, assert_parity
     CMP = built.CMP
     n = 1 << 18
     st = synthetic_states_2m(n, seed=1234, number=number)
     mp = CMP.Microphysics2MParams(np.float64, is_limited=limited)
     tps = CMP.ThermodynamicsParameters(np.float64)
     out = _gpu_bmt(built, mp, tps, _to_dev(st, cuda))
-    ref, sens = _oracle_with_sens(orc, CMP.pack_2m_warm(mp, tps), st)
+    ref, bound = _oracle_with_bound(orc, CMP.pack_2m_warm(mp, tps), st)
     for k in OUTS:
-        rep = compare_report(out[k].cpu().numpy(), ref[k], sens=sens[k])
-        assert rep["n_bad"] == 0 and rep["max_rel"] <= 1e-12, (k, rep)
-        assert rep["n_zero_mismatch"] == 0 and rep["n_nonfinite_mismatch"] == 0, (k, rep)
-        assert rep["frac_forward_ok"] > 0.99, (k, rep)
+        rep = assert_parity(k, out[k].cpu().numpy(), ref[k], bound=bound[k])
+        assert rep["max_rel"] <= 1e-12 and rep["frac_forward_ok"] > 0.99, (k, rep)
     for k in ("dq_ice_dt", "dq_rim_dt", "db_rim_dt", "dn_lcl_activation_dt"):
         assert out[k].shape[0] == n and float(out[k].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("limited", [True, False])
 def test_sb2006_leaves_f64_parity_and_regimes(built, orc, cuda, limited):
-    from cumicro.testing import synthetic_states_2m, compare_report
+    from cumicro.testing import synthetic_states_2m, assert_parity
     CMP, abi = built.CMP, built._abi
     n = 1 << 17
     st = synthetic_states_2m(n, seed=99)
@@ -82,13 +67,11 @@ def test_sb2006_leaves_f64_parity_and_regimes(built, orc, cuda, limited):
     tps = CMP.ThermodynamicsParameters(np.float64)
     cols = _to_dev(st, cuda)
     got = built.CM2.sb2006_process_rates(mp, tps, *[cols[k] for k in KEYS])
-    ref, sens = _oracle_with_sens(orc, CMP.pack_2m_warm(mp, tps), st, leaves=True)
+    ref, bound = _oracle_with_bound(orc, CMP.pack_2m_warm(mp, tps), st, leaves=True)
     for i, name in enumerate(abi.SB2006_LEAVES):
-        g = got[name].cpu().numpy()
-        rep = compare_report(g, ref["leaves"][i], sens=sens["leaves"][i])
-        assert rep["n_bad"] == 0 and rep["max_rel"] <= 1e-12, (name, rep)
-        # bit-exact regime selection: gated-off (exact zero) points coincide
-        assert rep["n_zero_mismatch"] == 0, (name, rep)
+        # (assert_parity also checks bit-exact regime selection: gated-off exact zeros coincide)
+        rep = assert_parity(name, got[name].cpu().numpy(), ref["leaves"][i], bound=bound["leaves"][i])
+        assert rep["max_rel"] <= 1e-12, (name, rep)
     # breakup regimes (Dr < Dr_th | Dr <= Deq | else) all present in the limited run
     if limited:
         br = ref["leaves"][abi.SB2006_LEAVES.index("rai_breakup")]
@@ -128,29 +111,29 @@ def test_golden_values_through_the_gpu(built, cuda):
 @pytest.mark.parametrize("limited", [True, False])
 def test_terminal_velocities_f64_parity(built, orc, cuda, limited):
     import torch
-    from cumicro.testing import synthetic_states_2m, compare_report
+    from cumicro.testing import synthetic_states_2m, assert_parity
     CMP = built.CMP
     st = synthetic_states_2m(1 << 16, seed=11)
     cols = _to_dev(st, cuda)
     N_rai, N_lcl = st["n_rai"] * st["rho"], st["n_lcl"] * st["rho"]
     dN_rai, dN_lcl = cols["n_rai"] * cols["rho"], cols["n_lcl"] * cols["rho"]
     sb = CMP.SB2006(np.float64, is_limited=limited)
+    velsb, velch, velst = CMP.SB2006VelType(np.float64), CMP.Chen2022VelTypeRain(np.float64), CMP.StokesRegimeVelType(np.float64)
     cases = [
-        ("rain_sb", built.CM2.rain_terminal_velocity(sb, CMP.SB2006VelType(np.float64), cols["q_rai"], cols["rho"], dN_rai),
-         orc.termvel_2m_rain_sb(sb.pdf_r, CMP.SB2006VelType(np.float64), st["q_rai"], st["rho"], N_rai)),
-        ("rain_chen", built.CM2.rain_terminal_velocity(sb, CMP.Chen2022VelTypeRain(np.float64), cols["q_rai"], cols["rho"], dN_rai),
-         orc.termvel_2m_rain_chen(sb.pdf_r, CMP.Chen2022VelTypeRain(np.float64), st["q_rai"], st["rho"], N_rai)),
-        ("cloud", built.CM2.cloud_terminal_velocity(sb.pdf_c, CMP.StokesRegimeVelType(np.float64), cols["q_lcl"], cols["rho"], dN_lcl),
-         orc.termvel_2m_cloud(sb.pdf_c, CMP.StokesRegimeVelType(np.float64), st["q_lcl"], st["rho"], N_lcl)),
+        ("rain_sb", built.CM2.rain_terminal_velocity(sb, velsb, cols["q_rai"], cols["rho"], dN_rai),
+         orc.termvel_2m_rain_sb(sb.pdf_r, velsb, st["q_rai"], st["rho"], N_rai),
+         orc.termvel_bound("termvel_2m_rain_sb", sb.pdf_r, velsb, st["q_rai"], st["rho"], N_rai)),
+        ("rain_chen", built.CM2.rain_terminal_velocity(sb, velch, cols["q_rai"], cols["rho"], dN_rai),
+         orc.termvel_2m_rain_chen(sb.pdf_r, velch, st["q_rai"], st["rho"], N_rai),
+         orc.termvel_bound("termvel_2m_rain_chen", sb.pdf_r, velch, st["q_rai"], st["rho"], N_rai)),
+        ("cloud", built.CM2.cloud_terminal_velocity(sb.pdf_c, velst, cols["q_lcl"], cols["rho"], dN_lcl),
+         orc.termvel_2m_cloud(sb.pdf_c, velst, st["q_lcl"], st["rho"], N_lcl),
+         orc.termvel_bound("termvel_2m_cloud", sb.pdf_c, velst, st["q_lcl"], st["rho"], N_lcl)),
     ]
-    for name, got, ref in cases:
+    for name, got, ref, bound in cases:
         for j in (0, 1):
-            g, r = got[j].cpu().numpy(), ref[j]
-            # v = a - b/(...) differences of O(1) terms clipped at 0: measure against the velocity scale
-            rep = compare_report(g, r)
-            scale_err = np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-3))
-            assert scale_err <= 1e-12, (name, j, rep, scale_err)
-            assert rep["n_nonfinite_mismatch"] == 0
+            rep = assert_parity(f"{name}.vt{j}", got[j].cpu().numpy(), ref[j], bound=bound[j])
+            assert rep["max_rel"] <= 1e-12, (name, j, rep)
 
 
 def test_chen_rain_golden_gpu(built, cuda):
