@@ -43,50 +43,69 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region (NVML, in-process
+    thread, ~2 ms period; falls back to nvidia-smi -lms when NVML is unavailable)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop, self.t, self.max = index, [], False, None, None
+
+    def _loop_nvml(self):
+        import pynvml as nv
+        h = self.h
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box; map through CUDA_VISIBLE_DEVICES when set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    idx = self.index
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.nv = nv
+            self.t = threading.Thread(target=self._loop_nvml, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.t = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.t:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {}
+        for nm, attr in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                         ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                         ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                         ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            if hasattr(nv, attr):
+                names[nm] = getattr(nv, attr)
+        reasons = set()
+        for _, rs in self.rows:
+            for nm, bit in names.items():
+                if rs & bit:
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(self.max),
+                "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
 def reference_arm(args):
@@ -127,7 +146,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cumicro", choices=["cumicro", "reference"])
     ap.add_argument("--points", type=int, default=1 << 24, help="grid points per GPU")
@@ -246,7 +265,7 @@ def main():
                    "l2": "inputs (7 x 134 MB columns) larger than the 126 MB L2; no flush needed",
                    "psd": "SB2006 limited rain PSD, log-uniform number concentrations"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel<double,7,4,Warm2MFused>",
+                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel<double,7,4,Warm2MFused,scalar,128x8>",
                      "kernel_ms": kernel_ms, "bytes_per_point": BYTES_PER_POINT},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 7 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n,
                 "steps": args.e2e_steps, "api": "cumicro_bmt2m_warm_host_f64 (pinned host buffers, chunked H2D/kernel/D2H)"},

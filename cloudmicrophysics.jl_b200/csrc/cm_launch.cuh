@@ -6,9 +6,11 @@
 // __grid_constant__ kernel argument) with
 //     __device__ void operator()(const FT (&x)[NIN], FT (&y)[NOUT]) const;
 // and this header supplies the data movement:
-//   * one thread owns VEC = 16 B / sizeof(FT) consecutive points: every input column
-//     is read exactly once with one 128-bit ld.global.nc, every live output column is
-//     written exactly once with one 128-bit st.global.cs (streaming, never re-read);
+//   * vector variant: one thread owns VEC = 16 B / sizeof(FT) consecutive points, every
+//     input column is read exactly once with one 128-bit ld.global.nc and every live output
+//     column written exactly once with one 128-bit st.global.cs (streaming, never re-read);
+//     scalar variant: one point per thread, 64/32-bit accesses, a warp covers one contiguous
+//     256/128-byte run per column (used when registers, not bytes, are the scarce resource);
 //   * all loads of an item are issued before any arithmetic, so 7-12 independent
 //     128-bit requests per thread are in flight while the FP64 pipe works on the
 //     previous item of other warps;
@@ -20,6 +22,7 @@
 // NULL output pointers are skipped (optional diagnostics columns).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "cm_types.cuh"
 
@@ -36,7 +39,7 @@ template <class FT, int NIN, int NOUT, class F, bool VECTOR, int BLOCK, int MINB
 __global__ void __launch_bounds__(BLOCK, MINB)
 pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int64_t first) {
     constexpr int VEC = VECTOR ? vec<FT>::N : 1;
-    math_tables_init();  // exp/log tables -> shared memory (cm_math.cuh)
+    math_tables_init<BLOCK>();  // exp/log tables -> shared memory (cm_math.cuh)
     const int64_t stride = (int64_t)gridDim.x * BLOCK;
     const int64_t n_items = VECTOR ? (a.n / VEC) : (a.n - first);
     for (int64_t it = (int64_t)blockIdx.x * BLOCK + threadIdx.x; it < n_items; it += stride) {
@@ -74,18 +77,24 @@ pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int6
 }
 
 // Enqueue F over n points on `stream`.  BLOCK x MINB fixes the register budget
-// (65536 / (BLOCK*MINB) per thread); WAVES = resident-block multiples of the grid.
-template <class FT, int NIN, int NOUT, class F, int BLOCK = 256, int MINB = 1>
+// (65536 / (BLOCK*MINB) per thread).  USE_VEC = false launches the one-point-per-thread
+// variant even for aligned columns: for the FP64-pipe-bound families (2M, 1M) the
+// measured optimum is 32 resident warps/SM at 64 registers with 64-bit loads (a warp
+// still reads one contiguous 256-byte run per column), tools/tune_2m.py.
+template <class FT, int NIN, int NOUT, class F, int BLOCK = 256, int MINB = 1, bool USE_VEC = true>
 int launch_pointwise(const F& f, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[NOUT], cudaStream_t stream,
                      const char* what) {
     if (n == 0) return CUMICRO_OK;
     PointwiseArgs<FT, NIN, NOUT, F> a;
     a.f = f;
     a.n = n;
-    bool vec_ok = true;
+    bool vec_ok = USE_VEC;
     for (int c = 0; c < NIN; ++c) { a.in[c] = in[c]; vec_ok = vec_ok && cmh::aligned16(in[c]); }
     for (int c = 0; c < NOUT; ++c) { a.out[c] = out[c]; vec_ok = vec_ok && (out[c] == nullptr || cmh::aligned16(out[c])); }
     constexpr int VEC = vec<FT>::N;
+#ifdef CUMICRO_TUNING
+    { static const char* fs = getenv("CUMICRO_FORCE_SCALAR"); if (fs && fs[0] == '1') vec_ok = false; }
+#endif
     const int max_blocks = cmh::num_sms() * MINB * 4;  // 4 equal waves of the resident grid
     int64_t first = 0;
     if (vec_ok && n >= VEC) {

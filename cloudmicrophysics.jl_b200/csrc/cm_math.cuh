@@ -7,11 +7,11 @@
 // sites do not need; the versions below are written for the argument ranges the
 // physics produces and stay far inside the 1e-12 relative parity budget:
 //
-//   exp_   : table-driven, 2^(j/64) from shared memory + degree-5 polynomial      ~10 FP64
+//   exp_   : table-driven, 2^(j/256) from shared memory + degree-4 polynomial      10 FP64
 //   logp_  : table-driven (128 x (1/c, -log 1/c)) + degree-7 log1p polynomial    ~13 FP64
 //   powp_  : exp_(y * logp_(x)); relative error ~ |y ln x| * 3e-16               ~24 FP64
 //   cbrtp_ : FP32 MUFU (lg2/ex2) seed, one cubic step on x^(-1/3), one correction ~12 FP64
-//   rcp_   : MUFU.RCP64H seed + cubic + Newton step, <= 1 ulp                      ~5 FP64
+//   rcp_   : MUFU.RCP64H seed + two Newton steps, <= 1 ulp                         4 FP64
 // Suffix `p` = positive, normal, finite argument required (garbage, not NaN, outside;
 // call sites select the result away in those cases, exactly where the reference's
 // ifelse does).  + - * / sqrt are IEEE operations, identical to the CPU reference; the
@@ -86,19 +86,25 @@ template <> struct num<float> {
 // Global copies (host + device) and the per-block shared-memory copy the device
 // functions read.  A kernel that uses exp_/logp_/powp_ must call math_tables_init()
 // (all threads of the block) before its first use; cm_launch.cuh does.
-static const unsigned long long cm_exp_tab_host[64] = CM_EXP_TABLE_INIT;
+static const unsigned long long cm_exp_tab_host[256] = CM_EXP_TABLE_INIT;
 static const unsigned long long cm_log_tab_host[256] = CM_LOG_TABLE_INIT;
-static __device__ const unsigned long long cm_exp_tab_dev[64] = CM_EXP_TABLE_INIT;
+static __device__ const unsigned long long cm_exp_tab_dev[256] = CM_EXP_TABLE_INIT;
 static __device__ const unsigned long long cm_log_tab_dev[256] = CM_LOG_TABLE_INIT;
 #ifdef __CUDACC__
-static __shared__ unsigned long long cm_sh_exp[64];
+static __shared__ unsigned long long cm_sh_exp[256];
 static __shared__ ulonglong2 cm_sh_log[128];
+// the few coefficients that need all 53 bits (everything else in exp_/logp_/cbrtp_ is an
+// immediate operand: constants whose low 32 bits are zero cost no instruction on sm_100)
+static __constant__ double cm_kc[4] = {3.3333333333333331e-01, 0.2, CM_LOG_LN2_LO, 0.0};
 #endif
+#define CM_LOG_C3_HOST 3.3333333333333331e-01
 
-CM_DEV void math_tables_init() {
+template <int BLOCK> CM_DEV void math_tables_init() {
 #ifdef __CUDA_ARCH__
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) cm_sh_exp[i] = cm_exp_tab_dev[i];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x)
+#pragma unroll
+    for (int i = threadIdx.x; i < 256; i += BLOCK) cm_sh_exp[i] = cm_exp_tab_dev[i];
+#pragma unroll
+    for (int i = threadIdx.x; i < 128; i += BLOCK)
         cm_sh_log[i] = make_ulonglong2(cm_log_tab_dev[2 * i], cm_log_tab_dev[2 * i + 1]);
     __syncthreads();
 #endif
@@ -143,32 +149,33 @@ CM_HD double rcp_(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H: ~20 good bits
 #else
-    double r = mk64(hi32(1.0 / x) & 0xfffffc00, 0);  // host emulation of the 20-bit seed
+    double r = mk64(hi32(1.0 / x), 0);  // host emulation of the 20-bit seed
 #endif
     double e = fma(-x, r, 1.0);
-    r = fma(r, fma(e, e, e), r);  // cubic: 60 bits
+    r = fma(r, e, r);  // 40 bits
     e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    return fma(r, e, r);  // 80 bits -> rounding only
 }
 CM_HD float rcp_(float x) { return 1.0f / x; }
 
 // ---- exp: |x| <= 708 (callers' arguments are bounded; see exp_full_ otherwise) ---------------
-// x = (64 e + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^e * T[j] * (1 + expm1(r)).
+// x = (256 e + j) ln2/256 + r, |r| <= ln2/512;  exp(x) = 2^e * T[j] * (1 + expm1(r)).
+// All constants are immediates (21-bit pieces): 10 FP64 instructions, 1 LDS, ~6 integer.
 CM_HD double exp_(double x) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
-    const double t = fma(x, 9.23324826168936568e+01, magic);  // 64 / ln 2
+    const double t = fma(x, CM_EXP_INV_L, magic);
     const int ki = lo32(t);
     const double kf = t - magic;
-    double r = fma(kf, -1.08304246962491451e-02, x);  // -ln2/64: fl(ln2/64)
-    r = fma(kf, -3.62351064663484306e-19, r);         // -(ln2/64 - fl(ln2/64))
-    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);  // 1/120, 1/24
-    p = fma(p, r, 1.6666666666666666e-01);
+    double r = fma(kf, -CM_EXP_L1, x);  // exact
+    r = fma(kf, -CM_EXP_L2, r);
+    r = fma(kf, -CM_EXP_L3, r);
+    double p = fma(r, CM_EXP_C4, CM_EXP_C3);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r;  // expm1(r)
-    const double T = exp_tab(ki & 63);
+    const double T = exp_tab(ki & 255);
     const double y = fma(T, p, T);
-    return mk64(hi32(y) + ((ki >> 6) << 20), lo32(y));
+    return mk64(hi32(y) + ((ki >> 8) << 20), lo32(y));
 }
 // exp with the IEEE limits: 0 below the normal range, +Inf above, NaN propagated.
 CM_HD double exp_full_(double x) {
@@ -181,6 +188,11 @@ CM_HD float exp_full_(float x) { return expf(x); }
 // ---- log: positive, normal, finite x ------------------------------------------------------
 // x = 2^k z, z in [0.6875, 1.375); z = c (1 + r) with 1/c, -log(1/c) tabulated (128 cells).
 CM_HD double logp_(double x) {
+#ifdef __CUDA_ARCH__
+    const double c3 = cm_kc[0], c5 = cm_kc[1], ln2_lo = cm_kc[2];
+#else
+    const double c3 = CM_LOG_C3_HOST, c5 = 0.2, ln2_lo = CM_LOG_LN2_LO;
+#endif
     const int hx = hi32(x);
     const int tmp = hx - 0x3fe60000;
     const int i = (tmp >> 13) & 127;
@@ -190,14 +202,14 @@ CM_HD double logp_(double x) {
     log_tab(i, invc, logc);
     const double r = fma(z, invc, -1.0);
     const double kd = (double)k;
-    const double w = fma(kd, 6.93147180559945286e-01, logc);  // fl(ln2)
-    double q = fma(r, 1.4285714285714285e-01, -1.6666666666666666e-01);  // 1/7, -1/6
-    q = fma(q, r, 0.2);
+    const double w = fma(kd, CM_LOG_LN2_HI, logc);  // k * LN2_HI is exact (21-bit constant)
+    double q = fma(r, CM_LOG_C7, CM_LOG_C6);
+    q = fma(q, r, c5);
     q = fma(q, r, -0.25);
-    q = fma(q, r, 3.3333333333333331e-01);
+    q = fma(q, r, c3);
     q = fma(q, r, -0.5);
     const double r2 = r * r;
-    const double lo = fma(r2, q, kd * 2.31904681384629956e-17);  // + k (ln2 - fl(ln2))
+    const double lo = fma(r2, q, kd * ln2_lo);
     return (w + r) + lo;
 }
 CM_HD float logp_(float x) { return logf(x); }
@@ -229,13 +241,13 @@ CM_HD double cbrtp_(double x) {
     // one cubically convergent step on r -> a^(-1/3): e = 1 - a r^3, r *= 1 + e/3 + 2 e^2/9
     double r2 = r * r;
     const double err = fma(-(a * r), r2, 1.0);
-    const double pe = fma(err, 2.2222222222222221e-01, 3.3333333333333331e-01) * err;
+    const double pe = fma(err, CM_CBRT_C2, CM_CBRT_C1) * err;
     r = fma(r, pe, r);
     r2 = r * r;
     double y = a * r2;  // a^(1/3), ~2-3 ulp
     // one Newton correction with the residual computed by fma: y -= (y^3 - a) / (3 y^2)
     const double d = fma(-(y * y), y, a);
-    y = fma(d, r2 * 3.3333333333333331e-01, y);
+    y = fma(d, r2 * CM_CBRT_C1, y);
     return mk64(hi32(y) + (q << 20), lo32(y));
 }
 CM_HD float cbrtp_(float x) { return cbrtf(x); }

@@ -6,6 +6,7 @@
 // 128-bit streaming store per output column per thread item).  The parameter block
 // and the host-derived constants travel in kernel-parameter (constant-bank) space.
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 
 #include "cm_hostpipe.cuh"
@@ -71,10 +72,28 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
     if (q_ice != nullptr) {
         const FT* in8[8] = {rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice};
         Warm2MFused<FT, 8> f8{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
-        return launch_pointwise<FT, 8, 4, Warm2MFused<FT, 8>, 256, 1>(f8, n, in8, out, s, "bmt2m_warm kernel launch");
+        return launch_pointwise<FT, 8, 4, Warm2MFused<FT, 8>, 128, 8, false>(f8, n, in8, out, s, "bmt2m_warm kernel launch");
     }
     Warm2MFused<FT> f{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
-    return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 256, 1>(f, n, in, out, s, "bmt2m_warm kernel launch");
+#ifdef CUMICRO_TUNING
+    {   // launch-shape exploration (tools/tune_2m.py); not compiled into the product build
+        static const char* ev = getenv("CUMICRO_2M_VARIANT");
+        const int v = ev ? atoi(ev) : 0;
+        const char* w = "bmt2m_warm kernel launch";
+        switch (v) {
+            case 1: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 256, 2>(f, n, in, out, s, w);
+            case 2: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 3>(f, n, in, out, s, w);
+            case 3: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 4>(f, n, in, out, s, w);
+            case 4: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 5>(f, n, in, out, s, w);
+            case 5: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 6>(f, n, in, out, s, w);
+            case 6: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 8>(f, n, in, out, s, w);
+            case 7: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 64, 8>(f, n, in, out, s, w);
+            case 8: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 64, 12>(f, n, in, out, s, w);
+            default: break;
+        }
+    }
+#endif
+    return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 8, false>(f, n, in, out, s, "bmt2m_warm kernel launch");
 }
 
 template <class FT>
@@ -106,7 +125,7 @@ int bmt2m_warm_host_impl(const typename P<FT>::params_2m_warm* p, int64_t n, con
     Warm2MFused<FT> f{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
     return host_pipeline<FT, 7, 4>(n, in, out, chunk,
                                    [&](int64_t m, const FT* const(&din)[7], FT* const(&dout)[4], cudaStream_t s) {
-                                       return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 256, 1>(
+                                       return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 8, false>(
                                            f, m, din, dout, s, "bmt2m_warm (host pipeline) kernel launch");
                                    });
 }

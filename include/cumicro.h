@@ -69,6 +69,11 @@ int64_t cumicro_launch_count(void);
  * bench.py times it with CUDA events to obtain the FP64 pipe peak in place. */
 int cumicro_probe_fp64_fma(int64_t iters, int blocks_per_sm, double* scratch, double* flops_out, void* stream);
 
+/* Accuracy probe of the library's device math (cm_math.cuh) on the GPU itself:
+ * fn = 0 exp, 1 log, 2 cbrt, 3 reciprocal, 4 pow(x, y), 5 exp with IEEE limits;
+ * out[i] = fn(x[i] [, y[i]]).  Device pointers; used by tests/test_gpu_math.py. */
+int cumicro_probe_math_f64(int fn, int64_t n, const double* x, const double* y, double* out, void* stream);
+
 /* Free the per-thread device staging buffers that the `_host` entry points cache. */
 void cumicro_release_workspace(void);
 

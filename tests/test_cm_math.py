@@ -1,0 +1,78 @@
+"""Accuracy of the hand-written Float64 device math (cm_math.cuh), measured on the HOST
+instantiation of the same code against mpmath (40 digits).  The GPU instantiation differs
+only in the hardware seeds (MUFU.RCP64H / lg2 / ex2), which the Newton steps erase."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+mp = pytest.importorskip("mpmath")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "native", "cm_math_host.cu")
+SO = os.path.join(ROOT, "tests", "native", "_cm_math_host.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    deps = [SRC, os.path.join(ROOT, "cloudmicrophysics.jl_b200", "csrc", "cm_math.cuh"),
+            os.path.join(ROOT, "cloudmicrophysics.jl_b200", "csrc", "cm_math_tables.inc")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-gencode",
+                        "arch=compute_100a,code=sm_100a", "-o", SO, SRC], check=True, capture_output=True)
+    return C.CDLL(SO)
+
+
+def _run(lib, fn, x):
+    y = np.empty_like(x)
+    getattr(lib, fn)(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_long(x.size))
+    return y
+
+
+def _max_ulp(y, x, f):
+    mp.mp.dps = 40
+    worst = 0.0
+    for xi, yi in zip(x, y):
+        t = f(mp.mpf(float(xi)))
+        worst = max(worst, float(abs((mp.mpf(float(yi)) - t) / t) / mp.mpf(2) ** -52))
+    return worst
+
+
+def test_exp(lib):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 1500), rng.uniform(-2, 2, 1500), rng.uniform(-1e-3, 1e-3, 300), [0.0]])
+    assert _max_ulp(_run(lib, "cmt_exp", x), x, mp.exp) < 1.6   # relative error in units of 2^-52
+    y = _run(lib, "cmt_exp_full", np.array([-800.0, 800.0, np.nan, 0.0, -745.0, 709.5]))
+    assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and y[4] == 0 and np.isinf(y[5])
+
+
+def test_log(lib):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([10 ** rng.uniform(-300, 300, 1500), rng.uniform(0.5, 2, 1500), 1 + rng.uniform(-1e-2, 1e-2, 600),
+                        1 + rng.uniform(-1e-6, 1e-6, 300)])
+    assert _max_ulp(_run(lib, "cmt_log", x), x, mp.log) < 2.0
+    assert _run(lib, "cmt_log", np.array([1.0]))[0] == 0.0
+
+
+def test_cbrt_and_rcp(lib):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([10 ** rng.uniform(-300, 300, 1500), rng.uniform(0.5, 16, 1500)])
+    assert _max_ulp(_run(lib, "cmt_cbrt", x), x, mp.cbrt) < 1.0
+    assert _max_ulp(_run(lib, "cmt_rcp", x), x, lambda t: 1 / t) < 1.0
+
+
+def test_pow(lib):
+    """powp_(x, y) = exp_(y logp_(x)): relative error <= ~2 ulp * (|y ln x| + 1)."""
+    mp.mp.dps = 40
+    rng = np.random.default_rng(3)
+    xs = 10 ** rng.uniform(-12, 3, 1500)
+    ps = rng.uniform(-5, 5, 1500)
+    y = np.empty_like(xs)
+    lib.cmt_pow(xs.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_long(xs.size))
+    worst = 0.0
+    for a, b, c in zip(xs, ps, y):
+        t = mp.power(mp.mpf(float(a)), mp.mpf(float(b)))
+        amp = abs(mp.mpf(float(b)) * mp.log(mp.mpf(float(a)))) + 1
+        worst = max(worst, float(abs((mp.mpf(float(c)) - t) / t) / amp / mp.mpf(2) ** -52))
+    assert worst < 2.0

@@ -76,7 +76,8 @@ def test_sb2006_leaves_f64_parity_and_regimes(built, orc, cuda, limited):
     if limited:
         br = ref["leaves"][abi.SB2006_LEAVES.index("rai_breakup")]
         sc = ref["leaves"][abi.SB2006_LEAVES.index("rai_selfcol")]
-        assert ((br == 0) & (sc != 0)).any() and (br > 0).any() and (br < 0).any()
+        ratio = np.divide(br, -sc, out=np.zeros_like(br), where=sc != 0)   # = Phi_br + 1
+        assert ((br == 0) & (sc != 0)).any() and ((ratio > 0) & (ratio <= 1)).any() and (ratio > 1).any()
 
 
 def test_golden_values_through_the_gpu(built, cuda):

@@ -1,0 +1,51 @@
+"""Accuracy of the device math on the GPU itself (hardware MUFU seeds) vs mpmath."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+mp = pytest.importorskip("mpmath")
+
+
+def _probe(built, cuda, fn, x, y=None):
+    import torch
+    xd = torch.from_numpy(x).to(cuda)
+    yd = torch.from_numpy(y if y is not None else np.zeros_like(x)).to(cuda)
+    out = torch.empty_like(xd)
+    lib = built._abi.load()
+    st = lib.cumicro_probe_math_f64(fn, C.c_int64(x.size), C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr()),
+                                    C.c_void_p(out.data_ptr()), None)
+    built._abi.check(st, "cumicro_probe_math_f64")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _max_ulp(y, x, f):
+    mp.mp.dps = 40
+    worst = 0.0
+    for xi, yi in zip(x, y):
+        t = f(mp.mpf(float(xi)))
+        worst = max(worst, float(abs((mp.mpf(float(yi)) - t) / t) / mp.mpf(2) ** -52))
+    return worst
+
+
+def test_device_math_accuracy(built, cuda):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 2000), rng.uniform(-2, 2, 2000), rng.uniform(-1e-3, 1e-3, 400)])
+    assert _max_ulp(_probe(built, cuda, 0, x), x, mp.exp) < 1.6
+    x = np.concatenate([10 ** rng.uniform(-300, 300, 2000), rng.uniform(0.5, 2, 2000), 1 + rng.uniform(-1e-2, 1e-2, 600)])
+    assert _max_ulp(_probe(built, cuda, 1, x), x, mp.log) < 2.0
+    x = np.concatenate([10 ** rng.uniform(-300, 300, 2000), rng.uniform(0.5, 16, 2000)])
+    assert _max_ulp(_probe(built, cuda, 2, x), x, mp.cbrt) < 1.0
+    assert _max_ulp(_probe(built, cuda, 3, x), x, lambda t: 1 / t) < 1.0
+    xs, ps = 10 ** rng.uniform(-12, 3, 2000), rng.uniform(-5, 5, 2000)
+    got = _probe(built, cuda, 4, xs, ps)
+    mp.mp.dps = 40
+    worst = 0.0
+    for a, b, c in zip(xs, ps, got):
+        t = mp.power(mp.mpf(float(a)), mp.mpf(float(b)))
+        worst = max(worst, float(abs((mp.mpf(float(c)) - t) / t) / (abs(mp.mpf(float(b)) * mp.log(mp.mpf(float(a)))) + 1) / mp.mpf(2) ** -52))
+    assert worst < 2.0
+    y = _probe(built, cuda, 5, np.array([-800.0, 800.0, np.nan, 0.0, -745.0, 709.5]))
+    assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and y[4] == 0 and np.isinf(y[5])
