@@ -1,0 +1,59 @@
+"""1-moment array methods behind ``BMT.bulk_microphysics_tendencies`` (BMT:505-632)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from . import parameters as CMP
+from ._columns import Tendencies, check_columns, ptr, ptr_table, stream_handle
+
+OUT_1M = ("dq_lcl_dt", "dq_icl_dt", "dq_rai_dt", "dq_sno_dt")
+# field order of _microphysics_source_terms (BMT:206-216)
+SRC_1M = ("S_phase_change_vap_lcl", "S_phase_change_vap_icl", "S_acnv_lcl_rai", "S_acnv_icl_sno", "S_accr_lcl_rai",
+          "S_accr_lcl_sno_cold", "S_accr_lcl_sno_warm", "S_accr_melt_lcl_sno", "S_accr_icl_rai", "S_accr_freeze_icl_rai",
+          "S_accr_icl_sno", "S_accr_rai_sno_cold", "S_accr_rai_sno_warm", "S_accr_melt_rai_sno", "S_phase_change_vap_rai",
+          "S_phase_change_vap_sno", "S_melt_icl_lcl", "S_melt_sno_rai")
+NAMES = ["rho", "T", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno"]
+
+
+def bmt_1m(mode, mp, tps, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, Δt=None, nsub=1, *, out=None):
+    from .BulkMicrophysicsTendencies import Instantaneous, InstantaneousVerbose, LinearizedAverage
+    cols = [rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno]
+    suf, n, dev = check_columns(cols, NAMES)
+    block = CMP.pack_1m(mp, tps)
+    if not type(block).__name__.endswith(suf):
+        raise TypeError(f"parameter float type does not match the columns ({suf})")
+    outs = list(out) if out is not None else [torch.empty_like(rho) for _ in range(4)]
+    check_columns([rho] + outs, ["rho"] + ["out"] * 4)
+    lib = _abi.load()
+    res = Tendencies(zip(OUT_1M, outs))
+    with torch.cuda.device(dev):
+        if isinstance(mode, InstantaneousVerbose):
+            src = [torch.empty_like(rho) for _ in SRC_1M]
+            st = getattr(lib, f"cumicro_bmt1m_verbose_{suf}")(C.byref(block), C.c_int64(n), *[ptr(c) for c in cols],
+                                                              ptr_table(outs), ptr_table(src), stream_handle(dev))
+            res.update(zip(SRC_1M, src))
+        elif isinstance(mode, LinearizedAverage):
+            if Δt is None:
+                raise TypeError("LinearizedAverage needs Δt (BMT:572-586)")
+            cdt = C.c_double(float(Δt)) if suf == "f64" else C.c_float(float(Δt))
+            st = getattr(lib, f"cumicro_bmt1m_linavg_{suf}")(C.byref(block), C.c_int64(n), *[ptr(c) for c in cols], cdt,
+                                                             C.c_int(int(nsub)), ptr_table(outs), stream_handle(dev))
+        elif isinstance(mode, Instantaneous):
+            st = getattr(lib, f"cumicro_bmt1m_inst_{suf}")(C.byref(block), C.c_int64(n), *[ptr(c) for c in cols],
+                                                           ptr_table(outs), stream_handle(dev))
+        else:
+            raise TypeError(f"unknown tendency mode {mode!r}")
+    _abi.check(st, "cumicro_bmt1m")
+    return res
+
+
+def bmt_0m(mp, tps, T, q_lcl, q_icl, q_vap_sat=None):
+    """BMT:658-680 → Microphysics0M.remove_precipitation (src/Microphysics0M.jl:35-46):
+    ``-max(0, q_lcl + q_icl - threshold)/τ_precip`` with threshold ``qc_0`` or ``S_0 q_vap_sat``.
+    One fused elementwise pass; ``mp`` is a Parameters0M-like object with τ_precip, qc_0, S_0."""
+    check_columns([T, q_lcl, q_icl] + ([q_vap_sat] if q_vap_sat is not None else []), ["T", "q_lcl", "q_icl", "q_vap_sat"])
+    thr = mp.qc_0 if q_vap_sat is None else mp.S_0 * q_vap_sat
+    return Tendencies(dq_tot_dt=-torch.clamp_min(q_lcl + q_icl - thr, 0) / mp.τ_precip)

@@ -4,7 +4,10 @@
 // columns, NOUT output columns, n points, no coupling between points.  A family
 // supplies a functor F (parameters by value, constant-bank resident through the
 // __grid_constant__ kernel argument) with
-//     __device__ void operator()(const FT (&x)[NIN], FT (&y)[NOUT]) const;
+//     __device__ void operator()(const double (&x)[NIN], double (&y)[NOUT]) const;
+// The column type FT (double or float) is the I/O type only: arithmetic is always
+// Float64 (a Float32 method loads float, computes in double with the Float32 method's
+// regime thresholds, and rounds once on store — DESIGN.md §Float32);
 // and this header supplies the data movement:
 //   * vector variant: one thread owns VEC = 16 B / sizeof(FT) consecutive points, every
 //     input column is read exactly once with one 128-bit ld.global.nc and every live output
@@ -44,19 +47,19 @@ pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int6
     const int64_t n_items = VECTOR ? (a.n / VEC) : (a.n - first);
     for (int64_t it = (int64_t)blockIdx.x * BLOCK + threadIdx.x; it < n_items; it += stride) {
         const int64_t i0 = VECTOR ? it * VEC : first + it;
-        FT x[VEC][NIN];
+        double x[VEC][NIN];
         if constexpr (VECTOR) {
 #pragma unroll
             for (int c = 0; c < NIN; ++c) {
                 auto pk = ldg_vec(a.in[c] + i0);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) x[v][c] = pk.v[v];
+                for (int v = 0; v < VEC; ++v) x[v][c] = (double)pk.v[v];
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < NIN; ++c) x[0][c] = __ldg(a.in[c] + i0);
+            for (int c = 0; c < NIN; ++c) x[0][c] = (double)__ldg(a.in[c] + i0);
         }
-        FT y[VEC][NOUT];
+        double y[VEC][NOUT];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) a.f(x[v], y[v]);
         if constexpr (VECTOR) {
@@ -65,13 +68,13 @@ pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int6
                 if (a.out[c] == nullptr) continue;
                 pack<FT, VEC> pk;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) pk.v[v] = y[v][c];
+                for (int v = 0; v < VEC; ++v) pk.v[v] = (FT)y[v][c];
                 st_vec(a.out[c] + i0, pk);
             }
         } else {
 #pragma unroll
             for (int c = 0; c < NOUT; ++c)
-                if (a.out[c]) a.out[c][i0] = y[0][c];
+                if (a.out[c]) a.out[c][i0] = (FT)y[0][c];
         }
     }
 }

@@ -36,7 +36,8 @@ template <class FT> struct SB2006K {
 };
 
 template <class FT>
-__host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, const typename P<FT>::air& aps) {
+__host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, const typename P<FT>::air& aps,
+                                          bool method_is_f32 = false) {
     SB2006K<FT> k;
     const FT pi = FT(3.141592653589793238462643383279502884L);
     const FT nu_c = sb.pdf_c.nu_c;
@@ -47,7 +48,7 @@ __host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, cons
     k.six_over_pi_rho_w = FT(6) / (pi * sb.pdf_r.rho_w);
     k.six_x_star_r = FT(6) * sb.pdf_r.xr_min;
     k.inv_xr_min = FT(1) / sb.pdf_r.xr_min;
-    const FT epsn = std::cbrt(std::numeric_limits<FT>::min());
+    const FT epsn = method_is_f32 ? FT(2.2737367544323206e-13) : FT(2.8126442852362996e-103);
     k.cbrt_Sc = std::cbrt(aps.nu_air / std::max(aps.D_vapor, epsn));
     k.inv_nu_air = FT(1) / aps.nu_air;
     k.inv_K_safe = FT(1) / std::max(aps.K_therm, epsn);
@@ -76,8 +77,7 @@ template <class FT> struct RainPDF { FT N0r, Dr_mean, xr_mean, lam; };
 // CM2.pdf_rain_parameters                                          CM2:67-110
 // (q and N are the caller's already-floored safe values, as at every reference call site.)
 template <class FT>
-CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT pi_rho_w, FT q, FT rho, FT N) {
-    const FT e = num<FT>::eps();
+CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT pi_rho_w, FT e, FT q, FT rho, FT N) {
     const FT safe_q = fmax_(q, e);
     const FT safe_N = fmax_(N, e);
     const FT L = rho * safe_q;
@@ -106,8 +106,8 @@ CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT p
 }
 
 // CM2.number_tendency_from_mass_limits                              CM2:882-891
-template <class FT> CM_DEV FT number_tendency_from_mass_limits(FT inv_x_min, FT inv_x_max, FT inv_tau, FT q, FT n) {
-    const FT n_target = (q < num<FT>::eps()) ? FT(0) : clamp_(n, q * inv_x_max, q * inv_x_min);
+template <class FT> CM_DEV FT number_tendency_from_mass_limits(FT e, FT inv_x_min, FT inv_x_max, FT inv_tau, FT q, FT n) {
+    const FT n_target = (q < e) ? FT(0) : clamp_(n, q * inv_x_max, q * inv_x_min);
     return (n_target - n) * inv_tau;
 }
 
@@ -126,7 +126,7 @@ template <class FT>
 CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& p, const ThermoK<FT>& tk,
                                           const SB2006K<FT>& sk, FT rho, FT T, FT q_tot, FT q_lcl, FT n_lcl,
                                           FT q_rai, FT n_rai, FT q_ice) {
-    const FT e = num<FT>::eps();
+    const FT e = tk.eps;
     const auto& sb = p.sb;
     Warm2M<FT> o;
 
@@ -144,7 +144,7 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     // ---- thermodynamic state shared by cond/evap and rain evaporation
     const TempState<FT> ts = temp_state(tk, T);
     const FT p_vs = p_sat_liq(tk, ts);
-    const FT inv_p_vs = rcp_(fmax_(p_vs, num<FT>::eps_numerics()));
+    const FT inv_p_vs = rcp_(fmax_(p_vs, tk.eps_n));
     const FT Lv = latent_heat_vapor(tk, T);
     const FT q_liq = q_lcl + q_rai;
     const FT qv = q_vap(q_tot, q_liq, q_ice);
@@ -165,7 +165,7 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     // ---- rain size distribution (shared by evaporation, self-collection, breakup)
     const FT safe_q_rai = fmax_(q_rai, e);
     const FT safe_N_rai = fmax_(N_rai, e);
-    const RainPDF<FT> rp = pdf_rain_parameters<FT>(sb.pdf_r, sk.pi_rho_w, safe_q_rai, rho, safe_N_rai);
+    const RainPDF<FT> rp = pdf_rain_parameters<FT>(sb.pdf_r, sk.pi_rho_w, e, safe_q_rai, rho, safe_N_rai);
     const FT xr_mean = rp.xr_mean;
     // every power of xr_mean below comes from ONE cube root and ONE logarithm
     const FT cx = cbrtp_(xr_mean);
@@ -259,9 +259,9 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
 
     // ---- number adjustment (Horn 2012)                                 BMT:771-779
     o.leaf[CUMICRO_SB_NUMADJ_LCL] =
-        number_tendency_from_mass_limits<FT>(sk.inv_xc_min, sk.inv_xc_max, sk.inv_numadj_tau, q_lcl, n_lcl);
+        number_tendency_from_mass_limits<FT>(e, sk.inv_xc_min, sk.inv_xc_max, sk.inv_numadj_tau, q_lcl, n_lcl);
     o.leaf[CUMICRO_SB_NUMADJ_RAI] =
-        number_tendency_from_mass_limits<FT>(sk.inv_xr_min, sk.inv_xr_max, sk.inv_numadj_tau, q_rai, n_rai);
+        number_tendency_from_mass_limits<FT>(e, sk.inv_xr_min, sk.inv_xr_max, sk.inv_numadj_tau, q_rai, n_rai);
 
     // ---- aggregate in the order of BMT:736-779
     o.dq_lcl_dt = o.leaf[CUMICRO_SB_COND_DQ_LCL] + o.leaf[CUMICRO_SB_ACNV_DQ_LCL] + o.leaf[CUMICRO_SB_ACCR_DQ_LCL];
@@ -283,9 +283,8 @@ namespace cm {
 // (+ _sb_rain_terminal_velocity_helper CM2:720-739: limited -> (1,1,1,1)).
 template <class FT>
 CM_DEV void rain_terminal_velocity_sb(const typename P<FT>::sb_pdf_r& pdf_r, const typename P<FT>::vel_sb2006& vel,
-                                      FT pi_rho_w, FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) {
-    const FT e = num<FT>::eps();
-    const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, fmax_(q_rai, e), rho, fmax_(N_rai, e));
+                                      FT pi_rho_w, FT e, FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) {
+    const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, e, fmax_(q_rai, e), rho, fmax_(N_rai, e));
     const FT Dr_mean = r.Dr_mean;
     FT pa0 = FT(1), pb0 = FT(1), pa1 = FT(1), pb1 = FT(1);
     if (!pdf_r.limited) {
@@ -330,11 +329,10 @@ template <class FT> CM_DEV FT chen2022_exponential_pdf(FT a, FT b, FT c, FT log_
 // CM2.rain_terminal_velocity(::SB2006, ::Chen2022VelTypeRain, ...)          CM2:703-719
 template <class FT>
 CM_DEV void rain_terminal_velocity_chen(const typename P<FT>::sb_pdf_r& pdf_r, const typename P<FT>::vel_chen_rain& vel,
-                                        FT pi_rho_w, FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) {
-    const FT e = num<FT>::eps();
+                                        FT pi_rho_w, FT e, FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) {
     FT aiu[3], bi[3], ciu[3];
     chen2022_vel_coeffs_rain<FT>(vel, rho, aiu, bi, ciu);
-    const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, fmax_(q_rai, e), rho, fmax_(N_rai, e));
+    const RainPDF<FT> r = pdf_rain_parameters<FT>(pdf_r, pi_rho_w, e, fmax_(q_rai, e), rho, fmax_(N_rai, e));
     const FT ll = log_full_(r.Dr_mean), il = FT(1) / r.Dr_mean;
     FT v0 = FT(0), v3 = FT(0);
 #pragma unroll
@@ -351,8 +349,7 @@ CM_DEV void rain_terminal_velocity_chen(const typename P<FT>::sb_pdf_r& pdf_r, c
 // 1/18 cbrt((6/rho_w/pi)^2) grav/nu_air are parameter-only (host-side).
 template <class FT>
 CM_DEV void cloud_terminal_velocity(const typename P<FT>::sb_pdf_c& pdf_c, const typename P<FT>::vel_stokes& vel,
-                                    FT pref0, const FT gratio[2], FT q_liq, FT rho, FT N_liq, FT& vt0, FT& vt1) {
-    const FT e = num<FT>::eps();
+                                    FT pref0, const FT gratio[2], FT e, FT q_liq, FT rho, FT N_liq, FT& vt0, FT& vt1) {
     const FT safe_q = fmax_(q_liq, e), safe_N = fmax_(N_liq, e);
     const FT logx = log_full_(rho * safe_q / safe_N);
     const FT logB = -pdf_c.mu_c * (logx + pdf_c.loggamma_z1 - pdf_c.loggamma_z2);

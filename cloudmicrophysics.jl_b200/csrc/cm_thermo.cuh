@@ -17,10 +17,16 @@ template <class FT> struct ThermoK {
     FT LH_v0, LH_s0, dcp_vl, dcp_vi;  // cp_v-cp_l, cp_v-cp_i
     FT a_liq, b_liq, a_ice, b_ice;    // p_sat exponents: dcp/R_v, (LH_0 - dcp T_0)/R_v
     FT cv_l, q_min, LH_f0, dcp_li;    // cp_l; q_min; LH_s0-LH_v0; cp_l-cp_i
+    // Numerical thresholds of the METHOD's float type (UT:318-340): eps(FT) and
+    // ϵ_numerics(FT) = cbrt(floatmin(FT)).  The Float32 entry points compute in Float64 but
+    // gate regimes with the Float32 thresholds, so branch selection is the reference's.
+    FT eps, eps_n;
 };
 
-template <class FT> __host__ inline ThermoK<FT> make_thermo_k(const typename P<FT>::thermo& t) {
+template <class FT> __host__ inline ThermoK<FT> make_thermo_k(const typename P<FT>::thermo& t, bool method_is_f32 = false) {
     ThermoK<FT> k;
+    k.eps = method_is_f32 ? FT(1.1920928955078125e-07) : FT(2.220446049250313e-16);
+    k.eps_n = method_is_f32 ? FT(2.2737367544323206e-13) : FT(2.8126442852362996e-103);
     k.T_0 = t.T_0; k.T_triple = t.T_triple; k.inv_T_triple = FT(1) / t.T_triple;
     k.press_triple = t.press_triple; k.T_freeze = t.T_freeze;
     k.R_v = t.R_v; k.inv_R_v = FT(1) / t.R_v;

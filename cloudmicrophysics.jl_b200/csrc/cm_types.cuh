@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/cumicro.h"
 #include "cm_math.cuh"
+#include "cm_widen.inc"
 
 namespace cm {
 
@@ -18,6 +19,9 @@ template <> struct P<double> {
     using vel_chen_small_ice = cumicro_vel_chen_small_ice_f64;
     using vel_chen_large_ice = cumicro_vel_chen_large_ice_f64;
     using params_2m_warm = cumicro_params_2m_warm_f64;
+    using params_1m = cumicro_params_1m_f64;
+    using particle_mass = cumicro_particle_mass_f64;
+    using frostenberg = cumicro_frostenberg2023_f64;
 };
 template <> struct P<float> {
     using thermo = cumicro_thermo_f32;
@@ -31,6 +35,9 @@ template <> struct P<float> {
     using vel_chen_small_ice = cumicro_vel_chen_small_ice_f32;
     using vel_chen_large_ice = cumicro_vel_chen_large_ice_f32;
     using params_2m_warm = cumicro_params_2m_warm_f32;
+    using params_1m = cumicro_params_1m_f32;
+    using particle_mass = cumicro_particle_mass_f32;
+    using frostenberg = cumicro_frostenberg2023_f32;
 };
 
 }  // namespace cm

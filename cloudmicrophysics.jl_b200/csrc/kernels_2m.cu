@@ -20,13 +20,16 @@ using namespace cm;
 // ---- BMT:820-854: 7 columns in, 4 tendencies out --------------------------------------
 // (NIN = 8 adds the optional q_ice column that the reference's warm-only method
 // accepts and forwards to the thermodynamics, BMT:823,836,843.)
-template <class FT, int NIN = 7> struct Warm2MFused {
-    typename P<FT>::params_2m_warm p;
-    ThermoK<FT> tk;
-    SB2006K<FT> sk;
-    __device__ __forceinline__ void operator()(const FT (&x)[NIN], FT (&y)[4]) const {
-        const FT q_ice = (NIN == 8) ? fmax_(FT(0), x[NIN - 1]) : FT(0);
-        Warm2M<FT> o = warm_rain_tendencies_2m<FT>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], q_ice);
+// Functors compute in Float64 (D = double); the entry points below are templated on the
+// column type FT and widen Float32 parameter blocks exactly.
+using D = double;
+template <int NIN = 7> struct Warm2MFused {
+    P<D>::params_2m_warm p;
+    ThermoK<D> tk;
+    SB2006K<D> sk;
+    __device__ __forceinline__ void operator()(const D (&x)[NIN], D (&y)[4]) const {
+        const D q_ice = (NIN == 8) ? fmax_(D(0), x[NIN - 1]) : D(0);
+        Warm2M<D> o = warm_rain_tendencies_2m<D>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], q_ice);
         y[0] = o.dq_lcl_dt;
         y[1] = o.dn_lcl_dt;
         y[2] = o.dq_rai_dt;
@@ -35,16 +38,27 @@ template <class FT, int NIN = 7> struct Warm2MFused {
 };
 
 // ---- the 15 SB2006 process rates one by one (leaf API) ----------------------------------
-template <class FT> struct Warm2MLeaves {
-    typename P<FT>::params_2m_warm p;
-    ThermoK<FT> tk;
-    SB2006K<FT> sk;
-    __device__ __forceinline__ void operator()(const FT (&x)[7], FT (&y)[CUMICRO_SB2006_NLEAF]) const {
-        Warm2M<FT> o = warm_rain_tendencies_2m<FT>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], FT(0));
+struct Warm2MLeaves {
+    P<D>::params_2m_warm p;
+    ThermoK<D> tk;
+    SB2006K<D> sk;
+    __device__ __forceinline__ void operator()(const D (&x)[7], D (&y)[CUMICRO_SB2006_NLEAF]) const {
+        Warm2M<D> o = warm_rain_tendencies_2m<D>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], D(0));
 #pragma unroll
         for (int k = 0; k < CUMICRO_SB2006_NLEAF; ++k) y[k] = o.leaf[k];
     }
 };
+
+template <class FT> constexpr bool is_f32() { return sizeof(FT) == 4; }
+
+// (p wide, tk, sk) of one call: Float32 blocks are widened exactly, thresholds follow FT.
+template <class FT, class F> F make_2m(const typename P<FT>::params_2m_warm* p) {
+    F f{};
+    widen(*p, f.p);
+    f.tk = make_thermo_k<D>(f.p.tps, is_f32<FT>());
+    f.sk = make_sb2006_k<D>(f.p.sb, f.p.aps, is_f32<FT>());
+    return f;
+}
 
 template <class FT> int check_2m_options(const typename P<FT>::params_2m_warm* p) {
     if (p->sb.pdf_r.limited != 0 && p->sb.pdf_r.limited != 1)
@@ -71,29 +85,29 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
             }
     if (q_ice != nullptr) {
         const FT* in8[8] = {rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice};
-        Warm2MFused<FT, 8> f8{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
-        return launch_pointwise<FT, 8, 4, Warm2MFused<FT, 8>, 128, 8, false>(f8, n, in8, out, s, "bmt2m_warm kernel launch");
+        return launch_pointwise<FT, 8, 4, Warm2MFused<8>, 128, 8, false>(make_2m<FT, Warm2MFused<8>>(p), n, in8, out, s,
+                                                                        "bmt2m_warm kernel launch");
     }
-    Warm2MFused<FT> f{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
+    Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
 #ifdef CUMICRO_TUNING
     {   // launch-shape exploration (tools/tune_2m.py); not compiled into the product build
         static const char* ev = getenv("CUMICRO_2M_VARIANT");
         const int v = ev ? atoi(ev) : 0;
         const char* w = "bmt2m_warm kernel launch";
         switch (v) {
-            case 1: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 256, 2>(f, n, in, out, s, w);
-            case 2: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 3>(f, n, in, out, s, w);
-            case 3: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 4>(f, n, in, out, s, w);
-            case 4: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 5>(f, n, in, out, s, w);
-            case 5: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 6>(f, n, in, out, s, w);
-            case 6: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 8>(f, n, in, out, s, w);
-            case 7: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 64, 8>(f, n, in, out, s, w);
-            case 8: return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 64, 12>(f, n, in, out, s, w);
+            case 1: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 256, 2>(f, n, in, out, s, w);
+            case 2: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 3>(f, n, in, out, s, w);
+            case 3: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 4>(f, n, in, out, s, w);
+            case 4: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 5>(f, n, in, out, s, w);
+            case 5: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 6>(f, n, in, out, s, w);
+            case 6: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8>(f, n, in, out, s, w);
+            case 7: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 8>(f, n, in, out, s, w);
+            case 8: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 12>(f, n, in, out, s, w);
             default: break;
         }
     }
 #endif
-    return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 8, false>(f, n, in, out, s, "bmt2m_warm kernel launch");
+    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false>(f, n, in, out, s, "bmt2m_warm kernel launch");
 }
 
 template <class FT>
@@ -107,9 +121,8 @@ int sb2006_leaves_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const
     if (out_tbl == nullptr) return cmh::fail(CUMICRO_E_NULL, "leaf pointer table is NULL");
     FT* out[CUMICRO_SB2006_NLEAF];
     for (int k = 0; k < CUMICRO_SB2006_NLEAF; ++k) out[k] = out_tbl[k];
-    Warm2MLeaves<FT> f{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
-    return launch_pointwise<FT, 7, CUMICRO_SB2006_NLEAF, Warm2MLeaves<FT>, 256, 1>(f, n, in, out, (cudaStream_t)stream,
-                                                                                  "sb2006_leaves kernel launch");
+    return launch_pointwise<FT, 7, CUMICRO_SB2006_NLEAF, Warm2MLeaves, 128, 4, false>(make_2m<FT, Warm2MLeaves>(p), n, in, out,
+                                                                                     (cudaStream_t)stream, "sb2006_leaves kernel launch");
 }
 
 template <class FT>
@@ -122,38 +135,38 @@ int bmt2m_warm_host_impl(const typename P<FT>::params_2m_warm* p, int64_t n, con
     if (st) return st;
     if ((st = check_2m_options<FT>(p))) return st;
     if ((st = require_outputs<FT, 4>(n, out, 4))) return st;
-    Warm2MFused<FT> f{*p, make_thermo_k<FT>(p->tps), make_sb2006_k<FT>(p->sb, p->aps)};
+    Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
     return host_pipeline<FT, 7, 4>(n, in, out, chunk,
                                    [&](int64_t m, const FT* const(&din)[7], FT* const(&dout)[4], cudaStream_t s) {
-                                       return launch_pointwise<FT, 7, 4, Warm2MFused<FT>, 128, 8, false>(
+                                       return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false>(
                                            f, m, din, dout, s, "bmt2m_warm (host pipeline) kernel launch");
                                    });
 }
 
 // ---- terminal velocities: (q, rho, N) -> (vt0, vt1) ---------------------------------------
-template <class FT> struct RainVelSB {
-    typename P<FT>::sb_pdf_r pdf_r;
-    typename P<FT>::vel_sb2006 vel;
-    FT pi_rho_w;
-    __device__ __forceinline__ void operator()(const FT (&x)[3], FT (&y)[2]) const {
-        rain_terminal_velocity_sb<FT>(pdf_r, vel, pi_rho_w, x[0], x[1], x[2], y[0], y[1]);
+struct RainVelSB {
+    P<D>::sb_pdf_r pdf_r;
+    P<D>::vel_sb2006 vel;
+    D pi_rho_w, eps;
+    __device__ __forceinline__ void operator()(const D (&x)[3], D (&y)[2]) const {
+        rain_terminal_velocity_sb<D>(pdf_r, vel, pi_rho_w, eps, x[0], x[1], x[2], y[0], y[1]);
     }
 };
-template <class FT> struct RainVelChen {
-    typename P<FT>::sb_pdf_r pdf_r;
-    typename P<FT>::vel_chen_rain vel;
-    FT pi_rho_w;
-    __device__ __forceinline__ void operator()(const FT (&x)[3], FT (&y)[2]) const {
-        rain_terminal_velocity_chen<FT>(pdf_r, vel, pi_rho_w, x[0], x[1], x[2], y[0], y[1]);
+struct RainVelChen {
+    P<D>::sb_pdf_r pdf_r;
+    P<D>::vel_chen_rain vel;
+    D pi_rho_w, eps;
+    __device__ __forceinline__ void operator()(const D (&x)[3], D (&y)[2]) const {
+        rain_terminal_velocity_chen<D>(pdf_r, vel, pi_rho_w, eps, x[0], x[1], x[2], y[0], y[1]);
     }
 };
-template <class FT> struct CloudVel {
-    typename P<FT>::sb_pdf_c pdf_c;
-    typename P<FT>::vel_stokes vel;
-    FT pref0;
-    FT gratio[2];
-    __device__ __forceinline__ void operator()(const FT (&x)[3], FT (&y)[2]) const {
-        cloud_terminal_velocity<FT>(pdf_c, vel, pref0, gratio, x[0], x[1], x[2], y[0], y[1]);
+struct CloudVel {
+    P<D>::sb_pdf_c pdf_c;
+    P<D>::vel_stokes vel;
+    D pref0, eps;
+    D gratio[2];
+    __device__ __forceinline__ void operator()(const D (&x)[3], D (&y)[2]) const {
+        cloud_terminal_velocity<D>(pdf_c, vel, pref0, gratio, eps, x[0], x[1], x[2], y[0], y[1]);
     }
 };
 
@@ -169,22 +182,39 @@ int termvel_impl(const void* p1, const void* p2, const F& f, int64_t n, const FT
     return launch_pointwise<FT, 3, 2, F, 256, 2>(f, n, in, out, (cudaStream_t)stream, what);
 }
 
-template <class FT> FT pi_rho_w_of(const typename P<FT>::sb_pdf_r* pdf) {
-    return pdf ? FT(3.141592653589793238462643383279502884L) * pdf->rho_w : FT(0);
-}
+template <class FT> D method_eps() { return is_f32<FT>() ? 1.1920928955078125e-07 : 2.220446049250313e-16; }
+const D kPi = 3.141592653589793238462643383279502884;
 
-template <class FT>
-CloudVel<FT> make_cloud_vel(const typename P<FT>::sb_pdf_c* pdf, const typename P<FT>::vel_stokes* vel) {
-    CloudVel<FT> f{};
+template <class FT, class PDF, class VEL> RainVelSB make_rain_vel_sb(const PDF* pdf, const VEL* vel) {
+    RainVelSB f{};
     if (!pdf || !vel) return f;
-    f.pdf_c = *pdf;
-    f.vel = *vel;
-    const FT pi = FT(3.141592653589793238462643383279502884L);
-    const FT t = FT(6) / vel->rho_w / pi;
-    f.pref0 = FT(1.0 / 18) * std::cbrt(t * t) * vel->grav / vel->nu_air;
-    const FT z = (pdf->nu_c + 1) / pdf->mu_c;
-    f.gratio[0] = std::tgamma((pdf->nu_c + 1 + FT(2.0 / 3)) / pdf->mu_c) / std::tgamma(z);
-    f.gratio[1] = std::tgamma((pdf->nu_c + 1 + FT(5.0 / 3)) / pdf->mu_c) / std::tgamma(z);
+    widen(*pdf, f.pdf_r);
+    widen(*vel, f.vel);
+    f.pi_rho_w = kPi * f.pdf_r.rho_w;
+    f.eps = method_eps<FT>();
+    return f;
+}
+template <class FT, class PDF, class VEL> RainVelChen make_rain_vel_chen(const PDF* pdf, const VEL* vel) {
+    RainVelChen f{};
+    if (!pdf || !vel) return f;
+    widen(*pdf, f.pdf_r);
+    widen(*vel, f.vel);
+    f.pi_rho_w = kPi * f.pdf_r.rho_w;
+    f.eps = method_eps<FT>();
+    return f;
+}
+template <class FT, class PDF, class VEL> CloudVel make_cloud_vel(const PDF* pdf, const VEL* vel) {
+    CloudVel f{};
+    if (!pdf || !vel) return f;
+    widen(*pdf, f.pdf_c);
+    widen(*vel, f.vel);
+    const D t = 6.0 / f.vel.rho_w / kPi;
+    f.pref0 = (1.0 / 18) * std::cbrt(t * t) * f.vel.grav / f.vel.nu_air;
+    const D nu = f.pdf_c.nu_c, mu = f.pdf_c.mu_c;
+    const D z = (nu + 1) / mu;
+    f.gratio[0] = std::tgamma((nu + 1 + D(2.0 / 3)) / mu) / std::tgamma(z);
+    f.gratio[1] = std::tgamma((nu + 1 + D(5.0 / 3)) / mu) / std::tgamma(z);
+    f.eps = method_eps<FT>();
     return f;
 }
 
@@ -215,23 +245,20 @@ extern "C" {
     int cumicro_termvel_2m_rain_sb_##SUF(const cumicro_sb_pdf_r_##SUF* pdf_r, const cumicro_vel_sb2006_##SUF* vel,      \
                                          int64_t n, const FT* q_rai, const FT* rho, const FT* N_rai, FT* vt0, FT* vt1, \
                                          void* stream) {                                                               \
-        RainVelSB<FT> f{};                                                                                             \
-        if (pdf_r && vel) f = RainVelSB<FT>{*pdf_r, *vel, pi_rho_w_of<FT>(pdf_r)};                                     \
-        return termvel_impl<FT>(pdf_r, vel, f, n, q_rai, rho, N_rai, vt0, vt1, stream, "termvel_2m_rain_sb launch");   \
+        return termvel_impl<FT>(pdf_r, vel, make_rain_vel_sb<FT>(pdf_r, vel), n, q_rai, rho, N_rai, vt0, vt1, stream,  \
+                                "termvel_2m_rain_sb launch");                                                          \
     }                                                                                                                  \
     int cumicro_termvel_2m_rain_chen_##SUF(const cumicro_sb_pdf_r_##SUF* pdf_r,                                         \
                                            const cumicro_vel_chen_rain_##SUF* vel, int64_t n, const FT* q_rai,         \
                                            const FT* rho, const FT* N_rai, FT* vt0, FT* vt1, void* stream) {           \
-        RainVelChen<FT> f{};                                                                                           \
-        if (pdf_r && vel) f = RainVelChen<FT>{*pdf_r, *vel, pi_rho_w_of<FT>(pdf_r)};                                   \
-        return termvel_impl<FT>(pdf_r, vel, f, n, q_rai, rho, N_rai, vt0, vt1, stream,                                 \
-                                "termvel_2m_rain_chen launch");                                                        \
+        return termvel_impl<FT>(pdf_r, vel, make_rain_vel_chen<FT>(pdf_r, vel), n, q_rai, rho, N_rai, vt0, vt1,       \
+                                stream, "termvel_2m_rain_chen launch");                                                \
     }                                                                                                                  \
     int cumicro_termvel_2m_cloud_##SUF(const cumicro_sb_pdf_c_##SUF* pdf_c, const cumicro_vel_stokes_##SUF* vel,        \
                                        int64_t n, const FT* q_lcl, const FT* rho, const FT* N_lcl, FT* vt0, FT* vt1,   \
                                        void* stream) {                                                                 \
-        CloudVel<FT> f = make_cloud_vel<FT>(pdf_c, vel);                                                               \
-        return termvel_impl<FT>(pdf_c, vel, f, n, q_lcl, rho, N_lcl, vt0, vt1, stream, "termvel_2m_cloud launch");     \
+        return termvel_impl<FT>(pdf_c, vel, make_cloud_vel<FT>(pdf_c, vel), n, q_lcl, rho, N_lcl, vt0, vt1, stream,   \
+                                "termvel_2m_cloud launch");                                                            \
     }
 
 CUMICRO_DEF_2M(f64, double)

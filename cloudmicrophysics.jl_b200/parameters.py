@@ -98,6 +98,81 @@ DEFAULTS = {
     "Chen2022_table_B1_c1_coeff": 0.0,
     "Chen2022_table_B1_c2_coeff": 0.184325,
     "Chen2022_table_B1_c3_coeff": 0.184325,
+    # --- Chen 2022, Tables B3 (small ice) and B5 (large ice); tuple order as consumed by CO:304-349
+    "Chen2022_table_B3_As": (-0.263503, 0.00174079, 0.0378769),
+    "Chen2022_table_B3_Bs": (0.575231, 0.0909307, 0.515579),
+    "Chen2022_table_B3_Cs": (-0.345387, 0.177362, -0.000427794, 0.00419647),
+    "Chen2022_table_B3_Es": (-0.156593, 0.0189334, 0.1377817),
+    "Chen2022_table_B3_Fs": (-3.35641, 0.0156199, 0.765337),
+    "Chen2022_table_B3_Gs": (-0.0309715, 1.55054, 0.518349),
+    "Chen2022_ice_cutoff": 625e-6,
+    "Chen2022_table_B5_Al": (-0.475897, -0.00231270, 1.12293),
+    "Chen2022_table_B5_Bl": (-2.56289, -0.00513504, 0.608459),
+    "Chen2022_table_B5_Cl": (-0.756064, 0.935922, -1.70952),
+    "Chen2022_table_B5_El": (0.00639847, 0.00906454, -0.108232),
+    "Chen2022_table_B5_Fl": (0.515453, -0.0725042, -1.86810e19),
+    "Chen2022_table_B5_Gl": (2.65236, 0.00158269, 259.935),
+    "Chen2022_table_B5_Hl": (-0.346044, -7.17829e-11, -1.24394e20),
+    # --- 1-moment scheme (docs/src/Microphysics1M.md tables)
+    "liquid_cloud_effective_radius": 14e-6,
+    "cloud_liquid_sedimentation_number_concentration": 5e8,
+    "cloud_ice_apparent_density": 500.0,
+    "cloud_ice_size_distribution_coefficient_n0": 2e7,
+    "ice_cloud_effective_radius": 25e-6,
+    "cloud_ice_sedimentation_number_concentration": 5e8,
+    "cloud_ice_crystals_length_scale": 1e-5,
+    "cloud_ice_mass_size_relation_coefficient_me": 3.0,
+    "cloud_ice_mass_size_relation_coefficient_delm": 0.0,
+    "cloud_ice_mass_size_relation_coefficient_chim": 1.0,
+    "rain_drop_size_distribution_coefficient_n0": 16e6,
+    "rain_ventilation_coefficient_a": 1.5,
+    "rain_ventilation_coefficient_b": 0.53,
+    "rain_drop_length_scale": 1e-3,
+    "rain_mass_size_relation_coefficient_me": 3.0,
+    "rain_mass_size_relation_coefficient_delm": 0.0,
+    "rain_mass_size_relation_coefficient_chim": 1.0,
+    "rain_cross_section_size_relation_coefficient_ae": 2.0,
+    "rain_cross_section_size_relation_coefficient_dela": 0.0,
+    "rain_cross_section_size_relation_coefficient_chia": 1.0,
+    "snow_apparent_density": 100.0,
+    "snow_flake_size_distribution_coefficient_mu": 4.36e9,
+    "snow_flake_size_distribution_coefficient_nu": 0.63,
+    "snow_ventilation_coefficient_a": 0.65,
+    "snow_ventilation_coefficient_b": 0.44,
+    "snow_aspect_ratio": 0.15,
+    "snow_aspect_ratio_coefficient": 1.0 / 3.0,
+    "snow_flake_length_scale": 1e-3,
+    "snow_mass_size_relation_coefficient_me": 2.0,
+    "snow_mass_size_relation_coefficient_delm": 0.0,
+    "snow_mass_size_relation_coefficient_chim": 1.0,
+    "snow_cross_section_size_relation_coefficient": 2.0,
+    "snow_cross_section_size_relation_coefficient_dela": 0.0,
+    "snow_cross_section_size_relation_coefficient_chia": 1.0,
+    "rain_terminal_velocity_size_relation_coefficient_ve": 0.5,
+    "rain_terminal_velocity_size_relation_coefficient_delv": 0.0,
+    "rain_terminal_velocity_size_relation_coefficient_chiv": 1.0,
+    "rain_drop_drag_coefficient": 0.55,
+    "snow_terminal_velocity_size_relation_coefficient": 0.25,
+    "snow_terminal_velocity_size_relation_coefficient_delv": 0.0,
+    "snow_terminal_velocity_size_relation_coefficient_chiv": 1.0,
+    "rain_autoconversion_timescale": 1e3,
+    "cloud_liquid_water_specific_humidity_autoconversion_threshold": 5e-4,
+    "threshold_smooth_transition_steepness": 2.0,     # not pinned by any reference test
+    "snow_autoconversion_timescale": 1e2,
+    "cloud_ice_specific_humidity_autoconversion_threshold": 1e-6,
+    "ice_snow_threshold_radius": 62.5e-6,
+    "Variable_time_scale_autoconversion_coeff_alpha": 1.0,
+    "prescribed_cloud_droplet_number_concentration": 1e8,
+    "cloud_liquid_rain_collision_efficiency": 0.8,
+    "cloud_liquid_snow_collision_efficiency": 0.1,
+    "cloud_ice_rain_collision_efficiency": 1.0,
+    "cloud_ice_snow_collision_efficiency": 0.1,
+    "rain_snow_collision_efficiency": 1.0,
+    "rain_snow_velocity_dispersion_coefficient": 0.2,  # back-solved (exact) from both goldens of test/microphysics1M_tests.jl:380-453
+    # --- Frostenberg et al. 2023 INP concentration (IN:219-253)
+    "Frostenberg2023_standard_deviation": 1.37,         # sigma: not pinned (mean golden is sigma-independent)
+    "Frostenberg2023_a_coefficient": 1.0,
+    "Frostenberg2023_b_coefficient": 1.0,
 }
 
 # CMP/toml/SB2006_limiters.toml:1-11 — the override file the reference's CPU unit
@@ -132,7 +207,10 @@ class ParamDict:
             self.values.update(overrides)
 
     def __getitem__(self, name):
-        return self.FT(self.values[name])
+        v = self.values[name]
+        if isinstance(v, (tuple, list)):
+            return [self.FT(x) for x in v]
+        return self.FT(v)
 
     @property
     def suffix(self):
@@ -345,3 +423,232 @@ def pack_2m_warm(mp: Microphysics2MParams_, tps):
         tps=tps, sb=wr.seifert_beheng, aps=wr.air_properties,
         condevap_tau_relax=wr.condevap_tau_relax, subdep_tau_relax=wr.subdep_tau_relax,
     )
+
+
+def Chen2022VelTypeSmallIce(FT=np.float64, overrides=None):
+    """CMP.Chen2022VelTypeSmallIce (TerminalVelocity.jl, Table B3)."""
+    td = _td(FT, overrides)
+    return _abi.struct("vel_chen_small_ice", td.suffix)(
+        A=td["Chen2022_table_B3_As"], B=td["Chen2022_table_B3_Bs"], C=td["Chen2022_table_B3_Cs"],
+        E=td["Chen2022_table_B3_Es"], F=td["Chen2022_table_B3_Fs"], G=td["Chen2022_table_B3_Gs"],
+        cutoff=td["Chen2022_ice_cutoff"])
+
+
+def Chen2022VelTypeLargeIce(FT=np.float64, overrides=None):
+    """CMP.Chen2022VelTypeLargeIce (TerminalVelocity.jl, Table B5)."""
+    td = _td(FT, overrides)
+    return _abi.struct("vel_chen_large_ice", td.suffix)(
+        A=td["Chen2022_table_B5_Al"], B=td["Chen2022_table_B5_Bl"], C=td["Chen2022_table_B5_Cl"],
+        E=td["Chen2022_table_B5_El"], F=td["Chen2022_table_B5_Fl"], G=td["Chen2022_table_B5_Gl"],
+        H=td["Chen2022_table_B5_Hl"], cutoff=td["Chen2022_ice_cutoff"])
+
+
+# ============================ 1-moment scheme ==========================================
+# Process options (CMP/Microphysics1MOptions.jl:62-152): singleton classes, `None` disables.
+class _Option:
+    code = 1
+
+    def __repr__(self):
+        return type(self).__name__ + "()"
+
+
+class CloudLiquidFormation(_Option): pass
+class ConstantTimescale(_Option): pass
+class TemperatureDependent(_Option): code = 2
+class Kessler1M(_Option): pass
+class PrescribedNd(_Option): code = 2
+class NoSupersaturation(_Option): pass
+class WithSupersaturation(_Option): code = 2
+class CloudLiquidRainAccretion(_Option): pass
+class CloudLiquidSnowAccretion(_Option): pass
+class CloudIceRainAccretion(_Option): pass
+class CloudIceSnowAccretion(_Option): pass
+class RainSnowAccretion(_Option): pass
+class SublimationOnly(_Option): pass
+class DepositionAndSublimation(_Option): code = 2
+class RainEvaporation(_Option): pass
+class CloudIceMelt(_Option): pass
+class SnowMelt(_Option): pass
+
+
+_OPTION_SLOTS = {   # slot -> (default, allowed classes)   Microphysics1MOptions.jl:169-198
+    "cloud_liquid_formation": (CloudLiquidFormation, (CloudLiquidFormation,)),
+    "cloud_ice_formation": (ConstantTimescale, (ConstantTimescale, TemperatureDependent)),
+    "cloud_ice_melt": (CloudIceMelt, (CloudIceMelt,)),
+    "rain_autoconversion": (Kessler1M, (Kessler1M, PrescribedNd)),
+    "snow_autoconversion": (NoSupersaturation, (NoSupersaturation, WithSupersaturation)),
+    "rain_condensation_evaporation": (RainEvaporation, (RainEvaporation,)),
+    "snow_deposition_sublimation": (DepositionAndSublimation, (SublimationOnly, DepositionAndSublimation)),
+    "snow_melt": (SnowMelt, (SnowMelt,)),
+    "cloud_liquid_rain_accretion": (CloudLiquidRainAccretion, (CloudLiquidRainAccretion,)),
+    "cloud_liquid_snow_accretion": (CloudLiquidSnowAccretion, (CloudLiquidSnowAccretion,)),
+    "cloud_ice_rain_accretion": (CloudIceRainAccretion, (CloudIceRainAccretion,)),
+    "cloud_ice_snow_accretion": (CloudIceSnowAccretion, (CloudIceSnowAccretion,)),
+    "rain_snow_accretion": (RainSnowAccretion, (RainSnowAccretion,)),
+}
+_UNSET = object()
+
+
+def Microphysics1MOptions(**kw):
+    """CMP.Microphysics1MOptions(; kwargs...): dict slot -> option instance or None."""
+    unknown = set(kw) - set(_OPTION_SLOTS)
+    if unknown:
+        raise TypeError(f"unknown Microphysics1MOptions fields: {sorted(unknown)}")
+    opts = {}
+    for slot, (default, allowed) in _OPTION_SLOTS.items():
+        v = kw.get(slot, _UNSET)
+        if v is _UNSET:
+            v = default()
+        elif v is not None and not isinstance(v, allowed):
+            raise TypeError(f"{slot}: expected one of {[a.__name__ for a in allowed]} or None, got {v!r}")
+        opts[slot] = v
+    return opts
+
+
+def _particle_mass(td, prefix, m0):
+    F = td.FT
+    me, dm = td[f"{prefix}_mass_size_relation_coefficient_me"], td[f"{prefix}_mass_size_relation_coefficient_delm"]
+    return dict(me=me, dm=dm, chi_m=td[f"{prefix}_mass_size_relation_coefficient_chim"], m0=F(m0),
+                gamma_coeff=_gamma(me + dm + F(1)))
+
+
+def FrostenbergParameters(FT=np.float64, overrides=None):
+    """CMP.Frostenberg2023 (IceNucleation.jl): sigma, a, b, T_freeze, log_a = log(a)."""
+    td = _td(FT, overrides)
+    a = td["Frostenberg2023_a_coefficient"]
+    return _abi.struct("frostenberg2023", td.suffix)(
+        sigma=td["Frostenberg2023_standard_deviation"], a=a, b=td["Frostenberg2023_b_coefficient"],
+        T_freeze=td["temperature_water_freeze"], log_a=td.FT(np.log(a)))
+
+
+@dataclass
+class Microphysics1MParams_:
+    """CMP.Microphysics1MParams (Microphysics1MParams.jl:84-91); `block` is the flattened POD
+    (without tps)."""
+    processes: dict
+    block: Any
+    FT: Any = np.float64
+
+    @property
+    def process_params(self):
+        return self.block.pp
+
+
+def Microphysics1MParams(FT=np.float64, overrides=None, **options):
+    """``CMP.Microphysics1MParams(FT; options_kwargs...)`` (Microphysics1MParams.jl:95-160).
+    Host-side derived constants (m0, a0, the gammas, v0_snow) are computed here in FT
+    arithmetic exactly where the reference's constructors compute them."""
+    td = _td(FT, overrides)
+    F = td.FT
+    suf = td.suffix
+    S = lambda name: _abi.struct(name, suf)
+    pi = F(np.pi)
+    opts = Microphysics1MOptions(**options)
+    blk = S("params_1m")()
+    # cloud
+    blk.cloud_liquid = S("cloud_liquid")(rho_w=td["density_liquid_water"], r_eff=td["liquid_cloud_effective_radius"],
+                                         N_0=td["cloud_liquid_sedimentation_number_concentration"])
+    rho_i_c = td["cloud_ice_apparent_density"]
+    r0c = td["cloud_ice_crystals_length_scale"]
+    mc = _particle_mass(td, "cloud_ice", rho_i_c * r0c ** td["cloud_ice_mass_size_relation_coefficient_me"] * pi * F(4) / F(3))
+    blk.cloud_ice = S("cloud_ice")(n0=td["cloud_ice_size_distribution_coefficient_n0"],
+                                   mass=S("particle_mass")(r0=r0c, **mc), rho_i=rho_i_c,
+                                   r_eff=td["ice_cloud_effective_radius"], N_0=td["cloud_ice_sedimentation_number_concentration"])
+    # rain
+    r0r = td["rain_drop_length_scale"]
+    mr = _particle_mass(td, "rain", td["density_liquid_water"] * r0r ** td["rain_mass_size_relation_coefficient_me"] * pi * F(4) / F(3))
+    aer = td["rain_cross_section_size_relation_coefficient_ae"]
+    blk.rain = S("rain")(n0=td["rain_drop_size_distribution_coefficient_n0"], mass=S("particle_mass")(r0=r0r, **mr),
+                         area=S("particle_area")(a0=pi * r0r ** aer, ae=aer,
+                                                 da=td["rain_cross_section_size_relation_coefficient_dela"],
+                                                 chi_a=td["rain_cross_section_size_relation_coefficient_chia"]),
+                         vent=S("ventilation")(a=td["rain_ventilation_coefficient_a"], b=td["rain_ventilation_coefficient_b"]))
+    # snow
+    r0s = td["snow_flake_length_scale"]
+    mes = td["snow_mass_size_relation_coefficient_me"]
+    ms = _particle_mass(td, "snow", r0s ** mes / F(10))
+    aes = td["snow_cross_section_size_relation_coefficient"]
+    das = td["snow_cross_section_size_relation_coefficient_dela"]
+    alpha_obl = ms["me"] + ms["dm"] - F(1.5) * (aes + das)
+    alpha_pro = F(3) * (aes + das) - F(2) * (ms["me"] + ms["dm"])
+    blk.snow = S("snow")(mu=td["snow_flake_size_distribution_coefficient_mu"], nu=td["snow_flake_size_distribution_coefficient_nu"],
+                         mass=S("particle_mass")(r0=r0s, **ms),
+                         area=S("particle_area")(a0=F(0.3 * float(pi) * float(r0s) ** float(aes)), ae=aes, da=das,
+                                                 chi_a=td["snow_cross_section_size_relation_coefficient_chia"]),
+                         vent=S("ventilation")(a=td["snow_ventilation_coefficient_a"], b=td["snow_ventilation_coefficient_b"]),
+                         aspr_phi=td["snow_aspect_ratio"], aspr_kappa=td["snow_aspect_ratio_coefficient"],
+                         rho_i=td["snow_apparent_density"],
+                         gamma_aspect_oblate=_gamma(alpha_obl + F(4)) / _gamma(F(4)),
+                         gamma_aspect_prolate=_gamma(alpha_pro + F(4)) / _gamma(F(4)))
+    blk.aps = AirProperties(td)
+    # terminal velocity (TerminalVelocity.jl:33-62, 88-117); note r0 of BOTH is snow_flake_length_scale
+    ver, dvr = td["rain_terminal_velocity_size_relation_coefficient_ve"], td["rain_terminal_velocity_size_relation_coefficient_delv"]
+    blk.vel_rain = S("vel_blk1m_rain")(
+        r0=r0s, ve=ver, dv=dvr, chi_v=td["rain_terminal_velocity_size_relation_coefficient_chiv"],
+        rho_w=td["density_liquid_water"], C_drag=td["rain_drop_drag_coefficient"], grav=td["gravitational_acceleration"],
+        gamma_vent=_gamma((ver + dvr + F(5)) / F(2)),
+        gamma_term=_gamma(mr["me"] + ver + mr["dm"] + dvr + F(1)),
+        gamma_accr=_gamma(aer + ver + blk.rain.area.da + dvr + F(1)),
+        gamma_accr_rain_sink=_gamma(mr["me"] + aer + ver + mr["dm"] + blk.rain.area.da + dvr + F(1)))
+    ves, dvs = td["snow_terminal_velocity_size_relation_coefficient"], td["snow_terminal_velocity_size_relation_coefficient_delv"]
+    blk.vel_snow = S("vel_blk1m_snow")(
+        r0=r0s, ve=ves, dv=dvs, chi_v=td["snow_terminal_velocity_size_relation_coefficient_chiv"],
+        v0=F(2 ** (9 / 4) * float(r0s) ** float(ves)),
+        gamma_vent=_gamma((ves + dvs + F(5)) / F(2)),
+        gamma_term=_gamma(ms["me"] + ves + ms["dm"] + dvs + F(1)),
+        gamma_accr=_gamma(aes + ves + das + dvs + F(1)))
+    # process parameters (Microphysics1MOptions.jl:207-396)
+    pp = S("process_params_1m")(
+        cloud_liquid_tau_relax=td["condensation_evaporation_timescale"],
+        cloud_ice_tau_relax=td["sublimation_deposition_timescale"],
+        frostenberg=FrostenbergParameters(td),
+        rain_acnv_tau=td["rain_autoconversion_timescale"],
+        rain_acnv_q_threshold=td["cloud_liquid_water_specific_humidity_autoconversion_threshold"],
+        rain_acnv_k=td["threshold_smooth_transition_steepness"],
+        rain_acnv_alpha=td["Variable_time_scale_autoconversion_coeff_alpha"],
+        rain_acnv_Nc=td["prescribed_cloud_droplet_number_concentration"],
+        snow_acnv_tau=td["snow_autoconversion_timescale"],
+        snow_acnv_q_threshold=td["cloud_ice_specific_humidity_autoconversion_threshold"],
+        snow_acnv_k=td["threshold_smooth_transition_steepness"],
+        snow_acnv_r_ice_snow=td["ice_snow_threshold_radius"],
+        e_lcl_rai=td["cloud_liquid_rain_collision_efficiency"], e_lcl_sno=td["cloud_liquid_snow_collision_efficiency"],
+        e_icl_rai=td["cloud_ice_rain_collision_efficiency"], e_icl_sno=td["cloud_ice_snow_collision_efficiency"],
+        e_rai_sno=td["rain_snow_collision_efficiency"], coeff_disp=td["rain_snow_velocity_dispersion_coefficient"])
+    blk.pp = pp
+    blk.processes = S("options_1m")(**{k: (0 if v is None else v.code) for k, v in opts.items()})
+    return Microphysics1MParams_(processes=opts, block=blk, FT=td.FT)
+
+
+def pack_1m(mp: Microphysics1MParams_, tps):
+    """Flatten (mp, tps) into cumicro_params_1m (what the Julia extension's packer does)."""
+    suf = suffix(mp.FT)
+    if type(tps) is not _abi.struct("thermo", suf):
+        raise TypeError("tps float type does not match mp")
+    blk = mp.block.copy()
+    blk.tps = tps
+    return blk
+
+
+def widen(block):
+    """Float32 parameter block -> the Float64 block with exactly the same values (what the
+    library does internally for the Float32 methods; tests use it to build the reference)."""
+    name = type(block).__name__
+    if name.endswith("_f64"):
+        return block.copy()
+    cls = _abi.STRUCTS[name[:-4] + "_f64"]
+
+    def conv(src, dst):
+        import ctypes as C
+        for fname, _ in src._fields_:
+            v = getattr(src, fname)
+            if isinstance(v, _abi._Block):
+                conv(v, getattr(dst, fname))
+            elif isinstance(v, C.Array):
+                d = getattr(dst, fname)
+                for i, x in enumerate(v):
+                    d[i] = x
+            else:
+                setattr(dst, fname, v)
+    out = cls()
+    conv(block, out)
+    return out

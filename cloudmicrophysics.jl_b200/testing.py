@@ -216,3 +216,26 @@ def ulp_error_f32(got, truth64):
     t32 = np.abs(truth64.astype(np.float32))
     ulp = np.spacing(np.maximum(t32, np.finfo(np.float32).tiny)).astype(np.float64)
     return np.abs(got - truth64) / ulp
+
+
+def assert_f32_method(name, got32, ref32, truth64, bound64=None, max_ulps=F32_ULPS):
+    """Float32 method criterion: every output within ``max_ulps`` Float32
+    ULPs of the true value (the Float64 reference evaluated on the same Float32 inputs and
+    parameters), except where the reference algorithm's own Float64 rounding bound already
+    exceeds one Float32 ULP; exact zeros / non-finite values coincide with the Float32
+    reference's (its regime selection)."""
+    got32 = np.asarray(got32)
+    assert got32.dtype == np.float32, name
+    ref32 = np.asarray(ref32)
+    fin = np.isfinite(ref32)
+    assert np.array_equal(np.isfinite(got32), fin), (name, "non-finite pattern differs")
+    assert np.array_equal((got32 == 0)[fin], (ref32 == 0)[fin]), (name, "zero (regime) pattern differs",
+                                                                     int(np.sum((got32 == 0)[fin] != (ref32 == 0)[fin])))
+    err = ulp_error_f32(got32[fin], np.asarray(truth64)[fin])
+    if bound64 is not None:
+        t32 = np.abs(np.asarray(truth64, dtype=np.float64)[fin].astype(np.float32))
+        ulp = np.spacing(np.maximum(t32, np.finfo(np.float32).tiny)).astype(np.float64)
+        err = np.where(8 * np.abs(np.asarray(bound64)[fin]) > ulp, 0.0, err)
+    worst = float(err.max()) if err.size else 0.0
+    assert worst <= max_ulps, (name, "max Float32 ULP error", worst, "at", int(np.argmax(err)))
+    return worst

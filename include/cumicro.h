@@ -45,6 +45,20 @@ extern "C" {
 #define CUMICRO_E_NODEVICE (-4)  /* no CUDA device / driver */
 #define CUMICRO_E_ARG (-5)       /* other invalid argument */
 
+/* Option values of cumicro_options_1m_* (one slot per process; see cumicro_params.inc). */
+enum {
+    CUMICRO_1M_OFF = 0,
+    CUMICRO_1M_CLOUD_ICE_CONSTANT_TIMESCALE = 1, /* ConstantTimescale */
+    CUMICRO_1M_CLOUD_ICE_TEMPERATURE_DEPENDENT = 2, /* TemperatureDependent */
+    CUMICRO_1M_RAIN_ACNV_KESSLER = 1, /* Kessler1M */
+    CUMICRO_1M_RAIN_ACNV_PRESCRIBED_ND = 2, /* PrescribedNd */
+    CUMICRO_1M_SNOW_ACNV_NO_SUPERSAT = 1, /* NoSupersaturation */
+    CUMICRO_1M_SNOW_ACNV_WITH_SUPERSAT = 2, /* WithSupersaturation */
+    CUMICRO_1M_SNOW_SUBLIMATION_ONLY = 1, /* SublimationOnly */
+    CUMICRO_1M_SNOW_DEPOSITION_AND_SUBLIMATION = 2, /* DepositionAndSublimation */
+    CUMICRO_1M_ON = 1
+};
+
 #define CUMICRO_FT double
 #define CUMICRO_T(x) x##_f64
 #include "cumicro_params.inc"
@@ -183,6 +197,59 @@ int cumicro_termvel_2m_cloud_f32(const cumicro_sb_pdf_c_f32* pdf_c,
                                  const cumicro_vel_stokes_f32* vel, int64_t n,
                                  const float* q_lcl, const float* rho, const float* N_lcl,
                                  float* vt0, float* vt1, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * 1-moment scheme.  Input columns: rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno.
+ * out4 = HOST array of 4 device column pointers: dq_lcl_dt, dq_icl_dt, dq_rai_dt, dq_sno_dt.
+ *
+ * cumicro_bmt1m_inst_*    replaces bulk_microphysics_tendencies(::Instantaneous,
+ *                         ::Microphysics1Moment, mp, tps, ...)                    BMT:505-514
+ * cumicro_bmt1m_verbose_* replaces the ::InstantaneousVerbose method              BMT:533-543
+ *                         src18 = HOST array of 18 device column pointers (NULL entries skipped)
+ *                         in the field order of _microphysics_source_terms       BMT:206-216:
+ *                         S_phase_change_vap_lcl, S_phase_change_vap_icl, S_acnv_lcl_rai, S_acnv_icl_sno,
+ *                         S_accr_lcl_rai, S_accr_lcl_sno_cold, S_accr_lcl_sno_warm, S_accr_melt_lcl_sno,
+ *                         S_accr_icl_rai, S_accr_freeze_icl_rai, S_accr_icl_sno, S_accr_rai_sno_cold,
+ *                         S_accr_rai_sno_warm, S_accr_melt_rai_sno, S_phase_change_vap_rai,
+ *                         S_phase_change_vap_sno, S_melt_icl_lcl, S_melt_sno_rai
+ * cumicro_bmt1m_linavg_*  replaces the ::LinearizedAverage method (dt, nsub)       BMT:572-632
+ * ------------------------------------------------------------------------- */
+#define CUMICRO_1M_NSRC 18
+int cumicro_bmt1m_inst_f64(const cumicro_params_1m_f64* p, int64_t n, const double* rho, const double* T,
+                           const double* q_tot, const double* q_lcl, const double* q_icl,
+                           const double* q_rai, const double* q_sno, double* const* out4, void* stream);
+int cumicro_bmt1m_inst_f32(const cumicro_params_1m_f32* p, int64_t n, const float* rho, const float* T,
+                           const float* q_tot, const float* q_lcl, const float* q_icl,
+                           const float* q_rai, const float* q_sno, float* const* out4, void* stream);
+int cumicro_bmt1m_verbose_f64(const cumicro_params_1m_f64* p, int64_t n, const double* rho, const double* T,
+                              const double* q_tot, const double* q_lcl, const double* q_icl,
+                              const double* q_rai, const double* q_sno, double* const* out4,
+                              double* const* src18, void* stream);
+int cumicro_bmt1m_verbose_f32(const cumicro_params_1m_f32* p, int64_t n, const float* rho, const float* T,
+                              const float* q_tot, const float* q_lcl, const float* q_icl,
+                              const float* q_rai, const float* q_sno, float* const* out4,
+                              float* const* src18, void* stream);
+int cumicro_bmt1m_linavg_f64(const cumicro_params_1m_f64* p, int64_t n, const double* rho, const double* T,
+                             const double* q_tot, const double* q_lcl, const double* q_icl,
+                             const double* q_rai, const double* q_sno, double dt, int nsub,
+                             double* const* out4, void* stream);
+int cumicro_bmt1m_linavg_f32(const cumicro_params_1m_f32* p, int64_t n, const float* rho, const float* T,
+                             const float* q_tot, const float* q_lcl, const float* q_icl,
+                             const float* q_rai, const float* q_sno, float dt, int nsub,
+                             float* const* out4, void* stream);
+
+/* Terminal velocities of the 1-moment and non-equilibrium schemes, (rho, q) -> v [m/s].
+ * kind 0: CM1.terminal_velocity(::Rain, ::Blk1MVelTypeRain, rho, q)              CM1:240-249
+ *      1: CM1.terminal_velocity(::Snow, ::Blk1MVelTypeSnow, rho, q)
+ *      2: CM1.terminal_velocity(::Rain, ::Chen2022VelTypeRain, rho, q)           CM1:251-270  (vel = cumicro_vel_chen_rain_*)
+ *      3: CM1.terminal_velocity(::Snow, ::Chen2022VelTypeLargeIce, rho, q)       CM1:272-291  (vel = cumicro_vel_chen_large_ice_*)
+ *      4: NEQ.terminal_velocity(::CloudLiquid, ::StokesRegimeVelType, rho, q)    NEQ:250-262  (vel = cumicro_vel_stokes_*)
+ *      5: NEQ.terminal_velocity(::CloudIce, ::Chen2022VelTypeSmallIce, rho, q)   NEQ:264-281  (vel = cumicro_vel_chen_small_ice_*)
+ * `vel` may be NULL for kinds 0 and 1 (the Blk1M parameters are part of `p`). */
+int cumicro_termvel_1m_f64(const cumicro_params_1m_f64* p, const void* vel, int kind, int64_t n,
+                           const double* rho, const double* q, double* out, void* stream);
+int cumicro_termvel_1m_f32(const cumicro_params_1m_f32* p, const void* vel, int kind, int64_t n,
+                           const float* rho, const float* q, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,17 @@ def set_num_threads(n: int):
     lib().oracle_set_num_threads(int(n))
 
 
+class f32_thresholds:
+    """Context manager: Float64 evaluations use the Float32 method's thresholds, i.e. they
+    compute the true value of the Float32 method (regimes of Float32, exact arithmetic)."""
+
+    def __enter__(self):
+        lib().oracle_set_f32_thresholds(1)
+
+    def __exit__(self, *a):
+        lib().oracle_set_f32_thresholds(0)
+
+
 def _suf(dtype):
     return {"float64": "f64", "float32": "f32"}[np.dtype(dtype).name]
 
@@ -128,3 +139,49 @@ def termvel_2m_rain_chen(pdf_r, vel, q, rho, N):
 
 def termvel_2m_cloud(pdf_c, vel, q, rho, N):
     return _termvel("termvel_2m_cloud", pdf_c, vel, q, rho, N)
+
+
+# ---- 1-moment scheme ---------------------------------------------------------------------
+SRC_1M = ("S_phase_change_vap_lcl", "S_phase_change_vap_icl", "S_acnv_lcl_rai", "S_acnv_icl_sno", "S_accr_lcl_rai",
+          "S_accr_lcl_sno_cold", "S_accr_lcl_sno_warm", "S_accr_melt_lcl_sno", "S_accr_icl_rai", "S_accr_freeze_icl_rai",
+          "S_accr_icl_sno", "S_accr_rai_sno_cold", "S_accr_rai_sno_warm", "S_accr_melt_rai_sno", "S_phase_change_vap_rai",
+          "S_phase_change_vap_sno", "S_melt_icl_lcl", "S_melt_sno_rai")
+OUT_1M = ("dq_lcl_dt", "dq_icl_dt", "dq_rai_dt", "dq_sno_dt")
+MODES_1M = {"instantaneous": 0, "verbose": 1, "linearized_average": 2}
+
+
+def bmt1m(params, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, mode="instantaneous", dt=0.0, nsub=1, bound=False):
+    """BMT:505-632 over arrays.  mode in MODES_1M; ``bound=True`` returns the rounding-error
+    bounds of the reference algorithm (Float64 only) instead of the values."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    cols, n = _cols((rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno), dtype)
+    out = {k: np.empty(n, dtype) for k in OUT_1M}
+    o4 = (C.c_void_p * 4)(*[_ptr(out[k]) for k in OUT_1M])
+    m = MODES_1M[mode]
+    s18 = None
+    if m == 1:
+        for k in SRC_1M:
+            out[k] = np.empty(n, dtype)
+        s18 = (C.c_void_p * 18)(*[_ptr(out[k]) for k in SRC_1M])
+    if bound:
+        assert dtype == np.float64
+        fn = lib().oracle_bmt1m_bound_f64
+    else:
+        fn = getattr(lib(), f"oracle_bmt1m_{_suf(dtype)}")
+    cdt = C.c_double(dt) if dtype == np.float64 else C.c_float(dt)
+    st = fn(C.byref(params), C.c_int(m), C.c_int64(n), *[_ptr(a) for a in cols], cdt, C.c_int(nsub), o4, s18)
+    assert st == 0
+    return out
+
+
+TERMVEL_1M = {"rain_blk1m": 0, "snow_blk1m": 1, "rain_chen": 2, "snow_chen": 3, "cloud_liquid_stokes": 4, "cloud_ice_chen": 5}
+
+
+def termvel_1m(params, kind, rho, q, vel=None, bound=False):
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    (rho, q), n = _cols((rho, q), dtype)
+    out = np.empty(n, dtype)
+    fn = lib().oracle_termvel_1m_bound_f64 if bound else getattr(lib(), f"oracle_termvel_1m_{_suf(dtype)}")
+    st = fn(C.byref(params), C.byref(vel) if vel is not None else None, C.c_int(TERMVEL_1M[kind]), C.c_int64(n), _ptr(rho), _ptr(q), _ptr(out))
+    assert st == 0
+    return out

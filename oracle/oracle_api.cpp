@@ -4,7 +4,7 @@
 // multithreaded driver of its own; hosts broadcast the scalar methods).
 #include <omp.h>
 
-#include "oracle_2m.hpp"
+#include "oracle_1m.hpp"
 
 using namespace orc;
 
@@ -12,6 +12,8 @@ extern "C" {
 
 int oracle_num_threads(void) { return omp_get_max_threads(); }
 void oracle_set_num_threads(int n) { omp_set_num_threads(n); }
+// 1: Float64 / error-bound evaluations use the Float32 method's thresholds (oracle_base.hpp)
+void oracle_set_f32_thresholds(int on) { f32_thresholds() = (on != 0); }
 
 #define DEF_BMT2M_WARM(SUF, FT)                                                                      \
     int oracle_bmt2m_warm_##SUF(const cumicro_params_2m_warm_##SUF* p, int64_t n, const FT* rho,     \
@@ -95,5 +97,95 @@ DEF_TERMVEL_BOUND(termvel_2m_cloud, cumicro_sb_pdf_c_f64, cumicro_vel_stokes_f64
     }
 DEF_TERMVEL_2M(f64, double)
 DEF_TERMVEL_2M(f32, float)
+
+// ---- 1-moment scheme ------------------------------------------------------------------------
+// mode: 0 Instantaneous (out4), 1 InstantaneousVerbose (out4 + src18), 2 LinearizedAverage (out4; dt, nsub)
+#define DEF_BMT1M(SUF, FT)                                                                                         \
+    int oracle_bmt1m_##SUF(const cumicro_params_1m_##SUF* p, int mode, int64_t n, const FT* rho, const FT* T,      \
+                           const FT* q_tot, const FT* q_lcl, const FT* q_icl, const FT* q_rai, const FT* q_sno,    \
+                           FT dt, int nsub, FT* const* out4, FT* const* src18) {                                   \
+        _Pragma("omp parallel for schedule(static)") for (int64_t i = 0; i < n; ++i) {                             \
+            FT o[4];                                                                                               \
+            if (mode == 2) {                                                                                       \
+                bmt1m_linearized_average<FT>(*p, rho[i], T[i], q_tot[i], q_lcl[i], q_icl[i], q_rai[i], q_sno[i],   \
+                                             dt, nsub, o);                                                         \
+            } else {                                                                                               \
+                Src1M<FT> r = microphysics_source_terms_1m<FT>(*p, rho[i], T[i], q_tot[i], q_lcl[i], q_icl[i],     \
+                                                               q_rai[i], q_sno[i]);                                \
+                aggregate_tendencies_1m<FT>(r, o);                                                                 \
+                if (src18)                                                                                         \
+                    for (int k = 0; k < S1M_NSRC; ++k)                                                             \
+                        if (src18[k]) src18[k][i] = r.s[k];                                                        \
+            }                                                                                                      \
+            for (int k = 0; k < 4; ++k)                                                                            \
+                if (out4 && out4[k]) out4[k][i] = o[k];                                                            \
+        }                                                                                                          \
+        return 0;                                                                                                  \
+    }
+DEF_BMT1M(f64, double)
+DEF_BMT1M(f32, float)
+
+int oracle_bmt1m_bound_f64(const cumicro_params_1m_f64* p, int mode, int64_t n, const double* rho, const double* T,
+                           const double* q_tot, const double* q_lcl, const double* q_icl, const double* q_rai,
+                           const double* q_sno, double dt, int nsub, double* const* out4, double* const* src18) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        Tr o[4];
+        if (mode == 2) {
+            bmt1m_linearized_average<Tr>(*p, Tr(rho[i]), Tr(T[i]), Tr(q_tot[i]), Tr(q_lcl[i]), Tr(q_icl[i]), Tr(q_rai[i]),
+                                         Tr(q_sno[i]), Tr(dt), nsub, o);
+        } else {
+            Src1M<Tr> r = microphysics_source_terms_1m<Tr>(*p, Tr(rho[i]), Tr(T[i]), Tr(q_tot[i]), Tr(q_lcl[i]), Tr(q_icl[i]),
+                                                           Tr(q_rai[i]), Tr(q_sno[i]));
+            aggregate_tendencies_1m<Tr>(r, o);
+            if (src18)
+                for (int k = 0; k < S1M_NSRC; ++k)
+                    if (src18[k]) src18[k][i] = r.s[k].e;
+        }
+        for (int k = 0; k < 4; ++k)
+            if (out4 && out4[k]) out4[k][i] = o[k].e;
+    }
+    return 0;
+}
+
+// terminal velocities of the 1-moment / non-equilibrium schemes; kind:
+// 0 rain Blk1M, 1 snow Blk1M, 2 rain Chen2022, 3 snow Chen2022 (large ice), 4 cloud liquid Stokes, 5 cloud ice Chen2022 (small ice)
+#define DEF_TERMVEL_1M(SUF, FT)                                                                                    \
+    int oracle_termvel_1m_##SUF(const cumicro_params_1m_##SUF* p, const void* vel, int kind, int64_t n,            \
+                                const FT* rho, const FT* q, FT* out) {                                             \
+        _Pragma("omp parallel for schedule(static)") for (int64_t i = 0; i < n; ++i) {                             \
+            switch (kind) {                                                                                        \
+                case 0: out[i] = terminal_velocity_1m_rain_blk<FT>(*p, rho[i], q[i]); break;                       \
+                case 1: out[i] = terminal_velocity_1m_snow_blk<FT>(*p, rho[i], q[i]); break;                       \
+                case 2: out[i] = terminal_velocity_1m_rain_chen<FT>(*p, *(const cumicro_vel_chen_rain_##SUF*)vel, rho[i], q[i]); break; \
+                case 3: out[i] = terminal_velocity_1m_snow_chen<FT>(*p, *(const cumicro_vel_chen_large_ice_##SUF*)vel, rho[i], q[i]); break; \
+                case 4: out[i] = terminal_velocity_noneq_liquid<FT>(*p, *(const cumicro_vel_stokes_##SUF*)vel, rho[i], q[i]); break; \
+                case 5: out[i] = terminal_velocity_noneq_ice<FT>(*p, *(const cumicro_vel_chen_small_ice_##SUF*)vel, rho[i], q[i]); break; \
+                default: out[i] = 0;                                                                               \
+            }                                                                                                      \
+        }                                                                                                          \
+        return 0;                                                                                                  \
+    }
+DEF_TERMVEL_1M(f64, double)
+DEF_TERMVEL_1M(f32, float)
+
+int oracle_termvel_1m_bound_f64(const cumicro_params_1m_f64* p, const void* vel, int kind, int64_t n, const double* rho,
+                                const double* q, double* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        Tr r(rho[i]), qq(q[i]), v;
+        switch (kind) {
+            case 0: v = terminal_velocity_1m_rain_blk<Tr>(*p, r, qq); break;
+            case 1: v = terminal_velocity_1m_snow_blk<Tr>(*p, r, qq); break;
+            case 2: v = terminal_velocity_1m_rain_chen<Tr>(*p, *(const cumicro_vel_chen_rain_f64*)vel, r, qq); break;
+            case 3: v = terminal_velocity_1m_snow_chen<Tr>(*p, *(const cumicro_vel_chen_large_ice_f64*)vel, r, qq); break;
+            case 4: v = terminal_velocity_noneq_liquid<Tr>(*p, *(const cumicro_vel_stokes_f64*)vel, r, qq); break;
+            case 5: v = terminal_velocity_noneq_ice<Tr>(*p, *(const cumicro_vel_chen_small_ice_f64*)vel, r, qq); break;
+            default: break;
+        }
+        out[i] = v.e;
+    }
+    return 0;
+}
 
 }  // extern "C"

@@ -92,9 +92,20 @@ inline Tr jmax(Tr a, Tr b) { return (a < b) ? b : a; }
 inline Tr jmin(Tr a, Tr b) { return (b < a) ? b : a; }
 inline Tr jclamp(Tr x, Tr lo, Tr hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }
 inline Tr ifelse(bool c, Tr a, Tr b) { return c ? a : b; }
+// Threshold mode: when set, the Float64 (and Tr) instantiations use the FLOAT32 method's
+// thresholds eps(Float32), ϵ_numerics(Float32).  This evaluates "the Float32 method in exact
+// arithmetic" — the true value a Float32 implementation is judged against (its regime
+// selection is the Float32 reference's, its arithmetic error-free to ~1e-16).
+inline bool& f32_thresholds() {
+    static bool flag = false;
+    return flag;
+}
 template <class FT> inline FT eps() { return std::numeric_limits<FT>::epsilon(); }
 template <class FT> inline FT inf() { return std::numeric_limits<FT>::infinity(); }
-template <> inline Tr eps<Tr>() { return Tr(std::numeric_limits<double>::epsilon()); }
+template <> inline double eps<double>() {
+    return f32_thresholds() ? double(std::numeric_limits<float>::epsilon()) : std::numeric_limits<double>::epsilon();
+}
+template <> inline Tr eps<Tr>() { return Tr(eps<double>()); }
 template <> inline Tr inf<Tr>() { return Tr(std::numeric_limits<double>::infinity()); }
 template <class FT> inline FT pi() { return FT(3.141592653589793238462643383279502884L); }
 

@@ -1,0 +1,188 @@
+"""GPU parity tests of the 1-moment path (BMT:505-632, CM1, NEQ) through the C-ABI vs the CPU
+oracle.  Same criteria as test_gpu_2m.py: Float64 <= 1e-12 relative per output, or (where the
+reference algorithm itself cancels) within 8x the reference's own first-order rounding-error
+bound; exact zeros (gated regimes) must coincide bit for bit."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+KEYS = ("rho", "T", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno")
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "m1_goldens.json")))
+
+
+def _dev(st, cuda):
+    import torch
+    return [torch.from_numpy(st[k]).to(cuda) for k in KEYS]
+
+
+def _call(built, mode, mp, tps, cols, **kw):
+    BMT = built.BMT
+    return BMT.bulk_microphysics_tendencies(mode, BMT.Microphysics1Moment(), mp, tps, *cols, **kw)
+
+
+OPTION_SETS = [
+    {},
+    dict(cloud_ice_formation="TemperatureDependent", rain_autoconversion="PrescribedNd", snow_autoconversion="WithSupersaturation",
+         snow_deposition_sublimation="SublimationOnly"),
+    dict(rain_snow_accretion=None, snow_melt=None, cloud_ice_melt=None, cloud_liquid_formation=None, cloud_ice_rain_accretion=None),
+]
+
+
+def _opts(CMP, d):
+    return {k: (None if v is None else getattr(CMP, v)()) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("optset", range(len(OPTION_SETS)))
+def test_bmt1m_verbose_f64_parity(built, orc, cuda, optset):
+    from cumicro.testing import synthetic_states_1m, assert_parity
+    CMP, BMT = built.CMP, built.BMT
+    n = 1 << 17
+    st = synthetic_states_1m(n, seed=1234 + optset)
+    mp = CMP.Microphysics1MParams(np.float64, **_opts(CMP, OPTION_SETS[optset]))
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk = CMP.pack_1m(mp, tps)
+    out = _call(built, BMT.InstantaneousVerbose(), mp, tps, _dev(st, cuda))
+    ref = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="verbose")
+    bnd = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="verbose", bound=True)
+    for k in orc.OUT_1M + orc.SRC_1M:
+        rep = assert_parity(k, out[k].cpu().numpy(), ref[k], bound=bnd[k])
+        assert rep["max_rel"] <= 1e-12, (k, rep)
+    inst = _call(built, BMT.Instantaneous(), mp, tps, _dev(st, cuda))
+    for k in orc.OUT_1M:
+        assert np.array_equal(inst[k].cpu().numpy(), out[k].cpu().numpy())   # same kernel maths, fewer stores
+
+
+@pytest.mark.parametrize("dt,nsub", [(1.0, 1), (60.0, 1), (300.0, 3)])
+def test_bmt1m_linearized_average_f64_parity(built, orc, cuda, dt, nsub):
+    from cumicro.testing import synthetic_states_1m, assert_parity
+    CMP, BMT = built.CMP, built.BMT
+    n = 1 << 16
+    st = synthetic_states_1m(n, seed=77)
+    mp = CMP.Microphysics1MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk = CMP.pack_1m(mp, tps)
+    out = _call(built, BMT.LinearizedAverage(), mp, tps, _dev(st, cuda), Δt=dt, nsub=nsub)
+    ref = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="linearized_average", dt=dt, nsub=nsub)
+    bnd = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="linearized_average", dt=dt, nsub=nsub, bound=True)
+    for k in orc.OUT_1M:
+        rep = assert_parity(k, out[k].cpu().numpy(), ref[k], bound=bnd[k])
+        assert rep["max_rel"] <= 1e-12, (k, rep)
+
+
+def test_goldens_through_the_gpu(built, cuda):
+    import torch
+    CMP, BMT = built.CMP, built.BMT
+    mp = CMP.Microphysics1MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    s = G["accretion"]["state"]
+    f = lambda v: torch.full((4,), v, dtype=torch.float64, device=cuda)
+    q = f(s["q"])
+    cold = _call(built, BMT.InstantaneousVerbose(), mp, tps, [f(s["rho"]), f(263.0), f(15e-3), q, q, q, q])
+    warm = _call(built, BMT.InstantaneousVerbose(), mp, tps, [f(s["rho"]), f(283.0), f(15e-3), q, q, q, q])
+    for k, (val, where) in G["accretion"].items():
+        if k == "state":
+            continue
+        got = float((warm if k.endswith("_warm") else cold)[k][0])
+        assert abs(got / val - 1) < 1e-13, (k, got, val, where)
+    g = G["snow_melt"]
+    z = f(0.0)
+    o = _call(built, BMT.InstantaneousVerbose(), mp, tps, [f(g["rho"]), f(273.15 + g["dT"]), f(1e-2), z, z, z, f(g["q_sno"])])
+    assert abs(float(o["S_melt_sno_rai"][0]) / g["value"] - 1) < 1e-13
+    vels = {"rain_chen": ("rain", CMP.Chen2022VelTypeRain), "snow_chen": ("snow", CMP.Chen2022VelTypeLargeIce),
+            "cloud_liquid_stokes": ("cloud_liquid", CMP.StokesRegimeVelType), "cloud_ice_chen": ("cloud_ice", CMP.Chen2022VelTypeSmallIce)}
+    for kind, rho, qq, val, where in G["velocities"]:
+        sp, V = vels[kind]
+        got = float(built.CM1.terminal_velocity(mp, tps, sp, V(np.float64), f(rho), f(qq))[0])
+        assert abs(got / val - 1) < 1e-12, (kind, got, val, where)
+
+
+def test_terminal_velocities_f64_parity(built, orc, cuda):
+    import torch
+    from cumicro.testing import synthetic_states_1m, assert_parity
+    CMP = built.CMP
+    st = synthetic_states_1m(1 << 15, seed=5)
+    mp = CMP.Microphysics1MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk = CMP.pack_1m(mp, tps)
+    rho = torch.from_numpy(st["rho"]).to(cuda)
+    cases = [("rain", None, "rain_blk1m", "q_rai"), ("snow", None, "snow_blk1m", "q_sno"),
+             ("rain", CMP.Chen2022VelTypeRain(np.float64), "rain_chen", "q_rai"),
+             ("snow", CMP.Chen2022VelTypeLargeIce(np.float64), "snow_chen", "q_sno"),
+             ("cloud_liquid", CMP.StokesRegimeVelType(np.float64), "cloud_liquid_stokes", "q_lcl"),
+             ("cloud_ice", CMP.Chen2022VelTypeSmallIce(np.float64), "cloud_ice_chen", "q_icl")]
+    for sp, vel, kind, qk in cases:
+        got = built.CM1.terminal_velocity(mp, tps, sp, vel, rho, torch.from_numpy(st[qk]).to(cuda)).cpu().numpy()
+        ref = orc.termvel_1m(blk, kind, st["rho"], st[qk], vel)
+        bnd = orc.termvel_1m(blk, kind, st["rho"], st[qk], vel, bound=True)
+        rep = assert_parity(kind, got, ref, bound=bnd)
+        assert rep["max_rel"] <= 1e-12, (kind, rep)
+
+
+def test_edge_cases(built, orc, cuda):
+    """Zeros / negatives in every slot, T exactly at T_freeze (>=, <=, > predicates), n = 0, 1, 3."""
+    CMP, BMT = built.CMP, built.BMT
+    mp = CMP.Microphysics1MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk = CMP.pack_1m(mp, tps)
+    base = dict(rho=1.0, T=270.0, q_tot=8e-3, q_lcl=1e-3, q_icl=5e-4, q_rai=2e-4, q_sno=3e-4)
+    rows = [dict(base), dict(base, T=273.15), dict(base, T=np.nextafter(273.15, 300)), dict(base, T=np.nextafter(273.15, 0)), dict(base, T=290.0)]
+    for k in ("q_tot", "q_lcl", "q_icl", "q_rai", "q_sno"):
+        for v in (0.0, -1e-6):
+            rows.append(dict(base, **{k: v}))
+            rows.append(dict(base, T=280.0, **{k: v}))
+    rows.append(dict(base, q_lcl=0.0, q_icl=0.0, q_rai=0.0, q_sno=0.0))
+    st = {k: np.array([r[k] for r in rows]) for k in KEYS}
+    out = _call(built, BMT.InstantaneousVerbose(), mp, tps, _dev(st, cuda))
+    ref = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="verbose")
+    for k in orc.OUT_1M + orc.SRC_1M:
+        g = out[k].cpu().numpy()
+        assert np.all(np.isfinite(g)), k
+        np.testing.assert_allclose(g, ref[k], rtol=1e-11, atol=0, err_msg=k)
+        assert np.array_equal(g == 0, ref[k] == 0), k
+    for n in (0, 1, 3):
+        sub = {k: v[:n].copy() for k, v in st.items()}
+        o = _call(built, BMT.Instantaneous(), mp, tps, _dev(sub, cuda))
+        assert o["dq_rai_dt"].shape[0] == n
+        if n:
+            assert np.array_equal(o["dq_rai_dt"].cpu().numpy(), out["dq_rai_dt"].cpu().numpy()[:n])
+
+
+def test_bmt1m_f32(built, orc, cuda):
+    """Float32 method: <= 4 Float32 ULPs from the true value; regime selection = the Float32
+    reference's (Float32 thresholds)."""
+    from cumicro.testing import synthetic_states_1m, assert_f32_method
+    CMP, BMT = built.CMP, built.BMT
+    n = 1 << 15
+    st32 = synthetic_states_1m(n, seed=21, dtype=np.float32)
+    mp32, tps32 = CMP.Microphysics1MParams(np.float32), CMP.ThermodynamicsParameters(np.float32)
+    blk32 = CMP.pack_1m(mp32, tps32)
+    blk64 = CMP.widen(blk32)
+    out = _call(built, BMT.InstantaneousVerbose(), mp32, tps32, _dev(st32, cuda))
+    ref32 = orc.bmt1m(blk32, *[st32[k] for k in KEYS], mode="verbose")
+    st64 = [st32[k].astype(np.float64) for k in KEYS]
+    with orc.f32_thresholds():
+        truth = orc.bmt1m(blk64, *st64, mode="verbose")
+        bound = orc.bmt1m(blk64, *st64, mode="verbose", bound=True)
+    for k in orc.OUT_1M + orc.SRC_1M:
+        assert_f32_method(k, out[k].cpu().numpy(), ref32[k], truth[k], bound[k])
+
+
+def test_config1_grid_64cubed(built, orc, cuda):
+    """BASELINE config 1: the 64x64x64 column grid (262 144 points, flat SoA), full parity."""
+    from cumicro.testing import synthetic_states_1m, assert_parity
+    CMP, BMT = built.CMP, built.BMT
+    n = 64 * 64 * 64
+    st = synthetic_states_1m(n, seed=1234)
+    mp = CMP.Microphysics1MParams(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk = CMP.pack_1m(mp, tps)
+    out = _call(built, BMT.Instantaneous(), mp, tps, _dev(st, cuda))
+    ref = orc.bmt1m(blk, *[st[k] for k in KEYS])
+    bnd = orc.bmt1m(blk, *[st[k] for k in KEYS], bound=True)
+    for k in orc.OUT_1M:
+        rep = assert_parity(k, out[k].cpu().numpy(), ref[k], bound=bnd[k])
+        assert rep["max_rel"] <= 1e-12 and rep["frac_forward_ok"] > 0.98, (k, rep)
