@@ -13,7 +13,10 @@ def __getattr__(name):  # torch-dependent modules are imported on first use
     import importlib
     lazy = {"BulkMicrophysicsTendencies": "BulkMicrophysicsTendencies", "BMT": "BulkMicrophysicsTendencies",
             "Microphysics2M": "Microphysics2M", "CM2": "Microphysics2M",
-            "Microphysics1M": "Microphysics1M", "CM1": "Microphysics1M"}
+            "Microphysics1M": "Microphysics1M", "CM1": "Microphysics1M",
+            "AerosolActivation": "AerosolActivation", "AA": "AerosolActivation",
+            "AerosolModel": "AerosolModel", "AM": "AerosolModel",
+            "IceNucleation": "IceNucleation", "IN": "IceNucleation"}
     if name in lazy:
         return importlib.import_module("." + lazy[name], __name__)
     raise AttributeError(name)

@@ -1,0 +1,149 @@
+// cm_icenuc.cuh — ice-nucleation rates, water activities and ARG2000 aerosol activation.
+//
+// Device form of src/IceNucleation.jl (IN:44-205, 219-253, 557-584), the water activities of
+// src/Common.jl (CO:188-271) and src/AerosolActivation.jl (AA:35-433).  Per-mode quantities
+// that depend on parameters only (f_i, g_i, the T-independent part of the critical
+// supersaturation, log σ_i factors) are folded into ArgK on the host; per point the ARG2000
+// kernel needs 2 exponentials for the two saturation pressures, 1 logarithm + 2 exps per
+// mode for the (ζ/η)^p1 and (S_m²/(η+3ζ))^p2 powers, one erf per mode, and the handful of
+// sqrt / cbrt of the Korolev-Mazin terms.
+#pragma once
+#include "cm_thermo.cuh"
+
+namespace cm {
+
+constexpr int kMaxModes = 8;
+
+template <class FT> struct ArgK {
+    FT A_coef;             // 2 σ M_w / (ρ_w R)            -> A = A_coef / T        AA:35-40
+    FT sm_coef[kMaxModes]; // 2/sqrt(hygro) (A_coef/3/r_dry)^(3/2) -> S_m = sm_coef T^(-3/2)   AA:107-118
+    FT f[kMaxModes], g[kMaxModes];                  // f1 exp(f2 ln²σ), g1 + g2 ln σ     AA:175-176
+    FT inv_eta_coef[kMaxModes];                     // 2π ρ_w N_i
+    FT u_coef[kMaxModes];                           // 2 / (3 √2 ln σ_i)                AA:256
+    FT m_fac[kMaxModes];                            // 3 ln σ_i √2 / 2                   AA:320
+    FT inv_K_safe, inv_D_safe, ln10, c43pi_rho_w, c43pi_rho_i, four_pi;
+    FT Rv_over_Rd;
+};
+
+template <class FT> __host__ inline ArgK<FT> make_arg_k(const cumicro_params_icenuc_f64& p, bool method_is_f32) {
+    ArgK<FT> k{};
+    const FT pi = FT(3.141592653589793238462643383279502884L);
+    const FT epsn = method_is_f32 ? FT(2.2737367544323206e-13) : FT(2.8126442852362996e-103);
+    k.A_coef = FT(2) * p.arg.sigma * p.arg.M_w / p.arg.rho_w / p.arg.R;
+    for (int i = 0; i < p.n_modes && i < kMaxModes; ++i) {
+        const auto& m = p.modes[i];
+        const FT ls = std::log(m.stdev);
+        k.sm_coef[i] = FT(2) / std::sqrt(m.hygro) * std::pow(k.A_coef / 3 / m.r_dry, FT(1.5));
+        k.f[i] = p.arg.f1 * std::exp(p.arg.f2 * ls * ls);
+        k.g[i] = p.arg.g1 + p.arg.g2 * ls;
+        k.inv_eta_coef[i] = 2 * pi * p.arg.rho_w * m.N;
+        k.u_coef[i] = FT(2) / (FT(3) * std::sqrt(FT(2)) * ls);
+        k.m_fac[i] = FT(3) * ls * std::sqrt(FT(2)) / 2;
+    }
+    k.inv_K_safe = FT(1) / std::max(FT(p.aps.K_therm), epsn);
+    k.inv_D_safe = FT(1) / std::max(FT(p.aps.D_vapor), epsn);
+    k.ln10 = FT(2.302585092994045684017991454684364208L);
+    k.c43pi_rho_w = FT(4.0 / 3) * pi * p.arg.rho_w;
+    k.c43pi_rho_i = FT(4.0 / 3) * pi * p.arg.rho_i;
+    k.four_pi = 4 * pi;
+    k.Rv_over_Rd = p.tps.R_v / p.tps.R_d;
+    return k;
+}
+
+// 10^x                                                               (Julia `10^x`)
+template <class FT> CM_DEV FT exp10_(FT x, FT ln10) { return exp_full_(x * ln10); }
+
+// IN.deposition_J / ABIFM_J / HomIceNucleation.homogeneous_J_{cubic,linear}      IN:92-134, 557-584
+template <class FT> CM_DEV FT deposition_J(const cumicro_dust_f64& d, FT da_w, FT ln10) {
+    return d.has_deposition ? exp10_(fma_(d.deposition_m, da_w, d.deposition_c) + FT(4), ln10) : FT(0);
+}
+template <class FT> CM_DEV FT ABIFM_J(const cumicro_dust_f64& d, FT da_w, FT ln10) {
+    return d.has_ABIFM ? exp10_(fma_(d.ABIFM_m, da_w, d.ABIFM_c) + FT(4), ln10) : FT(0);
+}
+template <class FT> CM_DEV FT homogeneous_J_cubic(const cumicro_koop2000_f64& ip, FT da_w, FT ln10, bool& domain_error) {
+    domain_error = !(ip.da_w_min <= da_w && da_w <= ip.da_w_max);
+    const FT d2 = da_w * da_w;
+    const FT logJ = ip.c1 + ip.c2 * da_w - ip.c3 * d2 + ip.c4 * (d2 * da_w);
+    return exp10_(logJ + FT(6), ln10);
+}
+template <class FT> CM_DEV FT homogeneous_J_linear(const cumicro_koop2000_f64& ip, FT da_w, FT ln10) {
+    return exp10_(fma_(ip.linear_c2, da_w, ip.linear_c1) + FT(6), ln10);
+}
+
+struct ArgOut {
+    double S_max;
+    double N_act[kMaxModes];
+    double M_act[kMaxModes];
+    double da_w;     // a_w_eT(p_v, T) - a_w_ice(T)
+};
+
+// AA.max_supersaturation + N_activated_per_mode + M_activated_per_mode          AA:138-324
+template <bool WANT_M>
+CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>& tk, const ArgK<double>& k, double T, double pr,
+                      double w, double q_tot, double q_liq, double q_ice, double N_liq, double N_ice) {
+    using FT = double;
+    ArgOut o;
+    const auto& ap = p.arg;
+    const TempState<FT> ts = temp_state(tk, T);
+    const FT p_vs = p_sat_liq(tk, ts);
+    const FT p_vs_i = p_sat_ice(tk, ts);
+    const FT inv_pvs = rcp_(fmax_(p_vs, tk.eps_n));
+    const FT inv_pvs_i = rcp_(fmax_(p_vs_i, tk.eps_n));
+    const FT R_v = tk.R_v;
+    const FT R_m = p.tps.R_d * (FT(1) + (k.Rv_over_Rd - FT(1)) * q_tot - k.Rv_over_Rd * (q_liq + q_ice));   // TDI.Rₘ
+    const FT cpm = cp_m(tk, q_tot, q_liq, q_ice);
+    const FT Lv = latent_heat_vapor(tk, T);
+    const FT Ls = latent_heat_sublim(tk, T);
+    const FT rho_air = pr * rcp_(R_m * T);                                   // TDI.air_density
+    const FT p_v = (q_tot - q_liq - q_ice) * rho_air * R_v * T;
+    const FT pv_over_pvs = p_v * inv_pvs;
+    o.da_w = pv_over_pvs - p_vs_i * inv_pvs;                                  // CO.a_w_eT - CO.a_w_ice
+    const FT G = G_func(tk, k.inv_K_safe, k.inv_D_safe, Lv, inv_pvs, ts) / ap.rho_w;
+    const FT inv_cpm = rcp_(cpm), inv_Rm = rcp_(R_m), inv_p = rcp_(pr);
+    const FT alpha = pv_over_pvs * (Lv * ap.g * tk.inv_R_v * inv_cpm * ts.inv_T * ts.inv_T - ap.g * inv_Rm * ts.inv_T);
+    const FT common_g = pv_over_pvs * R_m * Lv * tk.inv_R_v * inv_cpm * ts.inv_T * inv_p;
+    const FT gamma = fma_(common_g, Lv, R_v * T * inv_pvs);
+    const FT A = k.A_coef * ts.inv_T;
+    const FT aw_G = alpha * w * rcp_(G);
+    const FT sq = sqrt_(aw_G);
+    const FT zeta = FT(2.0 / 3.0) * A * sq;
+    const FT sq3 = sq * sq * sq;
+    const FT inv_gamma = rcp_(gamma);
+    const FT Tm32 = ts.inv_T * sqrt_(ts.inv_T);
+    const FT l_zeta = logp_(zeta);
+    FT Sm[kMaxModes];
+    FT tmp = FT(0);
+#pragma unroll
+    for (int i = 0; i < kMaxModes; ++i) {
+        if (i >= p.n_modes) break;
+        Sm[i] = k.sm_coef[i] * Tm32;
+        const FT Sm2 = Sm[i] * Sm[i];
+        const FT eta = sq3 * inv_gamma * rcp_(k.inv_eta_coef[i]);
+        // (ζ/η)^p1 and (S_m²/(η+3ζ))^p2
+        const FT t1 = exp_full_(ap.p1 * (l_zeta - log_full_(eta)));
+        const FT t2 = exp_full_(ap.p2 * log_full_(Sm2 / fma_(FT(3), zeta, eta)));
+        tmp += rcp_(Sm2) * fma_(k.f[i], t1, k.g[i] * t2);
+    }
+    const FT S_max_ARG = FT(1) / sqrt_(tmp);
+    const FT r_liq = (N_liq < tk.eps) ? FT(0) : cbrt_full_(rho_air * q_liq / N_liq / k.c43pi_rho_w);
+    const FT K_liq = k.four_pi * ap.rho_w * N_liq * r_liq * G * gamma;
+    const FT gamma_i = fma_(common_g, Ls, R_v * T * inv_pvs);
+    const FT r_ice = (N_ice < tk.eps) ? FT(0) : cbrt_full_(rho_air * q_ice / N_ice / k.c43pi_rho_i);
+    const FT rhoGi = G_func(tk, k.inv_K_safe, k.inv_D_safe, Ls, inv_pvs_i, ts);
+    const FT xi = p_vs * inv_pvs_i;
+    const FT K_ice = k.four_pi * N_ice * r_ice * rhoGi * gamma_i;
+    const FT aw = alpha * w;
+    const FT S_max = S_max_ARG * (aw - K_ice * (xi - FT(1))) / fma_(K_liq + K_ice * xi, S_max_ARG, aw);
+    o.S_max = fmax_(FT(0), S_max);
+    const FT l_smax = log_full_(o.S_max);   // -Inf when S_max = 0: erf(+Inf) = 1 -> N_act = 0   (AA:256)
+#pragma unroll
+    for (int i = 0; i < kMaxModes; ++i) {
+        if (i >= p.n_modes) break;
+        const FT lr = log_full_(Sm[i]) - l_smax;   // log(S_m / S_max)
+        o.N_act[i] = p.modes[i].N * FT(0.5) * (FT(1) - erf_(k.u_coef[i] * lr));
+        if (WANT_M) o.M_act[i] = p.modes[i].molar_mass_mix * FT(0.5) * erfc_(lr / k.m_fac[i] - k.m_fac[i]);
+    }
+    return o;
+}
+
+}  // namespace cm

@@ -106,6 +106,46 @@ def synthetic_states_1m(n, seed=1234, dtype=np.float64, frac_empty=0.05):
     return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}
 
 
+def synthetic_states_activation(n, seed=1234, dtype=np.float64, with_hydrometeors=False):
+    """Inputs of the ice-nucleation / ARG2000 kernel: T in U[190,300] K,
+    p in U[2e4,1.01e5] Pa, w log-uniform in [0.01,10] m/s, q_tot at RH in U[0.5,1.1] over liquid."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d = DEFAULTS
+    Rd, Rv = d["gas_constant_dry_air"], d["gas_constant_vapor"]
+    T = rng.uniform(190.0, 300.0, n)
+    p = rng.uniform(2e4, 1.01e5, n)
+    w = 10.0 ** rng.uniform(-2, 1, n)
+    RH = rng.uniform(0.5, 1.1, n)
+    pv = RH * psat_liq(T)
+    eps_ = Rd / Rv
+    q_vap = eps_ * pv / (p - (1 - eps_) * pv)
+    if with_hydrometeors:
+        q_liq, q_ice = rng.random(n) * 1e-4, rng.random(n) * 1e-5
+        N_liq, N_ice = np.full(n, 1e3) * 10.0 ** rng.uniform(0, 5, n), np.full(n, 1e3) * 10.0 ** rng.uniform(0, 2, n)
+        N_liq[rng.random(n) < 0.1] = 0.0
+        N_ice[rng.random(n) < 0.3] = 0.0
+    else:
+        q_liq = q_ice = N_liq = N_ice = np.zeros(n)
+    st = dict(T=T, p=p, w=w, q_tot=q_vap + q_liq + q_ice, q_liq=q_liq, q_ice=q_ice, N_liq=N_liq, N_ice=N_ice)
+    return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}
+
+
+def arg_test_distribution(kind="kappa"):
+    """The three modes of SURVEY.md §8d / test/aerosol_activation_tests.jl:41-54: accumulation
+    (sea salt), coarse (sea salt), paper mode (sulfate)."""
+    from . import AerosolModel as AM
+    seasalt = dict(M=0.058443, nu=2.0, rho=2170.0, phi=0.9, kappa=1.12, eps=1.0)
+    sulfate = dict(M=0.132, nu=3.0, rho=1770.0, phi=1.0, kappa=0.53, eps=1.0)
+    spec = [(0.243e-6, 1.4, 1e8, seasalt), (1.5e-6, 2.1, 1e6, seasalt), (0.05e-6, 2.0, 1e8, sulfate)]
+    modes = []
+    for r, s, N, a in spec:
+        if kind == "kappa":
+            modes.append(AM.Mode_κ(r, s, N, (1.0,), (1.0,), (a["M"],), (a["kappa"],)))
+        else:
+            modes.append(AM.Mode_B(r, s, N, (1.0,), (a["eps"],), (a["phi"],), (a["M"],), (a["nu"],), (a["rho"],)))
+    return AM.AerosolDistribution(tuple(modes))
+
+
 def perturb(states, rel=2.0 ** -40, seed=7, skip=()):
     """Inputs with every element multiplied by (1 ± rel) (random signs): used to
     measure the reference's own conditioning at each point."""

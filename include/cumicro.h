@@ -251,6 +251,46 @@ int cumicro_termvel_1m_f64(const cumicro_params_1m_f64* p, const void* vel, int 
 int cumicro_termvel_1m_f32(const cumicro_params_1m_f32* p, const void* vel, int kind, int64_t n,
                            const float* rho, const float* q, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Ice nucleation, water activity (pointwise leaves): out[i] = fn(x[i] [, y[i]]).
+ *  what 0: IN.deposition_J(dust, x = Δa_w)                       IN:92-102
+ *       1: IN.ABIFM_J(dust, x = Δa_w)                            IN:124-134
+ *       2: HomIceNucleation.homogeneous_J_cubic(koop, x = Δa_w)  IN:557-565
+ *       3: HomIceNucleation.homogeneous_J_linear(koop, x = Δa_w) IN:581-584
+ *       4: CO.a_w_ice(tps, x = T)                                CO:268-271
+ *       5: CO.a_w_eT(tps, y = e, x = T)                          CO:256-258
+ *       6: CO.a_w_xT(h2so4, tps, y = x_frac, x = T)              CO:241-245
+ *       7: CO.H2SO4_soln_saturation_vapor_pressure(h2so4, y = x_frac, x = T)   CO:188-226
+ *       8: IN.P3_deposition_N_i(mm2014, x = T)                   IN:162-166
+ *       9: IN.INP_concentration_mean(frostenberg, x = T)         IN:250-253
+ *      10: IN.dust_activated_number_fraction(dust, mohler, x = Si, y = T)      IN:44-52
+ * `y` may be NULL for the one-argument functions.  Per-point domain violations (the reference
+ * throws DomainError, IN:558-562, or fails an @assert, IN:47): the output is NaN and, if
+ * `n_domain_errors` (a DEVICE counter the caller zeroes) is non-NULL, it is incremented.
+ * ------------------------------------------------------------------------- */
+int cumicro_icenuc_f64(const cumicro_params_icenuc_f64* p, int what, int64_t n, const double* x, const double* y,
+                       double* out, unsigned long long* n_domain_errors, void* stream);
+int cumicro_icenuc_f32(const cumicro_params_icenuc_f32* p, int what, int64_t n, const float* x, const float* y,
+                       float* out, unsigned long long* n_domain_errors, void* stream);
+
+/* ARG2000 aerosol activation fused with the nucleation rates (BASELINE config 3).
+ * Replaces AA.max_supersaturation (AA:138-214), AA.N_activated_per_mode (AA:235-273),
+ * AA.M_activated_per_mode (AA:294-338) and IN.deposition_J / ABIFM_J / homogeneous_J_cubic
+ * evaluated at Δa_w = CO.a_w_eT(tps, p_v, T) - CO.a_w_ice(tps, T), p_v the vapour pressure of
+ * the same state — one read of the 8 state columns, all outputs written once.
+ * N_act / M_act: HOST arrays of p->n_modes device column pointers (or NULL); any output
+ * pointer may be NULL.  J_hom is NaN (+ counter) outside Koop's validity range. */
+int cumicro_arg_icenuc_f64(const cumicro_params_icenuc_f64* p, int64_t n, const double* T, const double* p_air,
+                           const double* w, const double* q_tot, const double* q_liq, const double* q_ice,
+                           const double* N_liq, const double* N_ice, double* S_max, double* const* N_act,
+                           double* const* M_act, double* J_dep, double* J_abifm, double* J_hom, double* da_w,
+                           unsigned long long* n_domain_errors, void* stream);
+int cumicro_arg_icenuc_f32(const cumicro_params_icenuc_f32* p, int64_t n, const float* T, const float* p_air,
+                           const float* w, const float* q_tot, const float* q_liq, const float* q_ice,
+                           const float* N_liq, const float* N_ice, float* S_max, float* const* N_act,
+                           float* const* M_act, float* J_dep, float* J_abifm, float* J_hom, float* da_w,
+                           unsigned long long* n_domain_errors, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

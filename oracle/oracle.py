@@ -185,3 +185,39 @@ def termvel_1m(params, kind, rho, q, vel=None, bound=False):
     st = fn(C.byref(params), C.byref(vel) if vel is not None else None, C.c_int(TERMVEL_1M[kind]), C.c_int64(n), _ptr(rho), _ptr(q), _ptr(out))
     assert st == 0
     return out
+
+
+# ---- ice nucleation / water activity / ARG2000 ----------------------------------------------
+ICENUC_WHAT = {"deposition_J": 0, "ABIFM_J": 1, "homogeneous_J_cubic": 2, "homogeneous_J_linear": 3, "a_w_ice": 4, "a_w_eT": 5,
+               "a_w_xT": 6, "H2SO4_soln_saturation_vapor_pressure": 7, "P3_deposition_N_i": 8, "INP_concentration_mean": 9,
+               "dust_activated_number_fraction": 10}
+
+
+def icenuc(params, what, x, y=None):
+    """Pointwise leaves (same numbering as cumicro_icenuc_*).  Returns (out, n_domain_errors)."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    x = np.ascontiguousarray(x, dtype=dtype)
+    y = np.ascontiguousarray(y if y is not None else x, dtype=dtype)
+    out = np.empty_like(x)
+    fn = getattr(lib(), f"oracle_icenuc_{_suf(dtype)}")
+    fn.restype = C.c_int64
+    nerr = fn(C.byref(params), C.c_int(ICENUC_WHAT[what]), C.c_int64(x.size), _ptr(x), _ptr(y), _ptr(out))
+    return out, int(nerr)
+
+
+def arg_icenuc(params, T, p, w, q_tot, q_liq, q_ice, N_liq, N_ice, bound=False):
+    """ARG2000 (AA:138-324) + nucleation rates at Δa_w = a_w_eT(p_v,T) - a_w_ice(T)."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    cols, n = _cols((T, p, w, q_tot, q_liq, q_ice, N_liq, N_ice), dtype)
+    nm = params.n_modes
+    new = lambda: np.empty(n, dtype)
+    out = dict(S_max=new(), N_act=[new() for _ in range(nm)], M_act=[new() for _ in range(nm)], J_dep=new(), J_ABIFM=new(),
+               J_hom=new(), da_w=new())
+    na = (C.c_void_p * nm)(*[_ptr(a) for a in out["N_act"]])
+    ma = (C.c_void_p * nm)(*[_ptr(a) for a in out["M_act"]])
+    fn = lib().oracle_arg_icenuc_bound_f64 if bound else getattr(lib(), f"oracle_arg_icenuc_{_suf(dtype)}")
+    fn.restype = C.c_int64
+    nerr = fn(C.byref(params), C.c_int64(n), *[_ptr(a) for a in cols], _ptr(out["S_max"]), na, ma, _ptr(out["J_dep"]),
+              _ptr(out["J_ABIFM"]), _ptr(out["J_hom"]), _ptr(out["da_w"]))
+    out["n_domain_errors"] = int(nerr)
+    return out

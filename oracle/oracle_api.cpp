@@ -4,7 +4,7 @@
 // multithreaded driver of its own; hosts broadcast the scalar methods).
 #include <omp.h>
 
-#include "oracle_1m.hpp"
+#include "oracle_icenuc.hpp"
 
 using namespace orc;
 
@@ -184,6 +184,109 @@ int oracle_termvel_1m_bound_f64(const cumicro_params_1m_f64* p, const void* vel,
             default: break;
         }
         out[i] = v.e;
+    }
+    return 0;
+}
+
+// ---- ice nucleation, water activity, ARG2000 ---------------------------------------------------
+// what: 0 deposition_J, 1 ABIFM_J, 2 homogeneous_J_cubic, 3 homogeneous_J_linear (x = Δa_w)
+//       4 a_w_ice(T), 5 a_w_eT(e = y, T = x), 6 a_w_xT(x_frac = y, T = x), 7 H2SO4 p_sol(x_frac = y, T = x)
+//       8 P3_deposition_N_i(T), 9 INP_concentration_mean(T), 10 dust_activated_number_fraction(Si = x, T = y)
+// returns the number of per-point domain errors (DomainError / AssertionError of the reference)
+#define DEF_ICENUC(SUF, FT)                                                                                          \
+    int64_t oracle_icenuc_##SUF(const cumicro_params_icenuc_##SUF* p, int what, int64_t n, const FT* x, const FT* y,    \
+                                FT* out) {                                                                             \
+        int64_t nerr = 0;                                                                                              \
+        Thermo<FT> tps(p->tps);                                                                                        \
+        _Pragma("omp parallel for schedule(static) reduction(+ : nerr)") for (int64_t i = 0; i < n; ++i) {             \
+            bool err = false;                                                                                          \
+            FT v = 0;                                                                                                  \
+            switch (what) {                                                                                            \
+                case 0: v = deposition_J<FT>(p->dust, x[i]); break;                                                    \
+                case 1: v = ABIFM_J<FT>(p->dust, x[i]); break;                                                         \
+                case 2: v = homogeneous_J_cubic<FT>(p->koop, x[i], err); break;                                        \
+                case 3: v = homogeneous_J_linear<FT>(p->koop, x[i]); break;                                            \
+                case 4: v = a_w_ice<FT>(tps, x[i]); break;                                                             \
+                case 5: v = a_w_eT<FT>(tps, y[i], x[i]); break;                                                        \
+                case 6: v = a_w_xT<FT>(p->h2so4, tps, y[i], x[i]); break;                                              \
+                case 7: v = H2SO4_soln_saturation_vapor_pressure<FT>(p->h2so4, y[i], x[i]); break;                     \
+                case 8: v = P3_deposition_N_i<FT>(p->mm2014, x[i]); break;                                             \
+                case 9: v = INP_concentration_mean<FT>(p->frostenberg, x[i]); break;                                   \
+                case 10: v = dust_activated_number_fraction<FT>(p->dust, p->mohler, x[i], y[i], err); break;           \
+                default: break;                                                                                        \
+            }                                                                                                          \
+            if (err) { v = std::numeric_limits<FT>::quiet_NaN(); nerr += 1; }                                          \
+            out[i] = v;                                                                                                \
+        }                                                                                                              \
+        return nerr;                                                                                                   \
+    }                                                                                                                  \
+    /* ARG2000 + (optionally) the nucleation rates at Δa_w = a_w_eT(p_v, T) - a_w_ice(T): columns T,p,w,q_tot,q_liq,    \
+       q_ice,N_liq,N_ice -> S_max, N_act[n_modes], M_act[n_modes], J_dep, J_ABIFM, J_hom (any pointer may be NULL) */   \
+    int64_t oracle_arg_icenuc_##SUF(const cumicro_params_icenuc_##SUF* p, int64_t n, const FT* T, const FT* pr,         \
+                                    const FT* w, const FT* q_tot, const FT* q_liq, const FT* q_ice, const FT* N_liq,    \
+                                    const FT* N_ice, FT* S_max, FT* const* N_act, FT* const* M_act, FT* J_dep,         \
+                                    FT* J_abifm, FT* J_hom, FT* da_w_out) {                                            \
+        int64_t nerr = 0;                                                                                              \
+        _Pragma("omp parallel for schedule(static) reduction(+ : nerr)") for (int64_t i = 0; i < n; ++i) {             \
+            FT na[8], ma[8], sm;                                                                                       \
+            activated_per_mode<FT>(*p, T[i], pr[i], w[i], q_tot[i], q_liq[i], q_ice[i], N_liq[i], N_ice[i], sm, na,    \
+                                   ma);                                                                                \
+            if (S_max) S_max[i] = sm;                                                                                  \
+            for (int k = 0; k < p->n_modes; ++k) {                                                                     \
+                if (N_act && N_act[k]) N_act[k][i] = na[k];                                                            \
+                if (M_act && M_act[k]) M_act[k][i] = ma[k];                                                            \
+            }                                                                                                          \
+            if (J_dep || J_abifm || J_hom || da_w_out) {                                                               \
+                Thermo<FT> tps(p->tps);                                                                                \
+                FT R_m = tps.R_m(q_tot[i], q_liq[i], q_ice[i]);                                                        \
+                FT rho = pr[i] / (R_m * T[i]);                                                                         \
+                FT e = (q_tot[i] - q_liq[i] - q_ice[i]) * rho * tps.R_v() * T[i];                                      \
+                FT d = a_w_eT<FT>(tps, e, T[i]) - a_w_ice<FT>(tps, T[i]);                                              \
+                if (da_w_out) da_w_out[i] = d;                                                                         \
+                if (J_dep) J_dep[i] = deposition_J<FT>(p->dust, d);                                                    \
+                if (J_abifm) J_abifm[i] = ABIFM_J<FT>(p->dust, d);                                                     \
+                if (J_hom) {                                                                                           \
+                    bool err = false;                                                                                  \
+                    FT v = p->hom_linear ? homogeneous_J_linear<FT>(p->koop, d) : homogeneous_J_cubic<FT>(p->koop, d, err); \
+                    if (err) { v = std::numeric_limits<FT>::quiet_NaN(); nerr += 1; }                                  \
+                    J_hom[i] = v;                                                                                      \
+                }                                                                                                      \
+            }                                                                                                          \
+        }                                                                                                              \
+        return nerr;                                                                                                   \
+    }
+DEF_ICENUC(f64, double)
+DEF_ICENUC(f32, float)
+
+// rounding-error bounds of the reference algorithm for oracle_arg_icenuc_f64's outputs
+int64_t oracle_arg_icenuc_bound_f64(const cumicro_params_icenuc_f64* p, int64_t n, const double* T, const double* pr,
+                                    const double* w, const double* q_tot, const double* q_liq, const double* q_ice,
+                                    const double* N_liq, const double* N_ice, double* S_max, double* const* N_act,
+                                    double* const* M_act, double* J_dep, double* J_abifm, double* J_hom, double* da_w_out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        Tr na[8], ma[8], sm;
+        activated_per_mode<Tr>(*p, Tr(T[i]), Tr(pr[i]), Tr(w[i]), Tr(q_tot[i]), Tr(q_liq[i]), Tr(q_ice[i]), Tr(N_liq[i]), Tr(N_ice[i]),
+                               sm, na, ma);
+        if (S_max) S_max[i] = sm.e;
+        for (int k = 0; k < p->n_modes; ++k) {
+            if (N_act && N_act[k]) N_act[k][i] = na[k].e;
+            if (M_act && M_act[k]) M_act[k][i] = ma[k].e;
+        }
+        if (J_dep || J_abifm || J_hom || da_w_out) {
+            Thermo<Tr> tps(p->tps);
+            Tr R_m = tps.R_m(Tr(q_tot[i]), Tr(q_liq[i]), Tr(q_ice[i]));
+            Tr rho = Tr(pr[i]) / (R_m * Tr(T[i]));
+            Tr e = (Tr(q_tot[i]) - Tr(q_liq[i]) - Tr(q_ice[i])) * rho * tps.R_v() * Tr(T[i]);
+            Tr d = a_w_eT<Tr>(tps, e, Tr(T[i])) - a_w_ice<Tr>(tps, Tr(T[i]));
+            if (da_w_out) da_w_out[i] = d.e;
+            if (J_dep) J_dep[i] = deposition_J<Tr>(p->dust, d).e;
+            if (J_abifm) J_abifm[i] = ABIFM_J<Tr>(p->dust, d).e;
+            if (J_hom) {
+                bool err = false;
+                J_hom[i] = p->hom_linear ? homogeneous_J_linear<Tr>(p->koop, d).e : homogeneous_J_cubic<Tr>(p->koop, d, err).e;
+            }
+        }
     }
     return 0;
 }

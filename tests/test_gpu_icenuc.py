@@ -1,0 +1,137 @@
+"""GPU parity of the ice-nucleation / water-activity leaves and the fused ARG2000 + nucleation
+kernel (BASELINE config 3) through the C-ABI vs the CPU oracle; Float64 1e-12 relative (or the
+reference's own rounding bound), Float32 <= 4 ULP of the true value."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "icenuc_goldens.json")))
+KEYS = ("T", "p", "w", "q_tot", "q_liq", "q_ice", "N_liq", "N_ice")
+
+
+def test_goldens_through_the_gpu(built, cuda):
+    import torch
+    CMP, IN = built.CMP, built.IN
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    f = lambda v: torch.full((3,), v, dtype=torch.float64, device=cuda)
+    for name, da, J in G["deposition_J"]:
+        assert abs(float(IN.deposition_J(CMP.DustType(name), tps, f(da))[0]) / J - 1) < 1e-12
+    for name, da, J in G["ABIFM_J"]:
+        assert abs(float(IN.ABIFM_J(CMP.DustType(name), tps, f(da))[0]) / J - 1) < 1e-9
+    k = G["koop"]
+    koop = CMP.Koop2000(np.float64)
+    assert abs(float(IN.homogeneous_J_cubic(koop, tps, f(k["da_w"]))[0]) / k["cubic"] - 1) < 1e-12
+    assert abs(float(IN.homogeneous_J_linear(koop, tps, f(k["da_w"]))[0]) / k["linear"] - 1) < 1e-12
+    with pytest.raises(IN.DomainError):                               # DomainError of IN:558-562
+        IN.homogeneous_J_cubic(koop, tps, torch.tensor([0.3, 0.1], dtype=torch.float64, device=cuda))
+    out = IN.homogeneous_J_cubic(koop, tps, torch.tensor([0.3, 0.1], dtype=torch.float64, device=cuda), check_domain=False)
+    assert bool(torch.isfinite(out[0])) and bool(torch.isnan(out[1]))
+    assert abs(float(IN.a_w_ice(tps, f(G["a_w_ice"]["T"]))[0]) / G["a_w_ice"]["value"] - 1) < 1e-13
+    g = G["a_w_eT"]
+    assert abs(float(IN.a_w_eT(tps, f(g["e"]), f(g["T"]))[0]) / g["value"] - 1) < 1e-13
+    g = G["h2so4"]
+    h = CMP.H2SO4SolutionParameters(np.float64)
+    assert abs(float(IN.H2SO4_soln_saturation_vapor_pressure(h, tps, f(g["x"]), f(g["T"]))[0]) / g["p_sol"] - 1) < 1e-12
+    assert abs(float(IN.a_w_xT(h, tps, f(g["x"]), f(g["T"]))[0]) / g["a_w"] - 1) < 1e-12
+    assert abs(float(IN.P3_deposition_N_i(CMP.MorrisonMilbrandt2014(np.float64), tps, f(240.0))[0]) / G["P3_deposition_N_i"]["value"] - 1) < 1e-12
+    d = G["dust_fraction"]
+    for name in ("DesertDust", "ArizonaTestDust"):
+        got = float(IN.dust_activated_number_fraction(CMP.DustType(name), CMP.Mohler2006(np.float64), tps, f(d["Si"]), f(d["T"]))[0])
+        assert abs(got / d[name] - 1) < 1e-8
+
+
+def test_leaves_f64_parity(built, orc, cuda):
+    import torch
+    from cumicro.testing import assert_parity
+    CMP, IN = built.CMP, built.IN
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    rng = np.random.default_rng(3)
+    n = 1 << 15
+    da = rng.uniform(0.0, 0.45, n)
+    T = rng.uniform(185.0, 300.0, n)
+    e = rng.uniform(1.0, 3000.0, n)
+    x = rng.uniform(0.0, 0.5, n)
+    d = lambda a: torch.from_numpy(a).to(cuda)
+    dust = CMP.DustType("Illite")
+    blk = CMP.pack_icenuc(tps, dust=dust)
+    cases = [("deposition_J", IN.deposition_J(dust, tps, d(da)), (da, None)), ("ABIFM_J", IN.ABIFM_J(dust, tps, d(da)), (da, None)),
+             ("homogeneous_J_linear", IN.homogeneous_J_linear(CMP.Koop2000(np.float64), tps, d(da)), (da, None)),
+             ("homogeneous_J_cubic", IN.homogeneous_J_cubic(CMP.Koop2000(np.float64), tps, d(da), check_domain=False), (da, None)),
+             ("a_w_ice", IN.a_w_ice(tps, d(T)), (T, None)), ("a_w_eT", IN.a_w_eT(tps, d(e), d(T)), (T, e)),
+             ("a_w_xT", IN.a_w_xT(CMP.H2SO4SolutionParameters(np.float64), tps, d(x), d(T)), (T, x)),
+             ("P3_deposition_N_i", IN.P3_deposition_N_i(CMP.MorrisonMilbrandt2014(np.float64), tps, d(T)), (T, None)),
+             ("INP_concentration_mean", IN.INP_concentration_mean(CMP.FrostenbergParameters(np.float64), tps, d(T)), (T, None))]
+    for name, got, (a, b) in cases:
+        ref, nerr = orc.icenuc(blk, name, a, b)
+        rep = assert_parity(name, got.cpu().numpy(), ref)       # includes NaN (domain) and -Inf (log 0) pattern equality
+        assert rep["max_rel"] <= 1e-12, (name, rep)
+        if name == "homogeneous_J_cubic":
+            assert nerr == int(np.isnan(ref).sum()) > 0
+
+
+@pytest.mark.parametrize("kind,hyd", [("kappa", False), ("B", True)])
+def test_arg_icenuc_fused_f64_parity(built, orc, cuda, kind, hyd):
+    import torch
+    from cumicro.testing import synthetic_states_activation, arg_test_distribution, assert_parity
+    CMP, AA = built.CMP, built.AA
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    ap, aip, ad = CMP.AerosolActivationParameters(np.float64), CMP.AirProperties(np.float64), arg_test_distribution(kind)
+    dust, koop = CMP.DustType("Kaolinite"), CMP.Koop2000(np.float64)
+    n = 1 << 16
+    st = synthetic_states_activation(n, seed=9, with_hydrometeors=hyd)
+    cols = [torch.from_numpy(st[k]).to(cuda) for k in KEYS]
+    for hom_linear in (False, True):
+        got = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *cols, hom_linear=hom_linear, with_mass=True)
+        blk = CMP.pack_icenuc(tps, aps=aip, ap=ap, ad=ad, dust=dust, koop=koop, hom_linear=hom_linear)
+        ref = orc.arg_icenuc(blk, *[st[k] for k in KEYS])
+        bnd = orc.arg_icenuc(blk, *[st[k] for k in KEYS], bound=True)
+        for k in ("S_max", "J_dep", "J_ABIFM", "J_hom", "da_w"):
+            rep = assert_parity(k, got[k].cpu().numpy(), ref[k], bound=bnd[k])
+            assert rep["max_rel"] <= 1e-12, (k, rep)
+        for m in range(3):
+            for k in ("N_act", "M_act"):
+                rep = assert_parity(f"{k}[{m}]", got[k][m].cpu().numpy(), ref[k][m], bound=bnd[k][m])
+                assert rep["max_rel"] <= 1e-12, (k, m, rep)
+        assert int(got["n_domain_errors"].item()) == ref["n_domain_errors"]
+        assert (ref["n_domain_errors"] == 0) == hom_linear
+    # module-level entry points select the same columns
+    N = AA.N_activated_per_mode(ap, ad, aip, tps, *cols)
+    tot = AA.total_N_activated(ap, ad, aip, tps, *cols)
+    assert torch.equal(N[1], got["N_act"][1]) and torch.equal(tot, N[0] + N[1] + N[2])
+    assert torch.equal(AA.max_supersaturation(ap, ad, aip, tps, *cols), got["S_max"])
+
+
+def test_config3_f32_2pow20(built, orc, cuda):
+    """BASELINE config 3 (Float32, 3 aerosol modes, deposition + ABIFM + Koop J): the Float32
+    method within 4 Float32 ULP of the true value."""
+    import torch
+    from cumicro.testing import synthetic_states_activation, arg_test_distribution, assert_f32_method
+    CMP, AA = built.CMP, built.AA
+    F = np.float32
+    tps = CMP.ThermodynamicsParameters(F)
+    ap, aip, ad = CMP.AerosolActivationParameters(F), CMP.AirProperties(F), arg_test_distribution("kappa")
+    dust, koop = CMP.DustType("Kaolinite", F), CMP.Koop2000(F)
+    n = 1 << 20
+    st = synthetic_states_activation(n, seed=11, dtype=F)
+    cols = [torch.from_numpy(st[k]).to(cuda) for k in KEYS]
+    got = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *cols, hom_linear=True)
+    blk32 = CMP.pack_icenuc(tps, aps=aip, ap=ap, ad=ad, dust=dust, koop=koop, hom_linear=True)
+    blk64 = CMP.widen(blk32)
+    m = 1 << 16                                                   # the CPU reference on a 65 536-point sample
+    s64 = [st[k][:m].astype(np.float64) for k in KEYS]
+    ref32 = orc.arg_icenuc(blk32, *[st[k][:m] for k in KEYS])
+    with orc.f32_thresholds():
+        truth = orc.arg_icenuc(blk64, *s64)
+        bound = orc.arg_icenuc(blk64, *s64, bound=True)
+    for k in ("S_max", "J_dep", "J_ABIFM", "J_hom"):
+        g = got[k].cpu().numpy()
+        assert g.dtype == np.float32 and g.shape == (n,)
+        # Float32 reference overflows J to Inf / underflows to 0 where the true value is outside Float32 range
+        assert_f32_method(k, g[:m], np.where(np.isfinite(ref32[k]), ref32[k], truth[k].astype(np.float32)), truth[k], bound[k])
+    for i in range(3):
+        assert_f32_method(f"N_act[{i}]", got["N_act"][i].cpu().numpy()[:m], ref32["N_act"][i], truth["N_act"][i],
+                          np.maximum(bound["N_act"][i], 1e-9 * blk64.modes[i].N))
