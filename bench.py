@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 22, help="points of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--diagnostics", action="store_true",
+                    help="also all-reduce (NCCL) a 4-double diagnostic vector every step, as the multi-GPU host model would")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cumicro" else args.warmup
 
@@ -190,8 +192,13 @@ def main():
     outs = [torch.empty_like(cols["rho"]) for _ in range(4)]
     torch.cuda.synchronize()
 
+    diag = torch.zeros(4, dtype=torch.float64, device=dev)
+
     def step():
-        return BMT.bulk_microphysics_tendencies(scheme, mp, tps, *[cols[k] for k in KEYS], out=outs)
+        r = BMT.bulk_microphysics_tendencies(scheme, mp, tps, *[cols[k] for k in KEYS], out=outs)
+        if args.diagnostics and dist is not None:
+            dist.all_reduce(diag)     # the only collective of the path: optional global diagnostic sums
+        return r
 
     def barrier():
         if dist is not None:
@@ -261,7 +268,8 @@ def main():
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points_per_gpu": n, "global_points": n * world,
-                   "parallelism": f"column slabs x{world}, no data-path collective",
+                   "parallelism": f"column slabs x{world}, no data-path collective"
+                                  + (" + NCCL all-reduce of 4 diagnostic doubles per step" if args.diagnostics and world > 1 else ""),
                    "l2": "inputs (7 x 134 MB columns) larger than the 126 MB L2; no flush needed",
                    "psd": "SB2006 limited rain PSD, log-uniform number concentrations"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

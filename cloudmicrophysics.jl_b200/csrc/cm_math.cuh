@@ -177,10 +177,16 @@ CM_HD double exp_(double x) {
     const double y = fma(T, p, T);
     return mk64(hi32(y) + ((ki >> 8) << 20), lo32(y));
 }
-// exp with the IEEE limits: 0 below the normal range, +Inf above, NaN propagated.
+// exp with the IEEE limits: gradual underflow into the subnormals, 0 below them, +Inf
+// above the range, NaN propagated.
 CM_HD double exp_full_(double x) {
-    const double y = exp_(fmin(fmax(x, -708.0), 709.0));
-    return (x != x) ? x : ((x < -708.0) ? 0.0 : ((x > 709.0) ? num<double>::inf() : y));
+    const double xc = fmin(fmax(x, -708.0), 709.0);
+    double y = exp_(xc);
+    if (x < -708.0) {
+        // e^x = e^(x + 64 ln2) * 2^-64: the scaling multiply rounds once into the subnormal range
+        y = (x < -746.0) ? 0.0 : exp_(x + 44.361419555836500) * 5.421010862427522170e-20;
+    }
+    return (x != x) ? x : ((x > 709.0) ? ((x > 709.782712893384) ? num<double>::inf() : exp_(x - 1.0) * 2.718281828459045) : y);
 }
 CM_HD float exp_(float x) { return expf(x); }
 CM_HD float exp_full_(float x) { return expf(x); }

@@ -130,6 +130,18 @@ def synthetic_states_activation(n, seed=1234, dtype=np.float64, with_hydrometeor
     return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}
 
 
+def synthetic_states_fused(n, seed=1234, dtype=np.float64):
+    """The 11 input columns of the fused 1M+2M+ice-nucleation kernel (config 5): the 1-moment
+    atmospheric state plus updraft speed and number concentrations."""
+    st = synthetic_states_1m(n, seed=seed, dtype=np.float64)
+    rng = np.random.Generator(np.random.PCG64(seed + 1000))
+    st["w"] = 10.0 ** rng.uniform(-2, 1, n)
+    st["n_lcl"] = 10.0 ** rng.uniform(7, 9, n)
+    st["n_rai"] = 10.0 ** rng.uniform(2, 6, n)
+    keys = ("rho", "T", "p", "w", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno", "n_lcl", "n_rai")
+    return {k: np.ascontiguousarray(st[k], dtype=dtype) for k in keys}
+
+
 def arg_test_distribution(kind="kappa"):
     """The three modes of SURVEY.md §8d / test/aerosol_activation_tests.jl:41-54: accumulation
     (sea salt), coarse (sea salt), paper mode (sulfate)."""

@@ -291,6 +291,29 @@ int cumicro_arg_icenuc_f32(const cumicro_params_icenuc_f32* p, int64_t n, const 
                            float* const* M_act, float* J_dep, float* J_abifm, float* J_hom, float* da_w,
                            unsigned long long* n_domain_errors, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Fused 1-moment + 2-moment warm rain + ice nucleation (+ ARG2000 activation) with in-kernel
+ * domain diagnostics (BASELINE config 5).  One read of the state, one write of every tendency.
+ * in11  = HOST array of 11 device columns: rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai
+ * out11 = HOST array of 11 device columns (NULL entries skipped):
+ *         [0..3]  dq_lcl_dt, dq_icl_dt, dq_rai_dt, dq_sno_dt of the 1-moment scheme      BMT:505-514
+ *         [4..7]  dq_lcl_dt, dn_lcl_dt, dq_rai_dt, dn_rai_dt of the 2-moment warm rain   BMT:820-854
+ *                 (q_ice seen by its thermodynamics = q_icl + q_sno)
+ *         [8..10] J_dep, J_ABIFM, J_hom at Δa_w = a_w_eT(p_v, T) - a_w_ice(T)              IN:92-134, 557-584
+ * diag  = DEVICE array of CUMICRO_NDIAG doubles (or NULL), written (not accumulated):
+ *         [0] Σ rho (dq_rai_dt + dq_sno_dt) 1-moment   [1] Σ rho dq_rai_dt 2-moment
+ *         [2] Σ N_act (all modes of p3; 0 if p3->n_modes == 0)   [3] number of points
+ *         Sums are Float64 and bit-reproducible (fixed reduction order).  Multi-GPU: each rank
+ *         reduces its slab; the cross-rank sum is one all-reduce of CUMICRO_NDIAG doubles.
+ * ------------------------------------------------------------------------- */
+#define CUMICRO_NDIAG 4
+int cumicro_fused_1m2m_icenuc_f64(const cumicro_params_1m_f64* p1, const cumicro_params_2m_warm_f64* p2,
+                                  const cumicro_params_icenuc_f64* p3, int64_t n, const double* const* in11,
+                                  double* const* out11, double* diag, void* stream);
+int cumicro_fused_1m2m_icenuc_f32(const cumicro_params_1m_f32* p1, const cumicro_params_2m_warm_f32* p2,
+                                  const cumicro_params_icenuc_f32* p3, int64_t n, const float* const* in11,
+                                  float* const* out11, double* diag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

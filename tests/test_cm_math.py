@@ -43,8 +43,11 @@ def test_exp(lib):
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-700, 700, 1500), rng.uniform(-2, 2, 1500), rng.uniform(-1e-3, 1e-3, 300), [0.0]])
     assert _max_ulp(_run(lib, "cmt_exp", x), x, mp.exp) < 1.6   # relative error in units of 2^-52
-    y = _run(lib, "cmt_exp_full", np.array([-800.0, 800.0, np.nan, 0.0, -745.0, 709.5]))
-    assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and y[4] == 0 and np.isinf(y[5])
+    y = _run(lib, "cmt_exp_full", np.array([-800.0, 800.0, np.nan, 0.0, -745.0, 709.5, -720.0, -744.0, 709.9]))
+    assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and np.isinf(y[8])
+    # gradual underflow into the subnormals and the top of the range, like libm
+    for got, x in zip(y[[4, 5, 6, 7]], (-745.0, 709.5, -720.0, -744.0)):
+        assert abs(got - np.exp(x)) <= max(2e-15 * np.exp(x), 5e-324), (x, got, np.exp(x))
 
 
 def test_log(lib):

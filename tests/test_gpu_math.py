@@ -47,5 +47,8 @@ def test_device_math_accuracy(built, cuda):
         t = mp.power(mp.mpf(float(a)), mp.mpf(float(b)))
         worst = max(worst, float(abs((mp.mpf(float(c)) - t) / t) / (abs(mp.mpf(float(b)) * mp.log(mp.mpf(float(a)))) + 1) / mp.mpf(2) ** -52))
     assert worst < 2.0
-    y = _probe(built, cuda, 5, np.array([-800.0, 800.0, np.nan, 0.0, -745.0, 709.5]))
-    assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and y[4] == 0 and np.isinf(y[5])
+    xs = np.array([-800.0, 800.0, np.nan, 0.0, -745.0, 709.5, -720.0, -744.0, 709.9])
+    y = _probe(built, cuda, 5, xs)
+    assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and np.isinf(y[8])
+    for got, x in zip(y[[4, 5, 6, 7]], (-745.0, 709.5, -720.0, -744.0)):
+        assert abs(got - np.exp(x)) <= max(2e-15 * np.exp(x), 5e-324), (x, got, np.exp(x))

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Device-resident throughput of every kernel family (one JSON line per family) — the per-
+config numbers quoted in DESIGN.md §5; bench.py remains the contract benchmark (2M, config 1)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cumicro  # noqa: E402
+from cumicro import AA, BMT, CMP, fused  # noqa: E402
+from cumicro.testing import (arg_test_distribution, synthetic_states_1m, synthetic_states_2m, synthetic_states_activation,  # noqa: E402
+                             synthetic_states_fused)
+
+dev = torch.device("cuda:0")
+HBM = 6548.5
+
+
+def timeit(f, reps=20, warm=3):
+    for _ in range(warm):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def report(name, n, ms, bytes_per_point):
+    print(json.dumps({"family": name, "points": n, "ms": round(ms, 4), "points_per_s": n / ms * 1e3,
+                      "algorithmic_GBps": bytes_per_point * n / ms / 1e6, "frac_of_hbm_copy": bytes_per_point * n / ms / 1e6 / HBM}), flush=True)
+
+
+def dcols(st, keys, dtype=None):
+    return [torch.from_numpy(st[k] if dtype is None else st[k].astype(dtype)).to(dev) for k in keys]
+
+
+tps = CMP.ThermodynamicsParameters(np.float64)
+K2 = ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai")
+K1 = ("rho", "T", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno")
+
+n = 1 << 24
+c = dcols(synthetic_states_2m(n), K2)
+mp2 = CMP.Microphysics2MParams(np.float64)
+o = [torch.empty_like(c[0]) for _ in range(4)]
+report("2M warm SB2006 f64 (config 2)", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp2, tps, *c, out=o)), 88)
+c32 = [x.float() for x in c]
+mp2f, tpsf = CMP.Microphysics2MParams(np.float32), CMP.ThermodynamicsParameters(np.float32)
+o32 = [torch.empty_like(c32[0]) for _ in range(4)]
+report("2M warm SB2006 f32", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp2f, tpsf, *c32, out=o32)), 44)
+del c, c32, o, o32
+
+c = dcols(synthetic_states_1m(n), K1)
+mp1 = CMP.Microphysics1MParams(np.float64)
+o = [torch.empty_like(c[0]) for _ in range(4)]
+m1 = BMT.Microphysics1Moment()
+report("1M Instantaneous f64 2^24", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), m1, mp1, tps, *c, out=o)), 88)
+report("1M LinearizedAverage nsub=1 f64", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.LinearizedAverage(), m1, mp1, tps, *c, Δt=60.0, nsub=1, out=o)), 88)
+report("1M LinearizedAverage nsub=3 f64", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.LinearizedAverage(), m1, mp1, tps, *c, Δt=60.0, nsub=3, out=o), reps=10), 88)
+n1 = 64 ** 3
+c1 = [x[:n1].contiguous() for x in c]
+o1 = [torch.empty_like(c1[0]) for _ in range(4)]
+report("1M Instantaneous f64 64^3 (config 1)", n1, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), m1, mp1, tps, *c1, out=o1), reps=50), 88)
+del c, o
+
+n3 = 1 << 25
+KA = ("T", "p", "w", "q_tot", "q_liq", "q_ice", "N_liq", "N_ice")
+F = np.float32
+c = dcols(synthetic_states_activation(n3, dtype=F), KA)
+tf = CMP.ThermodynamicsParameters(F)
+args = (CMP.AerosolActivationParameters(F), arg_test_distribution("kappa"), CMP.AirProperties(F), tf, CMP.DustType("Kaolinite", F), CMP.Koop2000(F))
+report("ice nucleation + ARG2000 3 modes f32 2^25 (config 3)", n3, timeit(lambda: AA.activation_and_ice_nucleation(*args, *c, hom_linear=True), reps=10), 4 * (8 + 1 + 3 + 4))
+del c
+
+n5 = 1 << 24
+st = synthetic_states_fused(n5)
+c = dcols(st, fused.IN_NAMES)
+blk3 = CMP.pack_icenuc(tps, ad=arg_test_distribution("kappa"), dust=CMP.DustType("Kaolinite"), hom_linear=True)
+o = [torch.empty_like(c[0]) for _ in fused.OUT_NAMES]
+report("fused 1M+2M+ice nucleation(+ARG) f64 2^24 per GPU (config 5)", n5,
+       timeit(lambda: fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *c, out=o), reps=10), 176)
