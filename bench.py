@@ -123,6 +123,7 @@ def reference_arm(args):
     st = synthetic_states_2m(n, seed=1234)
     block = CMP.pack_2m_warm(CMP.Microphysics2MParams(np.float64), CMP.ThermodynamicsParameters(np.float64))
     cols = [st[k] for k in KEYS]
+    orc.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     threads = orc.num_threads()
     for _ in range(args.warmup):
         orc.bmt2m_warm(block, *cols)
@@ -298,6 +299,7 @@ def main():
 
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as orc
+        orc.set_num_threads(os.cpu_count() or 1)
         m = min(args.cpu_sample, n)
         block = CMP.pack_2m_warm(mp, tps)
         sample = [st[k][:m] for k in KEYS]

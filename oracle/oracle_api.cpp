@@ -4,7 +4,7 @@
 // multithreaded driver of its own; hosts broadcast the scalar methods).
 #include <omp.h>
 
-#include "oracle_icenuc.hpp"
+#include "oracle_p3.hpp"
 
 using namespace orc;
 
@@ -288,6 +288,105 @@ int64_t oracle_arg_icenuc_bound_f64(const cumicro_params_icenuc_f64* p, int64_t 
             }
         }
     }
+    return 0;
+}
+
+// ---- P3 (Float64 and error-bound evaluations; parameters are the Float64 block) -----------------
+// leaf: what = 0 gamma_inc P(a = x, x = y)   1 gamma_inc_inv(a = x, p = y, q = 1 - y)
+//              2 rime_mass_fraction(q_rim = x, q_ice = y)   3 rime_density(q_rim = x, b_rim = y)
+}  // extern "C"
+template <class FT> static void p3_leaf(int what, int64_t n, const double* x, const double* y, double* out, bool bound) {
+    for (int64_t i = 0; i < n; ++i) {
+        FT r = FT(0);
+        if (what == 0) { FT P, Q; gamma_inc<FT>(FT(x[i]), FT(y[i]), P, Q); r = P; }
+        else if (what == 1) r = gamma_inc_inv<FT>(FT(x[i]), FT(y[i]), FT(1) - FT(y[i]));
+        else if (what == 2) r = regularised_ratio<FT>(jmin(FT(x[i]), FT(y[i])), FT(y[i]));
+        else if (what == 3) r = regularised_ratio<FT>(FT(x[i]), FT(y[i]));
+        out[i] = bound ? Tr(r).e : val_(r);
+    }
+}
+extern "C" {
+int oracle_p3_leaf_f64(int what, int64_t n, const double* x, const double* y, double* out, int bound) {
+    if (bound) p3_leaf<Tr>(what, n, x, y, out, true); else p3_leaf<double>(what, n, x, y, out, false);
+    return 0;
+}
+
+// state-level functions over columns (L_ice, N_ice, F_rim | L_rim, rho_rim | B_rim, ...):
+// from_prognostic = 1: the third / fourth columns are (L_rim, B_rim) and the state comes from state_from_prognostic
+// outputs (each optional): thresholds[5] = rho_g, D_th, D_gr, D_cr, F_rim ; logl ; D_m ; v_n, v_m ; melt dN, dL ; self-collection dN ;
+// collisions[10] ; sources[7] ; max_freeze(Dbar) ; rime_density_local(Dbar, Dbar)
+}  // extern "C"
+template <class FT>
+static void p3_state_fns(const cumicro_params_p3_f64* p, int64_t n, int from_prognostic, const double* L_ice, const double* N_ice,
+                         const double* c3, const double* c4, const double* rho_a, const double* T, const double* logl_in,
+                         const double* L_c, const double* N_c, const double* L_r, const double* N_r, int logl_iters,
+                         double* const* thr, double* logl_out, double* Dm, double* v_n, double* v_m, double* melt_dN,
+                         double* melt_dL, double* selfcol, double* const* coll10, double* const* src7, double* maxfrz,
+                         double* rimeloc, bool bound) {
+    auto put = [&](double* dst, int64_t i, FT v) { if (dst) dst[i] = bound ? Tr(v).e : val_(v); };
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; ++i) {
+        P3State<FT> s = from_prognostic ? state_from_prognostic<FT>(p->scheme, FT(L_ice[i]), FT(N_ice[i]), FT(c3[i]), FT(c4[i]))
+                                        : make_p3_state<FT>(p->scheme, FT(L_ice[i]), FT(N_ice[i]), FT(c3[i]), FT(c4[i]));
+        if (thr) { put(thr[0], i, s.rho_g); put(thr[1], i, s.D_th); put(thr[2], i, s.D_gr); put(thr[3], i, s.D_cr); put(thr[4], i, s.F_rim); }
+        FT logl = logl_in ? FT(logl_in[i]) : get_distribution_loglambda<FT>(s, logl_iters);
+        put(logl_out, i, logl);
+        if (Dm) put(Dm, i, D_m<FT>(s, logl));
+        FT ra = rho_a ? FT(rho_a[i]) : FT(1.2), Ta = T ? FT(T[i]) : FT(270);
+        if (v_n || v_m) { FT a, b; ice_terminal_velocity_weighted<FT>(*p, ra, s, logl, FT(1e-6), a, b); put(v_n, i, a); put(v_m, i, b); }
+        if (melt_dN || melt_dL) { FT a, b; ice_melt<FT>(*p, Ta, ra, s, logl, a, b); put(melt_dN, i, a); put(melt_dL, i, b); }
+        if (selfcol) put(selfcol, i, ice_self_collection<FT>(*p, s, logl, ra));
+        if (coll10) {
+            Vec10<FT> r = liquid_ice_collisions<FT>(*p, s, logl, FT(L_c[i]), FT(N_c[i]), FT(L_r[i]), FT(N_r[i]), ra, Ta);
+            for (int k = 0; k < 10; ++k) put(coll10[k], i, r.v[k]);
+        }
+        if (src7) {
+            CollisionSources<FT> c = bulk_liquid_ice_collision_sources<FT>(*p, s, logl, FT(L_c[i]), FT(N_c[i]), FT(L_r[i]), FT(N_r[i]), ra, Ta);
+            FT v[7] = {c.dq_c, c.dq_r, c.dN_c, c.dN_r, c.dL_rim, c.dL_ice, c.dB_rim};
+            for (int k = 0; k < 7; ++k) put(src7[k], i, v[k]);
+        }
+        if (maxfrz || rimeloc) {
+            using PP = cumicro_params_p3_f64;
+            CollisionCtx<FT, PP> c;
+            c.p = p; c.s = &s; c.rho_a = ra; c.T = Ta; c.rho_w = FT(p->warm.sb.pdf_c.rho_w);
+            c.v_ice = ice_particle_terminal_velocity<FT>(*p, ra, s);
+            c.v_liq = rain_particle_terminal_velocity<FT>(*p, ra);
+            FT Dbar = exp_(-logl);
+            put(maxfrz, i, max_freeze_rate<FT>(*p, c, Dbar));
+            put(rimeloc, i, c.rho_rim_local(Dbar, Dbar));
+        }
+    }
+}
+extern "C" {
+int oracle_p3_state_f64(const cumicro_params_p3_f64* p, int64_t n, int from_prognostic, const double* L_ice, const double* N_ice,
+                        const double* c3, const double* c4, const double* rho_a, const double* T, const double* logl_in,
+                        const double* L_c, const double* N_c, const double* L_r, const double* N_r, int logl_iters,
+                        double* const* thr, double* logl_out, double* Dm, double* v_n, double* v_m, double* melt_dN, double* melt_dL,
+                        double* selfcol, double* const* coll10, double* const* src7, double* maxfrz, double* rimeloc, int bound) {
+    if (bound)
+        p3_state_fns<Tr>(p, n, from_prognostic, L_ice, N_ice, c3, c4, rho_a, T, logl_in, L_c, N_c, L_r, N_r, logl_iters, thr, logl_out, Dm,
+                         v_n, v_m, melt_dN, melt_dL, selfcol, coll10, src7, maxfrz, rimeloc, true);
+    else
+        p3_state_fns<double>(p, n, from_prognostic, L_ice, N_ice, c3, c4, rho_a, T, logl_in, L_c, N_c, L_r, N_r, logl_iters, thr, logl_out,
+                             Dm, v_n, v_m, melt_dN, melt_dL, selfcol, coll10, src7, maxfrz, rimeloc, false);
+    return 0;
+}
+
+// BMT:898-1083 over columns: in13 = rho,T,q_tot,q_lcl,n_lcl,q_rai,n_rai,q_ice,n_ice,q_rim,b_rim,logl,inpc_log_shift ; out9
+}  // extern "C"
+template <class FT> static void bmt2m_p3_cols(const cumicro_params_p3_f64* p, int64_t n, const double* const* in, double* const* out, bool bound) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; ++i) {
+        BMT2MP3Out<FT> o = bmt2m_p3<FT>(*p, FT(in[0][i]), FT(in[1][i]), FT(in[2][i]), FT(in[3][i]), FT(in[4][i]), FT(in[5][i]), FT(in[6][i]),
+                                        FT(in[7][i]), FT(in[8][i]), FT(in[9][i]), FT(in[10][i]), FT(in[11][i]), in[12] ? FT(in[12][i]) : FT(0));
+        FT v[9] = {o.dq_lcl, o.dn_lcl, o.dq_rai, o.dn_rai, o.dq_ice, o.dn_ice, o.dq_rim, o.db_rim, o.dn_act};
+        for (int k = 0; k < 9; ++k)
+            if (out[k]) out[k][i] = bound ? Tr(v[k]).e : val_(v[k]);
+    }
+}
+extern "C" {
+int oracle_bmt2m_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in13, double* const* out9, int bound) {
+    if (bound) bmt2m_p3_cols<Tr>(p, n, in13, out9, true); else bmt2m_p3_cols<double>(p, n, in13, out9, false);
     return 0;
 }
 
