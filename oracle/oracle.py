@@ -221,3 +221,81 @@ def arg_icenuc(params, T, p, w, q_tot, q_liq, q_ice, N_liq, N_ice, bound=False):
               _ptr(out["J_ABIFM"]), _ptr(out["J_hom"]), _ptr(out["da_w"]))
     out["n_domain_errors"] = int(nerr)
     return out
+
+
+# ---- P3 ice scheme (oracle_p3.hpp; Float64 parameter block) -----------------------------------
+P3_LEAF = {"gamma_inc_P": 0, "gamma_inc_inv": 1, "rime_mass_fraction": 2, "rime_density": 3}
+P3_COLL10 = ("QCFRZ", "QCSHD", "NCCOL", "QRFRZ", "QRSHD", "NRCOL", "M_col", "BCCOL", "BRCOL", "wet_M_col")
+P3_SRC7 = ("dq_c", "dq_r", "dN_c", "dN_r", "dL_rim", "dL_ice", "dB_rim")
+P3_THR = ("rho_g", "D_th", "D_gr", "D_cr", "F_rim")
+P3_BMT_IN = ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim", "logl")
+P3_BMT_OUT = ("dq_lcl_dt", "dn_lcl_dt", "dq_rai_dt", "dn_rai_dt", "dq_ice_dt", "dn_ice_dt", "dq_rim_dt", "db_rim_dt",
+              "dn_lcl_activation_dt")
+
+
+def p3_leaf(what, x, y, bound=False):
+    """UT.gamma_inc / gamma_inc_inv / rime_mass_fraction / rime_density over arrays."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(x)
+    st = lib().oracle_p3_leaf_f64(C.c_int(P3_LEAF[what]), C.c_int64(x.size), _ptr(x), _ptr(y), _ptr(out), C.c_int(int(bound)))
+    assert st == 0
+    return out
+
+
+def p3_state(params, L_ice, N_ice, c3, c4, *, from_prognostic=False, rho_a=None, T=None, logl=None, L_c=None, N_c=None, L_r=None,
+             N_r=None, logl_iters=-1, want=("logl",), bound=False):
+    """State-level P3 functions over columns.  (c3, c4) = (F_rim, rho_rim), or (L_rim, B_rim) with
+    ``from_prognostic``.  ``logl=None`` solves get_distribution_logλ (``logl_iters`` Brent iterations,
+    -1 = the reference's 10 / 8).  ``want`` selects outputs among: thresholds, logl, D_m, v_n, v_m, melt,
+    selfcol, coll10, src7, max_freeze, rime_local."""
+    assert type(params).__name__.endswith("p3_f64")
+    req = [L_ice, N_ice, c3, c4]
+    (L_ice, N_ice, c3, c4), n = _cols(req, np.float64)
+    opt = {}
+    for k, v in dict(rho_a=rho_a, T=T, logl=logl, L_c=L_c, N_c=N_c, L_r=L_r, N_r=N_r).items():
+        opt[k] = None if v is None else np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)))
+    new = lambda: np.empty(n, np.float64)
+    out = {}
+    thr = None
+    if "thresholds" in want:
+        for k in P3_THR:
+            out[k] = new()
+        thr = (C.c_void_p * 5)(*[_ptr(out[k]) for k in P3_THR])
+    for k in ("logl", "D_m", "v_n", "v_m", "selfcol", "max_freeze", "rime_local"):
+        if k in want:
+            out[k] = new()
+    if "melt" in want:
+        out["melt_dN"], out["melt_dL"] = new(), new()
+    c10 = s7 = None
+    if "coll10" in want:
+        for k in P3_COLL10:
+            out[k] = new()
+        c10 = (C.c_void_p * 10)(*[_ptr(out[k]) for k in P3_COLL10])
+    if "src7" in want:
+        for k in P3_SRC7:
+            out[k] = new()
+        s7 = (C.c_void_p * 7)(*[_ptr(out[k]) for k in P3_SRC7])
+    if ("coll10" in want or "src7" in want) and any(opt[k] is None for k in ("L_c", "N_c", "L_r", "N_r")):
+        raise ValueError("collisions need L_c, N_c, L_r, N_r")
+    g = lambda k: _ptr(out[k]) if k in out else None
+    st = lib().oracle_p3_state_f64(
+        C.byref(params), C.c_int64(n), C.c_int(int(from_prognostic)), _ptr(L_ice), _ptr(N_ice), _ptr(c3), _ptr(c4),
+        _ptr(opt["rho_a"]), _ptr(opt["T"]), _ptr(opt["logl"]), _ptr(opt["L_c"]), _ptr(opt["N_c"]), _ptr(opt["L_r"]), _ptr(opt["N_r"]),
+        C.c_int(logl_iters), thr, g("logl"), g("D_m"), g("v_n"), g("v_m"), g("melt_dN"), g("melt_dL"), g("selfcol"), c10, s7,
+        g("max_freeze"), g("rime_local"), C.c_int(int(bound)))
+    assert st == 0
+    return out
+
+
+def bmt2m_p3(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl, inpc_log_shift=None, bound=False):
+    """BMT:898-1083 over arrays -> dict of the 9 tendencies."""
+    assert type(params).__name__.endswith("p3_f64")
+    cols, n = _cols((rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl), np.float64)
+    shift = None if inpc_log_shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(inpc_log_shift, np.float64), (n,)))
+    in13 = (C.c_void_p * 13)(*([_ptr(a) for a in cols] + [_ptr(shift)]))
+    out = {k: np.empty(n, np.float64) for k in P3_BMT_OUT}
+    o9 = (C.c_void_p * 9)(*[_ptr(out[k]) for k in P3_BMT_OUT])
+    st = lib().oracle_bmt2m_p3_f64(C.byref(params), C.c_int64(n), in13, o9, C.c_int(int(bound)))
+    assert st == 0
+    return out
