@@ -1,0 +1,96 @@
+"""Array methods of the reference's ``CloudMicrophysics.P3Scheme`` module (``src/P3.jl`` and
+``src/P3_*.jl``) over structure-of-arrays CUDA columns.
+
+Names and argument order follow the reference's pointwise wrappers that hosts broadcast
+(``test/gpu_clima_core_test.jl:35-43, 134-138``):
+
+* ``get_distribution_logλ_from_prognostic(params, ρq_ice, ρn_ice, ρq_rim, ρb_rim)``
+  (P3_size_distribution.jl:329-334)
+* ``ice_terminal_velocity_number_weighted_from_prognostic`` /
+  ``ice_terminal_velocity_mass_weighted_from_prognostic(velocity_params, ρₐ, params, ρq_ice, ρn_ice,
+  ρq_rim, ρb_rim, logλ; quad)`` (P3_terminal_velocity.jl:135-173)
+* ``process_rates(mp, tps, ρ, T, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ)``: the
+  stand-alone P3 integrals of one state in one launch (velocities, ``ice_melt``,
+  ``ice_self_collection``, ``bulk_liquid_ice_collision_sources``).
+
+``params`` / ``velocity_params`` are carried by the flattened block, so these methods take the
+``Microphysics2MParams`` object ``mp`` (built ``with_ice=True``) and ``tps``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from . import parameters as CMP
+from . import parameters_p3 as CMP3
+from ._columns import Tendencies, check_columns, ptr, ptr_table, stream_handle
+
+from .parameters_p3 import ChebyshevGauss, GaussLegendre, build_quadrature  # noqa: F401  (re-exported like P3.jl)
+
+RATE_NAMES = ("v_n", "v_m", "melt_dNdt", "melt_dLdt", "self_collection_dNdt", "dq_c", "dq_r", "dN_c", "dN_r", "dL_rim", "dL_ice",
+              "dB_rim")
+
+
+def _block(mp, tps, suf, quad):
+    blk = CMP3.pack_p3(mp, tps, quad=quad)
+    if not type(blk).__name__.endswith(suf):
+        raise TypeError(f"parameter float type does not match the columns ({suf})")
+    return blk
+
+
+def get_distribution_logλ_from_prognostic(mp, tps, ρq_ice, ρn_ice, ρq_rim, ρb_rim, *, brent_iters=0, out=None):
+    cols = [ρq_ice, ρn_ice, ρq_rim, ρb_rim]
+    suf, n, dev = check_columns(cols, ["ρq_ice", "ρn_ice", "ρq_rim", "ρb_rim"])
+    blk = _block(mp, tps, suf, None)
+    out = out if out is not None else torch.empty_like(ρq_ice)
+    check_columns([ρq_ice, out], ["ρq_ice", "out"])
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_p3_logl_{suf}")(C.byref(blk), C.c_int64(n), *[ptr(c) for c in cols], C.c_int(brent_iters),
+                                                           ptr(out), stream_handle(dev))
+    _abi.check(st, "cumicro_p3_logl")
+    return out
+
+
+get_distribution_loglambda_from_prognostic = get_distribution_logλ_from_prognostic
+
+
+def _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, want_n, want_m):
+    cols = [ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ]
+    suf, n, dev = check_columns(cols, ["ρₐ", "ρq_ice", "ρn_ice", "ρq_rim", "ρb_rim", "logλ"])
+    blk = _block(mp, tps, suf, quad)
+    v_n = torch.empty_like(ρₐ) if want_n else None
+    v_m = torch.empty_like(ρₐ) if want_m else None
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_termvel_p3_{suf}")(C.byref(blk), C.c_int64(n), *[ptr(c) for c in cols], ptr(v_n), ptr(v_m),
+                                                              stream_handle(dev))
+    _abi.check(st, "cumicro_termvel_p3")
+    return v_n, v_m
+
+
+def ice_terminal_velocity_number_weighted_from_prognostic(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, *, quad=None):
+    return _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, True, False)[0]
+
+
+def ice_terminal_velocity_mass_weighted_from_prognostic(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, *, quad=None):
+    return _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, False, True)[1]
+
+
+def ice_terminal_velocities_from_prognostic(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, *, quad=None):
+    """Both weighted velocities from one pass over the quadrature nodes."""
+    return _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, True, True)
+
+
+def process_rates(mp, tps, ρ, T, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ, *, quad=None, which=None):
+    """Stand-alone P3 integrals (BASELINE config 4) -> Tendencies with RATE_NAMES (``which`` selects a subset)."""
+    cols = [ρ, T, ρ, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ]   # slot 2 (q_tot) is not read
+    suf, n, dev = check_columns(cols, ["ρ", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim", "logλ"])
+    blk = _block(mp, tps, suf, quad)
+    names = RATE_NAMES if which is None else tuple(which)
+    outs = {k: torch.empty_like(ρ) for k in names}
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_p3_rates_{suf}")(C.byref(blk), C.c_int64(n), ptr_table(cols),
+                                                            ptr_table([outs.get(k) for k in RATE_NAMES]), stream_handle(dev))
+    _abi.check(st, "cumicro_p3_rates")
+    return Tendencies(**outs)

@@ -16,7 +16,8 @@ def __getattr__(name):  # torch-dependent modules are imported on first use
             "Microphysics1M": "Microphysics1M", "CM1": "Microphysics1M",
             "AerosolActivation": "AerosolActivation", "AA": "AerosolActivation",
             "AerosolModel": "AerosolModel", "AM": "AerosolModel",
-            "IceNucleation": "IceNucleation", "IN": "IceNucleation", "fused": "fused"}
+            "IceNucleation": "IceNucleation", "IN": "IceNucleation", "fused": "fused",
+            "P3Scheme": "P3Scheme", "P3": "P3Scheme", "CMP3": "parameters_p3"}
     if name in lazy:
         return importlib.import_module("." + lazy[name], __name__)
     raise AttributeError(name)

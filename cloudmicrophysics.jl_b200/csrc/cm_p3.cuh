@@ -1,0 +1,747 @@
+// cm_p3.cuh — P3 ice scheme: particle properties, size distribution, incomplete-gamma
+// utilities, quadrature-based process rates.
+//
+// Device form of src/P3_particle_properties.jl (:43-475), P3_size_distribution.jl (:8-237),
+// P3_integral_properties.jl (:34-45), P3_terminal_velocity.jl (:4-173), P3_processes.jl
+// (:64-712), src/Quadrature.jl (:62-125), UT.gamma_inc / gamma_inc_inv (UT:92-252), the
+// regularised ratios (UT:445-509) and the PSD closures / bounds of CM2 (CM2:176-355).
+//
+// Work decomposition (one WARP per ice-bearing grid point).  Every integral of
+// the reference is a fixed-order quadrature over up to 4 mass-regime segments, so one point is
+// ~2e6 FP64 instructions of perfectly regular work:
+//   * the outer quadrature nodes (4 segments x n) are spread over the 32 lanes, partial sums
+//     are combined with warp shuffles;
+//   * everything that does not depend on the outer ice diameter is evaluated ONCE per point and
+//     staged in shared memory: the cloud / rain inner nodes (D, w n(D), m(D), v(D)), and for the
+//     closed-form rain integral the 24 (z, α) incomplete-gamma pairs at the two fixed ends of
+//     the rain spectrum together with Γ(z)/α^z (the reference re-evaluates 96 gamma_inc per outer
+//     node; 24 remain, at the crossover diameter);
+//   * all powers D^b are exp(b log D) from one logarithm per node.
+// The fixed iteration counts of the reference (30 / 20 gamma_inc terms, 10 / 8 Brent steps) are
+// kept: their truncation error is part of the reference's result.
+#pragma once
+#include "cm_sb2006.cuh"
+
+namespace cm {
+
+constexpr int kQuadMax = 128;
+constexpr int kGam = 24;          // (z, α) pairs of closed_rain_inner_NM: 4 velocity terms x (p + i) in 0..5
+
+// ---- UT.gamma_inc: series (x < a + 1) or Lentz continued fraction, fixed iterations   UT:92-144
+// The series loop leaves early once a term is below half an ulp of the sum: the terms decrease
+// monotonically (x/(a+k) < 1), so every later addition is a no-op and the result is bit-identical
+// to the full loop.
+CM_HD void gamma_inc_(double a, double x, double lga, int iters, double& P, double& Q) {
+    if (x <= 0.0) { P = 0.0; Q = 1.0; return; }
+    if (x == num<double>::inf()) { P = 1.0; Q = 0.0; return; }
+    const double factor = exp_full_(a * logp_(x) - x - lga);
+    if (x < a + 1.0) {
+        double term = div_(1.0, a);
+        double sum = term;
+        for (int k = 1; k <= iters; ++k) {
+            term *= x * rcp_(a + (double)k);
+            sum += term;
+            if (term < sum * 5.5e-17) break;
+        }
+        P = clamp_(factor * sum, 0.0, 1.0);
+        Q = 1.0 - P;
+    } else {
+        const double tiny = 1e-30;
+        const double b1 = x + 1.0 - a;
+        double c = b1 + 1.0 / tiny;
+        double d = rcp_(b1);
+        double h = d;
+        for (int k = 1; k <= iters; ++k) {
+            const double kd = (double)k;
+            const double a_k = -kd * (kd - a);
+            const double b_k = x + 2.0 * kd + 1.0 - a;
+            const double d_tmp = b_k + a_k * d;
+            d = (fabs(d_tmp) < tiny) ? tiny : d_tmp;
+            const double c_tmp = b_k + a_k * rcp_(c);
+            c = (fabs(c_tmp) < tiny) ? tiny : c_tmp;
+            d = rcp_(d);
+            h *= c * d;
+        }
+        Q = clamp_(factor * h, 0.0, 1.0);
+        P = 1.0 - Q;
+    }
+}
+
+// ---- UT.gamma_inc_inv: Halley, <= 15 steps with the reference's exits                UT:205-252
+CM_HD double gamma_inc_inv_(double a, double p, double q, int iters, double eps) {
+    if (p <= 0.0) return 0.0;
+    if (q <= 0.0) return num<double>::inf();
+    double x = (p < 0.5) ? pow_full_(p * tgamma_(a + 1.0), 1.0 / a) : (a - log_full_(q));
+    const bool use_q = p > 0.5;
+    const double lga = lgamma_(a);
+    for (int i = 1; i <= 15; ++i) {
+        double P, Q;
+        gamma_inc_(a, x, lga, iters, P, Q);
+        const double f = use_q ? Q - q : P - p;
+        double fprime = exp_full_((a - 1.0) * log_full_(x) - x - lga);
+        fprime = use_q ? -fprime : fprime;
+        if (fprime == 0.0) break;
+        const double f2 = (a - 1.0 - x) / x;
+        double step = f / (fprime * (1.0 - 0.5 * f * f2 / fprime));
+        if (x - step <= 0.0) step = 0.5 * x;
+        x = x - step;
+        if (fabs(step) < eps * x) break;
+    }
+    return x;
+}
+
+// ---- UT.sgs_weight_function / _regularised_ratio                                   UT:445-485
+CM_HD double regularised_ratio_(double num_, double den, double eps) {
+    double w;
+    if (den < 0.0) w = 0.0;
+    else if (den > fmin(1.0, 42.0 * eps)) w = 1.0;
+    else if (4.0 * den < eps) w = 0.0;
+    else w = (1.0 + tanh(2.0 * atanh(1.0 - 2.0 * pow(1.0 - den, -1.0 / log2(1.0 - eps))))) / 2.0;
+    return (den < eps * eps) ? 0.0 : w * num_ / den;
+}
+
+// ---- host-derived constants of one launch ------------------------------------------------------
+struct P3K {
+    // ParametersP3
+    double alpha_va, beta_va, gamma_a, sigma_a;
+    double slope_a, slope_b, slope_c, mu_max, mu_const;
+    double vent_a, vent_b, rim_a, rim_b, rim_c, rim_rho_ice, rim8;
+    double tau_wet, rho_i, rho_l08, T_freeze;
+    int slope_power_law, aspect_oblate;
+    // thresholds: (6 α_va / (π ρ))^(1/(3 - β_va))
+    double thr_p, thr_coef, D_th;
+    double pi6, phi_coef;                 // π/6, 3 sqrt(π)/4
+    // air
+    double cbrt_Nsc, inv_nu_air, K_therm, D_vapor;
+    // Chen 2022 ice tables at ρᵢ = 916.7 (hard-coded in the reference, P3_terminal_velocity.jl:32)
+    double As, Bs, Cs, Es, Fs, Gs1000, Al, Bl, Cl, El, Fl, Gl1000, Hl, cutoff;
+    // liquid PSDs
+    double rho_w, mliq_coef, m_shd, log_km;
+    double nu_cD, mu_cD, cloud_log_z_lo, cloud_log_z_hi;      // log gamma_inc_inv((νcD+1)/μcD, p | 1-p), p = 1e-5
+    double rain_cll_lo, rain_cll_hi;                        // cloglog(p), cloglog(1 - p)
+    // Bigg / F23
+    double het_a, het_B, tau_act, m_nuc, V1, cloud_M3_ratio, cloud_M6_ratio, frost_b, frost_log_a, frost_T_freeze;
+    double subdep_tau;
+    int n, gamma_iters, brent_iters;
+    double eps;
+};
+
+__host__ inline P3K make_p3_k(const cumicro_params_p3_f64& p, bool method_is_f32) {
+    P3K k{};
+    const double pi = 3.141592653589793;
+    const auto& s = p.scheme;
+    k.eps = method_is_f32 ? 1.1920928955078125e-07 : 2.220446049250313e-16;
+    k.gamma_iters = method_is_f32 ? 20 : 30;
+    k.brent_iters = method_is_f32 ? 8 : 10;
+    k.alpha_va = s.alpha_va; k.beta_va = s.beta_va; k.gamma_a = s.gamma; k.sigma_a = s.sigma;
+    k.slope_a = s.slope_a; k.slope_b = s.slope_b; k.slope_c = s.slope_c; k.mu_max = s.slope_mu_max; k.mu_const = s.slope_mu_const;
+    k.vent_a = s.vent_a; k.vent_b = s.vent_b; k.rim_a = s.rim_a; k.rim_b = s.rim_b; k.rim_c = s.rim_c; k.rim_rho_ice = s.rim_rho_ice;
+    k.rim8 = s.rim_a + s.rim_b * 8.0 + s.rim_c * (8.0 * 8.0);
+    k.tau_wet = s.tau_wet; k.rho_i = s.rho_i; k.rho_l08 = 0.8 * s.rho_l; k.T_freeze = s.T_freeze;
+    k.slope_power_law = s.slope_power_law; k.aspect_oblate = s.aspect_oblate;
+    k.thr_p = 1.0 / (3.0 - s.beta_va);
+    k.thr_coef = 6.0 * s.alpha_va;
+    k.D_th = std::pow(6.0 * s.alpha_va / (pi * s.rho_i), 1.0 / (3.0 - s.beta_va));
+    k.pi6 = pi / 6.0;
+    k.phi_coef = 3.0 * std::sqrt(pi);
+    const auto& aps = p.warm.aps;
+    k.cbrt_Nsc = std::cbrt(aps.nu_air / aps.D_vapor);
+    k.inv_nu_air = 1.0 / aps.nu_air; k.K_therm = aps.K_therm; k.D_vapor = aps.D_vapor;
+    {   // CO.Chen2022_vel_coeffs small / large ice, ρᵢ-only parts                      CO:302-349
+        const double ri = 916.7, l = std::log(ri), sq = std::sqrt(ri);
+        const auto& c = p.vel_small_ice;
+        k.As = c.A[1] * (l * l) - c.A[2] * l + c.A[0];
+        k.Bs = 1.0 / (c.B[0] + c.B[1] * l + c.B[2] / sq);
+        k.Cs = c.C[0] + c.C[1] * std::exp(c.C[2] * ri) + c.C[3] * sq;
+        k.Es = c.E[0] - c.E[1] * (l * l) + c.E[2] * sq;
+        k.Fs = -std::exp(c.F[0] - c.F[1] * (l * l) + c.F[2] * l);
+        k.Gs1000 = 1.0 / (c.G[0] + c.G[1] / l - c.G[2] * l / ri) * 1000.0;
+        const auto& g = p.vel_large_ice;
+        k.Al = g.A[0] + g.A[1] * l + g.A[2] / (ri * sq);
+        k.Bl = std::exp(g.B[0] + g.B[1] * (l * l) + g.B[2] * l);
+        k.Cl = std::exp(g.C[0] + g.C[1] / l + g.C[2] / ri);
+        k.El = g.E[0] + g.E[1] * l * sq + g.E[2] * sq;
+        k.Fl = g.F[0] + g.F[1] * l - std::exp(std::log(-g.F[2]) - ri);
+        k.Gl1000 = 1.0 / (g.G[0] + g.G[1] * l * sq + g.G[2] / sq) * 1000.0;
+        k.Hl = g.H[0] + g.H[1] * (ri * ri) * sq + std::exp(std::log(-g.H[2]) - ri);
+        k.cutoff = c.cutoff;
+    }
+    const auto& pc = p.warm.sb.pdf_c;
+    k.rho_w = pc.rho_w;
+    k.mliq_coef = pc.rho_w;                                   // m_liq(D) = ρw (D³ π / 6)
+    k.m_shd = pc.rho_w * (1e-3 * 1e-3 * 1e-3 * pi / 6.0);
+    k.log_km = std::log(pc.rho_w * pi / 6.0);
+    k.nu_cD = 3.0 * pc.nu_c + 2.0;
+    k.mu_cD = 3.0 * pc.mu_c;
+    {
+        const double pq = 0.00001, Y1 = 1.0 - pq, a = (k.nu_cD + 1.0) / k.mu_cD;
+        k.cloud_log_z_lo = std::log(gamma_inc_inv_(a, pq, 1.0 - pq, k.gamma_iters, k.eps));
+        k.cloud_log_z_hi = std::log(gamma_inc_inv_(a, Y1, 1.0 - Y1, k.gamma_iters, k.eps));
+        k.rain_cll_lo = std::log(-std::log1p(-pq));
+        k.rain_cll_hi = std::log(-std::log1p(-Y1));
+        k.cloud_M3_ratio = std::tgamma((k.nu_cD + 1.0 + 3.0) / k.mu_cD) / std::tgamma((k.nu_cD + 1.0) / k.mu_cD);
+        k.cloud_M6_ratio = std::tgamma((k.nu_cD + 1.0 + 6.0) / k.mu_cD) / std::tgamma((k.nu_cD + 1.0) / k.mu_cD);
+    }
+    k.het_a = p.rain_freezing_het_a; k.het_B = p.rain_freezing_het_B; k.tau_act = p.tau_act;
+    k.m_nuc = s.rho_i * (10e-6 * 10e-6 * 10e-6 * pi / 6.0);
+    k.V1 = pi / 6.0;
+    k.frost_b = p.ice_nucleation.b; k.frost_log_a = p.ice_nucleation.log_a; k.frost_T_freeze = p.ice_nucleation.T_freeze;
+    k.subdep_tau = p.warm.subdep_tau_relax;
+    k.n = p.quad.n;
+    return k;
+}
+
+#ifdef __CUDACC__
+CM_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+CM_DEV double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Per-warp scratch in shared memory (sized for the launch's quadrature order n).
+struct P3Scratch {
+    double* cD;    // cloud inner nodes: diameter
+    double* cWN;   //   w_j n_c(D_j)
+    double* cM;    //   m_liq(D_j)
+    double* cV;    //   v_liq(D_j)
+    double* rD;    // rain inner nodes
+    double* rWNM;  //   w_j n_r(D_j) m_liq(D_j)
+    double* rV;
+    double* gz;    // [kGam] z_k
+    double* glg;   // [kGam] loggamma(z_k)
+    double* gG;    // [kGam] Γ(z_k) / α_k^z_k
+    double* gP0;   // [kGam] P, Q at α_k D_min and α_k D_max
+    double* gQ0;
+    double* gP1;
+    double* gQ1;
+    __host__ __device__ static constexpr int doubles(int n) { return 7 * n + 7 * kGam; }
+    __device__ void bind(double* base, int n) {
+        cD = base; cWN = cD + n; cM = cWN + n; cV = cM + n; rD = cV + n; rWNM = rD + n; rV = rWNM + n;
+        gz = rV + n; glg = gz + kGam; gG = glg + kGam; gP0 = gG + kGam; gQ0 = gP0 + kGam; gP1 = gQ0 + kGam; gQ1 = gP1 + kGam;
+    }
+};
+
+// One ice-bearing grid point, evaluated cooperatively by the 32 lanes of a warp.  All members are
+// warp-uniform.
+struct P3Point {
+    // inputs
+    double rho, T, L_ice, N_ice, F_rim, rho_rim;
+    // P3State thresholds                                        P3_particle_properties.jl:43-56
+    double rho_g, D_gr, D_cr;
+    // mass regime coefficients: a D^b as exp(la + b log D)
+    double la_small, la_unr, la_grp, la_part;
+    // PSD
+    double mu, logN0, lam;
+    // Chen velocity curves at this air density
+    double sa0, sa1, sb, sc1;          // small ice: a0 D^b + a1 D^b e^{-c1 D}
+    double ga0, ga1, gb0, gb1, gc1;    // large ice
+    double ra[3], rb[3], rc[3];        // rain / cloud liquid
+
+    CM_DEV int regime(double D, const P3K& k) const {
+        return (D < k.D_th) ? 0 : ((F_rim == 0.0) ? 1 : ((D < D_gr) ? 2 : ((D < D_cr) ? 3 : 4)));
+    }
+    // everything the integrands need at one ice diameter
+    struct Node { double logD, mass, dmass_dD_overD, area, v, n; };
+    template <bool NEED_V>
+    CM_DEV Node node(double D, const P3K& k) const {
+        Node o;
+        const double lD = logp_(D);
+        o.logD = lD;
+        const int r = regime(D, k);
+        const double la = (r == 0) ? la_small : ((r == 3) ? la_grp : ((r == 4) ? la_part : la_unr));
+        const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
+        o.mass = exp_(fma_(b, lD, la));
+        // ∂m/∂D / D = a b D^(b-2)
+        o.dmass_dD_overD = b * exp_(fma_(b - 2.0, lD, la));
+        const double sph = D * D * (num<double>::pi() / 4.0);
+        const double non = k.gamma_a * exp_(k.sigma_a * lD);
+        o.area = (r == 0 || r == 3) ? sph : ((r == 4) ? F_rim * sph + (1.0 - F_rim) * non : non);
+        o.n = exp_full_(logN0 + mu * lD - lam * D);
+        if (NEED_V) {
+            double v;
+            if (D <= k.cutoff) {
+                const double pw = exp_(sb * lD);
+                v = sa0 * pw + sa1 * pw * exp_full_(-sc1 * D);
+            } else {
+                v = ga0 * exp_(gb0 * lD) + ga1 * exp_full_(fma_(gb1, lD, -gc1 * D));
+            }
+            if (k.aspect_oblate) {
+                const double rho_m = (r == 3) ? rho_g : k.rho_i;
+                const double phi = k.phi_coef * o.mass / (4.0 * rho_m * o.area * sqrt_(o.area));
+                v *= cbrtp_(phi);
+            }
+            o.v = v;
+        } else {
+            o.v = 0.0;
+        }
+        return o;
+    }
+    CM_DEV double v_liq(double D, double lD) const {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v += ra[j] * exp_full_(fma_(rb[j], lD, -rc[j] * D));
+        return v;
+    }
+    CM_DEV double v_liq(double D) const { return v_liq(D, logp_(D)); }
+};
+
+// P3.state_from_prognostic + P3State + PSD parameters + velocity coefficients
+CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K& k, double rho, double T, double L_ice, double N_ice,
+                          double L_rim, double B_rim, double logl) {
+    s.rho = rho; s.T = T; s.L_ice = L_ice; s.N_ice = N_ice;
+    s.F_rim = fmin_(regularised_ratio_(fmin_(L_rim, L_ice), L_ice, k.eps), 1.0 - k.eps);
+    s.rho_rim = fmin_(regularised_ratio_(L_rim, B_rim, k.eps), k.rho_l08);
+    // get_ρ_d (exprel form)                                            P3_particle_properties.jl:191-199
+    const double pp = k.thr_p;
+    const double logFu = log1p_(-s.F_rim);
+    auto exprel1 = [](double x) { return expm1_(x) / x; };
+    auto exprel2 = [](double x) {
+        if (fabs(x) < 0.2) {
+            double r = 1.0 / 362880.0;
+            const double c[7] = {1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 1.0 / 2.0};
+#pragma unroll
+            for (int i = 0; i < 7; ++i) r = r * x + c[i];
+            return r;
+        }
+        return (expm1_(x) - x) / (x * x);
+    };
+    const double phi1 = exprel1(logFu);
+    const double phi1mp = exprel1((1.0 - pp) * logFu);
+    const double H = -pp * exprel2(-pp * logFu) - (1.0 - pp) * exprel2((1.0 - pp) * logFu);
+    const double G = H - phi1mp * phi1;
+    const double rho_d = -(s.rho_rim * phi1 * phi1mp) / G;
+    s.rho_g = s.F_rim * s.rho_rim + (1.0 - s.F_rim) * rho_d;
+    const bool unrimed = (s.F_rim == 0.0);
+    const double pi = num<double>::pi();
+    s.D_gr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * s.rho_g), pp);
+    s.D_cr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * (s.rho_g * (1.0 - s.F_rim))), pp);
+    // ice_mass_coeffs                                                 P3_particle_properties.jl:346-359
+    const double Fu = fmax_(1.0 - s.F_rim, k.eps);
+    s.la_small = log_full_(k.rho_i * pi / 6.0);
+    s.la_unr = log_full_(k.alpha_va);
+    s.la_grp = unrimed ? 0.0 : log_full_(s.rho_g * pi / 6.0);
+    s.la_part = log_full_(k.alpha_va / Fu);
+    // get_μ, get_logN₀                                               P3_size_distribution.jl:171-237
+    s.lam = exp_full_(logl);
+    s.mu = k.slope_power_law ? clamp_(k.slope_a * pow_full_(s.lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+    {
+        const double z = 0.0 + s.mu + 1.0;
+        s.logN0 = log_full_(N_ice) - (-z * logl + lgamma_(z) + 0.0);
+    }
+    // Chen 2022 coefficients at ρₐ                                     CO:290-349
+    const double ra_ = fmax_(rho, 0.0);
+    const double log1000 = 6.907755278982137;
+    {
+        const double pa = pow_full_(ra_, k.As);
+        const double b = k.Bs + ra_ * k.Cs;
+        const double u = exp_full_(b * log1000);
+        s.sa0 = (k.Es * pa) * u; s.sa1 = (k.Fs * pa) * u; s.sb = b; s.sc1 = k.Gs1000;
+        const double pl = pow_full_(ra_, k.Al);
+        s.ga0 = (k.Bl * pl) * exp_full_(k.Cl * log1000);
+        s.ga1 = (k.El * pl * exp_full_(k.Hl * ra_)) * exp_full_(k.Fl * log1000);
+        s.gb0 = k.Cl; s.gb1 = k.Fl; s.gc1 = k.Gl1000;
+    }
+    chen2022_vel_coeffs_rain<double>(p.vel_rain, rho, s.ra, s.rb, s.rc);
+}
+
+// P3.integral_bounds -> segment_boundaries                       P3_integral_properties.jl:34-45
+CM_DEV void p3_segments(const P3Point& s, const P3K& k, double D_min, double D_max, double (&b)[5]) {
+    b[0] = D_min;
+    b[1] = clamp_(k.D_th, D_min, D_max);
+    b[2] = clamp_(s.D_gr, D_min, D_max);
+    b[3] = clamp_(s.D_cr, D_min, D_max);
+    b[4] = D_max;
+}
+
+// Enumerates the quadrature nodes of the non-empty segments of b[0..4] across lanes:
+// node index t in [0, count) -> (x, weight * scale).  Quadrature.integrate   src/Quadrature.jl:62-125
+struct SegNodes {
+    double lo[4], hw[4];   // shift, scale of the active segments
+    int nact, n;
+    CM_DEV void init(const double (&b)[5], int n_) {
+        n = n_;
+        nact = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (b[i] < b[i + 1]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j == nact) { lo[j] = (b[i] + b[i + 1]) / 2.0; hw[j] = (b[i + 1] - b[i]) / 2.0; }
+                ++nact;
+            }
+    }
+    CM_DEV int count() const { return nact * n; }
+    CM_DEV void get(int t, const double* qx, const double* qw, double& x, double& w) const {
+        const int sgm = t / n, i = t - sgm * n;
+        double shift = lo[0], scale = hw[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+            if (sgm == j) { shift = lo[j]; scale = hw[j]; }
+        x = scale * qx[i] + shift;
+        w = qw[i] * scale;
+    }
+};
+
+// LocalRimeDensity callable                                        CMP/MicrophysicsP3.jl:222-239
+CM_DEV double local_rime_density(const P3K& k, double Ri) {
+    Ri = clamp_(Ri, 1.0, 12.0);
+    if (Ri <= 8.0) return k.rim_a + k.rim_b * Ri + k.rim_c * (Ri * Ri);
+    const double f = (Ri - 8.0) / (12.0 - 8.0);
+    return (1.0 - f) * k.rim8 + f * k.rim_rho_ice;
+}
+
+// RootSolvers.BrentsMethod with an always-false tolerance: Brent (1973), fixed iterations.
+// Same statement order as the oracle's restatement (oracle/oracle_p3.hpp brent_fixed).
+template <class F> CM_DEV double brent_fixed(F f, double a, double b, double fa, double fb, int iters) {
+    if (fabs(fa) < fabs(fb)) { double t = a; a = b; b = t; t = fa; fa = fb; fb = t; }
+    double c = a, fc = fa, d = c;
+    bool mflag = true;
+    for (int it = 0; it < iters; ++it) {
+        if (fb == 0.0) break;
+        double s;
+        if (fa != fc && fb != fc)
+            s = a * fb * fc / ((fa - fb) * (fa - fc)) + b * fa * fc / ((fb - fa) * (fb - fc)) + c * fa * fb / ((fc - fa) * (fc - fb));
+        else
+            s = b - fb * (b - a) / (fb - fa);
+        double lo = (3.0 * a + b) / 4.0, hi = b;
+        if (lo > hi) { const double t = lo; lo = hi; hi = t; }
+        const bool bis = !(s > lo && s < hi) || (mflag && fabs(s - b) >= fabs(b - c) / 2.0) || (!mflag && fabs(s - b) >= fabs(c - d) / 2.0);
+        if (bis) { s = (a + b) / 2.0; mflag = true; } else mflag = false;
+        const double fs = f(s);
+        d = c; c = b; fc = fb;
+        if (fa * fs < 0.0) { b = s; fb = fs; } else { a = s; fa = fs; }
+        if (fabs(fa) < fabs(fb)) { double t = a; a = b; b = t; t = fa; fa = fb; fb = t; }
+    }
+    return b;
+}
+
+struct P3Rates {
+    double v_n, v_m;                 // ice_terminal_velocity_{number,mass}_weighted
+    double melt_dN, melt_dL;         // ice_melt
+    double agg_dN;                   // ice_self_collection
+    double src[7];                   // bulk_liquid_ice_collision_sources: dq_c, dq_r, dN_c, dN_r, dL_rim, dL_ice, dB_rim
+};
+
+enum { P3_WANT_VEL = 1, P3_WANT_MELT = 2, P3_WANT_AGG = 4, P3_WANT_COLL = 8 };
+
+// The quantile pairs the requested integrals need (one Halley solve per lane).
+CM_DEV void p3_bounds(const P3Point& s, const P3K& k, int want, int lane, double (&bv)[5], double (&bc)[5], double (&ba)[5]) {
+    // lane 0,1: p = 1e-6 (velocities, melt)   2,3: p = 1e-5 (collisions)   4,5: p = eps (self-collection)
+    double x = 0.0;
+    if (lane < 6) {
+        const int g = lane >> 1;
+        const bool need = (g == 0) ? (want & (P3_WANT_VEL | P3_WANT_MELT)) : ((g == 1) ? (want & P3_WANT_COLL) : (want & P3_WANT_AGG));
+        if (need) {
+            const double pq = (g == 0) ? 1e-6 : ((g == 1) ? 0.00001 : k.eps);
+            const double Y = (lane & 1) ? (1.0 - pq) : pq;
+            x = gamma_inc_inv_(s.mu + 1.0, Y, 1.0 - Y, k.gamma_iters, k.eps) / s.lam;
+        }
+    }
+    p3_segments(s, k, bcast(x, 0), bcast(x, 1), bv);
+    p3_segments(s, k, bcast(x, 2), bcast(x, 3), bc);
+    p3_segments(s, k, bcast(x, 4), bcast(x, 5), ba);
+}
+
+// All requested P3 process rates of one point.  `qx`, `qw`: quadrature nodes / weights in shared
+// memory; `sc`: this warp's scratch.  L_c, N_c, L_r, N_r: volumetric liquid contents.
+CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, const P3K& k, const ThermoK<double>& tk,
+                           const SB2006K<double>& sk, const double* qx, const double* qw, P3Scratch& sc, int want, double L_c,
+                           double N_c, double L_r, double N_r, P3Rates& out) {
+    const int lane = threadIdx.x & 31;
+    const int n = k.n;
+    const double pi = num<double>::pi();
+    double bv[5], bc[5], ba[5];
+    p3_bounds(s, k, want, lane, bv, bc, ba);
+    SegNodes sn;
+
+    // ---- bulk terminal velocities + melt: single integrals over the p = 1e-6 bounds
+    //      P3_terminal_velocity.jl:73-133, P3_processes.jl:64-94
+    out.v_n = out.v_m = out.melt_dN = out.melt_dL = 0.0;
+    if (want & (P3_WANT_VEL | P3_WANT_MELT)) {
+        sn.init(bv, n);
+        double a_n = 0.0, a_m = 0.0, a_melt = 0.0;
+        for (int t = lane; t < sn.count(); t += 32) {
+            double D, w;
+            sn.get(t, qx, qw, D, w);
+            const P3Point::Node nd = s.node<true>(D, k);
+            const double nv = nd.n * nd.v;
+            a_n += nv * w;
+            a_m += nv * nd.mass * w;
+            const double Fv = k.vent_a + k.vent_b * k.cbrt_Nsc * sqrt_(D * nd.v * k.inv_nu_air);
+            a_melt += nd.dmass_dD_overD * Fv * nd.n * w;
+        }
+        const bool empty = (s.N_ice < k.eps) || (s.L_ice < k.eps);
+        if (want & P3_WANT_VEL) {
+            out.v_n = empty ? 0.0 : warp_sum(a_n) / s.N_ice;
+            out.v_m = empty ? 0.0 : warp_sum(a_m) / s.L_ice;
+        }
+        if ((want & P3_WANT_MELT) && s.T > tk.T_freeze) {
+            const double L_f = latent_heat_fusion(tk, s.T);
+            const double fac = 4.0 * k.K_therm / L_f * (s.T - k.T_freeze);
+            out.melt_dL = fmax_(0.0, fac * warp_sum(a_melt));
+            out.melt_dN = s.N_ice / s.L_ice * out.melt_dL;
+        }
+    }
+
+    // ---- ice self-collection: outer nodes by chunks of 32 (one per lane), inner 2n nodes across lanes
+    //      P3_processes.jl:676-712
+    out.agg_dN = 0.0;
+    if (want & P3_WANT_AGG) {
+        sn.init(ba, n);
+        const double D_lo = ba[0], D_hi = ba[4];
+        double acc = 0.0;
+        const int tot = sn.count();
+        for (int base = 0; base < tot; base += 32) {
+            double D1 = 0.0, v1 = 0.0, r1 = 0.0, W1 = 0.0;
+            if (base + lane < tot) {
+                double w;
+                sn.get(base + lane, qx, qw, D1, w);
+                const P3Point::Node nd = s.node<true>(D1, k);
+                v1 = nd.v;
+                r1 = sqrt_(nd.area / pi);
+                W1 = nd.n * w;
+            }
+            const int cnt = min(32, tot - base);
+            for (int t = 0; t < cnt; ++t) {
+                const double d1 = bcast(D1, t), vv1 = bcast(v1, t), rr1 = bcast(r1, t), ww1 = bcast(W1, t);
+                double part = 0.0;
+                for (int u = lane; u < 2 * n; u += 32) {
+                    const int half = (u >= n) ? 1 : 0;
+                    const int i = u - half * n;
+                    const double a = half ? d1 : D_lo, b = half ? D_hi : d1;
+                    if (a < b) {
+                        const double scale = (b - a) / 2.0, shift = (a + b) / 2.0;
+                        const double D2 = scale * qx[i] + shift;
+                        const P3Point::Node nd = s.node<true>(D2, k);
+                        const double r2 = sqrt_(nd.area / pi);
+                        const double K = pi * ((rr1 + r2) * (rr1 + r2));
+                        part += K * fabs(vv1 - nd.v) * nd.n * (qw[i] * scale);
+                    }
+                }
+                acc += part * ww1;
+            }
+        }
+        out.agg_dN = 0.5 * warp_sum(acc);
+    }
+
+    // ---- liquid-ice collisions                                          P3_processes.jl:112-655
+#pragma unroll
+    for (int i = 0; i < 7; ++i) out.src[i] = 0.0;
+    if (want & P3_WANT_COLL) {
+        const double e = k.eps;
+        const double rho = s.rho;
+        // cloud PSD n_c(D) = exp(logN0c + νcD log D - λc D^μcD) and its p-quantile bounds   CM2:203-236, 346-355
+        const double q_c = L_c / rho, q_r = L_r / rho;
+        const bool cloud_off = (N_c < e) || (q_c < e);
+        double logN0c, loglam_c, cb0, cb1;
+        {
+            const auto& pc = p.warm.sb.pdf_c;
+            const double safe_q = fmax_(q_c, e), safe_N = fmax_(N_c, e);
+            const double logx = log_full_(rho * safe_q / safe_N);
+            const double z1 = (pc.nu_c + 1.0) / pc.mu_c;
+            const double lB = -pc.mu_c * (logx + pc.loggamma_z1 - pc.loggamma_z2);
+            const double lA = log_full_(pc.mu_c) + log_full_(safe_N) + z1 * lB - pc.loggamma_z1;
+            logN0c = lA + log_full_(3.0) + (pc.nu_c + 1.0) * k.log_km;
+            loglam_c = lB + pc.mu_c * k.log_km;
+            cb0 = exp_full_((k.cloud_log_z_lo - loglam_c) / k.mu_cD);
+            cb1 = exp_full_((k.cloud_log_z_hi - loglam_c) / k.mu_cD);
+        }
+        // rain PSD, bounds                                                             CM2:270-276, 337-345
+        const RainPDF<double> rp = pdf_rain_parameters<double>(p.warm.sb.pdf_r, sk.pi_rho_w, e, q_r, rho, N_r);
+        double rb0 = 0.0, rb1 = 0.0;
+        if (!(rp.Dr_mean == 0.0)) {
+            const double lDr = log_full_(rp.Dr_mean);
+            rb0 = exp_full_(lDr + k.rain_cll_lo);
+            rb1 = exp_full_(lDr + k.rain_cll_hi);
+        }
+        const bool rain_on = !(rp.N0r == 0.0 || !(rb1 > rb0));
+        const bool cloud_on = !cloud_off && (cb0 < cb1);
+        const double TC = s.T - k.T_freeze;
+        const double two_TC = 2.0 * TC;
+
+        // inner nodes -> shared
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) {
+            {
+                const double scale = (cb1 - cb0) / 2.0, shift = (cb0 + cb1) / 2.0;
+                const double D = cloud_on ? scale * qx[j] + shift : 1e-6;
+                const double lD = logp_(D);
+                const double nc = exp_full_(logN0c + k.nu_cD * lD - exp_full_(fma_(k.mu_cD, lD, loglam_c)));
+                sc.cD[j] = D;
+                sc.cWN[j] = cloud_on ? nc * (qw[j] * scale) : 0.0;
+                sc.cM[j] = k.mliq_coef * (D * D * D * pi / 6.0);
+                sc.cV[j] = s.v_liq(D, lD);
+            }
+            {
+                const double scale = (rb1 - rb0) / 2.0, shift = (rb0 + rb1) / 2.0;
+                const double D = rain_on ? scale * qx[j] + shift : 1e-6;
+                const double lD = logp_(D);
+                const double nr = rp.N0r * exp_full_(-D / (rain_on ? rp.Dr_mean : 1.0));
+                sc.rD[j] = D;
+                sc.rWNM[j] = rain_on ? nr * (k.mliq_coef * (D * D * D * pi / 6.0)) * (qw[j] * scale) : 0.0;
+                sc.rV[j] = s.v_liq(D, lD);
+            }
+        }
+        // closed-form rain inner integral: the (z, α) table at the fixed ends       P3_processes.jl:344-369
+        const double lam_r = rain_on ? 1.0 / rp.Dr_mean : 1.0;
+        double vl_min = 0.0, vl_max = 0.0;
+        if (rain_on) {
+            vl_min = s.v_liq(rb0);
+            vl_max = s.v_liq(rb1);
+            if (lane < kGam) {
+                const int j = lane / 6, pi_ = lane - j * 6;     // velocity term (0: the v_i term), p + i
+                const double cj = (j == 0) ? 0.0 : s.rc[j - 1];
+                const double alpha = lam_r + cj;
+                const double p0v = (pi_ >= 3) ? 3.0 : 0.0;
+                const double pj = (j == 0) ? p0v : p0v + s.rb[j - 1];     // flux: p + bi[j]
+                const double z = (pj + (double)(pi_ - (int)p0v)) + 1.0;   // Iᵖ: p + (i - 1); gamma_inc_moment: z = p + 1
+                const double lg = lgamma_(z);
+                sc.gz[lane] = z;
+                sc.glg[lane] = lg;
+                sc.gG[lane] = tgamma_(z) / pow_full_(alpha, z);
+                double P, Q;
+                gamma_inc_(z, alpha * rb0, lg, k.gamma_iters, P, Q);
+                sc.gP0[lane] = P; sc.gQ0[lane] = Q;
+                gamma_inc_(z, alpha * rb1, lg, k.gamma_iters, P, Q);
+                sc.gP1[lane] = P; sc.gQ1[lane] = Q;
+            }
+        }
+        __syncwarp();
+
+        // compute_max_freeze_rate: the D-independent part                          P3_processes.jl:184-219
+        const double T_frz = tk.T_freeze;
+        const double dT = T_frz - s.T;
+        const TempState<double> ts_f = temp_state(tk, T_frz), ts_a = temp_state(tk, s.T);
+        const double drho_sat = rho * (p_sat_ice(tk, ts_f) / (tk.R_v * rho * T_frz) - p_sat_ice(tk, ts_a) / (tk.R_v * rho * s.T));
+        const double Lv = latent_heat_vapor(tk, s.T), L_f = latent_heat_fusion(tk, s.T);
+        const double denom = L_f - tk.cv_l * dT;
+        const double frz_num = k.K_therm * dT + Lv * k.D_vapor * drho_sat;
+        const double mfac = k.rho_w * (1.0 * 1.0 * 1.0 * pi / 6.0);
+
+        sn.init(bc, n);
+        double acc[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+        for (int t = lane; t < sn.count(); t += 32) {
+            double Di, w;
+            sn.get(t, qx, qw, Di, w);
+            const P3Point::Node nd = s.node<true>(Di, k);
+            const double v_i = nd.v;
+            const double r_i = sqrt_(nd.area / pi);
+            const double k0 = pi * (r_i * r_i), k1 = pi * r_i, k2 = pi / 4.0;
+            // cloud inner integrals (N, M, B)                                            :304-319
+            double cN = 0.0, cMm = 0.0, cB = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const double Dl = sc.cD[j];
+                const double dv = fabs(v_i - sc.cV[j]);
+                const double K = k0 + Dl * (k1 + Dl * k2);
+                const double t1 = (K * dv) * sc.cWN[j];
+                const double t2 = t1 * sc.cM[j];
+                const double Ri = (Dl * 1000000.0 * dv) / two_TC;
+                cN += t1;
+                cMm += t2;
+                cB += t2 / local_rime_density(k, Ri);
+            }
+            // rain inner integrals: closed form for N, M; quadrature for B             :381-415
+            double rN = 0.0, rM = 0.0, rB = 0.0;
+            if (rain_on) {
+                const double Dstar = brent_fixed([&](double D) { return s.v_liq(D) - v_i; }, rb0, rb1, vl_min - v_i, vl_max - v_i, k.brent_iters);
+                double fl[2][2];   // flux[piece][p = 0 | 3]
+                {
+                    double Ip[2][2][4];   // [piece][p0][term]
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double alpha = lam_r + ((j == 0) ? 0.0 : s.rc[j - 1]);
+                        const double xs = alpha * Dstar;
+#pragma unroll
+                        for (int p0 = 0; p0 < 2; ++p0) {
+                            double a_lo = 0.0, a_hi = 0.0;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                const int g = j * 6 + p0 * 3 + i;
+                                const double z = sc.gz[g];
+                                double Ps, Qs;
+                                gamma_inc_(z, xs, sc.glg[g], k.gamma_iters, Ps, Qs);
+                                // gamma_inc_moment(D_min, Dstar) and (Dstar, D_max)     P3_size_distribution.jl:121-133
+                                double m_lo = 0.0, m_hi = 0.0;
+                                if (Dstar > rb0) m_lo = sc.gG[g] * fmax_((xs < z + 1.0) ? Ps - sc.gP0[g] : sc.gQ0[g] - Qs, 0.0);
+                                if (rb1 > Dstar) m_hi = sc.gG[g] * fmax_((alpha * rb1 < z + 1.0) ? sc.gP1[g] - Ps : Qs - sc.gQ1[g], 0.0);
+                                const double coef = (i == 0) ? k0 : ((i == 1) ? k1 : k2);
+                                a_lo = (i == 0) ? coef * m_lo : a_lo + coef * m_lo;
+                                a_hi = (i == 0) ? coef * m_hi : a_hi + coef * m_hi;
+                            }
+                            Ip[0][p0][j] = a_lo;
+                            Ip[1][p0][j] = a_hi;
+                        }
+                    }
+#pragma unroll
+                    for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+                        for (int p0 = 0; p0 < 2; ++p0) {
+                            double f = v_i * Ip[pc][p0][0];
+#pragma unroll
+                            for (int j = 1; j < 4; ++j) f -= s.ra[j - 1] * Ip[pc][p0][j];
+                            fl[pc][p0] = f;
+                        }
+                }
+                const double dN = rp.N0r * (fl[0][0] - fl[1][0]);
+                const double dM = rp.N0r * mfac * (fl[0][1] - fl[1][1]);
+                if (isfinite(dN) && isfinite(dM)) {
+                    rN = dN;
+                    rM = dM;
+                    for (int j = 0; j < n; ++j) {
+                        const double Dl = sc.rD[j];
+                        const double dv = fabs(v_i - sc.rV[j]);
+                        const double K = k0 + Dl * (k1 + Dl * k2);
+                        const double Ri = (Dl * 1000000.0 * dv) / two_TC;
+                        rB += (K * dv) * sc.rWNM[j] / local_rime_density(k, Ri);
+                    }
+                }
+            }
+            // partition between freezing and shedding                                   :462-489
+            const double M_col = cMm + rM;
+            double M_max;
+            if (s.T >= T_frz) M_max = 0.0;
+            else if (!(denom > 0.0)) M_max = 1.7976931348623157e308;
+            else {
+                const double Fv = k.vent_a + k.vent_b * k.cbrt_Nsc * sqrt_(Di * v_i * k.inv_nu_air);
+                M_max = 2.0 * (pi * Di) * Fv * frz_num / denom;
+            }
+            const double M_frz = fmin_(M_col, M_max);
+            const double f_frz = (M_col == 0.0) ? 0.0 : M_frz / M_col;
+            const double wet = (M_col > M_frz) ? 1.0 : 0.0;
+            const double nw = nd.n * w;
+            acc[0] += nw * cMm * f_frz;
+            acc[1] += nw * cMm * (1.0 - f_frz);
+            acc[2] += nw * cN;
+            acc[3] += nw * rM * f_frz;
+            acc[4] += nw * rM * (1.0 - f_frz);
+            acc[5] += nw * rN;
+            acc[6] += nw * M_col;
+            acc[7] += nw * cB * f_frz;
+            acc[8] += nw * rB * f_frz;
+            acc[9] += nw * wet * M_col;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) acc[i] = warp_sum(acc[i]);
+        // bulk_liquid_ice_collision_sources                                              :606-655
+        const double QCFRZ = acc[0], QCSHD = acc[1], NCCOL = acc[2], QRFRZ = acc[3], QRSHD = acc[4], NRCOL = acc[5], M_col = acc[6],
+                     BCCOL = acc[7], BRCOL = acc[8], wetM = acc[9];
+        const double f_wet = (M_col == 0.0) ? 0.0 : wetM / M_col;
+        const double NRSHD = QRSHD / k.m_shd;
+        const double B_rim = (s.rho_rim == 0.0) ? 0.0 : (s.L_ice * s.F_rim) / s.rho_rim;
+        const double QIWET = f_wet * s.L_ice * (1.0 - s.F_rim) / k.tau_wet;
+        const double BIWET = f_wet * (s.L_ice / k.rho_i - B_rim) / k.tau_wet;
+        out.src[0] = (-QCFRZ - QCSHD) / rho;
+        out.src[1] = (-QRFRZ + QCSHD) / rho;
+        out.src[2] = -NCCOL;
+        out.src[3] = -NRCOL + NRSHD;
+        out.src[4] = QCFRZ + QRFRZ + QIWET;
+        out.src[5] = QCFRZ + QRFRZ;
+        out.src[6] = BCCOL + BRCOL + BIWET;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace cm

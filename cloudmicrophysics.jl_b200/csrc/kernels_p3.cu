@@ -1,0 +1,436 @@
+// kernels_p3.cu — P3 ice scheme kernels and their C-ABI entry points (include/cumicro.h):
+//   cumicro_p3_rates_*     stand-alone P3 terminal velocities + process rates (BASELINE config 4)
+//   cumicro_bmt2m_p3_*     BMT.bulk_microphysics_tendencies(::Microphysics2Moment, mp{WR,<:P3IceParams}, ...)  BMT:898-1083
+//   cumicro_termvel_p3_*   P3.ice_terminal_velocity_{number,mass}_weighted_from_prognostic   P3_terminal_velocity.jl:135-173
+//   cumicro_p3_logl_*      P3.get_distribution_logλ_from_prognostic                          P3_size_distribution.jl:284-334
+//
+// Kernel shape (cm_p3.cuh): a warp owns a tile of 32 consecutive points.  Lanes load their own
+// point (coalesced), the cheap pointwise parts (warm rain, nucleation, deposition, number
+// adjustment) run one point per lane, and the quadrature-based ice processes of every
+// ice-bearing point of the tile are evaluated by the whole warp, one point after the other.
+// Tiles are dealt to warps round-robin so that ice-free and ice-bearing regions of the grid mix.
+#include <algorithm>
+#include <cmath>
+
+#include "cm_launch.cuh"
+#include "cm_p3.cuh"
+
+namespace {
+
+using namespace cm;
+
+constexpr int BLOCK = 128;
+constexpr int MINB = 3;
+enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
+constexpr int NIN_MAX = 13, NOUT_MAX = 12;
+
+template <class FT> struct P3Args {
+    cumicro_params_p3_f64 p;
+    ThermoK<double> tk;
+    SB2006K<double> sk;
+    P3K k;
+    const FT* in[NIN_MAX];
+    FT* out[NOUT_MAX];
+    int64_t n;
+    int want;
+};
+
+// ---- pointwise parts of BMT:898-1083 -------------------------------------------------------------
+// IN.INP_concentration_mean                                                        IN:250-253
+CM_DEV double inp_log_mean(const P3K& k, double T) {
+    const double Tc = fmin_(T - k.frost_T_freeze, 0.0);
+    return 9.0 * log_full_(-k.frost_b * Tc / 10.0) - k.frost_log_a;
+}
+
+struct Pt {   // one grid point, clamped (BMT:911-930)
+    double rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl, shift;
+    double L_lcl, N_lcl, L_rai, N_rai, L_ice, N_ice, L_rim, B_rim;
+};
+
+CM_DEV void bmt2m_p3_assemble(const cumicro_params_p3_f64& p, const ThermoK<double>& tk, const SB2006K<double>& sk, const P3K& k,
+                              const Pt& x, bool ice_on, const P3Rates& r, double F_rim, double rho_rim, double (&y)[9]) {
+    const double e = tk.eps;
+    const double rho = x.rho, T = x.T;
+    const Warm2M<double> w = warm_rain_tendencies_2m<double>(p.warm, tk, sk, rho, T, x.q_tot, x.q_lcl, x.n_lcl, x.q_rai, x.n_rai, x.q_ice);
+    double dq_lcl = w.dq_lcl_dt, dn_lcl = w.dn_lcl_dt, dq_rai = w.dq_rai_dt, dn_rai = w.dn_rai_dt;
+    double dq_ice = 0.0, dn_ice = 0.0, dq_rim = 0.0, db_rim = 0.0;
+    if (ice_on) {                                                                   // BMT:961-996
+        dq_lcl += r.src[0];
+        dq_rai += r.src[1];
+        dn_lcl += r.src[2] / rho;
+        dn_rai += r.src[3] / rho;
+        dq_ice += r.src[5] / rho;
+        dq_rim += r.src[4] / rho;
+        db_rim += r.src[6] / rho;
+        dn_ice -= r.agg_dN / rho;
+        const double dq_m = r.melt_dL / rho, dn_m = r.melt_dN / rho;
+        dq_rai += dq_m;
+        dn_rai += dn_m;
+        dq_ice -= dq_m;
+        dn_ice -= dn_m;
+        dq_rim -= dq_m * F_rim;
+        db_rim -= (rho_rim > 0.0) ? dq_m * F_rim / rho_rim : 0.0;
+    }
+    // ---- F23 deposition nucleation                                                BMT:998-1015, IN:491-511
+    const TempState<double> ts = temp_state(tk, T);
+    const double q_sat_ice = p_sat_ice(tk, ts) / (tk.R_v * rho * T);
+    const double q_liq = x.q_lcl + x.q_rai;
+    const double qv = q_vap(x.q_tot, q_liq, x.q_ice);
+    const double inpc = exp_full_(inp_log_mean(k, T) + x.shift) / rho;
+    {
+        const double S_i = qv / q_sat_ice - 1.0;
+        const bool cond = (T < k.frost_T_freeze - 15.0) && (S_i > 0.05);
+        const double a = fmax_(0.0, inpc - x.n_ice) / k.tau_act;
+        const double dn = cond ? a : 0.0;
+        const double q_excess = fmax_(0.0, qv - q_sat_ice);
+        const double dq = fmin_(k.m_nuc * dn, q_excess / (2.0 * k.tau_act));
+        dn_ice += dn;
+        dq_ice += dq;
+    }
+    // ---- Bigg immersion freezing of cloud drops, capped by F23                    BMT:1017-1036, IN:356-430
+    const double J_bigg = k.het_B * exp_full_(k.het_a * (tk.T_freeze - T));
+    {
+        const auto& pc = p.warm.sb.pdf_c;
+        const double n = x.N_lcl / rho;
+        const bool off = (x.N_lcl < e) || (x.q_lcl < e);
+        const double safe_q = fmax_(x.q_lcl, e), safe_N = fmax_(x.N_lcl, e);
+        const double logx = log_full_(rho * safe_q / safe_N);
+        const double lB = -pc.mu_c * (logx + pc.loggamma_z1 - pc.loggamma_z2);
+        const double loglam_c = off ? num<double>::inf() : lB + pc.mu_c * k.log_km;
+        const double M3 = n * exp_full_(-3.0 / k.mu_cD * loglam_c) * k.cloud_M3_ratio;
+        const double M6 = n * exp_full_(-6.0 / k.mu_cD * loglam_c) * k.cloud_M6_ratio;
+        const bool cond = (n > e) && (x.q_lcl > e) && (T < tk.T_freeze - 4.0);
+        const double bn = cond ? J_bigg * k.V1 * M3 : 0.0;
+        const double bq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
+        const double cap = (T >= k.frost_T_freeze) ? 0.0 : fmax_(0.0, inpc - x.n_ice) / k.tau_act;
+        const double dn_imm = fmin_(bn, cap);
+        const double dq_imm = (bn > 0.0) ? bq * dn_imm / bn : 0.0;
+        dq_lcl -= dq_imm;
+        dn_lcl -= dn_imm;
+        dq_ice += dq_imm;
+        dn_ice += dn_imm;
+        dq_rim += dq_imm;
+        db_rim += dq_imm / k.rho_i;
+    }
+    // ---- ice deposition / sublimation                                            BMT:1038-1054, NEQ:168-193
+    {
+        const double n_per_q = (x.q_ice > e) ? x.n_ice / x.q_ice : 0.0;
+        const double Ls = latent_heat_sublim(tk, T);
+        const double cp_air = cp_m(tk, x.q_tot, q_liq, x.q_ice + 0.0);
+        const double dqsi_dT = q_sat_ice * (Ls / (tk.R_v * (T * T)) - 1.0 / T);
+        const double Gam = 1.0 + Ls / cp_air * dqsi_dT;
+        const double se = qv - q_sat_ice;
+        const double timescale = k.subdep_tau * Gam;
+        double tend = (se < 0.0) ? -fmin_(-se, fmax_(0.0, x.q_ice)) / timescale : se / timescale;
+        tend = ((T > tk.T_freeze) && (tend > 0.0)) ? 0.0 : tend;                       // NEQ.INP_limiter
+        tend = (T > tk.T_freeze) ? fmin_(tend, 0.0) : tend;
+        const double dn_d = (tend < 0.0) ? n_per_q * tend : 0.0;
+        dq_ice += tend;
+        dn_ice += dn_d;
+        const double sub = fmin_(tend, 0.0);
+        dq_rim += sub * F_rim;
+        db_rim += (rho_rim > 0.0) ? sub * F_rim / rho_rim : 0.0;
+    }
+    // ---- ice number adjustment (τ = 100, x in [1e-12, 1e-5])                       BMT:1056-1064
+    dn_ice += number_tendency_from_mass_limits<double>(e, 1.0 / 1e-12, 1.0 / 1e-5, 1.0 / 100.0, x.q_ice, x.n_ice);
+    // ---- rain Bigg freezing                                                        BMT:1066-1075, IN:274-311
+    {
+        const double n = x.N_rai / rho;
+        const RainPDF<double> rp = pdf_rain_parameters<double>(p.warm.sb.pdf_r, sk.pi_rho_w, e, x.q_rai, rho, x.N_rai);
+        const double Dr = rp.Dr_mean, D3 = Dr * Dr * Dr;
+        const double M3 = n * 6.0 * D3, M6 = n * 720.0 * (D3 * D3);
+        const bool cond = (n > e) && (x.q_rai > e) && (T < tk.T_freeze - 4.0);
+        const double rn = cond ? J_bigg * k.V1 * M3 : 0.0;
+        const double rq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
+        dq_rai -= rq;
+        dn_rai -= rn;
+        dq_ice += rq;
+        dn_ice += rn;
+        dq_rim += rq;
+        db_rim += rq / k.rho_i;
+    }
+    y[0] = dq_lcl; y[1] = dn_lcl; y[2] = dq_rai; y[3] = dn_rai; y[4] = dq_ice; y[5] = dn_ice; y[6] = dq_rim; y[7] = db_rim;
+    y[8] = 0.0;   // dn_lcl_activation_dt: plumbed but zero in the reference (BMT:729, 1077-1078)
+}
+
+template <class FT, int MODE>
+__global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_constant__ P3Args<FT> a) {
+    extern __shared__ double smem[];
+    math_tables_init<BLOCK>();
+    const int nq = a.k.n;
+    double* qx = smem;
+    double* qw = smem + nq;
+    for (int i = threadIdx.x; i < nq; i += BLOCK) {
+        qx[i] = a.p.quad.nodes[i];
+        qw[i] = a.p.quad.weights[i];
+    }
+    __syncthreads();
+    P3Scratch sc;
+    sc.bind(smem + 2 * nq + (threadIdx.x >> 5) * P3Scratch::doubles(nq), nq);
+    const int lane = threadIdx.x & 31;
+    const double e = a.k.eps;
+    const int64_t n_tiles = (a.n + 31) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * BLOCK) >> 5;
+    for (int64_t tile = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) >> 5; tile < n_tiles; tile += n_warps) {
+        const int64_t i = (tile << 5) + lane;
+        const bool valid = i < a.n;
+        Pt x;
+        auto ld = [&](int c) { return (valid && a.in[c]) ? (double)__ldg(a.in[c] + i) : 0.0; };
+        if (MODE == MODE_VEL) {   // in: rho_a, L_ice, N_ice, L_rim, B_rim, logl (volumetric, as the reference's wrapper takes them)
+            x.rho = ld(0); x.T = 273.15; x.q_tot = 0.0; x.q_lcl = x.n_lcl = x.q_rai = x.n_rai = 0.0;
+            x.L_ice = ld(1); x.N_ice = ld(2); x.L_rim = ld(3); x.B_rim = ld(4); x.logl = ld(5); x.shift = 0.0;
+            x.q_ice = x.n_ice = x.q_rim = x.b_rim = 0.0;
+            x.L_lcl = x.N_lcl = x.L_rai = x.N_rai = 0.0;
+        } else {                  // in: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl [, inpc_log_shift]
+            x.rho = fmax_(0.0, ld(0)); x.T = ld(1); x.q_tot = fmax_(0.0, ld(2)); x.q_lcl = fmax_(0.0, ld(3)); x.n_lcl = fmax_(0.0, ld(4));
+            x.q_rai = fmax_(0.0, ld(5)); x.n_rai = fmax_(0.0, ld(6)); x.q_ice = fmax_(0.0, ld(7)); x.n_ice = fmax_(0.0, ld(8));
+            x.q_rim = fmax_(0.0, ld(9)); x.b_rim = fmax_(0.0, ld(10)); x.logl = ld(11); x.shift = ld(12);
+            x.L_lcl = x.q_lcl * x.rho; x.L_rai = x.q_rai * x.rho; x.N_lcl = x.n_lcl * x.rho; x.N_rai = x.n_rai * x.rho;
+            x.L_ice = x.q_ice * x.rho; x.N_ice = x.n_ice * x.rho; x.L_rim = x.q_rim * x.rho; x.B_rim = x.b_rim * x.rho;
+        }
+        // which integrals this point needs
+        int want = 0;
+        if (valid) {
+            const bool vel_on = !((x.N_ice < e) || (x.L_ice < e));                  // P3_terminal_velocity.jl:79-81
+            const bool ice_on = (MODE == MODE_VEL) ? false : (x.q_ice > e && x.n_ice > e);   // BMT:961
+            if (vel_on) want |= P3_WANT_VEL;
+            if (ice_on) want |= P3_WANT_AGG | P3_WANT_COLL | ((x.T > a.tk.T_freeze) ? P3_WANT_MELT : 0);
+            want &= a.want;
+        }
+        P3Rates mine;
+        mine.v_n = mine.v_m = mine.melt_dN = mine.melt_dL = mine.agg_dN = 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) mine.src[c] = 0.0;
+        double F_rim = 0.0, rho_rim = 0.0;
+        unsigned m = __ballot_sync(0xffffffffu, want != 0);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            P3Point s;
+            p3_point_init(s, a.p, a.k, bcast(x.rho, b), bcast(x.T, b), bcast(x.L_ice, b), bcast(x.N_ice, b), bcast(x.L_rim, b),
+                          bcast(x.B_rim, b), bcast(x.logl, b));
+            P3Rates r;
+            p3_point_rates(s, a.p, a.k, a.tk, a.sk, qx, qw, sc, __shfl_sync(0xffffffffu, want, b), bcast(x.L_lcl, b), bcast(x.N_lcl, b),
+                           bcast(x.L_rai, b), bcast(x.N_rai, b), r);
+            if (lane == b) { mine = r; F_rim = s.F_rim; rho_rim = s.rho_rim; }
+        }
+        if (!valid) continue;
+        if (MODE == MODE_BMT) {
+            if (want == 0) {   // state_from_prognostic for the rim bookkeeping of the pointwise processes (BMT:930)
+                F_rim = fmin_(regularised_ratio_(fmin_(x.L_rim, x.L_ice), x.L_ice, e), 1.0 - e);
+                rho_rim = fmin_(regularised_ratio_(x.L_rim, x.B_rim, e), a.k.rho_l08);
+            }
+            double y[9];
+            bmt2m_p3_assemble(a.p, a.tk, a.sk, a.k, x, (x.q_ice > e && x.n_ice > e), mine, F_rim, rho_rim, y);
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                if (a.out[c]) a.out[c][i] = (FT)y[c];
+        } else if (MODE == MODE_RATES) {
+            const double y[12] = {mine.v_n, mine.v_m, mine.melt_dN, mine.melt_dL, mine.agg_dN, mine.src[0], mine.src[1],
+                                  mine.src[2], mine.src[3], mine.src[4], mine.src[5], mine.src[6]};
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+                if (a.out[c]) a.out[c][i] = (FT)y[c];
+        } else {
+            if (a.out[0]) a.out[0][i] = (FT)mine.v_n;
+            if (a.out[1]) a.out[1][i] = (FT)mine.v_m;
+        }
+    }
+}
+
+template <class FT> struct PP3;
+template <> struct PP3<double> { using type = cumicro_params_p3_f64; };
+template <> struct PP3<float> { using type = cumicro_params_p3_f32; };
+template <class FT> constexpr bool is_f32() { return sizeof(FT) == 4; }
+
+template <class FT> int p3_check(const typename PP3<FT>::type* p) {
+    if (p == nullptr) return cmh::fail(CUMICRO_E_NULL, "parameter block is NULL");
+    if (p->quad.n < 1 || p->quad.n > kQuadMax) return cmh::fail(CUMICRO_E_OPTION, "quad.n = %d (expected 1..%d)", (int)p->quad.n, kQuadMax);
+    if (p->warm.sb.pdf_r.limited != 0 && p->warm.sb.pdf_r.limited != 1) return cmh::fail(CUMICRO_E_OPTION, "sb.pdf_r.limited = %d", (int)p->warm.sb.pdf_r.limited);
+    if (p->scheme.slope_power_law != 0 && p->scheme.slope_power_law != 1) return cmh::fail(CUMICRO_E_OPTION, "scheme.slope_power_law = %d", (int)p->scheme.slope_power_law);
+    if (p->scheme.aspect_oblate != 0 && p->scheme.aspect_oblate != 1) return cmh::fail(CUMICRO_E_OPTION, "scheme.aspect_oblate = %d", (int)p->scheme.aspect_oblate);
+    // P3_processes.jl:616: @assert ρw == psd_r.ρw
+    if (p->warm.sb.pdf_c.rho_w != p->warm.sb.pdf_r.rho_w) return cmh::fail(CUMICRO_E_OPTION, "cloud and rain PSDs must share the liquid water density");
+    return CUMICRO_OK;
+}
+
+template <class FT, int MODE>
+int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, int nin, int nin_required, FT* const* out, int nout, int want,
+              void* stream, const char* what) {
+    int st = p3_check<FT>(p);
+    if (st) return st;
+    if (n < 0) return cmh::fail(CUMICRO_E_SIZE, "n = %lld is negative", (long long)n);
+    if (!in || !out) return cmh::fail(CUMICRO_E_NULL, "%s: column pointer table is NULL", what);
+    for (int c = 0; c < nin_required; ++c)
+        if (n > 0 && in[c] == nullptr) return cmh::fail(CUMICRO_E_NULL, "%s: input column %d is NULL", what, c);
+    if (n == 0) return CUMICRO_OK;
+    P3Args<FT> a{};
+    widen(*p, a.p);
+    a.tk = make_thermo_k<double>(a.p.warm.tps, is_f32<FT>());
+    a.sk = make_sb2006_k<double>(a.p.warm.sb, a.p.warm.aps, is_f32<FT>());
+    a.k = make_p3_k(a.p, is_f32<FT>());
+    for (int c = 0; c < NIN_MAX; ++c) a.in[c] = (c < nin) ? in[c] : nullptr;
+    for (int c = 0; c < NOUT_MAX; ++c) a.out[c] = (c < nout) ? out[c] : nullptr;
+    a.n = n;
+    a.want = want;
+    const int nq = a.k.n;
+    const size_t shmem = sizeof(double) * (size_t)(2 * nq + (BLOCK / 32) * P3Scratch::doubles(nq));
+    const int64_t tiles = (n + 31) / 32;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BLOCK / 32 - 1) / (BLOCK / 32), (int64_t)cmh::num_sms() * MINB));
+    auto kern = p3_tile_kernel<FT, MODE>;
+    if (shmem > 48 * 1024) {
+        st = cmh::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem), "cudaFuncSetAttribute");
+        if (st) return st;
+    }
+    kern<<<blocks, BLOCK, shmem, (cudaStream_t)stream>>>(a);
+    cmh::count_launch();
+    return cmh::cuda_status(cudaGetLastError(), what);
+}
+
+// ---- P3.get_distribution_logλ_from_prognostic: one point per thread ------------------------------
+struct P3LogLambda {
+    cumicro_p3_scheme_f64 prm;
+    P3K k;
+    int iters;   // Brent iterations (reference: 10 / 8)
+    // logLdivN(state, logλ) - target                                    P3_size_distribution.jl:193-216
+    __device__ double shape(double logl, double F_rim, double rho_g, double D_gr, double D_cr, double target) const {
+        const double lam = exp_full_(logl);
+        const double mu = k.slope_power_law ? clamp_(k.slope_a * pow_full_(lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+        const double pi = num<double>::pi();
+        const double inf = num<double>::inf();
+        const double bnd[5] = {0.0, clamp_(k.D_th, 0.0, inf), clamp_(D_gr, 0.0, inf), clamp_(D_cr, 0.0, inf), inf};
+        const double Fu = fmax_(1.0 - F_rim, k.eps);
+        double m[4];
+#pragma unroll
+        for (int sgm = 0; sgm < 4; ++sgm) {
+            const double D1 = bnd[sgm], D2 = bnd[sgm + 1];
+            const double Dm = (D1 + D2) / 2.0;
+            const int r = (Dm < k.D_th) ? 0 : ((F_rim == 0.0) ? 1 : ((Dm < D_gr) ? 2 : ((Dm < D_cr) ? 3 : 4)));
+            const double a = (r == 0) ? k.rho_i * pi / 6.0 : ((r == 3) ? rho_g * pi / 6.0 : ((r == 4) ? k.alpha_va / Fu : k.alpha_va));
+            const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
+            if (!(D1 < D2)) { m[sgm] = -inf; continue; }
+            const double z = (b + 0.0) + mu + 1.0;
+            const double x1 = D1 * lam, x2 = D2 * lam;
+            const double lg = lgamma_(z);
+            double p1, q1, p2, q2;
+            gamma_inc_(z, x1, lg, k.gamma_iters, p1, q1);
+            gamma_inc_(z, x2, lg, k.gamma_iters, p2, q2);
+            double dq = (x2 < z + 1.0) ? p2 - p1 : q1 - q2;
+            dq = fmax_(dq, k.eps);
+            m[sgm] = -z * logl + lg + log_full_(dq) + log_full_(a);
+        }
+        double mx = m[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) mx = fmax_(mx, m[i]);
+        double lse = mx;
+        if (isfinite(mx)) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sum += exp_full_(m[i] - mx);
+            lse = mx + log_full_(sum);
+        }
+        const double z0 = 0.0 + mu + 1.0;
+        return (lse - (-z0 * logl + lgamma_(z0) + 0.0)) - target;
+    }
+    __device__ __forceinline__ void operator()(const double (&x)[4], double (&y)[1]) const {
+        const double L_ice = x[0], N_ice = x[1], L_rim = x[2], B_rim = x[3];
+        const double F_rim = fmin_(regularised_ratio_(fmin_(L_rim, L_ice), L_ice, k.eps), 1.0 - k.eps);
+        const double rho_rim = fmin_(regularised_ratio_(L_rim, B_rim, k.eps), k.rho_l08);
+        if (N_ice < k.eps || L_ice < k.eps) { y[0] = -num<double>::inf(); return; }
+        // thresholds (as p3_point_init)
+        const double pp = k.thr_p;
+        const double logFu = log1p_(-F_rim);
+        auto exprel1 = [](double v) { return expm1_(v) / v; };
+        auto exprel2 = [](double v) {
+            if (fabs(v) < 0.2) {
+                double r = 1.0 / 362880.0;
+                const double c[7] = {1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 1.0 / 2.0};
+#pragma unroll
+                for (int i = 0; i < 7; ++i) r = r * v + c[i];
+                return r;
+            }
+            return (expm1_(v) - v) / (v * v);
+        };
+        const double phi1 = exprel1(logFu), phi1mp = exprel1((1.0 - pp) * logFu);
+        const double H = -pp * exprel2(-pp * logFu) - (1.0 - pp) * exprel2((1.0 - pp) * logFu);
+        const double rho_d = -(rho_rim * phi1 * phi1mp) / (H - phi1mp * phi1);
+        const double rho_g = F_rim * rho_rim + (1.0 - F_rim) * rho_d;
+        const bool unrimed = (F_rim == 0.0);
+        const double pi = num<double>::pi();
+        const double D_gr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * rho_g), pp);
+        const double D_cr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * (rho_g * (1.0 - F_rim))), pp);
+        const double target = log_full_(L_ice) - log_full_(N_ice);
+        auto f = [&](double l) { return shape(l, F_rim, rho_g, D_gr, D_cr, target); };
+        const double lo = 2.0, hi = 17.0;
+        const double f_lo = f(lo), f_hi = f(hi);
+        if (!isfinite(f_lo) || !isfinite(f_hi) || f_lo * f_hi > 0.0) { y[0] = (fabs(f_lo) <= fabs(f_hi)) ? lo : hi; return; }
+        y[0] = brent_fixed(f, lo, hi, f_lo, f_hi, iters);
+    }
+};
+
+template <class FT>
+int p3_logl_impl(const typename PP3<FT>::type* p, int64_t n, const FT* L_ice, const FT* N_ice, const FT* L_rim, const FT* B_rim, int iters,
+                 FT* logl, void* stream) {
+    int st = p3_check<FT>(p);
+    if (st) return st;
+    const FT* in[4] = {L_ice, N_ice, L_rim, B_rim};
+    if ((st = validate_columns<FT, 4>(p, n, in))) return st;
+    FT* out[1] = {logl};
+    if ((st = require_outputs<FT, 1>(n, out, 1))) return st;
+    cumicro_params_p3_f64 wide;
+    widen(*p, wide);
+    P3LogLambda f{};
+    f.prm = wide.scheme;
+    f.k = make_p3_k(wide, is_f32<FT>());
+    f.iters = iters > 0 ? iters : f.k.brent_iters;
+    return launch_pointwise<FT, 4, 1, P3LogLambda, 128, 3, false>(f, n, in, out, (cudaStream_t)stream, "p3_logl kernel launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int cumicro_p3_rates_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in12, double* const* out12, void* stream) {
+    return p3_launch<double, MODE_RATES>(p, n, in12, 12, 12, out12, 12, P3_WANT_VEL | P3_WANT_MELT | P3_WANT_AGG | P3_WANT_COLL, stream, "p3_rates");
+}
+int cumicro_p3_rates_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in12, float* const* out12, void* stream) {
+    return p3_launch<float, MODE_RATES>(p, n, in12, 12, 12, out12, 12, P3_WANT_VEL | P3_WANT_MELT | P3_WANT_AGG | P3_WANT_COLL, stream, "p3_rates");
+}
+int cumicro_bmt2m_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in12, const double* inpc_log_shift,
+                         double* const* out9, void* stream) {
+    if (!in12) return cmh::fail(CUMICRO_E_NULL, "bmt2m_p3: column pointer table is NULL");
+    const double* in[13];
+    for (int c = 0; c < 12; ++c) in[c] = in12[c];
+    in[12] = inpc_log_shift;
+    return p3_launch<double, MODE_BMT>(p, n, in, 13, 12, out9, 9, P3_WANT_MELT | P3_WANT_AGG | P3_WANT_COLL, stream, "bmt2m_p3");
+}
+int cumicro_bmt2m_p3_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in12, const float* inpc_log_shift,
+                         float* const* out9, void* stream) {
+    if (!in12) return cmh::fail(CUMICRO_E_NULL, "bmt2m_p3: column pointer table is NULL");
+    const float* in[13];
+    for (int c = 0; c < 12; ++c) in[c] = in12[c];
+    in[12] = inpc_log_shift;
+    return p3_launch<float, MODE_BMT>(p, n, in, 13, 12, out9, 9, P3_WANT_MELT | P3_WANT_AGG | P3_WANT_COLL, stream, "bmt2m_p3");
+}
+int cumicro_termvel_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double* rho_a, const double* L_ice, const double* N_ice,
+                           const double* L_rim, const double* B_rim, const double* logl, double* v_n, double* v_m, void* stream) {
+    const double* in[6] = {rho_a, L_ice, N_ice, L_rim, B_rim, logl};
+    double* out[2] = {v_n, v_m};
+    return p3_launch<double, MODE_VEL>(p, n, in, 6, 6, out, 2, P3_WANT_VEL, stream, "termvel_p3");
+}
+int cumicro_termvel_p3_f32(const cumicro_params_p3_f32* p, int64_t n, const float* rho_a, const float* L_ice, const float* N_ice,
+                           const float* L_rim, const float* B_rim, const float* logl, float* v_n, float* v_m, void* stream) {
+    const float* in[6] = {rho_a, L_ice, N_ice, L_rim, B_rim, logl};
+    float* out[2] = {v_n, v_m};
+    return p3_launch<float, MODE_VEL>(p, n, in, 6, 6, out, 2, P3_WANT_VEL, stream, "termvel_p3");
+}
+int cumicro_p3_logl_f64(const cumicro_params_p3_f64* p, int64_t n, const double* L_ice, const double* N_ice, const double* L_rim,
+                        const double* B_rim, int brent_iters, double* logl, void* stream) {
+    return p3_logl_impl<double>(p, n, L_ice, N_ice, L_rim, B_rim, brent_iters, logl, stream);
+}
+int cumicro_p3_logl_f32(const cumicro_params_p3_f32* p, int64_t n, const float* L_ice, const float* N_ice, const float* L_rim,
+                        const float* B_rim, int brent_iters, float* logl, void* stream) {
+    return p3_logl_impl<float>(p, n, L_ice, N_ice, L_rim, B_rim, brent_iters, logl, stream);
+}
+
+}  // extern "C"

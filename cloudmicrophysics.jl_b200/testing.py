@@ -291,3 +291,31 @@ def assert_f32_method(name, got32, ref32, truth64, bound64=None, max_ulps=F32_UL
     worst = float(err.max()) if err.size else 0.0
     assert worst <= max_ulps, (name, "max Float32 ULP error", worst, "at", int(np.argmax(err)))
     return worst
+
+
+def synthetic_states_p3(n, seed=1234, dtype=np.float64, frac_ice_free=0.3, frac_unrimed=0.15):
+    """Inputs of the 2-moment + P3 method (BMT:898-1083) without logλ: the 2-moment warm-rain state plus
+    q_ice, n_ice, q_rim, b_rim.  Follows test/gpu_performance.jl:244-248 (ice content from the profile)
+    with a mixed population: ~30 % ice-free points (the BMT:961 branch), unrimed
+    (F_rim = 0), partially and heavily rimed ice, rime densities 100-900 kg/m³, mean particle masses
+    1e-12..1e-7 kg.  logλ comes from get_distribution_logλ_from_prognostic (host model does the same)."""
+    st = synthetic_states_2m(n, seed=seed, dtype=np.float64)
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    T, rho = st["T"], st["rho"]
+    qsi = psat_ice(T) / (rho * DEFAULTS["gas_constant_vapor"] * T)
+    q_vap = st["q_tot"] - st["q_lcl"] - st["q_rai"]
+    q_ice = np.maximum(0.0, q_vap - qsi) * rng.random(n) + rng.random(n) * 1e-4
+    x_mean = 10.0 ** rng.uniform(-12, -7, n)
+    n_ice = q_ice / x_mean
+    F_rim = rng.uniform(0.0, 0.95, n)
+    F_rim[rng.random(n) < frac_unrimed] = 0.0
+    rho_rim = rng.uniform(100.0, 900.0, n)
+    q_rim = F_rim * q_ice
+    b_rim = q_rim / rho_rim
+    u = rng.random(n)
+    q_ice[u < frac_ice_free * 0.6] = 0.0
+    n_ice[(u > frac_ice_free * 0.5) & (u < frac_ice_free)] = 0.0
+    q_rim = np.minimum(q_rim, q_ice)
+    st["q_tot"] = st["q_tot"] + q_ice
+    st.update(q_ice=q_ice, n_ice=n_ice, q_rim=q_rim, b_rim=b_rim)
+    return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}

@@ -314,6 +314,51 @@ int cumicro_fused_1m2m_icenuc_f32(const cumicro_params_1m_f32* p1, const cumicro
                                   const cumicro_params_icenuc_f32* p3, int64_t n, const float* const* in11,
                                   float* const* out11, double* diag, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * P3 ice scheme (src/P3_*.jl, src/Quadrature.jl).  Parameter block: cumicro_params_p3_* =
+ * mp::Microphysics2MParams{WR, <:P3IceParams} + tps, flattened (quadrature nodes / weights of
+ * mp.ice.quad included; the stand-alone reference functions take `quad` as a keyword).
+ *
+ * cumicro_p3_rates_*: the stand-alone P3 integrals of one state, BASELINE config 4.
+ *   in12  = HOST array of 12 device columns: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice,
+ *           q_rim, b_rim, logλ  (specific quantities, as BMT takes them; volumetric L = q rho, N = n rho
+ *           and state_from_prognostic are formed as at BMT:911-930; q_tot is not read)
+ *   out12 = HOST array of 12 device columns (NULL entries skipped):
+ *     [0] ice_terminal_velocity_number_weighted   [1] ..._mass_weighted      P3_terminal_velocity.jl:73-133
+ *     [2] ice_melt dNdt  [3] ice_melt dLdt                                   P3_processes.jl:64-94
+ *     [4] ice_self_collection dNdt                                           P3_processes.jl:676-712
+ *     [5..11] bulk_liquid_ice_collision_sources: ∂ₜq_c, ∂ₜq_r, ∂ₜN_c, ∂ₜN_r, ∂ₜL_rim, ∂ₜL_ice, ∂ₜB_rim   :606-655
+ *   Velocities are 0 where ρn_ice < eps or ρq_ice < eps (:79-81); [2..11] are 0 where the branch
+ *   BMT:961 (q_ice > eps && n_ice > eps) is not taken.
+ *
+ * cumicro_bmt2m_p3_*: bulk_microphysics_tendencies(::Microphysics2Moment, mp{WR,<:P3IceParams}, tps, rho, T,
+ *   q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ, inpc_log_shift)       BMT:898-1083
+ *   in12 as above; inpc_log_shift: device column or NULL (= 0);
+ *   out9 = dq_lcl_dt, dn_lcl_dt, dq_rai_dt, dn_rai_dt, dq_ice_dt, dn_ice_dt, dq_rim_dt, db_rim_dt,
+ *          dn_lcl_activation_dt (identically zero in the reference; NULL = not materialised).
+ *
+ * cumicro_termvel_p3_*: ice_terminal_velocity_{number,mass}_weighted_from_prognostic(vel, ρₐ, params, ρq_ice,
+ *   ρn_ice, ρq_rim, ρb_rim, logλ; p = 1e-6, quad)                            P3_terminal_velocity.jl:135-173
+ *
+ * cumicro_p3_logl_*: get_distribution_logλ_from_prognostic(params, ρq_ice, ρn_ice, ρq_rim, ρb_rim)
+ *   P3_size_distribution.jl:284-334.  brent_iters <= 0 selects the reference's fixed 10 (Float64) / 8 (Float32)
+ *   Brent iterations; -Inf for empty ice (:289).
+ * ------------------------------------------------------------------------- */
+int cumicro_p3_rates_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in12, double* const* out12, void* stream);
+int cumicro_p3_rates_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in12, float* const* out12, void* stream);
+int cumicro_bmt2m_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in12, const double* inpc_log_shift,
+                         double* const* out9, void* stream);
+int cumicro_bmt2m_p3_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in12, const float* inpc_log_shift,
+                         float* const* out9, void* stream);
+int cumicro_termvel_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double* rho_a, const double* L_ice, const double* N_ice,
+                           const double* L_rim, const double* B_rim, const double* logl, double* v_n, double* v_m, void* stream);
+int cumicro_termvel_p3_f32(const cumicro_params_p3_f32* p, int64_t n, const float* rho_a, const float* L_ice, const float* N_ice,
+                           const float* L_rim, const float* B_rim, const float* logl, float* v_n, float* v_m, void* stream);
+int cumicro_p3_logl_f64(const cumicro_params_p3_f64* p, int64_t n, const double* L_ice, const double* N_ice, const double* L_rim,
+                        const double* B_rim, int brent_iters, double* logl, void* stream);
+int cumicro_p3_logl_f32(const cumicro_params_p3_f32* p, int64_t n, const float* L_ice, const float* N_ice, const float* L_rim,
+                        const float* B_rim, int brent_iters, float* logl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
