@@ -1,0 +1,205 @@
+"""GPU parity of the P3 kernels through the C-ABI vs the CPU oracle (BASELINE config 4 and the
+2-moment + P3 fused tendencies, BMT:898-1083).  Float64: 1e-12 relative, or the reference
+algorithm's own first-order rounding bound where it subtracts nearly equal numbers
+(cumicro.testing.compare_report); regime selection (exact zeros, non-finite values) bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "p3_goldens.json")))
+EPS = np.finfo(np.float64).eps
+IN12 = ("rho", "T", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim")
+RATE2ORC = dict(v_n="v_n", v_m="v_m", melt_dNdt="melt_dN", melt_dLdt="melt_dL", self_collection_dNdt="selfcol", dq_c="dq_c", dq_r="dq_r",
+                dN_c="dN_c", dN_r="dN_r", dL_rim="dL_rim", dL_ice="dL_ice", dB_rim="dB_rim")
+
+
+def _setup(built, n, seed=1234, **mpkw):
+    CMP, T_ = built.CMP, built.testing
+    mp = CMP.Microphysics2MParams(np.float64, with_ice=True, **mpkw)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    st = T_.synthetic_states_p3(n, seed=seed)
+    return mp, tps, st
+
+
+def _volumetric(st):
+    return [st[k] * st["rho"] for k in ("q_ice", "n_ice", "q_rim", "b_rim")]
+
+
+def _converged_logl(orc, blk, st):
+    l = orc.p3_state(blk, *_volumetric(st), from_prognostic=True, want=("logl",), logl_iters=40)["logl"]
+    return np.where(np.isfinite(l), l, 0.0)
+
+
+def _oracle_rates(orc, blk, st, logl, sel, bound=False):
+    rho = st["rho"]
+    o = orc.p3_state(blk, *[v[sel] for v in _volumetric(st)], from_prognostic=True, rho_a=rho[sel], T=st["T"][sel], logl=logl[sel],
+                     L_c=(st["q_lcl"] * rho)[sel], N_c=(st["n_lcl"] * rho)[sel], L_r=(st["q_rai"] * rho)[sel], N_r=(st["n_rai"] * rho)[sel],
+                     want=("v_n", "v_m", "melt", "selfcol", "src7"), bound=bound)
+    warm = st["T"][sel] > 273.15     # BMT:981-985 evaluates ice_melt only above freezing (below, max(0, .) gives 0 anyway)
+    for k in ("melt_dN", "melt_dL"):
+        o[k] = np.where(warm, o[k], 0.0)
+    return o
+
+
+@pytest.mark.parametrize("variant", ["default_gl16", "cheb20_unlimited", "gl12_noar_constslope"])
+def test_p3_rates_f64_parity(built, orc, cuda, variant):
+    import torch
+    from cumicro.testing import assert_parity
+    P3, CMP3 = built.P3, built.CMP3
+    kw, quad, ice_kw = {}, None, {}
+    if variant == "cheb20_unlimited":
+        kw = dict(is_limited=False, quadrature_order=20)          # build_quadrature(20) -> ChebyshevGauss
+    mp, tps, st = _setup(built, 800, seed=11 + len(variant), **kw)
+    if variant == "gl12_noar_constslope":
+        mp.ice = CMP3.P3IceParams(np.float64, slope_law="constant", aspect_ratio=CMP3.NoAspectRatio(), quadrature_order=12,
+                                  overrides={"P3_constant_slope_parameterization_value": 1.5})
+        quad = CMP3.GaussLegendre(np.float64, 12)
+    blk = CMP3.pack_p3(mp, tps, quad=quad)
+    logl = _converged_logl(orc, blk, st)
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in st.items()}
+    got = P3.process_rates(mp, tps, *[d[k] for k in IN12], torch.from_numpy(logl).to(cuda), quad=quad)
+    ice = (st["q_ice"] > EPS) & (st["n_ice"] > EPS)
+    assert 0.5 < ice.mean() < 0.9
+    ref, bnd = _oracle_rates(orc, blk, st, logl, ice), _oracle_rates(orc, blk, st, logl, ice, bound=True)
+    F_rim0 = (st["q_rim"][ice] == 0).mean()
+    assert F_rim0 > 0.05                                            # the unrimed regime (Inf thresholds) is populated
+    worst = 0.0
+    for g, r in RATE2ORC.items():
+        gg = got[g].cpu().numpy()
+        rep = assert_parity(f"{variant}:{g}", gg[ice], ref[r], bound=bnd[r])
+        worst = max(worst, rep["max_rel"])
+        if g not in ("v_n", "v_m"):
+            assert np.all(gg[~ice] == 0), g                        # BMT:961 branch not taken
+    vel_off = (st["n_ice"] * st["rho"] < EPS) | (st["q_ice"] * st["rho"] < EPS)
+    assert np.all(got["v_n"].cpu().numpy()[vel_off] == 0) and np.all(got["v_m"].cpu().numpy()[vel_off] == 0)
+    assert worst < 1e-12
+
+
+def test_bmt2m_p3_f64_parity(built, orc, cuda):
+    import torch
+    from cumicro.testing import assert_parity
+    BMT, CMP3 = built.BMT, built.CMP3
+    mp, tps, st = _setup(built, 1500, seed=5)
+    # cold points so that F23 deposition / Bigg freezing / immersion cap are all active somewhere
+    st["T"][::3] -= 25.0
+    blk = CMP3.pack_p3(mp, tps)
+    logl = _converged_logl(orc, blk, st)
+    shift = np.random.default_rng(1).normal(0, 1.0, st["rho"].size)
+    cols = [st[k] for k in orc.P3_BMT_IN[:-1]] + [logl]
+    ref = orc.bmt2m_p3(blk, *cols, inpc_log_shift=shift)
+    bnd = orc.bmt2m_p3(blk, *cols, inpc_log_shift=shift, bound=True)
+    dcols = [torch.from_numpy(c).to(cuda) for c in cols]
+    got = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *dcols, torch.from_numpy(shift).to(cuda))
+    for k in orc.P3_BMT_OUT[:-1]:
+        assert_parity(k, got[k].cpu().numpy(), ref[k], bound=bnd[k])
+    assert float(got["dn_lcl_activation_dt"].abs().max()) == 0.0
+    # regimes exercised: ice-free points, melting points, freezing points, deposition nucleation
+    ice = (st["q_ice"] > EPS) & (st["n_ice"] > EPS)
+    assert (~ice).sum() > 100 and (ice & (st["T"] > 273.15)).sum() > 20 and (st["T"] < 258.15).sum() > 100
+    assert (ref["dq_rim_dt"] != 0).mean() > 0.3
+    # without the optional shift column (inpc_log_shift = 0, BMT:903)
+    ref0 = orc.bmt2m_p3(blk, *cols)
+    got0 = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *dcols)
+    bnd0 = orc.bmt2m_p3(blk, *cols, bound=True)
+    for k in ("dq_ice_dt", "dn_ice_dt", "dq_lcl_dt"):
+        assert_parity(k + ":noshift", got0[k].cpu().numpy(), ref0[k], bound=bnd0[k])
+
+
+def test_p3_goldens_through_the_gpu(built, cuda):
+    """The reference's own P3 literals (tests/golden/p3_goldens.json) through the C-ABI."""
+    import torch
+    P3, CMP, CMP3 = built.P3, built.CMP, built.CMP3
+    mp = CMP.Microphysics2MParams(np.float64, with_ice=True)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    q12 = CMP3.GaussLegendre(np.float64, 12)
+    f = lambda v: torch.full((3,), float(v), dtype=torch.float64, device=cuda)
+    g = G["bulk_velocity"]
+    for k, F in enumerate(g["F_rims"]):
+        L, N = g["L_ice"], g["N_ice"]
+        L_rim = F * L
+        B_rim = L_rim / g["rho_rim"]
+        logl = P3.get_distribution_logλ_from_prognostic(mp, tps, f(L), f(N), f(L_rim), f(B_rim))
+        v_n, v_m = P3.ice_terminal_velocities_from_prognostic(mp, tps, f(g["rho_a"]), f(L), f(N), f(L_rim), f(B_rim), logl, quad=q12)
+        # state_from_prognostic regularises F_rim = L_rim / L: equal to the literal F_rim to rounding
+        assert abs(float(v_n[0]) / g["v_n_phi"][k] - 1) < 1e-12
+        assert abs(float(v_m[0]) / g["v_m_phi"][k] - 1) < 1e-12
+    s = G["process_state"]
+    rho = s["rho_a"]
+    q_rim = s["F_rim"] * s["q_ice"]
+    b_rim = q_rim / s["rho_rim"]
+    Tf = 273.15
+    c = G["collisions"]
+    logl = P3.get_distribution_logλ_from_prognostic(mp, tps, f(s["q_ice"] * rho), f(s["n_ice"] * rho), f(q_rim * rho), f(b_rim * rho))
+    for m in G["melt"]:
+        r = P3.process_rates(mp, tps, f(rho), f(Tf + m["dT"]), f(0), f(0), f(0), f(0), f(s["q_ice"]), f(s["n_ice"]), f(q_rim), f(b_rim), logl,
+                             quad=q12, which=("melt_dNdt", "melt_dLdt"))
+        assert abs(float(r.melt_dNdt[0]) / m["dNdt"] - 1) < 1e-11
+        assert abs(float(r.melt_dLdt[0]) / m["dLdt"] - 1) < 1e-11
+    r = P3.process_rates(mp, tps, f(rho), f(Tf + c["dT"]), f(c["L_c"] / rho), f(c["N_c"] / rho), f(c["L_r"] / rho), f(c["N_r"] / rho),
+                         f(s["q_ice"]), f(s["n_ice"]), f(q_rim), f(b_rim), logl, quad=q12)
+    v = c["values"]
+    # ∂ₜL_ice = QCFRZ + QRFRZ, ∂ₜq_c = -(QCFRZ + QCSHD)/ρ ... (P3_processes.jl:640-650); the cloud literals are stale at 4.5e-4
+    assert abs(float(r.dL_ice[0]) / (v["QCFRZ"] + v["QRFRZ"]) - 1) < 1e-5
+    assert abs(float(r.dq_c[0]) / (-(v["QCFRZ"] + v["QCSHD"]) / rho) - 1) < c["rtol"]
+    assert abs(float(r.dN_c[0]) / (-v["NCCOL"]) - 1) < c["rtol"]
+    assert float(r.self_collection_dNdt[0]) > 0
+
+
+def test_p3_logl_solver_parity(built, orc, cuda):
+    import torch
+    P3, CMP3 = built.P3, built.CMP3
+    mp, tps, st = _setup(built, 4000, seed=3)
+    blk = CMP3.pack_p3(mp, tps)
+    vol = _volumetric(st)
+    ref = orc.p3_state(blk, *vol, from_prognostic=True, want=("logl",))["logl"]
+    dv = [torch.from_numpy(v).to(cuda) for v in vol]
+    got = P3.get_distribution_logλ_from_prognostic(mp, tps, *dv).cpu().numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and (~fin).sum() > 500     # empty ice -> log(0)  (:289)
+    # same fixed 10 Brent iterations as the oracle: the iterates agree to rounding except where a branch of
+    # Brent's method flips on a rounding-level tie (both then sit within the solver's own residual error)
+    d = np.abs(got[fin] - ref[fin])
+    assert np.mean(d < 1e-10) > 0.99, np.mean(d < 1e-10)
+    conv = orc.p3_state(blk, *vol, from_prognostic=True, want=("logl",), logl_iters=40)["logl"]
+    assert np.max(np.abs(got[fin] - conv[fin])) <= np.max(np.abs(ref[fin] - conv[fin])) + 1e-6
+    got40 = P3.get_distribution_logλ_from_prognostic(mp, tps, *dv, brent_iters=40).cpu().numpy()
+    assert np.max(np.abs(got40[fin] - conv[fin])) < 1e-9
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 100])
+def test_p3_ragged_sizes_and_slab_independence(built, orc, cuda, n):
+    import torch
+    P3, CMP3, BMT = built.P3, built.CMP3, built.BMT
+    mp, tps, st = _setup(built, 100, seed=9)
+    blk = CMP3.pack_p3(mp, tps)
+    logl = _converged_logl(orc, blk, st)
+    cols = [torch.from_numpy(st[k]).to(cuda) for k in orc.P3_BMT_IN[:-1]] + [torch.from_numpy(logl).to(cuda)]
+    full = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *cols)
+    part = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[c[:n].contiguous() for c in cols])
+    for k in orc.P3_BMT_OUT[:-1]:
+        assert part[k].shape[0] == n
+        assert torch.equal(part[k], full[k][:n]), k            # a point's result does not depend on its tile mates
+    if n:   # an offset slab (different tile alignment) gives the same bits
+        off = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[c[100 - n:].contiguous() for c in cols])
+        for k in orc.P3_BMT_OUT[:-1]:
+            assert torch.equal(off[k], full[k][100 - n:]), k
+
+
+def test_p3_api_errors(built, cuda):
+    import torch
+    CMP, BMT, CMP3 = built.CMP, built.BMT, built.CMP3
+    mp = CMP.Microphysics2MParams(np.float64, with_ice=True)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    x = torch.ones(8, dtype=torch.float64, device=cuda)
+    with pytest.raises(built._abi.CuMicroError):
+        BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[torch.ones(8, dtype=torch.float64)] * 12)   # CPU tensors
+    bad = CMP3.GaussLegendre(np.float64, 12)
+    bad.n = 0
+    with pytest.raises(built._abi.CuMicroError):
+        BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[x] * 12, quad=bad)
+    with pytest.raises(ValueError):
+        CMP3.GaussLegendre(np.float64, 200)

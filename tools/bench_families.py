@@ -85,3 +85,27 @@ blk3 = CMP.pack_icenuc(tps, ad=arg_test_distribution("kappa"), dust=CMP.DustType
 o = [torch.empty_like(c[0]) for _ in fused.OUT_NAMES]
 report("fused 1M+2M+ice nucleation(+ARG) f64 2^24 per GPU (config 5)", n5,
        timeit(lambda: fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *c, out=o), reps=10), 176)
+del c, o
+
+# ---- P3 (config 4): stand-alone process rates + the fused 2M+P3 tendencies, Float64, 2^22 points
+from cumicro import P3  # noqa: E402
+from cumicro.testing import synthetic_states_p3  # noqa: E402
+
+n4 = 1 << (int(os.environ.get("CUMICRO_P3_LOG2N", "22")))
+st = synthetic_states_p3(n4)
+mp3 = CMP.Microphysics2MParams(np.float64, with_ice=True)
+KP = ("rho", "T", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim")
+d = {k: torch.from_numpy(v).to(dev) for k, v in st.items()}
+vol = [d[k] * d["rho"] for k in ("q_ice", "n_ice", "q_rim", "b_rim")]
+ms = timeit(lambda: P3.get_distribution_logλ_from_prognostic(mp3, tps, *vol), reps=5, warm=1)
+report("P3 get_distribution_logλ_from_prognostic f64", n4, ms, 40)
+logl = P3.get_distribution_logλ_from_prognostic(mp3, tps, *vol, brent_iters=30)
+logl = torch.where(torch.isfinite(logl), logl, torch.zeros_like(logl))
+ice_frac = float(((d["q_ice"] > 2.3e-16) & (d["n_ice"] > 2.3e-16)).double().mean())
+ms = timeit(lambda: P3.ice_terminal_velocities_from_prognostic(mp3, tps, d["rho"], *vol, logl), reps=5, warm=1)
+report("P3 ice terminal velocities (number + mass weighted) f64", n4, ms, 64)
+ms = timeit(lambda: P3.process_rates(mp3, tps, *[d[k] for k in KP], logl), reps=2, warm=1)
+report(f"P3 process rates GL(16) f64 2^{int(np.log2(n4))} (config 4; {ice_frac:.2f} of the points ice-bearing)", n4, ms, 192)
+cols = [d[k] for k in ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim")] + [logl]
+ms = timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp3, tps, *cols), reps=2, warm=1)
+report("2M + P3 fused tendencies (BMT:898-1083) f64", n4, ms, 160)
