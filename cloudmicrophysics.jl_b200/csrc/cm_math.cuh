@@ -180,13 +180,15 @@ CM_HD double exp_(double x) {
 // exp with the IEEE limits: gradual underflow into the subnormals, 0 below them, +Inf
 // above the range, NaN propagated.
 CM_HD double exp_full_(double x) {
-    const double xc = fmin(fmax(x, -708.0), 709.0);
-    double y = exp_(xc);
-    if (x < -708.0) {
-        // e^x = e^(x + 64 ln2) * 2^-64: the scaling multiply rounds once into the subnormal range
-        y = (x < -746.0) ? 0.0 : exp_(x + 44.361419555836500) * 5.421010862427522170e-20;
-    }
-    return (x != x) ? x : ((x > 709.0) ? ((x > 709.782712893384) ? num<double>::inf() : exp_(x - 1.0) * 2.718281828459045) : y);
+    // one exp_ evaluation on a shifted argument: e^x = e^(x + 64 ln2) 2^-64 below the normal range (the scaling
+    // multiply rounds once into the subnormals), e^x = e^(x - 1) e just below overflow
+    const bool lo = x < -708.0, hi = x > 709.0;
+    const double xs = lo ? x + 44.361419555836500 : (hi ? x - 1.0 : x);
+    const double sc = lo ? 5.421010862427522170e-20 : (hi ? 2.718281828459045 : 1.0);
+    double y = exp_(fmin(fmax(xs, -708.0), 709.0)) * sc;
+    y = (x < -746.0) ? 0.0 : y;
+    y = (x > 709.782712893384) ? num<double>::inf() : y;
+    return (x != x) ? x : y;
 }
 CM_HD float exp_(float x) { return expf(x); }
 CM_HD float exp_full_(float x) { return expf(x); }

@@ -31,26 +31,30 @@ constexpr int kGam = 24;          // (z, α) pairs of closed_rain_inner_NM: 4 ve
 // The series loop leaves early once a term is below half an ulp of the sum: the terms decrease
 // monotonically (x/(a+k) < 1), so every later addition is a no-op and the result is bit-identical
 // to the full loop.
-CM_HD void gamma_inc_(double a, double x, double lga, int iters, double& P, double& Q) {
-    if (x <= 0.0) { P = 0.0; Q = 1.0; return; }
-    if (x == num<double>::inf()) { P = 1.0; Q = 0.0; return; }
+struct PQ { double P, Q; };
+__host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double lga, int iters) {
+    PQ r;
+    if (x <= 0.0) { r.P = 0.0; r.Q = 1.0; return r; }
+    if (x == num<double>::inf()) { r.P = 1.0; r.Q = 0.0; return r; }
     const double factor = exp_full_(a * logp_(x) - x - lga);
     if (x < a + 1.0) {
         double term = div_(1.0, a);
         double sum = term;
+#pragma unroll 5
         for (int k = 1; k <= iters; ++k) {
             term *= x * rcp_(a + (double)k);
             sum += term;
             if (term < sum * 5.5e-17) break;
         }
-        P = clamp_(factor * sum, 0.0, 1.0);
-        Q = 1.0 - P;
+        r.P = clamp_(factor * sum, 0.0, 1.0);
+        r.Q = 1.0 - r.P;
     } else {
         const double tiny = 1e-30;
         const double b1 = x + 1.0 - a;
         double c = b1 + 1.0 / tiny;
         double d = rcp_(b1);
         double h = d;
+#pragma unroll 5
         for (int k = 1; k <= iters; ++k) {
             const double kd = (double)k;
             const double a_k = -kd * (kd - a);
@@ -62,22 +66,23 @@ CM_HD void gamma_inc_(double a, double x, double lga, int iters, double& P, doub
             d = rcp_(d);
             h *= c * d;
         }
-        Q = clamp_(factor * h, 0.0, 1.0);
-        P = 1.0 - Q;
+        r.Q = clamp_(factor * h, 0.0, 1.0);
+        r.P = 1.0 - r.Q;
     }
+    return r;
 }
 
 // ---- UT.gamma_inc_inv: Halley, <= 15 steps with the reference's exits                UT:205-252
-CM_HD double gamma_inc_inv_(double a, double p, double q, int iters, double eps) {
+__host__ __device__ __noinline__ inline double gamma_inc_inv_(double a, double p, double q, int iters, double eps) {
     if (p <= 0.0) return 0.0;
     if (q <= 0.0) return num<double>::inf();
     double x = (p < 0.5) ? pow_full_(p * tgamma_(a + 1.0), 1.0 / a) : (a - log_full_(q));
     const bool use_q = p > 0.5;
     const double lga = lgamma_(a);
+#pragma unroll 1
     for (int i = 1; i <= 15; ++i) {
-        double P, Q;
-        gamma_inc_(a, x, lga, iters, P, Q);
-        const double f = use_q ? Q - q : P - p;
+        const PQ g = gamma_inc_(a, x, lga, iters);
+        const double f = use_q ? g.Q - q : g.P - p;
         double fprime = exp_full_((a - 1.0) * log_full_(x) - x - lga);
         fprime = use_q ? -fprime : fprime;
         if (fprime == 0.0) break;
@@ -215,10 +220,12 @@ struct P3Scratch {
     double* gQ0;
     double* gP1;
     double* gQ1;
-    __host__ __device__ static constexpr int doubles(int n) { return 7 * n + 7 * kGam; }
+    double* tA;    // [4] α_j = λ_r + c_j of the 4 velocity terms (j = 0: the v_i term)
+    double* tC;    // [4] a_j (j >= 1)
+    __host__ __device__ static constexpr int doubles(int n) { return 7 * n + 7 * kGam + 8; }
     __device__ void bind(double* base, int n) {
         cD = base; cWN = cD + n; cM = cWN + n; cV = cM + n; rD = cV + n; rWNM = rD + n; rV = rWNM + n;
-        gz = rV + n; glg = gz + kGam; gG = glg + kGam; gP0 = gG + kGam; gQ0 = gP0 + kGam; gP1 = gQ0 + kGam; gQ1 = gP1 + kGam;
+        gz = rV + n; glg = gz + kGam; gG = glg + kGam; gP0 = gG + kGam; gQ0 = gP0 + kGam; gP1 = gQ0 + kGam; gQ1 = gP1 + kGam; tA = gQ1 + kGam; tC = tA + 4;
     }
 };
 
@@ -243,7 +250,7 @@ struct P3Point {
     }
     // everything the integrands need at one ice diameter
     struct Node { double logD, mass, dmass_dD_overD, area, v, n; };
-    template <bool NEED_V>
+    template <bool NEED_V, bool NEED_MELT = false>
     CM_DEV Node node(double D, const P3K& k) const {
         Node o;
         const double lD = logp_(D);
@@ -253,7 +260,7 @@ struct P3Point {
         const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
         o.mass = exp_(fma_(b, lD, la));
         // ∂m/∂D / D = a b D^(b-2)
-        o.dmass_dD_overD = b * exp_(fma_(b - 2.0, lD, la));
+        o.dmass_dD_overD = NEED_MELT ? b * exp_(fma_(b - 2.0, lD, la)) : 0.0;
         const double sph = D * D * (num<double>::pi() / 4.0);
         const double non = k.gamma_a * exp_(k.sigma_a * lD);
         o.area = (r == 0 || r == 3) ? sph : ((r == 4) ? F_rim * sph + (1.0 - F_rim) * non : non);
@@ -280,7 +287,7 @@ struct P3Point {
     CM_DEV double v_liq(double D, double lD) const {
         double v = 0.0;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) v += ra[j] * exp_full_(fma_(rb[j], lD, -rc[j] * D));
+        for (int j = 0; j < 3; ++j) v += ra[j] * exp_(fmax_(fma_(rb[j], lD, -rc[j] * D), -700.0));
         return v;
     }
     CM_DEV double v_liq(double D) const { return v_liq(D, logp_(D)); }
@@ -464,7 +471,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         for (int t = lane; t < sn.count(); t += 32) {
             double D, w;
             sn.get(t, qx, qw, D, w);
-            const P3Point::Node nd = s.node<true>(D, k);
+            const P3Point::Node nd = s.node<true, true>(D, k);
             const double nv = nd.n * nd.v;
             a_n += nv * w;
             a_m += nv * nd.mass * w;
@@ -600,11 +607,11 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                 sc.gz[lane] = z;
                 sc.glg[lane] = lg;
                 sc.gG[lane] = tgamma_(z) / pow_full_(alpha, z);
-                double P, Q;
-                gamma_inc_(z, alpha * rb0, lg, k.gamma_iters, P, Q);
-                sc.gP0[lane] = P; sc.gQ0[lane] = Q;
-                gamma_inc_(z, alpha * rb1, lg, k.gamma_iters, P, Q);
-                sc.gP1[lane] = P; sc.gQ1[lane] = Q;
+                PQ g = gamma_inc_(z, alpha * rb0, lg, k.gamma_iters);
+                sc.gP0[lane] = g.P; sc.gQ0[lane] = g.Q;
+                g = gamma_inc_(z, alpha * rb1, lg, k.gamma_iters);
+                sc.gP1[lane] = g.P; sc.gQ1[lane] = g.Q;
+                if (pi_ == 0) { sc.tA[j] = alpha; sc.tC[j] = (j == 0) ? 0.0 : s.ra[j - 1]; }
             }
         }
         __syncwarp();
@@ -632,6 +639,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
             const double k0 = pi * (r_i * r_i), k1 = pi * r_i, k2 = pi / 4.0;
             // cloud inner integrals (N, M, B)                                            :304-319
             double cN = 0.0, cMm = 0.0, cB = 0.0;
+#pragma unroll 1
             for (int j = 0; j < n; ++j) {
                 const double Dl = sc.cD[j];
                 const double dv = fabs(v_i - sc.cV[j]);
@@ -647,49 +655,40 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
             double rN = 0.0, rM = 0.0, rB = 0.0;
             if (rain_on) {
                 const double Dstar = brent_fixed([&](double D) { return s.v_liq(D) - v_i; }, rb0, rb1, vl_min - v_i, vl_max - v_i, k.brent_iters);
-                double fl[2][2];   // flux[piece][p = 0 | 3]
-                {
-                    double Ip[2][2][4];   // [piece][p0][term]
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double alpha = lam_r + ((j == 0) ? 0.0 : s.rc[j - 1]);
-                        const double xs = alpha * Dstar;
-#pragma unroll
-                        for (int p0 = 0; p0 < 2; ++p0) {
-                            double a_lo = 0.0, a_hi = 0.0;
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const int g = j * 6 + p0 * 3 + i;
-                                const double z = sc.gz[g];
-                                double Ps, Qs;
-                                gamma_inc_(z, xs, sc.glg[g], k.gamma_iters, Ps, Qs);
-                                // gamma_inc_moment(D_min, Dstar) and (Dstar, D_max)     P3_size_distribution.jl:121-133
-                                double m_lo = 0.0, m_hi = 0.0;
-                                if (Dstar > rb0) m_lo = sc.gG[g] * fmax_((xs < z + 1.0) ? Ps - sc.gP0[g] : sc.gQ0[g] - Qs, 0.0);
-                                if (rb1 > Dstar) m_hi = sc.gG[g] * fmax_((alpha * rb1 < z + 1.0) ? sc.gP1[g] - Ps : Qs - sc.gQ1[g], 0.0);
-                                const double coef = (i == 0) ? k0 : ((i == 1) ? k1 : k2);
-                                a_lo = (i == 0) ? coef * m_lo : a_lo + coef * m_lo;
-                                a_hi = (i == 0) ? coef * m_hi : a_hi + coef * m_hi;
-                            }
-                            Ip[0][p0][j] = a_lo;
-                            Ip[1][p0][j] = a_hi;
-                        }
+                // flux(a, b, p) = v_i Iᵖ(a, b, p, λ) - Σ_j a_j Iᵖ(a, b, p + b_j, λ + c_j) over the two pieces, p = 0 | 3
+                double f_lo0 = 0.0, f_hi0 = 0.0, f_lo3 = 0.0, f_hi3 = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const double alpha = sc.tA[j];
+                    const double xs = alpha * Dstar, x1 = alpha * rb1;
+                    double a_lo0 = 0.0, a_hi0 = 0.0, a_lo3 = 0.0, a_hi3 = 0.0;
+#pragma unroll 1
+                    for (int pi_ = 0; pi_ < 6; ++pi_) {
+                        const int g = j * 6 + pi_;
+                        const double z = sc.gz[g];
+                        const PQ q = gamma_inc_(z, xs, sc.glg[g], k.gamma_iters);
+                        // gamma_inc_moment(D_min, Dstar) and (Dstar, D_max)                P3_size_distribution.jl:121-133
+                        double m_lo = 0.0, m_hi = 0.0;
+                        if (Dstar > rb0) m_lo = sc.gG[g] * fmax_((xs < z + 1.0) ? q.P - sc.gP0[g] : sc.gQ0[g] - q.Q, 0.0);
+                        if (rb1 > Dstar) m_hi = sc.gG[g] * fmax_((x1 < z + 1.0) ? sc.gP1[g] - q.P : q.Q - sc.gQ1[g], 0.0);
+                        const int i = (pi_ >= 3) ? pi_ - 3 : pi_;
+                        const double coef = (i == 0) ? k0 : ((i == 1) ? k1 : k2);
+                        const double t_lo = coef * m_lo, t_hi = coef * m_hi;
+                        if (pi_ < 3) { a_lo0 = (i == 0) ? t_lo : a_lo0 + t_lo; a_hi0 = (i == 0) ? t_hi : a_hi0 + t_hi; }
+                        else         { a_lo3 = (i == 0) ? t_lo : a_lo3 + t_lo; a_hi3 = (i == 0) ? t_hi : a_hi3 + t_hi; }
                     }
-#pragma unroll
-                    for (int pc = 0; pc < 2; ++pc)
-#pragma unroll
-                        for (int p0 = 0; p0 < 2; ++p0) {
-                            double f = v_i * Ip[pc][p0][0];
-#pragma unroll
-                            for (int j = 1; j < 4; ++j) f -= s.ra[j - 1] * Ip[pc][p0][j];
-                            fl[pc][p0] = f;
-                        }
+                    if (j == 0) { f_lo0 = v_i * a_lo0; f_hi0 = v_i * a_hi0; f_lo3 = v_i * a_lo3; f_hi3 = v_i * a_hi3; }
+                    else {
+                        const double aj = sc.tC[j];
+                        f_lo0 -= aj * a_lo0; f_hi0 -= aj * a_hi0; f_lo3 -= aj * a_lo3; f_hi3 -= aj * a_hi3;
+                    }
                 }
-                const double dN = rp.N0r * (fl[0][0] - fl[1][0]);
-                const double dM = rp.N0r * mfac * (fl[0][1] - fl[1][1]);
+                const double dN = rp.N0r * (f_lo0 - f_hi0);
+                const double dM = rp.N0r * mfac * (f_lo3 - f_hi3);
                 if (isfinite(dN) && isfinite(dM)) {
                     rN = dN;
                     rM = dM;
+#pragma unroll 1
                     for (int j = 0; j < n; ++j) {
                         const double Dl = sc.rD[j];
                         const double dv = fabs(v_i - sc.rV[j]);

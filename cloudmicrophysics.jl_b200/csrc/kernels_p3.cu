@@ -20,7 +20,7 @@ namespace {
 using namespace cm;
 
 constexpr int BLOCK = 128;
-constexpr int MINB = 3;
+constexpr int MINB = 4;
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
 constexpr int NIN_MAX = 13, NOUT_MAX = 12;
 
@@ -312,10 +312,8 @@ struct P3LogLambda {
             const double z = (b + 0.0) + mu + 1.0;
             const double x1 = D1 * lam, x2 = D2 * lam;
             const double lg = lgamma_(z);
-            double p1, q1, p2, q2;
-            gamma_inc_(z, x1, lg, k.gamma_iters, p1, q1);
-            gamma_inc_(z, x2, lg, k.gamma_iters, p2, q2);
-            double dq = (x2 < z + 1.0) ? p2 - p1 : q1 - q2;
+            const PQ g1 = gamma_inc_(z, x1, lg, k.gamma_iters), g2 = gamma_inc_(z, x2, lg, k.gamma_iters);
+            double dq = (x2 < z + 1.0) ? g2.P - g1.P : g1.Q - g2.Q;
             dq = fmax_(dq, k.eps);
             m[sgm] = -z * logl + lg + log_full_(dq) + log_full_(a);
         }
