@@ -36,14 +36,17 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double
     PQ r;
     if (x <= 0.0) { r.P = 0.0; r.Q = 1.0; return r; }
     if (x == num<double>::inf()) { r.P = 1.0; r.Q = 0.0; return r; }
-    const double factor = exp_full_(a * logp_(x) - x - lga);
+    const double factor = exp_(fmin_(fmax_(a * logp_(x) - x - lga, -700.0), 700.0));
     if (x < a + 1.0) {
         double term = div_(1.0, a);
         double sum = term;
-#pragma unroll 5
-        for (int k = 1; k <= iters; ++k) {
-            term *= x * rcp_(a + (double)k);
-            sum += term;
+#pragma unroll 1
+        for (int k0 = 1; k0 <= iters; k0 += 5) {   // iters is 30 or 20
+#pragma unroll
+            for (int k = k0; k < k0 + 5; ++k) {
+                term *= x * rcp_(a + (double)k);
+                sum += term;
+            }
             if (term < sum * 5.5e-17) break;
         }
         r.P = clamp_(factor * sum, 0.0, 1.0);
@@ -249,12 +252,13 @@ struct P3Point {
         return (D < k.D_th) ? 0 : ((F_rim == 0.0) ? 1 : ((D < D_gr) ? 2 : ((D < D_cr) ? 3 : 4)));
     }
     // everything the integrands need at one ice diameter
-    struct Node { double logD, mass, dmass_dD_overD, area, v, n; };
+    // One code path for all regimes and both velocity curves (coefficients are selected, not branched on): the body
+    // stays within the ~6 KB L0 instruction cache of an SM sub-partition, which is what bounds this kernel.
+    struct Node { double mass, dmass_dD_overD, r, v, n; };   // r = sqrt(area / π)
     template <bool NEED_V, bool NEED_MELT = false>
     CM_DEV Node node(double D, const P3K& k) const {
         Node o;
         const double lD = logp_(D);
-        o.logD = lD;
         const int r = regime(D, k);
         const double la = (r == 0) ? la_small : ((r == 3) ? la_grp : ((r == 4) ? la_part : la_unr));
         const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
@@ -263,19 +267,18 @@ struct P3Point {
         o.dmass_dD_overD = NEED_MELT ? b * exp_(fma_(b - 2.0, lD, la)) : 0.0;
         const double sph = D * D * (num<double>::pi() / 4.0);
         const double non = k.gamma_a * exp_(k.sigma_a * lD);
-        o.area = (r == 0 || r == 3) ? sph : ((r == 4) ? F_rim * sph + (1.0 - F_rim) * non : non);
-        o.n = exp_full_(logN0 + mu * lD - lam * D);
+        const double area = (r == 0 || r == 3) ? sph : ((r == 4) ? F_rim * sph + (1.0 - F_rim) * non : non);
+        const double sa = sqrt_(area);
+        o.r = sa * 0.5641895835477563;   // 1/sqrt(π)
+        o.n = exp_(fmax_(logN0 + mu * lD - lam * D, -700.0));
         if (NEED_V) {
-            double v;
-            if (D <= k.cutoff) {
-                const double pw = exp_(sb * lD);
-                v = sa0 * pw + sa1 * pw * exp_full_(-sc1 * D);
-            } else {
-                v = ga0 * exp_(gb0 * lD) + ga1 * exp_full_(fma_(gb1, lD, -gc1 * D));
-            }
+            const bool small_ = D <= k.cutoff;
+            const double A0 = small_ ? sa0 : ga0, B0 = small_ ? sb : gb0, A1 = small_ ? sa1 : ga1, B1 = small_ ? sb : gb1,
+                         C1 = small_ ? sc1 : gc1;
+            double v = A0 * exp_(B0 * lD) + A1 * exp_(fmax_(fma_(B1, lD, -C1 * D), -700.0));
             if (k.aspect_oblate) {
                 const double rho_m = (r == 3) ? rho_g : k.rho_i;
-                const double phi = k.phi_coef * o.mass / (4.0 * rho_m * o.area * sqrt_(o.area));
+                const double phi = k.phi_coef * o.mass * rcp_(4.0 * rho_m * area * sa);
                 v *= cbrtp_(phi);
             }
             o.v = v;
@@ -394,7 +397,7 @@ struct SegNodes {
 CM_DEV double local_rime_density(const P3K& k, double Ri) {
     Ri = clamp_(Ri, 1.0, 12.0);
     if (Ri <= 8.0) return k.rim_a + k.rim_b * Ri + k.rim_c * (Ri * Ri);
-    const double f = (Ri - 8.0) / (12.0 - 8.0);
+    const double f = (Ri - 8.0) * 0.25;   // (Rᵢ - 8) / (12 - 8), exact
     return (1.0 - f) * k.rim8 + f * k.rim_rho_ice;
 }
 
@@ -506,7 +509,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                 sn.get(base + lane, qx, qw, D1, w);
                 const P3Point::Node nd = s.node<true>(D1, k);
                 v1 = nd.v;
-                r1 = sqrt_(nd.area / pi);
+                r1 = nd.r;
                 W1 = nd.n * w;
             }
             const int cnt = min(32, tot - base);
@@ -521,7 +524,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                         const double scale = (b - a) / 2.0, shift = (a + b) / 2.0;
                         const double D2 = scale * qx[i] + shift;
                         const P3Point::Node nd = s.node<true>(D2, k);
-                        const double r2 = sqrt_(nd.area / pi);
+                        const double r2 = nd.r;
                         const double K = pi * ((rr1 + r2) * (rr1 + r2));
                         part += K * fabs(vv1 - nd.v) * nd.n * (qw[i] * scale);
                     }
@@ -565,7 +568,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         const bool rain_on = !(rp.N0r == 0.0 || !(rb1 > rb0));
         const bool cloud_on = !cloud_off && (cb0 < cb1);
         const double TC = s.T - k.T_freeze;
-        const double two_TC = 2.0 * TC;
+        const double inv_two_TC = 1.0 / (2.0 * TC);   // Inf at T = T_freeze, like the reference's division by zero
 
         // inner nodes -> shared
         __syncwarp();
@@ -635,7 +638,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
             sn.get(t, qx, qw, Di, w);
             const P3Point::Node nd = s.node<true>(Di, k);
             const double v_i = nd.v;
-            const double r_i = sqrt_(nd.area / pi);
+            const double r_i = nd.r;
             const double k0 = pi * (r_i * r_i), k1 = pi * r_i, k2 = pi / 4.0;
             // cloud inner integrals (N, M, B)                                            :304-319
             double cN = 0.0, cMm = 0.0, cB = 0.0;
@@ -646,10 +649,10 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                 const double K = k0 + Dl * (k1 + Dl * k2);
                 const double t1 = (K * dv) * sc.cWN[j];
                 const double t2 = t1 * sc.cM[j];
-                const double Ri = (Dl * 1000000.0 * dv) / two_TC;
+                const double Ri = (Dl * 1000000.0 * dv) * inv_two_TC;
                 cN += t1;
                 cMm += t2;
-                cB += t2 / local_rime_density(k, Ri);
+                cB += t2 * rcp_(local_rime_density(k, Ri));
             }
             // rain inner integrals: closed form for N, M; quadrature for B             :381-415
             double rN = 0.0, rM = 0.0, rB = 0.0;
@@ -693,8 +696,8 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                         const double Dl = sc.rD[j];
                         const double dv = fabs(v_i - sc.rV[j]);
                         const double K = k0 + Dl * (k1 + Dl * k2);
-                        const double Ri = (Dl * 1000000.0 * dv) / two_TC;
-                        rB += (K * dv) * sc.rWNM[j] / local_rime_density(k, Ri);
+                        const double Ri = (Dl * 1000000.0 * dv) * inv_two_TC;
+                        rB += (K * dv) * sc.rWNM[j] * rcp_(local_rime_density(k, Ri));
                     }
                 }
             }
