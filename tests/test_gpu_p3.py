@@ -203,3 +203,49 @@ def test_p3_api_errors(built, cuda):
         BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *[x] * 12, quad=bad)
     with pytest.raises(ValueError):
         CMP3.GaussLegendre(np.float64, 200)
+
+
+def test_p3_f32_methods(built, orc, cuda):
+    """Float32 methods: Float32 columns and parameters, Float64 arithmetic with the Float32
+    method's thresholds and iteration counts (eps(Float32) gates, 20 gamma_inc terms, 8 Brent steps), one rounding
+    on store.  Criterion: <= 4 Float32 ULP from the true value of the Float32 method (the Float64 oracle in
+    f32_thresholds mode on the same Float32 inputs and widened parameters)."""
+    import torch
+    from cumicro.testing import assert_f32_method
+    CMP, CMP3, P3, BMT, T_ = built.CMP, built.CMP3, built.P3, built.BMT, built.testing
+    F = np.float32
+    mp = CMP.Microphysics2MParams(F, with_ice=True)
+    tps = CMP.ThermodynamicsParameters(F)
+    blk64 = CMP.widen(CMP3.pack_p3(mp, tps))
+    st = T_.synthetic_states_p3(700, seed=21, dtype=F)
+    st["T"][::3] -= F(25.0)
+    w = {k: v.astype(np.float64) for k, v in st.items()}
+    # Float32 arithmetic of BMT:921-929 for the volumetric quantities
+    vol32 = [(st[k] * st["rho"]).astype(np.float64) for k in ("q_ice", "n_ice", "q_rim", "b_rim")]
+    e32 = np.finfo(F).eps
+    with orc.f32_thresholds():
+        l = orc.p3_state(blk64, *vol32, from_prognostic=True, want=("logl",), logl_iters=40)["logl"]
+    logl = np.where(np.isfinite(l), l, 0.0).astype(F)
+    dcols = [torch.from_numpy(st[k]).to(cuda) for k in orc.P3_BMT_IN[:-1]] + [torch.from_numpy(logl).to(cuda)]
+    got = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp, tps, *dcols)
+    assert got["dq_ice_dt"].dtype == torch.float32
+    # truth: the volumetric products are formed in Float64 by the library from the Float32 specific quantities, as
+    # the Float64 oracle does from the widened inputs
+    cols64 = [w[k] for k in orc.P3_BMT_IN[:-1]] + [logl.astype(np.float64)]
+    with orc.f32_thresholds():
+        truth = orc.bmt2m_p3(blk64, *cols64)
+        bound = orc.bmt2m_p3(blk64, *cols64, bound=True)
+    worst = 0.0
+    for k in orc.P3_BMT_OUT[:-1]:
+        g = got[k].cpu().numpy()
+        worst = max(worst, assert_f32_method(k, g, truth[k].astype(F), truth[k], bound[k]))
+    ice = (st["q_ice"] > e32) & (st["n_ice"] > e32)
+    assert 0.5 < ice.mean() < 0.9 and worst <= 4
+    # logλ solver, Float32 method: 8 Brent iterations
+    dv = [torch.from_numpy(v.astype(F)).to(cuda) for v in vol32]
+    gl = P3.get_distribution_logλ_from_prognostic(mp, tps, *dv).cpu().numpy()
+    with orc.f32_thresholds():
+        rl = orc.p3_state(blk64, *[v.astype(F).astype(np.float64) for v in vol32], from_prognostic=True, want=("logl",))["logl"]
+    fin = np.isfinite(rl)
+    assert np.array_equal(np.isneginf(gl), np.isneginf(rl))
+    assert np.mean(np.abs(gl[fin] - rl[fin]) <= 4 * np.spacing(np.abs(rl[fin]).astype(F))) > 0.99
