@@ -33,6 +33,8 @@ template <class FT> struct SB2006K {
     FT inv_numadj_tau;
     FT inv_xc_min, inv_xc_max, inv_xr_max;
     FT two_pi;
+    int pw_acnv_b, pw_accr_c, pw_self_d;   // pow_param_code of the three parameter exponents
+    int same_rho0_evap, same_rho0_accr;    // evap.rho0 / accr.rho0 equal pdf_r.rho0 (one sqrt(rho0/rho) serves all)
 };
 
 template <class FT>
@@ -69,6 +71,8 @@ __host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, cons
     k.inv_xc_max = FT(1) / sb.pdf_c.xc_max;
     k.inv_xr_max = FT(1) / sb.pdf_r.xr_max;
     k.two_pi = 2 * pi;
+    k.pw_acnv_b = pow_param_code(sb.acnv.b); k.pw_accr_c = pow_param_code(sb.accr.c); k.pw_self_d = pow_param_code(sb.self.d);
+    k.same_rho0_evap = sb.evap.rho0 == sb.pdf_r.rho0; k.same_rho0_accr = sb.accr.rho0 == sb.pdf_r.rho0;
     return k;
 }
 
@@ -94,7 +98,7 @@ CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT p
         const FT inv_L = rcp_(L);
         const FT xt = clamp_(L * rcp_(safe_N), pdf.xr_min, pdf.xr_max);                       // SB2006 Eq. (94)
         const FT N0r = clamp_(safe_N * cbrtp_(pi_rho_w * rcp_(xt)), pdf.N0_min, pdf.N0_max);  // Eq. (95)
-        const FT lam = clamp_(sqrt_(sqrt_(pi_rho_w * N0r * inv_L)), pdf.lam_min, pdf.lam_max);  // Eq. (96)
+        const FT lam = clamp_(sqrtp_(sqrtp_(pi_rho_w * N0r * inv_L)), pdf.lam_min, pdf.lam_max);  // Eq. (96)
         const FT xr_mean = clamp_(L * lam * rcp_(N0r), pdf.xr_min, pdf.xr_max);                // Eq. (97)
         const bool cond = (N < e) && (q < e);
         r.lam = lam;
@@ -172,7 +176,7 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     const FT inv_cx = rcp_(cx);
     const FT inv_xr_mean = inv_cx * inv_cx * inv_cx;
     const FT Dr = cx * sk.cbrt_six_over_pi_rho_w;  // cbrt(6 xr/(pi rho_w)): mean-volume diameter  CM2:590, 802
-    const FT sqrt_rho0_rho = sqrt_(sb.pdf_r.rho0 * inv_rho);
+    const FT sqrt_rho0_rho = sqrtp_(sb.pdf_r.rho0 * inv_rho);
     const bool no_rain = (q_rai < e) || (N_rai < e);
 
     // ---- CM2.rain_evaporation                                       CM2:780-828
@@ -187,9 +191,10 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
         const FT gi1 = exp_(fma_(-sk.gi_e1[1], lt, -t_star)) * rcp_(fma_(sk.gi_c2[1], exp_(sk.gi_de[1] * lt), sk.gi_c1[1]));
         const FT a_vent_0 = sb.evap.a_vent_0_coeff * gi0;
         const FT b_vent_0 = sb.evap.b_vent_0_coeff * gi1;
-        const FT sqrt_rho0e = (sb.evap.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.evap.rho0 * inv_rho);
+        FT sqrt_rho0e = sqrt_rho0_rho;
+        if (!sk.same_rho0_evap) sqrt_rho0e = sqrt_(sb.evap.rho0 * inv_rho);
         const FT N_Re = sb.evap.alpha * exp_(sb.evap.beta * lx) * sqrt_rho0e * Dr * sk.inv_nu_air;
-        const FT v = sk.cbrt_Sc * sqrt_(N_Re);
+        const FT v = sk.cbrt_Sc * sqrtp_(N_Re);
         const FT Fv0 = fma_(b_vent_0, v, a_vent_0);
         const FT Fv1 = fma_(sb.evap.b_vent_1, v, sb.evap.a_vent_1);
         const FT common = sk.two_pi * G * S * N_rai * Dr;
@@ -211,7 +216,7 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
         const FT tau = FT(1) - div_(safe_q_lcl, safe_q_lcl + q_rai);          // SB2006 Eq. (5), IEEE, reference order
         const FT one_m_tau = FT(1) - tau;
         const FT tau_a = powp_(tau, sb.acnv.a);
-        const FT phi_au = (q_rai < e) ? FT(0) : sb.acnv.A * tau_a * pow_param(FT(1) - tau_a, sb.acnv.b);
+        const FT phi_au = (q_rai < e) ? FT(0) : sb.acnv.A * tau_a * pow_param(FT(1) - tau_a, sb.acnv.b, sk.pw_acnv_b);
         const FT LL = L_lcl * L_lcl;
         const FT dL_rai_dt = sk.acnv_pref * LL * (x_lcl * x_lcl) *
                              fma_(phi_au, rcp_(one_m_tau * one_m_tau), FT(1)) * inv_rho;   // Eq. (4)
@@ -233,8 +238,9 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
         // CM2.accretion                                                  CM2:445-470
         const FT L_rai = rho * safe_q_rai;
         // (accretion floors q_rai at eps instead of 0, CM2:452, but is gated off below eps: same tau)
-        const FT sqrt_rho0a = (sb.accr.rho0 == sb.pdf_r.rho0) ? sqrt_rho0_rho : sqrt_(sb.accr.rho0 * inv_rho);
-        const FT phi_ac = pow_param(tau * rcp_(tau + sb.accr.tau0), sb.accr.c);   // Eq. (8)
+        FT sqrt_rho0a = sqrt_rho0_rho;
+        if (!sk.same_rho0_accr) sqrt_rho0a = sqrt_(sb.accr.rho0 * inv_rho);
+        const FT phi_ac = pow_param(tau * rcp_(tau + sb.accr.tau0), sb.accr.c, sk.pw_accr_c);   // Eq. (8)
         const FT dLr = sb.accr.kcr * L_lcl * L_rai * phi_ac * sqrt_rho0a;             // Eq. (7)
         const bool off_ac = (q_lcl < e) || (q_rai < e) || (N_lcl < e);
         const FT dq_ac = off_ac ? FT(0) : dLr * inv_rho;
@@ -247,7 +253,7 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     {
         const FT L_rai = rho * safe_q_rai;
         const FT inv_Br = cx * sk.cbrt_one_sixth;   // 1/Br, Br = cbrt(6/xr_mean)   CM2:141-146
-        FT sc = -sb.self.krr * N_rai * L_rai * sqrt_rho0_rho * pow_param(fma_(sb.self.kappa_rr, inv_Br, FT(1)), sb.self.d);
+        FT sc = -sb.self.krr * N_rai * L_rai * sqrt_rho0_rho * pow_param(fma_(sb.self.kappa_rr, inv_Br, FT(1)), sb.self.d, sk.pw_self_d);
         sc = no_rain ? FT(0) : sc;
         const FT dD = Dr - sb.brek.Deq;
         const FT phi_p1 = (Dr < sb.brek.Dr_th) ? FT(0)

@@ -8,5 +8,6 @@ void cmt_exp_full(const double* x, double* y, long n) { for (long i = 0; i < n; 
 void cmt_log(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::logp_(x[i]); }
 void cmt_cbrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::cbrtp_(x[i]); }
 void cmt_rcp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::rcp_(x[i]); }
+void cmt_sqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::sqrtp_(x[i]); }
 void cmt_pow(const double* x, const double* p, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::powp_(x[i], p[i]); }
 }

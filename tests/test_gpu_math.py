@@ -39,6 +39,7 @@ def test_device_math_accuracy(built, cuda):
     x = np.concatenate([10 ** rng.uniform(-300, 300, 2000), rng.uniform(0.5, 16, 2000)])
     assert _max_ulp(_probe(built, cuda, 2, x), x, mp.cbrt) < 1.0
     assert _max_ulp(_probe(built, cuda, 3, x), x, lambda t: 1 / t) < 1.0
+    assert _max_ulp(_probe(built, cuda, 6, x), x, mp.sqrt) < 1.0
     xs, ps = 10 ** rng.uniform(-12, 3, 2000), rng.uniform(-5, 5, 2000)
     got = _probe(built, cuda, 4, xs, ps)
     mp.mp.dps = 40
