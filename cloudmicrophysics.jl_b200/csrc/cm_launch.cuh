@@ -19,8 +19,8 @@
 //     previous item of other warps;
 //   * the VEC points of one thread are evaluated in one unrolled body so the compiler
 //     interleaves their (independent) FP64 dependency chains;
-//   * persistent grid-stride launch: blocks = SMs x resident blocks, so the grid is a
-//     whole number of waves on the 148 SMs;
+//   * grid-stride launch: blocks = SMs x resident blocks x 16, a whole number of waves on the
+//     148 SMs (dynamic block scheduling evens out the SM-to-SM spread);
 //   * a scalar variant covers misaligned columns and the n % VEC tail.
 // NULL output pointers are skipped (optional diagnostics columns).
 #pragma once
@@ -79,12 +79,58 @@ pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int6
     }
 }
 
+
+// Software-pipelined one-point-per-thread variant: the inputs of a thread's NEXT grid-stride item are fetched with
+// per-thread asynchronous copies (cp.async / LDGSTS, global -> shared, no registers held) while the current item
+// is computed, so the ~900-instruction FP64 body never waits on HBM latency (ncu: long-scoreboard stalls were the
+// largest stall class of the register-loading variant).  Each thread reads back only its own slots: no block barrier.
+template <class T> __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(sizeof(T)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+pointwise_kernel_pipelined(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a) {
+    math_tables_init<BLOCK>();
+    __shared__ FT stage[2][NIN][BLOCK];
+    const int tid = threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK;
+    int64_t it = (int64_t)blockIdx.x * BLOCK + tid;
+    if (it < a.n) {
+#pragma unroll
+        for (int c = 0; c < NIN; ++c) cp_async_elem(&stage[0][c][tid], a.in[c] + it);
+    }
+    cp_async_commit();
+    int buf = 0;
+    for (; it < a.n; it += stride) {
+        const int64_t nxt = it + stride;
+        if (nxt < a.n) {
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) cp_async_elem(&stage[buf ^ 1][c][tid], a.in[c] + nxt);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();   // everything but the group just committed has landed
+        double x[NIN];
+#pragma unroll
+        for (int c = 0; c < NIN; ++c) x[c] = (double)stage[buf][c][tid];
+        double y[NOUT];
+        a.f(x, y);
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c)
+            if (a.out[c]) __stcs(a.out[c] + it, (FT)y[c]);
+        buf ^= 1;
+    }
+}
+
 // Enqueue F over n points on `stream`.  BLOCK x MINB fixes the register budget
 // (65536 / (BLOCK*MINB) per thread).  USE_VEC = false launches the one-point-per-thread
 // variant even for aligned columns: for the FP64-pipe-bound families (2M, 1M) the
 // measured optimum is 32 resident warps/SM at 64 registers with 64-bit loads (a warp
 // still reads one contiguous 256-byte run per column), tools/tune_2m.py.
-template <class FT, int NIN, int NOUT, class F, int BLOCK = 256, int MINB = 1, bool USE_VEC = true>
+template <class FT, int NIN, int NOUT, class F, int BLOCK = 256, int MINB = 1, bool USE_VEC = true, bool PIPELINED = false>
 int launch_pointwise(const F& f, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[NOUT], cudaStream_t stream,
                      const char* what) {
     if (n == 0) return CUMICRO_OK;
@@ -98,7 +144,32 @@ int launch_pointwise(const F& f, int64_t n, const FT* const (&in)[NIN], FT* cons
 #ifdef CUMICRO_TUNING
     { static const char* fs = getenv("CUMICRO_FORCE_SCALAR"); if (fs && fs[0] == '1') vec_ok = false; }
 #endif
-    const int max_blocks = cmh::num_sms() * MINB * 4;  // 4 equal waves of the resident grid
+    // 16 waves of the resident grid: blocks are dealt to SMs as they finish, which evens out the SM-to-SM spread
+    // (measured on the 2M kernel: 2 waves 0.699 ms, 4: 0.666, 16: 0.643, 32: 0.633, one item per thread 0.659)
+    int waves = 16;
+#ifdef CUMICRO_TUNING
+    { static const char* wv0 = getenv("CUMICRO_WAVES"); if (wv0) waves = atoi(wv0); }
+#endif
+    const int max_blocks = cmh::num_sms() * MINB * waves;
+    if constexpr (PIPELINED && !USE_VEC) {
+        bool ok = true;   // cp.async needs naturally aligned elements (always true for FT columns) -- keep the plain path for odd pointers
+        for (int c = 0; c < NIN; ++c) ok = ok && (reinterpret_cast<uintptr_t>(in[c]) % sizeof(FT) == 0);
+#ifdef CUMICRO_TUNING
+        { static const char* np = getenv("CUMICRO_NO_PIPELINE"); if (np && np[0] == '1') ok = false; }
+#endif
+        if (ok) {
+            auto kern = pointwise_kernel_pipelined<FT, NIN, NOUT, F, BLOCK, MINB>;
+            static bool carveout_set = false;   // 2 x NIN x BLOCK staged elements + the math tables per block, MINB blocks per SM
+            if (!carveout_set) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                carveout_set = true;
+            }
+            const int blocks = (int)std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)max_blocks);
+            kern<<<blocks, BLOCK, 0, stream>>>(a);
+            cmh::count_launch();
+            return cmh::cuda_status(cudaGetLastError(), what);
+        }
+    }
     int64_t first = 0;
     if (vec_ok && n >= VEC) {
         int64_t items = n / VEC;

@@ -107,7 +107,7 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
         }
     }
 #endif
-    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false>(f, n, in, out, s, "bmt2m_warm kernel launch");
+    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false, true>(f, n, in, out, s, "bmt2m_warm kernel launch");
 }
 
 template <class FT>
