@@ -27,6 +27,53 @@ namespace cm {
 constexpr int kQuadMax = 128;
 constexpr int kGam = 24;          // (z, α) pairs of closed_rain_inner_NM: 4 velocity terms x (p + i) in 0..5
 
+// ---- compact special functions for the per-point set-up -------------------------------------------
+// The set-up of one point (thresholds, PSD normalisation, Γ tables) runs once per ~80 k warp-instructions, but the
+// CUDA libm expansions of pow / lgamma / tgamma / log it would inline are ~8000 SASS instructions (130 KB): walking
+// them evicts the hot quadrature loops from the 32 KB instruction cache on every point.  These versions are a few
+// hundred instructions in total, out of line, and accurate to ~1e-15 on the argument ranges of the scheme.
+#include "cm_gamma_poly.inc"
+static const double cm_gamma_poly_host[CM_GAMMA_POLY_DEG + 1] = CM_GAMMA_POLY_INIT;
+#ifdef __CUDACC__
+static __constant__ double cm_gamma_poly_dev[CM_GAMMA_POLY_DEG + 1] = CM_GAMMA_POLY_INIT;
+#endif
+// Γ(x) for x >= 1: Γ(x) = (x-1)(x-2)...(x-k) Γ(x-k), x-k in [1, 2), 1/Γ on [1, 2] by a degree-15 polynomial.
+__host__ __device__ __noinline__ inline double tgamma_pos_(double x) {
+    if (!(x >= 1.0) || x > 64.0) return tgamma(x);
+    double p = 1.0;
+    while (x >= 2.0) { x -= 1.0; p *= x; }
+    const double u = 2.0 * x - 3.0;
+#ifdef __CUDA_ARCH__
+    const double* c = cm_gamma_poly_dev;
+#else
+    const double* c = cm_gamma_poly_host;
+#endif
+    double q = c[CM_GAMMA_POLY_DEG];
+#pragma unroll
+    for (int i = CM_GAMMA_POLY_DEG - 1; i >= 0; --i) q = fma(q, u, c[i]);
+    return p / q;
+}
+__host__ __device__ __noinline__ inline double lgamma_pos_(double x) {
+    if (!(x >= 1.0) || x > 64.0) return lgamma(x);
+    return logp_(tgamma_pos_(x));
+}
+// x^y, x positive normal: integer part of y by multiplication, fractional part through exp/log, so that the
+// relative error stays ~1e-15 for the large exponents of Γ(z)/α^z (|y ln x| up to ~100)
+__host__ __device__ __noinline__ inline double pow_pos_(double x, double y) {
+    if (!(x > 2.3e-308 && x < 1.7e308)) return pow(x, y);   // 0, Inf, NaN, subnormal (e.g. ρ_g = 0 -> D_gr = Inf): libm semantics
+    const double yi = floor(y);
+    const int n = (fabs(yi) <= 64.0) ? (int)yi : 0;
+    const double f = y - (double)n;
+    double r = 1.0, b = (n < 0) ? 1.0 / x : x;
+    for (int i = (n < 0 ? -n : n); i > 0; i >>= 1) { if (i & 1) r *= b; b *= b; }
+    return (f == 0.0) ? r : r * exp_full_(f * logp_(x));
+}
+__host__ __device__ __noinline__ inline double expm1_nl_(double x) { return expm1(x); }
+__host__ __device__ __noinline__ inline double log1p_nl_(double x) { return log1p(x); }
+__host__ __device__ __noinline__ inline double logp_nl_(double x) {     // one copy of logp_ for cold callers
+    return (x > 2.3e-308 && x < 1.7e308) ? logp_(x) : log(x);
+}
+
 // ---- UT.gamma_inc: series (x < a + 1) or Lentz continued fraction, fixed iterations   UT:92-144
 // The series loop leaves early once a term is below half an ulp of the sum: the terms decrease
 // monotonically (x/(a+k) < 1), so every later addition is a no-op and the result is bit-identical
@@ -79,14 +126,14 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double
 __host__ __device__ __noinline__ inline double gamma_inc_inv_(double a, double p, double q, int iters, double eps) {
     if (p <= 0.0) return 0.0;
     if (q <= 0.0) return num<double>::inf();
-    double x = (p < 0.5) ? pow_full_(p * tgamma_(a + 1.0), 1.0 / a) : (a - log_full_(q));
+    double x = (p < 0.5) ? pow_pos_(p * tgamma_pos_(a + 1.0), 1.0 / a) : (a - logp_nl_(q));
     const bool use_q = p > 0.5;
-    const double lga = lgamma_(a);
+    const double lga = lgamma_pos_(a);
 #pragma unroll 1
     for (int i = 1; i <= 15; ++i) {
         const PQ g = gamma_inc_(a, x, lga, iters);
         const double f = use_q ? g.Q - q : g.P - p;
-        double fprime = exp_full_((a - 1.0) * log_full_(x) - x - lga);
+        double fprime = exp_full_((a - 1.0) * logp_nl_(x) - x - lga);
         fprime = use_q ? -fprime : fprime;
         if (fprime == 0.0) break;
         const double f2 = (a - 1.0 - x) / x;
@@ -118,7 +165,8 @@ struct P3K {
     int slope_power_law, aspect_oblate;
     // thresholds: (6 α_va / (π ρ))^(1/(3 - β_va))
     double thr_p, thr_coef, D_th;
-    double pi6, phi_coef;                 // π/6, 3 sqrt(π)/4
+    double pi6, phi_coef;                 // π/6, 3 sqrt(π)
+    double log_rho_i_pi6, log_alpha_va, log_mu_c, log3;
     // air
     double cbrt_Nsc, inv_nu_air, K_therm, D_vapor;
     // Chen 2022 ice tables at ρᵢ = 916.7 (hard-coded in the reference, P3_terminal_velocity.jl:32)
@@ -151,6 +199,8 @@ __host__ inline P3K make_p3_k(const cumicro_params_p3_f64& p, bool method_is_f32
     k.thr_coef = 6.0 * s.alpha_va;
     k.D_th = std::pow(6.0 * s.alpha_va / (pi * s.rho_i), 1.0 / (3.0 - s.beta_va));
     k.pi6 = pi / 6.0;
+    k.log_rho_i_pi6 = std::log(s.rho_i * pi / 6.0); k.log_alpha_va = std::log(s.alpha_va);
+    k.log_mu_c = std::log(p.warm.sb.pdf_c.mu_c); k.log3 = std::log(3.0);
     k.phi_coef = 3.0 * std::sqrt(pi);
     const auto& aps = p.warm.aps;
     k.cbrt_Nsc = std::cbrt(aps.nu_air / aps.D_vapor);
@@ -304,8 +354,8 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
     s.rho_rim = fmin_(regularised_ratio_(L_rim, B_rim, k.eps), k.rho_l08);
     // get_ρ_d (exprel form)                                            P3_particle_properties.jl:191-199
     const double pp = k.thr_p;
-    const double logFu = log1p_(-s.F_rim);
-    auto exprel1 = [](double x) { return expm1_(x) / x; };
+    const double logFu = log1p_nl_(-s.F_rim);
+    auto exprel1 = [](double x) { return expm1_nl_(x) / x; };
     auto exprel2 = [](double x) {
         if (fabs(x) < 0.2) {
             double r = 1.0 / 362880.0;
@@ -314,7 +364,7 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
             for (int i = 0; i < 7; ++i) r = r * x + c[i];
             return r;
         }
-        return (expm1_(x) - x) / (x * x);
+        return (expm1_nl_(x) - x) / (x * x);
     };
     const double phi1 = exprel1(logFu);
     const double phi1mp = exprel1((1.0 - pp) * logFu);
@@ -324,30 +374,30 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
     s.rho_g = s.F_rim * s.rho_rim + (1.0 - s.F_rim) * rho_d;
     const bool unrimed = (s.F_rim == 0.0);
     const double pi = num<double>::pi();
-    s.D_gr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * s.rho_g), pp);
-    s.D_cr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * (s.rho_g * (1.0 - s.F_rim))), pp);
+    s.D_gr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * s.rho_g), pp);
+    s.D_cr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * (s.rho_g * (1.0 - s.F_rim))), pp);
     // ice_mass_coeffs                                                 P3_particle_properties.jl:346-359
     const double Fu = fmax_(1.0 - s.F_rim, k.eps);
-    s.la_small = log_full_(k.rho_i * pi / 6.0);
-    s.la_unr = log_full_(k.alpha_va);
-    s.la_grp = unrimed ? 0.0 : log_full_(s.rho_g * pi / 6.0);
-    s.la_part = log_full_(k.alpha_va / Fu);
+    s.la_small = k.log_rho_i_pi6;
+    s.la_unr = k.log_alpha_va;
+    s.la_grp = unrimed ? 0.0 : logp_nl_(s.rho_g * pi / 6.0);
+    s.la_part = logp_nl_(k.alpha_va / Fu);
     // get_μ, get_logN₀                                               P3_size_distribution.jl:171-237
     s.lam = exp_full_(logl);
-    s.mu = k.slope_power_law ? clamp_(k.slope_a * pow_full_(s.lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+    s.mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(s.lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
     {
         const double z = 0.0 + s.mu + 1.0;
-        s.logN0 = log_full_(N_ice) - (-z * logl + lgamma_(z) + 0.0);
+        s.logN0 = logp_nl_(N_ice) - (-z * logl + lgamma_pos_(z) + 0.0);
     }
     // Chen 2022 coefficients at ρₐ                                     CO:290-349
     const double ra_ = fmax_(rho, 0.0);
     const double log1000 = 6.907755278982137;
     {
-        const double pa = pow_full_(ra_, k.As);
+        const double pa = pow_pos_(ra_, k.As);
         const double b = k.Bs + ra_ * k.Cs;
         const double u = exp_full_(b * log1000);
         s.sa0 = (k.Es * pa) * u; s.sa1 = (k.Fs * pa) * u; s.sb = b; s.sc1 = k.Gs1000;
-        const double pl = pow_full_(ra_, k.Al);
+        const double pl = pow_pos_(ra_, k.Al);
         s.ga0 = (k.Bl * pl) * exp_full_(k.Cl * log1000);
         s.ga1 = (k.El * pl * exp_full_(k.Hl * ra_)) * exp_full_(k.Fl * log1000);
         s.gb0 = k.Cl; s.gb1 = k.Fl; s.gc1 = k.Gl1000;
@@ -548,11 +598,11 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         {
             const auto& pc = p.warm.sb.pdf_c;
             const double safe_q = fmax_(q_c, e), safe_N = fmax_(N_c, e);
-            const double logx = log_full_(rho * safe_q / safe_N);
+            const double logx = logp_nl_(rho * safe_q / safe_N);
             const double z1 = (pc.nu_c + 1.0) / pc.mu_c;
             const double lB = -pc.mu_c * (logx + pc.loggamma_z1 - pc.loggamma_z2);
-            const double lA = log_full_(pc.mu_c) + log_full_(safe_N) + z1 * lB - pc.loggamma_z1;
-            logN0c = lA + log_full_(3.0) + (pc.nu_c + 1.0) * k.log_km;
+            const double lA = k.log_mu_c + logp_nl_(safe_N) + z1 * lB - pc.loggamma_z1;
+            logN0c = lA + k.log3 + (pc.nu_c + 1.0) * k.log_km;
             loglam_c = lB + pc.mu_c * k.log_km;
             cb0 = exp_full_((k.cloud_log_z_lo - loglam_c) / k.mu_cD);
             cb1 = exp_full_((k.cloud_log_z_hi - loglam_c) / k.mu_cD);
@@ -561,7 +611,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         const RainPDF<double> rp = pdf_rain_parameters<double>(p.warm.sb.pdf_r, sk.pi_rho_w, e, q_r, rho, N_r);
         double rb0 = 0.0, rb1 = 0.0;
         if (!(rp.Dr_mean == 0.0)) {
-            const double lDr = log_full_(rp.Dr_mean);
+            const double lDr = logp_nl_(rp.Dr_mean);
             rb0 = exp_full_(lDr + k.rain_cll_lo);
             rb1 = exp_full_(lDr + k.rain_cll_hi);
         }
@@ -606,10 +656,11 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                 const double p0v = (pi_ >= 3) ? 3.0 : 0.0;
                 const double pj = (j == 0) ? p0v : p0v + s.rb[j - 1];     // flux: p + bi[j]
                 const double z = (pj + (double)(pi_ - (int)p0v)) + 1.0;   // Iᵖ: p + (i - 1); gamma_inc_moment: z = p + 1
-                const double lg = lgamma_(z);
+                const double tg = tgamma_pos_(z);
+                const double lg = logp_nl_(tg);
                 sc.gz[lane] = z;
                 sc.glg[lane] = lg;
-                sc.gG[lane] = tgamma_(z) / pow_full_(alpha, z);
+                sc.gG[lane] = tg / pow_pos_(alpha, z);
                 PQ g = gamma_inc_(z, alpha * rb0, lg, k.gamma_iters);
                 sc.gP0[lane] = g.P; sc.gQ0[lane] = g.Q;
                 g = gamma_inc_(z, alpha * rb1, lg, k.gamma_iters);

@@ -295,7 +295,7 @@ struct P3LogLambda {
     // logLdivN(state, logλ) - target                                    P3_size_distribution.jl:193-216
     __device__ double shape(double logl, double F_rim, double rho_g, double D_gr, double D_cr, double target) const {
         const double lam = exp_full_(logl);
-        const double mu = k.slope_power_law ? clamp_(k.slope_a * pow_full_(lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+        const double mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
         const double pi = num<double>::pi();
         const double inf = num<double>::inf();
         const double bnd[5] = {0.0, clamp_(k.D_th, 0.0, inf), clamp_(D_gr, 0.0, inf), clamp_(D_cr, 0.0, inf), inf};
@@ -311,7 +311,7 @@ struct P3LogLambda {
             if (!(D1 < D2)) { m[sgm] = -inf; continue; }
             const double z = (b + 0.0) + mu + 1.0;
             const double x1 = D1 * lam, x2 = D2 * lam;
-            const double lg = lgamma_(z);
+            const double lg = lgamma_pos_(z);
             const PQ g1 = gamma_inc_(z, x1, lg, k.gamma_iters), g2 = gamma_inc_(z, x2, lg, k.gamma_iters);
             double dq = (x2 < z + 1.0) ? g2.P - g1.P : g1.Q - g2.Q;
             dq = fmax_(dq, k.eps);
@@ -328,7 +328,7 @@ struct P3LogLambda {
             lse = mx + log_full_(sum);
         }
         const double z0 = 0.0 + mu + 1.0;
-        return (lse - (-z0 * logl + lgamma_(z0) + 0.0)) - target;
+        return (lse - (-z0 * logl + lgamma_pos_(z0) + 0.0)) - target;
     }
     __device__ __forceinline__ void operator()(const double (&x)[4], double (&y)[1]) const {
         const double L_ice = x[0], N_ice = x[1], L_rim = x[2], B_rim = x[3];
@@ -355,8 +355,8 @@ struct P3LogLambda {
         const double rho_g = F_rim * rho_rim + (1.0 - F_rim) * rho_d;
         const bool unrimed = (F_rim == 0.0);
         const double pi = num<double>::pi();
-        const double D_gr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * rho_g), pp);
-        const double D_cr = unrimed ? num<double>::inf() : pow_full_(k.thr_coef / (pi * (rho_g * (1.0 - F_rim))), pp);
+        const double D_gr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * rho_g), pp);
+        const double D_cr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * (rho_g * (1.0 - F_rim))), pp);
         const double target = log_full_(L_ice) - log_full_(N_ice);
         auto f = [&](double l) { return shape(l, F_rim, rho_g, D_gr, D_cr, target); };
         const double lo = 2.0, hi = 17.0;

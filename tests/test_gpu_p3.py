@@ -248,4 +248,10 @@ def test_p3_f32_methods(built, orc, cuda):
         rl = orc.p3_state(blk64, *[v.astype(F).astype(np.float64) for v in vol32], from_prognostic=True, want=("logl",))["logl"]
     fin = np.isfinite(rl)
     assert np.array_equal(np.isneginf(gl), np.isneginf(rl))
-    assert np.mean(np.abs(gl[fin] - rl[fin]) <= 4 * np.spacing(np.abs(rl[fin]).astype(F))) > 0.99
+    # 8 Brent iterations are not converged everywhere (tests/test_oracle_p3.py): where a branch of Brent's method flips on
+    # a rounding-level tie the two 8th iterates differ, both within the solver's own residual of the converged root
+    with orc.f32_thresholds():
+        conv = orc.p3_state(blk64, *[v.astype(F).astype(np.float64) for v in vol32], from_prognostic=True, want=("logl",), logl_iters=40)["logl"]
+    close = np.abs(gl[fin] - rl[fin]) <= 4 * np.spacing(np.abs(rl[fin]).astype(F))
+    assert np.mean(close) > 0.99, np.mean(close)
+    assert np.max(np.abs(gl[fin] - conv[fin])) <= np.max(np.abs(rl[fin] - conv[fin])) + 1e-5
