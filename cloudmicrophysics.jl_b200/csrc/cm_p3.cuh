@@ -55,8 +55,15 @@ __host__ __device__ __noinline__ inline double tgamma_pos_(double x) {
 }
 __host__ __device__ __noinline__ inline double lgamma_pos_(double x) {
     if (!(x >= 1.0) || x > 64.0) return lgamma(x);
-    return logp_(tgamma_pos_(x));
+    return log(tgamma_pos_(x));
 }
+__host__ __device__ __noinline__ inline double exp_nl_(double x) { return exp_full_(x); }            // one copy of exp for cold callers
+__host__ __device__ __noinline__ inline double expm1_nl_(double x) { return expm1(x); }
+__host__ __device__ __noinline__ inline double log1p_nl_(double x) { return log1p(x); }
+__host__ __device__ __noinline__ inline double logp_nl_(double x) {     // one copy of logp_ for cold callers
+    return (x > 2.3e-308 && x < 1.7e308) ? logp_(x) : log(x);
+}
+
 // x^y, x positive normal: integer part of y by multiplication, fractional part through exp/log, so that the
 // relative error stays ~1e-15 for the large exponents of Γ(z)/α^z (|y ln x| up to ~100)
 __host__ __device__ __noinline__ inline double pow_pos_(double x, double y) {
@@ -66,14 +73,8 @@ __host__ __device__ __noinline__ inline double pow_pos_(double x, double y) {
     const double f = y - (double)n;
     double r = 1.0, b = (n < 0) ? 1.0 / x : x;
     for (int i = (n < 0 ? -n : n); i > 0; i >>= 1) { if (i & 1) r *= b; b *= b; }
-    return (f == 0.0) ? r : r * exp_full_(f * logp_(x));
+    return (f == 0.0) ? r : r * exp_nl_(f * logp_nl_(x));
 }
-__host__ __device__ __noinline__ inline double expm1_nl_(double x) { return expm1(x); }
-__host__ __device__ __noinline__ inline double log1p_nl_(double x) { return log1p(x); }
-__host__ __device__ __noinline__ inline double logp_nl_(double x) {     // one copy of logp_ for cold callers
-    return (x > 2.3e-308 && x < 1.7e308) ? logp_(x) : log(x);
-}
-
 // ---- UT.gamma_inc: series (x < a + 1) or Lentz continued fraction, fixed iterations   UT:92-144
 // The series loop leaves early once a term is below half an ulp of the sum: the terms decrease
 // monotonically (x/(a+k) < 1), so every later addition is a no-op and the result is bit-identical
@@ -133,7 +134,7 @@ __host__ __device__ __noinline__ inline double gamma_inc_inv_(double a, double p
     for (int i = 1; i <= 15; ++i) {
         const PQ g = gamma_inc_(a, x, lga, iters);
         const double f = use_q ? g.Q - q : g.P - p;
-        double fprime = exp_full_((a - 1.0) * logp_nl_(x) - x - lga);
+        double fprime = exp_nl_((a - 1.0) * logp_nl_(x) - x - lga);
         fprime = use_q ? -fprime : fprime;
         if (fprime == 0.0) break;
         const double f2 = (a - 1.0 - x) / x;
@@ -170,7 +171,7 @@ struct P3K {
     // air
     double cbrt_Nsc, inv_nu_air, K_therm, D_vapor;
     // Chen 2022 ice tables at ρᵢ = 916.7 (hard-coded in the reference, P3_terminal_velocity.jl:32)
-    double As, Bs, Cs, Es, Fs, Gs1000, Al, Bl, Cl, El, Fl, Gl1000, Hl, cutoff;
+    double As, Bs, Cs, Es, Fs, Gs1000, Al, Bl, Cl, El, Fl, Gl1000, Hl, cutoff, pow1000_Cl, pow1000_Fl;
     // liquid PSDs
     double rho_w, mliq_coef, m_shd, log_km;
     double nu_cD, mu_cD, cloud_log_z_lo, cloud_log_z_hi;      // log gamma_inc_inv((νcD+1)/μcD, p | 1-p), p = 1e-5
@@ -223,6 +224,7 @@ __host__ inline P3K make_p3_k(const cumicro_params_p3_f64& p, bool method_is_f32
         k.Gl1000 = 1.0 / (g.G[0] + g.G[1] * l * sq + g.G[2] / sq) * 1000.0;
         k.Hl = g.H[0] + g.H[1] * (ri * ri) * sq + std::exp(std::log(-g.H[2]) - ri);
         k.cutoff = c.cutoff;
+        k.pow1000_Cl = std::exp(k.Cl * 6.907755278982137); k.pow1000_Fl = std::exp(k.Fl * 6.907755278982137);
     }
     const auto& pc = p.warm.sb.pdf_c;
     k.rho_w = pc.rho_w;
@@ -344,6 +346,12 @@ struct P3Point {
         return v;
     }
     CM_DEV double v_liq(double D) const { return v_liq(D, logp_(D)); }
+    CM_DEV double v_liq_nl(double D, double lD) const {   // the same through the out-of-line exp (set-up code)
+        double v = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) v += ra[j] * exp_nl_(fmax_(fma_(rb[j], lD, -rc[j] * D), -700.0));
+        return v;
+    }
 };
 
 // P3.state_from_prognostic + P3State + PSD parameters + velocity coefficients
@@ -383,7 +391,7 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
     s.la_grp = unrimed ? 0.0 : logp_nl_(s.rho_g * pi / 6.0);
     s.la_part = logp_nl_(k.alpha_va / Fu);
     // get_μ, get_logN₀                                               P3_size_distribution.jl:171-237
-    s.lam = exp_full_(logl);
+    s.lam = exp_nl_(logl);
     s.mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(s.lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
     {
         const double z = 0.0 + s.mu + 1.0;
@@ -395,14 +403,24 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
     {
         const double pa = pow_pos_(ra_, k.As);
         const double b = k.Bs + ra_ * k.Cs;
-        const double u = exp_full_(b * log1000);
+        const double u = exp_nl_(b * log1000);
         s.sa0 = (k.Es * pa) * u; s.sa1 = (k.Fs * pa) * u; s.sb = b; s.sc1 = k.Gs1000;
         const double pl = pow_pos_(ra_, k.Al);
-        s.ga0 = (k.Bl * pl) * exp_full_(k.Cl * log1000);
-        s.ga1 = (k.El * pl * exp_full_(k.Hl * ra_)) * exp_full_(k.Fl * log1000);
+        s.ga0 = (k.Bl * pl) * k.pow1000_Cl;
+        s.ga1 = (k.El * pl * exp_nl_(k.Hl * ra_)) * k.pow1000_Fl;
         s.gb0 = k.Cl; s.gb1 = k.Fl; s.gc1 = k.Gl1000;
     }
-    chen2022_vel_coeffs_rain<double>(p.vel_rain, rho, s.ra, s.rb, s.rc);
+    {   // CO.Chen2022_vel_coeffs(::Chen2022VelTypeRain, ρₐ)                          CO:290-300
+        const auto& v = p.vel_rain;
+        const double q = exp_nl_(v.rho0 * ra_);
+        const double ai[3] = {v.a[0] * q, v.a[1] * q, v.a[2] * q * pow_pos_(ra_, v.a3_pow)};
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) {
+            s.rb[i] = v.b[i] - v.b_rho * ra_;
+            s.ra[i] = ai[i] * exp_nl_(s.rb[i] * log1000);
+            s.rc[i] = v.c[i] * 1000.0;
+        }
+    }
 }
 
 // P3.integral_bounds -> segment_boundaries                       P3_integral_properties.jl:34-45
@@ -604,16 +622,16 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
             const double lA = k.log_mu_c + logp_nl_(safe_N) + z1 * lB - pc.loggamma_z1;
             logN0c = lA + k.log3 + (pc.nu_c + 1.0) * k.log_km;
             loglam_c = lB + pc.mu_c * k.log_km;
-            cb0 = exp_full_((k.cloud_log_z_lo - loglam_c) / k.mu_cD);
-            cb1 = exp_full_((k.cloud_log_z_hi - loglam_c) / k.mu_cD);
+            cb0 = exp_nl_((k.cloud_log_z_lo - loglam_c) / k.mu_cD);
+            cb1 = exp_nl_((k.cloud_log_z_hi - loglam_c) / k.mu_cD);
         }
         // rain PSD, bounds                                                             CM2:270-276, 337-345
         const RainPDF<double> rp = pdf_rain_parameters<double>(p.warm.sb.pdf_r, sk.pi_rho_w, e, q_r, rho, N_r);
         double rb0 = 0.0, rb1 = 0.0;
         if (!(rp.Dr_mean == 0.0)) {
             const double lDr = logp_nl_(rp.Dr_mean);
-            rb0 = exp_full_(lDr + k.rain_cll_lo);
-            rb1 = exp_full_(lDr + k.rain_cll_hi);
+            rb0 = exp_nl_(lDr + k.rain_cll_lo);
+            rb1 = exp_nl_(lDr + k.rain_cll_hi);
         }
         const bool rain_on = !(rp.N0r == 0.0 || !(rb1 > rb0));
         const bool cloud_on = !cloud_off && (cb0 < cb1);
@@ -626,29 +644,29 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
             {
                 const double scale = (cb1 - cb0) / 2.0, shift = (cb0 + cb1) / 2.0;
                 const double D = cloud_on ? scale * qx[j] + shift : 1e-6;
-                const double lD = logp_(D);
-                const double nc = exp_full_(logN0c + k.nu_cD * lD - exp_full_(fma_(k.mu_cD, lD, loglam_c)));
+                const double lD = logp_nl_(D);
+                const double nc = exp_nl_(logN0c + k.nu_cD * lD - exp_nl_(fma_(k.mu_cD, lD, loglam_c)));
                 sc.cD[j] = D;
                 sc.cWN[j] = cloud_on ? nc * (qw[j] * scale) : 0.0;
                 sc.cM[j] = k.mliq_coef * (D * D * D * pi / 6.0);
-                sc.cV[j] = s.v_liq(D, lD);
+                sc.cV[j] = s.v_liq_nl(D, lD);
             }
             {
                 const double scale = (rb1 - rb0) / 2.0, shift = (rb0 + rb1) / 2.0;
                 const double D = rain_on ? scale * qx[j] + shift : 1e-6;
-                const double lD = logp_(D);
-                const double nr = rp.N0r * exp_full_(-D / (rain_on ? rp.Dr_mean : 1.0));
+                const double lD = logp_nl_(D);
+                const double nr = rp.N0r * exp_nl_(-D / (rain_on ? rp.Dr_mean : 1.0));
                 sc.rD[j] = D;
                 sc.rWNM[j] = rain_on ? nr * (k.mliq_coef * (D * D * D * pi / 6.0)) * (qw[j] * scale) : 0.0;
-                sc.rV[j] = s.v_liq(D, lD);
+                sc.rV[j] = s.v_liq_nl(D, lD);
             }
         }
         // closed-form rain inner integral: the (z, α) table at the fixed ends       P3_processes.jl:344-369
         const double lam_r = rain_on ? 1.0 / rp.Dr_mean : 1.0;
         double vl_min = 0.0, vl_max = 0.0;
         if (rain_on) {
-            vl_min = s.v_liq(rb0);
-            vl_max = s.v_liq(rb1);
+            vl_min = s.v_liq_nl(rb0, logp_nl_(rb0));
+            vl_max = s.v_liq_nl(rb1, logp_nl_(rb1));
             if (lane < kGam) {
                 const int j = lane / 6, pi_ = lane - j * 6;     // velocity term (0: the v_i term), p + i
                 const double cj = (j == 0) ? 0.0 : s.rc[j - 1];
