@@ -11,7 +11,8 @@
 //   logp_  : table-driven (128 x (1/c, -log 1/c)) + degree-7 log1p polynomial    ~13 FP64
 //   powp_  : exp_(y * logp_(x)); relative error ~ |y ln x| * 3e-16               ~24 FP64
 //   cbrtp_ : FP32 MUFU (lg2/ex2) seed, one cubic step on x^(-1/3), one correction ~12 FP64
-//   rcp_   : MUFU.RCP64H seed + two Newton steps, <= 1 ulp                         4 FP64
+//   rcp_   : MUFU.RCP64H seed + one cubically convergent step, <= 1 ulp              3 FP64
+//   sqrtp_ : MUFU.RSQ64H seed + two coupled Newton steps, branch-free, < 1 ulp        7 FP64
 // Suffix `p` = positive, normal, finite argument required (garbage, not NaN, outside;
 // call sites select the result away in those cases, exactly where the reference's
 // ifelse does).  + - * / sqrt are IEEE operations, identical to the CPU reference; the
