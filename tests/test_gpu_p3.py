@@ -255,3 +255,42 @@ def test_p3_f32_methods(built, orc, cuda):
     close = np.abs(gl[fin] - rl[fin]) <= 4 * np.spacing(np.abs(rl[fin]).astype(F))
     assert np.mean(close) > 0.99, np.mean(close)
     assert np.max(np.abs(gl[fin] - conv[fin])) <= np.max(np.abs(rl[fin] - conv[fin])) + 1e-5
+
+
+def test_p3_full_size_properties_2pow22(built, cuda):
+    """BASELINE config 4 size (2^22 points, Float64): size-independent properties of the P3 process rates.
+    * liquid + ice mass is conserved by the collisions: ρ (∂ₜq_c + ∂ₜq_r) + ∂ₜL_ice = 0  (P3_processes.jl:640-650)
+    * velocities, melt and self-collection are non-negative and finite; outside the BMT:961 gate the rates are exactly 0
+    * a slab of the grid evaluated on its own gives the same bits (no coupling between points / tiles)."""
+    import torch
+    CMP, P3, T_ = built.CMP, built.P3, built.testing
+    n = 1 << 22
+    mp = CMP.Microphysics2MParams(np.float64, with_ice=True)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    st = T_.synthetic_states_p3(n, seed=1234)
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in st.items()}
+    vol = [d[k] * d["rho"] for k in ("q_ice", "n_ice", "q_rim", "b_rim")]
+    logl = P3.get_distribution_logλ_from_prognostic(mp, tps, *vol)
+    ice = (d["q_ice"] > EPS) & (d["n_ice"] > EPS)
+    assert bool(torch.isfinite(logl[ice]).all()) and bool(torch.isneginf(logl[(vol[0] < EPS) | (vol[1] < EPS)]).all())
+    assert float(logl[ice].min()) >= 2.0 and float(logl[ice].max()) <= 17.0
+    logl = torch.where(torch.isfinite(logl), logl, torch.zeros_like(logl))
+    cols = [d[k] for k in IN12] + [logl]
+    r = P3.process_rates(mp, tps, *cols)
+    for k, v in r.items():
+        assert bool(torch.isfinite(v).all()), k
+    for k in ("v_n", "v_m", "melt_dNdt", "melt_dLdt", "self_collection_dNdt", "dL_ice", "dL_rim"):
+        assert float(r[k].min()) >= 0.0, k
+    for k in ("dq_c", "dN_c"):
+        assert float(r[k].max()) <= 0.0, k
+    for k in P3.RATE_NAMES[2:]:
+        assert float(r[k][~ice].abs().max()) == 0.0, k
+    assert float(r["v_m"][ice].min()) > 0.0 and float((r["v_m"] >= r["v_n"])[ice].double().mean()) > 0.99
+    resid = d["rho"] * (r["dq_c"] + r["dq_r"]) + r["dL_ice"]
+    scale = r["dL_ice"].abs() + (d["rho"] * r["dq_r"]).abs() + (d["rho"] * r["dq_c"]).abs()
+    assert float((resid.abs() / torch.clamp(scale, min=1e-300)).max()) < 1e-14
+    assert float((r["melt_dLdt"][ice & (d["T"] <= 273.15)]).abs().max()) == 0.0
+    lo, hi = n // 3 + 5, n // 3 + 5 + (1 << 16) + 7        # a slab that is not tile-aligned
+    part = P3.process_rates(mp, tps, *[c[lo:hi].contiguous() for c in cols])
+    for k in P3.RATE_NAMES:
+        assert torch.equal(part[k], r[k][lo:hi]), k

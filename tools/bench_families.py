@@ -106,6 +106,21 @@ ms = timeit(lambda: P3.ice_terminal_velocities_from_prognostic(mp3, tps, d["rho"
 report("P3 ice terminal velocities (number + mass weighted) f64", n4, ms, 64)
 ms = timeit(lambda: P3.process_rates(mp3, tps, *[d[k] for k in KP], logl), reps=2, warm=1)
 report(f"P3 process rates GL(16) f64 2^{int(np.log2(n4))} (config 4; {ice_frac:.2f} of the points ice-bearing)", n4, ms, 192)
+# CPU port of the same integrals on a bounded sample (all host cores), for the GPU/CPU ratio quoted in DESIGN.md
+from oracle import oracle as orc  # noqa: E402
+orc.set_num_threads(os.cpu_count() or 1)
+m = 1 << 12
+blk = cumicro.CMP3.pack_p3(mp3, tps)
+hs = {k: v[:m] for k, v in st.items()}
+hl = logl[:m].cpu().numpy()
+import time  # noqa: E402
+t0 = time.perf_counter()
+orc.p3_state(blk, *[hs[k] * hs["rho"] for k in ("q_ice", "n_ice", "q_rim", "b_rim")], from_prognostic=True, rho_a=hs["rho"], T=hs["T"], logl=hl,
+             L_c=hs["q_lcl"] * hs["rho"], N_c=hs["n_lcl"] * hs["rho"], L_r=hs["q_rai"] * hs["rho"], N_r=hs["n_rai"] * hs["rho"],
+             want=("v_n", "v_m", "melt", "selfcol", "src7"))
+dt = time.perf_counter() - t0
+print(json.dumps({"family": "P3 process rates, CPU port (oracle, OpenMP)", "points": m, "ms": dt * 1e3, "points_per_s": m / dt,
+                  "threads": orc.num_threads()}), flush=True)
 cols = [d[k] for k in ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim")] + [logl]
 ms = timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp3, tps, *cols), reps=2, warm=1)
 report("2M + P3 fused tendencies (BMT:898-1083) f64", n4, ms, 160)
