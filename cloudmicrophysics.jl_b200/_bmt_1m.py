@@ -50,10 +50,19 @@ def bmt_1m(mode, mp, tps, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, Δt=None, n
     return res
 
 
-def bmt_0m(mp, tps, T, q_lcl, q_icl, q_vap_sat=None):
-    """BMT:658-680 → Microphysics0M.remove_precipitation (src/Microphysics0M.jl:35-46):
-    ``-max(0, q_lcl + q_icl - threshold)/τ_precip`` with threshold ``qc_0`` or ``S_0 q_vap_sat``.
-    One fused elementwise pass; ``mp`` is a Parameters0M-like object with τ_precip, qc_0, S_0."""
-    check_columns([T, q_lcl, q_icl] + ([q_vap_sat] if q_vap_sat is not None else []), ["T", "q_lcl", "q_icl", "q_vap_sat"])
-    thr = mp.qc_0 if q_vap_sat is None else mp.S_0 * q_vap_sat
-    return Tendencies(dq_tot_dt=-torch.clamp_min(q_lcl + q_icl - thr, 0) / mp.τ_precip)
+def bmt_0m(mp, tps, T, q_lcl, q_icl, q_vap_sat=None, *, out=None):
+    """BMT:658-680 -> Microphysics0M.remove_precipitation (src/Microphysics0M.jl:35-46):
+    ``-max(0, q_lcl + q_icl - threshold)/τ_precip`` with threshold ``qc_0`` or ``S_0 q_vap_sat``, inputs clamped to >= 0.
+    ``mp`` is a ``Microphysics0MParams`` (or a bare ``Parameters0M`` block); ``T`` is accepted and not read, as in the reference."""
+    cols = [q_lcl, q_icl] + ([q_vap_sat] if q_vap_sat is not None else [])
+    suf, n, dev = check_columns(cols, ["q_lcl", "q_icl", "q_vap_sat"])
+    blk = getattr(mp, "precip", mp)
+    if not type(blk).__name__.endswith(suf):
+        raise TypeError(f"parameter float type does not match the columns ({suf})")
+    out = out if out is not None else torch.empty_like(q_lcl)
+    check_columns([q_lcl, out], ["q_lcl", "out"])
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_bmt0m_{suf}")(C.byref(blk), C.c_int64(n), ptr(q_lcl), ptr(q_icl), ptr(q_vap_sat), ptr(out),
+                                                         stream_handle(dev))
+    _abi.check(st, "cumicro_bmt0m")
+    return Tendencies(dq_tot_dt=out)

@@ -235,3 +235,44 @@ CUMICRO_DEF_1M(f64, double)
 CUMICRO_DEF_1M(f32, float)
 
 }  // extern "C"
+
+// ---- 0-moment scheme (BMT:658-680, src/Microphysics0M.jl:35-46): HBM-bound, 24-32 B/point ----------------------
+namespace {
+template <class FT, bool WITH_SAT> struct ZeroM {
+    FT tau_precip, qc_0, S_0;
+    __device__ __forceinline__ void operator()(const double (&x)[WITH_SAT ? 3 : 2], double (&y)[1]) const {
+        // the Float32 method's arithmetic is Float32 (three operations: nothing to gain from widening)
+        const FT q_lcl = cm::fmax_(FT(0), (FT)x[0]), q_icl = cm::fmax_(FT(0), (FT)x[1]);
+        const FT thr = WITH_SAT ? S_0 * (FT)x[2] : qc_0;
+        y[0] = (double)(-cm::fmax_(FT(0), q_lcl + q_icl - thr) / tau_precip);
+    }
+};
+template <class FT, class PB>
+int bmt0m_impl(const PB* p, int64_t n, const FT* q_lcl, const FT* q_icl, const FT* q_vap_sat, FT* out, void* stream) {
+    FT* o[1] = {out};
+    if (p == nullptr) return cmh::fail(CUMICRO_E_NULL, "parameter block is NULL");
+    int st;
+    if (q_vap_sat) {
+        const FT* in[3] = {q_lcl, q_icl, q_vap_sat};
+        if ((st = cm::validate_columns<FT, 3>(p, n, in))) return st;
+        if ((st = cm::require_outputs<FT, 1>(n, o, 1))) return st;
+        return cm::launch_pointwise<FT, 3, 1, ZeroM<FT, true>, 256, 4>(ZeroM<FT, true>{p->tau_precip, p->qc_0, p->S_0}, n, in, o,
+                                                                      (cudaStream_t)stream, "bmt0m launch");
+    }
+    const FT* in[2] = {q_lcl, q_icl};
+    if ((st = cm::validate_columns<FT, 2>(p, n, in))) return st;
+    if ((st = cm::require_outputs<FT, 1>(n, o, 1))) return st;
+    return cm::launch_pointwise<FT, 2, 1, ZeroM<FT, false>, 256, 4>(ZeroM<FT, false>{p->tau_precip, p->qc_0, p->S_0}, n, in, o,
+                                                                   (cudaStream_t)stream, "bmt0m launch");
+}
+}  // namespace
+extern "C" {
+int cumicro_bmt0m_f64(const cumicro_params_0m_f64* p, int64_t n, const double* q_lcl, const double* q_icl, const double* q_vap_sat,
+                      double* dq_tot_dt, void* stream) {
+    return bmt0m_impl<double>(p, n, q_lcl, q_icl, q_vap_sat, dq_tot_dt, stream);
+}
+int cumicro_bmt0m_f32(const cumicro_params_0m_f32* p, int64_t n, const float* q_lcl, const float* q_icl, const float* q_vap_sat,
+                      float* dq_tot_dt, void* stream) {
+    return bmt0m_impl<float>(p, n, q_lcl, q_icl, q_vap_sat, dq_tot_dt, stream);
+}
+}  // extern "C"

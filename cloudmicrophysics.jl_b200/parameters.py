@@ -169,6 +169,11 @@ DEFAULTS = {
     "cloud_ice_snow_collision_efficiency": 0.1,
     "rain_snow_collision_efficiency": 1.0,
     "rain_snow_velocity_dispersion_coefficient": 0.2,  # back-solved (exact) from both goldens of test/microphysics1M_tests.jl:380-453
+    # --- 0-moment scheme (CMP/Microphysics0M.jl:20-28); ClimaParams defaults, not pinned by any reference test
+    #     (its tests compare remove_precipitation with the formula evaluated on the same parameters)
+    "precipitation_timescale": 1000.0,
+    "specific_humidity_precipitation_threshold": 5e-6,
+    "supersaturation_precipitation_threshold": 0.02,
     # --- Frostenberg et al. 2023 INP concentration (IN:219-253)
     "Frostenberg2023_standard_deviation": 1.5,          # sigma: only loosely pinned (test/gpu_tests.jl:1035: 0.26 +- 10 %)
     "Frostenberg2023_a_coefficient": 1.0,
@@ -484,6 +489,27 @@ def Chen2022VelTypeLargeIce(FT=np.float64, overrides=None):
         A=td["Chen2022_table_B5_Al"], B=td["Chen2022_table_B5_Bl"], C=td["Chen2022_table_B5_Cl"],
         E=td["Chen2022_table_B5_El"], F=td["Chen2022_table_B5_Fl"], G=td["Chen2022_table_B5_Gl"],
         H=td["Chen2022_table_B5_Hl"], cutoff=td["Chen2022_ice_cutoff"])
+
+
+# ============================ 0-moment scheme ==========================================
+def Parameters0M(FT=np.float64, overrides=None):
+    """CMP.Parameters0M (Microphysics0M.jl:11-28): τ_precip, qc_0, S_0."""
+    td = _td(FT, overrides)
+    return _abi.struct("params_0m", td.suffix)(tau_precip=td["precipitation_timescale"],
+                                               qc_0=td["specific_humidity_precipitation_threshold"],
+                                               S_0=td["supersaturation_precipitation_threshold"])
+
+
+@dataclass
+class Microphysics0MParams_:
+    """CMP.Microphysics0MParams{P} (Microphysics0MParams.jl:20-22): a single field ``precip``."""
+    precip: Any
+    FT: Any = np.float64
+
+
+def Microphysics0MParams(FT=np.float64, overrides=None):
+    td = _td(FT, overrides)
+    return Microphysics0MParams_(precip=Parameters0M(td), FT=td.FT)
 
 
 # ============================ 1-moment scheme ==========================================

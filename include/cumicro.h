@@ -359,6 +359,17 @@ int cumicro_p3_logl_f64(const cumicro_params_p3_f64* p, int64_t n, const double*
 int cumicro_p3_logl_f32(const cumicro_params_p3_f32* p, int64_t n, const float* L_ice, const float* N_ice, const float* L_rim,
                         const float* B_rim, int brent_iters, float* logl, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * 0-moment scheme: bulk_microphysics_tendencies(::Microphysics0Moment, mp, tps, T, q_lcl, q_icl[, q_vap_sat])
+ * BMT:658-680 -> CM0.remove_precipitation (src/Microphysics0M.jl:35-46):
+ *   dq_tot_dt = -max(0, q_lcl + q_icl - threshold) / tau_precip, threshold = qc_0 (q_vap_sat == NULL) or S_0 q_vap_sat,
+ * with the inputs clamped to >= 0 (BMT:662-663).  T does not enter the arithmetic and is not read.
+ * ------------------------------------------------------------------------- */
+int cumicro_bmt0m_f64(const cumicro_params_0m_f64* p, int64_t n, const double* q_lcl, const double* q_icl,
+                      const double* q_vap_sat, double* dq_tot_dt, void* stream);
+int cumicro_bmt0m_f32(const cumicro_params_0m_f32* p, int64_t n, const float* q_lcl, const float* q_icl,
+                      const float* q_vap_sat, float* dq_tot_dt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

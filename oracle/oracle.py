@@ -18,7 +18,8 @@ _lib = None
 
 def build(force: bool = False):
     """Compile the oracle with the committed Makefile (g++, -ffp-contract=off, OpenMP)."""
-    if force or not os.path.exists(LIB_PATH):
+    # always through make (incremental: a no-op when the library is newer than every source / header)
+    if force or not os.path.exists(LIB_PATH) or os.path.exists(os.path.join(_HERE, "Makefile")):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -297,5 +298,18 @@ def bmt2m_p3(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_
     out = {k: np.empty(n, np.float64) for k in P3_BMT_OUT}
     o9 = (C.c_void_p * 9)(*[_ptr(out[k]) for k in P3_BMT_OUT])
     st = lib().oracle_bmt2m_p3_f64(C.byref(params), C.c_int64(n), in13, o9, C.c_int(int(bound)))
+    assert st == 0
+    return out
+
+
+# ---- 0-moment scheme ---------------------------------------------------------------------------
+def bmt0m(params, q_lcl, q_icl, q_vap_sat=None):
+    """BMT:658-680 over arrays (native arithmetic of the block's float type)."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    cols = [q_lcl, q_icl] + ([q_vap_sat] if q_vap_sat is not None else [])
+    cols, n = _cols(cols, dtype)
+    out = np.empty(n, dtype)
+    st = getattr(lib(), f"oracle_bmt0m_{_suf(dtype)}")(C.byref(params), C.c_int64(n), _ptr(cols[0]), _ptr(cols[1]),
+                                                      _ptr(cols[2]) if len(cols) == 3 else None, _ptr(out))
     assert st == 0
     return out

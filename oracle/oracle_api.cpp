@@ -390,4 +390,24 @@ int oracle_bmt2m_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double*
     return 0;
 }
 
+
+// ---- 0-moment scheme: BMT:658-680 -> CM0.remove_precipitation (src/Microphysics0M.jl:35-46), native FT arithmetic
+}  // extern "C"
+template <class FT, class PB> static void bmt0m_cols(const PB* p, int64_t n, const FT* q_lcl, const FT* q_icl, const FT* q_vap_sat, FT* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        FT ql = clamp_to_nonneg(q_lcl[i]), qi = clamp_to_nonneg(q_icl[i]);
+        FT thr = q_vap_sat ? FT(p->S_0 * q_vap_sat[i]) : FT(p->qc_0);
+        out[i] = -jmax(FT(0), FT(ql + qi - thr)) / FT(p->tau_precip);
+    }
+}
+extern "C" {
+int oracle_bmt0m_f64(const cumicro_params_0m_f64* p, int64_t n, const double* q_lcl, const double* q_icl, const double* q_vap_sat, double* out) {
+    bmt0m_cols<double>(p, n, q_lcl, q_icl, q_vap_sat, out);
+    return 0;
+}
+int oracle_bmt0m_f32(const cumicro_params_0m_f32* p, int64_t n, const float* q_lcl, const float* q_icl, const float* q_vap_sat, float* out) {
+    bmt0m_cols<float>(p, n, q_lcl, q_icl, q_vap_sat, out);
+    return 0;
+}
+
 }  // extern "C"

@@ -186,3 +186,24 @@ def test_config1_grid_64cubed(built, orc, cuda):
     for k in orc.OUT_1M:
         rep = assert_parity(k, out[k].cpu().numpy(), ref[k], bound=bnd[k])
         assert rep["max_rel"] <= 1e-12 and rep["frac_forward_ok"] > 0.98, (k, rep)
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_0m_bit_exact(built, orc, cuda, FT):
+    """BMT:658-680: three IEEE operations per point in the method's own float type -> bit-exact against the oracle."""
+    import torch
+    CMP, BMT = built.CMP, built.BMT
+    mp = CMP.Microphysics0MParams(FT)
+    tps = CMP.ThermodynamicsParameters(FT)
+    rng = np.random.default_rng(4)
+    n = 100003
+    ql = (rng.random(n) * 4e-3 - 5e-4).astype(FT)
+    qi = (rng.random(n) * 4e-3 - 5e-4).astype(FT)
+    qvs = (rng.random(n) * 2e-2).astype(FT)
+    T = np.full(n, 280.0, FT)
+    d = lambda a: torch.from_numpy(a).to(cuda)
+    got = BMT.bulk_microphysics_tendencies(BMT.Microphysics0Moment(), mp, tps, d(T), d(ql), d(qi))
+    assert np.array_equal(got.dq_tot_dt.cpu().numpy(), orc.bmt0m(mp.precip, ql, qi))
+    got = BMT.bulk_microphysics_tendencies(BMT.Microphysics0Moment(), mp, tps, d(T), d(ql), d(qi), d(qvs))
+    ref = orc.bmt0m(mp.precip, ql, qi, qvs)
+    assert np.array_equal(got.dq_tot_dt.cpu().numpy(), ref) and (ref < 0).mean() > 0.3 and (ref == 0).mean() > 0.01

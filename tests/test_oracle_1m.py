@@ -112,3 +112,20 @@ def test_linearized_average_properties(built, orc):
         for k, q in zip(orc.OUT_1M, ("q_lcl", "q_icl", "q_rai", "q_sno")):
             assert np.all(np.isfinite(avg[k]))
             assert np.all(st[q] + dt * avg[k] >= -1e-12)
+
+
+def test_0m_remove_precipitation(built, orc):
+    """test/microphysics0M_tests.jl:12-55: no removal without cloud, the qc_0 and S_0 thresholds, input clamps (BMT:662-663)."""
+    CMP = built.CMP
+    for FT in (np.float64, np.float32):
+        p = CMP.Parameters0M(FT)
+        tau, qc0, S0 = FT(p.tau_precip), FT(p.qc_0), FT(p.S_0)
+        z = np.zeros(3, FT)
+        assert np.all(orc.bmt0m(p, z, z) == 0) and np.all(orc.bmt0m(p, z, z, np.full(3, 10e-3, FT)) == 0)
+        qc = FT(3e-3)
+        lf = np.array([0, 0.5, 1.0], FT)
+        ql, qi = qc * lf, (FT(1) - lf) * qc
+        assert np.array_equal(orc.bmt0m(p, ql, qi), -np.maximum(FT(0), ql + qi - qc0) / tau)
+        qvs = np.full(3, 10e-3, FT)
+        assert np.array_equal(orc.bmt0m(p, ql, qi, qvs), -np.maximum(FT(0), ql + qi - S0 * qvs) / tau)
+        assert np.array_equal(orc.bmt0m(p, -ql, qi), orc.bmt0m(p, z, qi))
