@@ -89,3 +89,45 @@ def INP_concentration_mean(frostenberg, tps, T):
 def dust_activated_number_fraction(dust, ip, tps, Si, T, check_domain=True):
     """IN.dust_activated_number_fraction (IN:44-52)."""
     return _leaf("dust_activated_number_fraction", CMP.pack_icenuc(tps, dust=dust, mohler=ip), Si, T, check_domain=check_domain)
+
+
+# ---- multi-argument rates (cumicro_icenuc_rates_*) ---------------------------------------------------------
+RATES = {"MohlerDepositionRate": 0, "P3_het_N_i": 1, "INP_concentration_frequency": 2, "het_ice_nucleation": 3}
+
+
+def _rates(what, blk, cols, two=False, check_domain=True):
+    from ._columns import ptr_table
+    suf, n, dev = check_columns(cols, [f"arg{i}" for i in range(len(cols))])
+    out = torch.empty_like(cols[0])
+    out2 = torch.empty_like(cols[0]) if two else None
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    fn = getattr(_abi.load(), f"cumicro_icenuc_rates_{suf}")
+    with torch.cuda.device(dev):
+        st = fn(C.byref(blk), C.c_int(RATES[what]), C.c_int64(n), ptr_table(list(cols) + [None] * (5 - len(cols))), ptr(out), ptr(out2),
+                ptr(counter), stream_handle(dev))
+    _abi.check(st, "cumicro_icenuc_rates")
+    if check_domain:
+        nerr = int(counter.item())
+        if nerr:
+            raise DomainError(f"{what}: {nerr} of {n} points fail the reference's @assert (outputs are NaN there)")
+    return (out, out2) if two else out
+
+
+def MohlerDepositionRate(dust, ip, tps, Si, T, dSi_dt, N_aer, check_domain=True):
+    """IN.MohlerDepositionRate(dust, ip, Si, T, dSi_dt, N_aer) (IN:68-77); ``@assert Si < ip.Sᵢ_max`` -> DomainError."""
+    return _rates("MohlerDepositionRate", CMP.pack_icenuc(tps, dust=dust, mohler=ip), [Si, T, dSi_dt, N_aer], check_domain=check_domain)
+
+
+def P3_het_N_i(ip, tps, T, N_l, V_l, Δt):
+    """IN.P3_het_N_i(ip, T, Nₗ, Vₗ, Δt) (IN:202-205)."""
+    return _rates("P3_het_N_i", CMP.pack_icenuc(tps, mm2014=ip), [T, N_l, V_l, Δt])
+
+
+def INP_concentration_frequency(frostenberg, tps, INPC, T):
+    """IN.INP_concentration_frequency(params, INPC, T) (IN:219-224)."""
+    return _rates("INP_concentration_frequency", CMP.pack_icenuc(tps, frostenberg=frostenberg), [INPC, T])
+
+
+def het_ice_nucleation(aerosol, tps, q_lcl, N_lcl, RH, T, ρₐ):
+    """P3.het_ice_nucleation(aerosol, tps, q_lcl, N_lcl, RH, T, ρₐ) (P3_processes.jl:20-45) -> (dNdt, dLdt)."""
+    return _rates("het_ice_nucleation", CMP.pack_icenuc(tps, dust=aerosol), [q_lcl, N_lcl, RH, T, ρₐ], two=True)

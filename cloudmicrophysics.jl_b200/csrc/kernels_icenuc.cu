@@ -78,6 +78,50 @@ struct IceNucLeaf : IceNucBase {
     }
 };
 
+// multi-argument nucleation rates: (in[0..4]) -> (out, out2);  `what` as in include/cumicro.h (cumicro_icenuc_rates_*)
+struct IceNucRates : IceNucBase {
+    int what;
+    __device__ __forceinline__ void operator()(const D (&x)[5], D (&y)[2]) const {
+        const D nan = __longlong_as_double(0x7ff8000000000000LL);
+        D v = 0, v2 = 0;
+        bool err = false;
+        switch (what) {
+            case 0: {                                                            // IN.MohlerDepositionRate(Si, T, dSi_dt, N_aer)
+                err = !(x[0] < p.mohler.Si_max);
+                const D a = (x[1] > p.mohler.T_thr) ? p.dust.a_warm : p.dust.a_cold;
+                v = fmax_(0.0, x[3] * a * x[2]);
+                break;
+            }
+            case 1: {                                                            // IN.P3_het_N_i(T, N_l, V_l, dt)
+                const auto& ip = p.mm2014;
+                v = x[1] * (1.0 - exp_full_(-ip.het_B * x[2] * x[3] * exp_full_(ip.het_a * (ip.T0 - x[0]))));
+                break;
+            }
+            case 2: {                                                            // IN.INP_concentration_frequency(INPC, T)
+                const auto& f = p.frostenberg;
+                const D Tc = fmin_(x[1] - f.T_freeze, 0.0);
+                const D mu = 9.0 * log_full_(-f.b * Tc / 10.0) - f.log_a;
+                const D s2 = f.sigma * f.sigma, d = log_full_(x[0]) - mu;
+                v = (x[1] >= f.T_freeze) ? 0.0 : exp_full_(-(d * d) / (2.0 * s2)) / sqrt_(3.141592653589793 * 2.0 * s2);
+                break;
+            }
+            case 3: {                                                            // P3.het_ice_nucleation(q_lcl, N_lcl, RH, T, rho)
+                const TempState<D> ts = temp_state(tk, x[3]);
+                const D a_w_ice = p_sat_ice(tk, ts) / p_sat_liq(tk, ts);
+                const D J = ABIFM_J<D>(p.dust, x[2] - a_w_ice, k.ln10);
+                const D JA = isfinite(J) ? J * 1e-10 : 0.0;
+                v = fmax_(0.0, JA * x[1]);
+                v2 = fmax_(0.0, JA * x[0] * x[4]);
+                break;
+            }
+            default: break;
+        }
+        if (err) { v = nan; flag(); }
+        y[0] = v;
+        y[1] = v2;
+    }
+};
+
 // ARG2000 + nucleation rates, MODES aerosol modes:
 //   in : T, p, w, q_tot, q_liq, q_ice, N_liq, N_ice
 //   out: S_max, N_act[MODES], M_act[MODES], J_dep, J_ABIFM, J_hom, Δa_w   (NULL columns skipped)
@@ -127,6 +171,23 @@ int icenuc_leaf_impl(const typename PI<FT>::params* p, int what, int64_t n, cons
     IceNucLeaf f = make_icenuc<FT, IceNucLeaf>(p, n_domain_errors);
     f.what = what;
     return launch_pointwise<FT, 2, 1, IceNucLeaf, 256, 2>(f, n, in, o, (cudaStream_t)stream, "icenuc leaf launch");
+}
+
+template <class FT>
+int icenuc_rates_impl(const typename PI<FT>::params* p, int what, int64_t n, const FT* const* in5, FT* out, FT* out2,
+                      unsigned long long* n_domain_errors, void* stream) {
+    static const int nin[4] = {4, 4, 2, 5};
+    if (what < 0 || what > 3) return cmh::fail(CUMICRO_E_OPTION, "icenuc_rates: what = %d (expected 0..3)", what);
+    if (in5 == nullptr) return cmh::fail(CUMICRO_E_NULL, "icenuc_rates: column pointer table is NULL");
+    const FT* in[5];
+    for (int c = 0; c < 5; ++c) in[c] = (c < nin[what]) ? in5[c] : in5[0];
+    FT* o[2] = {out, out2};
+    int st = validate_columns<FT, 5>(p, n, in);
+    if (st) return st;
+    if ((st = require_outputs<FT, 2>(n, o, 1))) return st;
+    IceNucRates f = make_icenuc<FT, IceNucRates>(p, n_domain_errors);
+    f.what = what;
+    return launch_pointwise<FT, 5, 2, IceNucRates, 256, 2>(f, n, in, o, (cudaStream_t)stream, "icenuc rates launch");
 }
 
 template <class FT, int MODES>
@@ -188,5 +249,14 @@ extern "C" {
     }
 CUMICRO_DEF_ICENUC(f64, double)
 CUMICRO_DEF_ICENUC(f32, float)
+
+int cumicro_icenuc_rates_f64(const cumicro_params_icenuc_f64* p, int what, int64_t n, const double* const* in5, double* out,
+                             double* out2, unsigned long long* n_domain_errors, void* stream) {
+    return icenuc_rates_impl<double>(p, what, n, in5, out, out2, n_domain_errors, stream);
+}
+int cumicro_icenuc_rates_f32(const cumicro_params_icenuc_f32* p, int what, int64_t n, const float* const* in5, float* out,
+                             float* out2, unsigned long long* n_domain_errors, void* stream) {
+    return icenuc_rates_impl<float>(p, what, n, in5, out, out2, n_domain_errors, stream);
+}
 
 }  // extern "C"

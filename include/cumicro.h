@@ -273,6 +273,18 @@ int cumicro_icenuc_f64(const cumicro_params_icenuc_f64* p, int what, int64_t n, 
 int cumicro_icenuc_f32(const cumicro_params_icenuc_f32* p, int what, int64_t n, const float* x, const float* y,
                        float* out, unsigned long long* n_domain_errors, void* stream);
 
+/* Multi-argument nucleation rates: out[i] (, out2[i]) = fn(in5[0][i], ...); in5 = HOST array of device columns.
+ *  what 0: IN.MohlerDepositionRate(dust, mohler, Si, T, dSi_dt, N_aer)                 IN:68-77   (4 columns)
+ *          @assert Si < Sᵢ_max -> NaN + n_domain_errors
+ *       1: IN.P3_het_N_i(mm2014, T, N_l, V_l, Δt)                                      IN:202-205 (4 columns)
+ *       2: IN.INP_concentration_frequency(frostenberg, INPC, T)                        IN:219-224 (2 columns)
+ *       3: P3.het_ice_nucleation(dust, tps, q_lcl, N_lcl, RH, T, ρₐ) -> out = dNdt, out2 = dLdt   P3_processes.jl:20-45 (5 columns)
+ * out2 may be NULL. */
+int cumicro_icenuc_rates_f64(const cumicro_params_icenuc_f64* p, int what, int64_t n, const double* const* in5, double* out,
+                             double* out2, unsigned long long* n_domain_errors, void* stream);
+int cumicro_icenuc_rates_f32(const cumicro_params_icenuc_f32* p, int what, int64_t n, const float* const* in5, float* out,
+                             float* out2, unsigned long long* n_domain_errors, void* stream);
+
 /* ARG2000 aerosol activation fused with the nucleation rates (BASELINE config 3).
  * Replaces AA.max_supersaturation (AA:138-214), AA.N_activated_per_mode (AA:235-273),
  * AA.M_activated_per_mode (AA:294-338) and IN.deposition_J / ABIFM_J / homogeneous_J_cubic

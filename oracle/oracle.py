@@ -313,3 +313,20 @@ def bmt0m(params, q_lcl, q_icl, q_vap_sat=None):
                                                       _ptr(cols[2]) if len(cols) == 3 else None, _ptr(out))
     assert st == 0
     return out
+
+
+ICENUC_RATES = {"MohlerDepositionRate": (0, 4), "P3_het_N_i": (1, 4), "INP_concentration_frequency": (2, 2), "het_ice_nucleation": (3, 5)}
+
+
+def icenuc_rates(params, what, *cols):
+    """Multi-argument nucleation rates (same numbering as cumicro_icenuc_rates_*). Returns (out, out2, n_domain_errors)."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    code, nin = ICENUC_RATES[what]
+    assert len(cols) == nin
+    cols, n = _cols(cols, dtype)
+    tbl = (C.c_void_p * 5)(*([_ptr(c) for c in cols] + [None] * (5 - nin)))
+    out, out2 = np.empty(n, dtype), np.empty(n, dtype)
+    fn = getattr(lib(), f"oracle_icenuc_rates_{_suf(dtype)}")
+    fn.restype = C.c_int64
+    nerr = fn(C.byref(params), C.c_int(code), C.c_int64(n), tbl, _ptr(out), _ptr(out2))
+    return out, out2, int(nerr)

@@ -391,6 +391,40 @@ int oracle_bmt2m_p3_f64(const cumicro_params_p3_f64* p, int64_t n, const double*
 }
 
 
+// ---- multi-argument ice-nucleation rates: out[i] (and out2[i]) = fn(in[0][i], ...)
+//   what 0: IN.MohlerDepositionRate(dust, mohler, Si, T, dSi_dt, N_aer)             IN:68-77
+//        1: IN.P3_het_N_i(mm2014, T, N_l, V_l, dt)                                  IN:202-205
+//        2: IN.INP_concentration_frequency(frostenberg, INPC, T)                    IN:219-224
+//        3: P3.het_ice_nucleation(dust, tps, q_lcl, N_lcl, RH, T, rho) -> dNdt, dLdt   P3_processes.jl:20-45
+}  // extern "C"
+template <class FT, class PB>
+static int64_t icenuc_rates_cols(const PB* p, int what, int64_t n, const FT* const* in, FT* out, FT* out2) {
+    int64_t nerr = 0;
+    Thermo<FT> tps(p->tps);
+    for (int64_t i = 0; i < n; ++i) {
+        bool err = false;
+        FT v = FT(0), v2 = FT(0);
+        switch (what) {
+            case 0: v = MohlerDepositionRate<FT>(p->dust, p->mohler, in[0][i], in[1][i], in[2][i], in[3][i], err); break;
+            case 1: v = P3_het_N_i<FT>(p->mm2014, in[0][i], in[1][i], in[2][i], in[3][i]); break;
+            case 2: v = INP_concentration_frequency<FT>(p->frostenberg, in[0][i], in[1][i]); break;
+            case 3: p3_het_ice_nucleation<FT>(p->dust, tps, in[0][i], in[1][i], in[2][i], in[3][i], in[4][i], v, v2); break;
+            default: break;
+        }
+        if (err) { v = std::numeric_limits<FT>::quiet_NaN(); nerr += 1; }
+        if (out) out[i] = v;
+        if (out2) out2[i] = v2;
+    }
+    return nerr;
+}
+extern "C" {
+int64_t oracle_icenuc_rates_f64(const cumicro_params_icenuc_f64* p, int what, int64_t n, const double* const* in, double* out, double* out2) {
+    return icenuc_rates_cols<double>(p, what, n, in, out, out2);
+}
+int64_t oracle_icenuc_rates_f32(const cumicro_params_icenuc_f32* p, int what, int64_t n, const float* const* in, float* out, float* out2) {
+    return icenuc_rates_cols<float>(p, what, n, in, out, out2);
+}
+
 // ---- 0-moment scheme: BMT:658-680 -> CM0.remove_precipitation (src/Microphysics0M.jl:35-46), native FT arithmetic
 }  // extern "C"
 template <class FT, class PB> static void bmt0m_cols(const PB* p, int64_t n, const FT* q_lcl, const FT* q_icl, const FT* q_vap_sat, FT* out) {

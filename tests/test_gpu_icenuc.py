@@ -135,3 +135,57 @@ def test_config3_f32_2pow20(built, orc, cuda):
     for i in range(3):
         assert_f32_method(f"N_act[{i}]", got["N_act"][i].cpu().numpy()[:m], ref32["N_act"][i], truth["N_act"][i],
                           np.maximum(bound["N_act"][i], 1e-9 * blk64.modes[i].N))
+
+
+def test_multi_argument_rates_parity(built, orc, cuda):
+    """cumicro_icenuc_rates_* vs the oracle: Float64 1e-12, Float32 <= 4 ULP of the true value, domain errors counted."""
+    import torch
+    from cumicro.testing import assert_parity, assert_f32_method
+    CMP, IN = built.CMP, built.IN
+    rng = np.random.default_rng(8)
+    n = 20000
+    T = rng.uniform(200.0, 280.0, n)
+    for FT in (np.float64, np.float32):
+        tps = CMP.ThermodynamicsParameters(FT)
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=FT)).to(cuda)
+        c = lambda a: np.ascontiguousarray(a, dtype=FT)
+        dust, moh = CMP.DustType("ArizonaTestDust", FT), CMP.Mohler2006(FT)
+        cases = {
+            "MohlerDepositionRate": ([rng.uniform(1.0, 1.34, n), T, rng.uniform(-0.01, 0.05, n), rng.uniform(0, 5000, n)],
+                                     lambda a: IN.MohlerDepositionRate(dust, moh, tps, *a), CMP.pack_icenuc(tps, dust=dust, mohler=moh)),
+            "P3_het_N_i": ([T, 10 ** rng.uniform(2, 8, n), 10 ** rng.uniform(-18, -12, n), rng.uniform(0.1, 100, n)],
+                           lambda a: IN.P3_het_N_i(CMP.MorrisonMilbrandt2014(FT), tps, *a), CMP.pack_icenuc(tps)),
+            "INP_concentration_frequency": ([10 ** rng.uniform(0, 7, n), T],
+                                            lambda a: IN.INP_concentration_frequency(CMP.FrostenbergParameters(FT), tps, *a), CMP.pack_icenuc(tps)),
+        }
+        for name, (cols, fn, blk) in cases.items():
+            cols = [c(a) for a in cols]
+            got = fn([d(a) for a in cols]).cpu().numpy()
+            # P3_het_N_i = N_l (1 - exp(-x)) subtracts nearly equal numbers for small x (the reference's own Float32 literal
+            # has lost 13 % there, test/gpu_tests.jl:1024-1031): its first-order rounding bound is N_l * ulp(1)
+            bound = cols[1].astype(np.float64) * 2.0 ** -52 if name == "P3_het_N_i" else None
+            if FT is np.float64:
+                assert_parity(name, got, orc.icenuc_rates(blk, name, *cols)[0], bound=bound)
+            else:
+                truth = orc.icenuc_rates(CMP.widen(blk), name, *[a.astype(np.float64) for a in cols])[0]
+                assert_f32_method(name, got, truth.astype(FT), truth, bound)
+        ill = CMP.DustType("Illite", FT)
+        cols = [c(rng.uniform(0, 1e-3, n)), c(10 ** rng.uniform(6, 9, n)), c(rng.uniform(0.8, 1.15, n)), c(T), c(rng.uniform(0.3, 1.3, n))]
+        dN, dL = IN.het_ice_nucleation(ill, tps, *[d(a) for a in cols])
+        blk = CMP.pack_icenuc(tps, dust=ill)
+        if FT is np.float64:
+            rN, rL, _ = orc.icenuc_rates(blk, "het_ice_nucleation", *cols)
+            assert_parity("het dNdt", dN.cpu().numpy(), rN)
+            assert_parity("het dLdt", dL.cpu().numpy(), rL)
+        else:
+            tN, tL, _ = orc.icenuc_rates(CMP.widen(blk), "het_ice_nucleation", *[a.astype(np.float64) for a in cols])
+            big = tN < 3e38                                        # Float32 overflow of J -> the isfinite guard (P3_processes.jl:36-42) differs by type
+            assert_f32_method("het dNdt f32", dN.cpu().numpy()[big], tN[big].astype(FT), tN[big])
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    bad = torch.tensor([1.2, 1.36], dtype=torch.float64, device=cuda)
+    two = lambda v: torch.full((2,), v, dtype=torch.float64, device=cuda)
+    with pytest.raises(IN.DomainError):
+        IN.MohlerDepositionRate(CMP.DustType("DesertDust"), CMP.Mohler2006(np.float64), tps, bad, two(240.0), two(0.03), two(3000.0))
+    g = G["mohler_rate"]
+    got = IN.MohlerDepositionRate(CMP.DustType("DesertDust"), CMP.Mohler2006(np.float64), tps, two(g["Si"]), two(g["T"]), two(g["dSi_dt"]), two(g["N_aer"]))
+    assert abs(float(got[0]) / g["DesertDust"] - 1) < 1e-9

@@ -141,3 +141,37 @@ def test_kappa_and_B_descriptions_agree(built, orc):
     K = AM.AerosolDistribution((AM.Mode_κ(0.05e-6, 2.0, 1e8, (1.0,), (1.0,), (0.132,), (float(hB),)),))
     assert abs(AA.mean_hygroscopicity_parameter(ap, K)[0] / hB - 1) < 1e-15
     assert abs(hB / (3.0 * 1.0 * 1.0 / 0.132 * 1770.0 * 0.01801528 / 1000.0) - 1) < 1e-12
+
+
+def test_multi_argument_rates_goldens(built, orc):
+    """MohlerDepositionRate, P3_het_N_i, INP_concentration_frequency, P3.het_ice_nucleation on the reference's literals."""
+    CMP = built.CMP
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    g = G["mohler_rate"]
+    for name in ("DesertDust", "ArizonaTestDust"):
+        blk = CMP.pack_icenuc(tps, dust=CMP.DustType(name))
+        out, _, nerr = orc.icenuc_rates(blk, "MohlerDepositionRate", one(g["Si"]), one(g["T"]), one(g["dSi_dt"]), one(g["N_aer"]))
+        assert nerr == 0 and abs(out[0] / g[name] - 1) < 1e-9
+    out, _, nerr = orc.icenuc_rates(CMP.pack_icenuc(tps, dust=CMP.DustType("DesertDust")), "MohlerDepositionRate", one(1.4), one(240.0), one(0.03), one(3000.0))
+    assert nerr == 1 and np.isnan(out[0])                      # @assert Si < Sᵢ_max  (IN:73)
+    g = G["P3_het_N_i"]
+    out, _, _ = orc.icenuc_rates(CMP.pack_icenuc(tps), "P3_het_N_i", one(g["T"]), one(g["N_l"]), one(g["V_l"]), one(g["dt"]))
+    assert abs(out[0] / g["value"] - 1) < 1e-12
+    out, _, _ = orc.icenuc_rates(CMP.pack_icenuc(tps), "INP_concentration_frequency", one(220000.0), one(233.0))
+    assert abs(out[0] / 0.26 - 1) < 0.1                        # test/gpu_tests.jl:1050 (rtol 0.1; pins sigma loosely)
+    assert orc.icenuc_rates(CMP.pack_icenuc(tps), "INP_concentration_frequency", one(220000.0), one(274.0))[0][0] == 0.0
+    # P3.het_ice_nucleation sweep (test/p3_tests.jl:573-614)
+    g = G["p3_het_freezing"]
+    d = CMP.DEFAULTS
+    Rd, Rv = d["gas_constant_dry_air"], d["gas_constant_vapor"]
+    from cumicro.testing import psat_liq
+    blk = CMP.pack_icenuc(tps, dust=CMP.DustType(g["aerosol"]))
+    for qv, rN, rL in zip(g["qv"], g["dNdt"], g["dLdt"]):
+        eps_ = Rd / Rv
+        e_v = g["p"] * qv / (eps_ + qv * (1 - eps_))
+        RH = e_v / psat_liq(g["T"])
+        q_tot = qv + g["q_lcl"]
+        R_m = Rd * (1 + (Rv / Rd - 1) * q_tot - Rv / Rd * g["q_lcl"])
+        rho = g["p"] / (R_m * g["T"])
+        dN, dL, _ = orc.icenuc_rates(blk, "het_ice_nucleation", one(g["q_lcl"]), one(g["N_lcl"]), one(RH), one(g["T"]), one(rho))
+        assert abs(dN[0] / rN - 1) < g["rtol"] and abs(dL[0] / rL - 1) < g["rtol"], (qv, dN[0], rN, dL[0], rL)
