@@ -131,3 +131,24 @@ def INP_concentration_frequency(frostenberg, tps, INPC, T):
 def het_ice_nucleation(aerosol, tps, q_lcl, N_lcl, RH, T, ρₐ):
     """P3.het_ice_nucleation(aerosol, tps, q_lcl, N_lcl, RH, T, ρₐ) (P3_processes.jl:20-45) -> (dNdt, dLdt)."""
     return _rates("het_ice_nucleation", CMP.pack_icenuc(tps, dust=aerosol), [q_lcl, N_lcl, RH, T, ρₐ], two=True)
+
+
+F23_OUT = ("rain_dn_frz", "rain_dq_frz", "cloud_dn_frz", "cloud_dq_frz", "immersion_limit_dn", "deposition_dn", "deposition_dq")
+
+
+def f23_and_bigg_rates(mp, tps, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, inpc_log_shift=None):
+    """``IN.liquid_freezing_rate`` (rain and cloud PSD, IN:274-388), ``IN.immersion_limit_rate`` (IN:420-430) and
+    ``IN.deposition_rate`` (IN:491-511) over columns, with the arguments BMT:998-1075 passes (``mp`` built ``with_ice=True``)."""
+    from . import parameters_p3 as CMP3
+    from ._columns import Tendencies, ptr_table
+    cols = [rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice]
+    suf, n, dev = check_columns(cols + ([inpc_log_shift] if inpc_log_shift is not None else []), ["col"] * 10)
+    blk = CMP3.pack_p3(mp, tps)
+    if not type(blk).__name__.endswith(suf):
+        raise TypeError(f"parameter float type does not match the columns ({suf})")
+    outs = [torch.empty_like(rho) for _ in F23_OUT]
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_icenuc_f23_{suf}")(C.byref(blk), C.c_int64(n), ptr_table(cols), ptr(inpc_log_shift), ptr_table(outs),
+                                                              stream_handle(dev))
+    _abi.check(st, "cumicro_icenuc_f23")
+    return Tendencies(zip(F23_OUT, outs))

@@ -47,6 +47,54 @@ struct Pt {   // one grid point, clamped (BMT:911-930)
     double L_lcl, N_lcl, L_rai, N_rai, L_ice, N_ice, L_rim, B_rim;
 };
 
+// IN.liquid_freezing_rate (rain: IN:274-311, cloud PSD: IN:356-388), IN.immersion_limit_rate (IN:420-430) and
+// IN.deposition_rate (IN:491-511) with n_active = n_ice (IN:526), as BMT:998-1075 calls them.
+struct F23Rates { double rain_dn, rain_dq, cld_dn, cld_dq, cap_dn, dep_dn, dep_dq; };
+CM_DEV F23Rates f23_rates(const cumicro_params_p3_f64& p, const ThermoK<double>& tk, const SB2006K<double>& sk, const P3K& k, const Pt& x) {
+    F23Rates o;
+    const double e = tk.eps;
+    const double rho = x.rho, T = x.T;
+    const TempState<double> ts = temp_state(tk, T);
+    const double q_sat_ice = p_sat_ice(tk, ts) / (tk.R_v * rho * T);
+    const double q_liq = x.q_lcl + x.q_rai;
+    const double qv = q_vap(x.q_tot, q_liq, x.q_ice);
+    const double inpc = exp_full_(inp_log_mean(k, T) + x.shift) / rho;
+    {
+        const double S_i = qv / q_sat_ice - 1.0;
+        const bool cond = (T < k.frost_T_freeze - 15.0) && (S_i > 0.05);
+        const double a = fmax_(0.0, inpc - x.n_ice) / k.tau_act;
+        o.dep_dn = cond ? a : 0.0;
+        const double q_excess = fmax_(0.0, qv - q_sat_ice);
+        o.dep_dq = fmin_(k.m_nuc * o.dep_dn, q_excess / (2.0 * k.tau_act));
+    }
+    const double J_bigg = k.het_B * exp_full_(k.het_a * (tk.T_freeze - T));
+    {
+        const auto& pc = p.warm.sb.pdf_c;
+        const double n = x.N_lcl / rho;
+        const bool off = (x.N_lcl < e) || (x.q_lcl < e);
+        const double safe_q = fmax_(x.q_lcl, e), safe_N = fmax_(x.N_lcl, e);
+        const double logx = log_full_(rho * safe_q / safe_N);
+        const double lB = -pc.mu_c * (logx + pc.loggamma_z1 - pc.loggamma_z2);
+        const double loglam_c = off ? num<double>::inf() : lB + pc.mu_c * k.log_km;
+        const double M3 = n * exp_full_(-3.0 / k.mu_cD * loglam_c) * k.cloud_M3_ratio;
+        const double M6 = n * exp_full_(-6.0 / k.mu_cD * loglam_c) * k.cloud_M6_ratio;
+        const bool cond = (n > e) && (x.q_lcl > e) && (T < tk.T_freeze - 4.0);
+        o.cld_dn = cond ? J_bigg * k.V1 * M3 : 0.0;
+        o.cld_dq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
+        o.cap_dn = (T >= k.frost_T_freeze) ? 0.0 : fmax_(0.0, inpc - x.n_ice) / k.tau_act;
+    }
+    {
+        const double n = x.N_rai / rho;
+        const RainPDF<double> rp = pdf_rain_parameters<double>(p.warm.sb.pdf_r, sk.pi_rho_w, e, x.q_rai, rho, x.N_rai);
+        const double Dr = rp.Dr_mean, D3 = Dr * Dr * Dr;
+        const double M3 = n * 6.0 * D3, M6 = n * 720.0 * (D3 * D3);
+        const bool cond = (n > e) && (x.q_rai > e) && (T < tk.T_freeze - 4.0);
+        o.rain_dn = cond ? J_bigg * k.V1 * M3 : 0.0;
+        o.rain_dq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
+    }
+    return o;
+}
+
 CM_DEV void bmt2m_p3_assemble(const cumicro_params_p3_f64& p, const ThermoK<double>& tk, const SB2006K<double>& sk, const P3K& k,
                               const Pt& x, bool ice_on, const P3Rates& r, double F_rim, double rho_rim, double (&y)[9]) {
     const double e = tk.eps;
@@ -71,40 +119,17 @@ CM_DEV void bmt2m_p3_assemble(const cumicro_params_p3_f64& p, const ThermoK<doub
         dq_rim -= dq_m * F_rim;
         db_rim -= (rho_rim > 0.0) ? dq_m * F_rim / rho_rim : 0.0;
     }
-    // ---- F23 deposition nucleation                                                BMT:998-1015, IN:491-511
+    // ---- F23 deposition nucleation, Bigg freezing of cloud drops capped by F23    BMT:998-1036
+    const F23Rates f = f23_rates(p, tk, sk, k, x);
     const TempState<double> ts = temp_state(tk, T);
     const double q_sat_ice = p_sat_ice(tk, ts) / (tk.R_v * rho * T);
     const double q_liq = x.q_lcl + x.q_rai;
     const double qv = q_vap(x.q_tot, q_liq, x.q_ice);
-    const double inpc = exp_full_(inp_log_mean(k, T) + x.shift) / rho;
+    dn_ice += f.dep_dn;
+    dq_ice += f.dep_dq;
     {
-        const double S_i = qv / q_sat_ice - 1.0;
-        const bool cond = (T < k.frost_T_freeze - 15.0) && (S_i > 0.05);
-        const double a = fmax_(0.0, inpc - x.n_ice) / k.tau_act;
-        const double dn = cond ? a : 0.0;
-        const double q_excess = fmax_(0.0, qv - q_sat_ice);
-        const double dq = fmin_(k.m_nuc * dn, q_excess / (2.0 * k.tau_act));
-        dn_ice += dn;
-        dq_ice += dq;
-    }
-    // ---- Bigg immersion freezing of cloud drops, capped by F23                    BMT:1017-1036, IN:356-430
-    const double J_bigg = k.het_B * exp_full_(k.het_a * (tk.T_freeze - T));
-    {
-        const auto& pc = p.warm.sb.pdf_c;
-        const double n = x.N_lcl / rho;
-        const bool off = (x.N_lcl < e) || (x.q_lcl < e);
-        const double safe_q = fmax_(x.q_lcl, e), safe_N = fmax_(x.N_lcl, e);
-        const double logx = log_full_(rho * safe_q / safe_N);
-        const double lB = -pc.mu_c * (logx + pc.loggamma_z1 - pc.loggamma_z2);
-        const double loglam_c = off ? num<double>::inf() : lB + pc.mu_c * k.log_km;
-        const double M3 = n * exp_full_(-3.0 / k.mu_cD * loglam_c) * k.cloud_M3_ratio;
-        const double M6 = n * exp_full_(-6.0 / k.mu_cD * loglam_c) * k.cloud_M6_ratio;
-        const bool cond = (n > e) && (x.q_lcl > e) && (T < tk.T_freeze - 4.0);
-        const double bn = cond ? J_bigg * k.V1 * M3 : 0.0;
-        const double bq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
-        const double cap = (T >= k.frost_T_freeze) ? 0.0 : fmax_(0.0, inpc - x.n_ice) / k.tau_act;
-        const double dn_imm = fmin_(bn, cap);
-        const double dq_imm = (bn > 0.0) ? bq * dn_imm / bn : 0.0;
+        const double dn_imm = fmin_(f.cld_dn, f.cap_dn);
+        const double dq_imm = (f.cld_dn > 0.0) ? f.cld_dq * dn_imm / f.cld_dn : 0.0;
         dq_lcl -= dq_imm;
         dn_lcl -= dn_imm;
         dq_ice += dq_imm;
@@ -133,15 +158,9 @@ CM_DEV void bmt2m_p3_assemble(const cumicro_params_p3_f64& p, const ThermoK<doub
     }
     // ---- ice number adjustment (τ = 100, x in [1e-12, 1e-5])                       BMT:1056-1064
     dn_ice += number_tendency_from_mass_limits<double>(e, 1.0 / 1e-12, 1.0 / 1e-5, 1.0 / 100.0, x.q_ice, x.n_ice);
-    // ---- rain Bigg freezing                                                        BMT:1066-1075, IN:274-311
+    // ---- rain Bigg freezing                                                        BMT:1066-1075
     {
-        const double n = x.N_rai / rho;
-        const RainPDF<double> rp = pdf_rain_parameters<double>(p.warm.sb.pdf_r, sk.pi_rho_w, e, x.q_rai, rho, x.N_rai);
-        const double Dr = rp.Dr_mean, D3 = Dr * Dr * Dr;
-        const double M3 = n * 6.0 * D3, M6 = n * 720.0 * (D3 * D3);
-        const bool cond = (n > e) && (x.q_rai > e) && (T < tk.T_freeze - 4.0);
-        const double rn = cond ? J_bigg * k.V1 * M3 : 0.0;
-        const double rq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
+        const double rn = f.rain_dn, rq = f.rain_dq;
         dq_rai -= rq;
         dn_rai -= rn;
         dq_ice += rq;
@@ -287,6 +306,56 @@ int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, i
     return cmh::cuda_status(cudaGetLastError(), what);
 }
 
+// ---- the F23 / Bigg nucleation rates on their own: one point per thread --------------------------------------
+template <bool WITH_SHIFT> struct F23Functor {
+    cumicro_params_p3_f64 p;
+    ThermoK<double> tk;
+    SB2006K<double> sk;
+    P3K k;
+    __device__ __forceinline__ void operator()(const double (&v)[WITH_SHIFT ? 10 : 9], double (&y)[7]) const {
+        Pt x{};
+        x.rho = fmax_(0.0, v[0]); x.T = v[1]; x.q_tot = fmax_(0.0, v[2]); x.q_lcl = fmax_(0.0, v[3]); x.n_lcl = fmax_(0.0, v[4]);
+        x.q_rai = fmax_(0.0, v[5]); x.n_rai = fmax_(0.0, v[6]); x.q_ice = fmax_(0.0, v[7]); x.n_ice = fmax_(0.0, v[8]); x.shift = WITH_SHIFT ? v[WITH_SHIFT ? 9 : 0] : 0.0;
+        x.N_lcl = x.n_lcl * x.rho; x.N_rai = x.n_rai * x.rho;
+        const F23Rates f = f23_rates(p, tk, sk, k, x);
+        y[0] = f.rain_dn; y[1] = f.rain_dq; y[2] = f.cld_dn; y[3] = f.cld_dq; y[4] = f.cap_dn; y[5] = f.dep_dn; y[6] = f.dep_dq;
+    }
+};
+
+template <class FT>
+int icenuc_f23_impl(const typename PP3<FT>::type* p, int64_t n, const FT* const* in9, const FT* shift, FT* const* out7, void* stream) {
+    int st = p3_check<FT>(p);
+    if (st) return st;
+    if (!in9 || !out7) return cmh::fail(CUMICRO_E_NULL, "icenuc_f23: column pointer table is NULL");
+    if (n < 0) return cmh::fail(CUMICRO_E_SIZE, "n = %lld is negative", (long long)n);
+    if (n == 0) return CUMICRO_OK;
+    const FT* in[10];
+    for (int c = 0; c < 9; ++c) {
+        if (in9[c] == nullptr) return cmh::fail(CUMICRO_E_NULL, "icenuc_f23: input column %d is NULL", c);
+        in[c] = in9[c];
+    }
+    FT* out[7];
+    for (int c = 0; c < 7; ++c) out[c] = out7[c];
+    cudaStream_t s = (cudaStream_t)stream;
+    auto fill = [&](auto& f) {
+        widen(*p, f.p);
+        f.tk = make_thermo_k<double>(f.p.warm.tps, is_f32<FT>());
+        f.sk = make_sb2006_k<double>(f.p.warm.sb, f.p.warm.aps, is_f32<FT>());
+        f.k = make_p3_k(f.p, is_f32<FT>());
+    };
+    if (shift) {
+        in[9] = shift;
+        F23Functor<true> f{};
+        fill(f);
+        return launch_pointwise<FT, 10, 7, F23Functor<true>, 128, 4, false>(f, n, in, out, s, "icenuc_f23 launch");
+    }
+    const FT* in9c[9];
+    for (int c = 0; c < 9; ++c) in9c[c] = in[c];
+    F23Functor<false> f{};
+    fill(f);
+    return launch_pointwise<FT, 9, 7, F23Functor<false>, 128, 4, false>(f, n, in9c, out, s, "icenuc_f23 launch");
+}
+
 // ---- P3.get_distribution_logλ_from_prognostic: one point per thread ------------------------------
 struct P3LogLambda {
     cumicro_p3_scheme_f64 prm;
@@ -429,6 +498,15 @@ int cumicro_p3_logl_f64(const cumicro_params_p3_f64* p, int64_t n, const double*
 int cumicro_p3_logl_f32(const cumicro_params_p3_f32* p, int64_t n, const float* L_ice, const float* N_ice, const float* L_rim,
                         const float* B_rim, int brent_iters, float* logl, void* stream) {
     return p3_logl_impl<float>(p, n, L_ice, N_ice, L_rim, B_rim, brent_iters, logl, stream);
+}
+
+int cumicro_icenuc_f23_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in9, const double* inpc_log_shift,
+                           double* const* out7, void* stream) {
+    return icenuc_f23_impl<double>(p, n, in9, inpc_log_shift, out7, stream);
+}
+int cumicro_icenuc_f23_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in9, const float* inpc_log_shift,
+                           float* const* out7, void* stream) {
+    return icenuc_f23_impl<float>(p, n, in9, inpc_log_shift, out7, stream);
 }
 
 }  // extern "C"

@@ -382,6 +382,19 @@ int cumicro_bmt0m_f64(const cumicro_params_0m_f64* p, int64_t n, const double* q
 int cumicro_bmt0m_f32(const cumicro_params_0m_f32* p, int64_t n, const float* q_lcl, const float* q_icl,
                       const float* q_vap_sat, float* dq_tot_dt, void* stream);
 
+/* The Frostenberg-2023 / Bigg nucleation rates of the 2-moment + P3 method on their own (BMT:998-1075):
+ *   in9  = HOST array of 9 device columns: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice (specific, clamped >= 0)
+ *   inpc_log_shift: device column or NULL (= 0)
+ *   out7 = HOST array of 7 device columns (NULL entries skipped):
+ *     [0,1] IN.liquid_freezing_rate(rain_freezing, pdf_r, tps, q_rai, ρ, N_rai, T) -> ∂ₜn_frz, ∂ₜq_frz        IN:274-311
+ *     [2,3] IN.liquid_freezing_rate(rain_freezing, pdf_c, tps, q_lcl, ρ, N_lcl, T) -> ∂ₜn_frz, ∂ₜq_frz        IN:356-388
+ *     [4]   IN.immersion_limit_rate(frostenberg, T, ρ; τ = τ_act, inpc_log_shift, n_active = n_ice)         IN:420-430
+ *     [5,6] IN.deposition_rate(frostenberg, tps, T, ρ, q_tot, q_lcl + q_rai, q_ice, n_ice; m_nuc, τ_act, inpc_log_shift)   IN:491-511 */
+int cumicro_icenuc_f23_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in9, const double* inpc_log_shift,
+                           double* const* out7, void* stream);
+int cumicro_icenuc_f23_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in9, const float* inpc_log_shift,
+                           float* const* out7, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

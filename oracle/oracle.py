@@ -330,3 +330,18 @@ def icenuc_rates(params, what, *cols):
     fn.restype = C.c_int64
     nerr = fn(C.byref(params), C.c_int(code), C.c_int64(n), tbl, _ptr(out), _ptr(out2))
     return out, out2, int(nerr)
+
+
+F23_OUT = ("rain_dn_frz", "rain_dq_frz", "cloud_dn_frz", "cloud_dq_frz", "immersion_limit_dn", "deposition_dn", "deposition_dq")
+
+
+def icenuc_f23(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, inpc_log_shift=None, bound=False):
+    """The F23 / Bigg rates as BMT:998-1075 calls them (same layout as cumicro_icenuc_f23_*)."""
+    assert type(params).__name__.endswith("p3_f64")
+    cols, n = _cols((rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice), np.float64)
+    shift = None if inpc_log_shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(inpc_log_shift, np.float64), (n,)))
+    out = {k: np.empty(n, np.float64) for k in F23_OUT}
+    st = lib().oracle_icenuc_f23_f64(C.byref(params), C.c_int64(n), (C.c_void_p * 9)(*[_ptr(a) for a in cols]), _ptr(shift),
+                                     (C.c_void_p * 7)(*[_ptr(out[k]) for k in F23_OUT]), C.c_int(int(bound)))
+    assert st == 0
+    return out

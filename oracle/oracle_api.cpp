@@ -425,6 +425,30 @@ int64_t oracle_icenuc_rates_f32(const cumicro_params_icenuc_f32* p, int what, in
     return icenuc_rates_cols<float>(p, what, n, in, out, out2);
 }
 
+// ---- F23 / Bigg nucleation rates as BMT:998-1075 calls them: in9 = rho,T,q_tot,q_lcl,n_lcl,q_rai,n_rai,q_ice,n_ice (+ shift)
+}  // extern "C"
+template <class FT> static void icenuc_f23_cols(const cumicro_params_p3_f64* p, int64_t n, const double* const* in, const double* shift, double* const* out, bool bound) {
+    for (int64_t i = 0; i < n; ++i) {
+        FT rho = clamp_to_nonneg(FT(in[0][i])), T = FT(in[1][i]), q_tot = clamp_to_nonneg(FT(in[2][i])), q_lcl = clamp_to_nonneg(FT(in[3][i])),
+           n_lcl = clamp_to_nonneg(FT(in[4][i])), q_rai = clamp_to_nonneg(FT(in[5][i])), n_rai = clamp_to_nonneg(FT(in[6][i])),
+           q_ice = clamp_to_nonneg(FT(in[7][i])), n_ice = clamp_to_nonneg(FT(in[8][i]));
+        FT sh = shift ? FT(shift[i]) : FT(0);
+        FT v[7];
+        rain_freezing_rate<FT>(*p, q_rai, rho, FT(n_rai * rho), T, v[0], v[1]);
+        cloud_freezing_rate<FT>(*p, q_lcl, rho, FT(n_lcl * rho), T, v[2], v[3]);
+        v[4] = immersion_limit_rate<FT>(p->ice_nucleation, T, rho, FT(p->tau_act), sh, n_ice);
+        FT m_nuc = FT(p->scheme.rho_i) * volume_sphere_D<FT>(FT(10e-6));
+        f23_deposition_rate<FT>(*p, T, rho, q_tot, FT(q_lcl + q_rai), q_ice, n_ice, m_nuc, FT(p->tau_act), sh, v[5], v[6]);
+        for (int k = 0; k < 7; ++k)
+            if (out[k]) out[k][i] = bound ? Tr(v[k]).e : val_(v[k]);
+    }
+}
+extern "C" {
+int oracle_icenuc_f23_f64(const cumicro_params_p3_f64* p, int64_t n, const double* const* in9, const double* shift, double* const* out7, int bound) {
+    if (bound) icenuc_f23_cols<Tr>(p, n, in9, shift, out7, true); else icenuc_f23_cols<double>(p, n, in9, shift, out7, false);
+    return 0;
+}
+
 // ---- 0-moment scheme: BMT:658-680 -> CM0.remove_precipitation (src/Microphysics0M.jl:35-46), native FT arithmetic
 }  // extern "C"
 template <class FT, class PB> static void bmt0m_cols(const PB* p, int64_t n, const FT* q_lcl, const FT* q_icl, const FT* q_vap_sat, FT* out) {

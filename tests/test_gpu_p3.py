@@ -294,3 +294,24 @@ def test_p3_full_size_properties_2pow22(built, cuda):
     part = P3.process_rates(mp, tps, *[c[lo:hi].contiguous() for c in cols])
     for k in P3.RATE_NAMES:
         assert torch.equal(part[k], r[k][lo:hi]), k
+
+
+def test_f23_and_bigg_rates_standalone(built, orc, cuda):
+    """IN.liquid_freezing_rate (rain / cloud PSD), immersion_limit_rate, deposition_rate as BMT:998-1075 calls them."""
+    import torch
+    from cumicro.testing import assert_parity
+    IN, CMP3 = built.IN, built.CMP3
+    mp, tps, st = _setup(built, 6000, seed=31)
+    st["T"][::2] -= 30.0
+    blk = CMP3.pack_p3(mp, tps)
+    keys = ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice")
+    shift = np.random.default_rng(2).normal(0, 1.0, st["rho"].size)
+    d = [torch.from_numpy(st[k]).to(cuda) for k in keys]
+    for sh in (None, shift):
+        got = IN.f23_and_bigg_rates(mp, tps, *d, None if sh is None else torch.from_numpy(sh).to(cuda))
+        ref = orc.icenuc_f23(blk, *[st[k] for k in keys], inpc_log_shift=sh)
+        bnd = orc.icenuc_f23(blk, *[st[k] for k in keys], inpc_log_shift=sh, bound=True)
+        for k in IN.F23_OUT:
+            assert_parity(k, got[k].cpu().numpy(), ref[k], bound=bnd[k])
+        assert (ref["rain_dn_frz"] > 0).mean() > 0.2 and (ref["cloud_dq_frz"] > 0).mean() > 0.2 and (ref["deposition_dn"] > 0).mean() > 0.005
+        assert (ref["immersion_limit_dn"] == 0).mean() > 0.1           # T >= T_freeze (IN:425)
