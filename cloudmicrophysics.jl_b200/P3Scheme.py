@@ -94,3 +94,52 @@ def process_rates(mp, tps, ρ, T, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_ri
                                                             ptr_table([outs.get(k) for k in RATE_NAMES]), stream_handle(dev))
     _abi.check(st, "cumicro_p3_rates")
     return Tendencies(**outs)
+
+
+STATE_NAMES = ("F_rim", "ρ_rim", "ρ_g", "D_th", "D_gr", "D_cr", "D_m")
+_LEAF = {"gamma_inc_P": 0, "gamma_inc_Q": 1, "gamma_inc_inv": 2, "rime_mass_fraction": 3, "rime_density": 4}
+
+
+def state_from_prognostic(mp, tps, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ):
+    """``P3.state_from_prognostic`` thresholds (P3_particle_properties.jl:43-56, 101-106) and ``P3.D_m(state, logλ)``
+    (P3_integral_properties.jl:56-61) over columns -> Tendencies with STATE_NAMES."""
+    cols = [ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ]
+    suf, n, dev = check_columns(cols, ["ρq_ice", "ρn_ice", "ρq_rim", "ρb_rim", "logλ"])
+    blk = _block(mp, tps, suf, None)
+    outs = [torch.empty_like(ρq_ice) for _ in STATE_NAMES]
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_p3_state_{suf}")(C.byref(blk), C.c_int64(n), *[ptr(c) for c in cols], ptr_table(outs),
+                                                            stream_handle(dev))
+    _abi.check(st, "cumicro_p3_state")
+    return Tendencies(zip(STATE_NAMES, outs))
+
+
+def D_m(mp, tps, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ):
+    return state_from_prognostic(mp, tps, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ)["D_m"]
+
+
+def _leaf(what, x, y):
+    suf, n, dev = check_columns([x, y], ["x", "y"])
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_p3_leaf_{suf}")(C.c_int(_LEAF[what]), C.c_int64(n), ptr(x), ptr(y), ptr(out), stream_handle(dev))
+    _abi.check(st, "cumicro_p3_leaf")
+    return out
+
+
+def gamma_inc(a, x):
+    """``UT.gamma_inc(a, x)`` -> (P, Q) (UT:92-144)."""
+    return _leaf("gamma_inc_P", a, x), _leaf("gamma_inc_Q", a, x)
+
+
+def gamma_inc_inv(a, p):
+    """``UT.gamma_inc_inv(a, p, 1 - p)`` (UT:205-252)."""
+    return _leaf("gamma_inc_inv", a, p)
+
+
+def rime_mass_fraction(q_rim, q_ice):
+    return _leaf("rime_mass_fraction", q_rim, q_ice)
+
+
+def rime_density(q_rim, b_rim):
+    return _leaf("rime_density", q_rim, b_rim)

@@ -357,81 +357,121 @@ int icenuc_f23_impl(const typename PP3<FT>::type* p, int64_t n, const FT* const*
 }
 
 // ---- P3.get_distribution_logλ_from_prognostic: one point per thread ------------------------------
+// P3.state_from_prognostic + P3State thresholds                     P3_particle_properties.jl:43-56, 101-106, 191-272
+struct P3Thresholds { double F_rim, rho_rim, rho_g, D_gr, D_cr; };
+__device__ inline P3Thresholds p3_thresholds(const P3K& k, double L_ice, double L_rim, double B_rim) {
+    P3Thresholds t;
+    t.F_rim = fmin_(regularised_ratio_(fmin_(L_rim, L_ice), L_ice, k.eps), 1.0 - k.eps);
+    t.rho_rim = fmin_(regularised_ratio_(L_rim, B_rim, k.eps), k.rho_l08);
+    const double pp = k.thr_p;
+    const double logFu = log1p_(-t.F_rim);
+    auto exprel1 = [](double v) { return expm1_(v) / v; };
+    auto exprel2 = [](double v) {
+        if (fabs(v) < 0.2) {
+            double r = 1.0 / 362880.0;
+            const double c[7] = {1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 1.0 / 2.0};
+#pragma unroll
+            for (int i = 0; i < 7; ++i) r = r * v + c[i];
+            return r;
+        }
+        return (expm1_(v) - v) / (v * v);
+    };
+    const double phi1 = exprel1(logFu), phi1mp = exprel1((1.0 - pp) * logFu);
+    const double H = -pp * exprel2(-pp * logFu) - (1.0 - pp) * exprel2((1.0 - pp) * logFu);
+    const double rho_d = -(t.rho_rim * phi1 * phi1mp) / (H - phi1mp * phi1);
+    t.rho_g = t.F_rim * t.rho_rim + (1.0 - t.F_rim) * rho_d;
+    const bool unrimed = (t.F_rim == 0.0);
+    const double pi = num<double>::pi();
+    t.D_gr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * t.rho_g), pp);
+    t.D_cr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * (t.rho_g * (1.0 - t.F_rim))), pp);
+    return t;
+}
+// get_μ and logmass_gamma_moment(state, μ, logλ; n)                   P3_size_distribution.jl:171, 193-200
+__device__ inline double p3_logmass_moment(const P3K& k, const P3Thresholds& t, double logl, double n_mom, double& mu) {
+    const double lam = exp_full_(logl);
+    mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+    const double pi = num<double>::pi();
+    const double inf = num<double>::inf();
+    const double bnd[5] = {0.0, clamp_(k.D_th, 0.0, inf), clamp_(t.D_gr, 0.0, inf), clamp_(t.D_cr, 0.0, inf), inf};
+    const double Fu = fmax_(1.0 - t.F_rim, k.eps);
+    double m[4];
+#pragma unroll
+    for (int sgm = 0; sgm < 4; ++sgm) {
+        const double D1 = bnd[sgm], D2 = bnd[sgm + 1];
+        const double Dm = (D1 + D2) / 2.0;
+        const int r = (Dm < k.D_th) ? 0 : ((t.F_rim == 0.0) ? 1 : ((Dm < t.D_gr) ? 2 : ((Dm < t.D_cr) ? 3 : 4)));
+        const double a = (r == 0) ? k.rho_i * pi / 6.0 : ((r == 3) ? t.rho_g * pi / 6.0 : ((r == 4) ? k.alpha_va / Fu : k.alpha_va));
+        const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
+        if (!(D1 < D2)) { m[sgm] = -inf; continue; }
+        const double z = (b + n_mom) + mu + 1.0;
+        const double x1 = D1 * lam, x2 = D2 * lam;
+        const double lg = lgamma_pos_(z);
+        const PQ g1 = gamma_inc_(z, x1, lg, k.gamma_iters), g2 = gamma_inc_(z, x2, lg, k.gamma_iters);
+        double dq = (x2 < z + 1.0) ? g2.P - g1.P : g1.Q - g2.Q;
+        dq = fmax_(dq, k.eps);
+        m[sgm] = -z * logl + lg + log_full_(dq) + log_full_(a);
+    }
+    double mx = m[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) mx = fmax_(mx, m[i]);
+    if (!isfinite(mx)) return mx;
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum += exp_full_(m[i] - mx);
+    return mx + log_full_(sum);
+}
+
 struct P3LogLambda {
-    cumicro_p3_scheme_f64 prm;
     P3K k;
     int iters;   // Brent iterations (reference: 10 / 8)
-    // logLdivN(state, logλ) - target                                    P3_size_distribution.jl:193-216
-    __device__ double shape(double logl, double F_rim, double rho_g, double D_gr, double D_cr, double target) const {
-        const double lam = exp_full_(logl);
-        const double mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
-        const double pi = num<double>::pi();
-        const double inf = num<double>::inf();
-        const double bnd[5] = {0.0, clamp_(k.D_th, 0.0, inf), clamp_(D_gr, 0.0, inf), clamp_(D_cr, 0.0, inf), inf};
-        const double Fu = fmax_(1.0 - F_rim, k.eps);
-        double m[4];
-#pragma unroll
-        for (int sgm = 0; sgm < 4; ++sgm) {
-            const double D1 = bnd[sgm], D2 = bnd[sgm + 1];
-            const double Dm = (D1 + D2) / 2.0;
-            const int r = (Dm < k.D_th) ? 0 : ((F_rim == 0.0) ? 1 : ((Dm < D_gr) ? 2 : ((Dm < D_cr) ? 3 : 4)));
-            const double a = (r == 0) ? k.rho_i * pi / 6.0 : ((r == 3) ? rho_g * pi / 6.0 : ((r == 4) ? k.alpha_va / Fu : k.alpha_va));
-            const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
-            if (!(D1 < D2)) { m[sgm] = -inf; continue; }
-            const double z = (b + 0.0) + mu + 1.0;
-            const double x1 = D1 * lam, x2 = D2 * lam;
-            const double lg = lgamma_pos_(z);
-            const PQ g1 = gamma_inc_(z, x1, lg, k.gamma_iters), g2 = gamma_inc_(z, x2, lg, k.gamma_iters);
-            double dq = (x2 < z + 1.0) ? g2.P - g1.P : g1.Q - g2.Q;
-            dq = fmax_(dq, k.eps);
-            m[sgm] = -z * logl + lg + log_full_(dq) + log_full_(a);
-        }
-        double mx = m[0];
-#pragma unroll
-        for (int i = 1; i < 4; ++i) mx = fmax_(mx, m[i]);
-        double lse = mx;
-        if (isfinite(mx)) {
-            double sum = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sum += exp_full_(m[i] - mx);
-            lse = mx + log_full_(sum);
-        }
-        const double z0 = 0.0 + mu + 1.0;
-        return (lse - (-z0 * logl + lgamma_pos_(z0) + 0.0)) - target;
-    }
     __device__ __forceinline__ void operator()(const double (&x)[4], double (&y)[1]) const {
         const double L_ice = x[0], N_ice = x[1], L_rim = x[2], B_rim = x[3];
-        const double F_rim = fmin_(regularised_ratio_(fmin_(L_rim, L_ice), L_ice, k.eps), 1.0 - k.eps);
-        const double rho_rim = fmin_(regularised_ratio_(L_rim, B_rim, k.eps), k.rho_l08);
+        const P3Thresholds t = p3_thresholds(k, L_ice, L_rim, B_rim);
         if (N_ice < k.eps || L_ice < k.eps) { y[0] = -num<double>::inf(); return; }
-        // thresholds (as p3_point_init)
-        const double pp = k.thr_p;
-        const double logFu = log1p_(-F_rim);
-        auto exprel1 = [](double v) { return expm1_(v) / v; };
-        auto exprel2 = [](double v) {
-            if (fabs(v) < 0.2) {
-                double r = 1.0 / 362880.0;
-                const double c[7] = {1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 1.0 / 2.0};
-#pragma unroll
-                for (int i = 0; i < 7; ++i) r = r * v + c[i];
-                return r;
-            }
-            return (expm1_(v) - v) / (v * v);
-        };
-        const double phi1 = exprel1(logFu), phi1mp = exprel1((1.0 - pp) * logFu);
-        const double H = -pp * exprel2(-pp * logFu) - (1.0 - pp) * exprel2((1.0 - pp) * logFu);
-        const double rho_d = -(rho_rim * phi1 * phi1mp) / (H - phi1mp * phi1);
-        const double rho_g = F_rim * rho_rim + (1.0 - F_rim) * rho_d;
-        const bool unrimed = (F_rim == 0.0);
-        const double pi = num<double>::pi();
-        const double D_gr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * rho_g), pp);
-        const double D_cr = unrimed ? num<double>::inf() : pow_pos_(k.thr_coef / (pi * (rho_g * (1.0 - F_rim))), pp);
         const double target = log_full_(L_ice) - log_full_(N_ice);
-        auto f = [&](double l) { return shape(l, F_rim, rho_g, D_gr, D_cr, target); };
+        // shape_problem(logλ) = logLdivN(state, logλ) - target                        P3_size_distribution.jl:211-216, 292
+        auto f = [&](double l) {
+            double mu;
+            const double lse = p3_logmass_moment(k, t, l, 0.0, mu);
+            const double z0 = 0.0 + mu + 1.0;
+            return (lse - (-z0 * l + lgamma_pos_(z0) + 0.0)) - target;
+        };
         const double lo = 2.0, hi = 17.0;
         const double f_lo = f(lo), f_hi = f(hi);
         if (!isfinite(f_lo) || !isfinite(f_hi) || f_lo * f_hi > 0.0) { y[0] = (fabs(f_lo) <= fabs(f_hi)) ? lo : hi; return; }
         y[0] = brent_fixed(f, lo, hi, f_lo, f_hi, iters);
+    }
+};
+
+// P3State thresholds and the mass-weighted mean diameter D_m of (state, logλ)     P3_integral_properties.jl:56-61
+struct P3StateDiag {
+    P3K k;
+    __device__ __forceinline__ void operator()(const double (&x)[5], double (&y)[7]) const {
+        const double L_ice = x[0], N_ice = x[1], L_rim = x[2], B_rim = x[3], logl = x[4];
+        const P3Thresholds t = p3_thresholds(k, L_ice, L_rim, B_rim);
+        y[0] = t.F_rim; y[1] = t.rho_rim; y[2] = t.rho_g; y[3] = k.D_th; y[4] = t.D_gr; y[5] = t.D_cr;
+        double mu;
+        const double lse = p3_logmass_moment(k, t, logl, 1.0, mu);
+        const double z0 = 0.0 + mu + 1.0;
+        const double logN0 = log_full_(N_ice) - (-z0 * logl + lgamma_pos_(z0) + 0.0);
+        y[6] = exp_full_(logN0 + lse) / L_ice;
+    }
+};
+
+// UT.gamma_inc / gamma_inc_inv / rime_mass_fraction / rime_density over columns (the reference tests them on the
+// device, test/gpu_tests.jl:1305-1338)
+struct P3Leaf {
+    int what, gamma_iters;
+    double eps;
+    __device__ __forceinline__ void operator()(const double (&x)[2], double (&y)[1]) const {
+        switch (what) {
+            case 0: y[0] = gamma_inc_(x[0], x[1], lgamma_pos_(x[0]), gamma_iters).P; break;
+            case 1: y[0] = gamma_inc_(x[0], x[1], lgamma_pos_(x[0]), gamma_iters).Q; break;
+            case 2: y[0] = gamma_inc_inv_(x[0], x[1], 1.0 - x[1], gamma_iters, eps); break;
+            case 3: y[0] = regularised_ratio_(fmin_(x[0], x[1]), x[1], eps); break;
+            case 4: y[0] = regularised_ratio_(x[0], x[1], eps); break;
+            default: y[0] = 0.0;
+        }
     }
 };
 
@@ -447,10 +487,37 @@ int p3_logl_impl(const typename PP3<FT>::type* p, int64_t n, const FT* L_ice, co
     cumicro_params_p3_f64 wide;
     widen(*p, wide);
     P3LogLambda f{};
-    f.prm = wide.scheme;
     f.k = make_p3_k(wide, is_f32<FT>());
     f.iters = iters > 0 ? iters : f.k.brent_iters;
     return launch_pointwise<FT, 4, 1, P3LogLambda, 128, 3, false>(f, n, in, out, (cudaStream_t)stream, "p3_logl kernel launch");
+}
+
+template <class FT>
+int p3_state_impl(const typename PP3<FT>::type* p, int64_t n, const FT* L_ice, const FT* N_ice, const FT* L_rim, const FT* B_rim,
+                  const FT* logl, FT* const* out7, void* stream) {
+    int st = p3_check<FT>(p);
+    if (st) return st;
+    const FT* in[5] = {L_ice, N_ice, L_rim, B_rim, logl};
+    if ((st = validate_columns<FT, 5>(p, n, in))) return st;
+    if (out7 == nullptr) return cmh::fail(CUMICRO_E_NULL, "p3_state: output pointer table is NULL");
+    FT* out[7];
+    for (int c = 0; c < 7; ++c) out[c] = out7[c];
+    cumicro_params_p3_f64 wide;
+    widen(*p, wide);
+    P3StateDiag f{};
+    f.k = make_p3_k(wide, is_f32<FT>());
+    return launch_pointwise<FT, 5, 7, P3StateDiag, 128, 3, false>(f, n, in, out, (cudaStream_t)stream, "p3_state kernel launch");
+}
+
+template <class FT> int p3_leaf_impl(int what, int64_t n, const FT* x, const FT* y, FT* out, void* stream) {
+    if (what < 0 || what > 4) return cmh::fail(CUMICRO_E_OPTION, "p3_leaf: what = %d (expected 0..4)", what);
+    const FT* in[2] = {x, y};
+    int st = validate_columns<FT, 2>(&what, n, in);
+    if (st) return st;
+    FT* o[1] = {out};
+    if ((st = require_outputs<FT, 1>(n, o, 1))) return st;
+    P3Leaf f{what, is_f32<FT>() ? 20 : 30, is_f32<FT>() ? 1.1920928955078125e-07 : 2.220446049250313e-16};
+    return launch_pointwise<FT, 2, 1, P3Leaf, 128, 4, false>(f, n, in, o, (cudaStream_t)stream, "p3_leaf kernel launch");
 }
 
 }  // namespace
@@ -507,6 +574,21 @@ int cumicro_icenuc_f23_f64(const cumicro_params_p3_f64* p, int64_t n, const doub
 int cumicro_icenuc_f23_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in9, const float* inpc_log_shift,
                            float* const* out7, void* stream) {
     return icenuc_f23_impl<float>(p, n, in9, inpc_log_shift, out7, stream);
+}
+
+int cumicro_p3_state_f64(const cumicro_params_p3_f64* p, int64_t n, const double* L_ice, const double* N_ice, const double* L_rim,
+                         const double* B_rim, const double* logl, double* const* out7, void* stream) {
+    return p3_state_impl<double>(p, n, L_ice, N_ice, L_rim, B_rim, logl, out7, stream);
+}
+int cumicro_p3_state_f32(const cumicro_params_p3_f32* p, int64_t n, const float* L_ice, const float* N_ice, const float* L_rim,
+                         const float* B_rim, const float* logl, float* const* out7, void* stream) {
+    return p3_state_impl<float>(p, n, L_ice, N_ice, L_rim, B_rim, logl, out7, stream);
+}
+int cumicro_p3_leaf_f64(int what, int64_t n, const double* x, const double* y, double* out, void* stream) {
+    return p3_leaf_impl<double>(what, n, x, y, out, stream);
+}
+int cumicro_p3_leaf_f32(int what, int64_t n, const float* x, const float* y, float* out, void* stream) {
+    return p3_leaf_impl<float>(what, n, x, y, out, stream);
 }
 
 }  // extern "C"

@@ -395,6 +395,20 @@ int cumicro_icenuc_f23_f64(const cumicro_params_p3_f64* p, int64_t n, const doub
 int cumicro_icenuc_f23_f32(const cumicro_params_p3_f32* p, int64_t n, const float* const* in9, const float* inpc_log_shift,
                            float* const* out7, void* stream);
 
+/* P3State thresholds and mass-weighted mean diameter over columns (volumetric inputs as state_from_prognostic takes them):
+ *   out7 = F_rim, ρ_rim (regularised, clamped; P3_particle_properties.jl:101-106), ρ_g, D_th, D_gr, D_cr (:43-56; Inf when
+ *   F_rim = 0), D_m(state, logλ) (P3_integral_properties.jl:56-61).  NULL entries are skipped. */
+int cumicro_p3_state_f64(const cumicro_params_p3_f64* p, int64_t n, const double* L_ice, const double* N_ice, const double* L_rim,
+                         const double* B_rim, const double* logl, double* const* out7, void* stream);
+int cumicro_p3_state_f32(const cumicro_params_p3_f32* p, int64_t n, const float* L_ice, const float* N_ice, const float* L_rim,
+                         const float* B_rim, const float* logl, float* const* out7, void* stream);
+/* Shared numerics over columns (the reference tests them on the device, test/gpu_tests.jl:1305-1338): out = fn(x, y)
+ *   what 0 / 1: UT.gamma_inc(a = x, x = y) -> P / Q  (UT:92-144; fixed 30 / 20 iterations)
+ *        2: UT.gamma_inc_inv(a = x, p = y, q = 1 - y)  (UT:205-252)
+ *        3: UT.rime_mass_fraction(q_rim = x, q_ice = y)   4: UT.rime_density(q_rim = x, b_rim = y)  (UT:445-509) */
+int cumicro_p3_leaf_f64(int what, int64_t n, const double* x, const double* y, double* out, void* stream);
+int cumicro_p3_leaf_f32(int what, int64_t n, const float* x, const float* y, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -315,3 +315,52 @@ def test_f23_and_bigg_rates_standalone(built, orc, cuda):
             assert_parity(k, got[k].cpu().numpy(), ref[k], bound=bnd[k])
         assert (ref["rain_dn_frz"] > 0).mean() > 0.2 and (ref["cloud_dq_frz"] > 0).mean() > 0.2 and (ref["deposition_dn"] > 0).mean() > 0.005
         assert (ref["immersion_limit_dn"] == 0).mean() > 0.1           # T >= T_freeze (IN:425)
+
+
+def test_p3_state_and_shared_numerics(built, orc, cuda):
+    """Thresholds / D_m and UT.gamma_inc / gamma_inc_inv / regularised ratios on the device vs the oracle (and scipy,
+    at the reference's own tolerances, test/gpu_tests.jl:1305-1338)."""
+    import torch
+    from cumicro.testing import assert_parity
+    sp = pytest.importorskip("scipy.special")
+    P3, CMP3 = built.P3, built.CMP3
+    mp, tps, st = _setup(built, 3000, seed=41)
+    blk = CMP3.pack_p3(mp, tps)
+    vol = _volumetric(st)
+    ice = (vol[0] > EPS) & (vol[1] > EPS)
+    logl = _converged_logl(orc, blk, st)
+    d = [torch.from_numpy(v).to(cuda) for v in vol] + [torch.from_numpy(logl).to(cuda)]
+    got = P3.state_from_prognostic(mp, tps, *d)
+    ref = orc.p3_state(blk, *[v[ice] for v in vol], from_prognostic=True, logl=logl[ice], want=("thresholds", "D_m"))
+    for g, r in (("F_rim", "F_rim"), ("ρ_g", "rho_g"), ("D_th", "D_th"), ("D_gr", "D_gr"), ("D_cr", "D_cr"), ("D_m", "D_m")):
+        gg = got[g].cpu().numpy()[ice]
+        rr = ref[r]
+        if g == "ρ_g":   # NaN for unrimed ice in both (P3_particle_properties.jl:33)
+            assert np.array_equal(np.isnan(gg), np.isnan(rr)) and np.isnan(rr).sum() > 50
+        assert_parity(g, gg, rr)
+    assert np.isinf(ref["D_gr"]).sum() > 50
+    g = G["bulk_velocity"]
+    f = lambda v: torch.full((2,), float(v), dtype=torch.float64, device=cuda)
+    for k, F in enumerate(g["F_rims"]):
+        L, N = g["L_ice"], g["N_ice"]
+        ll = P3.get_distribution_logλ_from_prognostic(mp, tps, f(L), f(N), f(F * L), f(F * L / g["rho_rim"]))
+        assert abs(float(P3.D_m(mp, tps, f(L), f(N), f(F * L), f(F * L / g["rho_rim"]), ll)[0]) / g["D_m"][k] - 1) < 1e-12   # p3_tests.jl:440
+    # gamma_inc / gamma_inc_inv
+    gg = G["gamma_inc_grid"]
+    a, x = np.meshgrid(np.array(gg["a"], float), np.array(gg["x"], float), indexing="ij")
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v.ravel())).to(cuda)
+    P, Q = P3.gamma_inc(t(a), t(x))
+    assert np.max(np.abs(P.cpu().numpy() - sp.gammainc(a.ravel(), x.ravel()))) < gg["atol_PQ"]
+    assert np.max(np.abs(Q.cpu().numpy() - sp.gammaincc(a.ravel(), x.ravel()))) < gg["atol_PQ"]
+    a, pq = np.meshgrid(np.array(gg["a"], float), np.array(gg["p"], float), indexing="ij")
+    xi = P3.gamma_inc_inv(t(a), t(pq)).cpu().numpy()
+    assert np.max(np.abs(xi / sp.gammaincinv(a.ravel(), pq.ravel()) - 1)) < gg["rtol_inv"]
+    rng = np.random.default_rng(5)
+    a, x = rng.uniform(1.0, 12, 20000), rng.uniform(0, 40, 20000)
+    assert_parity("gamma_inc P", P3.gamma_inc(t(a), t(x))[0].cpu().numpy(), orc.p3_leaf("gamma_inc_P", a, x), bound=np.full(a.size, 4 * EPS))
+    pq = rng.uniform(1e-6, 1 - 1e-6, 20000)
+    assert_parity("gamma_inc_inv", P3.gamma_inc_inv(t(a), t(pq)).cpu().numpy(), orc.p3_leaf("gamma_inc_inv", a, pq), rtol=1e-11)
+    q_ice = 10 ** rng.uniform(-18, -3, 20000)
+    q_rim = q_ice * rng.uniform(0, 1.2, 20000)
+    assert_parity("rime_mass_fraction", P3.rime_mass_fraction(t(q_rim), t(q_ice)).cpu().numpy(), orc.p3_leaf("rime_mass_fraction", q_rim, q_ice), rtol=1e-11)
+    assert_parity("rime_density", P3.rime_density(t(q_rim), t(q_ice)).cpu().numpy(), orc.p3_leaf("rime_density", q_rim, q_ice), rtol=1e-11)
