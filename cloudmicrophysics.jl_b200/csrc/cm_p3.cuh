@@ -84,17 +84,14 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double
     PQ r;
     if (x <= 0.0) { r.P = 0.0; r.Q = 1.0; return r; }
     if (x == num<double>::inf()) { r.P = 1.0; r.Q = 0.0; return r; }
-    const double factor = exp_(fmin_(fmax_(a * logp_(x) - x - lga, -700.0), 700.0));
+    const double factor = exp_nl_(a * logp_nl_(x) - x - lga);
     if (x < a + 1.0) {
         double term = div_(1.0, a);
         double sum = term;
 #pragma unroll 1
-        for (int k0 = 1; k0 <= iters; k0 += 5) {   // iters is 30 or 20
-#pragma unroll
-            for (int k = k0; k < k0 + 5; ++k) {
-                term *= x * rcp_(a + (double)k);
-                sum += term;
-            }
+        for (int k = 1; k <= iters; ++k) {
+            term *= x * rcp_(a + (double)k);
+            sum += term;
             if (term < sum * 5.5e-17) break;
         }
         r.P = clamp_(factor * sum, 0.0, 1.0);
@@ -105,7 +102,7 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double
         double c = b1 + 1.0 / tiny;
         double d = rcp_(b1);
         double h = d;
-#pragma unroll 5
+#pragma unroll 1
         for (int k = 1; k <= iters; ++k) {
             const double kd = (double)k;
             const double a_k = -kd * (kd - a);
