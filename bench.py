@@ -274,7 +274,7 @@ def main():
                    "l2": "inputs (7 x 134 MB columns) larger than the 126 MB L2; no flush needed",
                    "psd": "SB2006 limited rain PSD, log-uniform number concentrations"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel_pipelined<double,7,4,Warm2MFused,128x8> (cp.async double-buffered inputs, 16 waves)",
+                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel_pipelined<double,7,4,Warm2MFused,128x7> (cp.async double-buffered inputs, 16 waves)",
                      "kernel_ms": kernel_ms, "bytes_per_point": BYTES_PER_POINT},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 7 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n,
                 "steps": args.e2e_steps, "api": "cumicro_bmt2m_warm_host_f64 (pinned host buffers, chunked H2D/kernel/D2H)"},

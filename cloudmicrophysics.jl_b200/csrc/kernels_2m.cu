@@ -103,11 +103,19 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
             case 6: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8>(f, n, in, out, s, w);
             case 7: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 8>(f, n, in, out, s, w);
             case 8: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 12>(f, n, in, out, s, w);
+            case 10: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, n, in, out, s, w);
+            case 11: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 6, false, true>(f, n, in, out, s, w);
+            case 12: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 16, false, true>(f, n, in, out, s, w);
+            case 13: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 256, 4, false, true>(f, n, in, out, s, w);
+            case 14: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 5, false, true>(f, n, in, out, s, w);
+            case 15: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 96, 10, false, true>(f, n, in, out, s, w);
             default: break;
         }
     }
 #endif
-    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false, true>(f, n, in, out, s, "bmt2m_warm kernel launch");
+    // 128 x 7 blocks/SM (72 registers): sweep of the pipelined kernel 128x8 0.630, 128x7 0.623, 128x6 0.633, 128x5 0.659,
+    // 64x16 0.632, 256x4 0.634, 96x10 0.638 ms
+    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, n, in, out, s, "bmt2m_warm kernel launch");
 }
 
 template <class FT>
