@@ -96,7 +96,7 @@ static __shared__ unsigned long long cm_sh_exp[256];
 static __shared__ ulonglong2 cm_sh_log[128];
 // the few coefficients that need all 53 bits (everything else in exp_/logp_/cbrtp_ is an
 // immediate operand: constants whose low 32 bits are zero cost no instruction on sm_100)
-static __constant__ double cm_kc[4] = {3.3333333333333331e-01, 0.2, CM_LOG_LN2_LO, 0.0};
+static __constant__ double cm_kc[6] = {3.3333333333333331e-01, 0.2, CM_LOG_LN2_LO, 0.0, CM_EXP_INV_L, CM_EXP_C4};
 #endif
 #define CM_LOG_C3_HOST 3.3333333333333331e-01
 
@@ -183,13 +183,20 @@ CM_HD float rcp_(float x) { return 1.0f / x; }
 // All constants are immediates (21-bit pieces): 10 FP64 instructions, 1 LDS, ~6 integer.
 CM_HD double exp_(double x) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
-    const double t = fma(x, CM_EXP_INV_L, magic);
+    // an FP64 instruction takes ONE non-register operand: the second constant of a two-constant fma comes from the
+    // constant bank (one uniform load) instead of two 32-bit moves
+#ifdef __CUDA_ARCH__
+    const double inv_l = cm_kc[4], c4 = cm_kc[5];
+#else
+    const double inv_l = CM_EXP_INV_L, c4 = CM_EXP_C4;
+#endif
+    const double t = fma(x, inv_l, magic);
     const int ki = lo32(t);
     const double kf = t - magic;
     double r = fma(kf, -CM_EXP_L1, x);  // exact
     r = fma(kf, -CM_EXP_L2, r);
     r = fma(kf, -CM_EXP_L3, r);
-    double p = fma(r, CM_EXP_C4, CM_EXP_C3);
+    double p = fma(r, c4, CM_EXP_C3);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r;  // expm1(r)
