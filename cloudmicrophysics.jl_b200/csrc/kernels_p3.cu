@@ -20,7 +20,7 @@ namespace {
 using namespace cm;
 
 constexpr int BLOCK = 128;
-constexpr int MINB = 4;
+constexpr int MINB = 10;   // 48 registers: the kernel is instruction-fetch / latency bound, resident warps matter more than spills (2^19 points: MINB 4: 66.0, 6: 62.9, 8: 59.3, 10: 57.5, 12: 57.4 ms)
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
 constexpr int NIN_MAX = 13, NOUT_MAX = 12;
 
