@@ -9,6 +9,12 @@
 #include "cm_launch.cuh"
 #include "cm_sb2006.cuh"
 
+#ifndef CUMICRO_1MV_MINB
+#define CUMICRO_1MV_MINB 8   /* verbose: 4 -> 1.75 ms, 6 -> 1.34, 8 -> 1.22; linavg: 3.07, 3.01, 2.94 */
+#endif
+#ifndef CUMICRO_1M_MINB
+#define CUMICRO_1M_MINB 8   /* sweep at 2^24 points: 5 -> 1.224 ms, 6 -> 1.118, 8 -> 1.043 */
+#endif
 namespace {
 
 using namespace cm;
@@ -81,13 +87,13 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
     if ((st = require_outputs<FT, 4>(n, o4, 4))) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == 0) {
-        return launch_pointwise<FT, 7, 4, OneMInst, 128, 5, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
+        return launch_pointwise<FT, 7, 4, OneMInst, 128, CUMICRO_1M_MINB, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
     } else if (mode == 1) {
         if (src18 == nullptr) return cmh::fail(CUMICRO_E_NULL, "source-term pointer table is NULL");
         FT* o22[4 + S1M_NSRC];
         for (int i = 0; i < 4; ++i) o22[i] = o4[i];
         for (int i = 0; i < S1M_NSRC; ++i) o22[4 + i] = src18[i];
-        return launch_pointwise<FT, 7, 4 + S1M_NSRC, OneMVerbose, 128, 4, false>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
+        return launch_pointwise<FT, 7, 4 + S1M_NSRC, OneMVerbose, 128, CUMICRO_1MV_MINB, false>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
                                                                                    "bmt1m_verbose launch");
     } else {
         if (!(dt > FT(0))) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: dt must be > 0");
@@ -97,7 +103,7 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
         f.nsub = nsub;
         f.Lv_over_cp = f.p.tps.LH_v0 / f.p.tps.cp_d;
         f.Ls_over_cp = f.p.tps.LH_s0 / f.p.tps.cp_d;
-        return launch_pointwise<FT, 7, 4, OneMLinAvg, 128, 4, false>(f, n, in, o4, s, "bmt1m_linavg launch");
+        return launch_pointwise<FT, 7, 4, OneMLinAvg, 128, CUMICRO_1MV_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
     }
 }
 

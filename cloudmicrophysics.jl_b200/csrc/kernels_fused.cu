@@ -25,6 +25,9 @@ constexpr int NIN = 11;   // rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_
 constexpr int NOUT = 11;  // 1M: dq_lcl, dq_icl, dq_rai, dq_sno | 2M: dq_lcl, dn_lcl, dq_rai, dn_rai | J_dep, J_ABIFM, J_hom
 constexpr int NDIAG = CUMICRO_NDIAG;
 constexpr int BLOCK = 128;
+#ifndef CUMICRO_FUSED_MINB
+#define CUMICRO_FUSED_MINB 4
+#endif
 
 struct FusedParams {
     P<D>::params_1m p1;
@@ -46,7 +49,7 @@ template <class FT> struct FusedArgs {
 };
 
 template <class FT>
-__global__ void __launch_bounds__(BLOCK, 4) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
+__global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     math_tables_init<BLOCK>();
     const FusedParams& f = a.f;
     double diag[NDIAG];

@@ -6,6 +6,9 @@
 #include "cm_icenuc.cuh"
 #include "cm_launch.cuh"
 
+#ifndef CUMICRO_ARG_MINB
+#define CUMICRO_ARG_MINB 6   /* sweep, config 3: 4 -> 3.50 ms, 6 -> 3.09, 8 -> 3.10 */
+#endif
 namespace {
 
 using namespace cm;
@@ -206,9 +209,9 @@ int arg_icenuc_launch(const typename PI<FT>::params* p, int64_t n, const FT* con
     out[1 + 2 * MODES + 2] = J_hom;
     out[1 + 2 * MODES + 3] = da_w;
     if (want_m)
-        return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, 4, false>(
+        return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, CUMICRO_ARG_MINB, false>(
             make_icenuc<FT, ArgIceNuc<MODES, true>>(p, counter), n, in, out, s, "arg_icenuc launch");
-    return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, 4, false>(
+    return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, CUMICRO_ARG_MINB, false>(
         make_icenuc<FT, ArgIceNuc<MODES, false>>(p, counter), n, in, out, s, "arg_icenuc launch");
 }
 
