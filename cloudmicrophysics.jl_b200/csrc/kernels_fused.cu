@@ -26,7 +26,7 @@ constexpr int NOUT = 11;  // 1M: dq_lcl, dq_icl, dq_rai, dq_sno | 2M: dq_lcl, dn
 constexpr int NDIAG = CUMICRO_NDIAG;
 constexpr int BLOCK = 128;
 #ifndef CUMICRO_FUSED_MINB
-#define CUMICRO_FUSED_MINB 4
+#define CUMICRO_FUSED_MINB 6   /* 2^24 points: 4 (all inputs and outputs live) 4.54 ms; staged inputs + early stores: 6 -> 4.00, 8 -> 4.04 */
 #endif
 
 struct FusedParams {
@@ -48,41 +48,64 @@ template <class FT> struct FusedArgs {
     int64_t n;
 };
 
+// The three families run one after the other on the same point.  Their inputs wait in shared memory (per-thread cp.async
+// copies, double-buffered: the next item streams in while this one is computed) and every family stores its tendencies and
+// accumulates its diagnostic as soon as it is done, so the live register set is that of ONE family at a time and the kernel
+// keeps the occupancy of the single-family kernels.
+#define CM_FUSED_FENCE() asm volatile("" ::: "memory")
 template <class FT>
 __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     math_tables_init<BLOCK>();
+    __shared__ FT stage[2][NIN][BLOCK];
     const FusedParams& f = a.f;
+    const int tid = threadIdx.x;
     double diag[NDIAG];
 #pragma unroll
     for (int k = 0; k < NDIAG; ++k) diag[k] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += stride) {
-        double x[NIN];
+    int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
+    if (i < a.n) {
 #pragma unroll
-        for (int c = 0; c < NIN; ++c) x[c] = (double)__ldg(a.in[c] + i);
-        const double rho = x[0], T = x[1], pr = x[2], w = x[3], q_tot = x[4], q_lcl = x[5], q_icl = x[6], q_rai = x[7],
-                     q_sno = x[8], n_lcl = x[9], n_rai = x[10];
-        double y[NOUT];
+        for (int c = 0; c < NIN; ++c) cp_async_elem(&stage[0][c][tid], a.in[c] + i);
+    }
+    cp_async_commit();
+    int buf = 0;
+    for (; i < a.n; i += stride) {
+        const int64_t nxt = i + stride;
+        if (nxt < a.n) {
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) cp_async_elem(&stage[buf ^ 1][c][tid], a.in[c] + nxt);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        auto in = [&](int c) { return (double)stage[buf][c][tid]; };   // rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai
+        auto put = [&](int c, double v) { if (a.out[c]) __stcs(a.out[c] + i, (FT)v); };
         // 1-moment tendencies                                         BMT:505-514
         {
-            const Src1M<D> r = microphysics_source_terms_1m<D>(f.p1, f.tk, f.k1, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno);
+            const Src1M<D> r = microphysics_source_terms_1m<D>(f.p1, f.tk, f.k1, in(0), in(1), in(4), in(5), in(6), in(7), in(8));
             double t[4];
             aggregate_tendencies_1m<D>(r, t);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = t[k];
+            for (int k = 0; k < 4; ++k) put(k, t[k]);
+            diag[0] += in(0) * (t[2] + t[3]);   // 1M precipitation production  Σ ρ (dq_rai + dq_sno)   [kg m^-3 s^-1]
         }
+        CM_FUSED_FENCE();
         // 2-moment warm rain (cloud ice seen by the thermodynamics = q_icl + q_sno)   BMT:820-854
         {
-            const Warm2M<D> o = warm_rain_tendencies_2m<D>(f.p2, f.tk, f.k2, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai,
-                                                           fmax_(0.0, q_icl) + fmax_(0.0, q_sno));
-            y[4] = o.dq_lcl_dt;
-            y[5] = o.dn_lcl_dt;
-            y[6] = o.dq_rai_dt;
-            y[7] = o.dn_rai_dt;
+            const Warm2M<D> o = warm_rain_tendencies_2m<D>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10),
+                                                           fmax_(0.0, in(6)) + fmax_(0.0, in(8)));
+            put(4, o.dq_lcl_dt);
+            put(5, o.dn_lcl_dt);
+            put(6, o.dq_rai_dt);
+            put(7, o.dn_rai_dt);
+            diag[1] += in(0) * o.dq_rai_dt;     // 2M rain production           Σ ρ dq_rai
         }
+        CM_FUSED_FENCE();
         // ice-nucleation rates (+ ARG2000 activated number)              IN:92-134, 557-584; AA:138-273
-        double n_act = 0.0;
         {
+            const double rho = in(0), T = in(1), pr = in(2), w = in(3), q_tot = in(4), q_lcl = in(5), q_icl = in(6), q_rai = in(7),
+                         q_sno = in(8), n_lcl = in(9);
+            double n_act = 0.0;
             double da_w;
             if (f.with_activation) {
                 const ArgOut o = arg2000<false>(f.p3, f.tk, f.k3, T, pr, w, q_tot, q_lcl + q_rai, q_icl + q_sno, rho * n_lcl, 0.0);
@@ -98,20 +121,17 @@ __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const 
                 da_w = p_v / pl - p_sat_ice(f.tk, ts) / pl;
             }
             bool err = false;
-            y[8] = deposition_J<D>(f.p3.dust, da_w, f.k3.ln10);
-            y[9] = ABIFM_J<D>(f.p3.dust, da_w, f.k3.ln10);
-            y[10] = f.p3.hom_linear ? homogeneous_J_linear<D>(f.p3.koop, da_w, f.k3.ln10)
-                                    : homogeneous_J_cubic<D>(f.p3.koop, da_w, f.k3.ln10, err);
-            if (err) y[10] = __longlong_as_double(0x7ff8000000000000LL);
+            put(8, deposition_J<D>(f.p3.dust, da_w, f.k3.ln10));
+            put(9, ABIFM_J<D>(f.p3.dust, da_w, f.k3.ln10));
+            double jh = f.p3.hom_linear ? homogeneous_J_linear<D>(f.p3.koop, da_w, f.k3.ln10)
+                                        : homogeneous_J_cubic<D>(f.p3.koop, da_w, f.k3.ln10, err);
+            if (err) jh = __longlong_as_double(0x7ff8000000000000LL);
+            put(10, jh);
+            diag[2] += n_act;                   // activated aerosol number     Σ N_act                  [m^-3]
+            diag[3] += 1.0;                     // points
         }
-#pragma unroll
-        for (int c = 0; c < NOUT; ++c)
-            if (a.out[c]) __stcs(a.out[c] + i, (FT)y[c]);
-        // diagnostics of this point (the rounded stored values are NOT used: Float64 sums)
-        diag[0] += rho * (y[2] + y[3]);   // 1M precipitation production  Σ ρ (dq_rai + dq_sno)   [kg m^-3 s^-1]
-        diag[1] += rho * y[6];            // 2M rain production           Σ ρ dq_rai
-        diag[2] += n_act;                 // activated aerosol number     Σ N_act                  [m^-3]
-        diag[3] += 1.0;                   // points
+        CM_FUSED_FENCE();
+        buf ^= 1;
     }
     // block reduction: shuffle within warps, then across the (BLOCK/32) warps through shared memory
     __shared__ double red[BLOCK / 32][NDIAG];
@@ -131,13 +151,22 @@ __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const 
     }
 }
 
-// fixed-order second pass: one block, thread k sums partial k of every block in block order
+// fixed-order second pass: one block; thread t sums the partials of blocks t, t + 256, ... in that order, then a fixed
+// binary tree over the 256 thread sums -> bit-reproducible for a given grid size
 __global__ void fused_diag_finish(const double* partials, int n_blocks, double* diag) {
-    const int k = threadIdx.x;
-    if (k >= NDIAG) return;
-    double v = 0.0;
-    for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * NDIAG + k];
-    diag[k] = v;
+    __shared__ double sh[256];
+    for (int k = 0; k < NDIAG; ++k) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < n_blocks; b += 256) v += partials[(size_t)b * NDIAG + k];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) diag[k] = sh[0];
+        __syncthreads();
+    }
 }
 
 template <class FT> struct PF;
@@ -166,7 +195,7 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
     for (int c = 0; c < NOUT; ++c) a.out[c] = out[c];
     a.n = n;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * 4 * 4));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * CUMICRO_FUSED_MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
     void* ws = nullptr;
     int st = cmh::workspace(cmh::kPipeSlots /* slot reserved for the diagnostics partials */, sizeof(double) * NDIAG * (size_t)blocks + 64, &ws);
     if (st) return st;
@@ -174,7 +203,7 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     fused_kernel<FT><<<blocks, BLOCK, 0, s>>>(a);
     cmh::count_launch();
     if (diag) {
-        fused_diag_finish<<<1, 32, 0, s>>>(a.partials, blocks, diag);
+        fused_diag_finish<<<1, 256, 0, s>>>(a.partials, blocks, diag);
         cmh::count_launch();
     }
     return cmh::cuda_status(cudaGetLastError(), "fused_1m2m_icenuc launch");
