@@ -19,6 +19,8 @@ template <class FT> struct ArgK {
     FT sm_coef[kMaxModes]; // 2/sqrt(hygro) (A_coef/3/r_dry)^(3/2) -> S_m = sm_coef T^(-3/2)   AA:107-118
     FT f[kMaxModes], g[kMaxModes];                  // f1 exp(f2 ln²σ), g1 + g2 ln σ     AA:175-176
     FT inv_eta_coef[kMaxModes];                     // 2π ρ_w N_i
+    FT log_sm_coef[kMaxModes], log_inv_eta_coef[kMaxModes];   // their logarithms (host): one log per mode per point instead of three
+    FT log_T_triple;
     FT u_coef[kMaxModes];                           // 2 / (3 √2 ln σ_i)                AA:256
     FT m_fac[kMaxModes];                            // 3 ln σ_i √2 / 2                   AA:320
     FT inv_K_safe, inv_D_safe, ln10, c43pi_rho_w, c43pi_rho_i, four_pi;
@@ -37,6 +39,8 @@ template <class FT> __host__ inline ArgK<FT> make_arg_k(const cumicro_params_ice
         k.f[i] = p.arg.f1 * std::exp(p.arg.f2 * ls * ls);
         k.g[i] = p.arg.g1 + p.arg.g2 * ls;
         k.inv_eta_coef[i] = 2 * pi * p.arg.rho_w * m.N;
+        k.log_sm_coef[i] = std::log(k.sm_coef[i]);
+        k.log_inv_eta_coef[i] = std::log(k.inv_eta_coef[i]);   // -Inf for an empty mode: η = Inf, both powers vanish
         k.u_coef[i] = FT(2) / (FT(3) * std::sqrt(FT(2)) * ls);
         k.m_fac[i] = FT(3) * ls * std::sqrt(FT(2)) / 2;
     }
@@ -47,6 +51,7 @@ template <class FT> __host__ inline ArgK<FT> make_arg_k(const cumicro_params_ice
     k.c43pi_rho_i = FT(4.0 / 3) * pi * p.arg.rho_i;
     k.four_pi = 4 * pi;
     k.Rv_over_Rd = p.tps.R_v / p.tps.R_d;
+    k.log_T_triple = std::log(FT(p.tps.T_triple));
     return k;
 }
 
@@ -111,17 +116,24 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT inv_gamma = rcp_(gamma);
     const FT Tm32 = ts.inv_T * sqrt_(ts.inv_T);
     const FT l_zeta = logp_(zeta);
-    FT Sm[kMaxModes];
+    // logarithms: log S_m,i = log(sm_coef_i) - 3/2 log T and log η_i = log(sq³/γ) - log(2π ρ_w N_i) come from host-side
+    // logarithms of the parameters plus two per-point ones; per mode only log(η_i + 3ζ) remains
+    auto log_g = [](FT v) { return (v > FT(2.3e-308) && v < FT(1.7e308)) ? logp_(v) : log_full_(v); };
+    const FT l_T32 = FT(-1.5) * (ts.log_Tr + k.log_T_triple);
+    const FT eta_common = sq3 * inv_gamma;
+    const FT l_eta_common = log_g(eta_common);
+    FT Sm[kMaxModes], l_Sm[kMaxModes];
     FT tmp = FT(0);
 #pragma unroll
     for (int i = 0; i < kMaxModes; ++i) {
         if (i >= p.n_modes) break;
         Sm[i] = k.sm_coef[i] * Tm32;
+        l_Sm[i] = k.log_sm_coef[i] + l_T32;
         const FT Sm2 = Sm[i] * Sm[i];
-        const FT eta = sq3 * inv_gamma * rcp_(k.inv_eta_coef[i]);
+        const FT eta = eta_common * rcp_(k.inv_eta_coef[i]);
         // (ζ/η)^p1 and (S_m²/(η+3ζ))^p2
-        const FT t1 = exp_full_(ap.p1 * (l_zeta - log_full_(eta)));
-        const FT t2 = exp_full_(ap.p2 * log_full_(Sm2 / fma_(FT(3), zeta, eta)));
+        const FT t1 = exp_full_(ap.p1 * (l_zeta - (l_eta_common - k.log_inv_eta_coef[i])));
+        const FT t2 = exp_full_(ap.p2 * (FT(2) * l_Sm[i] - log_g(fma_(FT(3), zeta, eta))));
         tmp += rcp_(Sm2) * fma_(k.f[i], t1, k.g[i] * t2);
     }
     const FT S_max_ARG = FT(1) / sqrt_(tmp);
@@ -139,7 +151,7 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
 #pragma unroll
     for (int i = 0; i < kMaxModes; ++i) {
         if (i >= p.n_modes) break;
-        const FT lr = log_full_(Sm[i]) - l_smax;   // log(S_m / S_max)
+        const FT lr = l_Sm[i] - l_smax;   // log(S_m / S_max)
         o.N_act[i] = p.modes[i].N * FT(0.5) * (FT(1) - erf_(k.u_coef[i] * lr));
         if (WANT_M) o.M_act[i] = p.modes[i].molar_mass_mix * FT(0.5) * erfc_(lr / k.m_fac[i] - k.m_fac[i]);
     }
