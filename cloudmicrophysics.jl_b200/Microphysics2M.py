@@ -58,3 +58,42 @@ def rain_terminal_velocity(sb, vel, q_rai, rho, N_rai):
 def cloud_terminal_velocity(pdf_c, vel, q_liq, rho, N_liq):
     """CM2.cloud_terminal_velocity(pdf_c, ::StokesRegimeVelType, q_liq, ρₐ, N_liq) (CM2:647-664)."""
     return _termvel("termvel_2m_cloud", pdf_c, vel, q_liq, rho, N_liq)
+
+
+# ---- alternative closures (CM2:920-1002): KK2000, B1994, TC1980, LD2004 ---------------------------------------
+_ALT = {"acnv": {"KK2000": 0, "B1994": 1, "TC1980": 2, "LD2004": 3}, "accr": {"KK2000": 4, "B1994": 5, "TC1980": 6}}
+
+
+def _alt(scheme, what, smooth, q_lcl, q_rai, rho, N_d):
+    cols = [c for c in (q_lcl, q_rai, rho, N_d) if c is not None]
+    suf, n, dev = check_columns(cols, ["q_lcl", "column 2", "column 3"])
+    if not type(scheme.block).__name__.endswith(suf):
+        raise TypeError(f"parameter float type does not match the columns ({suf})")
+    out = torch.empty_like(q_lcl)
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_2m_alt_{suf}")(C.byref(scheme.block), C.c_int(what), C.c_int(int(bool(smooth))), C.c_int64(n),
+                                                          ptr(q_lcl), ptr(q_rai), ptr(rho), ptr(N_d), ptr(out), stream_handle(dev))
+    _abi.check(st, "cumicro_2m_alt")
+    return out
+
+
+def conv_q_lcl_to_q_rai(scheme, q_lcl, rho, N_d, smooth_transition=False):
+    """CM2.conv_q_lcl_to_q_rai(::KK2000 | ::B1994 | ::TC1980 | ::LD2004, q_lcl, ρ, N_d[, smooth_transition]) (CM2:920-969)."""
+    try:
+        what = _ALT["acnv"][scheme.name]
+    except (AttributeError, KeyError):
+        raise TypeError(f"no conv_q_lcl_to_q_rai method for {scheme!r}") from None
+    if what == 0 and smooth_transition:
+        raise TypeError("conv_q_lcl_to_q_rai(::KK2000, q_lcl, ρ, N_d) takes no smooth_transition argument (CM2:920)")
+    return _alt(scheme, what, smooth_transition, q_lcl, None, rho, N_d)
+
+
+def accretion(scheme, q_lcl, q_rai, rho=None):
+    """CM2.accretion(::KK2000 | ::B1994, q_lcl, q_rai, ρ) and accretion(::TC1980, q_lcl, q_rai) (CM2:985-1002)."""
+    try:
+        what = _ALT["accr"][scheme.name]
+    except (AttributeError, KeyError):
+        raise TypeError(f"no accretion method for {scheme!r}") from None
+    if (what == 6) != (rho is None):
+        raise TypeError("accretion(::TC1980, q_lcl, q_rai) takes no density; KK2000 and B1994 need ρ (CM2:985-1002)")
+    return _alt(scheme, what, False, q_lcl, q_rai, rho, None)

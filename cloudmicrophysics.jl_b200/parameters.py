@@ -169,6 +169,19 @@ DEFAULTS = {
     "cloud_ice_snow_collision_efficiency": 0.1,
     "rain_snow_collision_efficiency": 1.0,
     "rain_snow_velocity_dispersion_coefficient": 0.2,  # back-solved (exact) from both goldens of test/microphysics1M_tests.jl:380-453
+    # --- alternative 2-moment closures (CMP/Microphysics2M.jl:11-310; docs/src/Microphysics2M.md:686-878); every value
+    #     verified exactly on the autoconversion / accretion literals of test/gpu_tests.jl:795-818
+    "KK2000_autoconversion_coeff_A": 7.42e13, "KK2000_autoconversion_coeff_a": 2.47,
+    "KK2000_autoconversion_coeff_b": -1.79, "KK2000_autoconversion_coeff_c": -1.47,
+    "KK2000_accretion_coeff_A": 67.0, "KK2000_accretion_coeff_a": 1.15, "KK2000_accretion_coeff_b": -1.3,
+    "B1994_autoconversion_coeff_C": 3e34, "B1994_autoconversion_coeff_a": -1.7, "B1994_autoconversion_coeff_b": 4.7,
+    "B1994_autoconversion_coeff_c": -3.3, "B1994_autoconversion_coeff_N_0": 2e8,
+    "B1994_autoconversion_coeff_d_low": 3.9, "B1994_autoconversion_coeff_d_high": 9.9,
+    "B1994_accretion_coeff_A": 6.0,
+    "TC1980_autoconversion_coeff_a": 7.0 / 3.0, "TC1980_autoconversion_coeff_b": -1.0 / 3.0,
+    "TC1980_autoconversion_coeff_D": 3268.0, "TC1980_autoconversion_coeff_r_0": 7e-6,
+    "TC1980_autoconversion_coeff_me_liq": 3.0, "TC1980_accretion_coeff_A": 4.7,
+    "LD2004_R_6C_coeff": 7.5, "LD2004_E_0_coeff": 1.08e10,
     # --- 0-moment scheme (CMP/Microphysics0M.jl:20-28); ClimaParams defaults, not pinned by any reference test
     #     (its tests compare remove_precipitation with the formula evaluated on the same parameters)
     "precipitation_timescale": 1000.0,
@@ -489,6 +502,55 @@ def Chen2022VelTypeLargeIce(FT=np.float64, overrides=None):
         A=td["Chen2022_table_B5_Al"], B=td["Chen2022_table_B5_Bl"], C=td["Chen2022_table_B5_Cl"],
         E=td["Chen2022_table_B5_El"], F=td["Chen2022_table_B5_Fl"], G=td["Chen2022_table_B5_Gl"],
         H=td["Chen2022_table_B5_Hl"], cutoff=td["Chen2022_ice_cutoff"])
+
+
+# ============================ alternative 2-moment closures ============================
+@dataclass
+class _AltScheme:
+    """KK2000 / B1994 / TC1980 / LD2004 (CMP/Microphysics2M.jl:52-241): a tag plus the shared POD block; the array
+    methods of ``Microphysics2M`` dispatch on ``name`` the way the reference dispatches on the struct type."""
+    name: str
+    block: object
+
+
+def _alt_block(FT=np.float64, overrides=None):
+    td = _td(FT, overrides)
+    F = td.FT
+    k = td["threshold_smooth_transition_steepness"]
+    return _abi.struct("params_2m_alt", td.suffix)(
+        kk_acnv_A=td["KK2000_autoconversion_coeff_A"], kk_acnv_a=td["KK2000_autoconversion_coeff_a"],
+        kk_acnv_b=td["KK2000_autoconversion_coeff_b"], kk_acnv_c=td["KK2000_autoconversion_coeff_c"],
+        kk_accr_A=td["KK2000_accretion_coeff_A"], kk_accr_a=td["KK2000_accretion_coeff_a"], kk_accr_b=td["KK2000_accretion_coeff_b"],
+        b_acnv_C=td["B1994_autoconversion_coeff_C"], b_acnv_a=td["B1994_autoconversion_coeff_a"],
+        b_acnv_b=td["B1994_autoconversion_coeff_b"], b_acnv_c=td["B1994_autoconversion_coeff_c"],
+        b_acnv_N_0=td["B1994_autoconversion_coeff_N_0"], b_acnv_k=k, b_acnv_d_low=td["B1994_autoconversion_coeff_d_low"],
+        b_acnv_d_high=td["B1994_autoconversion_coeff_d_high"], b_accr_A=td["B1994_accretion_coeff_A"],
+        # m0_liq_coeff = ρ_w · 4/3 · π in the constructor's operation order (CMP/Microphysics2M.jl:200)
+        tc_acnv_m0_liq_coeff=td["density_liquid_water"] * F(4) / F(3) * F(math.pi), tc_acnv_me_liq=td["TC1980_autoconversion_coeff_me_liq"],
+        tc_acnv_D=td["TC1980_autoconversion_coeff_D"], tc_acnv_a=td["TC1980_autoconversion_coeff_a"],
+        tc_acnv_b=td["TC1980_autoconversion_coeff_b"], tc_acnv_r_0=td["TC1980_autoconversion_coeff_r_0"], tc_acnv_k=k,
+        tc_accr_A=td["TC1980_accretion_coeff_A"],
+        ld_rho_w=td["density_liquid_water"], ld_R_6C_0=td["LD2004_R_6C_coeff"], ld_E_0=td["LD2004_E_0_coeff"], ld_k=k)
+
+
+def KK2000(FT=np.float64, overrides=None):
+    """CMP.KK2000 (Khairoutdinov & Kogan 2000; CMP/Microphysics2M.jl:52-62)."""
+    return _AltScheme("KK2000", _alt_block(FT, overrides))
+
+
+def B1994(FT=np.float64, overrides=None):
+    """CMP.B1994 (Beheng 1994; CMP/Microphysics2M.jl:122-132)."""
+    return _AltScheme("B1994", _alt_block(FT, overrides))
+
+
+def TC1980(FT=np.float64, overrides=None):
+    """CMP.TC1980 (Tripoli & Cotton 1980; CMP/Microphysics2M.jl:205-215)."""
+    return _AltScheme("TC1980", _alt_block(FT, overrides))
+
+
+def LD2004(FT=np.float64, overrides=None):
+    """CMP.LD2004 (Liu & Daum 2004; CMP/Microphysics2M.jl:225-241)."""
+    return _AltScheme("LD2004", _alt_block(FT, overrides))
 
 
 # ============================ 0-moment scheme ==========================================

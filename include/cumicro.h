@@ -409,6 +409,18 @@ int cumicro_p3_state_f32(const cumicro_params_p3_f32* p, int64_t n, const float*
 int cumicro_p3_leaf_f64(int what, int64_t n, const double* x, const double* y, double* out, void* stream);
 int cumicro_p3_leaf_f32(int what, int64_t n, const float* x, const float* y, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Alternative 2-moment closures (CM2:920-1002; goldens test/gpu_tests.jl:795-818): out = fn(columns)
+ *   what 0: conv_q_lcl_to_q_rai(::KK2000, q_lcl, ρ, N_d)        1: (::B1994, ...; smooth_transition)
+ *        2: (::TC1980, ...; smooth_transition)                 3: (::LD2004, ...; smooth_transition)
+ *        4: accretion(::KK2000, q_lcl, q_rai, ρ)   5: accretion(::B1994, q_lcl, q_rai, ρ)   6: accretion(::TC1980, q_lcl, q_rai)
+ *   Columns: q_lcl, q_rai (read by what >= 4, may be NULL otherwise), rho, N_d (read by what <= 3, may be NULL otherwise).
+ * ------------------------------------------------------------------------- */
+int cumicro_2m_alt_f64(const cumicro_params_2m_alt_f64* p, int what, int smooth_transition, int64_t n, const double* q_lcl,
+                       const double* q_rai, const double* rho, const double* N_d, double* out, void* stream);
+int cumicro_2m_alt_f32(const cumicro_params_2m_alt_f32* p, int what, int smooth_transition, int64_t n, const float* q_lcl,
+                       const float* q_rai, const float* rho, const float* N_d, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

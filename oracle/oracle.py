@@ -345,3 +345,19 @@ def icenuc_f23(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, 
                                      (C.c_void_p * 7)(*[_ptr(out[k]) for k in F23_OUT]), C.c_int(int(bound)))
     assert st == 0
     return out
+
+
+ALT_2M = {"acnv_KK2000": 0, "acnv_B1994": 1, "acnv_TC1980": 2, "acnv_LD2004": 3, "accr_KK2000": 4, "accr_B1994": 5, "accr_TC1980": 6}
+
+
+def alt_2m(params, what, q_lcl, q_rai=None, rho=None, N_d=None, smooth_transition=False):
+    """CM2.conv_q_lcl_to_q_rai / accretion of the alternative 2-moment closures (CM2:920-1002)."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    n = np.asarray(q_lcl).shape[0]
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dtype)
+    q_lcl, q_rai, rho, N_d = c(q_lcl), c(q_rai), c(rho), c(N_d)
+    out = np.empty(n, dtype)
+    st = getattr(lib(), f"oracle_2m_alt_{_suf(dtype)}")(C.byref(params), C.c_int(ALT_2M[what]), C.c_int(int(smooth_transition)), C.c_int64(n),
+                                                       _ptr(q_lcl), _ptr(q_rai), _ptr(rho), _ptr(N_d), _ptr(out))
+    assert st == 0
+    return out

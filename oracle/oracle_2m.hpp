@@ -419,4 +419,43 @@ inline Warm2MOut<FT> bmt2m_warm(const typename PT<FT>::params_2m_warm& p, FT rho
     return warm_rain_tendencies_2m<FT>(p, T, q_tot, q_lcl, q_rai, FT(0), rho, n_lcl, n_rai);
 }
 
+// ---- alternative closures: CM2.conv_q_lcl_to_q_rai / accretion for KK2000, B1994, TC1980, LD2004     CM2:920-1002
+template <class FT, class A> inline FT alt_2m(const A& p, int what, bool smooth, FT q_lcl, FT q_rai, FT rho, FT N_d) {
+    switch (what) {
+        case 0: { q_lcl = jmax(FT(0), q_lcl); return FT(p.kk_acnv_A) * pow_(q_lcl, FT(p.kk_acnv_a)) * pow_(N_d, FT(p.kk_acnv_b)) * pow_(rho, FT(p.kk_acnv_c)); }
+        case 1: {
+            q_lcl = jmax(FT(0), q_lcl);
+            FT d;
+            if (smooth) {
+                FT lo = logistic_function<FT>(N_d, FT(p.b_acnv_N_0), FT(p.b_acnv_k));
+                FT hi = 1 - lo;
+                d = lo * FT(p.b_acnv_d_low) + hi * FT(p.b_acnv_d_high);
+            } else d = (N_d >= FT(p.b_acnv_N_0)) ? FT(p.b_acnv_d_low) : FT(p.b_acnv_d_high);
+            return FT(p.b_acnv_C) * pow_(d, FT(p.b_acnv_a)) * pow_(FT(q_lcl * rho), FT(p.b_acnv_b)) * pow_(N_d, FT(p.b_acnv_c)) / rho;
+        }
+        case 2: {
+            q_lcl = jmax(FT(0), q_lcl);
+            FT thr = FT(p.tc_acnv_m0_liq_coeff) * N_d / rho * pow_(FT(p.tc_acnv_r_0), FT(p.tc_acnv_me_liq));
+            FT o = smooth ? logistic_function<FT>(q_lcl, thr, FT(p.tc_acnv_k)) : FT((q_lcl - thr > FT(0)) ? 1 : 0);
+            return FT(p.tc_acnv_D) * pow_(q_lcl, FT(p.tc_acnv_a)) * pow_(N_d, FT(p.tc_acnv_b)) * o;
+        }
+        case 3: {
+            if (q_lcl <= eps_2M<FT>()) return FT(0);
+            FT r_vol = cbrt_(3 * q_lcl * rho / 4 / pi<FT>() / FT(p.ld_rho_w) / N_d) * 1000000;
+            FT b6 = cbrt_((r_vol + 3) / r_vol);
+            FT b2 = b6 * b6;
+            FT E = FT(p.ld_E_0) * (b2 * b2 * b2);
+            FT R6 = b6 * r_vol;
+            FT R6C = FT(p.ld_R_6C_0) / cbrt_(sqrt_(FT(q_lcl * rho))) / sqrt_(R6);
+            FT o = smooth ? logistic_function<FT>(R6, R6C, FT(p.ld_k)) : FT((R6 - R6C > FT(0)) ? 1 : 0);
+            FT L = q_lcl * rho;
+            return E * (L * L * L) / N_d / rho * o;
+        }
+        case 4: { q_lcl = jmax(FT(0), q_lcl); q_rai = jmax(FT(0), q_rai); return FT(p.kk_accr_A) * pow_(FT(q_lcl * q_rai), FT(p.kk_accr_a)) * pow_(rho, FT(p.kk_accr_b)); }
+        case 5: { q_lcl = jmax(FT(0), q_lcl); q_rai = jmax(FT(0), q_rai); return FT(p.b_accr_A) * q_lcl * rho * q_rai; }
+        case 6: { q_lcl = jmax(FT(0), q_lcl); q_rai = jmax(FT(0), q_rai); return FT(p.tc_accr_A) * q_lcl * q_rai; }
+        default: return FT(0);
+    }
+}
+
 }  // namespace orc

@@ -449,6 +449,22 @@ int oracle_icenuc_f23_f64(const cumicro_params_p3_f64* p, int64_t n, const doubl
     return 0;
 }
 
+// ---- alternative 2-moment closures (KK2000, B1994, TC1980, LD2004)                       CM2:920-1002
+}  // extern "C"
+template <class FT, class PB> static void alt2m_cols(const PB* p, int what, int smooth, int64_t n, const FT* q_lcl, const FT* q_rai, const FT* rho, const FT* N_d, FT* out) {
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = alt_2m<FT>(*p, what, smooth != 0, q_lcl[i], q_rai ? q_rai[i] : FT(0), rho ? rho[i] : FT(1), N_d ? N_d[i] : FT(1));
+}
+extern "C" {
+int oracle_2m_alt_f64(const cumicro_params_2m_alt_f64* p, int what, int smooth, int64_t n, const double* q_lcl, const double* q_rai, const double* rho, const double* N_d, double* out) {
+    alt2m_cols<double>(p, what, smooth, n, q_lcl, q_rai, rho, N_d, out);
+    return 0;
+}
+int oracle_2m_alt_f32(const cumicro_params_2m_alt_f32* p, int what, int smooth, int64_t n, const float* q_lcl, const float* q_rai, const float* rho, const float* N_d, float* out) {
+    alt2m_cols<float>(p, what, smooth, n, q_lcl, q_rai, rho, N_d, out);
+    return 0;
+}
+
 // ---- 0-moment scheme: BMT:658-680 -> CM0.remove_precipitation (src/Microphysics0M.jl:35-46), native FT arithmetic
 }  // extern "C"
 template <class FT, class PB> static void bmt0m_cols(const PB* p, int64_t n, const FT* q_lcl, const FT* q_icl, const FT* q_vap_sat, FT* out) {

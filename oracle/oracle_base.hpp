@@ -112,6 +112,10 @@ template <class FT> inline FT pi() { return FT(3.1415926535897932384626433832795
 // ---- Utilities.jl -----------------------------------------------------------
 // UT.ϵ_numerics(FT) = cbrt(floatmin(FT))                         UT:318
 template <class FT> inline FT eps_numerics() { return cbrt_(std::numeric_limits<FT>::min()); }
+template <> inline double eps_numerics<double>() {
+    return f32_thresholds() ? double(std::cbrt(std::numeric_limits<float>::min())) : std::cbrt(std::numeric_limits<double>::min());
+}
+template <> inline Tr eps_numerics<Tr>() { return Tr(eps_numerics<double>()); }
 // UT.ϵ_numerics_2M_M / _2M_N / _P3_B = eps(FT)                   UT:325,332,340
 template <class FT> inline FT eps_2M() { return eps<FT>(); }
 // UT.clamp_to_nonneg                                             UT:296

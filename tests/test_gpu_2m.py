@@ -308,3 +308,96 @@ def test_full_size_properties_2pow24(built, cuda):
     assert torch.equal(dq_l, a["dq_lcl_dt"][:m]) and torch.equal(dq_r, a["dq_rai_dt"][:m])
     assert torch.equal(L["acnv_dq_lcl"], -L["acnv_dq_rai"]) and torch.equal(L["accr_dq_lcl"], -L["accr_dq_rai"])
     assert bool((L["evap_dq_rai"] <= 0).all()) and bool((L["rai_selfcol"] <= 0).all())
+
+
+# ---- alternative closures KK2000 / B1994 / TC1980 / LD2004 (CM2:920-1002) ---------------------------------------
+def _alt_call(built, scheme, name, cols, smooth=False):
+    CM2 = built.CM2
+    if name.startswith("acnv"):
+        args = (cols["q_lcl"], cols["rho"], cols["N_d"]) + ((True,) if smooth else ())
+        return CM2.conv_q_lcl_to_q_rai(scheme, *args)
+    if name.endswith("TC1980"):
+        return CM2.accretion(scheme, cols["q_lcl"], cols["q_rai"])
+    return CM2.accretion(scheme, cols["q_lcl"], cols["q_rai"], cols["rho"])
+
+
+def _alt_oracle(orc, blk, name, st, smooth=False):
+    if name.startswith("acnv"):
+        return orc.alt_2m(blk, name, q_lcl=st["q_lcl"], rho=st["rho"], N_d=st["N_d"], smooth_transition=smooth)
+    return orc.alt_2m(blk, name, q_lcl=st["q_lcl"], q_rai=st["q_rai"], rho=st["rho"])
+
+
+def test_alternative_closures_goldens_through_the_gpu(built, cuda):
+    """test/gpu_tests.jl:795-818 run through the C-ABI: ten identical points, Float64 and Float32."""
+    import torch
+    g = G["alt_closures"]
+    for FT, tol in ((np.float64, 1e-13), (np.float32, 3.4e-4)):   # Float32: the reference's own ≈ (rtol = sqrt(eps(Float32)))
+        cols = {k: torch.full((10,), v, dtype=torch.float64 if FT == np.float64 else torch.float32, device=cuda) for k, v in g["state"].items()}
+        for name in ("acnv_KK2000", "acnv_B1994", "acnv_TC1980", "acnv_LD2004", "accr_KK2000", "accr_B1994", "accr_TC1980"):
+            scheme = getattr(built.CMP, name.split("_")[1])(FT)
+            out = _alt_call(built, scheme, name, cols).cpu().numpy()
+            val, rtol, where = g[name]
+            assert np.all(out == out[0]), name
+            assert abs(out[0] / val - 1) <= max(rtol if rtol > 1e-7 else 0.0, tol), (name, out[0], val, where)
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_alternative_closures_parity(built, orc, cuda, smooth):
+    """Seeded columns through every closure vs the oracle: <= 1e-12 relative in Float64, <= 4 Float32 ULP of the true
+    value of the Float32 method, identical zero pattern (thresholds of B1994 / TC1980 / LD2004, q_lcl <= eps gate)."""
+    import torch
+    from cumicro.testing import assert_f32_method
+    n = 1 << 16
+    rng = np.random.Generator(np.random.PCG64(4321))
+    st = dict(q_lcl=10.0 ** rng.uniform(-7, -2, n), q_rai=10.0 ** rng.uniform(-8, -2.5, n), rho=rng.uniform(0.3, 1.3, n),
+              N_d=10.0 ** rng.uniform(6.5, 9.5, n))
+    st["q_lcl"][::97] = 0.0
+    st["q_lcl"][1::97] = -1e-9
+    st["q_lcl"][2::97] = 1e-17       # below eps(Float64): LD2004's gate
+    st["q_rai"][3::97] = -1e-7
+    names = [k for k in orc.ALT_2M if not (smooth and not k.startswith("acnv"))]
+    cols = {k: torch.from_numpy(v).to(cuda) for k, v in st.items()}
+    st32 = {k: v.astype(np.float32) for k, v in st.items()}
+    cols32 = {k: torch.from_numpy(v).to(cuda) for k, v in st32.items()}
+    wide32 = {k: v.astype(np.float64) for k, v in st32.items()}
+    for name in names:
+        if smooth and name == "acnv_KK2000":
+            continue
+        ctor = getattr(built.CMP, name.split("_")[1])
+        got = _alt_call(built, ctor(np.float64), name, cols, smooth).cpu().numpy()
+        ref = _alt_oracle(orc, ctor(np.float64).block, name, st, smooth)
+        assert np.array_equal(got == 0, ref == 0), (name, "zero pattern", int(np.sum((got == 0) != (ref == 0))))
+        assert np.array_equal(np.isfinite(got), np.isfinite(ref)), name
+        nz = (ref != 0) & np.isfinite(ref) & (np.abs(ref) > 1e-290)
+        rel = np.abs(got[nz] / ref[nz] - 1)
+        assert rel.max() <= 1e-12, (name, smooth, rel.max())
+        if name != "acnv_LD2004" and not smooth:
+            assert (ref != 0).sum() > n // 4, name
+        # Float32 method: columns and parameters in Float32, judged against its true value
+        got32 = _alt_call(built, ctor(np.float32), name, cols32, smooth).cpu().numpy()
+        blk32 = ctor(np.float32).block
+        ref32 = _alt_oracle(orc, blk32, name, st32, smooth)
+        with orc.f32_thresholds():
+            truth = _alt_oracle(orc, built.CMP.widen(blk32), name, wide32, smooth)
+        # the Float32 reference under/overflows where the exact value is still representable (C·(qρ)^4.7·N^-3.3):
+        # judge the zero pattern against the true value's own Float32 rounding
+        ok = np.isfinite(ref32) & (np.abs(truth) > 1e-30) & (np.abs(truth) < 1e30) | (truth == 0)
+        assert_f32_method(name, got32[ok], truth.astype(np.float32)[ok], truth[ok])
+
+
+def test_alternative_closures_api_errors(built, cuda):
+    import torch
+    q = torch.full((8,), 1e-3, dtype=torch.float64, device=cuda)
+    with pytest.raises(TypeError):
+        built.CM2.accretion(built.CMP.TC1980(np.float64), q, q, q)          # TC1980 takes no density
+    with pytest.raises(TypeError):
+        built.CM2.accretion(built.CMP.KK2000(np.float64), q, q)             # KK2000 needs it
+    with pytest.raises(TypeError):
+        built.CM2.accretion(built.CMP.LD2004(np.float64), q, q, q)          # no such method in the reference
+    with pytest.raises(TypeError):
+        built.CM2.conv_q_lcl_to_q_rai(built.CMP.KK2000(np.float32), q, q, q)  # Float32 parameters, Float64 columns
+    lib = built._abi.load()
+    blk = built.CMP.KK2000(np.float64).block
+    st = lib.cumicro_2m_alt_f64(C.byref(blk), C.c_int(9), C.c_int(0), C.c_int64(8), C.c_void_p(q.data_ptr()), None, C.c_void_p(q.data_ptr()),
+                                C.c_void_p(q.data_ptr()), C.c_void_p(q.data_ptr()), None)
+    assert st < 0 and b"unknown closure" in lib.cumicro_last_error()

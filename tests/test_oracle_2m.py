@@ -114,3 +114,41 @@ def test_f32_restatement_tracks_f64(built, orc):
         a, b = o32[k].astype(np.float64), o64[k]
         scale = np.maximum(np.abs(b), np.abs(b).mean())
         assert np.median(np.abs(a - b) / scale) < 1e-5
+
+
+def _alt_cols(name, s, FT):
+    one = lambda v: np.array([v], dtype=FT)
+    if name.startswith("acnv"):
+        return dict(q_lcl=one(s["q_lcl"]), rho=one(s["rho"]), N_d=one(s["N_d"]))
+    return dict(q_lcl=one(s["q_lcl"]), q_rai=one(s["q_rai"]), rho=one(s["rho"]))
+
+
+def test_alternative_closures_goldens(built, orc):
+    """KK2000 / B1994 / TC1980 / LD2004 autoconversion and accretion literals (test/gpu_tests.jl:795-818)."""
+    g = G["alt_closures"]
+    blk = built.CMP.KK2000(np.float64).block
+    for name in orc.ALT_2M:
+        val, rtol, where = g[name]
+        got = orc.alt_2m(blk, name, **_alt_cols(name, g["state"], np.float64))[0]
+        assert abs(got / val - 1) <= rtol, (name, got, val, where)
+        if rtol < 1e-7:   # the 16-digit literals are reproduced to rounding
+            assert abs(got / val - 1) < 1e-14, (name, got, val)
+    blk32 = built.CMP.KK2000(np.float32).block
+    for name in orc.ALT_2M:
+        val = g[name][0]
+        got = orc.alt_2m(blk32, name, **_alt_cols(name, g["state"], np.float32))[0]
+        assert got.dtype == np.float32 and abs(got / val - 1) < 2e-5, (name, got, val)
+
+
+def test_alternative_closures_smooth_transition_limits(built, orc):
+    """The smooth thresholds approach the sharp ones far from the threshold and stay between 0 and the sharp rate
+    (test/microphysics2M_tests.jl:118-192 checks the same property)."""
+    blk = built.CMP.B1994(np.float64).block
+    rho, q = np.full(4, 1.0), np.full(4, 1e-3)
+    for name, N_far in (("acnv_B1994", np.array([1e6, 1e7, 5e9, 1e10])), ("acnv_TC1980", np.array([1e6, 1e7, 1e12, 1e13]))):
+        sharp = orc.alt_2m(blk, name, q_lcl=q, rho=rho, N_d=N_far)
+        smooth = orc.alt_2m(blk, name, q_lcl=q, rho=rho, N_d=N_far, smooth_transition=True)
+        assert np.allclose(smooth, sharp, rtol=1e-3, atol=1e-300), (name, smooth, sharp)
+    q = np.array([0.0, 1e-18, 1e-7, 1e-3])
+    out = orc.alt_2m(blk, "acnv_LD2004", q_lcl=q, rho=rho, N_d=np.full(4, 1e8))
+    assert out[0] == 0 and out[1] == 0 and out[3] > 0
