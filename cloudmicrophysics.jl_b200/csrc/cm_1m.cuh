@@ -52,6 +52,9 @@ template <class FT> struct OneMK {
     FT prescribed_nd_inv;    // 1/(τ (Nc/1e8)^α)
     FT ice_med;              // cloud-ice me+Δm (WithSupersaturation)
     FT frost_c, frost_r0;    // 4 π D_vapor; FT(1e-6)
+    // IEEE reciprocals of uniform divisors whose numerators are exact zeros at gated-off points (divr_, cm_math.cuh)
+    FT rain_inv_k, snow_inv_k, rain_inv_tau, snow_inv_tau;
+    int linearize_fast_div;  // q_min > 0: the divisors max(q_min, q) of BMT._linearize are positive
 };
 
 template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::params_1m& p, bool method_is_f32 = false) {
@@ -117,6 +120,9 @@ template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::pa
     k.prescribed_nd_inv = FT(1) / (p.pp.rain_acnv_tau * std::pow(p.pp.rain_acnv_Nc / FT(100000000), p.pp.rain_acnv_alpha));
     k.ice_med = p.cloud_ice.mass.me + p.cloud_ice.mass.dm;
     k.frost_c = 4 * pi * p.aps.D_vapor;
+    k.rain_inv_k = FT(1) / p.pp.rain_acnv_k; k.snow_inv_k = FT(1) / p.pp.snow_acnv_k;
+    k.rain_inv_tau = FT(1) / p.pp.rain_acnv_tau; k.snow_inv_tau = FT(1) / p.pp.snow_acnv_tau;
+    k.linearize_fast_div = p.tps.q_min >= FT(1e-300);
     return k;
 }
 
@@ -135,12 +141,12 @@ CM_DEV float log1pexp_(float x) {
 }
 
 // CO.logistic_function_integral                                     CO:157-173
-template <class FT> CM_DEV FT logistic_function_integral(FT e, FT x, FT x_0, FT inv_x0_safe, FT k, FT trnslt) {
+template <class FT> CM_DEV FT logistic_function_integral(FT e, FT x, FT x_0, FT inv_x0_safe, FT k, FT inv_k, FT trnslt) {
     x = fmax_(FT(0), x);
     const FT x_safe = fmax_(x, e);
     const FT x0_safe = fmax_(x_0, e);
     const FT kt = k * (x_safe * inv_x0_safe - FT(1) + trnslt);
-    const FT result = (log1pexp_(kt) / k - trnslt) * x0_safe;
+    const FT result = (divr_(log1pexp_(kt), k, inv_k) - trnslt) * x0_safe;
     return (x < e) ? FT(0) : ((x_0 < e) ? x : result);
 }
 
@@ -234,14 +240,16 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     // ---- autoconversion                                               CM1:352-364, 412-446
     if (o.rain_autoconversion == CUMICRO_1M_RAIN_ACNV_KESSLER)
         r.s[S1M_ACNV_LCL_RAI] =
-            logistic_function_integral<FT>(e, q_lcl, pp.rain_acnv_q_threshold, k.rain_inv_q_thr, pp.rain_acnv_k, k.rain_trnslt) / pp.rain_acnv_tau;
+            divr_(logistic_function_integral<FT>(e, q_lcl, pp.rain_acnv_q_threshold, k.rain_inv_q_thr, pp.rain_acnv_k, k.rain_inv_k, k.rain_trnslt),
+                  pp.rain_acnv_tau, k.rain_inv_tau);
     else if (o.rain_autoconversion == CUMICRO_1M_RAIN_ACNV_PRESCRIBED_ND)
         r.s[S1M_ACNV_LCL_RAI] = q_lcl * k.prescribed_nd_inv;
     else
         r.s[S1M_ACNV_LCL_RAI] = FT(0);
     if (o.snow_autoconversion == CUMICRO_1M_SNOW_ACNV_NO_SUPERSAT)
         r.s[S1M_ACNV_ICL_SNO] =
-            logistic_function_integral<FT>(e, q_icl, pp.snow_acnv_q_threshold, k.snow_inv_q_thr, pp.snow_acnv_k, k.snow_trnslt) / pp.snow_acnv_tau;
+            divr_(logistic_function_integral<FT>(e, q_icl, pp.snow_acnv_q_threshold, k.snow_inv_q_thr, pp.snow_acnv_k, k.snow_inv_k, k.snow_trnslt),
+                  pp.snow_acnv_tau, k.snow_inv_tau);
     else if (o.snow_autoconversion == CUMICRO_1M_SNOW_ACNV_WITH_SUPERSAT) {
         const FT r_is = pp.snow_acnv_r_ice_snow;
         const FT x = r_is * rcp_(lam_i);
@@ -337,84 +345,102 @@ template <class FT> CM_DEV void aggregate_tendencies_1m(const Src1M<FT>& r, FT (
 // subtract nearly equal products.)
 template <class FT>
 CM_DEV void linearized_implicit_step_1m(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k, FT rho, FT T,
-                                        FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, FT dt, FT (&out)[4]) {
+                                        FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, FT inv_dt, FT (&out)[4]) {
     const Src1M<FT> r = microphysics_source_terms_1m<FT>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno);
     const FT* s = r.s;
     const FT q_min = tk.q_min;
     const FT d_lcl = fmax_(q_min, q_lcl), d_icl = fmax_(q_min, q_icl), d_rai = fmax_(q_min, q_rai), d_sno = fmax_(q_min, q_sno);
+    // 19 quotients over 4 divisors: one correctly rounded reciprocal per divisor (cm_math.cuh, divr_); q_min = 0 (a legal
+    // parameter value) can make a divisor zero — then the IEEE division, decided on the host
+    const bool fast = k.linearize_fast_div;
+    const FT r_lcl = fast ? rcp_cr_(d_lcl) : FT(0), r_icl = fast ? rcp_cr_(d_icl) : FT(0), r_rai = fast ? rcp_cr_(d_rai) : FT(0),
+             r_sno = fast ? rcp_cr_(d_sno) : FT(0);
+    auto over = [fast](FT x, FT d, FT r) { return fast ? divr_(x, d, r) : div_(x, d); };
     FT M11 = 0, M12 = 0, M22 = 0, M31 = 0, M33 = 0, M34 = 0, M41 = 0, M42 = 0, M43 = 0, M44 = 0, e1 = 0, e2 = 0, e4 = 0;
     FT D;
     bool src;
-    D = div_(s[S1M_PHASE_VAP_LCL], d_lcl); src = s[S1M_PHASE_VAP_LCL] >= FT(0);
+    D = over(s[S1M_PHASE_VAP_LCL], d_lcl, r_lcl); src = s[S1M_PHASE_VAP_LCL] >= FT(0);
     e1 += src ? s[S1M_PHASE_VAP_LCL] : FT(0); M11 += src ? FT(0) : D;
-    D = div_(s[S1M_PHASE_VAP_ICL], d_icl); src = s[S1M_PHASE_VAP_ICL] >= FT(0);
+    D = over(s[S1M_PHASE_VAP_ICL], d_icl, r_icl); src = s[S1M_PHASE_VAP_ICL] >= FT(0);
     e2 += src ? s[S1M_PHASE_VAP_ICL] : FT(0); M22 += src ? FT(0) : D;
-    D = div_(s[S1M_MELT_ICL_LCL], d_icl); M22 -= D; M12 += D;
-    D = div_(s[S1M_ACNV_LCL_RAI], d_lcl); M11 -= D; M31 += D;
-    D = div_(s[S1M_ACNV_ICL_SNO], d_icl); M22 -= D; M42 += D;
-    D = div_(s[S1M_ACCR_LCL_RAI], d_lcl); M11 -= D; M31 += D;
-    const FT D_cold = div_(s[S1M_ACCR_LCL_SNO_COLD], d_lcl);
-    const FT D_warm = div_(s[S1M_ACCR_LCL_SNO_WARM], d_lcl);
+    D = over(s[S1M_MELT_ICL_LCL], d_icl, r_icl); M22 -= D; M12 += D;
+    D = over(s[S1M_ACNV_LCL_RAI], d_lcl, r_lcl); M11 -= D; M31 += D;
+    D = over(s[S1M_ACNV_ICL_SNO], d_icl, r_icl); M22 -= D; M42 += D;
+    D = over(s[S1M_ACCR_LCL_RAI], d_lcl, r_lcl); M11 -= D; M31 += D;
+    const FT D_cold = over(s[S1M_ACCR_LCL_SNO_COLD], d_lcl, r_lcl);
+    const FT D_warm = over(s[S1M_ACCR_LCL_SNO_WARM], d_lcl, r_lcl);
     M11 -= D_cold + D_warm; M31 += D_warm; M41 += D_cold;
-    D = div_(s[S1M_ACCR_MELT_LCL_SNO], d_sno); M44 -= D; M34 += D;
-    D = div_(s[S1M_ACCR_ICL_RAI], d_icl); M22 -= D; M42 += D;
-    D = div_(s[S1M_ACCR_ICL_SNO], d_icl); M22 -= D; M42 += D;
-    D = div_(s[S1M_ACCR_FREEZE_ICL_RAI], d_rai); M33 -= D; M43 += D;
-    D = div_(s[S1M_ACCR_RAI_SNO_WARM], d_sno); M44 -= D; M34 += D;
-    D = div_(s[S1M_ACCR_MELT_RAI_SNO], d_sno); M44 -= D; M34 += D;
-    D = div_(s[S1M_ACCR_RAI_SNO_COLD], d_rai); M33 -= D; M43 += D;
-    D = div_(-s[S1M_PHASE_VAP_RAI], d_rai); M33 -= D;
-    D = div_(s[S1M_PHASE_VAP_SNO], d_sno); src = s[S1M_PHASE_VAP_SNO] >= FT(0);
+    D = over(s[S1M_ACCR_MELT_LCL_SNO], d_sno, r_sno); M44 -= D; M34 += D;
+    D = over(s[S1M_ACCR_ICL_RAI], d_icl, r_icl); M22 -= D; M42 += D;
+    D = over(s[S1M_ACCR_ICL_SNO], d_icl, r_icl); M22 -= D; M42 += D;
+    D = over(s[S1M_ACCR_FREEZE_ICL_RAI], d_rai, r_rai); M33 -= D; M43 += D;
+    D = over(s[S1M_ACCR_RAI_SNO_WARM], d_sno, r_sno); M44 -= D; M34 += D;
+    D = over(s[S1M_ACCR_MELT_RAI_SNO], d_sno, r_sno); M44 -= D; M34 += D;
+    D = over(s[S1M_ACCR_RAI_SNO_COLD], d_rai, r_rai); M33 -= D; M43 += D;
+    D = over(-s[S1M_PHASE_VAP_RAI], d_rai, r_rai); M33 -= D;
+    D = over(s[S1M_PHASE_VAP_SNO], d_sno, r_sno); src = s[S1M_PHASE_VAP_SNO] >= FT(0);
     e4 += src ? s[S1M_PHASE_VAP_SNO] : FT(0); M44 += src ? FT(0) : D;
-    D = div_(s[S1M_MELT_SNO_RAI], d_sno); M44 -= D; M34 += D;
+    D = over(s[S1M_MELT_SNO_RAI], d_sno, r_sno); M44 -= D; M34 += D;
 
-    const FT inv_dt = div_(FT(1), dt);
+    // inv_dt = RN(1/dt), from the host (uniform)
     // q_sat over liquid / ice at the (unclamped) state                       BMT:409-412
     const TempState<FT> ts = temp_state(tk, T);
     const FT rRT = rho * tk.R_v * T;
     const FT q_sat_min = fmin_(div_(p_sat_liq(tk, ts), rRT), div_(p_sat_ice(tk, ts), rRT));
     const FT q_v = q_tot - q_lcl - q_icl - q_rai - q_sno;
-    const FT alpha = fmin_(FT(1), div_(fmax_(FT(0), q_v - q_sat_min) * inv_dt, fmax_(e1 + e2 + e4, tk.eps)));
+    const FT e_sum = fmax_(e1 + e2 + e4, tk.eps);   // >= eps > 0; the numerator is an exact zero wherever the air is subsaturated
+    const FT alpha = fmin_(FT(1), divr_(fmax_(FT(0), q_v - q_sat_min) * inv_dt, e_sum, rcp_cr_(e_sum)));
     const FT a11 = inv_dt - M11, a12 = -M12, a22 = inv_dt - M22, a31 = -M31, a33 = inv_dt - M33, a34 = -M34, a41 = -M41, a42 = -M42,
              a43 = -M43, a44 = inv_dt - M44;
     const FT b1 = alpha * e1 + inv_dt * q_lcl;
     const FT b2 = alpha * e2 + inv_dt * q_icl;
     const FT b3 = inv_dt * q_rai;
     const FT b4 = alpha * e4 + inv_dt * q_sno;
+    // det12 >= 1/dt² > 0 and det > 0 (BMT:449-450): positive normal divisors, two quotients each
     const FT det12 = a11 * a22;
-    const FT q_lcl_new = div_(b1 * a22 - a12 * b2, det12);
-    const FT q_icl_new = div_(a11 * b2, det12);
+    const FT r_det12 = rcp_cr_(det12);
+    const FT q_lcl_new = divr_(b1 * a22 - a12 * b2, det12, r_det12);
+    const FT q_icl_new = divr_(a11 * b2, det12, r_det12);
     const FT r3 = fma_(-a31, q_lcl_new, b3);
     const FT r4 = fma_(-a41, q_lcl_new, fma_(-a42, q_icl_new, b4));
     const FT det = fma_(-a34, a43, a33 * a44);
-    const FT q_rai_new = div_(r3 * a44 - a34 * r4, det);
-    const FT q_sno_new = div_(a33 * r4 - r3 * a43, det);
+    const FT r_det = rcp_cr_(det);
+    const FT q_rai_new = divr_(r3 * a44 - a34 * r4, det, r_det);
+    const FT q_sno_new = divr_(a33 * r4 - r3 * a43, det, r_det);
     out[0] = (q_lcl_new - q_lcl) * inv_dt;
     out[1] = (q_icl_new - q_icl) * inv_dt;
     out[2] = (q_rai_new - q_rai) * inv_dt;
     out[3] = (q_sno_new - q_sno) * inv_dt;
 }
 
+// Δt, Δt/nsub and their IEEE reciprocals (host side: uniform over the grid)
+template <class FT> struct LinAvgK { FT dt, inv_dt, dt_sub, inv_dt_sub; };
+template <class FT> __host__ inline LinAvgK<FT> make_linavg_k(FT dt, int nsub) {
+    LinAvgK<FT> lk;
+    lk.dt = dt; lk.inv_dt = FT(1) / dt; lk.dt_sub = dt / FT(nsub); lk.inv_dt_sub = FT(1) / lk.dt_sub;
+    return lk;
+}
+
 // BMT.bulk_microphysics_tendencies(::LinearizedAverage, ...)                 BMT:572-632
 template <class FT>
 CM_DEV void bmt1m_linearized_average(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k, FT rho, FT T,
-                                     FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, FT dt, int nsub, FT Lv_over_cp, FT Ls_over_cp,
-                                     FT (&out)[4]) {
+                                     FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, const LinAvgK<FT>& lk, int nsub, FT Lv_over_cp,
+                                     FT Ls_over_cp, FT (&out)[4]) {
     const FT q0[4] = {q_lcl, q_icl, q_rai, q_sno};
-    const FT dt_sub = div_(dt, FT(nsub));
+    const FT dt_sub = lk.dt_sub;
     for (int it = 0; it < nsub; ++it) {
         FT rt[4];
-        linearized_implicit_step_1m<FT>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, dt_sub, rt);
+        linearized_implicit_step_1m<FT>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, lk.inv_dt_sub, rt);
         q_lcl += rt[0] * dt_sub;
         q_icl += rt[1] * dt_sub;
         q_rai += rt[2] * dt_sub;
         q_sno += rt[3] * dt_sub;
         T += (Lv_over_cp * (rt[0] + rt[2]) + Ls_over_cp * (rt[1] + rt[3])) * dt_sub;
     }
-    out[0] = div_(q_lcl - q0[0], dt);
-    out[1] = div_(q_icl - q0[1], dt);
-    out[2] = div_(q_rai - q0[2], dt);
-    out[3] = div_(q_sno - q0[3], dt);
+    out[0] = divr_(q_lcl - q0[0], lk.dt, lk.inv_dt);   // differences are exact zeros where nothing happens
+    out[1] = divr_(q_icl - q0[1], lk.dt, lk.inv_dt);
+    out[2] = divr_(q_rai - q0[2], lk.dt, lk.inv_dt);
+    out[3] = divr_(q_sno - q0[3], lk.dt, lk.inv_dt);
 }
 
 // ---- terminal velocities of the 1-moment / non-equilibrium schemes -------------------------------

@@ -159,6 +159,25 @@ CM_HD double rcp_(double x) {
     const double t = fma(e, e, e);
     return fma(r, t, r);
 }
+// ---- IEEE-quality division through a shared reciprocal ----------------------------------------
+// CUDA's a / b leaves its ~13-instruction fast path for a ~100-instruction subroutine whenever the NUMERATOR is zero (or below
+// 2^-969) — and gated-off source terms are exact zeros.  Where several quotients share a divisor (the four max(q_min, q) of
+// BMT._linearize, the two determinants of the 2x2 solves) one reciprocal r = RN(1/d) serves all of them:
+//   q = RN(x r), rem = x - q d (exact, FMA), q' = RN(q + rem r) is the correctly rounded x / d (Markstein 1990, Thm 3.1;
+//   r itself is correctly rounded after one FMA correction of the <= 1 ulp rcp_, except for divisors with an all-ones
+//   significand, where the quotient can be 1 ulp off).  x = 0 gives 0 (the sign of a zero quotient is not preserved), no branch.
+// d must be positive, normal and finite.
+CM_HD double rcp_cr_(double d) {
+    const double r = rcp_(d);
+    return fma(r, fma(-d, r, 1.0), r);
+}
+CM_HD double divr_(double x, double d, double r) {
+    const double q = x * r;
+    return fma(fma(-q, d, x), r, q);
+}
+CM_HD float rcp_cr_(float d) { return 1.0f / d; }
+CM_HD float divr_(float x, float d, float) { return x / d; }
+
 // ---- square root: positive, normal, finite x; faithfully rounded (< 1 ulp), no special cases -------
 CM_HD double sqrtp_(double x) {
 #ifdef __CUDA_ARCH__

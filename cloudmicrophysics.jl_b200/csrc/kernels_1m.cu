@@ -49,10 +49,11 @@ struct OneMVerbose : OneMBase {
 };
 // BMT:572-632 — nsub linearised implicit substeps
 struct OneMLinAvg : OneMBase {
-    D dt, Lv_over_cp, Ls_over_cp;
+    LinAvgK<D> lk;
+    D Lv_over_cp, Ls_over_cp;
     int nsub;
     __device__ __forceinline__ void operator()(const D (&x)[7], D (&y)[4]) const {
-        bmt1m_linearized_average<D>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], dt, nsub, Lv_over_cp, Ls_over_cp, y);
+        bmt1m_linearized_average<D>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], lk, nsub, Lv_over_cp, Ls_over_cp, y);
     }
 };
 
@@ -99,7 +100,7 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
         if (!(dt > FT(0))) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: dt must be > 0");
         if (nsub < 1) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: nsub = %d must be >= 1", nsub);
         OneMLinAvg f = make_1m<FT, OneMLinAvg>(p);
-        f.dt = dt;
+        f.lk = make_linavg_k<D>((D)dt, nsub);
         f.nsub = nsub;
         f.Lv_over_cp = f.p.tps.LH_v0 / f.p.tps.cp_d;
         f.Ls_over_cp = f.p.tps.LH_s0 / f.p.tps.cp_d;

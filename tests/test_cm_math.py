@@ -80,3 +80,19 @@ def test_pow(lib):
         amp = abs(mp.mpf(float(b)) * mp.log(mp.mpf(float(a)))) + 1
         worst = max(worst, float(abs((mp.mpf(float(c)) - t) / t) / amp / mp.mpf(2) ** -52))
     assert worst < 2.0
+
+
+def test_division_through_the_shared_reciprocal_is_ieee(lib):
+    """divr_(x, d, rcp_cr_(d)) equals the IEEE quotient x / d bit for bit (Markstein), including x = 0 — the case CUDA's
+    own division sends to its slow path, and the reason the linearised 1-moment step uses this form."""
+    rng = np.random.default_rng(5)
+    n = 200000
+    d = np.concatenate([10 ** rng.uniform(-12, 8, n // 2), rng.uniform(1e-10, 1.0, n // 2)])
+    x = np.concatenate([rng.normal(size=n // 2) * 10 ** rng.uniform(-30, 5, n // 2), rng.uniform(-1e-3, 1e-3, n // 2)])
+    x[::50] = 0.0
+    y = np.empty_like(x)
+    lib.cmt_divr(x.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_long(n))
+    ref = x / d
+    assert np.all(y[x == 0] == 0)
+    assert np.mean(y == ref) > 0.9999, np.mean(y == ref)
+    assert np.max(np.abs(y - ref) / np.maximum(np.abs(ref), 1e-300)) < 2.3e-16

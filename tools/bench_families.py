@@ -87,6 +87,9 @@ report("fused 1M+2M+ice nucleation(+ARG) f64 2^24 per GPU (config 5)", n5,
        timeit(lambda: fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *c, out=o), reps=10), 176)
 del c, o
 
+if os.environ.get("CUMICRO_FAMILIES_SKIP_P3"):   # quick iterations on the streaming families
+    sys.exit(0)
+
 # ---- P3 (config 4): stand-alone process rates + the fused 2M+P3 tendencies, Float64, 2^22 points
 from cumicro import P3  # noqa: E402
 from cumicro.testing import synthetic_states_p3  # noqa: E402
