@@ -14,6 +14,8 @@ def __getattr__(name):  # torch-dependent modules are imported on first use
     lazy = {"BulkMicrophysicsTendencies": "BulkMicrophysicsTendencies", "BMT": "BulkMicrophysicsTendencies",
             "Microphysics2M": "Microphysics2M", "CM2": "Microphysics2M",
             "Microphysics1M": "Microphysics1M", "CM1": "Microphysics1M",
+            "MicrophysicsNonEq": "MicrophysicsNonEq", "CMNonEq": "MicrophysicsNonEq",
+            "CloudDiagnostics": "CloudDiagnostics", "CMD": "CloudDiagnostics",
             "AerosolActivation": "AerosolActivation", "AA": "AerosolActivation",
             "AerosolModel": "AerosolModel", "AM": "AerosolModel",
             "IceNucleation": "IceNucleation", "IN": "IceNucleation", "fused": "fused",

@@ -50,6 +50,26 @@ def bmt_1m(mode, mp, tps, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, Δt=None, n
     return res
 
 
+def source_terms_1m(mp, tps, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, which):
+    """The named subset ``which`` of the 18 source terms of ``BMT._microphysics_source_terms`` (BMT:141-217) and nothing
+    else: one launch of the Verbose kernel with every other output column NULL.  Inputs are clamped to >= 0 as at the
+    BMT call sites (BMT:146-151)."""
+    cols = [rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno]
+    suf, n, dev = check_columns(cols, NAMES)
+    block = CMP.pack_1m(mp, tps)
+    if not type(block).__name__.endswith(suf):
+        raise TypeError(f"parameter float type does not match the columns ({suf})")
+    unknown = set(which) - set(SRC_1M)
+    if unknown:
+        raise KeyError(f"unknown source terms {sorted(unknown)}")
+    src = [torch.empty_like(rho) if nm in which else None for nm in SRC_1M]
+    with torch.cuda.device(dev):
+        st = getattr(_abi.load(), f"cumicro_bmt1m_verbose_{suf}")(C.byref(block), C.c_int64(n), *[ptr(c) for c in cols],
+                                                                 ptr_table([None] * 4), ptr_table(src), stream_handle(dev))
+    _abi.check(st, "cumicro_bmt1m_verbose")
+    return Tendencies({nm: t for nm, t in zip(SRC_1M, src) if t is not None})
+
+
 def bmt_0m(mp, tps, T, q_lcl, q_icl, q_vap_sat=None, *, out=None):
     """BMT:658-680 -> Microphysics0M.remove_precipitation (src/Microphysics0M.jl:35-46):
     ``-max(0, q_lcl + q_icl - threshold)/τ_precip`` with threshold ``qc_0`` or ``S_0 q_vap_sat``, inputs clamped to >= 0.

@@ -85,7 +85,9 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
     if ((st = check_1m_options<FT>(p))) return st;
     if (out4 == nullptr) return cmh::fail(CUMICRO_E_NULL, "output pointer table is NULL");
     FT* o4[4] = {out4[0], out4[1], out4[2], out4[3]};
-    if ((st = require_outputs<FT, 4>(n, o4, 4))) return st;
+    // Verbose: any subset of the 4 + 18 columns (NULL = not wanted) — the stand-alone leaf methods of CM1 / MicrophysicsNonEq
+    // (NEQ:110-224, CM1:352-1139) are single source-term columns of this kernel
+    if ((st = require_outputs<FT, 4>(n, o4, mode == 1 ? 0 : 4))) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == 0) {
         return launch_pointwise<FT, 7, 4, OneMInst, 128, CUMICRO_1M_MINB, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");

@@ -421,6 +421,27 @@ int cumicro_2m_alt_f64(const cumicro_params_2m_alt_f64* p, int what, int smooth_
 int cumicro_2m_alt_f32(const cumicro_params_2m_alt_f32* p, int what, int smooth_transition, int64_t n, const float* q_lcl,
                        const float* q_rai, const float* rho, const float* N_d, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Cloud diagnostics (src/CloudDiagnostics.jl:30-187; reference tests test/cloud_diagnostics.jl:30-125)
+ *   cumicro_diag_2m_*:  radar_reflectivity_2M(sb, q_lcl, q_rai, N_lcl, N_rai, ρ_air) -> Z [dBZ] and
+ *                       effective_radius_2M(...) -> r_eff [m] from one pass over the five columns (either output may be NULL)
+ *   cumicro_diag_1m_*:  radar_reflectivity_1M(rain, q_rai, ρ_air) -> Z [dBZ]
+ *   cumicro_diag_reff_lh97_*: effective_radius_Liu_Hallet_97((; ρw), ρ_air, q_lcl, N_lcl, q_rai, N_rai); N_lcl, q_rai, N_rai
+ *                       NULL selects the three-argument method (N_lcl = 100, no rain).
+ * ------------------------------------------------------------------------- */
+int cumicro_diag_2m_f64(const cumicro_sb_pdf_c_f64* pdf_c, const cumicro_sb_pdf_r_f64* pdf_r, int64_t n, const double* q_lcl,
+                        const double* q_rai, const double* N_lcl, const double* N_rai, const double* rho, double* Z, double* r_eff,
+                        void* stream);
+int cumicro_diag_2m_f32(const cumicro_sb_pdf_c_f32* pdf_c, const cumicro_sb_pdf_r_f32* pdf_r, int64_t n, const float* q_lcl,
+                        const float* q_rai, const float* N_lcl, const float* N_rai, const float* rho, float* Z, float* r_eff,
+                        void* stream);
+int cumicro_diag_1m_f64(const cumicro_params_1m_f64* p, int64_t n, const double* q_rai, const double* rho, double* Z, void* stream);
+int cumicro_diag_1m_f32(const cumicro_params_1m_f32* p, int64_t n, const float* q_rai, const float* rho, float* Z, void* stream);
+int cumicro_diag_reff_lh97_f64(double rho_w, int64_t n, const double* rho, const double* q_lcl, const double* N_lcl, const double* q_rai,
+                               const double* N_rai, double* r_eff, void* stream);
+int cumicro_diag_reff_lh97_f32(float rho_w, int64_t n, const float* rho, const float* q_lcl, const float* N_lcl, const float* q_rai,
+                               const float* N_rai, float* r_eff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

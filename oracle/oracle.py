@@ -361,3 +361,32 @@ def alt_2m(params, what, q_lcl, q_rai=None, rho=None, N_d=None, smooth_transitio
                                                        _ptr(q_lcl), _ptr(q_rai), _ptr(rho), _ptr(N_d), _ptr(out))
     assert st == 0
     return out
+
+
+# ---- cloud diagnostics (src/CloudDiagnostics.jl) ---------------------------------------------------------------
+def diag_2m(pdf_c, pdf_r, q_lcl, q_rai, N_lcl, N_rai, rho):
+    """(radar_reflectivity_2M, effective_radius_2M) over arrays."""
+    dtype = np.float64 if type(pdf_c).__name__.endswith("f64") else np.float32
+    cols, n = _cols((q_lcl, q_rai, N_lcl, N_rai, rho), dtype)
+    Z, reff = np.empty(n, dtype), np.empty(n, dtype)
+    st = getattr(lib(), f"oracle_diag_2m_{_suf(dtype)}")(C.byref(pdf_c), C.byref(pdf_r), C.c_int64(n), *[_ptr(a) for a in cols], _ptr(Z), _ptr(reff))
+    assert st == 0
+    return Z, reff
+
+
+def diag_1m(params, q_rai, rho):
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    cols, n = _cols((q_rai, rho), dtype)
+    Z = np.empty(n, dtype)
+    assert getattr(lib(), f"oracle_diag_1m_{_suf(dtype)}")(C.byref(params), C.c_int64(n), _ptr(cols[0]), _ptr(cols[1]), _ptr(Z)) == 0
+    return Z
+
+
+def diag_reff_lh97(rho_w, rho, q_lcl, N_lcl=None, q_rai=None, N_rai=None, dtype=np.float64):
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dtype)
+    rho, q_lcl, N_lcl, q_rai, N_rai = c(rho), c(q_lcl), c(N_lcl), c(q_rai), c(N_rai)
+    out = np.empty(rho.shape[0], dtype)
+    crho = C.c_double(rho_w) if dtype == np.float64 else C.c_float(rho_w)
+    assert getattr(lib(), f"oracle_diag_reff_lh97_{_suf(dtype)}")(crho, C.c_int64(rho.shape[0]), _ptr(rho), _ptr(q_lcl), _ptr(N_lcl), _ptr(q_rai),
+                                                                  _ptr(N_rai), _ptr(out)) == 0
+    return out

@@ -5,6 +5,7 @@
 #include <omp.h>
 
 #include "oracle_p3.hpp"
+#include "oracle_diag.hpp"
 
 using namespace orc;
 
@@ -464,6 +465,30 @@ int oracle_2m_alt_f32(const cumicro_params_2m_alt_f32* p, int what, int smooth, 
     alt2m_cols<float>(p, what, smooth, n, q_lcl, q_rai, rho, N_d, out);
     return 0;
 }
+
+// ---- cloud diagnostics (src/CloudDiagnostics.jl)
+#define DEF_DIAG(SUF, FT)                                                                                                              \
+    int oracle_diag_2m_##SUF(const cumicro_sb_pdf_c_##SUF* pc, const cumicro_sb_pdf_r_##SUF* pr, int64_t n, const FT* q_lcl,            \
+                             const FT* q_rai, const FT* N_lcl, const FT* N_rai, const FT* rho, FT* Z, FT* reff) {                      \
+        for (int64_t i = 0; i < n; ++i) {                                                                                              \
+            if (Z) Z[i] = radar_reflectivity_2M<FT>(*pc, *pr, q_lcl[i], q_rai[i], N_lcl[i], N_rai[i], rho[i]);                         \
+            if (reff) reff[i] = effective_radius_2M<FT>(*pc, *pr, q_lcl[i], q_rai[i], N_lcl[i], N_rai[i], rho[i]);                     \
+        }                                                                                                                              \
+        return 0;                                                                                                                      \
+    }                                                                                                                                  \
+    int oracle_diag_1m_##SUF(const cumicro_params_1m_##SUF* p, int64_t n, const FT* q_rai, const FT* rho, FT* Z) {                     \
+        for (int64_t i = 0; i < n; ++i) Z[i] = radar_reflectivity_1M<FT>(*p, q_rai[i], rho[i]);                                        \
+        return 0;                                                                                                                      \
+    }                                                                                                                                  \
+    int oracle_diag_reff_lh97_##SUF(FT rho_w, int64_t n, const FT* rho, const FT* q_lcl, const FT* N_lcl, const FT* q_rai,             \
+                                    const FT* N_rai, FT* reff) {                                                                       \
+        for (int64_t i = 0; i < n; ++i)                                                                                                \
+            reff[i] = effective_radius_Liu_Hallet_97<FT>(rho_w, rho[i], q_lcl[i], N_lcl ? N_lcl[i] : FT(100), q_rai ? q_rai[i] : FT(0), \
+                                                         N_rai ? N_rai[i] : FT(0));                                                    \
+        return 0;                                                                                                                      \
+    }
+DEF_DIAG(f64, double)
+DEF_DIAG(f32, float)
 
 // ---- 0-moment scheme: BMT:658-680 -> CM0.remove_precipitation (src/Microphysics0M.jl:35-46), native FT arithmetic
 }  // extern "C"

@@ -207,3 +207,40 @@ def test_0m_bit_exact(built, orc, cuda, FT):
     got = BMT.bulk_microphysics_tendencies(BMT.Microphysics0Moment(), mp, tps, d(T), d(ql), d(qi), d(qvs))
     ref = orc.bmt0m(mp.precip, ql, qi, qvs)
     assert np.array_equal(got.dq_tot_dt.cpu().numpy(), ref) and (ref < 0).mean() > 0.3 and (ref == 0).mean() > 0.01
+
+
+def test_noneq_leaf_methods(built, orc, cuda):
+    """CMNonEq.conv_q_vap_to_q_lcl / conv_q_vap_to_q_icl as stand-alone array methods (NEQ:110-224): the reference's
+    literals (test/microphysics_noneq_tests.jl:84-88, rho = 0.8, T = 263, q_tot = 1.2 q_sat) and seeded columns vs the oracle."""
+    import json
+    import os
+    import torch
+    from cumicro.testing import psat_liq, psat_ice, synthetic_states_1m, assert_parity
+    CMP, NEQ = built.CMP, built.CMNonEq
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "m1_goldens.json")))["noneq"]
+    mp, tps = CMP.Microphysics1MParams(np.float64), CMP.ThermodynamicsParameters(np.float64)
+    rho, T = g["rho"], g["T"]
+    Rv = CMP.DEFAULTS["gas_constant_vapor"]
+    col = lambda v: torch.full((16,), v, dtype=torch.float64, device=cuda)
+    for fn, opt, psat, want in ((NEQ.conv_q_vap_to_q_lcl, CMP.CloudLiquidFormation(), psat_liq, g["cond"]),
+                                (NEQ.conv_q_vap_to_q_icl, CMP.ConstantTimescale(), psat_ice, g["dep"])):
+        micro = dict(q_tot=col(1.2 * psat(T) / (Rv * rho * T)), q_lcl=col(0.0), q_icl=col(0.0), q_rai=col(0.0), q_sno=col(0.0))
+        out = fn(opt, mp, tps, micro, dict(ρ=col(rho), T=col(T))).cpu().numpy()
+        assert np.all(out == out[0]) and abs(out[0] / want - 1) < 1e-12, (out[0], want)
+        assert torch.all(fn(None, mp, tps, micro, dict(rho=col(rho), T=col(T))) == 0)
+    # seeded columns, both cloud-ice options, vs the oracle's source terms
+    n = 1 << 16
+    st = synthetic_states_1m(n, seed=99)
+    cols = {k: torch.from_numpy(v).to(cuda) for k, v in st.items()}
+    micro = {k: cols[k] for k in ("q_tot", "q_lcl", "q_icl", "q_rai", "q_sno")}
+    thermo = dict(ρ=cols["rho"], T=cols["T"])
+    for opt in (CMP.ConstantTimescale(), CMP.TemperatureDependent()):
+        mpo = CMP.Microphysics1MParams(np.float64, cloud_ice_formation=opt)
+        ref = orc.bmt1m(CMP.pack_1m(mpo, tps), *[st[k] for k in ("rho", "T", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno")], mode="verbose")
+        bound = orc.bmt1m(CMP.pack_1m(mpo, tps), *[st[k] for k in ("rho", "T", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno")], mode="verbose", bound=True)
+        got = NEQ.conv_q_vap_to_q_icl(opt, mp, tps, micro, thermo).cpu().numpy()   # mp has the default option: the method dispatches on `opt`
+        assert_parity("conv_q_vap_to_q_icl", got, ref["S_phase_change_vap_icl"], bound=bound["S_phase_change_vap_icl"])
+    got = NEQ.conv_q_vap_to_q_lcl(CMP.CloudLiquidFormation(), mp, tps, micro, thermo).cpu().numpy()
+    assert_parity("conv_q_vap_to_q_lcl", got, ref["S_phase_change_vap_lcl"], bound=bound["S_phase_change_vap_lcl"])
+    with pytest.raises(TypeError):
+        NEQ.conv_q_vap_to_q_icl(CMP.CloudLiquidFormation(), mp, tps, micro, thermo)
