@@ -92,10 +92,10 @@ int diag_2m_impl(const PC* pc, const PR* pr, int64_t n, const FT* q_lcl, const F
     f.pi_rho_w = pi * f.pdf_r.rho_w;
     f.eps = eps_of<FT>();
     f.eps_n = epsn_of<FT>();
-    // FT(4 / 3 * π * ρw) and, for the Float32 method, its Float32 rounding                CloudDiagnostics.jl:64, 99
+    // 4 / 3 * π * ρw (CloudDiagnostics.jl:64, 99).  Float32 method: parameters and thresholds are the Float32 ones, literal
+    // constants stay at Float64 precision (the result is judged against the method's exact-arithmetic value)
     f.C = 4.0 / 3 * 3.141592653589793 * f.pdf_r.rho_w;
-    D nm23 = 2.0 / 3;
-    if (sizeof(FT) == 4) { f.C = (D)(float)f.C; nm23 = (D)(2.0f / 3); }
+    const D nm23 = 2.0 / 3;
     f.C_23 = std::pow(f.C, nm23);
     const D ns[3] = {2.0, 1.0, nm23};
     for (int i = 0; i < 3; ++i) {
@@ -124,18 +124,16 @@ template <class FT, class PB> int diag_1m_impl(const PB* p, int64_t n, const FT*
     f.inv_exp = 1.0 / ((D)m.me + (D)m.dm + 1.0);
     f.r0_pow = std::pow((D)m.r0, (D)m.me + (D)m.dm);
     f.denom = (D)m.chi_m * (D)m.m0 * std::max((D)p->rain.n0, e) * (D)m.gamma_coeff;
-    f.lam_floor = (D)m.r0 * (f32 ? (D)1e-5f : 1e-5);
-    f.c1em12 = f32 ? (D)1e-12f : 1e-12;
-    f.c1em3 = f32 ? (D)1e-3f : 1e-3;
+    f.lam_floor = (D)m.r0 * (f32 ? (D)1e-5f : 1e-5);   // a threshold: the method's own FT(1e-5) (CM1:151)
+    f.c1em12 = 1e-12;
+    f.c1em3 = 1e-3;
     return launch_pointwise<FT, 2, 1, Diag1M, 256, 2>(f, n, in, out, (cudaStream_t)stream, "diag_1m launch");
 }
 
 template <class FT>
 int diag_lh97_impl(FT rho_w, int64_t n, const FT* rho, const FT* q_lcl, const FT* N_lcl, const FT* q_rai, const FT* N_rai, FT* reff, void* stream) {
     FT* out[1] = {reff};
-    const bool f32 = sizeof(FT) == 4;
-    const D third = f32 ? (D)(float)(1.0 / 3) : 1.0 / 3;
-    const D k = f32 ? (D)0.8f : 0.8;
+    const D third = 1.0 / 3, k = 0.8;
     int st;
     const int dummy = 0;
     if ((st = require_outputs<FT, 1>(n, out, 1))) return st;
