@@ -500,6 +500,22 @@ struct P3Rates {
 
 enum { P3_WANT_VEL = 1, P3_WANT_MELT = 2, P3_WANT_AGG = 4, P3_WANT_COLL = 8 };
 
+// Phase barriers (kernels_p3.cu, CUMICRO_P3_SYNC >= 2; measured slower than the per-point barrier alone, kept for the record:
+// 2^19 points, 1024x1: no barrier 64.5 ms, per-point barrier 50.7 ms, per-point + phase barriers 56.5 ms): every warp of the block executes exactly p3_phase_barriers(n) block
+// barriers per point, at the same phase boundaries, so that the warps of an SM walk the same loops at the same time and
+// share their instruction-cache lines.  All barrier sites are warp-uniform (`want`, `rain_on`, ... are broadcast values);
+// a warp without a point (or without a phase) executes the matching barriers of the branch it skips.
+#ifndef CUMICRO_P3_SYNC
+#define CUMICRO_P3_SYNC 1
+#endif
+#if CUMICRO_P3_SYNC >= 2 && defined(__CUDA_ARCH__)
+#define P3_BAR() do { __syncwarp(); asm volatile("bar.sync 0;" ::: "memory"); } while (0)
+#else
+#define P3_BAR() do { } while (0)
+#endif
+CM_HD int p3_coll_passes(int n) { return (4 * n + 31) / 32; }            // outer collision nodes: <= 4 segments x n, 32 per pass
+CM_HD int p3_phase_barriers(int n) { return 4 + p3_coll_passes(n); }
+
 // The quantile pairs the requested integrals need (one Halley solve per lane).
 CM_DEV void p3_bounds(const P3Point& s, const P3K& k, int want, int lane, double (&bv)[5], double (&bc)[5], double (&ba)[5]) {
     // lane 0,1: p = 1e-6 (velocities, melt)   2,3: p = 1e-5 (collisions)   4,5: p = eps (self-collection)
@@ -529,6 +545,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
     double bv[5], bc[5], ba[5];
     p3_bounds(s, k, want, lane, bv, bc, ba);
     SegNodes sn;
+    P3_BAR();   // 1
 
     // ---- bulk terminal velocities + melt: single integrals over the p = 1e-6 bounds
     //      P3_terminal_velocity.jl:73-133, P3_processes.jl:64-94
@@ -559,6 +576,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         }
     }
 
+    P3_BAR();   // 2
     // ---- ice self-collection: outer nodes by chunks of 32 (one per lane), inner 2n nodes across lanes
     //      P3_processes.jl:676-712
     out.agg_dN = 0.0;
@@ -600,10 +618,13 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         out.agg_dN = 0.5 * warp_sum(acc);
     }
 
+    P3_BAR();   // 3
     // ---- liquid-ice collisions                                          P3_processes.jl:112-655
 #pragma unroll
     for (int i = 0; i < 7; ++i) out.src[i] = 0.0;
-    if (want & P3_WANT_COLL) {
+    if (!(want & P3_WANT_COLL)) {
+        for (int b = 0; b < 1 + p3_coll_passes(n); ++b) P3_BAR();
+    } else {
         const double e = k.eps;
         const double rho = s.rho;
         // cloud PSD n_c(D) = exp(logN0c + νcD log D - λc D^μcD) and its p-quantile bounds   CM2:203-236, 346-355
@@ -699,7 +720,14 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         double acc[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+        P3_BAR();   // 4
+#if CUMICRO_P3_SYNC >= 2
+        for (int t = lane, pass = 0; pass < p3_coll_passes(n); t += 32, ++pass) {
+            P3_BAR();   // 5 ...
+            if (t >= sn.count()) continue;
+#else
         for (int t = lane; t < sn.count(); t += 32) {
+#endif
             double Di, w;
             sn.get(t, qx, qw, Di, w);
             const P3Point::Node nd = s.node<true>(Di, k);

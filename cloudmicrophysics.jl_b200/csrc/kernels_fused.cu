@@ -7,7 +7,9 @@
 // per-GPU diagnostics is the only collective of the whole path (NCCL all-reduce of
 // CUMICRO_NDIAG doubles, done by the host binding).
 #include <cmath>
+#include <cstdlib>
 #include <limits>
+#include <string>
 
 #include "cm_1m.cuh"
 #include "cm_hostpipe.cuh"
@@ -24,9 +26,16 @@ template <class FT> constexpr bool is_f32() { return sizeof(FT) == 4; }
 constexpr int NIN = 11;   // rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai
 constexpr int NOUT = 11;  // 1M: dq_lcl, dq_icl, dq_rai, dq_sno | 2M: dq_lcl, dn_lcl, dq_rai, dn_rai | J_dep, J_ABIFM, J_hom
 constexpr int NDIAG = CUMICRO_NDIAG;
-constexpr int BLOCK = 128;
-#ifndef CUMICRO_FUSED_MINB
-#define CUMICRO_FUSED_MINB 6   /* 2^24 points: 4 (all inputs and outputs live) 4.54 ms; staged inputs + early stores: 6 -> 4.00, 8 -> 4.04 */
+// Launch shape.  The loop body is the code of three kernel families (~80 KB of SASS) against a 32 KB L1.5 instruction cache:
+// with independent 128-thread blocks the resident warps sit in different families and thrash it (ncu: stall_no_instruction 1.9
+// per issue vs 0.15 in the 2M kernel alone).  ONE block of 768 threads per SM (optionally a block barrier after every family) keeps
+// all 24 warps of the SM inside the same family's code.   Measured, 2^24 points (tools/tune_fused.py; n = no barriers):
+//   128x6n 3.27   128x6 3.17   256x3n 3.12   256x3 2.88   384x2n 2.98   384x2 2.82   768x1n 2.77   768x1 2.93 ms
+// -> one block per SM WITHOUT barriers: its warps start together and stay loosely in phase; the barrier's wait for the
+// slowest warp then costs more than the residual drift.
+#ifndef CUMICRO_FUSED_BLOCK
+#define CUMICRO_FUSED_BLOCK 768
+#define CUMICRO_FUSED_MINB 1
 #endif
 
 struct FusedParams {
@@ -52,25 +61,27 @@ template <class FT> struct FusedArgs {
 // copies, double-buffered: the next item streams in while this one is computed) and every family stores its tendencies and
 // accumulates its diagnostic as soon as it is done, so the live register set is that of ONE family at a time and the kernel
 // keeps the occupancy of the single-family kernels.
-#define CM_FUSED_FENCE() asm volatile("" ::: "memory")
-template <class FT>
-__global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
+template <class FT, int BLOCK, int MINB, bool SYNC>
+__global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     math_tables_init<BLOCK>();
-    __shared__ FT stage[2][NIN][BLOCK];
+    extern __shared__ __align__(16) unsigned char fused_dyn_smem[];
+    FT (*stage)[NIN][BLOCK] = reinterpret_cast<FT (*)[NIN][BLOCK]>(fused_dyn_smem);   // [2][NIN][BLOCK]
     const FusedParams& f = a.f;
     const int tid = threadIdx.x;
     double diag[NDIAG];
 #pragma unroll
     for (int k = 0; k < NDIAG; ++k) diag[k] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * BLOCK;
-    int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
-    if (i < a.n) {
+    int64_t base = (int64_t)blockIdx.x * BLOCK;   // block-uniform trip count: the barriers sit inside the loop
+    if (base + tid < a.n) {
 #pragma unroll
-        for (int c = 0; c < NIN; ++c) cp_async_elem(&stage[0][c][tid], a.in[c] + i);
+        for (int c = 0; c < NIN; ++c) cp_async_elem(&stage[0][c][tid], a.in[c] + base + tid);
     }
     cp_async_commit();
     int buf = 0;
-    for (; i < a.n; i += stride) {
+    for (; base < a.n; base += stride) {
+        const int64_t i = base + tid;
+        const bool active = i < a.n;
         const int64_t nxt = i + stride;
         if (nxt < a.n) {
 #pragma unroll
@@ -81,7 +92,7 @@ __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const 
         auto in = [&](int c) { return (double)stage[buf][c][tid]; };   // rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai
         auto put = [&](int c, double v) { if (a.out[c]) __stcs(a.out[c] + i, (FT)v); };
         // 1-moment tendencies                                         BMT:505-514
-        {
+        if (active) {
             const Src1M<D> r = microphysics_source_terms_1m<D>(f.p1, f.tk, f.k1, in(0), in(1), in(4), in(5), in(6), in(7), in(8));
             double t[4];
             aggregate_tendencies_1m<D>(r, t);
@@ -89,9 +100,9 @@ __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const 
             for (int k = 0; k < 4; ++k) put(k, t[k]);
             diag[0] += in(0) * (t[2] + t[3]);   // 1M precipitation production  Σ ρ (dq_rai + dq_sno)   [kg m^-3 s^-1]
         }
-        CM_FUSED_FENCE();
+        if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         // 2-moment warm rain (cloud ice seen by the thermodynamics = q_icl + q_sno)   BMT:820-854
-        {
+        if (active) {
             const Warm2M<D> o = warm_rain_tendencies_2m<D>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10),
                                                            fmax_(0.0, in(6)) + fmax_(0.0, in(8)));
             put(4, o.dq_lcl_dt);
@@ -100,9 +111,9 @@ __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const 
             put(7, o.dn_rai_dt);
             diag[1] += in(0) * o.dq_rai_dt;     // 2M rain production           Σ ρ dq_rai
         }
-        CM_FUSED_FENCE();
+        if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         // ice-nucleation rates (+ ARG2000 activated number)              IN:92-134, 557-584; AA:138-273
-        {
+        if (active) {
             const double rho = in(0), T = in(1), pr = in(2), w = in(3), q_tot = in(4), q_lcl = in(5), q_icl = in(6), q_rai = in(7),
                          q_sno = in(8), n_lcl = in(9);
             double n_act = 0.0;
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(BLOCK, CUMICRO_FUSED_MINB) fused_kernel(const 
             diag[2] += n_act;                   // activated aerosol number     Σ N_act                  [m^-3]
             diag[3] += 1.0;                     // points
         }
-        CM_FUSED_FENCE();
+        if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         buf ^= 1;
     }
     // block reduction: shuffle within warps, then across the (BLOCK/32) warps through shared memory
@@ -173,6 +184,29 @@ template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
+template <class FT, int BLOCK, int MINB, bool SYNC> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
+    void* ws = nullptr;
+    int st = cmh::workspace(cmh::kPipeSlots /* slot reserved for the diagnostics partials */, sizeof(double) * NDIAG * (size_t)blocks + 64, &ws);
+    if (st) return st;
+    a.partials = static_cast<double*>(ws);
+    const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
+    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC>;
+    static bool attr_set = false;   // per instantiation; the attribute is per function and device-wide idempotent
+    if (!attr_set || smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cmh::cuda_status(e, "fused: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        attr_set = true;
+    }
+    kern<<<blocks, BLOCK, smem, s>>>(a);
+    cmh::count_launch();
+    if (diag) {
+        fused_diag_finish<<<1, 256, 0, s>>>(a.partials, blocks, diag);
+        cmh::count_launch();
+    }
+    return CUMICRO_OK;
+}
+
 template <class FT>
 int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, const typename PF<FT>::p3* p3, int64_t n,
                const FT* const* in, FT* const* out, double* diag, void* stream) {
@@ -195,17 +229,27 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
     for (int c = 0; c < NOUT; ++c) a.out[c] = out[c];
     a.n = n;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * CUMICRO_FUSED_MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
-    void* ws = nullptr;
-    int st = cmh::workspace(cmh::kPipeSlots /* slot reserved for the diagnostics partials */, sizeof(double) * NDIAG * (size_t)blocks + 64, &ws);
-    if (st) return st;
-    a.partials = static_cast<double*>(ws);
-    fused_kernel<FT><<<blocks, BLOCK, 0, s>>>(a);
-    cmh::count_launch();
-    if (diag) {
-        fused_diag_finish<<<1, 256, 0, s>>>(a.partials, blocks, diag);
-        cmh::count_launch();
+    // launch shape: 768x1, no family barriers (see the top of the file); CUMICRO_FUSED_SHAPE=128x6|256x3|384x2|768x1[n] selects
+    // another one for measurements (a trailing 'n' = no barriers)
+    int shape = 3;
+    bool sync = false;
+    if (const char* e = std::getenv("CUMICRO_FUSED_SHAPE")) {
+        const std::string v(e);
+        shape = v.rfind("128", 0) == 0 ? 0 : v.rfind("256", 0) == 0 ? 1 : v.rfind("384", 0) == 0 ? 2 : 3;
+        sync = v.empty() || v.back() != 'n';
     }
+    int st;
+    switch (shape * 2 + (sync ? 1 : 0)) {
+        case 0: st = launch_fused<FT, 128, 6, false>(a, n, s, diag); break;
+        case 1: st = launch_fused<FT, 128, 6, true>(a, n, s, diag); break;
+        case 2: st = launch_fused<FT, 256, 3, false>(a, n, s, diag); break;
+        case 3: st = launch_fused<FT, 256, 3, true>(a, n, s, diag); break;
+        case 4: st = launch_fused<FT, 384, 2, false>(a, n, s, diag); break;
+        case 5: st = launch_fused<FT, 384, 2, true>(a, n, s, diag); break;
+        case 6: st = launch_fused<FT, 768, 1, false>(a, n, s, diag); break;
+        default: st = launch_fused<FT, 768, 1, true>(a, n, s, diag); break;
+    }
+    if (st) return st;
     return cmh::cuda_status(cudaGetLastError(), "fused_1m2m_icenuc launch");
 }
 

@@ -19,8 +19,20 @@ namespace {
 
 using namespace cm;
 
-constexpr int BLOCK = 128;
-constexpr int MINB = 10;   // 48 registers: the kernel is instruction-fetch / latency bound, resident warps matter more than spills (2^19 points: MINB 4: 66.0, 6: 62.9, 8: 59.3, 10: 57.5, 12: 57.4 ms)
+// Launch shape: 2 blocks of 640 threads per SM (40 warps at 48 registers) and ONE block barrier per point (CUMICRO_P3_SYNC = 1):
+// the kernel is instruction-fetch bound — a point's pass walks ~93 KB of code against a 6 KB L0 / 32 KB L1.5
+// instruction cache — and warps that start every point together walk the same loops at the same time and share the lines.
+// 2^19 points, process rates: 128x10 unsynchronised 57.5 ms | with the per-point barrier: 256x5 50.3, 320x4 49.7, 512x2 49.8,
+// 640x2 47.2, 1024x1 (64 registers) 50.7 | 1024x1 unsynchronised 64.5 | 1024x1 with barriers at every phase as well 56.5.
+#ifndef CUMICRO_P3_BLOCK
+#define CUMICRO_P3_BLOCK 640
+#define CUMICRO_P3_MINB 2
+#endif
+#ifndef CUMICRO_P3_SYNC
+#define CUMICRO_P3_SYNC 1
+#endif
+constexpr int BLOCK = CUMICRO_P3_BLOCK;
+constexpr int MINB = CUMICRO_P3_MINB;   // 48 registers: resident warps matter more than spills (128-thread blocks, 2^19 points: MINB 4: 66.0, 6: 62.9, 8: 59.3, 10: 57.5, 12: 57.4 ms)
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
 constexpr int NIN_MAX = 13, NOUT_MAX = 12;
 
@@ -190,9 +202,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
     const double e = a.k.eps;
     const int64_t n_tiles = (a.n + 31) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * BLOCK) >> 5;
+#if CUMICRO_P3_SYNC
+    // block-uniform trip count: the point loop below holds a block barrier
+    for (int64_t tile0 = ((int64_t)blockIdx.x * BLOCK) >> 5; tile0 < n_tiles; tile0 += n_warps) {
+        const int64_t tile = tile0 + (threadIdx.x >> 5);
+        const int64_t i = (tile << 5) + lane;
+        const bool valid = tile < n_tiles && i < a.n;
+#else
     for (int64_t tile = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) >> 5; tile < n_tiles; tile += n_warps) {
         const int64_t i = (tile << 5) + lane;
         const bool valid = i < a.n;
+#endif
         Pt x;
         auto ld = [&](int c) { return (valid && a.in[c]) ? (double)__ldg(a.in[c] + i) : 0.0; };
         if (MODE == MODE_VEL) {   // in: rho_a, L_ice, N_ice, L_rim, B_rim, logl (volumetric, as the reference's wrapper takes them)
@@ -222,7 +242,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
         for (int c = 0; c < 7; ++c) mine.src[c] = 0.0;
         double F_rim = 0.0, rho_rim = 0.0;
         unsigned m = __ballot_sync(0xffffffffu, want != 0);
+#if CUMICRO_P3_SYNC
+        // every warp of the block starts its next point together: the SM's warps walk the same code at the same time
+        while (__syncthreads_or(m != 0)) {
+            if (m == 0) {   // no point left in this warp's tile: keep the block's barrier count (cm_p3.cuh, P3_BAR)
+                for (int b = 0; b < p3_phase_barriers(nq); ++b) P3_BAR();
+                continue;
+            }
+#else
         while (m) {
+#endif
             const int b = __ffs(m) - 1;
             m &= m - 1;
             P3Point s;
@@ -297,7 +326,7 @@ int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, i
     const int64_t tiles = (n + 31) / 32;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BLOCK / 32 - 1) / (BLOCK / 32), (int64_t)cmh::num_sms() * MINB));
     auto kern = p3_tile_kernel<FT, MODE>;
-    if (shmem > 48 * 1024) {
+    if (shmem + 8 * 1024 > 48 * 1024) {   // dynamic + the static math tables (4 KB) against the 48 KB default
         st = cmh::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem), "cudaFuncSetAttribute");
         if (st) return st;
     }
