@@ -9,6 +9,17 @@
 #include "cm_launch.cuh"
 #include "cm_sb2006.cuh"
 
+// Block size sweep at 2^24 points (tools/tune_1m.py; blocks x resident blocks = 1024 threads per SM throughout):
+//   128x8: Instantaneous 0.944, Verbose 1.127, LinearizedAverage 1.566 ms | 256x4: 0.954, 1.133, 1.529 | 512x2: 0.967, 1.157, 1.505
+//   | 1024x1: 0.989, 1.233, 1.469.  Only the largest body (LinearizedAverage, ~60 KB of code) gains from one block per SM
+//   (its warps stay in phase and share instruction-cache lines, cf. kernels_fused.cu).
+#ifndef CUMICRO_1M_BLOCK
+#define CUMICRO_1M_BLOCK 128
+#endif
+#ifndef CUMICRO_1ML_BLOCK
+#define CUMICRO_1ML_BLOCK 1024
+#define CUMICRO_1ML_MINB 1
+#endif
 #ifndef CUMICRO_1MV_MINB
 #define CUMICRO_1MV_MINB 8   /* verbose: 4 -> 1.75 ms, 6 -> 1.34, 8 -> 1.22; linavg: 3.07, 3.01, 2.94 */
 #endif
@@ -90,13 +101,13 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
     if ((st = require_outputs<FT, 4>(n, o4, mode == 1 ? 0 : 4))) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == 0) {
-        return launch_pointwise<FT, 7, 4, OneMInst, 128, CUMICRO_1M_MINB, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
+        return launch_pointwise<FT, 7, 4, OneMInst, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
     } else if (mode == 1) {
         if (src18 == nullptr) return cmh::fail(CUMICRO_E_NULL, "source-term pointer table is NULL");
         FT* o22[4 + S1M_NSRC];
         for (int i = 0; i < 4; ++i) o22[i] = o4[i];
         for (int i = 0; i < S1M_NSRC; ++i) o22[4 + i] = src18[i];
-        return launch_pointwise<FT, 7, 4 + S1M_NSRC, OneMVerbose, 128, CUMICRO_1MV_MINB, false>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
+        return launch_pointwise<FT, 7, 4 + S1M_NSRC, OneMVerbose, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB, false>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
                                                                                    "bmt1m_verbose launch");
     } else {
         if (!(dt > FT(0))) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: dt must be > 0");
@@ -106,7 +117,7 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
         f.nsub = nsub;
         f.Lv_over_cp = f.p.tps.LH_v0 / f.p.tps.cp_d;
         f.Ls_over_cp = f.p.tps.LH_s0 / f.p.tps.cp_d;
-        return launch_pointwise<FT, 7, 4, OneMLinAvg, 128, CUMICRO_1MV_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
+        return launch_pointwise<FT, 7, 4, OneMLinAvg, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
     }
 }
 
