@@ -25,16 +25,20 @@ using namespace cm;
 // 2^19 points, process rates: 128x10 unsynchronised 57.5 ms | with the per-point barrier: 256x5 50.3, 320x4 49.7, 512x2 49.8,
 // 640x2 47.2, 1024x1 (64 registers) 50.7 | 1024x1 unsynchronised 64.5 | 1024x1 with barriers at every phase as well 56.5.
 #ifndef CUMICRO_P3_BLOCK
-#define CUMICRO_P3_BLOCK 640
+#define CUMICRO_P3_BLOCK 576
 #define CUMICRO_P3_MINB 2
 #endif
 #ifndef CUMICRO_P3_SYNC
 #define CUMICRO_P3_SYNC 1
 #endif
+#ifndef CUMICRO_P3_SYNC_EVERY
+#define CUMICRO_P3_SYNC_EVERY 1
+#endif
 constexpr int BLOCK = CUMICRO_P3_BLOCK;
 constexpr int MINB = CUMICRO_P3_MINB;   // 48 registers: resident warps matter more than spills (128-thread blocks, 2^19 points: MINB 4: 66.0, 6: 62.9, 8: 59.3, 10: 57.5, 12: 57.4 ms)
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
 constexpr int NIN_MAX = 13, NOUT_MAX = 12;
+constexpr int kSlot = 14;   // doubles per point in the owner <-> evaluating-warp exchange (11 inputs out, 12 rates + F_rim, rho_rim back)
 
 template <class FT> struct P3Args {
     cumicro_params_p3_f64 p;
@@ -197,9 +201,117 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
     }
     __syncthreads();
     P3Scratch sc;
+    constexpr int W = BLOCK / 32;
     sc.bind(smem + 2 * nq + (threadIdx.x >> 5) * P3Scratch::doubles(nq), nq);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double e = a.k.eps;
+#if CUMICRO_P3_SYNC
+    // ---- block-balanced form.  A round = BLOCK consecutive points, one per thread.  The points that need integrals are
+    // compacted into a list in shared memory and dealt to the W warps round-robin, one point per warp per iteration, every
+    // iteration starting with a block barrier (the SM's warps walk the same loops together: see the launch-shape note).
+    // Inputs travel owner -> evaluating warp and the rates travel back through a 14-double slot per point.
+    double* slots = smem + 2 * nq + W * P3Scratch::doubles(nq);                      // [BLOCK][kSlot]
+    unsigned short* idx = reinterpret_cast<unsigned short*>(slots + BLOCK * kSlot);   // [BLOCK] owners of the listed points
+    unsigned char* wantv = reinterpret_cast<unsigned char*>(idx + BLOCK);             // [BLOCK]
+    __shared__ int warp_cnt[W];
+    for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < a.n; base += (int64_t)gridDim.x * BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        const bool valid = i < a.n;
+        Pt x;
+        auto ld = [&](int c) { return (valid && a.in[c]) ? (double)__ldg(a.in[c] + i) : 0.0; };
+        if (MODE == MODE_VEL) {   // in: rho_a, L_ice, N_ice, L_rim, B_rim, logl (volumetric, as the reference's wrapper takes them)
+            x.rho = ld(0); x.T = 273.15; x.q_tot = 0.0; x.q_lcl = x.n_lcl = x.q_rai = x.n_rai = 0.0;
+            x.L_ice = ld(1); x.N_ice = ld(2); x.L_rim = ld(3); x.B_rim = ld(4); x.logl = ld(5); x.shift = 0.0;
+            x.q_ice = x.n_ice = x.q_rim = x.b_rim = 0.0;
+            x.L_lcl = x.N_lcl = x.L_rai = x.N_rai = 0.0;
+        } else {                  // in: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl [, inpc_log_shift]
+            x.rho = fmax_(0.0, ld(0)); x.T = ld(1); x.q_tot = fmax_(0.0, ld(2)); x.q_lcl = fmax_(0.0, ld(3)); x.n_lcl = fmax_(0.0, ld(4));
+            x.q_rai = fmax_(0.0, ld(5)); x.n_rai = fmax_(0.0, ld(6)); x.q_ice = fmax_(0.0, ld(7)); x.n_ice = fmax_(0.0, ld(8));
+            x.q_rim = fmax_(0.0, ld(9)); x.b_rim = fmax_(0.0, ld(10)); x.logl = ld(11); x.shift = ld(12);
+            x.L_lcl = x.q_lcl * x.rho; x.L_rai = x.q_rai * x.rho; x.N_lcl = x.n_lcl * x.rho; x.N_rai = x.n_rai * x.rho;
+            x.L_ice = x.q_ice * x.rho; x.N_ice = x.n_ice * x.rho; x.L_rim = x.q_rim * x.rho; x.B_rim = x.b_rim * x.rho;
+        }
+        // which integrals this point needs
+        int want = 0;
+        if (valid) {
+            const bool vel_on = !((x.N_ice < e) || (x.L_ice < e));                  // P3_terminal_velocity.jl:79-81
+            const bool ice_on = (MODE == MODE_VEL) ? false : (x.q_ice > e && x.n_ice > e);   // BMT:961
+            if (vel_on) want |= P3_WANT_VEL;
+            if (ice_on) want |= P3_WANT_AGG | P3_WANT_COLL | ((x.T > a.tk.T_freeze) ? P3_WANT_MELT : 0);
+            want &= a.want;
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, want != 0);
+        if (lane == 0) warp_cnt[warp] = __popc(mb);
+        __syncthreads();   // also: the previous round's slot reads are done
+        int offset = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) { const int c = warp_cnt[w]; offset += (w < warp) ? c : 0; total += c; }
+        if (want) {
+            idx[offset + __popc(mb & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
+            wantv[threadIdx.x] = (unsigned char)want;
+            double* sl = slots + threadIdx.x * kSlot;
+            sl[0] = x.rho; sl[1] = x.T; sl[2] = x.L_ice; sl[3] = x.N_ice; sl[4] = x.L_rim; sl[5] = x.B_rim; sl[6] = x.logl;
+            sl[7] = x.L_lcl; sl[8] = x.N_lcl; sl[9] = x.L_rai; sl[10] = x.N_rai;
+        }
+        for (int it = 0; it * W < total; ++it) {
+            // it = 0: the list is complete; every CUMICRO_P3_SYNC_EVERY-th it: the block's warps start their next point together
+            if (CUMICRO_P3_SYNC_EVERY == 1 || it % CUMICRO_P3_SYNC_EVERY == 0) __syncthreads();
+            const int j = it * W + warp;
+            if (j < total) {
+                const int o = idx[j];
+                double* sl = slots + o * kSlot;
+                const double rho = sl[0], T = sl[1], L_ice = sl[2], N_ice = sl[3], L_rim = sl[4], B_rim = sl[5], logl = sl[6], L_lcl = sl[7],
+                             N_lcl = sl[8], L_rai = sl[9], N_rai = sl[10];
+                const int w_o = wantv[o];
+                __syncwarp();
+                P3Point s;
+                p3_point_init(s, a.p, a.k, rho, T, L_ice, N_ice, L_rim, B_rim, logl);
+                P3Rates r;
+                p3_point_rates(s, a.p, a.k, a.tk, a.sk, qx, qw, sc, w_o, L_lcl, N_lcl, L_rai, N_rai, r);
+                if (lane == 0) {
+                    sl[0] = r.v_n; sl[1] = r.v_m; sl[2] = r.melt_dN; sl[3] = r.melt_dL; sl[4] = r.agg_dN;
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) sl[5 + c] = r.src[c];
+                    sl[12] = s.F_rim; sl[13] = s.rho_rim;
+                }
+            }
+        }
+        __syncthreads();
+        P3Rates mine;
+        mine.v_n = mine.v_m = mine.melt_dN = mine.melt_dL = mine.agg_dN = 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) mine.src[c] = 0.0;
+        double F_rim = 0.0, rho_rim = 0.0;
+        if (want) {
+            const double* sl = slots + threadIdx.x * kSlot;
+            mine.v_n = sl[0]; mine.v_m = sl[1]; mine.melt_dN = sl[2]; mine.melt_dL = sl[3]; mine.agg_dN = sl[4];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) mine.src[c] = sl[5 + c];
+            F_rim = sl[12]; rho_rim = sl[13];
+        }
+        if (!valid) continue;
+        if (MODE == MODE_BMT) {
+            if (want == 0) {   // state_from_prognostic for the rim bookkeeping of the pointwise processes (BMT:930)
+                F_rim = fmin_(regularised_ratio_(fmin_(x.L_rim, x.L_ice), x.L_ice, e), 1.0 - e);
+                rho_rim = fmin_(regularised_ratio_(x.L_rim, x.B_rim, e), a.k.rho_l08);
+            }
+            double y[9];
+            bmt2m_p3_assemble(a.p, a.tk, a.sk, a.k, x, (x.q_ice > e && x.n_ice > e), mine, F_rim, rho_rim, y);
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                if (a.out[c]) a.out[c][i] = (FT)y[c];
+        } else if (MODE == MODE_RATES) {
+            const double y[12] = {mine.v_n, mine.v_m, mine.melt_dN, mine.melt_dL, mine.agg_dN, mine.src[0], mine.src[1],
+                                  mine.src[2], mine.src[3], mine.src[4], mine.src[5], mine.src[6]};
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+                if (a.out[c]) a.out[c][i] = (FT)y[c];
+        } else {
+            if (a.out[0]) a.out[0][i] = (FT)mine.v_n;
+            if (a.out[1]) a.out[1][i] = (FT)mine.v_m;
+        }
+    }
+#else
     const int64_t n_tiles = (a.n + 31) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * BLOCK) >> 5;
 #if CUMICRO_P3_SYNC
@@ -284,6 +396,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
             if (a.out[1]) a.out[1][i] = (FT)mine.v_m;
         }
     }
+#endif
 }
 
 template <class FT> struct PP3;
@@ -322,7 +435,10 @@ int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, i
     a.n = n;
     a.want = want;
     const int nq = a.k.n;
-    const size_t shmem = sizeof(double) * (size_t)(2 * nq + (BLOCK / 32) * P3Scratch::doubles(nq));
+    size_t shmem = sizeof(double) * (size_t)(2 * nq + (BLOCK / 32) * P3Scratch::doubles(nq));
+#if CUMICRO_P3_SYNC
+    shmem += sizeof(double) * BLOCK * kSlot + BLOCK * 3 + 16;
+#endif
     const int64_t tiles = (n + 31) / 32;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BLOCK / 32 - 1) / (BLOCK / 32), (int64_t)cmh::num_sms() * MINB));
     auto kern = p3_tile_kernel<FT, MODE>;

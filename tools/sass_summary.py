@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""SASS evidence for profiles/: per-kernel opcode histogram (static) of the hot kernels of libcumicro.so plus the full
+listing of the headline 2M kernel.  Run after a build:  python tools/sass_summary.py  ->  profiles/r01_sass_*.txt"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build")
+KERNELS = [  # (object, regex on the mangled name, label)
+    ("kernels_2m.o", r"pointwise_kernel_pipelinedIdLi7ELi4E.*Warm2MFused", "2m_warm_f64"),
+    ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMInstELb0", "1m_inst_f64"),
+    ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMLinAvgELb0", "1m_linavg_f64"),
+    ("kernels_icenuc.o", r"pointwise_kernelIfLi8ELi11E.*ArgIceNucILi3ELb0EEELb0", "arg_icenuc_f32"),
+    ("kernels_fused.o", r"fused_kernelIdLi768ELi1ELb0", "fused_f64"),
+    ("kernels_p3.o", r"p3_tile_kernelIdLi0", "p3_rates_f64"),
+]
+FP64 = ("DFMA", "DMUL", "DADD")
+
+
+def functions(obj):
+    txt = subprocess.run(["cuobjdump", "-sass", os.path.join(OBJ, obj)], capture_output=True, text=True, check=True).stdout
+    cur, out = None, {}
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            out[cur] = []
+        elif cur is not None:
+            out[cur].append(line)
+    return out
+
+
+def opcodes(lines):
+    h = collections.Counter()
+    for l in lines:
+        m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_]+)", l)
+        if m:
+            h[m.group(1)] += 1
+    return h
+
+
+def main():
+    summary = ["static SASS opcode counts of the hot kernels (sm_100a, nvcc 12.9, -fmad=false); dynamic counts are in the ncu summaries",
+               "tensor-core / TMA mnemonics (UTCMMA, UTMALDG, ...) are absent by design: nothing on this path is a contraction", ""]
+    cache = {}
+    for obj, pat, label in KERNELS:
+        fns = cache.setdefault(obj, functions(obj))
+        names = [n for n in fns if re.search(pat, n)]
+        if not names:
+            summary.append(f"{label}: kernel not found ({pat})")
+            continue
+        lines = fns[names[0]]
+        h = opcodes(lines)
+        total = sum(h.values())
+        fp64 = sum(h[k] for k in FP64)
+        summary.append(f"{label}: {total} instructions, {fp64} FP64 arithmetic (DFMA {h['DFMA']}, DMUL {h['DMUL']}, DADD {h['DADD']}), "
+                       f"DSETP {h['DSETP']}, MUFU {h['MUFU']}, LDS {h['LDS']}, LDG {h['LDG']}, LDGSTS {h['LDGSTS']}, STG {h['STG']}, "
+                       f"LDL {h['LDL']}, STL {h['STL']}, BRA {h['BRA']}, CALL {h['CALL']}")
+        summary.append("    " + "  ".join(f"{k} {v}" for k, v in h.most_common(24)))
+        summary.append(f"    {names[0][:150]}")
+        if label == "2m_warm_f64":
+            listing = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l) for l in lines if not re.match(r"^\s*/\* 0x[0-9a-f]+ \*/\s*$", l)]
+            open(os.path.join(ROOT, "profiles", "r01_sass_2m_warm_f64.txt"), "w").write("\n".join(listing) + "\n")
+    open(os.path.join(ROOT, "profiles", "r01_sass_summary.txt"), "w").write("\n".join(summary) + "\n")
+    print("\n".join(summary))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
