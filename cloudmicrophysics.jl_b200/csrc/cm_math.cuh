@@ -226,15 +226,27 @@ CM_HD double exp_(double x) {
 // exp with the IEEE limits: gradual underflow into the subnormals, 0 below them, +Inf
 // above the range, NaN propagated.
 CM_HD double exp_full_(double x) {
-    // one exp_ evaluation on a shifted argument: e^x = e^(x + 64 ln2) 2^-64 below the normal range (the scaling
-    // multiply rounds once into the subnormals), e^x = e^(x - 1) e just below overflow
-    const bool lo = x < -708.0, hi = x > 709.0;
-    const double xs = lo ? x + 44.361419555836500 : (hi ? x - 1.0 : x);
-    const double sc = lo ? 5.421010862427522170e-20 : (hi ? 2.718281828459045 : 1.0);
-    double y = exp_(fmin(fmax(xs, -708.0), 709.0)) * sc;
-    y = (x < -746.0) ? 0.0 : y;
-    y = (x > 709.782712893384) ? num<double>::inf() : y;
-    return (x != x) ? x : y;
+    // In range (all but pathological points, and warp-uniformly so) this is one compare, exp_ itself and one skipped branch;
+    // the branch-free form (six selects, IEEE fmin/fmax, three compares) cost more than the exponential — ncu source view of
+    // the ARG2000 kernel: 20 % of its instructions.  ONE inlined copy of exp_ serves both paths.
+    // Out of range: one exp_ evaluation on a shifted argument: e^x = e^(x + 64 ln2) 2^-64 below the normal range (the scaling
+    // multiply rounds once into the subnormals), e^x = e^(x - 1) e just below overflow.
+    const bool special = !(fabs(x) <= 708.0);   // also NaN
+    double xs = x, sc = 1.0;
+    if (special) {
+        const bool lo = x < -708.0, hi = x > 709.0;
+        xs = lo ? x + 44.361419555836500 : (hi ? x - 1.0 : x);
+        sc = lo ? 5.421010862427522170e-20 : (hi ? 2.718281828459045 : 1.0);
+        xs = fmin(fmax(xs, -708.0), 709.0);
+    }
+    double y = exp_(xs);
+    if (special) {
+        y *= sc;
+        y = (x < -746.0) ? 0.0 : y;
+        y = (x > 709.782712893384) ? num<double>::inf() : y;
+        y = (x != x) ? x : y;
+    }
+    return y;
 }
 CM_HD float exp_(float x) { return expf(x); }
 CM_HD float exp_full_(float x) { return expf(x); }
