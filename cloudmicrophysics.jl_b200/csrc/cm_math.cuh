@@ -348,6 +348,14 @@ template <class FT> CM_HD FT pow_param(FT x, FT y) {
     if (y == FT(1)) return x;
     return powp_(x, y);
 }
+// Compile-time integer power: exact products; N < 0 through the <= 1 ulp reciprocal (x positive, normal).
+template <int N, class FT> CM_HD FT pow_int_(FT x) {
+    if constexpr (N < 0) return rcp_(pow_int_<-N>(x));
+    else if constexpr (N == 0) return FT(1);
+    else if constexpr (N == 1) return x;
+    else if constexpr (N % 2 == 0) { const FT h = pow_int_<N / 2>(x); return h * h; }
+    else return pow_int_<N - 1>(x) * x;
+}
 // The same with the case decided once on the host (an integer code in the launch constants) instead of up to
 // five FP64 compares per point.
 template <class FT> inline int pow_param_code(FT y) {
@@ -359,7 +367,7 @@ template <class FT> CM_HD FT pow_param(FT x, FT y, int code) {
         case 2: return x * x;
         case 3: return x * x * x;
         case 4: { FT x2 = x * x; return x2 * x2; }
-        case 5: { FT x2 = x * x; return FT(1) / (x2 * x2 * x); }
+        case 5: { FT x2 = x * x; return rcp_(x2 * x2 * x); }   // x positive normal at every call site; same bits as pow_int_<-5>
         default: return powp_(x, y);
     }
 }

@@ -23,13 +23,14 @@ using namespace cm;
 // Functors compute in Float64 (D = double); the entry points below are templated on the
 // column type FT and widen Float32 parameter blocks exactly.
 using D = double;
-template <int NIN = 7> struct Warm2MFused {
+// SPEC: compile-time specialisation for the default structure of the SB2006 block (cm_sb2006.cuh, sb2006_spec()); -1 = generic.
+template <int NIN = 7, int SPEC = -1> struct Warm2MFused {
     P<D>::params_2m_warm p;
     ThermoK<D> tk;
     SB2006K<D> sk;
     __device__ __forceinline__ void operator()(const D (&x)[NIN], D (&y)[4]) const {
         const D q_ice = (NIN == 8) ? fmax_(D(0), x[NIN - 1]) : D(0);
-        Warm2M<D> o = warm_rain_tendencies_2m<D>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], q_ice);
+        Warm2M<D> o = warm_rain_tendencies_2m<D, SPEC>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], q_ice);
         y[0] = o.dq_lcl_dt;
         y[1] = o.dn_lcl_dt;
         y[2] = o.dq_rai_dt;
@@ -114,7 +115,12 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
     }
 #endif
     // 128 x 7 blocks/SM (72 registers): sweep of the pipelined kernel 128x8 0.630, 128x7 0.623, 128x6 0.633, 128x5 0.659,
-    // 64x16 0.632, 256x4 0.634, 96x10 0.638 ms
+    // 64x16 0.632, 256x4 0.634, 96x10 0.638 ms.  The default parameter structure runs the specialised instantiation.
+    switch (sb2006_spec<D>(f.p.sb)) {
+        case 1: return launch_pointwise<FT, 7, 4, Warm2MFused<7, 1>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7, 1>>(p), n, in, out, s, "bmt2m_warm kernel launch");
+        case 0: return launch_pointwise<FT, 7, 4, Warm2MFused<7, 0>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7, 0>>(p), n, in, out, s, "bmt2m_warm kernel launch");
+        default: break;
+    }
     return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, n, in, out, s, "bmt2m_warm kernel launch");
 }
 
