@@ -54,7 +54,6 @@ template <class FT> struct OneMK {
     FT frost_c, frost_r0;    // 4 π D_vapor; FT(1e-6)
     // IEEE reciprocals of uniform divisors whose numerators are exact zeros at gated-off points (divr_, cm_math.cuh)
     FT rain_inv_k, snow_inv_k, rain_inv_tau, snow_inv_tau;
-    int linearize_fast_div;  // q_min > 0: the divisors max(q_min, q) of BMT._linearize are positive
 };
 
 template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::params_1m& p, bool method_is_f32 = false) {
@@ -122,14 +121,13 @@ template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::pa
     k.frost_c = 4 * pi * p.aps.D_vapor;
     k.rain_inv_k = FT(1) / p.pp.rain_acnv_k; k.snow_inv_k = FT(1) / p.pp.snow_acnv_k;
     k.rain_inv_tau = FT(1) / p.pp.rain_acnv_tau; k.snow_inv_tau = FT(1) / p.pp.snow_acnv_tau;
-    k.linearize_fast_div = p.tps.q_min >= FT(1e-300);
     return k;
 }
 
 // LogExpFunctions.log1pexp (same branch cuts as the package for Float64 / Float32)
 CM_DEV double log1pexp_(double x) {
     if (x < -36.7368005696771) return exp_full_(x);
-    if (x < 18.021826694558577) return log1p_(exp_(x));
+    if (x < 18.021826694558577) return log1p_pos_(exp_(x));   // e^x in [1e-16, 6.7e7]
     if (x < 33.23111882352963) return x + exp_(-x);
     return x;
 }
@@ -350,12 +348,10 @@ CM_DEV void linearized_implicit_step_1m(const typename P<FT>::params_1m& p, cons
     const FT* s = r.s;
     const FT q_min = tk.q_min;
     const FT d_lcl = fmax_(q_min, q_lcl), d_icl = fmax_(q_min, q_icl), d_rai = fmax_(q_min, q_rai), d_sno = fmax_(q_min, q_sno);
-    // 19 quotients over 4 divisors: one correctly rounded reciprocal per divisor (cm_math.cuh, divr_); q_min = 0 (a legal
-    // parameter value) can make a divisor zero — then the IEEE division, decided on the host
-    const bool fast = k.linearize_fast_div;
-    const FT r_lcl = fast ? rcp_cr_(d_lcl) : FT(0), r_icl = fast ? rcp_cr_(d_icl) : FT(0), r_rai = fast ? rcp_cr_(d_rai) : FT(0),
-             r_sno = fast ? rcp_cr_(d_sno) : FT(0);
-    auto over = [fast](FT x, FT d, FT r) { return fast ? divr_(x, d, r) : div_(x, d); };
+    // 19 quotients over 4 divisors: one correctly rounded reciprocal per divisor (cm_math.cuh, divr_).  q_min = 0 (legal, not
+    // sensible) makes the divisor of an empty species zero: the reference's 0/0 = NaN is NaN here as well (rcp of 0 is not finite).
+    const FT r_lcl = rcp_cr_(d_lcl), r_icl = rcp_cr_(d_icl), r_rai = rcp_cr_(d_rai), r_sno = rcp_cr_(d_sno);
+    auto over = [](FT x, FT d, FT r) { return divr_(x, d, r); };
     FT M11 = 0, M12 = 0, M22 = 0, M31 = 0, M33 = 0, M34 = 0, M41 = 0, M42 = 0, M43 = 0, M44 = 0, e1 = 0, e2 = 0, e4 = 0;
     FT D;
     bool src;

@@ -150,10 +150,16 @@ int bmt2m_warm_host_impl(const typename P<FT>::params_2m_warm* p, int64_t n, con
     if ((st = check_2m_options<FT>(p))) return st;
     if ((st = require_outputs<FT, 4>(n, out, 4))) return st;
     Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
+    const int spec = sb2006_spec<D>(f.p.sb);
+    const Warm2MFused<7, 1> f1 = make_2m<FT, Warm2MFused<7, 1>>(p);
+    const Warm2MFused<7, 0> f0 = make_2m<FT, Warm2MFused<7, 0>>(p);
     return host_pipeline<FT, 7, 4>(n, in, out, chunk,
                                    [&](int64_t m, const FT* const(&din)[7], FT* const(&dout)[4], cudaStream_t s) {
+                                       const char* w = "bmt2m_warm (host pipeline) kernel launch";
+                                       if (spec == 1) return launch_pointwise<FT, 7, 4, Warm2MFused<7, 1>, 128, 8, false>(f1, m, din, dout, s, w);
+                                       if (spec == 0) return launch_pointwise<FT, 7, 4, Warm2MFused<7, 0>, 128, 8, false>(f0, m, din, dout, s, w);
                                        return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false>(
-                                           f, m, din, dout, s, "bmt2m_warm (host pipeline) kernel launch");
+                                           f, m, din, dout, s, w);
                                    });
 }
 

@@ -61,7 +61,7 @@ template <class FT> struct FusedArgs {
 // copies, double-buffered: the next item streams in while this one is computed) and every family stores its tendencies and
 // accumulates its diagnostic as soon as it is done, so the live register set is that of ONE family at a time and the kernel
 // keeps the occupancy of the single-family kernels.
-template <class FT, int BLOCK, int MINB, bool SYNC>
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     math_tables_init<BLOCK>();
     extern __shared__ __align__(16) unsigned char fused_dyn_smem[];
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
         if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         // 2-moment warm rain (cloud ice seen by the thermodynamics = q_icl + q_sno)   BMT:820-854
         if (active) {
-            const Warm2M<D> o = warm_rain_tendencies_2m<D>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10),
+            const Warm2M<D> o = warm_rain_tendencies_2m<D, SPEC>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10),
                                                            fmax_(0.0, in(6)) + fmax_(0.0, in(8)));
             put(4, o.dq_lcl_dt);
             put(5, o.dn_lcl_dt);
@@ -184,14 +184,14 @@ template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
-template <class FT, int BLOCK, int MINB, bool SYNC> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
     void* ws = nullptr;
     int st = cmh::workspace(cmh::kPipeSlots /* slot reserved for the diagnostics partials */, sizeof(double) * NDIAG * (size_t)blocks + 64, &ws);
     if (st) return st;
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
-    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC>;
+    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC>;
     static bool attr_set = false;   // per instantiation; the attribute is per function and device-wide idempotent
     if (!attr_set || smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -229,26 +229,17 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
     for (int c = 0; c < NOUT; ++c) a.out[c] = out[c];
     a.n = n;
-    // launch shape: 768x1, no family barriers (see the top of the file); CUMICRO_FUSED_SHAPE=128x6|256x3|384x2|768x1[n] selects
-    // another one for measurements (a trailing 'n' = no barriers)
-    int shape = 3;
-    bool sync = false;
-    if (const char* e = std::getenv("CUMICRO_FUSED_SHAPE")) {
-        const std::string v(e);
-        shape = v.rfind("128", 0) == 0 ? 0 : v.rfind("256", 0) == 0 ? 1 : v.rfind("384", 0) == 0 ? 2 : 3;
-        sync = v.empty() || v.back() != 'n';
-    }
+    // launch shape: 768x1, no family barriers (see the top of the file; the sweep was run with every shape instantiated).
+    // CUMICRO_FUSED_SHAPE=128x6 selects the old shape for comparison.  The 2-moment family runs the instantiation specialised
+    // for the default SB2006 block structure when the block has it (cm_sb2006.cuh, sb2006_spec()).
+    bool small_blocks = false;
+    if (const char* e = std::getenv("CUMICRO_FUSED_SHAPE")) small_blocks = std::string(e).rfind("128", 0) == 0;
+    const int spec = sb2006_spec<D>(a.f.p2.sb);
     int st;
-    switch (shape * 2 + (sync ? 1 : 0)) {
-        case 0: st = launch_fused<FT, 128, 6, false>(a, n, s, diag); break;
-        case 1: st = launch_fused<FT, 128, 6, true>(a, n, s, diag); break;
-        case 2: st = launch_fused<FT, 256, 3, false>(a, n, s, diag); break;
-        case 3: st = launch_fused<FT, 256, 3, true>(a, n, s, diag); break;
-        case 4: st = launch_fused<FT, 384, 2, false>(a, n, s, diag); break;
-        case 5: st = launch_fused<FT, 384, 2, true>(a, n, s, diag); break;
-        case 6: st = launch_fused<FT, 768, 1, false>(a, n, s, diag); break;
-        default: st = launch_fused<FT, 768, 1, true>(a, n, s, diag); break;
-    }
+    if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
+    else if (spec == 1) st = launch_fused<FT, 768, 1, false, 1>(a, n, s, diag);
+    else if (spec == 0) st = launch_fused<FT, 768, 1, false, 0>(a, n, s, diag);
+    else st = launch_fused<FT, 768, 1, false, -1>(a, n, s, diag);
     if (st) return st;
     return cmh::cuda_status(cudaGetLastError(), "fused_1m2m_icenuc launch");
 }

@@ -96,3 +96,10 @@ def test_division_through_the_shared_reciprocal_is_ieee(lib):
     assert np.all(y[x == 0] == 0)
     assert np.mean(y == ref) > 0.9999, np.mean(y == ref)
     assert np.max(np.abs(y - ref) / np.maximum(np.abs(ref), 1e-300)) < 2.3e-16
+
+
+def test_log1p_of_a_positive_argument(lib):
+    """log1p_pos_ (Kahan's log(u) y/(u-1) on the table-driven log) over the range log1pexp feeds it: e^x, x in [-36.7, 18.02]."""
+    rng = np.random.default_rng(6)
+    y = np.concatenate([np.exp(rng.uniform(-36.7, 18.02, 4000)), 10 ** rng.uniform(-17, -14, 300), [1e-300, 1.0, 2.0 ** -53, 2.0 ** -52]])
+    assert _max_ulp(_run(lib, "cmt_log1p_pos", y), y, mp.log1p) < 4.5
