@@ -140,7 +140,7 @@ CM_DEV float log1pexp_(float x) {
 
 // CO.logistic_function_integral                                     CO:157-173
 template <class FT> CM_DEV FT logistic_function_integral(FT e, FT x, FT x_0, FT inv_x0_safe, FT k, FT inv_k, FT trnslt) {
-    x = fmax_(FT(0), x);
+    x = clamp0_(x);
     const FT x_safe = fmax_(x, e);
     const FT x0_safe = fmax_(x_0, e);
     const FT kt = k * (x_safe * inv_x0_safe - FT(1) + trnslt);
@@ -165,12 +165,12 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     const auto& o = p.processes;
     const auto& pp = p.pp;
     Src1M<FT> r;
-    rho = fmax_(FT(0), rho);                                           // BMT:146-151
-    q_tot = fmax_(FT(0), q_tot);
-    q_lcl = fmax_(FT(0), q_lcl);
-    q_icl = fmax_(FT(0), q_icl);
-    q_rai = fmax_(FT(0), q_rai);
-    q_sno = fmax_(FT(0), q_sno);
+    rho = clamp0_(rho);                                           // BMT:146-151
+    q_tot = clamp0_(q_tot);
+    q_lcl = clamp0_(q_lcl);
+    q_icl = clamp0_(q_icl);
+    q_rai = clamp0_(q_rai);
+    q_sno = clamp0_(q_sno);
     const FT inv_rho = rcp_(rho);
     const FT T_freeze = tk.T_freeze;
 
@@ -310,13 +310,13 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     if (o.rain_condensation_evaporation) {
         const FT vent_r = fma_(k.vent_rai_b * sqrt_(v0_r), exp_(fma_(k.vent_rai_x, dl_r, FT(0.5) * ll_r)), k.vent_rai_a);
         const FT rate = k.four_pi * p.rain.n0 * inv_rho * S_liq * G_liq * (lam_r * lam_r) * vent_r;
-        r.s[S1M_PHASE_VAP_RAI] = fmin_(FT(0), (q_rai > e && S_liq < FT(0)) ? rate : FT(0));
+        r.s[S1M_PHASE_VAP_RAI] = cap0_((q_rai > e && S_liq < FT(0)) ? rate : FT(0));
     } else
         r.s[S1M_PHASE_VAP_RAI] = FT(0);
     if (o.snow_deposition_sublimation) {
         const FT rate = k.four_pi * n0_s * inv_rho * S_ice * G_ice * (lam_s * lam_s) * vent_s;
         const FT v = (q_sno > e) ? rate : FT(0);
-        r.s[S1M_PHASE_VAP_SNO] = (o.snow_deposition_sublimation == CUMICRO_1M_SNOW_SUBLIMATION_ONLY) ? fmin_(FT(0), v) : v;
+        r.s[S1M_PHASE_VAP_SNO] = (o.snow_deposition_sublimation == CUMICRO_1M_SNOW_SUBLIMATION_ONLY) ? cap0_(v) : v;
     } else
         r.s[S1M_PHASE_VAP_SNO] = FT(0);
     const FT melt_common = k.four_pi * inv_rho * p.aps.K_therm * rcp_(Lf) * (T - T_freeze);
@@ -385,7 +385,7 @@ CM_DEV void linearized_implicit_step_1m(const typename P<FT>::params_1m& p, cons
     const FT q_sat_min = fmin_(div_(p_sat_liq(tk, ts), rRT), div_(p_sat_ice(tk, ts), rRT));
     const FT q_v = q_tot - q_lcl - q_icl - q_rai - q_sno;
     const FT e_sum = fmax_(e1 + e2 + e4, tk.eps);   // >= eps > 0; the numerator is an exact zero wherever the air is subsaturated
-    const FT alpha = fmin_(FT(1), divr_(fmax_(FT(0), q_v - q_sat_min) * inv_dt, e_sum, rcp_cr_(e_sum)));
+    const FT alpha = fmin_(FT(1), divr_(clamp0_(q_v - q_sat_min) * inv_dt, e_sum, rcp_cr_(e_sum)));
     const FT a11 = inv_dt - M11, a12 = -M12, a22 = inv_dt - M22, a31 = -M31, a33 = inv_dt - M33, a34 = -M34, a41 = -M41, a42 = -M42,
              a43 = -M43, a44 = inv_dt - M44;
     const FT b1 = alpha * e1 + inv_dt * q_lcl;

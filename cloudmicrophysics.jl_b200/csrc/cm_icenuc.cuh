@@ -146,7 +146,7 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT K_ice = k.four_pi * N_ice * r_ice * rhoGi * gamma_i;
     const FT aw = alpha * w;
     const FT S_max = S_max_ARG * (aw - K_ice * (xi - FT(1))) / fma_(K_liq + K_ice * xi, S_max_ARG, aw);
-    o.S_max = fmax_(FT(0), S_max);
+    o.S_max = clamp0_(S_max);
     const FT l_smax = log_g(o.S_max);   // -Inf when S_max = 0 (libm path): erf(+Inf) = 1 -> N_act = 0   (AA:256)
 #pragma unroll
     for (int i = 0; i < kMaxModes; ++i) {

@@ -571,7 +571,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         if ((want & P3_WANT_MELT) && s.T > tk.T_freeze) {
             const double L_f = latent_heat_fusion(tk, s.T);
             const double fac = 4.0 * k.K_therm / L_f * (s.T - k.T_freeze);
-            out.melt_dL = fmax_(0.0, fac * warp_sum(a_melt));
+            out.melt_dL = clamp0_(fac * warp_sum(a_melt));
             out.melt_dN = s.N_ice / s.L_ice * out.melt_dL;
         }
     }

@@ -150,12 +150,12 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     Warm2M<FT> o;
 
     // input clamps                                                   BMT:827-836
-    rho = fmax_(FT(0), rho);
-    q_tot = fmax_(FT(0), q_tot);
-    q_lcl = fmax_(FT(0), q_lcl);
-    q_rai = fmax_(FT(0), q_rai);
-    n_lcl = fmax_(FT(0), n_lcl);
-    n_rai = fmax_(FT(0), n_rai);
+    rho = clamp0_(rho);
+    q_tot = clamp0_(q_tot);
+    q_lcl = clamp0_(q_lcl);
+    q_rai = clamp0_(q_rai);
+    n_lcl = clamp0_(n_lcl);
+    n_rai = clamp0_(n_rai);
     const FT N_lcl = rho * n_lcl;   // BMT:718-719
     const FT N_rai = rho * n_rai;
     const FT inv_rho = rcp_(rho);
@@ -214,8 +214,8 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
         const FT Fv0 = fma_(b_vent_0, v, a_vent_0);
         const FT Fv1 = fma_(sb.evap.b_vent_1, v, sb.evap.a_vent_1);
         const FT common = sk.two_pi * G * S * N_rai * Dr;
-        const FT dn = fmin_(FT(0), common * Fv0 * inv_xr_mean);
-        const FT dq = fmin_(FT(0), common * Fv1 * inv_rho);
+        const FT dn = cap0_(common * Fv0 * inv_xr_mean);
+        const FT dq = cap0_(common * Fv1 * inv_rho);
         const bool off_q = (q_rai < e) || (N_rai <= e) || (S >= FT(0));
         const bool off_n = off_q || (xr_mean * sk.inv_xr_min < e);
         o.leaf[CUMICRO_SB_EVAP_DN_RAI] = off_n ? FT(0) : dn;
@@ -324,8 +324,8 @@ CM_DEV void rain_terminal_velocity_sb(const typename P<FT>::sb_pdf_r& pdf_r, con
     const FT s = sqrt_(vel.rho0 / rho);
     const FT d1 = FT(1) + vel.cR * Dr_mean;
     const FT d2 = d1 * d1;
-    const FT v0 = fmax_(FT(0), s * (vel.aR * pa0 - vel.bR * pb0 / d1));
-    const FT v1 = fmax_(FT(0), s * (vel.aR * pa1 - vel.bR * pb1 / (d2 * d2)));
+    const FT v0 = clamp0_(s * (vel.aR * pa0 - vel.bR * pb0 / d1));
+    const FT v1 = clamp0_(s * (vel.aR * pa1 - vel.bR * pb1 / (d2 * d2)));
     vt0 = (N_rai < e) ? FT(0) : v0;
     vt1 = (q_rai < e) ? FT(0) : v1;
 }
@@ -363,8 +363,8 @@ CM_DEV void rain_terminal_velocity_chen(const typename P<FT>::sb_pdf_r& pdf_r, c
     for (int i = 0; i < 3; ++i) v0 += chen2022_exponential_pdf<FT>(aiu[i], bi[i], ciu[i], ll, il, FT(1), FT(1));
 #pragma unroll
     for (int i = 0; i < 3; ++i) v3 += chen2022_exponential_pdf<FT>(aiu[i], bi[i], ciu[i], ll, il, FT(4), FT(1.0 / 6.0));
-    vt0 = (N_rai < e) ? FT(0) : fmax_(FT(0), v0);
-    vt1 = (q_rai < e) ? FT(0) : fmax_(FT(0), v3);
+    vt0 = (N_rai < e) ? FT(0) : clamp0_(v0);
+    vt1 = (q_rai < e) ? FT(0) : clamp0_(v3);
 }
 
 // CM2.cloud_terminal_velocity                                               CM2:647-664

@@ -69,7 +69,7 @@ template <class FT> CM_DEV FT cp_m(const ThermoK<FT>& k, FT qt, FT ql, FT qi) {
     return fma_(k.dcp_iv, qi, fma_(k.dcp_lv, ql, fma_(k.dcp_vd, qt, k.cp_d)));
 }
 // TDI.q_vap                                                       TDI:60-61
-template <class FT> CM_DEV FT q_vap(FT qt, FT ql, FT qi) { return fmax_(FT(0), qt - ql - qi); }
+template <class FT> CM_DEV FT q_vap(FT qt, FT ql, FT qi) { return clamp0_(qt - ql - qi); }
 
 // CO.G_func_liquid / G_func_ice                                    CO:47-102
 //   1 / (L/K/T (L/R_v/T - 1) + R_v T / D / p_vs); inv_p_vs = 1/max(p_vs, eps) from the caller.

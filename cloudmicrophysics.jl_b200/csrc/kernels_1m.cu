@@ -134,7 +134,7 @@ struct TermVel1M : OneMBase {
     __device__ __forceinline__ void operator()(const D (&x)[2], D (&y)[1]) const {
         const FT e = tk.eps_n;
         const FT rho = x[0], q = x[1];
-        const FT qp = fmax_(FT(0), q), rhop = fmax_(FT(0), rho);
+        const FT qp = clamp0_(q), rhop = clamp0_(rho);
         FT w = FT(0);
         if (kind == 0) {
             const FT v0 = sqrt_(FT(8.0 / 3) / p.vel_rain.C_drag * fmax_(p.vel_rain.rho_w / rho - FT(1), FT(0)) * p.vel_rain.grav * p.vel_rain.r0);
@@ -149,7 +149,7 @@ struct TermVel1M : OneMBase {
                 lambda_inverse(k.rai, log_full_(rhop * qp), k.log_n0_rai, lam, ll);
                 FT aiu[3], bi[3], ciu[3];
                 chen2022_vel_coeffs_rain<FT>(chen_rain, rho, aiu, bi, ciu);
-                w = fmax_(FT(0), chen_exponential_pdf_sum3<FT, 3>(aiu, bi, ciu, FT(2) * lam));
+                w = clamp0_(chen_exponential_pdf_sum3<FT, 3>(aiu, bi, ciu, FT(2) * lam));
             } else {
                 const FT log_n0 = (q > e) ? fma_(p.snow.nu, log_full_(rho * fmax_(q, e)), k.log_mu_sno) : k.log_eps_numerics;
                 lambda_inverse(k.sno, log_full_(rhop * qp), log_n0, lam, ll);
@@ -170,7 +170,7 @@ struct TermVel1M : OneMBase {
                 const FT aiu[2] = {Bl * pa * exp_full_(bi[0] * log1000), El * pa * exp_full_(Hl * ra) * exp_full_(bi[1] * log1000)};
                 const FT ciu[2] = {FT(0), Gl * FT(1000)};
                 const FT pk = pow_full_(p.snow.aspr_phi, p.snow.aspr_kappa);
-                w = fmax_(FT(0), pk * chen_exponential_pdf_sum3<FT, 2>(aiu, bi, ciu, FT(2) * lam));
+                w = clamp0_(pk * chen_exponential_pdf_sum3<FT, 2>(aiu, bi, ciu, FT(2) * lam));
             }
             w = (q > e) ? w : FT(0);
         } else if (kind == 4) {
@@ -194,7 +194,7 @@ struct TermVel1M : OneMBase {
             const FT D = cbrt_full_(FT(6 / 3.141592653589793238462643383279502884L) * rho * qp / p.cloud_ice.N_0 / p.cloud_ice.rho_i);
             const FT Db = pow_full_(D, b);
             const FT v = Es * pa * u * Db + Fs * pa * u * Db * exp_full_(-(Gs * FT(1000)) * D);   // Chen2022VelocityCurve
-            w = (q > e) ? fmax_(FT(0), v) : FT(0);
+            w = (q > e) ? clamp0_(v) : FT(0);
         }
         y[0] = w;
     }
@@ -262,9 +262,9 @@ template <class FT, bool WITH_SAT> struct ZeroM {
     FT tau_precip, qc_0, S_0;
     __device__ __forceinline__ void operator()(const double (&x)[WITH_SAT ? 3 : 2], double (&y)[1]) const {
         // the Float32 method's arithmetic is Float32 (three operations: nothing to gain from widening)
-        const FT q_lcl = cm::fmax_(FT(0), (FT)x[0]), q_icl = cm::fmax_(FT(0), (FT)x[1]);
+        const FT q_lcl = cm::clamp0_((FT)x[0]), q_icl = cm::clamp0_((FT)x[1]);
         const FT thr = WITH_SAT ? S_0 * (FT)x[2] : qc_0;
-        y[0] = (double)(-cm::fmax_(FT(0), q_lcl + q_icl - thr) / tau_precip);
+        y[0] = (double)(-cm::clamp0_(q_lcl + q_icl - thr) / tau_precip);
     }
 };
 template <class FT, class PB>

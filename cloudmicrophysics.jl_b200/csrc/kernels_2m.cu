@@ -29,7 +29,7 @@ template <int NIN = 7, int SPEC = -1> struct Warm2MFused {
     ThermoK<D> tk;
     SB2006K<D> sk;
     __device__ __forceinline__ void operator()(const D (&x)[NIN], D (&y)[4]) const {
-        const D q_ice = (NIN == 8) ? fmax_(D(0), x[NIN - 1]) : D(0);
+        const D q_ice = (NIN == 8) ? clamp0_(x[NIN - 1]) : D(0);
         Warm2M<D> o = warm_rain_tendencies_2m<D, SPEC>(p, tk, sk, x[0], x[1], x[2], x[3], x[4], x[5], x[6], q_ice);
         y[0] = o.dq_lcl_dt;
         y[1] = o.dn_lcl_dt;

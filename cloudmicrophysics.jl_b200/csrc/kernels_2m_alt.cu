@@ -16,7 +16,7 @@ using D = double;
 
 // CO.logistic_function (src/Common.jl:124-138)
 CM_DEV D logistic_function(D e, D x, D x_0, D k) {
-    x = fmax_(0.0, x);
+    x = clamp0_(x);
     const D x_safe = fmax_(x, e), x0_safe = fmax_(x_0, e);
     const D z = k * (x_safe / x0_safe - x0_safe / x_safe);
     const D result = exp_full_(-log1pexp_(-z));
@@ -34,12 +34,12 @@ struct Alt2M {
         D r = 0.0;
         switch (what) {
             case 0: {  // CM2:920-924
-                q_lcl = fmax_(0.0, q_lcl);
+                q_lcl = clamp0_(q_lcl);
                 r = p.kk_acnv_A * pow_full_(q_lcl, p.kk_acnv_a) * pow_full_(x[2], p.kk_acnv_b) * pow_full_(x[1], p.kk_acnv_c);
                 break;
             }
             case 1: {  // CM2:925-937
-                q_lcl = fmax_(0.0, q_lcl);
+                q_lcl = clamp0_(q_lcl);
                 const D rho = x[1], N_d = x[2];
                 D d;
                 if (smooth) {
@@ -53,7 +53,7 @@ struct Alt2M {
                 break;
             }
             case 2: {  // CM2:938-947
-                q_lcl = fmax_(0.0, q_lcl);
+                q_lcl = clamp0_(q_lcl);
                 const D rho = x[1], N_d = x[2];
                 const D thr = p.tc_acnv_m0_liq_coeff * N_d / rho * pow_full_(p.tc_acnv_r_0, p.tc_acnv_me_liq);
                 const D o = smooth ? logistic_function(eps_n, q_lcl, thr, p.tc_acnv_k) : heaviside(q_lcl - thr);
@@ -75,20 +75,20 @@ struct Alt2M {
                 break;
             }
             case 4: {  // CM2:985-990
-                q_lcl = fmax_(0.0, q_lcl);
-                const D q_rai = fmax_(0.0, x[1]);
+                q_lcl = clamp0_(q_lcl);
+                const D q_rai = clamp0_(x[1]);
                 r = p.kk_accr_A * pow_full_(q_lcl * q_rai, p.kk_accr_a) * pow_full_(x[2], p.kk_accr_b);
                 break;
             }
             case 5: {  // CM2:992-997
-                q_lcl = fmax_(0.0, q_lcl);
-                const D q_rai = fmax_(0.0, x[1]);
+                q_lcl = clamp0_(q_lcl);
+                const D q_rai = clamp0_(x[1]);
                 r = p.b_accr_A * q_lcl * x[2] * q_rai;
                 break;
             }
             default: {  // 6: CM2:999-1005
-                q_lcl = fmax_(0.0, q_lcl);
-                const D q_rai = fmax_(0.0, x[1]);
+                q_lcl = clamp0_(q_lcl);
+                const D q_rai = clamp0_(x[1]);
                 r = p.tc_accr_A * q_lcl * q_rai;
                 break;
             }

@@ -42,7 +42,7 @@ struct Diag2M {
             Mr[i] = nr ? 0.0 : N_rai * pow_full_(Br, er[i]) * gr[i] / gr0;
         }
         const D Zc = nc ? 0.0 : Mc[0] / (C * C), Zr = nr ? 0.0 : Mr[0] / (C * C);
-        y[0] = fmax_(-150.0, 10.0 * (log10(fmax_(0.0, Zc + Zr)) - (-18.0)));
+        y[0] = fmax_(-150.0, 10.0 * (log10(clamp0_(Zc + Zr)) - (-18.0)));
         const D M3 = (nc ? 0.0 : Mc[1] / C) + (nr ? 0.0 : Mr[1] / C);
         const D M2 = (nc ? 0.0 : Mc[2] / C_23) + (nr ? 0.0 : Mr[2] / C_23);
         y[1] = (M2 <= eps_n) ? 0.0 : M3 / M2;
@@ -54,7 +54,7 @@ struct Diag1M {
     D n0, inv_exp, r0_pow, denom, lam_floor;   // CM1.lambda_inverse pieces (CM1:126-152)
     D eps_n, c1em12, c1em3;
     __device__ __forceinline__ void operator()(const D (&x)[2], D (&y)[1]) const {
-        const D q = fmax_(0.0, x[0]), rho = fmax_(0.0, x[1]);
+        const D q = clamp0_(x[0]), rho = clamp0_(x[1]);
         const D lam = fmax_(lam_floor, pow_full_(rho * q * r0_pow / denom, inv_exp));
         const D lam_mm = lam / c1em3;
         const D Z = 720.0 * (n0 * c1em12) * pow_full_(lam_mm, 7.0);

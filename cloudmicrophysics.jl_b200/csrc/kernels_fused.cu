@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
         // 2-moment warm rain (cloud ice seen by the thermodynamics = q_icl + q_sno)   BMT:820-854
         if (active) {
             const Warm2M<D> o = warm_rain_tendencies_2m<D, SPEC>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10),
-                                                           fmax_(0.0, in(6)) + fmax_(0.0, in(8)));
+                                                           clamp0_(in(6)) + clamp0_(in(8)));
             put(4, o.dq_lcl_dt);
             put(5, o.dn_lcl_dt);
             put(6, o.dq_rai_dt);

@@ -71,7 +71,7 @@ struct IceNucLeaf : IceNucBase {
                 const bool warm = x[1] > p.mohler.T_thr;
                 const D S0 = warm ? p.dust.S0_warm : p.dust.S0_cold;
                 const D a = warm ? p.dust.a_warm : p.dust.a_cold;
-                v = fmax_(0.0, exp_full_(a * (x[0] - S0)) - 1.0);
+                v = clamp0_(exp_full_(a * (x[0] - S0)) - 1.0);
                 break;
             }
             default: break;
@@ -92,7 +92,7 @@ struct IceNucRates : IceNucBase {
             case 0: {                                                            // IN.MohlerDepositionRate(Si, T, dSi_dt, N_aer)
                 err = !(x[0] < p.mohler.Si_max);
                 const D a = (x[1] > p.mohler.T_thr) ? p.dust.a_warm : p.dust.a_cold;
-                v = fmax_(0.0, x[3] * a * x[2]);
+                v = clamp0_(x[3] * a * x[2]);
                 break;
             }
             case 1: {                                                            // IN.P3_het_N_i(T, N_l, V_l, dt)
@@ -113,8 +113,8 @@ struct IceNucRates : IceNucBase {
                 const D a_w_ice = p_sat_ice(tk, ts) / p_sat_liq(tk, ts);
                 const D J = ABIFM_J<D>(p.dust, x[2] - a_w_ice, k.ln10);
                 const D JA = isfinite(J) ? J * 1e-10 : 0.0;
-                v = fmax_(0.0, JA * x[1]);
-                v2 = fmax_(0.0, JA * x[0] * x[4]);
+                v = clamp0_(JA * x[1]);
+                v2 = clamp0_(JA * x[0] * x[4]);
                 break;
             }
             default: break;

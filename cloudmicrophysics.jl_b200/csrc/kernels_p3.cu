@@ -78,9 +78,9 @@ CM_DEV F23Rates f23_rates(const cumicro_params_p3_f64& p, const ThermoK<double>&
     {
         const double S_i = qv / q_sat_ice - 1.0;
         const bool cond = (T < k.frost_T_freeze - 15.0) && (S_i > 0.05);
-        const double a = fmax_(0.0, inpc - x.n_ice) / k.tau_act;
+        const double a = clamp0_(inpc - x.n_ice) / k.tau_act;
         o.dep_dn = cond ? a : 0.0;
-        const double q_excess = fmax_(0.0, qv - q_sat_ice);
+        const double q_excess = clamp0_(qv - q_sat_ice);
         o.dep_dq = fmin_(k.m_nuc * o.dep_dn, q_excess / (2.0 * k.tau_act));
     }
     const double J_bigg = k.het_B * exp_full_(k.het_a * (tk.T_freeze - T));
@@ -97,7 +97,7 @@ CM_DEV F23Rates f23_rates(const cumicro_params_p3_f64& p, const ThermoK<double>&
         const bool cond = (n > e) && (x.q_lcl > e) && (T < tk.T_freeze - 4.0);
         o.cld_dn = cond ? J_bigg * k.V1 * M3 : 0.0;
         o.cld_dq = cond ? J_bigg * k.rho_w * (k.V1 * k.V1) * M6 : 0.0;
-        o.cap_dn = (T >= k.frost_T_freeze) ? 0.0 : fmax_(0.0, inpc - x.n_ice) / k.tau_act;
+        o.cap_dn = (T >= k.frost_T_freeze) ? 0.0 : clamp0_(inpc - x.n_ice) / k.tau_act;
     }
     {
         const double n = x.N_rai / rho;
@@ -162,7 +162,7 @@ CM_DEV void bmt2m_p3_assemble(const cumicro_params_p3_f64& p, const ThermoK<doub
         const double Gam = 1.0 + Ls / cp_air * dqsi_dT;
         const double se = qv - q_sat_ice;
         const double timescale = k.subdep_tau * Gam;
-        double tend = (se < 0.0) ? -fmin_(-se, fmax_(0.0, x.q_ice)) / timescale : se / timescale;
+        double tend = (se < 0.0) ? -fmin_(-se, clamp0_(x.q_ice)) / timescale : se / timescale;
         tend = ((T > tk.T_freeze) && (tend > 0.0)) ? 0.0 : tend;                       // NEQ.INP_limiter
         tend = (T > tk.T_freeze) ? fmin_(tend, 0.0) : tend;
         const double dn_d = (tend < 0.0) ? n_per_q * tend : 0.0;
@@ -225,9 +225,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
             x.q_ice = x.n_ice = x.q_rim = x.b_rim = 0.0;
             x.L_lcl = x.N_lcl = x.L_rai = x.N_rai = 0.0;
         } else {                  // in: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl [, inpc_log_shift]
-            x.rho = fmax_(0.0, ld(0)); x.T = ld(1); x.q_tot = fmax_(0.0, ld(2)); x.q_lcl = fmax_(0.0, ld(3)); x.n_lcl = fmax_(0.0, ld(4));
-            x.q_rai = fmax_(0.0, ld(5)); x.n_rai = fmax_(0.0, ld(6)); x.q_ice = fmax_(0.0, ld(7)); x.n_ice = fmax_(0.0, ld(8));
-            x.q_rim = fmax_(0.0, ld(9)); x.b_rim = fmax_(0.0, ld(10)); x.logl = ld(11); x.shift = ld(12);
+            x.rho = clamp0_(ld(0)); x.T = ld(1); x.q_tot = clamp0_(ld(2)); x.q_lcl = clamp0_(ld(3)); x.n_lcl = clamp0_(ld(4));
+            x.q_rai = clamp0_(ld(5)); x.n_rai = clamp0_(ld(6)); x.q_ice = clamp0_(ld(7)); x.n_ice = clamp0_(ld(8));
+            x.q_rim = clamp0_(ld(9)); x.b_rim = clamp0_(ld(10)); x.logl = ld(11); x.shift = ld(12);
             x.L_lcl = x.q_lcl * x.rho; x.L_rai = x.q_rai * x.rho; x.N_lcl = x.n_lcl * x.rho; x.N_rai = x.n_rai * x.rho;
             x.L_ice = x.q_ice * x.rho; x.N_ice = x.n_ice * x.rho; x.L_rim = x.q_rim * x.rho; x.B_rim = x.b_rim * x.rho;
         }
@@ -333,9 +333,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
             x.q_ice = x.n_ice = x.q_rim = x.b_rim = 0.0;
             x.L_lcl = x.N_lcl = x.L_rai = x.N_rai = 0.0;
         } else {                  // in: rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logl [, inpc_log_shift]
-            x.rho = fmax_(0.0, ld(0)); x.T = ld(1); x.q_tot = fmax_(0.0, ld(2)); x.q_lcl = fmax_(0.0, ld(3)); x.n_lcl = fmax_(0.0, ld(4));
-            x.q_rai = fmax_(0.0, ld(5)); x.n_rai = fmax_(0.0, ld(6)); x.q_ice = fmax_(0.0, ld(7)); x.n_ice = fmax_(0.0, ld(8));
-            x.q_rim = fmax_(0.0, ld(9)); x.b_rim = fmax_(0.0, ld(10)); x.logl = ld(11); x.shift = ld(12);
+            x.rho = clamp0_(ld(0)); x.T = ld(1); x.q_tot = clamp0_(ld(2)); x.q_lcl = clamp0_(ld(3)); x.n_lcl = clamp0_(ld(4));
+            x.q_rai = clamp0_(ld(5)); x.n_rai = clamp0_(ld(6)); x.q_ice = clamp0_(ld(7)); x.n_ice = clamp0_(ld(8));
+            x.q_rim = clamp0_(ld(9)); x.b_rim = clamp0_(ld(10)); x.logl = ld(11); x.shift = ld(12);
             x.L_lcl = x.q_lcl * x.rho; x.L_rai = x.q_rai * x.rho; x.N_lcl = x.n_lcl * x.rho; x.N_rai = x.n_rai * x.rho;
             x.L_ice = x.q_ice * x.rho; x.N_ice = x.n_ice * x.rho; x.L_rim = x.q_rim * x.rho; x.B_rim = x.b_rim * x.rho;
         }
@@ -459,8 +459,8 @@ template <bool WITH_SHIFT> struct F23Functor {
     P3K k;
     __device__ __forceinline__ void operator()(const double (&v)[WITH_SHIFT ? 10 : 9], double (&y)[7]) const {
         Pt x{};
-        x.rho = fmax_(0.0, v[0]); x.T = v[1]; x.q_tot = fmax_(0.0, v[2]); x.q_lcl = fmax_(0.0, v[3]); x.n_lcl = fmax_(0.0, v[4]);
-        x.q_rai = fmax_(0.0, v[5]); x.n_rai = fmax_(0.0, v[6]); x.q_ice = fmax_(0.0, v[7]); x.n_ice = fmax_(0.0, v[8]); x.shift = WITH_SHIFT ? v[WITH_SHIFT ? 9 : 0] : 0.0;
+        x.rho = clamp0_(v[0]); x.T = v[1]; x.q_tot = clamp0_(v[2]); x.q_lcl = clamp0_(v[3]); x.n_lcl = clamp0_(v[4]);
+        x.q_rai = clamp0_(v[5]); x.n_rai = clamp0_(v[6]); x.q_ice = clamp0_(v[7]); x.n_ice = clamp0_(v[8]); x.shift = WITH_SHIFT ? v[WITH_SHIFT ? 9 : 0] : 0.0;
         x.N_lcl = x.n_lcl * x.rho; x.N_rai = x.n_rai * x.rho;
         const F23Rates f = f23_rates(p, tk, sk, k, x);
         y[0] = f.rain_dn; y[1] = f.rain_dq; y[2] = f.cld_dn; y[3] = f.cld_dq; y[4] = f.cap_dn; y[5] = f.dep_dn; y[6] = f.dep_dq;
