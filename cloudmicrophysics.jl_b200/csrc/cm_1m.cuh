@@ -205,7 +205,7 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     const FT log_n0_s = has_sno ? fma_(p.snow.nu, L_sno, k.log_mu_sno) : k.log_eps_numerics;
     const FT n0_s = has_sno ? exp_(log_n0_s) : FT(0);                  // CM1.get_n0 (snow)
     lambda_inverse(k.sno, L_sno, log_n0_s, lam_s, ll_s);
-    const FT v0_r = sqrt_(k.v0_rai_pref * fmax_(p.vel_rain.rho_w * inv_rho - FT(1), FT(0)));   // CM1.get_v0 (rain)
+    const FT v0_r = sqrtg_(k.v0_rai_pref * fmax_(p.vel_rain.rho_w * inv_rho - FT(1), FT(0)));   // CM1.get_v0 (rain)
     const FT dl_r = ll_r - k.rai.log_r0, dl_s = ll_s - k.sno.log_r0;   // log(λ⁻¹/r0)
 
     // ---- phase change vapour <-> cloud                               NEQ:110-224
@@ -284,7 +284,7 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
         const FT v_r = (q_rai > e) ? k.vt_rai_pref * v0_r * exp_(k.vt_rai_x * dl_r) : FT(0);   // CM1.terminal_velocity (Blk1M)
         const FT v_s = (q_sno > e) ? k.vt_sno_pref * exp_(k.vt_sno_x * dl_s) : FT(0);
         const FT dv = v_s - v_r;                                        // IEEE, reference order (cancellation)
-        const FT dv_eff = sqrt_(dv * dv + k.coeff_disp * (v_s * v_s + v_r * v_r));
+        const FT dv_eff = sqrtg_(dv * dv + k.coeff_disp * (v_s * v_s + v_r * v_r));
         const FT common = inv_rho * n0_s * p.rain.n0 * dv_eff;
         // arm (i, j) = (snow, rain):  λ_i³λ_j^(δ+1) ... with δ = rain me+Δm
         const FT dr = k.rs_rai_delta, ds = k.rs_sno_delta;
@@ -308,7 +308,7 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     // a + b cbrt(Sc) Γvent sqrt(2 v0 χv/ν λ⁻¹) (λ⁻¹/r0)^((ve+Δv)/2)
     const FT vent_s = fma_(k.vent_sno_b, exp_(fma_(k.vent_sno_x, dl_s, FT(0.5) * ll_s)), k.vent_sno_a);
     if (o.rain_condensation_evaporation) {
-        const FT vent_r = fma_(k.vent_rai_b * sqrt_(v0_r), exp_(fma_(k.vent_rai_x, dl_r, FT(0.5) * ll_r)), k.vent_rai_a);
+        const FT vent_r = fma_(k.vent_rai_b * sqrtg_(v0_r), exp_(fma_(k.vent_rai_x, dl_r, FT(0.5) * ll_r)), k.vent_rai_a);
         const FT rate = k.four_pi * p.rain.n0 * inv_rho * S_liq * G_liq * (lam_r * lam_r) * vent_r;
         r.s[S1M_PHASE_VAP_RAI] = cap0_((q_rai > e && S_liq < FT(0)) ? rate : FT(0));
     } else

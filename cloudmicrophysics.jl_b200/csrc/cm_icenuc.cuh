@@ -110,11 +110,11 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT gamma = fma_(common_g, Lv, R_v * T * inv_pvs);
     const FT A = k.A_coef * ts.inv_T;
     const FT aw_G = alpha * w * rcp_(G);
-    const FT sq = sqrt_(aw_G);
+    const FT sq = sqrtg_(aw_G);
     const FT zeta = FT(2.0 / 3.0) * A * sq;
     const FT sq3 = sq * sq * sq;
     const FT inv_gamma = rcp_(gamma);
-    const FT Tm32 = ts.inv_T * sqrt_(ts.inv_T);
+    const FT Tm32 = ts.inv_T * sqrtg_(ts.inv_T);
     const FT l_zeta = logp_(zeta);
     // logarithms: log S_m,i = log(sm_coef_i) - 3/2 log T and log η_i = log(sq³/γ) - log(2π ρ_w N_i) come from host-side
     // logarithms of the parameters plus two per-point ones; per mode only log(η_i + 3ζ) remains
@@ -136,7 +136,7 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
         const FT t2 = exp_full_(ap.p2 * (FT(2) * l_Sm[i] - log_g(fma_(FT(3), zeta, eta))));
         tmp += rcp_(Sm2) * fma_(k.f[i], t1, k.g[i] * t2);
     }
-    const FT S_max_ARG = FT(1) / sqrt_(tmp);
+    const FT S_max_ARG = FT(1) / sqrtg_(tmp);
     const FT r_liq = (N_liq < tk.eps) ? FT(0) : cbrt_full_(rho_air * q_liq / N_liq / k.c43pi_rho_w);
     const FT K_liq = k.four_pi * ap.rho_w * N_liq * r_liq * G * gamma;
     const FT gamma_i = fma_(common_g, Ls, R_v * T * inv_pvs);

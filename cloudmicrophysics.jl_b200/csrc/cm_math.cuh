@@ -218,6 +218,9 @@ CM_HD double sqrtp_(double x) {
     return fma(g, e, g);       // 80 bits -> rounding only
 }
 CM_HD float sqrtp_(float x) { return sqrtf(x); }
+// guarded form: the faithful 7-instruction sqrtp_ for positive normal arguments, IEEE sqrt (0, subnormal, Inf, NaN, negative) otherwise
+CM_HD double sqrtg_(double x) { return (x > 2.3e-308 && x < 1.7e308) ? sqrtp_(x) : sqrt(x); }
+CM_HD float sqrtg_(float x) { return sqrtf(x); }
 CM_HD float rcp_(float x) { return 1.0f / x; }
 
 // ---- exp: |x| <= 708 (callers' arguments are bounded; see exp_full_ otherwise) ---------------
