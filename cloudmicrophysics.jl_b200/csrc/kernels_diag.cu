@@ -84,7 +84,7 @@ int diag_2m_impl(const PC* pc, const PR* pr, int64_t n, const FT* q_lcl, const F
     FT* out[2] = {Z, reff};
     int st;
     if ((st = validate_columns<FT, 5>(pc, n, in))) return st;
-    if (Z == nullptr && reff == nullptr) return cmh::fail(CUMICRO_E_NULL, "both output columns are NULL");
+    if (n > 0 && Z == nullptr && reff == nullptr) return cmh::fail(CUMICRO_E_NULL, "both output columns are NULL");
     Diag2M f{};
     widen(*pc, f.pdf_c);
     widen(*pr, f.pdf_r);

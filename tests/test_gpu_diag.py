@@ -93,3 +93,32 @@ def test_diag_1m_and_liu_hallett_parity(built, orc, cuda):
     assert np.abs(got3[ref3 != 0] / ref3[ref3 != 0] - 1).max() <= 1e-12
     with pytest.raises(TypeError):
         CMD.effective_radius_Liu_Hallet_97(1000.0, *_dev([rho, qa, N_l], cuda))
+
+
+@pytest.mark.parametrize("n", [0, 1, 33, 1000])
+def test_leaf_entry_points_ragged_sizes_and_misaligned_columns(built, orc, cuda, n):
+    """Empty, tiny and ragged columns, and columns that start 8 bytes off a 16-byte boundary (the scalar-access path),
+    through the diagnostics and the alternative-closure entry points: same bits as the aligned call."""
+    import torch
+    CMP, CMD, CM2 = built.CMP, built.CMD, built.CM2
+    rng = np.random.Generator(np.random.PCG64(n + 1))
+    mk = lambda lo, hi: torch.from_numpy(10.0 ** rng.uniform(lo, hi, n + 1)).to(cuda)
+    q_l, q_r, N_l, N_r, rho = mk(-6, -3), mk(-7, -3), mk(6, 9), mk(2, 6), mk(-0.5, 0.1)
+    sb = CMP.SB2006(np.float64)
+    al = [t[:n].clone() for t in (q_l, q_r, N_l, N_r, rho)]          # aligned copies
+    mis = [t[1:n + 1] for t in (q_l, q_r, N_l, N_r, rho)]            # views at +8 bytes
+    al_of_mis = [t.clone() for t in mis]
+    Z, r = CMD.radar_reflectivity_and_effective_radius_2M(sb, *al)
+    assert Z.shape == (n,) and r.shape == (n,)
+    Zm, rm = CMD.radar_reflectivity_and_effective_radius_2M(sb, *mis)
+    Za, ra = CMD.radar_reflectivity_and_effective_radius_2M(sb, *al_of_mis)
+    assert torch.equal(Zm, Za) and torch.equal(rm, ra)
+    if n:
+        Zr, rr = orc.diag_2m(sb.pdf_c, sb.pdf_r, *[t.cpu().numpy() for t in al])
+        assert np.all(np.abs(Z.cpu().numpy() - Zr) <= 1e-11 + 1e-12 * np.abs(Zr))
+    kk = CMP.KK2000(np.float64)
+    a = CM2.conv_q_lcl_to_q_rai(kk, mis[0], mis[4], mis[2])
+    b = CM2.conv_q_lcl_to_q_rai(kk, al_of_mis[0], al_of_mis[4], al_of_mis[2])
+    assert a.shape == (n,) and torch.equal(a, b)
+    lh = CMD.effective_radius_Liu_Hallet_97(1000.0, mis[4], mis[0])
+    assert lh.shape == (n,) and torch.equal(lh, CMD.effective_radius_Liu_Hallet_97(1000.0, al_of_mis[4], al_of_mis[0]))
