@@ -274,7 +274,7 @@ def main():
                    "l2": "inputs (7 x 134 MB columns) larger than the 126 MB L2; no flush needed",
                    "psd": "SB2006 limited rain PSD, log-uniform number concentrations"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel_pipelined<double,7,4,Warm2MFused,128x7> (cp.async double-buffered inputs, 16 waves)",
+                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel_pipelined<double,7,4,Warm2MFused<7,SPEC=1>,128x7> (cp.async double-buffered inputs, 16 waves; specialised for the default SB2006 block structure)",
                      "kernel_ms": kernel_ms, "bytes_per_point": BYTES_PER_POINT},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 7 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n,
                 "steps": args.e2e_steps, "api": "cumicro_bmt2m_warm_host_f64 (pinned host buffers, chunked H2D/kernel/D2H)"},
@@ -292,6 +292,10 @@ def main():
                 tf = fl * value / world / 1e12
                 line["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                          "frac": tf / fp64_peak, "flops_per_point": fl, "source": pj.get("source")}
+                ai = pj.get("fp64_arith_inst_per_point_2m_warm")
+                if ai:   # DFMA, DMUL and DADD all take one FP64 issue slot: the pipe's own roofline is instructions, not flops
+                    line["roofline_fp64"]["issue_frac"] = ai * value / world / (fp64_peak * 1e12 / 2.0)
+                    line["roofline_fp64"]["fp64_inst_per_point"] = ai
             if pj.get("dram_bytes_per_launch_2m_warm"):
                 line["roofline"]["traffic"] = pj["dram_bytes_per_launch_2m_warm"]
         except Exception:
