@@ -163,6 +163,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly ONE JSON line: libraries that print there on their own (NCCL's "NCCL version ..." banner at
+    # communicator creation) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import cumicro
     from cumicro import BMT, CMP
@@ -319,7 +325,8 @@ def main():
         line["cpu_baseline"] = {"value": m * reps / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                                 "sample": f"first {m} points of the workload x {reps} passes, OpenMP over points "
                                           "(C++ restatement of the reference's scalar Julia methods)"}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

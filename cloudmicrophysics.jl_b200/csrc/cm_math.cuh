@@ -325,7 +325,8 @@ CM_HD double pow_full_(double x, double y) { return pow(x, y); }
 CM_HD float pow_full_(float x, float y) { return powf(x, y); }
 
 // ---- cbrt: positive, normal, finite x -------------------------------------------------------
-CM_HD double cbrtp_(double x) {
+// cbrt_pair_: y = x^(1/3) (< 1 ulp) and rc = x^(-1/3) (< 1.5 ulp) for two more FMAs: the iterate the cube root is built from, refined
+CM_HD double cbrt_pair_(double x, double& rc) {
     const int hx = hi32(x);
     const int e = (hx >> 20) - 1023;               // x = m 2^e, m in [1, 2)
     const int q = ((e + 3072) * 43691 >> 17) - 1024;  // floor(e / 3) for |e| <= 1100
@@ -350,8 +351,22 @@ CM_HD double cbrtp_(double x) {
     // one Newton correction with the residual computed by fma: y -= (y^3 - a) / (3 y^2)
     const double d = fma(-(y * y), y, a);
     y = fma(d, r2 * CM_CBRT_C1, y);
+    // r is a^(-1/3) to ~1e-13 only (the 21-bit immediate 1/3 above): one Newton step against the finished cube root
+    const double rn = fma(r, fma(-y, r, 1.0), r);
+    rc = mk64(hi32(rn) - (q << 20), lo32(rn));
     return mk64(hi32(y) + (q << 20), lo32(y));
 }
+CM_HD double cbrtp_(double x) {
+    double rc;
+    return cbrt_pair_(x, rc);
+}
+CM_HD double rcbrtp_(double x) {   // x^(-1/3), ~2 ulp
+    double rc;
+    cbrt_pair_(x, rc);
+    return rc;
+}
+CM_HD float cbrt_pair_(float x, float& rc) { const float y = cbrtf(x); rc = 1.0f / y; return y; }
+CM_HD float rcbrtp_(float x) { return 1.0f / cbrtf(x); }
 CM_HD float cbrtp_(float x) { return cbrtf(x); }
 CM_HD double cbrt_full_(double x) { return cbrt(x); }
 CM_HD float cbrt_full_(float x) { return cbrtf(x); }

@@ -22,6 +22,7 @@ template <class FT> struct SB2006K {
     FT inv_x_star;    // 1/acnv.x_star
     FT lclsc_pref;    // kcc (nu_c+2)/(nu_c+1) rho0
     FT pi_rho_w;      // pi rho_w (rain pdf)
+    FT cbrt_pi_rho_w;
     FT six_over_pi_rho_w;
     FT six_x_star_r;  // 6 * pdf_r.xr_min (evaporation t_star)
     FT inv_xr_min;    // 1/pdf_r.xr_min
@@ -47,6 +48,7 @@ __host__ inline SB2006K<FT> make_sb2006_k(const typename P<FT>::sb2006& sb, cons
     k.inv_x_star = FT(1) / sb.acnv.x_star;
     k.lclsc_pref = sb.acnv.kcc * (nu_c + 2) / (nu_c + 1) * sb.acnv.rho0;
     k.pi_rho_w = pi * sb.pdf_r.rho_w;
+    k.cbrt_pi_rho_w = std::cbrt(k.pi_rho_w);
     k.six_over_pi_rho_w = FT(6) / (pi * sb.pdf_r.rho_w);
     k.six_x_star_r = FT(6) * sb.pdf_r.xr_min;
     k.inv_xr_min = FT(1) / sb.pdf_r.xr_min;
@@ -88,8 +90,10 @@ template <class FT> struct RainPDF { FT N0r, Dr_mean, xr_mean, lam; };
 // CM2.pdf_rain_parameters                                          CM2:67-110
 // (q and N are the caller's already-floored safe values, as at every reference call site.)
 // LIM: -1 = the variant is read from the block at run time, 0 / 1 = known at compile time (SB2006Spec below).
-template <class FT, int LIM = -1>
-CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT pi_rho_w, FT e, FT q, FT rho, FT N) {
+// cbrt_pi_rho_w: cbrt(π ρw) from the host (SB2006K) or 0 = not supplied (Eq. 95 then takes the cube root of the quotient).
+template <class FT, int LIM = -1, bool HAVE_CBRT = false>
+CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT pi_rho_w, FT e, FT q, FT rho, FT N,
+                                       FT cbrt_pi_rho_w = FT(0)) {
     const FT safe_q = fmax_(q, e);
     const FT safe_N = fmax_(N, e);
     const FT L = rho * safe_q;
@@ -106,7 +110,8 @@ CM_DEV RainPDF<FT> pdf_rain_parameters(const typename P<FT>::sb_pdf_r& pdf, FT p
     } else {
         const FT inv_L = rcp_(L);
         const FT xt = clamp_(L * rcp_(safe_N), pdf.xr_min, pdf.xr_max);                       // SB2006 Eq. (94)
-        const FT N0r = clamp_(safe_N * cbrtp_(pi_rho_w * rcp_(xt)), pdf.N0_min, pdf.N0_max);  // Eq. (95)
+        const FT c95 = HAVE_CBRT ? cbrt_pi_rho_w * rcbrtp_(xt) : cbrtp_(pi_rho_w * rcp_(xt));   // cbrt(π ρw / xt)
+        const FT N0r = clamp_(safe_N * c95, pdf.N0_min, pdf.N0_max);  // Eq. (95)
         const FT lam = clamp_(sqrtp_(sqrtp_(pi_rho_w * N0r * inv_L)), pdf.lam_min, pdf.lam_max);  // Eq. (96)
         const FT xr_mean = clamp_(L * lam * rcp_(N0r), pdf.xr_min, pdf.xr_max);                // Eq. (97)
         const bool cond = (N < e) && (q < e);
@@ -185,11 +190,12 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     const FT safe_q_rai = fmax_(q_rai, e);
     const FT safe_N_rai = fmax_(N_rai, e);
     constexpr bool STD = SPEC >= 0;
-    const RainPDF<FT> rp = pdf_rain_parameters<FT, STD ? (SPEC & 1) : -1>(sb.pdf_r, sk.pi_rho_w, e, safe_q_rai, rho, safe_N_rai);
+    const RainPDF<FT> rp = pdf_rain_parameters<FT, STD ? (SPEC & 1) : -1, true>(sb.pdf_r, sk.pi_rho_w, e, safe_q_rai, rho, safe_N_rai,
+                                                                               sk.cbrt_pi_rho_w);
     const FT xr_mean = rp.xr_mean;
     // every power of xr_mean below comes from ONE cube root and ONE logarithm
-    const FT cx = cbrtp_(xr_mean);
-    const FT inv_cx = rcp_(cx);
+    FT inv_cx;                                  // xr_mean^(-1/3) comes out of the same iteration as the cube root
+    const FT cx = cbrt_pair_(xr_mean, inv_cx);
     const FT inv_xr_mean = inv_cx * inv_cx * inv_cx;
     const FT Dr = cx * sk.cbrt_six_over_pi_rho_w;  // cbrt(6 xr/(pi rho_w)): mean-volume diameter  CM2:590, 802
     const FT sqrt_rho0_rho = sqrtp_(sb.pdf_r.rho0 * inv_rho);

@@ -63,6 +63,7 @@ def test_cbrt_and_rcp(lib):
     x = np.concatenate([10 ** rng.uniform(-300, 300, 1500), rng.uniform(0.5, 16, 1500)])
     assert _max_ulp(_run(lib, "cmt_cbrt", x), x, mp.cbrt) < 1.0
     assert _max_ulp(_run(lib, "cmt_rcp", x), x, lambda t: 1 / t) < 1.0
+    assert _max_ulp(_run(lib, "cmt_rcbrt", x), x, lambda t: 1 / mp.cbrt(t)) < 2.5   # the by-product x^(-1/3) of cbrt_pair_
     assert _max_ulp(_run(lib, "cmt_sqrt", x), x, mp.sqrt) < 1.0
 
 
