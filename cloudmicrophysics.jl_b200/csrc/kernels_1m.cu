@@ -24,7 +24,7 @@
 #define CUMICRO_1MV_MINB 8   /* verbose: 4 -> 1.75 ms, 6 -> 1.34, 8 -> 1.22; linavg: 3.07, 3.01, 2.94 */
 #endif
 #ifndef CUMICRO_1M_MINB
-#define CUMICRO_1M_MINB 8   /* sweep at 2^24 points: 5 -> 1.224 ms, 6 -> 1.118, 8 -> 1.043 */
+#define CUMICRO_1M_MINB 8   /* sweep at 2^24 points: 5 -> 1.224 ms, 6 -> 1.118, 8 -> 1.043; later: 7 -> 0.937, 8 -> 0.916 */
 #endif
 namespace {
 

@@ -34,7 +34,7 @@ constexpr int NDIAG = CUMICRO_NDIAG;
 // -> one block per SM WITHOUT barriers: its warps start together and stay loosely in phase; the barrier's wait for the
 // slowest warp then costs more than the residual drift.
 #ifndef CUMICRO_FUSED_BLOCK
-#define CUMICRO_FUSED_BLOCK 768
+#define CUMICRO_FUSED_BLOCK 896   /* one block per SM: 640 2.53, 768 2.47, 896 2.42, 1024 2.47 ms (after the SB2006 specialisation) */
 #define CUMICRO_FUSED_MINB 1
 #endif
 
@@ -229,7 +229,7 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
     for (int c = 0; c < NOUT; ++c) a.out[c] = out[c];
     a.n = n;
-    // launch shape: 768x1, no family barriers (see the top of the file; the sweep was run with every shape instantiated).
+    // launch shape: one block of CUMICRO_FUSED_BLOCK threads per SM, no family barriers (see the top of the file; the sweep was run with every shape instantiated).
     // CUMICRO_FUSED_SHAPE=128x6 selects the old shape for comparison.  The 2-moment family runs the instantiation specialised
     // for the default SB2006 block structure when the block has it (cm_sb2006.cuh, sb2006_spec()).
     bool small_blocks = false;
@@ -237,9 +237,9 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     const int spec = sb2006_spec<D>(a.f.p2.sb);
     int st;
     if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
-    else if (spec == 1) st = launch_fused<FT, 768, 1, false, 1>(a, n, s, diag);
-    else if (spec == 0) st = launch_fused<FT, 768, 1, false, 0>(a, n, s, diag);
-    else st = launch_fused<FT, 768, 1, false, -1>(a, n, s, diag);
+    else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag);
+    else if (spec == 0) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 0>(a, n, s, diag);
+    else st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, -1>(a, n, s, diag);
     if (st) return st;
     return cmh::cuda_status(cudaGetLastError(), "fused_1m2m_icenuc launch");
 }
