@@ -380,6 +380,10 @@ CM_HD double tgamma_(double x) { return tgamma(x); }
 CM_HD float tgamma_(float x) { return tgammaf(x); }
 CM_HD double lgamma_(double x) { return lgamma(x); }
 CM_HD float lgamma_(float x) { return lgammaf(x); }
+// erf: CUDA libm.  A table-driven replacement (x P(x²) below 0.875, 1 - exp_(-x²) R_i(x) on three intervals, degree-14
+// polynomials in shared memory, < 2 units of 2^-53) was built and measured: 60 instructions instead of ~90, but SLOWER in the
+// ARG2000 kernel (config 3: 2.01 -> 2.08 ms; lanes of a warp sit in different pieces and the 15 dependent LDS+DFMA pairs do not
+// overlap the way the libm's register-resident polynomial does), so it was dropped.
 CM_HD double erf_(double x) { return erf(x); }
 CM_HD float erf_(float x) { return erff(x); }
 CM_HD double erfc_(double x) { return erfc(x); }

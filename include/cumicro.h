@@ -84,7 +84,8 @@ int64_t cumicro_launch_count(void);
 int cumicro_probe_fp64_fma(int64_t iters, int blocks_per_sm, double* scratch, double* flops_out, void* stream);
 
 /* Accuracy probe of the library's device math (cm_math.cuh) on the GPU itself:
- * fn = 0 exp, 1 log, 2 cbrt, 3 reciprocal, 4 pow(x, y), 5 exp with IEEE limits;
+ * fn = 0 exp, 1 log, 2 cbrt, 3 reciprocal, 4 pow(x, y), 5 exp with IEEE limits, 6 sqrt, 7 erf, 8 log1p (x > 0),
+ *      9 x^(-1/3), 10 x / y through the shared correctly rounded reciprocal;
  * out[i] = fn(x[i] [, y[i]]).  Device pointers; used by tests/test_gpu_math.py. */
 int cumicro_probe_math_f64(int fn, int64_t n, const double* x, const double* y, double* out, void* stream);
 

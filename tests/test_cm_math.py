@@ -104,3 +104,4 @@ def test_log1p_of_a_positive_argument(lib):
     rng = np.random.default_rng(6)
     y = np.concatenate([np.exp(rng.uniform(-36.7, 18.02, 4000)), 10 ** rng.uniform(-17, -14, 300), [1e-300, 1.0, 2.0 ** -53, 2.0 ** -52]])
     assert _max_ulp(_run(lib, "cmt_log1p_pos", y), y, mp.log1p) < 4.5
+

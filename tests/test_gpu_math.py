@@ -53,3 +53,25 @@ def test_device_math_accuracy(built, cuda):
     assert y[0] == 0 and np.isinf(y[1]) and np.isnan(y[2]) and y[3] == 1 and np.isinf(y[8])
     for got, x in zip(y[[4, 5, 6, 7]], (-745.0, 709.5, -720.0, -744.0)):
         assert abs(got - np.exp(x)) <= max(2e-15 * np.exp(x), 5e-324), (x, got, np.exp(x))
+
+
+def test_device_erf_log1p_rcbrt_division(built, cuda):
+    """The functions added for the ARG2000 / 1-moment kernels, on the device: erf_ (absolute error in units of 2^-53),
+    log1p_pos_, the reciprocal cube root, and the shared-reciprocal division (bit-identical to IEEE)."""
+    mp.mp.dps = 40
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.uniform(-6.2, 6.2, 3000), rng.uniform(-0.9, 0.9, 1000)])
+    y = _probe(built, cuda, 7, x)
+    worst = max(float(abs(mp.mpf(float(b)) - mp.erf(mp.mpf(float(a)))) / mp.mpf(2) ** -53) for a, b in zip(x, y))
+    assert worst < 2.0, worst
+    s = _probe(built, cuda, 7, np.array([0.0, 7.0, -7.0, np.inf, -np.inf, np.nan]))
+    assert s[0] == 0 and s[1] == 1 and s[2] == -1 and s[3] == 1 and s[4] == -1 and np.isnan(s[5])
+    v = np.exp(rng.uniform(-36.7, 18.02, 3000))
+    assert _max_ulp(_probe(built, cuda, 8, v), v, mp.log1p) < 4.5
+    w = 10 ** rng.uniform(-300, 300, 2000)
+    assert _max_ulp(_probe(built, cuda, 9, w), w, lambda t: 1 / mp.cbrt(t)) < 2.5
+    d = 10 ** rng.uniform(-12, 8, 100000)
+    a = rng.normal(size=d.size) * 10 ** rng.uniform(-30, 5, d.size)
+    a[::50] = 0.0
+    q = _probe(built, cuda, 10, a, d)
+    assert np.mean(q == a / d) > 0.9999 and np.all(q[a == 0] == 0)
