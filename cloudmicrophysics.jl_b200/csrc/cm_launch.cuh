@@ -91,7 +91,8 @@ template <class T> __device__ __forceinline__ void cp_async_elem(T* smem_dst, co
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB>
+// ALL_OUT: every output column is wanted (decided at launch): no per-column NULL test in the store sequence
+template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB, bool ALL_OUT = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 pointwise_kernel_pipelined(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a) {
     math_tables_init<BLOCK>();
@@ -120,7 +121,7 @@ pointwise_kernel_pipelined(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, 
         a.f(x, y);
 #pragma unroll
         for (int c = 0; c < NOUT; ++c)
-            if (a.out[c]) __stcs(a.out[c] + it, (FT)y[c]);
+            if (ALL_OUT || a.out[c]) __stcs(a.out[c] + it, (FT)y[c]);
         buf ^= 1;
     }
 }
@@ -158,11 +159,14 @@ int launch_pointwise(const F& f, int64_t n, const FT* const (&in)[NIN], FT* cons
         { static const char* np = getenv("CUMICRO_NO_PIPELINE"); if (np && np[0] == '1') ok = false; }
 #endif
         if (ok) {
-            auto kern = pointwise_kernel_pipelined<FT, NIN, NOUT, F, BLOCK, MINB>;
-            static bool carveout_set = false;   // 2 x NIN x BLOCK staged elements + the math tables per block, MINB blocks per SM
-            if (!carveout_set) {
+            bool all_out = true;
+            for (int c = 0; c < NOUT; ++c) all_out = all_out && out[c] != nullptr;
+            auto kern = all_out ? pointwise_kernel_pipelined<FT, NIN, NOUT, F, BLOCK, MINB, true>
+                                : pointwise_kernel_pipelined<FT, NIN, NOUT, F, BLOCK, MINB, false>;
+            static bool carveout_set[2] = {false, false};   // 2 x NIN x BLOCK staged elements + the math tables per block, MINB blocks per SM
+            if (!carveout_set[all_out]) {
                 cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                carveout_set = true;
+                carveout_set[all_out] = true;
             }
             const int blocks = (int)std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)max_blocks);
             kern<<<blocks, BLOCK, 0, stream>>>(a);
