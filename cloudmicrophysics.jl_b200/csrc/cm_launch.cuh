@@ -26,10 +26,19 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "cm_types.cuh"
 
 namespace cm {
+
+// a functor that calls log_abs_ declares `static constexpr bool kNeedsLog2 = true;` (its 4 KB table is staged only then)
+template <class F, class = void> struct needs_log2 : std::false_type {};
+template <class F> struct needs_log2<F, std::void_t<decltype(F::kNeedsLog2)>> : std::true_type {};
+template <int BLOCK, class F> CM_DEV void math_tables_init_for() {
+    math_tables_init<BLOCK>();
+    if constexpr (needs_log2<F>::value) math_tables_init_log2<BLOCK>();
+}
 
 template <class FT, int NIN, int NOUT, class F> struct PointwiseArgs {
     F f;
@@ -42,7 +51,7 @@ template <class FT, int NIN, int NOUT, class F, bool VECTOR, int BLOCK, int MINB
 __global__ void __launch_bounds__(BLOCK, MINB)
 pointwise_kernel(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int64_t first) {
     constexpr int VEC = VECTOR ? vec<FT>::N : 1;
-    math_tables_init<BLOCK>();  // exp/log tables -> shared memory (cm_math.cuh)
+    math_tables_init_for<BLOCK, F>();  // exp/log tables -> shared memory (cm_math.cuh)
     const int64_t stride = (int64_t)gridDim.x * BLOCK;
     const int64_t n_items = VECTOR ? (a.n / VEC) : (a.n - first);
     for (int64_t it = (int64_t)blockIdx.x * BLOCK + threadIdx.x; it < n_items; it += stride) {
@@ -95,7 +104,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB, bool ALL_OUT = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 pointwise_kernel_pipelined(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a) {
-    math_tables_init<BLOCK>();
+    math_tables_init_for<BLOCK, F>();
     __shared__ FT stage[2][NIN][BLOCK];
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * BLOCK;

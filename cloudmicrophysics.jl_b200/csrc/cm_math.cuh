@@ -91,12 +91,15 @@ static const unsigned long long cm_exp_tab_host[256] = CM_EXP_TABLE_INIT;
 static const unsigned long long cm_log_tab_host[256] = CM_LOG_TABLE_INIT;
 static __device__ const unsigned long long cm_exp_tab_dev[256] = CM_EXP_TABLE_INIT;
 static __device__ const unsigned long long cm_log_tab_dev[256] = CM_LOG_TABLE_INIT;
+static const unsigned long long cm_log2_tab_host[512] = CM_LOG2_TABLE_INIT;
+static __device__ const unsigned long long cm_log2_tab_dev[512] = CM_LOG2_TABLE_INIT;
 #ifdef __CUDACC__
 static __shared__ unsigned long long cm_sh_exp[256];
 static __shared__ ulonglong2 cm_sh_log[128];
+static __shared__ ulonglong2 cm_sh_log2[256];   // log_abs_ (allocated only in kernels that call math_tables_init_log2)
 // the few coefficients that need all 53 bits (everything else in exp_/logp_/cbrtp_ is an
 // immediate operand: constants whose low 32 bits are zero cost no instruction on sm_100)
-static __constant__ double cm_kc[6] = {3.3333333333333331e-01, 0.2, CM_LOG_LN2_LO, 0.0, CM_EXP_INV_L, CM_EXP_C4};
+static __constant__ double cm_kc[8] = {3.3333333333333331e-01, 0.2, CM_LOG_LN2_LO, -(CM_EXP_L2F), CM_EXP_INV_L, CM_EXP_C4, CM_LN2, 0.0};
 #endif
 #define CM_LOG_C3_HOST 3.3333333333333331e-01
 
@@ -108,6 +111,24 @@ template <int BLOCK> CM_DEV void math_tables_init() {
     for (int i = threadIdx.x; i < 128; i += BLOCK)
         cm_sh_log[i] = make_ulonglong2(cm_log_tab_dev[2 * i], cm_log_tab_dev[2 * i + 1]);
     __syncthreads();
+#endif
+}
+template <int BLOCK> CM_DEV void math_tables_init_log2() {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int i = threadIdx.x; i < 256; i += BLOCK)
+        cm_sh_log2[i] = make_ulonglong2(cm_log2_tab_dev[2 * i], cm_log2_tab_dev[2 * i + 1]);
+    __syncthreads();
+#endif
+}
+CM_HD void log2_tab(int i, double& invc, double& logc) {
+#ifdef __CUDA_ARCH__
+    const ulonglong2 t = cm_sh_log2[i];
+    invc = bits2d(t.x);
+    logc = bits2d(t.y);
+#else
+    invc = bits2d(cm_log2_tab_host[2 * i]);
+    logc = bits2d(cm_log2_tab_host[2 * i + 1]);
 #endif
 }
 CM_HD double exp_tab(int j) {
@@ -225,29 +246,28 @@ CM_HD float rcp_(float x) { return 1.0f / x; }
 
 // ---- exp: |x| <= 708 (callers' arguments are bounded; see exp_full_ otherwise) ---------------
 // x = (256 e + j) ln2/256 + r, |r| <= ln2/512;  exp(x) = 2^e * T[j] * (1 + expm1(r)).
-// All constants are immediates (21-bit pieces): 10 FP64 instructions, 1 LDS, ~6 integer.
+// 9 FP64 instructions, 1 LDS, ~5 integer: ln2/256 = L1 (21 bits, immediate, kf L1 exact) + L2F (full double, constant bank).
 CM_HD double exp_(double x) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
     // an FP64 instruction takes ONE non-register operand: the second constant of a two-constant fma comes from the
     // constant bank (one uniform load) instead of two 32-bit moves
 #ifdef __CUDA_ARCH__
-    const double inv_l = cm_kc[4], c4 = cm_kc[5];
+    const double inv_l = cm_kc[4], c4 = cm_kc[5], nl2f = cm_kc[3];
 #else
-    const double inv_l = CM_EXP_INV_L, c4 = CM_EXP_C4;
+    const double inv_l = CM_EXP_INV_L, c4 = CM_EXP_C4, nl2f = -(CM_EXP_L2F);
 #endif
     const double t = fma(x, inv_l, magic);
     const int ki = lo32(t);
     const double kf = t - magic;
     double r = fma(kf, -CM_EXP_L1, x);  // exact
-    r = fma(kf, -CM_EXP_L2, r);
-    r = fma(kf, -CM_EXP_L3, r);
+    r = fma(kf, nl2f, r);
     double p = fma(r, c4, CM_EXP_C3);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r;  // expm1(r)
     const double T = exp_tab(ki & 255);
     const double y = fma(T, p, T);
-    return mk64(hi32(y) + ((ki >> 8) << 20), lo32(y));
+    return mk64(hi32(y) + (ki & ~255) * 4096, lo32(y));   // 2^(ki >> 8): one mask + one multiply-add on the high word
 }
 // exp with the IEEE limits: gradual underflow into the subnormals, 0 below them, +Inf
 // above the range, NaN propagated.
@@ -305,6 +325,29 @@ CM_HD double logp_(double x) {
     return (w + r) + lo;
 }
 CM_HD float logp_(float x) { return logf(x); }
+// log with ABSOLUTE accuracy ~1.5e-16 max(1, |log x|) (not relatively accurate near x = 1): positive, normal, finite x.
+// x = 2^k z, z in [1, 2); z = c (1 + r) with 1/c, -log(1/c) tabulated (256 cells, |r| <= 2^-9); degree-5 log1p: 8 FP64.
+// For arguments whose logarithm is an additive term of an exponent or of a log-space recurrence (log L, log N, log tau).
+CM_HD double log_abs_(double x) {
+#ifdef __CUDA_ARCH__
+    const double c3 = cm_kc[0], ln2 = cm_kc[6];
+#else
+    const double c3 = CM_LOG_C3_HOST, ln2 = CM_LN2;
+#endif
+    const int hx = hi32(x);
+    const int i = (hx >> 12) & 255;
+    const int k = (hx >> 20) - 1023;
+    const double z = mk64((hx & 0x000fffff) | 0x3ff00000, lo32(x));
+    double invc, logc;
+    log2_tab(i, invc, logc);
+    const double r = fma(z, invc, -1.0);
+    const double w = fma((double)k, ln2, logc);
+    double q = fma(r, CM_LOGA_C5, -0.25);
+    q = fma(q, r, c3);
+    q = fma(q, r, -0.5);
+    return w + fma(r * r, q, r);
+}
+CM_HD float log_abs_(float x) { return logf(x); }
 CM_HD double log_full_(double x) { return log(x); }
 CM_HD float log_full_(float x) { return logf(x); }
 

@@ -209,8 +209,16 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
         const FT t_star = sk.cbrt_six_x_star_r * inv_cx;           // cbrt(6 x*/xr)
         const FT lt = fma_(lx, FT(-1.0 / 3.0), sk.log_six_x_star_r_third);  // log(t_star)
         // Γ_incl(a, t) = exp(-t) / (c1 t^e1 + c2 t^e2) = exp(-t - e1 ln t) / (c1 + c2 t^(e2-e1))   CM2:746-753
-        const FT gi0 = exp_(fma_(-sk.gi_e1[0], lt, -t_star)) * rcp_(fma_(sk.gi_c2[0], exp_(sk.gi_de[0] * lt), sk.gi_c1[0]));
-        const FT gi1 = exp_(fma_(-sk.gi_e1[1], lt, -t_star)) * rcp_(fma_(sk.gi_c2[1], exp_(sk.gi_de[1] * lt), sk.gi_c1[1]));
+        // The not-limited PSD leaves xr_mean unclamped: t_star = cbrt(6 x*/xr_mean) exceeds exp_'s |x| <= 708 domain for tiny q_rai with
+        // leftover n_rai (the reference's exp underflows to 0 there; exp_ would wrap its exponent).  The limited PSD bounds t_star by
+        // cbrt(6).  `lim` is uniform over the grid: one branch, no divergence.
+        const bool lim = STD ? ((SPEC & 1) != 0) : (sb.pdf_r.limited != 0);
+        const FT ga0 = fma_(-sk.gi_e1[0], lt, -t_star), ga1 = fma_(-sk.gi_e1[1], lt, -t_star);
+        const FT ge0 = lim ? exp_(ga0) : exp_full_(ga0), ge1 = lim ? exp_(ga1) : exp_full_(ga1);
+        const FT gd0 = sk.gi_de[0] * lt, gd1 = sk.gi_de[1] * lt;
+        const FT gx0 = lim ? exp_(gd0) : exp_full_(gd0), gx1 = lim ? exp_(gd1) : exp_full_(gd1);
+        const FT gi0 = ge0 * rcp_(fma_(sk.gi_c2[0], gx0, sk.gi_c1[0]));
+        const FT gi1 = ge1 * rcp_(fma_(sk.gi_c2[1], gx1, sk.gi_c1[1]));
         const FT a_vent_0 = sb.evap.a_vent_0_coeff * gi0;
         const FT b_vent_0 = sb.evap.b_vent_0_coeff * gi1;
         FT sqrt_rho0e = sqrt_rho0_rho;
@@ -280,8 +288,10 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
         FT sc = -sb.self.krr * N_rai * L_rai * sqrt_rho0_rho * (STD ? pow_int_<-5>(sc_arg) : pow_param(sc_arg, sb.self.d, sk.pw_self_d));
         sc = no_rain ? FT(0) : sc;
         const FT dD = Dr - sb.brek.Deq;
+        const bool lim_b = STD ? ((SPEC & 1) != 0) : (sb.pdf_r.limited != 0);   // Dr is bounded only under the limited PSD
         const FT phi_p1 = (Dr < sb.brek.Dr_th) ? FT(0)
-                                               : ((Dr <= sb.brek.Deq) ? fma_(sb.brek.kbr, dD, FT(1)) : exp_(sb.brek.kappa_br * dD));
+                                               : ((Dr <= sb.brek.Deq) ? fma_(sb.brek.kbr, dD, FT(1))
+                                                                      : (lim_b ? exp_(sb.brek.kappa_br * dD) : exp_full_(sb.brek.kappa_br * dD)));
         const FT br = no_rain ? FT(0) : -phi_p1 * sc;   // Eq. (13): -(Φ_br + 1) dN_sc
         o.leaf[CUMICRO_SB_RAI_SELFCOL] = sc;
         o.leaf[CUMICRO_SB_RAI_BREAKUP] = br;

@@ -1,0 +1,176 @@
+// cm_tile2m.cuh — the launch shape of the headline kernel (fused 2-moment warm-rain tendencies, cm_sb2006_fast.cuh).
+//
+// The body is issue-slot bound together with the FP64 pipe: a point costs ~310 FP64-pipe instructions, each
+// holding the pipe for two cycles, so every other issue slot is all the rest of the kernel may use.  This shape removes the
+// per-thread instructions that are not arithmetic:
+//   * block-uniform tile loop (tile = BLOCK consecutive points, tiles dealt round-robin to the persistent blocks): the input
+//     tiles are fetched by ONE thread with 1-D bulk asynchronous copies (cp.async.bulk global -> shared, completion on an
+//     mbarrier, two tiles in flight) instead of 7 cp.async + 14 address instructions per thread and point;
+//   * the ~70 host-derived constants of the body are NOT hoisted out of the loop: 70 loop-invariant doubles need 140 uniform
+//     registers, ptxas has ~80 and spills the rest through vector registers and local memory (measured: 16 STL/LDL + 34 R2UR
+//     per point).  They are read at their point of use through an address that depends on the tile counter (an opaque zero),
+//     i.e. one uniform constant-bank load per use and no register held;
+//   * stores are streaming 64/32-bit st.global.cs, one per output column.
+// Columns must be 16-byte aligned for the bulk copies (any cudaMalloc'd or torch buffer is); the launcher falls back to
+// cm_launch.cuh's cp.async shape otherwise.  A partial last tile is loaded with guarded scalar loads.
+#pragma once
+#include "cm_launch.cuh"
+#include "cm_sb2006_fast.cuh"
+
+namespace cm {
+
+template <class FT, int NIN> struct Tile2MArgs {
+    W2K k;
+    const FT* in[NIN];
+    FT* out[4];
+    int64_t n;
+};
+
+namespace tile {
+CM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+CM_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+CM_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CM_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+CM_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one lane of a converged warp (the canonical leader election: ptxas keeps the guarded code on the uniform datapath)
+CM_DEV bool elect_one() {
+    unsigned p;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
+}
+}  // namespace tile
+
+// PPT points per thread: the PPT bodies of one thread are independent and share every constant load.
+template <class FT, int NIN, int LIM, int BLOCK, int MINB, bool ALL_OUT, int PPT>
+__global__ void __launch_bounds__(BLOCK, MINB) warm2m_tile_kernel(const __grid_constant__ Tile2MArgs<FT, NIN> a) {
+    constexpr int TILE = BLOCK * PPT;
+    constexpr int NWARP = BLOCK / 32;
+    __shared__ __align__(128) FT stage[2][NIN][TILE];
+    __shared__ __align__(8) unsigned long long full[2];
+    math_tables_init<BLOCK>();
+    math_tables_init_log2<BLOCK>();
+    const int tid = threadIdx.x;
+    const unsigned n_tiles = (unsigned)((a.n + TILE - 1) / TILE);
+    const unsigned n_full = (unsigned)(a.n / TILE);        // tiles [0, n_full) are complete
+    constexpr unsigned kTileBytes = TILE * sizeof(FT);
+    // the leader lane of warp w fetches columns w, w + NWARP, ...: the copy-issue instructions are spread over the SM sub-partitions
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction
+    const bool issuer = warp < NIN;
+    constexpr int kIssuers = NWARP < NIN ? NWARP : NIN;
+    if (tid == 0) {
+        tile::mbar_init(&full[0], kIssuers);
+        tile::mbar_init(&full[1], kIssuers);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](unsigned t, int buf) {   // converged issuer warps; one elected lane does the work
+        if (t < n_full && tile::elect_one()) {
+            const int ncol = (NIN - warp + NWARP - 1) / NWARP;
+            tile::mbar_expect_tx(&full[buf], ncol * kTileBytes);
+#pragma unroll 1
+            for (int c = warp; c < NIN; c += NWARP) tile::bulk_g2s(&stage[buf][c][0], a.in[c] + (size_t)t * TILE, kTileBytes, &full[buf]);
+        }
+    };
+    unsigned t = blockIdx.x;
+    if (issuer) {   // two tiles in flight
+        issue(t, 0);
+        if (t + gridDim.x < n_tiles) issue(t + gridDim.x, 1);
+    }
+    unsigned j = 0;
+    for (; t < n_tiles; t += gridDim.x, ++j) {
+        const int buf = j & 1;
+        const int64_t it0 = (int64_t)t * TILE + tid;
+        double x[PPT][NIN];
+        if (t < n_full) {
+            tile::mbar_wait(&full[buf], (j >> 1) & 1);
+#pragma unroll
+            for (int p = 0; p < PPT; ++p)
+#pragma unroll
+                for (int c = 0; c < NIN; ++c) x[p][c] = (double)stage[buf][c][p * BLOCK + tid];
+        } else {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p)
+#pragma unroll
+                for (int c = 0; c < NIN; ++c) x[p][c] = (it0 + p * BLOCK < a.n) ? (double)__ldg(a.in[c] + it0 + p * BLOCK) : 1.0;
+        }
+        __syncthreads();   // every thread has read stage[buf]: it may be refilled
+        if (issuer) {
+            const unsigned t2 = t + 2 * gridDim.x;
+            if (t2 < n_tiles) issue(t2, buf);
+        }
+        // The ~70 constants are read from the constant bank where they are used (LDCU.128 / LDC.64 per use): with the block barrier and
+        // the asynchronous copies inside the loop ptxas does not hoist them (hoisted, they need 140 uniform registers; ptxas has ~80 and
+        // spilled the rest through vector registers and local memory in the cp.async shape: 16 STL/LDL + 34 R2UR per point).
+        const W2K& k = a.k;
+        double y[PPT][4];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+            warm2m_fast<LIM>(k, x[p][0], x[p][1], x[p][2], x[p][3], x[p][4], x[p][5], x[p][6], (NIN == 8) ? clamp0_(x[p][NIN - 1]) : 0.0,
+                             NIN == 8, y[p]);
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+            if (it0 + p * BLOCK < a.n) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (ALL_OUT || a.out[c]) __stcs(a.out[c] + it0 + p * BLOCK, (FT)y[p][c]);
+            }
+    }
+}
+
+// Enqueue the tile kernel; returns -1 if the columns do not meet its alignment requirement (caller falls back).
+template <class FT, int NIN, int LIM, int BLOCK = 128, int MINB = 7, int PPT = 1>
+int launch_warm2m_tile(const W2K& k, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[4], cudaStream_t stream, const char* what,
+                       int waves = 16) {
+    if (n == 0) return CUMICRO_OK;
+    for (int c = 0; c < NIN; ++c)
+        if (!cmh::aligned16(in[c])) return -1;
+    Tile2MArgs<FT, NIN> a;
+    a.k = k;
+    a.n = n;
+    bool all_out = true;
+    for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
+    for (int c = 0; c < 4; ++c) { a.out[c] = out[c]; all_out = all_out && out[c] != nullptr; }
+    auto kern = all_out ? warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, true, PPT> : warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, false, PPT>;
+    static bool carveout_set[2] = {false, false};
+    if (!carveout_set[all_out]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set[all_out] = true;
+    }
+#ifdef CUMICRO_TUNING
+    { const char* wv0 = getenv("CUMICRO_WAVES"); if (wv0) waves = atoi(wv0); }
+#endif
+    constexpr int TILE = BLOCK * PPT;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int blocks = (int)std::min<int64_t>(n_tiles, (int64_t)cmh::num_sms() * MINB * waves);
+    kern<<<blocks, BLOCK, 0, stream>>>(a);
+    cmh::count_launch();
+    return cmh::cuda_status(cudaGetLastError(), what);
+}
+
+}  // namespace cm

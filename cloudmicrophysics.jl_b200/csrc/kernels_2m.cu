@@ -12,6 +12,8 @@
 #include "cm_hostpipe.cuh"
 #include "cm_launch.cuh"
 #include "cm_sb2006.cuh"
+#include "cm_sb2006_fast.cuh"
+#include "cm_tile2m.cuh"
 
 namespace {
 
@@ -23,6 +25,7 @@ using namespace cm;
 // Functors compute in Float64 (D = double); the entry points below are templated on the
 // column type FT and widen Float32 parameter blocks exactly.
 using D = double;
+template <class FT> constexpr bool is_f32() { return sizeof(FT) == 4; }
 // SPEC: compile-time specialisation for the default structure of the SB2006 block (cm_sb2006.cuh, sb2006_spec()); -1 = generic.
 template <int NIN = 7, int SPEC = -1> struct Warm2MFused {
     P<D>::params_2m_warm p;
@@ -38,6 +41,27 @@ template <int NIN = 7, int SPEC = -1> struct Warm2MFused {
     }
 };
 
+// The headline body (cm_sb2006_fast.cuh): default SB2006 block structure, LIM = limited rain PSD.
+template <int NIN, int LIM> struct Warm2MFast {
+    static constexpr bool kNeedsLog2 = true;
+    W2K k;
+    __device__ __forceinline__ void operator()(const D (&x)[NIN], D (&y)[4]) const {
+        warm2m_fast<LIM>(k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], (NIN == 8) ? clamp0_(x[NIN - 1]) : D(0), NIN == 8, y);
+    }
+};
+template <class FT, class F> F make_2m_fast(const typename P<FT>::params_2m_warm* p) {
+    F f{};
+    P<D>::params_2m_warm w;
+    widen(*p, w);
+    f.k = make_w2k(w, is_f32<FT>());
+    return f;
+}
+template <class FT> bool fast_ok(const typename P<FT>::params_2m_warm* p) {
+    P<D>::params_2m_warm w;
+    widen(*p, w);
+    return w2k_supported(w);
+}
+
 // ---- the 15 SB2006 process rates one by one (leaf API) ----------------------------------
 struct Warm2MLeaves {
     P<D>::params_2m_warm p;
@@ -49,8 +73,6 @@ struct Warm2MLeaves {
         for (int k = 0; k < CUMICRO_SB2006_NLEAF; ++k) y[k] = o.leaf[k];
     }
 };
-
-template <class FT> constexpr bool is_f32() { return sizeof(FT) == 4; }
 
 // (p wide, tk, sk) of one call: Float32 blocks are widened exactly, thresholds follow FT.
 template <class FT, class F> F make_2m(const typename P<FT>::params_2m_warm* p) {
@@ -84,44 +106,65 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
                 st = cmh::cuda_status(cudaMemsetAsync(zero4[k], 0, sizeof(FT) * (size_t)n, s), "cudaMemsetAsync");
                 if (st) return st;
             }
+    const char* w = "bmt2m_warm kernel launch";
+    const bool fast = fast_ok<FT>(p);
+    const bool lim = p->sb.pdf_r.limited != 0;
     if (q_ice != nullptr) {
         const FT* in8[8] = {rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice};
-        return launch_pointwise<FT, 8, 4, Warm2MFused<8>, 128, 8, false>(make_2m<FT, Warm2MFused<8>>(p), n, in8, out, s,
-                                                                        "bmt2m_warm kernel launch");
+        if (fast) {
+            const W2K k = make_2m_fast<FT, Warm2MFast<8, 1>>(p).k;
+            const int rc = lim ? launch_warm2m_tile<FT, 8, 1>(k, n, in8, out, s, w) : launch_warm2m_tile<FT, 8, 0>(k, n, in8, out, s, w);
+            if (rc != -1) return rc;
+        }
+        if (fast && lim) return launch_pointwise<FT, 8, 4, Warm2MFast<8, 1>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<8, 1>>(p), n, in8, out, s, w);
+        if (fast) return launch_pointwise<FT, 8, 4, Warm2MFast<8, 0>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<8, 0>>(p), n, in8, out, s, w);
+        return launch_pointwise<FT, 8, 4, Warm2MFused<8>, 128, 8, false>(make_2m<FT, Warm2MFused<8>>(p), n, in8, out, s, w);
     }
-    Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
 #ifdef CUMICRO_TUNING
-    {   // launch-shape exploration (tools/tune_2m.py); not compiled into the product build
-        static const char* ev = getenv("CUMICRO_2M_VARIANT");
+    if (fast && lim) {   // launch-shape exploration (tools/tune_2m.py); not compiled into the product build
+        const char* ev = getenv("CUMICRO_2M_VARIANT");
         const int v = ev ? atoi(ev) : 0;
-        const char* w = "bmt2m_warm kernel launch";
+        using F1 = Warm2MFast<7, 1>;
+        const F1 f1 = make_2m_fast<FT, F1>(p);
         switch (v) {
-            case 1: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 256, 2>(f, n, in, out, s, w);
-            case 2: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 3>(f, n, in, out, s, w);
-            case 3: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 4>(f, n, in, out, s, w);
-            case 4: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 5>(f, n, in, out, s, w);
-            case 5: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 6>(f, n, in, out, s, w);
-            case 6: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8>(f, n, in, out, s, w);
-            case 7: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 8>(f, n, in, out, s, w);
-            case 8: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 12>(f, n, in, out, s, w);
-            case 10: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, n, in, out, s, w);
-            case 11: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 6, false, true>(f, n, in, out, s, w);
-            case 12: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 64, 16, false, true>(f, n, in, out, s, w);
-            case 13: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 256, 4, false, true>(f, n, in, out, s, w);
-            case 14: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 5, false, true>(f, n, in, out, s, w);
-            case 15: return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 96, 10, false, true>(f, n, in, out, s, w);
+            case 1: return launch_pointwise<FT, 7, 4, F1, 128, 8, false, true>(f1, n, in, out, s, w);
+            case 2: return launch_pointwise<FT, 7, 4, F1, 128, 6, false, true>(f1, n, in, out, s, w);
+            case 3: return launch_pointwise<FT, 7, 4, F1, 128, 5, false, true>(f1, n, in, out, s, w);
+            case 4: return launch_pointwise<FT, 7, 4, F1, 256, 3, false, true>(f1, n, in, out, s, w);
+            case 5: return launch_pointwise<FT, 7, 4, F1, 256, 4, false, true>(f1, n, in, out, s, w);
+            case 6: return launch_pointwise<FT, 7, 4, F1, 64, 14, false, true>(f1, n, in, out, s, w);
+            case 7: return launch_pointwise<FT, 7, 4, F1, 128, 8, false, false>(f1, n, in, out, s, w);   // plain loads, 1 point / thread
+            case 8: return launch_pointwise<FT, 7, 4, F1, 128, 7, false, false>(f1, n, in, out, s, w);
+            case 9: return launch_pointwise<FT, 7, 4, F1, 128, 4, true, false>(f1, n, in, out, s, w);    // 128-bit, 2 points / thread
+            case 10: return launch_pointwise<FT, 7, 4, F1, 128, 3, true, false>(f1, n, in, out, s, w);
+            case 11: return launch_pointwise<FT, 7, 4, F1, 256, 2, true, false>(f1, n, in, out, s, w);
+            case 12: return launch_pointwise<FT, 7, 4, F1, 128, 5, true, false>(f1, n, in, out, s, w);
+            case 13: return launch_pointwise<FT, 7, 4, Warm2MFused<7, 1>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7, 1>>(p), n, in, out, s, w);  // round-1 kernel
+            case 14: return launch_pointwise<FT, 7, 4, F1, 128, 7, false, true>(f1, n, in, out, s, w);   // fast body, cp.async shape
+            case 20: return launch_warm2m_tile<FT, 7, 1, 128, 7, 1>(f1.k, n, in, out, s, w);
+            case 21: return launch_warm2m_tile<FT, 7, 1, 128, 8, 1>(f1.k, n, in, out, s, w);
+            case 22: return launch_warm2m_tile<FT, 7, 1, 128, 6, 1>(f1.k, n, in, out, s, w);
+            case 23: return launch_warm2m_tile<FT, 7, 1, 256, 3, 1>(f1.k, n, in, out, s, w);
+            case 24: return launch_warm2m_tile<FT, 7, 1, 128, 5, 1>(f1.k, n, in, out, s, w);
+            case 30: return launch_warm2m_tile<FT, 7, 1, 128, 4, 2>(f1.k, n, in, out, s, w);
+            case 31: return launch_warm2m_tile<FT, 7, 1, 128, 3, 2>(f1.k, n, in, out, s, w);
+            case 32: return launch_warm2m_tile<FT, 7, 1, 64, 8, 2>(f1.k, n, in, out, s, w);
+            case 33: return launch_warm2m_tile<FT, 7, 1, 64, 7, 2>(f1.k, n, in, out, s, w);
+            case 34: return launch_warm2m_tile<FT, 7, 1, 128, 5, 2>(f1.k, n, in, out, s, w);
             default: break;
         }
     }
 #endif
-    // 128 x 7 blocks/SM (72 registers): sweep of the pipelined kernel 128x8 0.630, 128x7 0.623, 128x6 0.633, 128x5 0.659,
-    // 64x16 0.632, 256x4 0.634, 96x10 0.638 ms.  The default parameter structure runs the specialised instantiation.
-    switch (sb2006_spec<D>(f.p.sb)) {
-        case 1: return launch_pointwise<FT, 7, 4, Warm2MFused<7, 1>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7, 1>>(p), n, in, out, s, "bmt2m_warm kernel launch");
-        case 0: return launch_pointwise<FT, 7, 4, Warm2MFused<7, 0>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7, 0>>(p), n, in, out, s, "bmt2m_warm kernel launch");
-        default: break;
+    // 128 x 7 blocks/SM: sweep in tools/tune_2m.py.  The default parameter STRUCTURE (exponents 3 / 4 / -5, any values) runs the
+    // fast body (tile kernel, cm_tile2m.cuh; cp.async shape for columns that are not 16-byte aligned); anything else the generic one.
+    if (fast) {
+        const W2K k = make_2m_fast<FT, Warm2MFast<7, 1>>(p).k;
+        const int rc = lim ? launch_warm2m_tile<FT, 7, 1>(k, n, in, out, s, w) : launch_warm2m_tile<FT, 7, 0>(k, n, in, out, s, w);
+        if (rc != -1) return rc;
     }
-    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, n, in, out, s, "bmt2m_warm kernel launch");
+    if (fast && lim) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 1>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<7, 1>>(p), n, in, out, s, w);
+    if (fast) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 0>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<7, 0>>(p), n, in, out, s, w);
+    return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7>>(p), n, in, out, s, w);
 }
 
 template <class FT>
@@ -149,17 +192,21 @@ int bmt2m_warm_host_impl(const typename P<FT>::params_2m_warm* p, int64_t n, con
     if (st) return st;
     if ((st = check_2m_options<FT>(p))) return st;
     if ((st = require_outputs<FT, 4>(n, out, 4))) return st;
-    Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
-    const int spec = sb2006_spec<D>(f.p.sb);
-    const Warm2MFused<7, 1> f1 = make_2m<FT, Warm2MFused<7, 1>>(p);
-    const Warm2MFused<7, 0> f0 = make_2m<FT, Warm2MFused<7, 0>>(p);
+    const bool fast = fast_ok<FT>(p);
+    const bool lim = p->sb.pdf_r.limited != 0;
+    const Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
+    const Warm2MFast<7, 1> f1 = make_2m_fast<FT, Warm2MFast<7, 1>>(p);
+    const Warm2MFast<7, 0> f0 = make_2m_fast<FT, Warm2MFast<7, 0>>(p);
     return host_pipeline<FT, 7, 4>(n, in, out, chunk,
                                    [&](int64_t m, const FT* const(&din)[7], FT* const(&dout)[4], cudaStream_t s) {
                                        const char* w = "bmt2m_warm (host pipeline) kernel launch";
-                                       if (spec == 1) return launch_pointwise<FT, 7, 4, Warm2MFused<7, 1>, 128, 8, false>(f1, m, din, dout, s, w);
-                                       if (spec == 0) return launch_pointwise<FT, 7, 4, Warm2MFused<7, 0>, 128, 8, false>(f0, m, din, dout, s, w);
-                                       return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 8, false>(
-                                           f, m, din, dout, s, w);
+                                       if (fast) {
+                                           const int rc = lim ? launch_warm2m_tile<FT, 7, 1>(f1.k, m, din, dout, s, w) : launch_warm2m_tile<FT, 7, 0>(f1.k, m, din, dout, s, w);
+                                           if (rc != -1) return rc;
+                                       }
+                                       if (fast && lim) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 1>, 128, 7, false, true>(f1, m, din, dout, s, w);
+                                       if (fast) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 0>, 128, 7, false, true>(f0, m, din, dout, s, w);
+                                       return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, m, din, dout, s, w);
                                    });
 }
 

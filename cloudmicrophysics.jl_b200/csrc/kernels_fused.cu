@@ -16,6 +16,7 @@
 #include "cm_icenuc.cuh"
 #include "cm_launch.cuh"
 #include "cm_sb2006.cuh"
+#include "cm_sb2006_fast.cuh"
 
 namespace {
 
@@ -45,6 +46,7 @@ struct FusedParams {
     ThermoK<D> tk;
     OneMK<D> k1;
     SB2006K<D> k2;
+    W2K w2k;            // constants of the fast 2-moment body (SPEC >= 0)
     ArgK<D> k3;
     int with_activation;
 };
@@ -64,6 +66,7 @@ template <class FT> struct FusedArgs {
 template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     math_tables_init<BLOCK>();
+    if constexpr (SPEC >= 0) math_tables_init_log2<BLOCK>();
     extern __shared__ __align__(16) unsigned char fused_dyn_smem[];
     FT (*stage)[NIN][BLOCK] = reinterpret_cast<FT (*)[NIN][BLOCK]>(fused_dyn_smem);   // [2][NIN][BLOCK]
     const FusedParams& f = a.f;
@@ -103,13 +106,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
         if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         // 2-moment warm rain (cloud ice seen by the thermodynamics = q_icl + q_sno)   BMT:820-854
         if (active) {
-            const Warm2M<D> o = warm_rain_tendencies_2m<D, SPEC>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10),
-                                                           clamp0_(in(6)) + clamp0_(in(8)));
-            put(4, o.dq_lcl_dt);
-            put(5, o.dn_lcl_dt);
-            put(6, o.dq_rai_dt);
-            put(7, o.dn_rai_dt);
-            diag[1] += in(0) * o.dq_rai_dt;     // 2M rain production           Σ ρ dq_rai
+            const double q_ice = clamp0_(in(6)) + clamp0_(in(8));
+            if constexpr (SPEC >= 0) {   // default SB2006 block structure: the headline body (cm_sb2006_fast.cuh), bit-identical to cumicro_bmt2m_warm_*
+                double y[4];
+                warm2m_fast<SPEC>(f.w2k, in(0), in(1), in(4), in(5), in(9), in(7), in(10), q_ice, true, y);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) put(4 + k, y[k]);
+                diag[1] += in(0) * y[2];        // 2M rain production           Σ ρ dq_rai
+            } else {
+                const Warm2M<D> o = warm_rain_tendencies_2m<D, -1>(f.p2, f.tk, f.k2, in(0), in(1), in(4), in(5), in(9), in(7), in(10), q_ice);
+                put(4, o.dq_lcl_dt);
+                put(5, o.dn_lcl_dt);
+                put(6, o.dq_rai_dt);
+                put(7, o.dn_rai_dt);
+                diag[1] += in(0) * o.dq_rai_dt;
+            }
         }
         if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         // ice-nucleation rates (+ ARG2000 activated number)              IN:92-134, 557-584; AA:138-273
@@ -121,9 +132,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
             if (f.with_activation) {
                 const ArgOut o = arg2000<false>(f.p3, f.tk, f.k3, T, pr, w, q_tot, q_lcl + q_rai, q_icl + q_sno, rho * n_lcl, 0.0);
                 da_w = o.da_w;
+                // Activation needs an updraft: AA.max_supersaturation takes sqrt(alpha w / G) (AA:170-176), a DomainError in the
+                // reference for w < 0 and S_max = 0 for w = 0.  A model slab has downdraft cells: they activate nothing, and they
+                // must not poison the domain sum (NaN from one cell would make the all-reduced diagnostic NaN everywhere).
+                const bool updraft = w > 0.0;
 #pragma unroll
                 for (int m = 0; m < kMaxModes; ++m)
-                    if (m < f.p3.n_modes) n_act += o.N_act[m];
+                    if (m < f.p3.n_modes) {
+                        const double na = o.N_act[m];
+                        n_act += (updraft && na == na && na < 1.7e308) ? na : 0.0;
+                    }
             } else {
                 const TempState<D> ts = temp_state(f.tk, T);
                 const D pl = p_sat_liq(f.tk, ts);
@@ -186,8 +204,10 @@ template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumi
 
 template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
+    // the block partials of THIS call: stream-ordered allocation (a cached per-thread buffer would be shared by calls in flight on
+    // different streams, and growing it would free memory a running kernel still writes)
     void* ws = nullptr;
-    int st = cmh::workspace(cmh::kPipeSlots /* slot reserved for the diagnostics partials */, sizeof(double) * NDIAG * (size_t)blocks + 64, &ws);
+    int st = cmh::cuda_status(cudaMallocAsync(&ws, sizeof(double) * NDIAG * (size_t)blocks + 64, s), "fused: cudaMallocAsync (diagnostic partials)");
     if (st) return st;
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
@@ -204,7 +224,7 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC> int launch_fused(F
         fused_diag_finish<<<1, 256, 0, s>>>(a.partials, blocks, diag);
         cmh::count_launch();
     }
-    return CUMICRO_OK;
+    return cmh::cuda_status(cudaFreeAsync(ws, s), "fused: cudaFreeAsync");
 }
 
 template <class FT>
@@ -224,6 +244,7 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     a.f.tk = make_thermo_k<D>(a.f.p1.tps, is_f32<FT>());
     a.f.k1 = make_1m_k<D>(a.f.p1, is_f32<FT>());
     a.f.k2 = make_sb2006_k<D>(a.f.p2.sb, a.f.p2.aps, is_f32<FT>());
+    a.f.w2k = make_w2k(a.f.p2, is_f32<FT>());
     a.f.k3 = make_arg_k<D>(a.f.p3, is_f32<FT>());
     a.f.with_activation = a.f.p3.n_modes > 0;
     for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
@@ -234,7 +255,7 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     // for the default SB2006 block structure when the block has it (cm_sb2006.cuh, sb2006_spec()).
     bool small_blocks = false;
     if (const char* e = std::getenv("CUMICRO_FUSED_SHAPE")) small_blocks = std::string(e).rfind("128", 0) == 0;
-    const int spec = sb2006_spec<D>(a.f.p2.sb);
+    const int spec = w2k_supported(a.f.p2) ? (a.f.p2.sb.pdf_r.limited ? 1 : 0) : -1;
     int st;
     if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
     else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag);

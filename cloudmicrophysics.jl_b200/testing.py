@@ -158,58 +158,15 @@ def arg_test_distribution(kind="kappa"):
     return AM.AerosolDistribution(tuple(modes))
 
 
-def perturb(states, rel=2.0 ** -40, seed=7, skip=()):
-    """Inputs with every element multiplied by (1 ± rel) (random signs): used to
-    measure the reference's own conditioning at each point."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    out = {}
-    for k, v in states.items():
-        if k in skip:
-            out[k] = v
-            continue
-        s = rng.integers(0, 2, v.shape[0]) * 2 - 1
-        out[k] = (v.astype(np.float64) * (1.0 + rel * s)).astype(v.dtype)
-    return out
-
-
-def sensitivity(fn, states, keys, rel=2.0 ** -40):
-    """Conditioning of the REFERENCE at each point: sum over the inputs of
-    |fn(x with input k scaled by (1+rel)) - fn(x)|.  ``fn(states) -> {name: array}``
-    (arrays or lists of arrays).  One-at-a-time perturbations cannot cancel each other."""
-    def flat(d):
-        out = {}
-        for k, v in d.items():
-            if isinstance(v, (list, tuple)):
-                for i, a in enumerate(v):
-                    out[(k, i)] = np.asarray(a, dtype=np.float64)
-            else:
-                out[k] = np.asarray(v, dtype=np.float64)
-        return out
-    base = flat(fn(states))
-    sens = {k: np.zeros_like(v) for k, v in base.items()}
-    for key in keys:
-        st = dict(states)
-        st[key] = (states[key].astype(np.float64) * (1.0 + rel)).astype(states[key].dtype)
-        pr = flat(fn(st))
-        for k in sens:
-            with np.errstate(invalid="ignore"):
-                d = np.abs(pr[k] - base[k])
-            sens[k] += np.where(np.isfinite(d), d, 0.0)
-    return sens
-
-
-def compare_report(got, ref, bound=None, sens=None, rtol=F64_RTOL, bound_factor=8.0, backward_ulps=16,
-                   eps=np.finfo(np.float64).eps, sens_rel=2.0 ** -40):
+def compare_report(got, ref, bound=None, rtol=F64_RTOL, bound_factor=2.0):
     """Parity metrics of one Float64 output column.
 
     A point passes when |got - ref| <= rtol * |ref| (the north-star 1e-12 relative
-    criterion).  A point that fails it is *excused* only if
-      * ``bound`` is given and |got - ref| <= bound_factor * bound, where ``bound`` is the
-        first-order rounding-error bound of the REFERENCE ALGORITHM ITSELF at that point
-        (oracle_tracked.hpp) — the reference subtracts nearly equal numbers there and two
-        correct Float64 implementations cannot agree more closely; or
-      * ``sens`` is given and the difference is below what ``backward_ulps`` ULPs of input
-        perturbation do to the reference's own output.
+    criterion).  A point that fails it is *excused* only if ``bound`` is given and
+    |got - ref| <= bound_factor * bound, where ``bound`` is the first-order rounding-error bound of the
+    REFERENCE ALGORITHM ITSELF at that point (oracle_tracked.hpp): the reference subtracts nearly equal
+    numbers there and two correct Float64 implementations cannot agree more closely.  bound_factor = 2
+    (the reference's own rounding plus ours; measured worst case 0.90).
     Everything else is ``n_bad``.  Exact zeros (gated-off regimes) and non-finite values
     must coincide exactly (``n_zero_mismatch``, ``n_nonfinite_mismatch``)."""
     got = np.asarray(got, dtype=np.float64)
@@ -233,9 +190,6 @@ def compare_report(got, ref, bound=None, sens=None, rtol=F64_RTOL, bound_factor=
         need = both & ~fwd_ok & (bnd > 0)
         if need.any():
             ratio = float(np.max(diff[need] / bnd[need]))
-    if sens is not None:
-        allow = np.abs(np.asarray(sens, dtype=np.float64)) * (backward_ulps * eps / sens_rel)
-        excused |= both & ~fwd_ok & (diff <= allow)
     bad = both & ~fwd_ok & ~excused
     zero_mismatch = int(np.sum(both & ((ref == 0) != (got == 0))))
     counted = both & ~excused
@@ -287,7 +241,7 @@ def assert_f32_method(name, got32, ref32, truth64, bound64=None, max_ulps=F32_UL
     if bound64 is not None:
         t32 = np.abs(np.asarray(truth64, dtype=np.float64)[fin].astype(np.float32))
         ulp = np.spacing(np.maximum(t32, np.finfo(np.float32).tiny)).astype(np.float64)
-        err = np.where(8 * np.abs(np.asarray(bound64)[fin]) > ulp, 0.0, err)
+        err = np.where(2 * np.abs(np.asarray(bound64)[fin]) > ulp, 0.0, err)
     worst = float(err.max()) if err.size else 0.0
     assert worst <= max_ulps, (name, "max Float32 ULP error", worst, "at", int(np.argmax(err)))
     return worst

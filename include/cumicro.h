@@ -443,6 +443,30 @@ int cumicro_diag_reff_lh97_f64(double rho_w, int64_t n, const double* rho, const
 int cumicro_diag_reff_lh97_f32(float rho_w, int64_t n, const float* rho, const float* q_lcl, const float* N_lcl, const float* q_rai,
                                const float* N_rai, float* r_eff, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Multi-GPU: the grid is cut into independent column slabs, one per GPU (no halo, no collective on the tendency path).
+ * The only exchange step is the optional domain diagnostics (BASELINE config 5):
+ *   cumicro_reduce_diagnostics_*: one slab's sums out[k] = Σ_i weight[i] cols[k][i] (weight = rho, or NULL = 1) over `ncols`
+ *     (<= 16) device columns (cols = HOST array of device pointers), Float64 accumulation in a fixed order (bit-reproducible).
+ *     `out` = device array of ncols doubles; `scratch` = caller-owned device buffer of cumicro_reduce_diagnostics_scratch_bytes(ncols)
+ *     bytes whose first 16 bytes are zero before the first use (the kernel leaves them zero); one scratch per stream in flight.
+ *     (The fused config-5 kernel produces its CUMICRO_NDIAG sums in-kernel; this is the same reduction for the other entry points.)
+ *   cumicro_nccl_allreduce_f64: in-place sum of `count` doubles over the ranks of `comm` (the caller's ncclComm_t), enqueued on
+ *     `stream` (a side stream overlaps it with the next tendency kernel).  NCCL is resolved at run time from the process
+ *     (dlsym) or libnccl.so.2; CUMICRO_E_NODEVICE if absent.
+ *   cumicro_nccl_unique_id / comm_init_rank / comm_destroy: thin wrappers of ncclGetUniqueId / ncclCommInitRank /
+ *     ncclCommDestroy (id128 = the 128-byte ncclUniqueId, exchanged by the host's own means) for hosts without an NCCL binding.
+ * ------------------------------------------------------------------------- */
+int64_t cumicro_reduce_diagnostics_scratch_bytes(int ncols);
+int cumicro_reduce_diagnostics_f64(int64_t n, const double* weight, const double* const* cols, int ncols, double* out, void* scratch,
+                                   int64_t scratch_bytes, void* stream);
+int cumicro_reduce_diagnostics_f32(int64_t n, const float* weight, const float* const* cols, int ncols, double* out, void* scratch,
+                                   int64_t scratch_bytes, void* stream);
+int cumicro_nccl_allreduce_f64(void* comm, double* buf, int64_t count, void* stream);
+int cumicro_nccl_unique_id(void* id128);
+int cumicro_nccl_comm_init_rank(void** comm, int nranks, const void* id128, int rank);
+int cumicro_nccl_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif
