@@ -6,7 +6,17 @@
 
 A "step" is one pass of the hot path (BMT.bulk_microphysics_tendencies, 2-moment warm
 rain) over one batch of 2^24 synthetic grid points per GPU (BASELINE.json configs[1]).
-Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+Prints ONE JSON line (rank 0).  See DESIGN.md §5 for every field.
+
+Legs of the cumicro arm (all on the device's current stream, CUDA-event timed):
+  value       EXACTLY K steps after W warm-up steps, inputs resident in HBM (burst figure)
+  sustained   the same step for >= 1 s, SM clock sampled throughout (what a long model run sees)
+  e2e         the same metric through the C-ABI host entry point: pinned host buffers in, pinned host buffers out,
+              H2D + kernel + D2H inside the timed region; beside it the measured pinned H2D / D2H link rates
+  config5     (N > 1, or --config5) BASELINE config 5: the fused 1M + 2M + ice-nucleation kernel on this rank's column slab with
+              the in-kernel domain diagnostics and their NCCL all-reduce (the only collective of the path, through the C-ABI
+              cumicro_nccl_allreduce_f64) inside the timed region
+  cpu_baseline (N = 1) the CPU restatement of the reference on the box's host cores, bounded sample
 """
 from __future__ import annotations
 
@@ -14,7 +24,6 @@ import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -30,6 +39,8 @@ METRIC = "grid points/sec, 2M bulk tendencies FP64"
 UNIT = "grid points/s"
 BYTES_PER_POINT = 88            # 7 input + 4 live output Float64 columns
 WORKLOAD = "2-moment Seifert-Beheng 2006 full tendency set Float64 over 2^24 grid points per GPU"
+KERNEL = ("warm2m_tile_kernel<double,7,LIM=1,128x6,ALL_OUT,TAB> (cm_tile2m.cuh: block-uniform tiles, bulk-copy inputs, "
+          "fast SB2006 body cm_sb2006_fast.cuh with the per-parameter-block ventilation table)")
 
 
 def _peaks():
@@ -42,9 +53,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _roofline_inputs():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+    except Exception:
+        return {}
+
+
 class ClockSampler:
-    """SM clock / throttle-reason samples DURING the timed region (NVML, in-process
-    thread, ~2 ms period; falls back to nvidia-smi -lms when NVML is unavailable)."""
+    """SM clock / throttle-reason samples DURING a timed region (NVML, in-process thread, ~2 ms period)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop, self.t, self.max = index, [], False, None, None
@@ -109,17 +126,17 @@ class ClockSampler:
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path.  Julia is
-    not installable here, so this is the CPU restatement (oracle/, OpenMP over points,
-    all host threads) — kind 'port'.  Each step = one pass over a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path.  Julia is not installable here (no network, no
+    depot), so this is the CPU restatement (oracle/, OpenMP over points, all host threads) — kind 'port'.  Each step = one
+    pass over the SAME workload as the cumicro arm (2^24 points, same generator and seed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import cumicro
+    import cumicro  # noqa: F401
     from cumicro import CMP
     from cumicro.testing import synthetic_states_2m
     from oracle import oracle as orc
-    n = args.ref_points
+    n = args.points
     st = synthetic_states_2m(n, seed=1234)
     block = CMP.pack_2m_warm(CMP.Microphysics2MParams(np.float64), CMP.ThermodynamicsParameters(np.float64))
     cols = [st[k] for k in KEYS]
@@ -135,13 +152,139 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_points_per_step": n},
+            "config": {"workload": WORKLOAD, "points_per_gpu": n, "global_points": n,
+                       "psd": "SB2006 limited rain PSD, log-uniform number concentrations"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{n} of the workload's points per step, OpenMP over points, {threads} threads "
+                             "sample": f"the whole workload ({n} points) per step, OpenMP over points, {threads} threads "
                                        "(C++ restatement of the Julia scalar methods; Julia itself is not in the image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _bind_near_gpu(torch, local):
+    """Pin this process (and with it the first-touch placement of its pinned host buffers) to the CPUs of the GPU's NUMA node."""
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(f"{base}/numa_node").read().strip()
+        cpus = open(f"{base}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = ids & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+        return {"numa_node": int(node), "cpus": len(use) if use else len(allowed), "bound": bool(use)}
+    except Exception as e:  # noqa
+        return {"numa_node": None, "bound": False, "why": str(e)[:80]}
+
+
+def _link_rates(torch, dev, barrier, mb=256, reps=4):
+    """Measured pinned-host <-> device copy rates of this rank [GB/s] (all ranks copy at the same time: the shared-host ceiling)."""
+    nbytes = mb << 20
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in (("h2d", (d, h)), ("d2h", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    # both directions at once (what the chunked pipeline does)
+    h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s2 = torch.cuda.Stream(device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["h2d_while_d2h"] = nbytes * reps / dt / 1e9
+    return out
+
+
+def _config5(torch, dist, dev, lib, args, rank, world):
+    """BASELINE config 5 on this rank's slab: fused 1M + 2M + ice nucleation (+ ARG2000) with in-kernel diagnostics, then the
+    all-reduce of the 4 diagnostic doubles over NCCL through the C-ABI."""
+    from cumicro import CMP, fused
+    from cumicro.testing import arg_test_distribution, synthetic_states_fused
+    n = args.points
+    st = synthetic_states_fused(n, seed=4321 + rank)
+    cols = [torch.from_numpy(st[k]).to(dev) for k in fused.IN_NAMES]
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    mp1, mp2 = CMP.Microphysics1MParams(np.float64), CMP.Microphysics2MParams(np.float64)
+    blk3 = CMP.pack_icenuc(tps, ad=arg_test_distribution("kappa"), dust=CMP.DustType("Kaolinite"), hom_linear=True)
+    outs = [torch.empty_like(cols[0]) for _ in fused.OUT_NAMES]
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    comm = C.c_void_p(0)
+    if world > 1:
+        # the host model's communicator: unique id from rank 0, exchanged over the existing process group
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            st_ = lib.cumicro_nccl_unique_id(raw)
+            if st_ != 0:
+                return {"error": lib.cumicro_last_error().decode()}
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idd = idbuf.to(dev)
+        dist.broadcast(idd, 0)
+        raw = (C.c_char * 128).from_buffer_copy(bytes(idd.cpu().numpy().tobytes()))
+        st_ = lib.cumicro_nccl_comm_init_rank(C.byref(comm), world, raw, rank)
+        if st_ != 0:
+            return {"error": lib.cumicro_last_error().decode()}
+
+    def step(reduce):
+        r = fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *cols, out=outs, diagnostics=True, reduce=False)
+        if reduce and world > 1:
+            st_ = lib.cumicro_nccl_allreduce_f64(comm, C.c_void_p(r["diag"].data_ptr()), C.c_int64(4), stream)
+            assert st_ == 0, lib.cumicro_last_error()
+        return r
+
+    def timed(reduce, k):
+        for _ in range(3):
+            step(reduce)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            r = step(reduce)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r
+
+    k = max(10, min(args.steps, 50))
+    ms_red, r = timed(True, k)
+    ms_loc, _ = timed(False, k)
+    diag = r["diag"].cpu().numpy().tolist()
+    if world > 1:
+        lib.cumicro_nccl_comm_destroy(comm)
+    return {"workload": "fused 1M + 2M + ice nucleation (+ARG2000, 3 modes) Float64, column slabs of 2^24 points per GPU, "
+                        "in-kernel domain diagnostics + NCCL all-reduce of 4 doubles per step (cumicro_nccl_allreduce_f64)",
+            "points_per_gpu": n, "global_points": n * world, "steps": k, "ms_per_step": ms_red,
+            "value": n * world / (ms_red * 1e-3), "unit": UNIT,
+            "ms_per_step_without_allreduce": ms_loc, "allreduce_us": max(0.0, (ms_red - ms_loc) * 1e3),
+            "collective": "ncclAllReduce(sum, 4 x f64) per step" if world > 1 else "none (single GPU)",
+            "diag_global": dict(zip(fused.DIAG_NAMES, diag))}
 
 
 def main():
@@ -150,13 +293,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cumicro", choices=["cumicro", "reference"])
-    ap.add_argument("--points", type=int, default=1 << 24, help="grid points per GPU")
-    ap.add_argument("--ref-points", type=int, default=1 << 22, help="points per step of the CPU arm")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 22, help="points of the cpu_baseline sample")
+    ap.add_argument("--points", type=int, default=1 << 24, help="grid points per GPU (and per step of the reference arm)")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 24, help="points of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--sustained-s", type=float, default=1.2, help="length of the sustained leg [s]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--diagnostics", action="store_true",
-                    help="also all-reduce (NCCL) a 4-double diagnostic vector every step, as the multi-GPU host model would")
+    ap.add_argument("--config5", action="store_true", help="run the config-5 leg at N = 1 too")
+    ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cumicro" else args.warmup
 
@@ -181,6 +324,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the cumicro arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_near_gpu(torch, local)      # before any pinned allocation: first touch lands on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -199,23 +343,24 @@ def main():
     outs = [torch.empty_like(cols["rho"]) for _ in range(4)]
     torch.cuda.synchronize()
 
-    diag = torch.zeros(4, dtype=torch.float64, device=dev)
-
     def step():
-        r = BMT.bulk_microphysics_tendencies(scheme, mp, tps, *[cols[k] for k in KEYS], out=outs)
-        if args.diagnostics and dist is not None:
-            dist.all_reduce(diag)     # the only collective of the path: optional global diagnostic sums
-        return r
+        return BMT.bulk_microphysics_tendencies(scheme, mp, tps, *[cols[k] for k in KEYS], out=outs)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         step()
     barrier()
-    # ---- timed region: K steps, CUDA events on the launching (current) stream -------------
+    # ---- timed region: EXACTLY K steps, CUDA events on the launching (current) stream -------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches0 = lib.cumicro_launch_count()
     with ClockSampler(local) as clocks:
@@ -228,11 +373,23 @@ def main():
     launches = lib.cumicro_launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(total_ms)
     value = n * world * args.steps / (total_ms_max * 1e-3)
+    kernel_ms = float(np.mean(per_launch_ms))
+
+    # ---- sustained leg: the same step for >= 1 s (clock under load, not a burst) -----------------------
+    n_sus = max(args.steps, int(args.sustained_s * 1e3 / max(kernel_ms, 1e-3)) + 1)
+    with ClockSampler(local) as clocks_sus:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_sus):
+            step()
+        e1.record()
+        barrier()
+    sus_ms = max_over_ranks(e0.elapsed_time(e1))
+    sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                 "value": n * world * n_sus / (sus_ms * 1e-3), "unit": UNIT, "clocks": clocks_sus.summary()}
 
     # ---- FP64 pipe peak measured in place --------------------------------------------------
     scratch = torch.zeros(8, dtype=torch.float64, device=dev)
@@ -249,6 +406,7 @@ def main():
             fp64_peak = max(fp64_peak or 0.0, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
 
     # ---- e2e: host buffers in, host buffers out, through the C-ABI host entry point --------
+    link = _link_rates(torch, dev, barrier)
     host_out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
     BMT.bulk_microphysics_tendencies_host(scheme, mp, tps, *[pinned[k] for k in KEYS], out=host_out)  # warm-up
     barrier()
@@ -256,11 +414,24 @@ def main():
     for _ in range(args.e2e_steps):
         BMT.bulk_microphysics_tendencies_host(scheme, mp, tps, *[pinned[k] for k in KEYS], out=host_out)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n * world * args.e2e_steps / e2e_s
+    h2d_bytes, d2h_bytes = 7 * 8 * n, 4 * 8 * n
+    # the longer of the two copy legs at this rank's measured link rate (both directions busy) bounds the step
+    link_bound_s = max(h2d_bytes / (link["h2d_while_d2h"] * 1e9), d2h_bytes / (link["d2h"] * 1e9))
+    link_all = None
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * args.e2e_steps / float(t.item())
+        g = [None] * world
+        dist.all_gather_object(g, {"rank": rank, **{k: round(v, 2) for k, v in link.items()}, "numa": numa})
+        link_all = g
+
+    # ---- config 5 with the only collective of the path -------------------------------------
+    cfg5 = None
+    if (world > 1 or args.config5) and not args.no_config5:
+        try:
+            cfg5 = _config5(torch, dist, dev, lib, args, rank, world)
+        except Exception as e:  # noqa
+            cfg5 = {"error": repr(e)[:300]}
 
     if rank != 0:
         if dist is not None:
@@ -268,44 +439,54 @@ def main():
         return
 
     hbm_peak, peak_src = _peaks()
-    kernel_ms = float(np.mean(per_launch_ms))
-    achieved = BYTES_PER_POINT * n / (kernel_ms * 1e-3) / 1e9
+    ri = _roofline_inputs()
+    achieved_gbs = BYTES_PER_POINT * n / (kernel_ms * 1e-3) / 1e9
+    pts_per_gpu_s = n / (kernel_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points_per_gpu": n, "global_points": n * world,
-                   "parallelism": f"column slabs x{world}, no data-path collective"
-                                  + (" + NCCL all-reduce of 4 diagnostic doubles per step" if args.diagnostics and world > 1 else ""),
+                   "parallelism": f"column slabs x{world}, no data-path collective (config5 leg: + NCCL all-reduce of 4 diagnostic doubles per step)",
                    "l2": "inputs (7 x 134 MB columns) larger than the 126 MB L2; no flush needed",
                    "psd": "SB2006 limited rain PSD, log-uniform number concentrations"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "pointwise_kernel_pipelined<double,7,4,Warm2MFused<7,SPEC=1>,128x7> (cp.async double-buffered inputs, 16 waves; specialised for the default SB2006 block structure)",
-                     "kernel_ms": kernel_ms, "bytes_per_point": BYTES_PER_POINT},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 7 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n,
-                "steps": args.e2e_steps, "api": "cumicro_bmt2m_warm_host_f64 (pinned host buffers, chunked H2D/kernel/D2H)"},
+        "sustained": sustained,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": args.e2e_steps, "api": "cumicro_bmt2m_warm_host_f64 (pinned host buffers, chunked H2D/kernel/D2H)",
+                "link_gbs": {k: round(v, 2) for k, v in link.items()},
+                "frac_of_link": (link_bound_s * args.e2e_steps) / e2e_s,
+                "link_note": "frac_of_link = time the longer copy leg needs at this rank's measured pinned-copy rate / measured e2e time",
+                "numa": numa, "ranks": link_all},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    # ---- rooflines.  The binding resource is the FP64 pipe: algorithmic flops per point (the direct
+    # formulation's FP64 work, counted by ncu on the round-1 kernel and used by the round-1 review) over the in-place DFMA probe.
+    fl_alg = ri.get("fp64_flops_per_point_algorithmic", 556.5881729125977)
+    roof = {"bound": "fp64", "unit": "TFLOP/s", "traffic": None, "kernel": KERNEL, "kernel_ms": kernel_ms,
+            "flops_per_point_algorithmic": fl_alg,
+            "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                    "bytes_per_point": BYTES_PER_POINT, "peak_source": peak_src,
+                    "traffic_ncu": ri.get("dram_bytes_per_launch_2m_warm"),
+                    "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/), not measured in this run"}}
     if fp64_peak:
-        line["fp64_probe_tflops"] = fp64_peak
-    prof = os.path.join(ROOT, "profiles", "roofline_inputs.json")
-    if os.path.exists(prof):
-        try:
-            pj = json.load(open(prof))
-            fl = pj.get("fp64_flops_per_point_2m_warm")
-            if fl and fp64_peak:
-                tf = fl * value / world / 1e12
-                line["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                                         "frac": tf / fp64_peak, "flops_per_point": fl, "source": pj.get("source")}
-                ai = pj.get("fp64_arith_inst_per_point_2m_warm")
-                if ai:   # DFMA, DMUL and DADD all take one FP64 issue slot: the pipe's own roofline is instructions, not flops
-                    line["roofline_fp64"]["issue_frac"] = ai * value / world / (fp64_peak * 1e12 / 2.0)
-                    line["roofline_fp64"]["fp64_inst_per_point"] = ai
-            if pj.get("dram_bytes_per_launch_2m_warm"):
-                line["roofline"]["traffic"] = pj["dram_bytes_per_launch_2m_warm"]
-        except Exception:
-            pass
+        ach = fl_alg * pts_per_gpu_s / 1e12
+        roof.update({"achieved": ach, "peak": fp64_peak, "frac": ach / fp64_peak,
+                     "peak_source": "cumicro_probe_fp64_fma timed in this run (in-place DFMA chain, 2 flops each)"})
+        fe, ie, oe = ri.get("fp64_flops_per_point_executed"), ri.get("fp64_pipe_inst_per_point_executed"), ri.get("other_inst_per_point_executed")
+        if fe and ie:
+            # executed view: an FP64 instruction holds the sub-partition's issue port for two cycles, every other instruction for one
+            inst_rate = fp64_peak * 1e12 / 2.0            # FP64 thread-instructions / s the pipe can start
+            roof["executed"] = {"flops_per_point": fe, "fp64_pipe_inst_per_point": ie, "other_inst_per_point": oe,
+                                "tflops": fe * pts_per_gpu_s / 1e12, "fp64_pipe_frac": ie * pts_per_gpu_s / inst_rate,
+                                "issue_cycles_frac": ((2 * ie + oe) * pts_per_gpu_s / (2 * inst_rate)) if oe else None,
+                                "source": ri.get("source")}
+    else:
+        roof.update({"achieved": None, "peak": None, "frac": None})
+    line["roofline"] = roof
+    line["fp64_probe_tflops"] = fp64_peak
+    if cfg5 is not None:
+        line["config5"] = cfg5
 
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as orc
@@ -323,7 +504,7 @@ def main():
                 break
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": m * reps / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                                "sample": f"first {m} points of the workload x {reps} passes, OpenMP over points "
+                                "sample": f"the workload's {m} points x {reps} passes, OpenMP over points "
                                           "(C++ restatement of the reference's scalar Julia methods)"}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -18,7 +18,7 @@ def __getattr__(name):  # torch-dependent modules are imported on first use
             "CloudDiagnostics": "CloudDiagnostics", "CMD": "CloudDiagnostics",
             "AerosolActivation": "AerosolActivation", "AA": "AerosolActivation",
             "AerosolModel": "AerosolModel", "AM": "AerosolModel",
-            "IceNucleation": "IceNucleation", "IN": "IceNucleation", "fused": "fused",
+            "IceNucleation": "IceNucleation", "IN": "IceNucleation", "fused": "fused", "collective": "collective",
             "P3Scheme": "P3Scheme", "P3": "P3Scheme", "CMP3": "parameters_p3"}
     if name in lazy:
         return importlib.import_module("." + lazy[name], __name__)

@@ -63,4 +63,10 @@ def zero_column(like: torch.Tensor):
 
 class Tendencies(dict):
     """NamedTuple-like result: ``out.dq_lcl_dt`` or ``out['dq_lcl_dt']``."""
-    __getattr__ = dict.__getitem__
+
+    def __getattr__(self, name):
+        # AttributeError (not KeyError) for a missing name: hasattr(), getattr(x, n, default), copy and pickle rely on it
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None

@@ -5,6 +5,7 @@
 #include <cstdio>
 
 #include <map>
+#include <vector>
 #include <utility>
 
 #include "cm_hostpipe.cuh"
@@ -15,6 +16,8 @@ std::atomic<int64_t> g_launches{0};
 }  // namespace
 
 namespace cmh {
+
+void release_tables();   // kernels_2m.cu: the cached ventilation tables
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -94,10 +97,38 @@ int slot_stream(int slot, cudaStream_t* s) {
     return CUMICRO_OK;
 }
 
+// Scratch keyed by (device, stream): two calls in flight on different streams never share it, and a buffer that has to grow is
+// retired (freed by release_workspaces()), not freed under a kernel that may still use it.
+namespace {
+thread_local std::map<std::pair<int, cudaStream_t>, Workspace> g_stream_ws;
+thread_local std::vector<void*> g_retired;
+}  // namespace
+int stream_workspace(cudaStream_t s, size_t bytes, void** ptr) {
+    int dev = 0;
+    int rc = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    Workspace& w = g_stream_ws[{dev, s}];
+    if (w.bytes < bytes) {
+        if (w.ptr) g_retired.push_back(w.ptr);
+        w.ptr = nullptr;
+        w.bytes = 0;
+        rc = cuda_status(cudaMalloc(&w.ptr, bytes), "cudaMalloc (per-stream scratch)");
+        if (rc) return rc;
+        w.bytes = bytes;
+    }
+    *ptr = w.ptr;
+    return CUMICRO_OK;
+}
+
 void release_workspaces() {
     for (auto& kv : g_pipe.ws)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     g_pipe.ws.clear();
+    for (auto& kv : g_stream_ws)
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+    g_stream_ws.clear();
+    for (void* p : g_retired) cudaFree(p);
+    g_retired.clear();
 }
 
 }  // namespace cmh
@@ -107,6 +138,6 @@ extern "C" {
 int cumicro_version(void) { return CUMICRO_VERSION; }
 const char* cumicro_last_error(void) { return g_err; }
 int64_t cumicro_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-void cumicro_release_workspace(void) { cmh::release_workspaces(); }
+void cumicro_release_workspace(void) { cmh::release_workspaces(); cmh::release_tables(); }
 
 }  // extern "C"

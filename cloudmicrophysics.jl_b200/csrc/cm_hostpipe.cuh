@@ -20,6 +20,8 @@ int workspace(int slot, size_t bytes, void** ptr);
 // Per-thread non-blocking stream of slot `slot` on the current device.
 int slot_stream(int slot, cudaStream_t* s);
 void release_workspaces();
+// Per-thread device scratch of the calling (device, stream): never shared between streams, never freed while it may be in use.
+int stream_workspace(cudaStream_t s, size_t bytes, void** ptr);
 }  // namespace cmh
 
 namespace cm {

@@ -46,7 +46,105 @@ struct W2K {
     double tau0, kcr;         // kcr sqrt(accr.rho0 / pdf_r.rho0)
     double krc, nkrr;         // kappa_rr cbrt(1/6), -krr
     double Deq, Dr_th, kbr, kappa_br;
+    // ventilation table (limited PSD; see W2Tab): u = tab_inv_h lx + tab_u0 is the interval coordinate of log xr_mean
+    double tab_inv_h, tab_u0;
+    double av1_Dr, cvx;       // av1 cDr (2 pi a_vent_1 Dr / cx);  cvx = cv + log(bv1 cDr): 2 pi b_vent_1 cbrt(Sc) Dr sqrt(N_Re) / r4 = exp((kv + 1/3) lx + cvx)
+    double kvx;               // kv + 1/3
 };
+
+// ---- ventilation table ------------------------------------------------------------------------------------------------------
+// Under the limited PSD log xr_mean lives in [log xr_min, log xr_max], and the number-tendency side of CM2.rain_evaporation depends
+// on it through two smooth functions only (t = cbrt(6 x*/xr), everything else is parameters):
+//     T1(lx) = Dr/xr 2 pi a_vent_0_coeff Γ_incl(-1, t)            T2(lx) = Dr/xr 2 pi b_vent_0_coeff cbrt(Sc) Γ_incl(beta_vent_0, t) sqrt(N_Re) / r4
+//     dN/dt = G S N_rai (T1 + T2 r4),   r4 = (rho0/rho)^(1/4)
+// i.e. four real powers of t, exp(-t) and a division per point (4 exp_, 2 reciprocals: ~60 FP64 instructions).  The host tabulates
+// T1 and T2 for the parameter block at hand: kTabN intervals of log xr_mean, degree-7 polynomials in the centred interval
+// coordinate s in [-1/2, 1/2] (Chebyshev interpolation in long double, converted to monomials), verified against the closed form
+// before use (max relative error < 1e-15, else the table is not used and the closed form runs).  The functions are analytic in
+// log xr (nearest singularity ~12 away from the real axis against an interval half-width of 0.08), so degree 7 converges to ~2e-16.
+// Per point: 3 + 14 FP64 instructions and 8 128-bit shared-memory loads.
+constexpr int kTabN = 64;            // intervals; rows = kTabN + 1 (nodes at the interval centres i h, i = 0..kTabN)
+constexpr int kTabRow = 18;          // doubles per row: 8 + 8 coefficients + 2 of padding (144 B: rows rotate over the banks)
+constexpr int kTabDoubles = (kTabN + 1) * kTabRow;
+
+struct W2TabEval {   // closed forms in long double (host only)
+    long double xr_min, cDr, two_pi_a0, two_pi_b0_sc, c1[2], c2[2], e1[2], e2[2], alpha_nu, beta, rho_ratio4;
+    void operator()(long double lx, long double& T1, long double& T2) const {
+        const long double xr = expl(lx), cx = expl(lx / 3), Dr = cDr * cx;
+        const long double t = cbrtl(6 * xr_min / xr);
+        long double g[2];
+        for (int i = 0; i < 2; ++i) g[i] = expl(-t) / (c1[i] * powl(t, e1[i]) + c2[i] * powl(t, e2[i]));
+        const long double sqrt_NRe = sqrtl(alpha_nu * powl(xr, beta) * Dr) * rho_ratio4;   // without (pdf_r.rho0/rho)^(1/4)
+        T1 = Dr / xr * two_pi_a0 * g[0];
+        T2 = Dr / xr * two_pi_b0_sc * g[1] * sqrt_NRe;
+    }
+};
+
+// Fills tab[kTabDoubles] and k.tab_*; returns the verified max relative error (the caller uses the table only if it is < 1e-15).
+inline double build_w2_table(const cumicro_params_2m_warm_f64& p, W2K& k, double* tab) {
+    const auto& sb = p.sb;
+    const long double pi = 3.141592653589793238462643383279502884L;
+    W2TabEval f;
+    f.xr_min = sb.pdf_r.xr_min;
+    f.cDr = cbrtl(6 / (pi * (long double)sb.pdf_r.rho_w));
+    const long double D = std::max((long double)p.aps.D_vapor, (long double)k.eps_n);
+    f.two_pi_a0 = 2 * pi * sb.evap.a_vent_0_coeff;
+    f.two_pi_b0_sc = 2 * pi * sb.evap.b_vent_0_coeff * cbrtl((long double)p.aps.nu_air / D);
+    const long double a[2] = {-1.0L, (long double)sb.evap.beta_vent_0};
+    for (int i = 0; i < 2; ++i) {   // the literals of CM2:746-753 as the Float64 method reads them
+        f.c1[i] = (long double)0.33 - (long double)0.7 * a[i];
+        f.c2[i] = (long double)1.34 - (long double)0.1 * a[i];
+        f.e1[i] = (long double)0.08 - (long double)0.93 * a[i];
+        f.e2[i] = (long double)0.8 - a[i];
+    }
+    f.alpha_nu = (long double)sb.evap.alpha / p.aps.nu_air;
+    f.beta = sb.evap.beta;
+    f.rho_ratio4 = powl((long double)sb.evap.rho0 / sb.pdf_r.rho0, 0.25L);
+    const long double lo = logl((long double)sb.pdf_r.xr_min), hi = logl((long double)sb.pdf_r.xr_max);
+    const long double h = (hi - lo) / kTabN;
+    k.tab_inv_h = (double)(1 / h);
+    k.tab_u0 = (double)(-lo / h);
+    // Chebyshev nodes on [-1/2, 1/2], interpolation in the Chebyshev basis (discrete orthogonality), then T_j(2 s) -> monomials in s
+    constexpr int M = 8;
+    long double xs[M], Tm[M][M];   // Tm[j][q]: coefficient of s^q in T_j(2 s)
+    for (int q = 0; q < M; ++q) xs[q] = 0.5L * cosl(pi * (2 * q + 1) / (2 * M));
+    for (int j = 0; j < M; ++j) for (int q = 0; q < M; ++q) Tm[j][q] = 0;
+    Tm[0][0] = 1; Tm[1][1] = 2;
+    for (int j = 2; j < M; ++j)
+        for (int q = 0; q < M; ++q) Tm[j][q] = (q > 0 ? 4 * Tm[j - 1][q - 1] : 0) - Tm[j - 2][q];   // T_j(y) = 2 y T_{j-1} - T_{j-2}, y = 2 s
+    for (int i = 0; i <= kTabN; ++i) {
+        long double v[2][M];
+        for (int q = 0; q < M; ++q) f(lo + (i + xs[q]) * h, v[0][q], v[1][q]);
+        for (int fn = 0; fn < 2; ++fn) {
+            long double cheb[M], mono[M];
+            for (int j = 0; j < M; ++j) {
+                long double acc = 0;
+                for (int q = 0; q < M; ++q) acc += v[fn][q] * cosl(pi * j * (2 * q + 1) / (2 * M));
+                cheb[j] = acc * (j == 0 ? 1.0L : 2.0L) / M;
+            }
+            for (int q = 0; q < M; ++q) { mono[q] = 0; for (int j = 0; j < M; ++j) mono[q] += cheb[j] * Tm[j][q]; }
+            for (int q = 0; q < M; ++q) tab[i * kTabRow + fn * M + q] = (double)mono[q];
+        }
+        tab[i * kTabRow + 16] = tab[i * kTabRow + 17] = 0.0;
+    }
+    // verification: Float64 Horner against the closed form at points that are not interpolation nodes
+    double worst = 0.0;
+    for (int i = 0; i <= kTabN; ++i)
+        for (int m = 0; m <= 8; ++m) {
+            const double sv = -0.5 + m / 8.0;
+            if ((i == 0 && sv < 0) || (i == kTabN && sv > 0)) continue;
+            long double t1, t2;
+            f(lo + (i + (long double)sv) * h, t1, t2);
+            for (int fn = 0; fn < 2; ++fn) {
+                const double* c = tab + i * kTabRow + fn * M;
+                double acc = c[M - 1];
+                for (int q = M - 2; q >= 0; --q) acc = fma(acc, sv, c[q]);
+                const long double tr = fn ? t2 : t1;
+                worst = std::max(worst, (double)fabsl(((long double)acc - tr) / tr));
+            }
+        }
+    return worst;
+}
 
 // STD structure (see warm2m_fast): exponents 3 / 4 / -5 and strictly positive ventilation coefficients.
 inline bool w2k_supported(const cumicro_params_2m_warm_f64& p) {
@@ -55,7 +153,8 @@ inline bool w2k_supported(const cumicro_params_2m_warm_f64& p) {
     return sb.acnv.b == 3.0 && sb.accr.c == 4.0 && sb.self.d == -5.0 && pos(sb.evap.a_vent_0_coeff) && pos(sb.evap.b_vent_0_coeff) &&
            pos(sb.evap.alpha) && pos(p.aps.nu_air) && pos(sb.pdf_r.rho_w) && pos(sb.pdf_r.xr_min) && pos(sb.pdf_r.xr_max) &&
            pos(sb.pdf_r.N0_min) && pos(sb.pdf_r.N0_max) && pos(sb.pdf_r.lam_min) && pos(sb.pdf_r.lam_max) && pos(sb.pdf_r.rho0) &&
-           pos(sb.evap.rho0) && pos(sb.accr.rho0) && pos(p.aps.D_vapor) && pos(p.aps.K_therm);
+           pos(sb.evap.rho0) && pos(sb.accr.rho0) && pos(p.aps.D_vapor) && pos(p.aps.K_therm) && pos(sb.evap.b_vent_1) &&
+           sb.pdf_r.xr_min < sb.pdf_r.xr_max;
 }
 
 inline W2K make_w2k(const cumicro_params_2m_warm_f64& p, bool method_is_f32) {
@@ -111,6 +210,10 @@ inline W2K make_w2k(const cumicro_params_2m_warm_f64& p, bool method_is_f32) {
     k.tau0 = sb.accr.tau0; k.kcr = sb.accr.kcr * std::sqrt(sb.accr.rho0 / sb.pdf_r.rho0);
     k.krc = sb.self.kappa_rr * std::cbrt(1.0 / 6.0); k.nkrr = -sb.self.krr;
     k.Deq = sb.brek.Deq; k.Dr_th = sb.brek.Dr_th; k.kbr = sb.brek.kbr; k.kappa_br = sb.brek.kappa_br;
+    k.tab_inv_h = 0.0; k.tab_u0 = 0.0;
+    k.av1_Dr = k.av1 * k.cDr;
+    k.kvx = k.kv + 1.0 / 3.0;
+    k.cvx = k.cv + std::log(k.bv1 * k.cDr);
     return k;
 }
 
@@ -119,9 +222,11 @@ CM_HD bool lt_eps_(double x, int eps_hi) { return hi32(x) < eps_hi; }
 CM_HD double neg_(double x) { return mk64(hi32(x) ^ (int)0x80000000, lo32(x)); }
 
 // LIM = 1 / 0: limited / not-limited rain PSD.  x = (rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai), q_ice as seen by the thermodynamics.
-template <int LIM>
+// TAB: `tab` (shared memory on the device) holds the verified ventilation table of this parameter block (limited PSD only).
+template <int LIM, bool TAB = false>
 CM_HD void warm2m_fast(const W2K& k, double rho, double T, double q_tot, double q_lcl, double n_lcl, double q_rai, double n_rai,
-                       double q_ice, bool have_ice, double (&y)[4]) {
+                       double q_ice, bool have_ice, double (&y)[4], const double* tab = nullptr) {
+    static_assert(!(TAB && LIM == 0), "the ventilation table covers the bounded log xr_mean of the limited PSD");
     const int eh = k.eps_hi;
     // input clamps                                                   BMT:827-836
     rho = clamp0_(rho); q_tot = clamp0_(q_tot); q_lcl = clamp0_(q_lcl);
@@ -161,7 +266,7 @@ CM_HD void warm2m_fast(const W2K& k, double rho, double T, double q_tot, double 
     const double sq_rai = qr_off ? k.eps : q_rai;
     const double sN_rai = Nr_off ? k.eps : N_rai;
     const double L_rai = rho * sq_rai;
-    double lx, cx, inv_cx, xr_ratio = 1.0;
+    double lx, cx, inv_cx = 0.0, xr_ratio = 1.0;
     if (LIM == 1) {
         const double lL = log_abs_(L_rai), lN = log_abs_(sN_rai);
         const double lxt = clamp_(lL - lN, k.lxmin, k.lxmax);                              // Eq. (94)
@@ -169,14 +274,13 @@ CM_HD void warm2m_fast(const W2K& k, double rho, double T, double q_tot, double 
         const double llam = clamp_(fma(lN0 - lL, 0.25, k.c4), k.llmin, k.llmax);           // Eq. (96)
         lx = clamp_((lL - lN0) + llam, k.lxmin, k.lxmax);                                  // Eq. (97)
         cx = exp_(lx * k.third);
-        inv_cx = rcp_(cx);
+        if (!TAB) inv_cx = rcp_(cx);
     } else {
         const double xr_mean = L_rai * rcp_(sN_rai);
         xr_ratio = xr_mean * k.inv_xr_min;
         cx = cbrt_pair_(xr_mean, inv_cx);
         lx = log_abs_(xr_mean);
     }
-    const double inv_xr_mean = inv_cx * inv_cx * inv_cx;
     const double Dr = cx * k.cDr;                               // CM2:590, 802
     const double sqrt_rho0_rho = sqrtp_(k.rho0 * inv_rho);
 
@@ -185,22 +289,41 @@ CM_HD void warm2m_fast(const W2K& k, double rho, double T, double q_tot, double 
     {
         const double S = fma(qv * rho_Rv_T, inv_p_vs, -1.0);                    // TDI.supersaturation_over_liquid
         const double G = rcp_(fma(LT * k.inv_K, g1, (T * inv_p_vs) * k.RvD));   // CO.G_func_liquid
-        const double lt = fma(lx, k.nthird, k.lt0);
-        const double t_star = k.ct * inv_cx;
-        const double a0 = fma(k.ne1[0], lt, -t_star), a1 = fma(k.ne1[1], lt, -t_star);
-        const double E0 = (LIM == 1) ? exp_(a0) : exp_full_(a0);
-        const double E1 = (LIM == 1) ? exp_(a1) : exp_full_(a1);
-        const double den0 = fma(k.c2[0], exp_(k.de[0] * lt), k.c1[0]);
-        const double den1 = fma(k.c2[1], exp_(k.de[1] * lt), k.c1[1]);
-        const double vv = exp_(fma(k.kv, lx, k.cv)) * sqrtp_(sqrt_rho0_rho);     // sqrt(N_Re)
-        const double Fv0 = fma(E1 * den0, vv, E0 * den1) * rcp_(den0 * den1);    // 2 pi (a_vent_0 + b_vent_0 cbrt(Sc) sqrt(N_Re))
-        const double Fv1 = fma(k.bv1, vv, k.av1);
+        const double r4 = sqrtp_(sqrt_rho0_rho);                                // (rho0/rho)^(1/4)
         // gates: q_rai < eps || N_rai <= eps zero the common factor (every other factor is finite: safe values); S >= 0 makes it
         // non-negative and min(0, .) returns the reference's 0                                                   CM2:822-827
         const bool off_q = qr_off || (N_rai <= k.eps);
-        const double common = off_q ? 0.0 : G * S * N_rai * Dr;
-        const double dn = cap0_(common * Fv0 * inv_xr_mean);
-        evap_dq = cap0_(common * Fv1 * inv_rho);
+        const double common = off_q ? 0.0 : G * S * N_rai;
+        double dn;
+        if (TAB) {
+            // dN/dt = G S N_rai (T1 + T2 r4) from the ventilation table;  dq/dt = G S N_rai / rho (2 pi a_vent_1 Dr + 2 pi b_vent_1 cbrt(Sc) Dr sqrt(N_Re))
+            const double magic = 6755399441055744.0;
+            const double u = fma(lx, k.tab_inv_h, k.tab_u0);
+            const double tm = u + magic;
+            const double sv = u - (tm - magic);                    // in [-1/2, 1/2]
+            const double* row = tab + lo32(tm) * kTabRow;
+            double t1 = row[7], t2 = row[15];
+#pragma unroll
+            for (int q = 6; q >= 0; --q) { t1 = fma(t1, sv, row[q]); t2 = fma(t2, sv, row[8 + q]); }
+            dn = cap0_(common * fma(t2, r4, t1));
+            const double w1 = exp_(fma(k.kvx, lx, k.cvx)) * r4;     // 2 pi b_vent_1 cbrt(Sc) Dr sqrt(N_Re)
+            evap_dq = cap0_(common * inv_rho * fma(k.av1_Dr, cx, w1));
+        } else {
+            const double inv_xr_mean = inv_cx * inv_cx * inv_cx;
+            const double lt = fma(lx, k.nthird, k.lt0);
+            const double t_star = k.ct * inv_cx;
+            const double a0 = fma(k.ne1[0], lt, -t_star), a1 = fma(k.ne1[1], lt, -t_star);
+            const double E0 = (LIM == 1) ? exp_(a0) : exp_full_(a0);
+            const double E1 = (LIM == 1) ? exp_(a1) : exp_full_(a1);
+            const double den0 = fma(k.c2[0], exp_(k.de[0] * lt), k.c1[0]);
+            const double den1 = fma(k.c2[1], exp_(k.de[1] * lt), k.c1[1]);
+            const double vv = exp_(fma(k.kv, lx, k.cv)) * r4;                           // sqrt(N_Re)
+            const double Fv0 = fma(E1 * den0, vv, E0 * den1) * rcp_(den0 * den1);       // 2 pi (a_vent_0 + b_vent_0 cbrt(Sc) sqrt(N_Re))
+            const double Fv1 = fma(k.bv1, vv, k.av1);
+            const double cD = common * Dr;
+            dn = cap0_(cD * Fv0 * inv_xr_mean);
+            evap_dq = cap0_(cD * Fv1 * inv_rho);
+        }
         evap_dn = (LIM == 0 && xr_ratio < k.eps) ? 0.0 : dn;
     }
 

@@ -11,19 +11,27 @@
 //     per point).  They are read at their point of use through an address that depends on the tile counter (an opaque zero),
 //     i.e. one uniform constant-bank load per use and no register held;
 //   * stores are streaming 64/32-bit st.global.cs, one per output column.
-// Columns must be 16-byte aligned for the bulk copies (any cudaMalloc'd or torch buffer is); the launcher falls back to
-// cm_launch.cuh's cp.async shape otherwise.  A partial last tile is loaded with guarded scalar loads.
+// Columns must be 16-byte aligned for the bulk copies (any cudaMalloc'd or torch buffer is); otherwise, and for a partial last
+// tile, the same kernel loads with guarded scalar loads (identical results).
 #pragma once
 #include "cm_launch.cuh"
 #include "cm_sb2006_fast.cuh"
+
+// Device copy of the verified ventilation table of a parameter block (cm_sb2006_fast.cuh), cached per device and block content;
+// fills k.tab_inv_h / tab_u0.  nullptr if the table cannot be used (verification failed, allocation failed, stream capture in progress):
+// the caller then runs the closed form.  The first call for a new parameter block builds the table on the host (~1 ms) and uploads
+// 9.4 KB with a blocking copy; later calls are a lookup.  Defined in kernels_2m.cu.
+namespace cmh { const double* w2_table(const cumicro_params_2m_warm_f64& p, cm::W2K& k); }
 
 namespace cm {
 
 template <class FT, int NIN> struct Tile2MArgs {
     W2K k;
+    const double* tab;
     const FT* in[NIN];
     FT* out[4];
     int64_t n;
+    int bulk_ok;   // every input column is 16-byte aligned: full tiles arrive by bulk copies (otherwise by guarded scalar loads, same bits)
 };
 
 namespace tile {
@@ -67,17 +75,22 @@ CM_DEV bool elect_one() {
 }  // namespace tile
 
 // PPT points per thread: the PPT bodies of one thread are independent and share every constant load.
-template <class FT, int NIN, int LIM, int BLOCK, int MINB, bool ALL_OUT, int PPT>
+template <class FT, int NIN, int LIM, int BLOCK, int MINB, bool ALL_OUT, int PPT, bool TAB>
 __global__ void __launch_bounds__(BLOCK, MINB) warm2m_tile_kernel(const __grid_constant__ Tile2MArgs<FT, NIN> a) {
     constexpr int TILE = BLOCK * PPT;
     constexpr int NWARP = BLOCK / 32;
     __shared__ __align__(128) FT stage[2][NIN][TILE];
+    __shared__ __align__(16) double tab_s[TAB ? kTabDoubles : 2];
     __shared__ __align__(8) unsigned long long full[2];
+    if (TAB) {
+        for (int i = threadIdx.x; i < kTabDoubles / 2; i += BLOCK)
+            reinterpret_cast<double2*>(tab_s)[i] = __ldg(reinterpret_cast<const double2*>(a.tab) + i);
+    }
     math_tables_init<BLOCK>();
     math_tables_init_log2<BLOCK>();
     const int tid = threadIdx.x;
     const unsigned n_tiles = (unsigned)((a.n + TILE - 1) / TILE);
-    const unsigned n_full = (unsigned)(a.n / TILE);        // tiles [0, n_full) are complete
+    const unsigned n_full = a.bulk_ok ? (unsigned)(a.n / TILE) : 0u;   // tiles [0, n_full) are complete and fetched by bulk copies
     constexpr unsigned kTileBytes = TILE * sizeof(FT);
     // the leader lane of warp w fetches columns w, w + NWARP, ...: the copy-issue instructions are spread over the SM sub-partitions
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction
@@ -131,8 +144,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) warm2m_tile_kernel(const __grid_c
         double y[PPT][4];
 #pragma unroll
         for (int p = 0; p < PPT; ++p)
-            warm2m_fast<LIM>(k, x[p][0], x[p][1], x[p][2], x[p][3], x[p][4], x[p][5], x[p][6], (NIN == 8) ? clamp0_(x[p][NIN - 1]) : 0.0,
-                             NIN == 8, y[p]);
+            warm2m_fast<LIM, TAB>(k, x[p][0], x[p][1], x[p][2], x[p][3], x[p][4], x[p][5], x[p][6], (NIN == 8) ? clamp0_(x[p][NIN - 1]) : 0.0,
+                                  NIN == 8, y[p], tab_s);
 #pragma unroll
         for (int p = 0; p < PPT; ++p)
             if (it0 + p * BLOCK < a.n) {
@@ -143,24 +156,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) warm2m_tile_kernel(const __grid_c
     }
 }
 
-// Enqueue the tile kernel; returns -1 if the columns do not meet its alignment requirement (caller falls back).
-template <class FT, int NIN, int LIM, int BLOCK = 128, int MINB = 7, int PPT = 1>
-int launch_warm2m_tile(const W2K& k, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[4], cudaStream_t stream, const char* what,
-                       int waves = 16) {
+// Enqueue the tile kernel.  `tab` = device ventilation table of this block (cmh::w2_table) or nullptr (closed form).
+// Columns that are not 16-byte aligned are read with scalar loads by the same kernel (identical results).
+// Launch shape (tools/tune_2m.py, 2^24 points, ms): 128x5 0.440, 128x6 0.407, 128x7 0.416, 128x8 0.423, 256x3 0.467 (16 waves);
+// 128x7 with 4 / 8 / 16 / 32 / 64 waves of blocks: 0.414 / 0.411 / 0.416 / 0.422 / 0.463.
+template <class FT, int NIN, int LIM, int BLOCK = 128, int MINB = 6, int PPT = 1>
+int launch_warm2m_tile(const W2K& k, const double* tab, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[4], cudaStream_t stream,
+                       const char* what, int waves = 8) {
     if (n == 0) return CUMICRO_OK;
-    for (int c = 0; c < NIN; ++c)
-        if (!cmh::aligned16(in[c])) return -1;
     Tile2MArgs<FT, NIN> a;
+    a.bulk_ok = 1;
+    for (int c = 0; c < NIN; ++c)
+        if (!cmh::aligned16(in[c])) a.bulk_ok = 0;
     a.k = k;
+    a.tab = tab;
     a.n = n;
     bool all_out = true;
     for (int c = 0; c < NIN; ++c) a.in[c] = in[c];
     for (int c = 0; c < 4; ++c) { a.out[c] = out[c]; all_out = all_out && out[c] != nullptr; }
-    auto kern = all_out ? warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, true, PPT> : warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, false, PPT>;
-    static bool carveout_set[2] = {false, false};
-    if (!carveout_set[all_out]) {
+    constexpr bool kCanTab = LIM == 1;
+    const bool use_tab = kCanTab && tab != nullptr;
+    void (*kern)(Tile2MArgs<FT, NIN>);
+    if (use_tab) kern = all_out ? warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, true, PPT, kCanTab> : warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, false, PPT, kCanTab>;
+    else kern = all_out ? warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, true, PPT, false> : warm2m_tile_kernel<FT, NIN, LIM, BLOCK, MINB, false, PPT, false>;
+    static bool carveout_set[4] = {false, false, false, false};
+    const int slot = (use_tab ? 2 : 0) + (all_out ? 1 : 0);
+    if (!carveout_set[slot]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set[all_out] = true;
+        carveout_set[slot] = true;
     }
 #ifdef CUMICRO_TUNING
     { const char* wv0 = getenv("CUMICRO_WAVES"); if (wv0) waves = atoi(wv0); }

@@ -15,6 +15,57 @@
 #include "cm_sb2006_fast.cuh"
 #include "cm_tile2m.cuh"
 
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace cmh {
+// Ventilation tables: one per (device, parameter-block content), built and verified on the host, uploaded once.
+namespace {
+struct TabEntry {
+    int device;
+    cumicro_params_2m_warm_f64 key;
+    double eps_n, tab_inv_h, tab_u0;
+    double* dev;      // nullptr: verification failed for this block (closed form is used)
+};
+std::mutex g_tab_mutex;
+std::vector<TabEntry> g_tabs;
+}  // namespace
+
+const double* w2_table(const cumicro_params_2m_warm_f64& p, cm::W2K& k) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    for (const TabEntry& e : g_tabs)
+        if (e.device == device && e.eps_n == k.eps_n && std::memcmp(&e.key, &p, sizeof(p)) == 0) {
+            k.tab_inv_h = e.tab_inv_h; k.tab_u0 = e.tab_u0;
+            return e.dev;
+        }
+    std::vector<double> host(cm::kTabDoubles);
+    TabEntry e{};
+    e.device = device; std::memcpy(&e.key, &p, sizeof(p)); e.eps_n = k.eps_n; e.dev = nullptr;
+    const double err = cm::build_w2_table(p, k, host.data());
+    e.tab_inv_h = k.tab_inv_h; e.tab_u0 = k.tab_u0;
+    if (err < 1e-15) {
+        double* d = nullptr;
+        // not cached on failure (e.g. a stream capture in progress forbids the allocation): the next call tries again
+        if (cudaMalloc(&d, sizeof(double) * cm::kTabDoubles) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaMemcpy(d, host.data(), sizeof(double) * cm::kTabDoubles, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(d); return nullptr;
+        }
+        e.dev = d;
+    }
+    g_tabs.push_back(e);
+    return e.dev;
+}
+void release_tables() {
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    for (TabEntry& e : g_tabs)
+        if (e.dev) cudaFree(e.dev);
+    g_tabs.clear();
+}
+}  // namespace cmh
+
 namespace {
 
 using namespace cm;
@@ -55,6 +106,11 @@ template <class FT, class F> F make_2m_fast(const typename P<FT>::params_2m_warm
     widen(*p, w);
     f.k = make_w2k(w, is_f32<FT>());
     return f;
+}
+template <class FT> const double* w2_table_for(const typename P<FT>::params_2m_warm* p, W2K& k) {
+    P<D>::params_2m_warm w;
+    widen(*p, w);
+    return cmh::w2_table(w, k);
 }
 template <class FT> bool fast_ok(const typename P<FT>::params_2m_warm* p) {
     P<D>::params_2m_warm w;
@@ -112,12 +168,10 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
     if (q_ice != nullptr) {
         const FT* in8[8] = {rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice};
         if (fast) {
-            const W2K k = make_2m_fast<FT, Warm2MFast<8, 1>>(p).k;
-            const int rc = lim ? launch_warm2m_tile<FT, 8, 1>(k, n, in8, out, s, w) : launch_warm2m_tile<FT, 8, 0>(k, n, in8, out, s, w);
-            if (rc != -1) return rc;
+            W2K k = make_2m_fast<FT, Warm2MFast<8, 1>>(p).k;
+            const double* tab = lim ? w2_table_for<FT>(p, k) : nullptr;
+            return lim ? launch_warm2m_tile<FT, 8, 1>(k, tab, n, in8, out, s, w) : launch_warm2m_tile<FT, 8, 0>(k, nullptr, n, in8, out, s, w);
         }
-        if (fast && lim) return launch_pointwise<FT, 8, 4, Warm2MFast<8, 1>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<8, 1>>(p), n, in8, out, s, w);
-        if (fast) return launch_pointwise<FT, 8, 4, Warm2MFast<8, 0>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<8, 0>>(p), n, in8, out, s, w);
         return launch_pointwise<FT, 8, 4, Warm2MFused<8>, 128, 8, false>(make_2m<FT, Warm2MFused<8>>(p), n, in8, out, s, w);
     }
 #ifdef CUMICRO_TUNING
@@ -126,31 +180,19 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
         const int v = ev ? atoi(ev) : 0;
         using F1 = Warm2MFast<7, 1>;
         const F1 f1 = make_2m_fast<FT, F1>(p);
+        W2K kv = f1.k;
+        const char* nt = getenv("CUMICRO_NO_TABLE");
+        const double* tabv = (nt && nt[0] == '1') ? nullptr : w2_table_for<FT>(p, kv);
         switch (v) {
-            case 1: return launch_pointwise<FT, 7, 4, F1, 128, 8, false, true>(f1, n, in, out, s, w);
-            case 2: return launch_pointwise<FT, 7, 4, F1, 128, 6, false, true>(f1, n, in, out, s, w);
-            case 3: return launch_pointwise<FT, 7, 4, F1, 128, 5, false, true>(f1, n, in, out, s, w);
-            case 4: return launch_pointwise<FT, 7, 4, F1, 256, 3, false, true>(f1, n, in, out, s, w);
-            case 5: return launch_pointwise<FT, 7, 4, F1, 256, 4, false, true>(f1, n, in, out, s, w);
-            case 6: return launch_pointwise<FT, 7, 4, F1, 64, 14, false, true>(f1, n, in, out, s, w);
-            case 7: return launch_pointwise<FT, 7, 4, F1, 128, 8, false, false>(f1, n, in, out, s, w);   // plain loads, 1 point / thread
-            case 8: return launch_pointwise<FT, 7, 4, F1, 128, 7, false, false>(f1, n, in, out, s, w);
-            case 9: return launch_pointwise<FT, 7, 4, F1, 128, 4, true, false>(f1, n, in, out, s, w);    // 128-bit, 2 points / thread
-            case 10: return launch_pointwise<FT, 7, 4, F1, 128, 3, true, false>(f1, n, in, out, s, w);
-            case 11: return launch_pointwise<FT, 7, 4, F1, 256, 2, true, false>(f1, n, in, out, s, w);
-            case 12: return launch_pointwise<FT, 7, 4, F1, 128, 5, true, false>(f1, n, in, out, s, w);
             case 13: return launch_pointwise<FT, 7, 4, Warm2MFused<7, 1>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7, 1>>(p), n, in, out, s, w);  // round-1 kernel
             case 14: return launch_pointwise<FT, 7, 4, F1, 128, 7, false, true>(f1, n, in, out, s, w);   // fast body, cp.async shape
-            case 20: return launch_warm2m_tile<FT, 7, 1, 128, 7, 1>(f1.k, n, in, out, s, w);
-            case 21: return launch_warm2m_tile<FT, 7, 1, 128, 8, 1>(f1.k, n, in, out, s, w);
-            case 22: return launch_warm2m_tile<FT, 7, 1, 128, 6, 1>(f1.k, n, in, out, s, w);
-            case 23: return launch_warm2m_tile<FT, 7, 1, 256, 3, 1>(f1.k, n, in, out, s, w);
-            case 24: return launch_warm2m_tile<FT, 7, 1, 128, 5, 1>(f1.k, n, in, out, s, w);
-            case 30: return launch_warm2m_tile<FT, 7, 1, 128, 4, 2>(f1.k, n, in, out, s, w);
-            case 31: return launch_warm2m_tile<FT, 7, 1, 128, 3, 2>(f1.k, n, in, out, s, w);
-            case 32: return launch_warm2m_tile<FT, 7, 1, 64, 8, 2>(f1.k, n, in, out, s, w);
-            case 33: return launch_warm2m_tile<FT, 7, 1, 64, 7, 2>(f1.k, n, in, out, s, w);
-            case 34: return launch_warm2m_tile<FT, 7, 1, 128, 5, 2>(f1.k, n, in, out, s, w);
+            case 20: return launch_warm2m_tile<FT, 7, 1, 128, 7, 1>(kv, tabv, n, in, out, s, w);
+            case 21: return launch_warm2m_tile<FT, 7, 1, 128, 8, 1>(kv, tabv, n, in, out, s, w);
+            case 22: return launch_warm2m_tile<FT, 7, 1, 128, 6, 1>(kv, tabv, n, in, out, s, w);
+            case 23: return launch_warm2m_tile<FT, 7, 1, 256, 3, 1>(kv, tabv, n, in, out, s, w);
+            case 24: return launch_warm2m_tile<FT, 7, 1, 128, 5, 1>(kv, tabv, n, in, out, s, w);
+            case 25: return launch_warm2m_tile<FT, 7, 1, 64, 12, 1>(kv, tabv, n, in, out, s, w);
+            case 26: return launch_warm2m_tile<FT, 7, 1, 192, 4, 1>(kv, tabv, n, in, out, s, w);
             default: break;
         }
     }
@@ -158,12 +200,10 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
     // 128 x 7 blocks/SM: sweep in tools/tune_2m.py.  The default parameter STRUCTURE (exponents 3 / 4 / -5, any values) runs the
     // fast body (tile kernel, cm_tile2m.cuh; cp.async shape for columns that are not 16-byte aligned); anything else the generic one.
     if (fast) {
-        const W2K k = make_2m_fast<FT, Warm2MFast<7, 1>>(p).k;
-        const int rc = lim ? launch_warm2m_tile<FT, 7, 1>(k, n, in, out, s, w) : launch_warm2m_tile<FT, 7, 0>(k, n, in, out, s, w);
-        if (rc != -1) return rc;
+        W2K k = make_2m_fast<FT, Warm2MFast<7, 1>>(p).k;
+        const double* tab = lim ? w2_table_for<FT>(p, k) : nullptr;
+        return lim ? launch_warm2m_tile<FT, 7, 1>(k, tab, n, in, out, s, w) : launch_warm2m_tile<FT, 7, 0>(k, nullptr, n, in, out, s, w);
     }
-    if (fast && lim) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 1>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<7, 1>>(p), n, in, out, s, w);
-    if (fast) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 0>, 128, 7, false, true>(make_2m_fast<FT, Warm2MFast<7, 0>>(p), n, in, out, s, w);
     return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7>>(p), n, in, out, s, w);
 }
 
@@ -196,16 +236,13 @@ int bmt2m_warm_host_impl(const typename P<FT>::params_2m_warm* p, int64_t n, con
     const bool lim = p->sb.pdf_r.limited != 0;
     const Warm2MFused<7> f = make_2m<FT, Warm2MFused<7>>(p);
     const Warm2MFast<7, 1> f1 = make_2m_fast<FT, Warm2MFast<7, 1>>(p);
-    const Warm2MFast<7, 0> f0 = make_2m_fast<FT, Warm2MFast<7, 0>>(p);
+    W2K kt = f1.k;
+    const double* tab = (fast && lim) ? w2_table_for<FT>(p, kt) : nullptr;
     return host_pipeline<FT, 7, 4>(n, in, out, chunk,
                                    [&](int64_t m, const FT* const(&din)[7], FT* const(&dout)[4], cudaStream_t s) {
                                        const char* w = "bmt2m_warm (host pipeline) kernel launch";
-                                       if (fast) {
-                                           const int rc = lim ? launch_warm2m_tile<FT, 7, 1>(f1.k, m, din, dout, s, w) : launch_warm2m_tile<FT, 7, 0>(f1.k, m, din, dout, s, w);
-                                           if (rc != -1) return rc;
-                                       }
-                                       if (fast && lim) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 1>, 128, 7, false, true>(f1, m, din, dout, s, w);
-                                       if (fast) return launch_pointwise<FT, 7, 4, Warm2MFast<7, 0>, 128, 7, false, true>(f0, m, din, dout, s, w);
+                                       if (fast)
+                                           return lim ? launch_warm2m_tile<FT, 7, 1>(kt, tab, m, din, dout, s, w) : launch_warm2m_tile<FT, 7, 0>(kt, nullptr, m, din, dout, s, w);
                                        return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, m, din, dout, s, w);
                                    });
 }

@@ -17,6 +17,7 @@
 #include "cm_launch.cuh"
 #include "cm_sb2006.cuh"
 #include "cm_sb2006_fast.cuh"
+#include "cm_tile2m.cuh"
 
 namespace {
 
@@ -56,6 +57,7 @@ template <class FT> struct FusedArgs {
     const FT* in[NIN];
     FT* out[NOUT];
     double* partials;   // [gridDim.x][NDIAG]
+    const double* tab;  // ventilation table of the 2-moment block (cmh::w2_table) or nullptr
     int64_t n;
 };
 
@@ -63,8 +65,13 @@ template <class FT> struct FusedArgs {
 // copies, double-buffered: the next item streams in while this one is computed) and every family stores its tendencies and
 // accumulates its diagnostic as soon as it is done, so the live register set is that of ONE family at a time and the kernel
 // keeps the occupancy of the single-family kernels.
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC>
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
+    __shared__ __align__(16) double tab_s[TAB ? kTabDoubles : 2];
+    if (TAB) {
+        for (int i = threadIdx.x; i < kTabDoubles / 2; i += BLOCK)
+            reinterpret_cast<double2*>(tab_s)[i] = __ldg(reinterpret_cast<const double2*>(a.tab) + i);
+    }
     math_tables_init<BLOCK>();
     if constexpr (SPEC >= 0) math_tables_init_log2<BLOCK>();
     extern __shared__ __align__(16) unsigned char fused_dyn_smem[];
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
             const double q_ice = clamp0_(in(6)) + clamp0_(in(8));
             if constexpr (SPEC >= 0) {   // default SB2006 block structure: the headline body (cm_sb2006_fast.cuh), bit-identical to cumicro_bmt2m_warm_*
                 double y[4];
-                warm2m_fast<SPEC>(f.w2k, in(0), in(1), in(4), in(5), in(9), in(7), in(10), q_ice, true, y);
+                warm2m_fast<SPEC, TAB>(f.w2k, in(0), in(1), in(4), in(5), in(9), in(7), in(10), q_ice, true, y, tab_s);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) put(4 + k, y[k]);
                 diag[1] += in(0) * y[2];        // 2M rain production           Σ ρ dq_rai
@@ -202,16 +209,16 @@ template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
-    // the block partials of THIS call: stream-ordered allocation (a cached per-thread buffer would be shared by calls in flight on
-    // different streams, and growing it would free memory a running kernel still writes)
+    // the block partials: scratch of this (device, stream) — calls in flight on different streams never share it, and work on ONE
+    // stream is ordered (the finish kernel of call k has read the partials before the main kernel of call k + 1 writes them)
     void* ws = nullptr;
-    int st = cmh::cuda_status(cudaMallocAsync(&ws, sizeof(double) * NDIAG * (size_t)blocks + 64, s), "fused: cudaMallocAsync (diagnostic partials)");
+    int st = cmh::stream_workspace(s, sizeof(double) * NDIAG * (size_t)blocks + 64, &ws);
     if (st) return st;
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
-    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC>;
+    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB>;
     static bool attr_set = false;   // per instantiation; the attribute is per function and device-wide idempotent
     if (!attr_set || smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -224,7 +231,7 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC> int launch_fused(F
         fused_diag_finish<<<1, 256, 0, s>>>(a.partials, blocks, diag);
         cmh::count_launch();
     }
-    return cmh::cuda_status(cudaFreeAsync(ws, s), "fused: cudaFreeAsync");
+    return CUMICRO_OK;
 }
 
 template <class FT>
@@ -256,8 +263,10 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     bool small_blocks = false;
     if (const char* e = std::getenv("CUMICRO_FUSED_SHAPE")) small_blocks = std::string(e).rfind("128", 0) == 0;
     const int spec = w2k_supported(a.f.p2) ? (a.f.p2.sb.pdf_r.limited ? 1 : 0) : -1;
+    a.tab = (spec == 1) ? cmh::w2_table(a.f.p2, a.f.w2k) : nullptr;
     int st;
     if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
+    else if (spec == 1 && a.tab) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true>(a, n, s, diag);
     else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag);
     else if (spec == 0) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 0>(a, n, s, diag);
     else st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, -1>(a, n, s, diag);

@@ -43,10 +43,11 @@ def all_reduce_diagnostics(diag: torch.Tensor, group=None, async_op=False):
 
 
 def fused_1m2m_icenuc(mp1, mp2, tps, icenuc_block, rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai, *,
-                      out=None, diagnostics=True, reduce_group=None):
+                      out=None, diagnostics=True, reduce_group=None, reduce=True):
     """One fused kernel over this rank's slab.  Returns a ``Tendencies`` of the 11 output columns
     plus ``diag`` (Float64 device tensor of NDIAG sums, all-reduced over ``torch.distributed``
-    ranks when a process group is initialised)."""
+    ranks when a process group is initialised; ``reduce=False`` leaves the slab's own sums, e.g. for a
+    host that reduces through ``cumicro_nccl_allreduce_f64`` with its own communicator)."""
     cols = [rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai]
     suf, n, dev = check_columns(cols, list(IN_NAMES))
     b1, b2 = CMP.pack_1m(mp1, tps), CMP.pack_2m_warm(mp2, tps)
@@ -59,7 +60,7 @@ def fused_1m2m_icenuc(mp1, mp2, tps, icenuc_block, rho, T, p, w, q_tot, q_lcl, q
         st = fn(C.byref(b1), C.byref(b2), C.byref(icenuc_block), C.c_int64(n), ptr_table(cols), ptr_table(outs),
                 C.c_void_p(diag.data_ptr()) if diag is not None else None, stream_handle(dev))
     _abi.check(st, "cumicro_fused_1m2m_icenuc")
-    if diag is not None:
+    if diag is not None and reduce:
         all_reduce_diagnostics(diag, reduce_group)
     res = Tendencies(zip(OUT_NAMES, outs))
     res["diag"] = diag

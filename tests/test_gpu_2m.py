@@ -329,8 +329,8 @@ def test_full_size_properties_2pow24(built, cuda):
     for got, want, mag in ((a["dq_lcl_dt"][:m], dq_l, mag_l), (a["dq_rai_dt"][:m], dq_r, mag_r)):
         d = (got - want).abs()
         assert float((d <= 1e-12 * mag).double().mean()) > 0.995 and bool((d <= 1e-9 * mag).all())
-    dn_r = (L["evap_dn_rai"] + L["acnv_dn_rai"] + L["rai_selfcol"] + L["rai_breakup"]) / rho + L["numadj_rai"]
-    mag_n = (L["evap_dn_rai"].abs() + L["acnv_dn_rai"].abs() + L["rai_selfcol"].abs() + L["rai_breakup"].abs()) / rho + L["numadj_rai"].abs()
+    dn_r = (L["evap_dN_rai"] + L["acnv_dN_rai"] + L["rai_selfcol"] + L["rai_breakup"]) / rho + L["numadj_rai"]
+    mag_n = (L["evap_dN_rai"].abs() + L["acnv_dN_rai"].abs() + L["rai_selfcol"].abs() + L["rai_breakup"].abs()) / rho + L["numadj_rai"].abs()
     d = (dn_r - a["dn_rai_dt"][:m]).abs()
     assert float((d <= 1e-12 * mag_n).double().mean()) > 0.995 and bool((d <= 1e-9 * mag_n).all())
     # regime selection agrees between the two bodies: gated-off (exactly zero) points coincide
