@@ -202,19 +202,25 @@ def _link_rates(torch, dev, barrier, mb=256, reps=4):
         e1.record()
         torch.cuda.synchronize()
         out[name] = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
-    # both directions at once (what the chunked pipeline does)
+    # both directions at once (what the chunked pipeline does): each direction timed on its own stream
     h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     d2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    s2 = torch.cuda.Stream(device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        d.copy_(h, non_blocking=True)
-        with torch.cuda.stream(s2):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.cuda.stream(s1):
+        ev[0].record()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        ev[1].record()
+    with torch.cuda.stream(s2):
+        ev[2].record()
+        for _ in range(reps):
             h2.copy_(d2, non_blocking=True)
+        ev[3].record()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["h2d_while_d2h"] = nbytes * reps / dt / 1e9
+    out["h2d_while_d2h"] = nbytes * reps / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
+    out["d2h_while_h2d"] = nbytes * reps / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9
     return out
 
 
@@ -377,6 +383,24 @@ def main():
     value = n * world * args.steps / (total_ms_max * 1e-3)
     kernel_ms = float(np.mean(per_launch_ms))
 
+    # ---- FP64 pipe peak measured in place (same power / clock state as the leg it is compared with) -------------
+    def fp64_probe():
+        scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+        flops = C.c_double(0)
+        best = None
+        for it in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = lib.cumicro_probe_fp64_fma(C.c_int64(1 << 15), 8, C.c_void_p(scratch.data_ptr()), C.byref(flops),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            e1.record()
+            torch.cuda.synchronize()
+            if rc == 0:
+                best = max(best or 0.0, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+
+    fp64_peak = fp64_probe()
+
     # ---- sustained leg: the same step for >= 1 s (clock under load, not a burst) -----------------------
     n_sus = max(args.steps, int(args.sustained_s * 1e3 / max(kernel_ms, 1e-3)) + 1)
     with ClockSampler(local) as clocks_sus:
@@ -389,21 +413,8 @@ def main():
         barrier()
     sus_ms = max_over_ranks(e0.elapsed_time(e1))
     sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
-                 "value": n * world * n_sus / (sus_ms * 1e-3), "unit": UNIT, "clocks": clocks_sus.summary()}
-
-    # ---- FP64 pipe peak measured in place --------------------------------------------------
-    scratch = torch.zeros(8, dtype=torch.float64, device=dev)
-    flops = C.c_double(0)
-    fp64_peak = None
-    for it in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = lib.cumicro_probe_fp64_fma(C.c_int64(1 << 15), 8, C.c_void_p(scratch.data_ptr()), C.byref(flops),
-                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        e1.record()
-        torch.cuda.synchronize()
-        if rc == 0:
-            fp64_peak = max(fp64_peak or 0.0, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+                 "value": n * world * n_sus / (sus_ms * 1e-3), "unit": UNIT, "clocks": clocks_sus.summary(),
+                 "fp64_probe_tflops": fp64_probe()}
 
     # ---- e2e: host buffers in, host buffers out, through the C-ABI host entry point --------
     link = _link_rates(torch, dev, barrier)
@@ -418,7 +429,7 @@ def main():
     e2e_value = n * world * args.e2e_steps / e2e_s
     h2d_bytes, d2h_bytes = 7 * 8 * n, 4 * 8 * n
     # the longer of the two copy legs at this rank's measured link rate (both directions busy) bounds the step
-    link_bound_s = max(h2d_bytes / (link["h2d_while_d2h"] * 1e9), d2h_bytes / (link["d2h"] * 1e9))
+    link_bound_s = max(h2d_bytes / (link["h2d_while_d2h"] * 1e9), d2h_bytes / (link["d2h_while_h2d"] * 1e9))
     link_all = None
     if dist is not None:
         g = [None] * world

@@ -58,7 +58,14 @@ def zero_column(like: torch.Tensor):
     """A length-n all-zero column that occupies one element of HBM (stride 0): the
     reference returns literal zeros for these fields (BMT:840-853); materialising
     them would add 32 B/point of dead traffic."""
-    return torch.zeros(1, dtype=like.dtype, device=like.device).expand(like.shape[0])
+    key = (like.device, like.dtype)
+    z = _ZERO.get(key)
+    if z is None:   # one element per (device, dtype) for the life of the process: no fill kernel per call
+        z = _ZERO[key] = torch.zeros(1, dtype=like.dtype, device=like.device)
+    return z.expand(like.shape[0])
+
+
+_ZERO = {}
 
 
 class Tendencies(dict):

@@ -21,36 +21,33 @@
 namespace cm {
 
 // Host-derived constants of one launch (doubles; the functor computes in Float64 for both method types).
-struct W2K {
-    double eps, eps_n;        // eps(FT), cbrt(floatmin(FT)) of the METHOD's float type
+struct W2K {   // (fields in the order the body reads them: neighbours share one 128-bit constant-bank load)
     int eps_hi, _pad;         // high word of eps (low word is zero: eps is a power of two)
+    double eps, eps_n;        // eps(FT), cbrt(floatmin(FT)) of the METHOD's float type
     // thermodynamics (cm_thermo.cuh)
-    double inv_T_triple, T_triple, a_liq, b_liq, press_triple, R_v, inv_R_v;
-    double dcp_vl, Lv0;       // Lv = dcp_vl T + Lv0
-    double cp_d, dcp_vd, dcp_lv, dcp_iv;
-    double tau_cond;
+    double inv_T_triple, T_triple, a_liq, b_liq, press_triple, dcp_vl, Lv0, R_v, inv_R_v;   // Lv = dcp_vl T + Lv0
+    double dcp_lv, dcp_vd, cp_d, dcp_iv, tau_cond;
+    // rain PSD: logs of the limiter bounds; log(pi rho_w)/3, /4; 1/3, -1/3 (full precision)
+    double lxmin, lxmax, nthird, c3, lN0min, lN0max, c4, llmin, llmax, third;
+    double cDr, rho0;         // Dr = cDr xr^(1/3); sqrt(rho0/rho)
     double inv_K, RvD;        // 1/max(K_therm, eps_n), R_v/max(D_vapor, eps_n)
-    // rain PSD
-    double lxmin, lxmax, lN0min, lN0max, llmin, llmax, c3, c4;   // logs of the limiter bounds; log(pi rho_w)/3, /4
-    double third, nthird;     // 1/3, -1/3 (full precision)
-    double pi_rho_w, rho0;    // not-limited variant / sqrt(rho0/rho)
-    // evaporation
+    // ventilation table (limited PSD; see W2Tab): u = tab_inv_h lx + tab_u0 is the interval coordinate of log xr_mean
+    double tab_inv_h, tab_u0;
+    double kvx, cvx, av1_Dr;  // 2 pi b_vent_1 cbrt(Sc) Dr sqrt(N_Re) / r4 = exp(kvx lx + cvx), kvx = kv + 1/3; av1 cDr
+    // autoconversion / accretion / self-collection / breakup
+    double x_star, acnv_a, acnv_A, acnv_pref, inv_x_star, lclsc_pref;
+    double tau0, kcr;         // kcr sqrt(accr.rho0 / pdf_r.rho0)
+    double krc, nkrr;         // kappa_rr cbrt(1/6), -krr
+    double Deq, kappa_br, Dr_th, kbr;
+    double inv_xc_max, inv_xc_min, inv_xr_max, inv_xr_min, inv_tau_adj;
+    // closed-form evaporation (no table / not-limited PSD)
     double lt0, ct;           // log t* = lt0 - lx/3,  t* = ct xr^(-1/3)
     double ne1[2], de[2], c1[2], c2[2];   // Γ_incl(a_k, t) = exp(-t + ne1 log t) / (c1 + c2 t^de), c1, c2 pre-divided (see make_w2k)
     double kv, cv;            // sqrt(N_Re) = exp(kv lx + cv) (rho0/rho)^(1/4)
     double av1, bv1;          // 2 pi a_vent_1, 2 pi b_vent_1 cbrt(Sc)
-    double cDr;               // Dr = cDr xr^(1/3)
-    double inv_xr_min, inv_xr_max, inv_xc_min, inv_xc_max, inv_tau_adj;
-    // autoconversion / accretion / self-collection / breakup
-    double x_star, inv_x_star, acnv_pref, acnv_a, acnv_A, lclsc_pref;
-    double tau0, kcr;         // kcr sqrt(accr.rho0 / pdf_r.rho0)
-    double krc, nkrr;         // kappa_rr cbrt(1/6), -krr
-    double Deq, Dr_th, kbr, kappa_br;
-    // ventilation table (limited PSD; see W2Tab): u = tab_inv_h lx + tab_u0 is the interval coordinate of log xr_mean
-    double tab_inv_h, tab_u0;
-    double av1_Dr, cvx;       // av1 cDr (2 pi a_vent_1 Dr / cx);  cvx = cv + log(bv1 cDr): 2 pi b_vent_1 cbrt(Sc) Dr sqrt(N_Re) / r4 = exp((kv + 1/3) lx + cvx)
-    double kvx;               // kv + 1/3
+    double pi_rho_w;
 };
+
 
 // ---- ventilation table ------------------------------------------------------------------------------------------------------
 // Under the limited PSD log xr_mean lives in [log xr_min, log xr_max], and the number-tendency side of CM2.rain_evaporation depends

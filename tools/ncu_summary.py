@@ -35,6 +35,10 @@ KEYS = [
     ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall: branch resolving"),
     ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall: no instruction"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/smem data pipe % of peak"),
+    ("idc__request_cycles_active.avg.pct_of_peak_sustained_elapsed", "constant cache (IDC) % of peak"),
+    ("sm__inst_executed_pipe_uniform_realtime.avg.pct_of_peak_sustained_elapsed", "uniform pipe %"),
 ]
 
 

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """SASS evidence for profiles/: per-kernel opcode histogram (static) of the hot kernels of libcumicro.so plus the full
-listing of the headline 2M kernel.  Run after a build:  python tools/sass_summary.py  ->  profiles/r01_sass_*.txt"""
+listing of the headline 2M kernel (the SHIPPED instantiation: the regexes name it exactly).  Run after a build:
+    python tools/sass_summary.py [round-tag]  ->  profiles/<tag>_sass_*.txt"""
 import collections
 import os
 import re
@@ -10,11 +11,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build")
 KERNELS = [  # (object, regex on the mangled name, label)
-    ("kernels_2m.o", r"pointwise_kernel_pipelinedIdLi7ELi4E.*Warm2MFused", "2m_warm_f64"),
+    # the launch bmt2m_warm_impl makes for a default-structure limited-PSD block with all four outputs: BLOCK 128, MINB 6, ALL_OUT, PPT 1, TAB
+    ("kernels_2m.o", r"warm2m_tile_kernelIdLi7ELi1ELi128ELi6ELb1ELi1ELb1E", "2m_warm_f64"),
+    ("kernels_2m.o", r"warm2m_tile_kernelIfLi7ELi1ELi128ELi6ELb1ELi1ELb1E", "2m_warm_f32"),
     ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMInstELb0", "1m_inst_f64"),
     ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMLinAvgELb0", "1m_linavg_f64"),
     ("kernels_icenuc.o", r"pointwise_kernelIfLi8ELi11E.*ArgIceNucILi3ELb0EEELb0", "arg_icenuc_f32"),
-    ("kernels_fused.o", r"fused_kernelIdLi768ELi1ELb0", "fused_f64"),
+    ("kernels_fused.o", r"fused_kernelIdLi896ELi1ELb0ELi1ELb1E", "fused_f64"),
     ("kernels_p3.o", r"p3_tile_kernelIdLi0", "p3_rates_f64"),
 ]
 FP64 = ("DFMA", "DMUL", "DADD")
@@ -43,6 +46,7 @@ def opcodes(lines):
 
 
 def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     summary = ["static SASS opcode counts of the hot kernels (sm_100a, nvcc 12.9, -fmad=false); dynamic counts are in the ncu summaries",
                "tensor-core / TMA mnemonics (UTCMMA, UTMALDG, ...) are absent by design: nothing on this path is a contraction", ""]
     cache = {}
@@ -52,6 +56,7 @@ def main():
         if not names:
             summary.append(f"{label}: kernel not found ({pat})")
             continue
+        assert len(names) == 1, (label, names)   # exactly the shipped instantiation, never "the first match"
         lines = fns[names[0]]
         h = opcodes(lines)
         total = sum(h.values())
@@ -63,8 +68,8 @@ def main():
         summary.append(f"    {names[0][:150]}")
         if label == "2m_warm_f64":
             listing = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l) for l in lines if not re.match(r"^\s*/\* 0x[0-9a-f]+ \*/\s*$", l)]
-            open(os.path.join(ROOT, "profiles", "r01_sass_2m_warm_f64.txt"), "w").write("\n".join(listing) + "\n")
-    open(os.path.join(ROOT, "profiles", "r01_sass_summary.txt"), "w").write("\n".join(summary) + "\n")
+            open(os.path.join(ROOT, "profiles", f"{tag}_sass_2m_warm_f64.txt"), "w").write("\n".join(listing) + "\n")
+    open(os.path.join(ROOT, "profiles", f"{tag}_sass_summary.txt"), "w").write("\n".join(summary) + "\n")
     print("\n".join(summary))
 
 
