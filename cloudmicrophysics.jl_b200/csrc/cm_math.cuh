@@ -103,13 +103,16 @@ static __constant__ double cm_kc[8] = {3.3333333333333331e-01, 0.2, CM_LOG_LN2_L
 #endif
 #define CM_LOG_C3_HOST 3.3333333333333331e-01
 
-template <int BLOCK> CM_DEV void math_tables_init() {
+// WITH_LOG = false: a kernel that never calls logp_ (the 2M tile kernel uses log_abs_) leaves the 2 KB logp_ table out
+template <int BLOCK, bool WITH_LOG = true> CM_DEV void math_tables_init() {
 #ifdef __CUDA_ARCH__
 #pragma unroll
     for (int i = threadIdx.x; i < 256; i += BLOCK) cm_sh_exp[i] = cm_exp_tab_dev[i];
+    if (WITH_LOG) {
 #pragma unroll
-    for (int i = threadIdx.x; i < 128; i += BLOCK)
-        cm_sh_log[i] = make_ulonglong2(cm_log_tab_dev[2 * i], cm_log_tab_dev[2 * i + 1]);
+        for (int i = threadIdx.x; i < 128; i += BLOCK)
+            cm_sh_log[i] = make_ulonglong2(cm_log_tab_dev[2 * i], cm_log_tab_dev[2 * i + 1]);
+    }
     __syncthreads();
 #endif
 }

@@ -332,9 +332,7 @@ CM_HD void warm2m_fast(const W2K& k, double rho, double T, double q_tot, double 
         const double sN_lcl = Nl_off ? k.eps : N_lcl;
         const double L_lcl = rho * sq_lcl;
         const double LL = L_lcl * L_lcl;
-        const double rLN = rcp_(L_lcl * sN_lcl);
-        const double xl = LL * rLN;                 // L_lcl / N_lcl
-        const double inv_xl = (sN_lcl * sN_lcl) * rLN;
+        const double xl = L_lcl * rcp_(sN_lcl);     // L_lcl / N_lcl
         const double xlc = (xl < k.x_star) ? xl : k.x_star;
         const double s = sq_lcl + q_rai;
         const double tau = 1.0 - divr_(sq_lcl, s, rcp_cr_(s));      // SB2006 Eq. (5), the IEEE quotient
@@ -352,9 +350,10 @@ CM_HD void warm2m_fast(const W2K& k, double rho, double T, double q_tot, double 
         const double sc_l = ql_off ? 0.0 : (-(k.lclsc_pref * inv_rho) * LL - dNl_au);    // CM2:488-501 (q_lcl >= eps: rho q_lcl = L_lcl)
         const double pa = tau * rcp_(tau + k.tau0);
         const double pa2 = pa * pa;
-        const double dLr = (off || qr_off) ? 0.0 : k.kcr * L_lcl * Lsq * (pa2 * pa2);        // Eq. (7), (8)
-        dq_ac = dLr * inv_rho;
-        const double dNl_ac = -dLr * inv_xl;
+        // dL_rai = kcr L_lcl L_rai phi sqrt(rho0/rho) (Eq. 7, 8);  dN_lcl = -dL_rai / x_lcl = -(kcr L_rai phi sqrt(rho0/rho)) N_lcl   CM2:462-466
+        const double acc = (off || qr_off) ? 0.0 : k.kcr * Lsq * (pa2 * pa2);
+        dq_ac = acc * L_lcl * inv_rho;
+        const double dNl_ac = -acc * sN_lcl;
         dNl_sum = (dNl_au + sc_l) + dNl_ac;
     }
 

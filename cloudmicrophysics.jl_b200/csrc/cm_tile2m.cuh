@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) warm2m_tile_kernel(const __grid_c
         for (int i = threadIdx.x; i < kTabDoubles / 2; i += BLOCK)
             reinterpret_cast<double2*>(tab_s)[i] = __ldg(reinterpret_cast<const double2*>(a.tab) + i);
     }
-    math_tables_init<BLOCK>();
+    math_tables_init<BLOCK, false>();
     math_tables_init_log2<BLOCK>();
     const int tid = threadIdx.x;
     const unsigned n_tiles = (unsigned)((a.n + TILE - 1) / TILE);
