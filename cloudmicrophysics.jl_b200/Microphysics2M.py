@@ -33,6 +33,34 @@ def sb2006_process_rates(mp, tps, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, whi
     return Tendencies({nm: o for nm, o in zip(names, outs) if o is not None})
 
 
+def _rain_evaporation(mp, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T, want):
+    cols = [q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T]
+    suf, n, dev = check_columns(cols, ["q_tot", "q_lcl", "q_icl", "q_rai", "q_sno", "rho", "N_rai", "T"])
+    block = CMP.pack_2m_warm(mp, tps)
+    outs = [torch.empty_like(rho) if w else None for w in want]
+    fn = getattr(_abi.load(), f"cumicro_rain_evaporation_2m_{suf}")
+    with torch.cuda.device(dev):
+        st = fn(C.byref(block), C.c_int64(n), ptr_table(cols), ptr_table(outs), stream_handle(dev))
+    _abi.check(st, "cumicro_rain_evaporation_2m")
+    return outs
+
+
+def rain_evaporation(mp, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T):
+    """CM2.rain_evaporation(sb, aps, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, ρ, N_rai, T) (CM2:780-828); ``mp`` carries ``sb``
+    and ``aps`` (mp.warm_rain).  Returns (∂ₜρn_rai, ∂ₜq_rai) columns."""
+    o = _rain_evaporation(mp, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T, (1, 1, 0, 0))
+    return Tendencies(dNrho_dt=o[0], dq_dt=o[1])
+
+
+def d_rain_evaporation_dN_rai_dq_rai(mp, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T):
+    """CM2.∂rain_evaporation_∂N_rai_∂q_rai (CM2:844-853): the leading-order derivatives ∂ₜρn_rai / N_rai and ∂ₜq_rai / q_rai."""
+    o = _rain_evaporation(mp, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T, (0, 0, 1, 1))
+    return Tendencies(dN_rai=o[2], dq_rai=o[3])
+
+
+globals()["∂rain_evaporation_∂N_rai_∂q_rai"] = d_rain_evaporation_dN_rai_dq_rai   # the reference's own name
+
+
 def _termvel(fname, pdf, vel, q, rho, N):
     suf, n, dev = check_columns([q, rho, N], ["q", "rho", "N"])
     vt0, vt1 = torch.empty_like(q), torch.empty_like(q)

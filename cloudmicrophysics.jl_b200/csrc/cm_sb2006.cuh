@@ -149,7 +149,7 @@ template <class FT> struct Warm2M {
 template <class FT, int SPEC = -1>
 CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& p, const ThermoK<FT>& tk,
                                           const SB2006K<FT>& sk, FT rho, FT T, FT q_tot, FT q_lcl, FT n_lcl,
-                                          FT q_rai, FT n_rai, FT q_ice) {
+                                          FT q_rai, FT n_rai, FT q_ice, FT N_rai_given = FT(-1)) {
     const FT e = tk.eps;
     const auto& sb = p.sb;
     Warm2M<FT> o;
@@ -162,7 +162,8 @@ CM_DEV Warm2M<FT> warm_rain_tendencies_2m(const typename P<FT>::params_2m_warm& 
     n_lcl = clamp0_(n_lcl);
     n_rai = clamp0_(n_rai);
     const FT N_lcl = rho * n_lcl;   // BMT:718-719
-    const FT N_rai = rho * n_rai;
+    // (the stand-alone leaf CM2.rain_evaporation takes the number density N_rai itself: N_rai_given >= 0)
+    const FT N_rai = (N_rai_given >= FT(0)) ? N_rai_given : rho * n_rai;
     const FT inv_rho = rcp_(rho);
 
     // ---- thermodynamic state shared by cond/evap and rain evaporation

@@ -131,6 +131,24 @@ struct Warm2MLeaves {
 };
 
 // (p wide, tk, sk) of one call: Float32 blocks are widened exactly, thresholds follow FT.
+// CM2.rain_evaporation(sb, aps, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T) (CM2:780-828) and
+// CM2.∂rain_evaporation_∂N_rai_∂q_rai (CM2:844-853): columns q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T -> 4 columns
+struct RainEvap2M {
+    P<D>::params_2m_warm p;
+    ThermoK<D> tk;
+    SB2006K<D> sk;
+    __device__ __forceinline__ void operator()(const D (&x)[8], D (&y)[4]) const {
+        const D q_tot = x[0], q_lcl = x[1], q_icl = x[2], q_rai = x[3], q_sno = x[4], rho = x[5], N_rai = x[6], T = x[7];
+        // q_liq = q_lcl + q_rai, q_ice = q_icl + q_sno (CM2:784); negative inputs are clamped to 0 as in the BMT caller (BMT:827-836)
+        const Warm2M<D> o = warm_rain_tendencies_2m<D>(p, tk, sk, rho, T, q_tot, q_lcl, D(0), q_rai, D(0), q_icl + q_sno, fmax_(N_rai, D(0)));
+        const D dn = o.leaf[CUMICRO_SB_EVAP_DN_RAI], dq = o.leaf[CUMICRO_SB_EVAP_DQ_RAI];
+        y[0] = dn;
+        y[1] = dq;
+        y[2] = (N_rai > tk.eps) ? div_(dn, N_rai) : D(0);     // ∂(∂ₜρn_rai/ρ)/∂N_rai ≈ ∂ₜρn_rai / N_rai
+        y[3] = (q_rai > tk.eps) ? div_(dq, q_rai) : D(0);     // ∂(∂ₜq_rai)/∂q_rai ≈ ∂ₜq_rai / q_rai
+    }
+};
+
 template <class FT, class F> F make_2m(const typename P<FT>::params_2m_warm* p) {
     F f{};
     widen(*p, f.p);
@@ -245,6 +263,20 @@ int bmt2m_warm_host_impl(const typename P<FT>::params_2m_warm* p, int64_t n, con
                                            return lim ? launch_warm2m_tile<FT, 7, 1>(kt, tab, m, din, dout, s, w) : launch_warm2m_tile<FT, 7, 0>(kt, nullptr, m, din, dout, s, w);
                                        return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(f, m, din, dout, s, w);
                                    });
+}
+
+template <class FT>
+int rain_evaporation_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT* const* in8, FT* const* out4, void* stream) {
+    if (in8 == nullptr || out4 == nullptr) return cmh::fail(CUMICRO_E_NULL, "column pointer table is NULL");
+    const FT* in[8];
+    FT* out[4];
+    for (int c = 0; c < 8; ++c) in[c] = in8[c];
+    for (int c = 0; c < 4; ++c) out[c] = out4[c];
+    int st = validate_columns<FT, 8>(p, n, in);
+    if (st) return st;
+    if ((st = check_2m_options<FT>(p))) return st;
+    return launch_pointwise<FT, 8, 4, RainEvap2M, 128, 4, false>(make_2m<FT, RainEvap2M>(p), n, in, out, (cudaStream_t)stream,
+                                                                 "rain_evaporation_2m kernel launch");
 }
 
 // ---- terminal velocities: (q, rho, N) -> (vt0, vt1) ---------------------------------------
@@ -367,5 +399,12 @@ extern "C" {
 
 CUMICRO_DEF_2M(f64, double)
 CUMICRO_DEF_2M(f32, float)
+
+int cumicro_rain_evaporation_2m_f64(const cumicro_params_2m_warm_f64* p, int64_t n, const double* const* in8, double* const* out4, void* stream) {
+    return rain_evaporation_impl<double>(p, n, in8, out4, stream);
+}
+int cumicro_rain_evaporation_2m_f32(const cumicro_params_2m_warm_f32* p, int64_t n, const float* const* in8, float* const* out4, void* stream) {
+    return rain_evaporation_impl<float>(p, n, in8, out4, stream);
+}
 
 }  // extern "C"

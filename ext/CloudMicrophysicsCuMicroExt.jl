@@ -997,6 +997,31 @@ function leaf_call(mp, tps, ρ::Col{FT}, T, q_tot, q_lcl, N_lcl, q_rai, N_rai, w
     return map(k -> getproperty(r, k), wanted)
 end
 
+# ---- CM2.rain_evaporation and its leading-order derivatives over columns (CM2:780-853) ------------------
+function rain_evaporation_columns(sb::CMP.SB2006, aps::CMP.AirProperties, tps::TDI.PS, cols::NTuple{8, Col{FT}}) where {FT}
+    n = same_length(cols...)
+    out = ntuple(_ -> similar(cols[1]), 4)
+    # the entry point reads sb, aps and tps of the warm-rain block; the relaxation time scales are not used by this leaf
+    blk = Ref(CParams2mWarm{FT}(pack_thermo(FT, tps), pack_sb2006(FT, sb), pack_air(FT, aps), one(FT), one(FT)))
+    itab, otab = ptr_table(FT, cols), ptr_table(FT, out)
+    GC.@preserve blk itab otab begin
+        st = ccall((sym(:cumicro_rain_evaporation_2m, FT), libcumicro), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{CuPtr{FT}}, Ptr{CuPtr{FT}}, Ptr{Cvoid}), blk, n, itab, otab, cur_stream())
+    end
+    check(st)
+    return out
+end
+function CM2.rain_evaporation(sb::CMP.SB2006, aps::CMP.AirProperties, tps::TDI.PS, q_tot::Col{FT}, q_lcl::Col{FT}, q_icl::Col{FT},
+                              q_rai::Col{FT}, q_sno::Col{FT}, ρ::Col{FT}, N_rai::Col{FT}, T::Col{FT}) where {FT <: FTs}
+    o = rain_evaporation_columns(sb, aps, tps, (q_tot, q_lcl, q_icl, q_rai, q_sno, ρ, N_rai, T))
+    return (; ∂ₜρn_rai = o[1], ∂ₜq_rai = o[2])
+end
+function CM2.∂rain_evaporation_∂N_rai_∂q_rai(sb::CMP.SB2006, aps::CMP.AirProperties, tps::TDI.PS, q_tot::Col{FT}, q_lcl::Col{FT},
+                                              q_icl::Col{FT}, q_rai::Col{FT}, q_sno::Col{FT}, ρ::Col{FT}, N_rai::Col{FT}, T::Col{FT}) where {FT <: FTs}
+    o = rain_evaporation_columns(sb, aps, tps, (q_tot, q_lcl, q_icl, q_rai, q_sno, ρ, N_rai, T))
+    return (; ∂N_rai = o[3], ∂q_rai = o[4])
+end
+
 # ---- alternative closures (CM2:920-1002) --------------------------------------------------------
 const AltScheme = Union{CMP.KK2000, CMP.B1994, CMP.TC1980, CMP.LD2004}
 alt_what_acnv(::CMP.KK2000) = 0

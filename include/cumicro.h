@@ -169,6 +169,15 @@ int cumicro_sb2006_leaves_f32(const cumicro_params_2m_warm_f32* p, int64_t n,
                               const float* q_rai, const float* n_rai,
                               float* const* out, void* stream);
 
+/* CM2.rain_evaporation(sb, aps, tps, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T) on its own (CM2:780-828; the leaf takes its
+ * arguments unclamped and N_rai as a number density [1/m3]) together with its leading-order derivatives
+ * CM2.∂rain_evaporation_∂N_rai_∂q_rai (CM2:844-853).
+ *   in8  = HOST array of 8 device columns in the reference's argument order: q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T
+ *   out4 = HOST array of 4 device columns (NULL entries skipped): ∂ₜρn_rai, ∂ₜq_rai, ∂N_rai = ∂ₜρn_rai / N_rai (0 unless N_rai > eps),
+ *          ∂q_rai = ∂ₜq_rai / q_rai (0 unless q_rai > eps) */
+int cumicro_rain_evaporation_2m_f64(const cumicro_params_2m_warm_f64* p, int64_t n, const double* const* in8, double* const* out4, void* stream);
+int cumicro_rain_evaporation_2m_f32(const cumicro_params_2m_warm_f32* p, int64_t n, const float* const* in8, float* const* out4, void* stream);
+
 /* 2-moment terminal velocities (number- and mass-weighted).
  * CM2.rain_terminal_velocity(::SB2006, ::SB2006VelType, q_rai, rho, N_rai)  CM2:685-702
  * CM2.rain_terminal_velocity(::SB2006, ::Chen2022VelTypeRain, ...)          CM2:703-719

@@ -89,6 +89,18 @@ def bmt2m_warm(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, leaves=False):
     return out
 
 
+def rain_evaporation_2m(params, q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T):
+    """CM2.rain_evaporation + CM2.∂rain_evaporation_∂N_rai_∂q_rai over arrays (CM2:780-853): 4 columns."""
+    dtype = np.float64 if type(params).__name__.endswith("f64") else np.float32
+    cols, n = _cols((q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T), dtype)
+    names = ("dNrho_dt", "dq_dt", "dN_rai", "dq_rai")
+    out = {k: np.empty(n, dtype) for k in names}
+    ip = (C.c_void_p * 8)(*[_ptr(a) for a in cols])
+    op = (C.c_void_p * 4)(*[_ptr(out[k]) for k in names])
+    assert getattr(lib(), f"oracle_rain_evaporation_2m_{_suf(dtype)}")(C.byref(params), C.c_int64(n), ip, op) == 0
+    return out
+
+
 def bmt2m_warm_bound(params, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, leaves=False):
     """First-order rounding-error bounds of the reference algorithm (oracle_tracked.hpp)
     for the outputs of ``bmt2m_warm`` on the same Float64 inputs."""

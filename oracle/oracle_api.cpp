@@ -9,6 +9,17 @@
 
 using namespace orc;
 
+// CM2.rain_evaporation + CM2.∂rain_evaporation_∂N_rai_∂q_rai (CM2:780-853): in8 = q_tot, q_lcl, q_icl, q_rai, q_sno, rho, N_rai, T
+template <class FT, class PB>
+static void rain_evap_point(const PB& p, const FT (&x)[8], FT (&y)[4]) {
+    Thermo<FT> tps(p.tps);
+    FT dn, dq;
+    rain_evaporation<FT>(p.sb, p.aps, tps, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], dn, dq);
+    y[0] = dn;
+    y[1] = dq;
+    y[2] = (x[6] > eps_2M<FT>()) ? dn / x[6] : FT(0);     // CM2:850
+    y[3] = (x[3] > eps_2M<FT>()) ? dq / x[3] : FT(0);     // CM2:851
+}
 extern "C" {
 
 int oracle_num_threads(void) { return omp_get_max_threads(); }
@@ -36,6 +47,19 @@ void oracle_set_f32_thresholds(int on) { f32_thresholds() = (on != 0); }
     }
 DEF_BMT2M_WARM(f64, double)
 DEF_BMT2M_WARM(f32, float)
+
+#define DEF_RAIN_EVAP(SUF, FT)                                                                                              \
+    int oracle_rain_evaporation_2m_##SUF(const cumicro_params_2m_warm_##SUF* p, int64_t n, const FT* const* in8, FT* const* out4) { \
+        _Pragma("omp parallel for schedule(static)") for (int64_t i = 0; i < n; ++i) {                                    \
+            FT x[8], y[4];                                                                                                  \
+            for (int c = 0; c < 8; ++c) x[c] = in8[c][i];                                                                   \
+            rain_evap_point<FT>(*p, x, y);                                                                                  \
+            for (int c = 0; c < 4; ++c) if (out4[c]) out4[c][i] = y[c];                                                     \
+        }                                                                                                                   \
+        return 0;                                                                                                           \
+    }
+DEF_RAIN_EVAP(f64, double)
+DEF_RAIN_EVAP(f32, float)
 
 // Rounding-error bounds of the reference algorithm itself (oracle_tracked.hpp): same
 // inputs, FT = Tr; returns only the bounds (the values equal the f64 run bit for bit).

