@@ -33,3 +33,17 @@ def cuda(built):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Float32 methods: ULP distance of the GPU results to the reference's own Float32 arithmetic (orc<float>) and of both to the
+    true value, collected by cumicro.testing.assert_f32_method — written where a GPU run leaves its artefacts."""
+    try:
+        import json
+        from cumicro import testing
+        if testing.F32_REPORT:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            json.dump(testing.F32_REPORT, open(os.path.join(out, "f32_ulp_report.json"), "w"), indent=1)
+    except Exception:
+        pass

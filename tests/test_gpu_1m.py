@@ -168,7 +168,7 @@ def test_bmt1m_f32(built, orc, cuda):
         truth = orc.bmt1m(blk64, *st64, mode="verbose")
         bound = orc.bmt1m(blk64, *st64, mode="verbose", bound=True)
     for k in orc.OUT_1M + orc.SRC_1M:
-        assert_f32_method(k, out[k].cpu().numpy(), ref32[k], truth[k], bound[k])
+        assert_f32_method("1m:" + k, out[k].cpu().numpy(), ref32[k], truth[k], bound[k], ref_is_f32_oracle=True)
 
 
 def test_config1_grid_64cubed(built, orc, cuda):

@@ -270,7 +270,7 @@ def test_bmt2m_warm_f32(built, orc, cuda):
         truth = orc.bmt2m_warm(blk64, *st64)
         bound = orc.bmt2m_warm_bound(blk64, *st64)
     for k in OUTS:
-        assert_f32_method(k, out[k].cpu().numpy(), ref32[k], truth[k], bound[k])
+        assert_f32_method("2m:" + k, out[k].cpu().numpy(), ref32[k], truth[k], bound[k], ref_is_f32_oracle=True)
 
 
 def test_host_buffer_pipeline_matches_device_path(built, cuda):
@@ -486,3 +486,32 @@ def test_plain_c_host_calls_the_library(built, cuda):
     ref = _gpu_bmt(built, CMP.Microphysics2MParams(np.float64), CMP.ThermodynamicsParameters(np.float64), cols)
     for g, k in zip(got, OUTS):
         assert g == float(ref[k][0]), (k, g, float(ref[k][0]))
+
+
+@pytest.mark.parametrize("limited", [True, False])
+def test_generic_body_with_non_default_structure(built, orc, cuda, limited):
+    """A parameter block WITHOUT the default SB2006 structure runs the general body (cm_sb2006.cuh, SPEC = -1): non-integer exponents
+    (pow_param's real-power branch), and evap.rho0 != accr.rho0 != pdf_r.rho0 (the two extra IEEE square roots).  VERDICT r1 #3."""
+    from cumicro.testing import synthetic_states_2m, assert_parity
+    CMP = built.CMP
+    n = 1 << 16
+    st = synthetic_states_2m(n, seed=31)
+    mp = CMP.Microphysics2MParams(np.float64, is_limited=limited)
+    sb = mp.warm_rain.seifert_beheng
+    sb.acnv.b = 2.5; sb.accr.c = 3.3; sb.self.d = -4.2
+    sb.accr.rho0 = 1.1; sb.evap.rho0 = 1.3; sb.pdf_r.rho0 = 1.225
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk = CMP.pack_2m_warm(mp, tps)
+    out = _gpu_bmt(built, mp, tps, _to_dev(st, cuda))
+    ref, bound = _oracle_with_bound(orc, blk, st)
+    for k in OUTS:
+        rep = assert_parity("generic:" + k, out[k].cpu().numpy(), ref[k], bound=bound[k])
+        assert rep["max_rel"] <= 1e-12 and rep["frac_forward_ok"] > 0.99, (k, rep)
+    # each exponent on its own (integer codes 1, 2 and the real power), same-rho0 arms on and off
+    for b, c, d, r_ac, r_ev in ((2.0, 1.0, -5.0, 1.225, 1.225), (3.0, 4.0, -4.5, 1.225, 1.0), (1.0, 2.0, -5.0, 0.9, 1.225)):
+        sb.acnv.b, sb.accr.c, sb.self.d, sb.accr.rho0, sb.evap.rho0 = b, c, d, r_ac, r_ev
+        sub = {k: v[:1 << 13] for k, v in st.items()}
+        out = _gpu_bmt(built, mp, tps, _to_dev(sub, cuda))
+        ref, bound = _oracle_with_bound(orc, CMP.pack_2m_warm(mp, tps), sub)
+        for k in OUTS:
+            assert_parity(f"generic({b},{c},{d}):{k}", out[k].cpu().numpy(), ref[k], bound=bound[k])

@@ -53,7 +53,8 @@ def test_p3_rates_f64_parity(built, orc, cuda, variant):
     kw, quad, ice_kw = {}, None, {}
     if variant == "cheb20_unlimited":
         kw = dict(is_limited=False, quadrature_order=20)          # build_quadrature(20) -> ChebyshevGauss
-    mp, tps, st = _setup(built, 800, seed=11 + len(variant), **kw)
+    # 2^14 points for the default configuration (BASELINE config 4's scheme), 2^11 for the two variants (the CPU port does ~1e4 points/s)
+    mp, tps, st = _setup(built, (1 << 14) if variant == "default_gl16" else (1 << 11), seed=11 + len(variant), **kw)
     if variant == "gl12_noar_constslope":
         mp.ice = CMP3.P3IceParams(np.float64, slope_law="constant", aspect_ratio=CMP3.NoAspectRatio(), quadrature_order=12,
                                   overrides={"P3_constant_slope_parameterization_value": 1.5})
@@ -83,7 +84,7 @@ def test_bmt2m_p3_f64_parity(built, orc, cuda):
     import torch
     from cumicro.testing import assert_parity
     BMT, CMP3 = built.BMT, built.CMP3
-    mp, tps, st = _setup(built, 1500, seed=5)
+    mp, tps, st = _setup(built, 1 << 13, seed=5)
     # cold points so that F23 deposition / Bigg freezing / immersion cap are all active somewhere
     st["T"][::3] -= 25.0
     blk = CMP3.pack_p3(mp, tps)
