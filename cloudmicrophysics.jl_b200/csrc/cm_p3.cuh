@@ -371,6 +371,12 @@ struct P3Point {
     }
 };
 
+// get_μ from λ = exp(logλ) (P3_size_distribution.jl:171-199): ONE definition, used by p3_point_init and by the quantile
+// solves ahead of the point's pass from logλ — the same expressions, so a quantile solved ahead of the point's pass has the same bits
+CM_DEV void p3_mu_lam(const P3K& k, double logl, double& mu, double& lam) {
+    lam = exp_nl_(logl);
+    mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+}
 // P3.state_from_prognostic + P3State + PSD parameters + velocity coefficients
 CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K& k, double rho, double T, double L_ice, double N_ice,
                           double L_rim, double B_rim, double logl) {
@@ -408,8 +414,7 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
     s.la_grp = unrimed ? 0.0 : logp_nl_(s.rho_g * pi / 6.0);
     s.la_part = logp_nl_(k.alpha_va / Fu);
     // get_μ, get_logN₀                                               P3_size_distribution.jl:171-237
-    s.lam = exp_nl_(logl);
-    s.mu = k.slope_power_law ? clamp_(k.slope_a * pow_pos_(s.lam, k.slope_b) - k.slope_c, 0.0, k.mu_max) : k.mu_const;
+    p3_mu_lam(k, logl, s.mu, s.lam);
     {
         const double z = 0.0 + s.mu + 1.0;
         s.logN0 = logp_nl_(N_ice) - (-z * logl + lgamma_pos_(z) + 0.0);
@@ -537,18 +542,23 @@ CM_HD int p3_coll_passes(int n) { return (4 * n + 31) / 32; }            // oute
 CM_HD int p3_phase_barriers(int n) { return 4 + p3_coll_passes(n); }
 
 // The quantile pairs the requested integrals need (one Halley solve per lane).
-CM_DEV void p3_bounds(const P3Point& s, const P3K& k, int want, int lane, double (&bv)[5], double (&bc)[5], double (&ba)[5]) {
-    // lane 0,1: p = 1e-6 (velocities, melt)   2,3: p = 1e-5 (collisions)   4,5: p = eps (self-collection)
+// Quantile `which` (0,1: p = 1e-6 and 1 - p: velocities, melt   2,3: p = 1e-5: collisions   4,5: p = eps: self-collection) of the
+// ice PSD with slope exp(logl), as a diameter; 0 when the point's `want` mask does not need it.     P3_size_distribution.jl:171-237
+CM_DEV double p3_quantile(const P3K& k, int want, int which, double mu, double lam) {
+    const int g = which >> 1;
+    const bool need = (g == 0) ? (want & (P3_WANT_VEL | P3_WANT_MELT)) : ((g == 1) ? (want & P3_WANT_COLL) : (want & P3_WANT_AGG));
+    if (!need) return 0.0;
+    const double pq = (g == 0) ? 1e-6 : ((g == 1) ? 0.00001 : k.eps);
+    const double Y = (which & 1) ? (1.0 - pq) : pq;
+    return gamma_inc_inv_(mu + 1.0, Y, 1.0 - Y, k.gamma_iters, k.eps) / lam;
+}
+
+// `have_pre`: lane l < 6 holds quantile l in `pre`, solved ahead (one per thread of the block, kernels_p3.cu); else one Halley
+// solve per lane here.
+CM_DEV void p3_bounds(const P3Point& s, const P3K& k, int want, int lane, double (&bv)[5], double (&bc)[5], double (&ba)[5],
+                      bool have_pre = false, double pre = 0.0) {
     double x = 0.0;
-    if (lane < 6) {
-        const int g = lane >> 1;
-        const bool need = (g == 0) ? (want & (P3_WANT_VEL | P3_WANT_MELT)) : ((g == 1) ? (want & P3_WANT_COLL) : (want & P3_WANT_AGG));
-        if (need) {
-            const double pq = (g == 0) ? 1e-6 : ((g == 1) ? 0.00001 : k.eps);
-            const double Y = (lane & 1) ? (1.0 - pq) : pq;
-            x = gamma_inc_inv_(s.mu + 1.0, Y, 1.0 - Y, k.gamma_iters, k.eps) / s.lam;
-        }
-    }
+    if (lane < 6) x = have_pre ? pre : p3_quantile(k, want, lane, s.mu, s.lam);
     p3_segments(s, k, bcast(x, 0), bcast(x, 1), bv);
     p3_segments(s, k, bcast(x, 2), bcast(x, 3), bc);
     p3_segments(s, k, bcast(x, 4), bcast(x, 5), ba);
@@ -558,12 +568,12 @@ CM_DEV void p3_bounds(const P3Point& s, const P3K& k, int want, int lane, double
 // memory; `sc`: this warp's scratch.  L_c, N_c, L_r, N_r: volumetric liquid contents.
 CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, const P3K& k, const ThermoK<double>& tk,
                            const SB2006K<double>& sk, const double* qx, const double* qw, P3Scratch& sc, int want, double L_c,
-                           double N_c, double L_r, double N_r, P3Rates& out) {
+                           double N_c, double L_r, double N_r, P3Rates& out, bool have_pre = false, double pre = 0.0) {
     const int lane = threadIdx.x & 31;
     const int n = k.n;
     const double pi = num<double>::pi();
     double bv[5], bc[5], ba[5];
-    p3_bounds(s, k, want, lane, bv, bc, ba);
+    p3_bounds(s, k, want, lane, bv, bc, ba, have_pre, pre);
     SegNodes sn;
     P3_BAR();   // 1
 

@@ -25,7 +25,7 @@ using namespace cm;
 // 2^19 points, process rates: 128x10 unsynchronised 57.5 ms | with the per-point barrier: 256x5 50.3, 320x4 49.7, 512x2 49.8,
 // 640x2 47.2, 1024x1 (64 registers) 50.7 | 1024x1 unsynchronised 64.5 | 1024x1 with barriers at every phase as well 56.5.
 #ifndef CUMICRO_P3_BLOCK
-#define CUMICRO_P3_BLOCK 576
+#define CUMICRO_P3_BLOCK 512
 #define CUMICRO_P3_MINB 2
 #endif
 #ifndef CUMICRO_P3_SYNC
@@ -38,7 +38,7 @@ constexpr int BLOCK = CUMICRO_P3_BLOCK;
 constexpr int MINB = CUMICRO_P3_MINB;   // 48 registers: resident warps matter more than spills (128-thread blocks, 2^19 points: MINB 4: 66.0, 6: 62.9, 8: 59.3, 10: 57.5, 12: 57.4 ms)
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
 constexpr int NIN_MAX = 13, NOUT_MAX = 12;
-constexpr int kSlot = 14;   // doubles per point in the owner <-> evaluating-warp exchange (11 inputs out, 12 rates + F_rim, rho_rim back)
+constexpr int kSlot = 17;   // doubles per point in the owner <-> evaluating-warp exchange (11 inputs + 6 quantiles out, 12 rates + F_rim, rho_rim back)
 
 template <class FT> struct P3Args {
     cumicro_params_p3_f64 p;
@@ -253,8 +253,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
             sl[0] = x.rho; sl[1] = x.T; sl[2] = x.L_ice; sl[3] = x.N_ice; sl[4] = x.L_rim; sl[5] = x.B_rim; sl[6] = x.logl;
             sl[7] = x.L_lcl; sl[8] = x.N_lcl; sl[9] = x.L_rai; sl[10] = x.N_rai;
         }
+        // ---- the quantile solves of the round's listed points, ONE PER THREAD (a Halley iteration is serial: solved inside the
+        // point's pass it kept 6 — velocities: 2 — lanes of the evaluating warp busy and the others waiting)
+        __syncthreads();
+        constexpr int NQ = (MODE == MODE_VEL) ? 2 : 6;
+        for (int task = threadIdx.x; task < total * NQ; task += BLOCK) {
+            const int j = task / NQ, which = task - j * NQ;
+            const int o = idx[j];
+            double mu, lam;
+            p3_mu_lam(a.k, slots[o * kSlot + 6], mu, lam);
+            slots[o * kSlot + 11 + which] = p3_quantile(a.k, wantv[o], which, mu, lam);
+        }
         for (int it = 0; it * W < total; ++it) {
-            // it = 0: the list is complete; every CUMICRO_P3_SYNC_EVERY-th it: the block's warps start their next point together
+            // it = 0: the list and the quantiles are complete; every CUMICRO_P3_SYNC_EVERY-th it: the block's warps start their next point together
             if (CUMICRO_P3_SYNC_EVERY == 1 || it % CUMICRO_P3_SYNC_EVERY == 0) __syncthreads();
             const int j = it * W + warp;
             if (j < total) {
@@ -263,11 +274,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
                 const double rho = sl[0], T = sl[1], L_ice = sl[2], N_ice = sl[3], L_rim = sl[4], B_rim = sl[5], logl = sl[6], L_lcl = sl[7],
                              N_lcl = sl[8], L_rai = sl[9], N_rai = sl[10];
                 const int w_o = wantv[o];
+                double pre = 0.0;
+                if (lane < NQ) pre = sl[11 + lane];
                 __syncwarp();
                 P3Point s;
                 p3_point_init(s, a.p, a.k, rho, T, L_ice, N_ice, L_rim, B_rim, logl);
                 P3Rates r;
-                p3_point_rates(s, a.p, a.k, a.tk, a.sk, qx, qw, sc, w_o, L_lcl, N_lcl, L_rai, N_rai, r);
+                p3_point_rates(s, a.p, a.k, a.tk, a.sk, qx, qw, sc, w_o, L_lcl, N_lcl, L_rai, N_rai, r, true, pre);
                 if (lane == 0) {
                     sl[0] = r.v_n; sl[1] = r.v_m; sl[2] = r.melt_dN; sl[3] = r.melt_dL; sl[4] = r.agg_dN;
 #pragma unroll
