@@ -75,15 +75,11 @@ __host__ __device__ __noinline__ inline double pow_pos_(double x, double y) {
     for (int i = (n < 0 ? -n : n); i > 0; i >>= 1) { if (i & 1) r *= b; b *= b; }
     return (f == 0.0) ? r : r * exp_nl_(f * logp_nl_(x));
 }
-// ---- UT.gamma_inc: series (x < a + 1) or Lentz continued fraction, fixed iterations   UT:92-144
-// The series loop leaves early once a term is below half an ulp of the sum: the terms decrease
-// monotonically (x/(a+k) < 1), so every later addition is a no-op and the result is bit-identical
-// to the full loop.
-// Unrolling is still a loss after the barrier-aligned launch (2^19 points: series x1 / CF x1 47.35 ms, series x3 47.0, series x5
-// 48.2, CF x2 51.3, both 52.1): the kernel stays code-size bound.
-#ifndef P3_SERIES_UNROLL
-#define P3_SERIES_UNROLL 1
-#endif
+// ---- UT.gamma_inc: series (x < a + 1) or continued fraction, the reference's fixed iteration counts   UT:92-144
+// Both branches are division-free restatements of the reference's loops (one division at the end instead of one / two per
+// step): they sum the same terms / reach the same convergent, so they agree with it to rounding (<= 6e-15 relative, measured
+// against a Float64 transcription of UT's loops over a in [0.5, 12], x to 1e4) including where 30 steps have not converged.
+// Unrolling further is a loss (2^19 points: CF x1 47.35 ms, CF x2 51.3): the kernel stays code-size bound.
 #ifndef P3_CF_UNROLL
 #define P3_CF_UNROLL 1
 #endif
@@ -95,46 +91,42 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double
     if (x == num<double>::inf()) { r.P = 1.0; r.Q = 0.0; return r; }
     const double factor = exp_nl_(a * logp_nl_(x) - x - lga);
     if (x < a + 1.0) {
-        double term = div_(1.0, a);
-        double sum = term;
-        // blocks of P3_SERIES_UNROLL terms, one convergence test per block: later terms are below half an ulp of the sum, adding
-        // them is a no-op, so the result is bit-identical to the term-by-term exit and to the reference's full loop
+        // Σ_k x^k / (a (a+1) ... (a+k)) = S_K / P_K with S_k = S_{k-1} (a+k) + x^k, P_k = P_{k-1} (a+k): the reference's term
+        // recurrence (term *= x / (a+k); sum += term) without its division per term — same sum, rounding-level difference.
+        // Magnitudes stay below (a+K)^K: a < 1e5 at K = 30 is safe; P3 calls this with a <= μ_max + 1 and the Chen exponents + 7.
+        // Exit test term < sum * 5.5e-17 on the scaled pair, every second term (a converged term adds less than half an ulp).
+        double P = a, X = 1.0, S = 1.0, ak = a;
         int k = 1;
 #pragma unroll 1
-        for (; k + P3_SERIES_UNROLL - 1 <= iters; k += P3_SERIES_UNROLL) {
-#pragma unroll
-            for (int u = 0; u < P3_SERIES_UNROLL; ++u) {
-                term *= x * rcp_(a + (double)(k + u));
-                sum += term;
-            }
-            if (term < sum * 5.5e-17) { k = iters + 1; break; }
+        for (; k + 1 <= iters; k += 2) {
+            ak += 1.0; P *= ak; X *= x; S = fma(S, ak, X);
+            ak += 1.0; P *= ak; X *= x; S = fma(S, ak, X);
+            if (X < S * 5.5e-17) { k = iters + 1; break; }
         }
-#pragma unroll 1
-        for (; k <= iters; ++k) {
-            term *= x * rcp_(a + (double)k);
-            sum += term;
-        }
-        r.P = clamp_(factor * sum, 0.0, 1.0);
+        if (k <= iters) { ak += 1.0; P *= ak; X *= x; S = fma(S, ak, X); }
+        r.P = clamp_(factor * div_(S, P), 0.0, 1.0);
         r.Q = 1.0 - r.P;
     } else {
-        const double tiny = 1e-30;
-        const double b1 = x + 1.0 - a;
-        double c = b1 + 1.0 / tiny;
-        double d = rcp_(b1);
-        double h = d;
+        // Legendre's continued fraction 1 / (b_0 + a_1 / (b_1 + a_2 / (b_2 + ...))), a_k = -k (k - a), b_k = x + 2k + 1 - a, cut
+        // after `iters` partial quotients like the reference's modified-Lentz loop (UT:155-180), evaluated by the three-term
+        // recurrence A_k = b_k A_{k-1} + a_k A_{k-2} of its numerator and denominator: no division per step (Lentz: two), the
+        // same convergent in exact arithmetic (its 1e-30 guards never engage for x >= a + 1), <= 6e-15 relative apart in
+        // Float64.  Both sequences carry s^k, s = the power of two below 1 / b_iters, so they stay O(1) for any x.
+        const double b0 = x + 1.0 - a;
+        const double top = b0 + 2.0 * (double)iters;
+        const double sc = mk64((2045 - ((hi32(top) >> 20) & 0x7ff)) << 20, 0);
+        const double sc2 = sc + sc;
+        double A2 = 1.0, A1 = b0 * sc, B2 = 0.0, B1 = sc;
+        double bs = b0 * sc, ks = 0.0, kas = -a * sc;
 #pragma unroll kP3CfUnroll
         for (int k = 1; k <= iters; ++k) {
-            const double kd = (double)k;
-            const double a_k = -kd * (kd - a);
-            const double b_k = x + 2.0 * kd + 1.0 - a;
-            const double d_tmp = b_k + a_k * d;
-            d = (fabs(d_tmp) < tiny) ? tiny : d_tmp;
-            const double c_tmp = b_k + a_k * rcp_(c);
-            c = (fabs(c_tmp) < tiny) ? tiny : c_tmp;
-            d = rcp_(d);
-            h *= c * d;
+            bs += sc2; ks += sc; kas += sc;
+            const double at = ks * kas;                 // -a_k s^2
+            const double A = fma(bs, A1, -(at * A2));
+            const double B = fma(bs, B1, -(at * B2));
+            A2 = A1; A1 = A; B2 = B1; B1 = B;
         }
-        r.Q = clamp_(factor * h, 0.0, 1.0);
+        r.Q = clamp_(factor * div_(B1, A1), 0.0, 1.0);
         r.P = 1.0 - r.Q;
     }
     return r;
