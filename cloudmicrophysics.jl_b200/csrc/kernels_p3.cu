@@ -19,14 +19,15 @@ namespace {
 
 using namespace cm;
 
-// Launch shape: 2 blocks of 640 threads per SM (40 warps at 48 registers) and ONE block barrier per point (CUMICRO_P3_SYNC = 1):
-// the kernel is instruction-fetch bound — a point's pass walks ~93 KB of code against a 6 KB L0 / 32 KB L1.5
-// instruction cache — and warps that start every point together walk the same loops at the same time and share the lines.
-// 2^19 points, process rates: 128x10 unsynchronised 57.5 ms | with the per-point barrier: 256x5 50.3, 320x4 49.7, 512x2 49.8,
-// 640x2 47.2, 1024x1 (64 registers) 50.7 | 1024x1 unsynchronised 64.5 | 1024x1 with barriers at every phase as well 56.5.
+// Launch shape: ONE block of 896 threads per SM (28 warps at 72 registers) and ONE block barrier per point (CUMICRO_P3_SYNC = 1):
+// the kernel is instruction-fetch bound — a point's pass walks ~90 KB of code against a 6 KB L0 / 32 KB L1.5
+// instruction cache — and warps that start every point together walk the same loops at the same time and share the lines.  The
+// more of an SM's warps share one barrier, the faster: 2^20 points, process rates (tools/tune_p3.py, round 2, after the quantile
+// solves moved ahead of the passes): 256x4 97.8 ms | 320x3 72.7 | 512x2 65.8 | 768x1 63.5 | 896x1 57.7 | 1024x1 (64 registers)
+// 60.2; a barrier every 2nd / 4th / no point (512x2): 77.9 / 86.6 / 90.8; barriers at every phase as well: 512x2 63.1, 1024x1 63.7.
 #ifndef CUMICRO_P3_BLOCK
-#define CUMICRO_P3_BLOCK 512
-#define CUMICRO_P3_MINB 2
+#define CUMICRO_P3_BLOCK 896
+#define CUMICRO_P3_MINB 1
 #endif
 #ifndef CUMICRO_P3_SYNC
 #define CUMICRO_P3_SYNC 1
@@ -35,7 +36,7 @@ using namespace cm;
 #define CUMICRO_P3_SYNC_EVERY 1
 #endif
 constexpr int BLOCK = CUMICRO_P3_BLOCK;
-constexpr int MINB = CUMICRO_P3_MINB;   // 48 registers: resident warps matter more than spills (128-thread blocks, 2^19 points: MINB 4: 66.0, 6: 62.9, 8: 59.3, 10: 57.5, 12: 57.4 ms)
+constexpr int MINB = CUMICRO_P3_MINB;
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
 constexpr int NIN_MAX = 13, NOUT_MAX = 12;
 constexpr int kSlot = 17;   // doubles per point in the owner <-> evaluating-warp exchange (11 inputs + 6 quantiles out, 12 rates + F_rim, rho_rim back)
@@ -287,6 +288,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
                     for (int c = 0; c < 7; ++c) sl[5 + c] = r.src[c];
                     sl[12] = s.F_rim; sl[13] = s.rho_rim;
                 }
+            } else {   // no point left for this warp: keep the block's barrier count (cm_p3.cuh, P3_BAR)
+                for (int b = 0; b < p3_phase_barriers(nq); ++b) P3_BAR();
             }
         }
         __syncthreads();
