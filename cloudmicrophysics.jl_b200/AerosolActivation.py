@@ -81,8 +81,14 @@ def max_supersaturation(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice, N_liq=No
     return _run(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice, N_liq, N_ice, want=("S",))["S_max"]
 
 
-def N_activated_per_mode(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice, N_liq=None, N_ice=None):
-    """AA.N_activated_per_mode (AA:235-273): tuple of columns, one per mode."""
+def N_activated_per_mode(ap, ad, aip, tps, T, p, w, q_tot, q_liq=None, q_ice=None, N_liq=None, N_ice=None):
+    """AA.N_activated_per_mode (AA:235-273): tuple of columns, one per mode.  With a trained emulator as the first argument
+    (``EmulatorModels.EmulatorMLP``) this is the method the reference's extension adds: ext/EmulatorModelsExt.jl:32-69."""
+    from . import EmulatorModels as EM
+    if isinstance(ap, EM.EmulatorMLP):   # (machine, ap, ad, aip, tps, T, p, w, qₜ, qₗ, qᵢ): the signature shifted by one
+        return EM.N_activated_per_mode(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice, N_liq)
+    if q_liq is None or q_ice is None:
+        raise TypeError("N_activated_per_mode(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice): q_liq and q_ice are required")
     return tuple(_run(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice, N_liq, N_ice, want=("N",))["N_act"])
 
 
@@ -92,7 +98,10 @@ def M_activated_per_mode(ap, ad, aip, tps, T, p, w, q_tot, q_liq, q_ice, N_liq=N
 
 
 def total_N_activated(*args, **kw):
-    """AA.total_N_activated (AA:355-384): sum over modes in mode order."""
+    """AA.total_N_activated (AA:355-384): sum over modes in mode order (ext/EmulatorModelsExt.jl:89-103 for an emulator)."""
+    from . import EmulatorModels as EM
+    if args and isinstance(args[0], EM.EmulatorMLP):
+        return EM.total_N_activated(*args, **kw)
     cols = N_activated_per_mode(*args, **kw)
     tot = cols[0].clone()
     for c in cols[1:]:

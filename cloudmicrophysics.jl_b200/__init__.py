@@ -19,6 +19,7 @@ def __getattr__(name):  # torch-dependent modules are imported on first use
             "AerosolActivation": "AerosolActivation", "AA": "AerosolActivation",
             "AerosolModel": "AerosolModel", "AM": "AerosolModel",
             "IceNucleation": "IceNucleation", "IN": "IceNucleation", "fused": "fused", "collective": "collective",
+            "EmulatorModels": "EmulatorModels",
             "P3Scheme": "P3Scheme", "P3": "P3Scheme", "CMP3": "parameters_p3"}
     if name in lazy:
         return importlib.import_module("." + lazy[name], __name__)

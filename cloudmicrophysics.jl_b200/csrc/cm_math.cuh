@@ -429,7 +429,11 @@ CM_HD float lgamma_(float x) { return lgammaf(x); }
 // erf: CUDA libm.  A table-driven replacement (x P(x²) below 0.875, 1 - exp_(-x²) R_i(x) on three intervals, degree-14
 // polynomials in shared memory, < 2 units of 2^-53) was built and measured: 60 instructions instead of ~90, but SLOWER in the
 // ARG2000 kernel (config 3: 2.01 -> 2.08 ms; lanes of a warp sit in different pieces and the 15 dependent LDS+DFMA pairs do not
-// overlap the way the libm's register-resident polynomial does), so it was dropped.
+// overlap the way the libm's register-resident polynomial does), so it was dropped.  Round 2 tried the other direction — ONE
+// branch-free piece, erf(|x|) = 1 - exp_(-|x| Q(|x|)), Q = -log(erfc x)/x as a degree-20 polynomial from the constant bank
+// (2.4e-16 absolute, 35 FP64 + ~35 other instructions) — against the libm's, which on sm_100a is itself ONE branch-free piece
+// (41 FP64 + a MUFU.EX2 + 68 UMOVs that ptxas hoists out of the grid-stride loop): config 3 2.01 -> 1.99 ms, config 5
+// 2.36 -> 2.42 ms.  Not kept: libm's erf is not where these kernels lose time.
 CM_HD double erf_(double x) { return erf(x); }
 CM_HD float erf_(float x) { return erff(x); }
 CM_HD double erfc_(double x) { return erfc(x); }

@@ -291,3 +291,41 @@ def synthetic_states_p3(n, seed=1234, dtype=np.float64, frac_ice_free=0.3, frac_
     st["q_tot"] = st["q_tot"] + q_ice
     st.update(q_ice=q_ice, n_ice=n_ice, q_rim=q_rim, b_rim=b_rim)
     return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in st.items()}
+
+
+def train_arg_emulator(orc, n_train=3000, hidden=(32, 16), seed=7, activation="relu", target_transform=True, kind="kappa"):
+    """A machine for the emulator methods the way the reference's pipeline makes one (ext/Common.jl): rows of
+    [mode features (modes 1 and i swapped), velocity, initial_temperature, initial_pressure], log-preprocessed and standardized,
+    fitted to the (target-transformed) ARG2000 activated fraction of the first listed mode — here with scikit-learn's
+    MLPRegressor standing in for the MLJ model.  Returns (EmulatorMLP, predict) with ``predict(X)`` scikit-learn's own evaluation
+    of the raw feature table, for the tests to compare against.  TEST INFRASTRUCTURE: needs the CPU oracle for the targets."""
+    from sklearn.neural_network import MLPRegressor
+    from sklearn.preprocessing import StandardScaler
+    from oracle import emulator as oe
+    from . import AerosolActivation as AA, parameters as CMP
+    from .EmulatorModels import EmulatorMLP
+    ad = arg_test_distribution(kind)
+    ap = CMP.AerosolActivationParameters(np.float64)
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    hyg = [float(h) for h in AA.mean_hygroscopicity_parameter(ap, ad)]
+    st = synthetic_states_activation(n_train, seed=seed)
+    blk = CMP.pack_icenuc(tps, ad=ad)
+    out = orc.arg_icenuc(blk, *[st[k] for k in ("T", "p", "w", "q_tot", "q_liq", "q_ice", "N_liq", "N_ice")])
+    nm = len(ad.modes)
+    X, y = [], []
+    for i in range(nm):
+        sel = slice(i, None, nm)
+        X.append(oe.feature_rows(ad.modes, hyg, st["T"][sel], st["p"][sel], st["w"][sel], i))
+        y.append(out["N_act"][i][sel] / ad.modes[i].N)
+    X, y = np.concatenate(X), np.clip(np.concatenate(y), 0.0, 1.0)
+    Xp = oe.preprocess(X, nm)
+    scaler = StandardScaler().fit(Xp)
+    scaler.scale_ = np.where(scaler.scale_ < 1e-300, 1.0, scaler.scale_)   # constant columns (the spectator modes' kappa ...)
+    yt = np.arctanh(2.0 * 0.99 * (y - 0.5)) if target_transform else y      # ext/Common.jl:154-156
+    mlp = MLPRegressor(hidden_layer_sizes=hidden, activation=activation, max_iter=400, random_state=seed, tol=1e-6).fit(scaler.transform(Xp), yt)
+    machine = EmulatorMLP.from_sklearn(mlp, scaler, log_features=True, target_transform=target_transform)
+
+    def predict(Xraw):
+        yy = mlp.predict(scaler.transform(oe.preprocess(Xraw, nm)))
+        return oe.inverse_target_transform(yy) if target_transform else yy
+    return machine, predict, ad, ap, tps, hyg

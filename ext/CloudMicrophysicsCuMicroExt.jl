@@ -551,6 +551,22 @@ struct CParams2mAlt{FT}
     ld_k::FT
 end
 
+# cumicro_params_emulator
+struct CParamsEmulator{FT}
+    mode_N::NTuple{8, FT}
+    mode_mean::NTuple{8, FT}
+    mode_stdev::NTuple{8, FT}
+    mode_kappa::NTuple{8, FT}
+    feat_mean::NTuple{35, FT}
+    feat_inv_scale::NTuple{35, FT}
+    n_modes::Int32
+    n_layers::Int32
+    width::NTuple{4, Int32}
+    activation::Int32
+    log_features::Int32
+    target_transform::Int32
+end
+
 # (END-MIRRORS)
 
 # =========================================================================================
@@ -1210,6 +1226,68 @@ AA.total_N_activated(ap::AP, ad::AD, aps::CMP.AirProperties, tps::TDI.PS, T::Col
     reduce(+, AA.N_activated_per_mode(ap, ad, aps, tps, T, args...))
 AA.total_M_activated(ap::AP, ad::AD, aps::CMP.AirProperties, tps::TDI.PS, T::Col{FT}, args::Vararg{Union{Col{FT}, Nothing}}) where {FT <: FTs} =
     reduce(+, AA.M_activated_per_mode(ap, ad, aps, tps, T, args...))
+
+# ---- the trained-emulator methods of ext/EmulatorModelsExt.jl:32-103 for a multilayer-perceptron machine ------------
+"""
+    CuMicroEmulatorMLP(layers; activation = :relu, log_features = true, feat_mean, feat_scale, target_transform = false)
+
+The machine of `AA.N_activated_per_mode(machine, ap, ad, aip, tps, T, p, w, qₜ, qₗ, qᵢ)` on the device: dense layers
+`layers = [(W₁, b₁), ...]` (`Wₗ` of size outputs × inputs, as `Flux.Dense` stores it) behind the preprocessing of the reference's
+training pipeline (`ext/Common.jl:57-77`: log of N, mean and velocity; a standardizer) and its inverse target transform
+(`ext/Common.jl:158-160`).  The weights are uploaded once, in the float type of the first call.
+"""
+struct CuMicroEmulatorMLP
+    layers::Vector{Tuple{Matrix{Float64}, Vector{Float64}}}
+    activation::Symbol
+    log_features::Bool
+    feat_mean::Vector{Float64}
+    feat_scale::Vector{Float64}
+    target_transform::Bool
+    device_weights::Dict{DataType, Any}
+end
+function CuMicroEmulatorMLP(layers; activation = :relu, log_features = true, feat_mean = nothing, feat_scale = nothing, target_transform = false)
+    nf = size(layers[1][1], 2)
+    CuMicroEmulatorMLP([(Matrix{Float64}(W), Vector{Float64}(b)) for (W, b) in layers], activation, log_features,
+        feat_mean === nothing ? zeros(nf) : Vector{Float64}(feat_mean), feat_scale === nothing ? ones(nf) : Vector{Float64}(feat_scale),
+        target_transform, Dict{DataType, Any}())
+end
+# the buffer layout of include/cumicro.h: per layer W as [inputs][outputs] (outputs fastest) then b
+packed_weights(::Type{FT}, m::CuMicroEmulatorMLP) where {FT} = FT.(reduce(vcat, [vcat(vec(W), b) for (W, b) in m.layers]))   # vec(W) of an outputs × inputs matrix: outputs fastest
+device_weights(::Type{FT}, m::CuMicroEmulatorMLP) where {FT} = get!(() -> CUDA.CuVector{FT}(packed_weights(FT, m)), m.device_weights, FT)
+pad_to(::Type{T}, v, n) where {T} = ntuple(i -> i <= length(v) ? T(v[i]) : T(0), n)
+function pack_emulator(::Type{FT}, m::CuMicroEmulatorMLP, ap, ad) where {FT}
+    nm = AM.n_modes(ad)
+    size(m.layers[1][1], 2) == 4nm + 3 || throw(ArgumentError("the emulator was trained for $((size(m.layers[1][1], 2) - 3) ÷ 4) modes, the distribution has $nm"))
+    hygro = AA.mean_hygroscopicity_parameter(ap, ad)                                   # EmulatorModelsExt.jl:45
+    act = Dict(:relu => 0, :tanh => 1, :logistic => 2, :identity => 3)[m.activation]
+    CParamsEmulator{FT}(
+        pad_to(FT, [ad.modes[j].N for j in 1:nm], 8), pad_to(FT, [ad.modes[j].r_dry for j in 1:nm], 8),
+        pad_to(FT, [ad.modes[j].stdev for j in 1:nm], 8), pad_to(FT, collect(hygro), 8),
+        pad_to(FT, m.feat_mean, 35), pad_to(FT, 1 ./ m.feat_scale, 35),
+        Int32(nm), Int32(length(m.layers)), pad_to(Int32, [size(W, 1) for (W, _) in m.layers], 4),
+        Int32(act), Int32(m.log_features), Int32(m.target_transform))
+end
+function aa_emulated(m::CuMicroEmulatorMLP, ap, ad, T::Col{FT}, p::Col{FT}, w::Col{FT}; total = false) where {FT}
+    n = same_length(T, p, w)
+    nm = AM.n_modes(ad)
+    N_act = [similar(T) for _ in 1:nm]
+    N_tot = total ? similar(T) : nothing
+    blk = Ref(pack_emulator(FT, m, ap, ad))
+    wts = device_weights(FT, m)
+    ntab = ptr_table(FT, N_act)
+    GC.@preserve blk ntab begin
+        st = ccall((sym(:cumicro_aa_emulated, FT), libcumicro), Cint,
+            (Ptr{Cvoid}, CuPtr{FT}, Int64, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, Ptr{CuPtr{FT}}, CuPtr{FT}, Ptr{Cvoid}),
+            blk, wts, n, T, p, w, ntab, dev(FT, N_tot), cur_stream())
+    end
+    check(st)
+    return (; N_act, N_tot)
+end
+# same names and argument order as the reference's extension methods; qₜ, qₗ, qᵢ are unused there as well
+AA.N_activated_per_mode(machine::CuMicroEmulatorMLP, ap::AP, ad::AD, aip::CMP.AirProperties, tps::TDI.PS, T::Col{FT}, p::Col{FT}, w::Col{FT},
+                        qₜ::Col{FT}, qₗ::Col{FT}, qᵢ::Col{FT}) where {FT <: FTs} = Tuple(aa_emulated(machine, ap, ad, T, p, w).N_act)
+AA.total_N_activated(machine::CuMicroEmulatorMLP, ap::AP, ad::AD, aip::CMP.AirProperties, tps::TDI.PS, T::Col{FT}, p::Col{FT}, w::Col{FT},
+                     qₜ::Col{FT}, qₗ::Col{FT}, qᵢ::Col{FT}) where {FT <: FTs} = aa_emulated(machine, ap, ad, T, p, w; total = true).N_tot
 
 # ---- fused 1-moment + 2-moment + ice nucleation with domain diagnostics (BASELINE config 5) ------
 """

@@ -78,6 +78,24 @@ args = (CMP.AerosolActivationParameters(F), arg_test_distribution("kappa"), CMP.
 report("ice nucleation + ARG2000 3 modes f32 2^25 (config 3)", n3, timeit(lambda: AA.activation_and_ice_nucleation(*args, *c, hom_linear=True), reps=10), 4 * (8 + 1 + 3 + 4))
 del c
 
+# ---- the trained-emulator variant of N_activated_per_mode (ext/EmulatorModelsExt.jl): random machines of the reference docs' shape
+from cumicro.EmulatorModels import EmulatorMLP  # noqa: E402
+ne = 1 << 20
+ce = dcols(synthetic_states_activation(ne), ("T", "p", "w"))
+ad3 = arg_test_distribution("kappa")
+ap64 = CMP.AerosolActivationParameters(np.float64)
+rng = np.random.default_rng(0)
+for widths in ((32, 16, 1), (250, 50, 5, 1)):
+    k, layers = 15, []
+    for h in widths:
+        layers.append((rng.normal(size=(k, h)) / np.sqrt(k), rng.normal(size=h) * 0.1))
+        k = h
+    mach = EmulatorMLP(layers, activation="relu", target_transform=True)
+    ms = timeit(lambda: AA.N_activated_per_mode(mach, ap64, ad3, None, tps, *ce, None, None, None), reps=5, warm=2)
+    flops = 2.0 * sum(W.size for W, _ in layers) * 3 * ne
+    report(f"emulated N_activated_per_mode, MLP 15-{'-'.join(map(str, widths))}, 3 modes f64 2^20 ({flops / ms / 1e9:.2f} FP64 TFLOP/s)", ne, ms, 8 * 6)
+del ce
+
 n5 = 1 << 24
 st = synthetic_states_fused(n5)
 c = dcols(st, fused.IN_NAMES)
