@@ -2,11 +2,13 @@
 // multilayer-perceptron machine: cumicro_aa_emulated_* and cumicro_emulator_weight_count_* (include/cumicro.h).
 //
 // A ROW is one (grid point, mode i) pair: the reference builds the feature row with modes 1 and i swapped and asks the machine
-// for the activated fraction of "mode 1".  A block owns the rows of floor(32 / n_modes) consecutive points.  The rows' activations live in shared memory as
+// for the activated fraction of "mode 1".  A block owns the rows of floor(32 / n_modes) consecutive points.  The rows'
+// activations live in shared memory as
 // [unit][row] (a warp reads one unit of 32 rows conflict-free; all threads of a layer read the same [unit][*] line, a broadcast),
-// every thread owns one output unit and keeps its 32 row accumulators in registers, and the weights stream through L1/L2 as
-// [in][out], out fastest: consecutive threads read consecutive words.  Per input unit a thread issues 1 global load, 8 shared
-// 128-bit loads and 32 DFMAs, so the dense layers run at the FP64 pipe's rate; the sums run in input order (the order of a plain
+// a thread owns one output unit of a layer and keeps its row accumulators in registers — all 32 rows for a layer at least 129
+// units wide, 32 / G rows when G = 2, 4, 8, 16 groups of threads fit a narrower layer into the block — and the weights stream
+// through L1/L2 as [in][out], out fastest: consecutive threads read consecutive words.  Per input unit a thread issues 1 global
+// load, R / 2 shared 128-bit loads and R DFMAs; the sums run in input order (the order of a plain
 // dot product), in Float64 for both float types.
 #include <algorithm>
 
@@ -43,8 +45,57 @@ __device__ __forceinline__ double emu_act(int kind, double x) {
     }
 }
 
+// One dense layer of a tile: thread t owns output unit h = t mod H' of the R = 32 / G rows [g R, g R + R), g = t / H' (H' = H for
+// G > 1; for G = 1 a thread walks h = t, t + 256, ...).  W as [K][H], H fastest; activations [unit][32 rows].
+template <class FT, int R>
+__device__ __forceinline__ void dense(const FT* __restrict__ W, const FT* __restrict__ B, const double* __restrict__ in, double* __restrict__ out,
+                                      int K, int H, bool last, int activation) {
+    constexpr int G = kRows / R;
+    const int g = (G == 1) ? 0 : threadIdx.x / H;
+    const int h0 = (G == 1) ? threadIdx.x : threadIdx.x - g * H;
+    if (g >= G) return;
+    const int r0 = g * R;
+    for (int h = h0; h < H; h += (G == 1 ? kThreads : H)) {
+        double acc[R];
+        const double b = (double)__ldg(B + h);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = b;
+        // weights of U input units are fetched ahead of their multiply-adds (an L1/L2 hit is ~10x the 2 R issue cycles of a unit)
+        constexpr int U = (R >= 32) ? 4 : 8;
+        int k = 0;
+        for (; k + U <= K; k += U) {
+            double wv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) wv[u] = (double)__ldg(W + (size_t)(k + u) * H + h);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double2* x2 = reinterpret_cast<const double2*>(in + (k + u) * kRows + r0);
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const double2 v = x2[r];
+                    acc[2 * r] = fma(wv[u], v.x, acc[2 * r]);
+                    acc[2 * r + 1] = fma(wv[u], v.y, acc[2 * r + 1]);
+                }
+            }
+        }
+        for (; k < K; ++k) {
+            const double wv = (double)__ldg(W + (size_t)k * H + h);
+            const double2* x2 = reinterpret_cast<const double2*>(in + k * kRows + r0);
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) {
+                const double2 v = x2[r];
+                acc[2 * r] = fma(wv, v.x, acc[2 * r]);
+                acc[2 * r + 1] = fma(wv, v.y, acc[2 * r + 1]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[h * kRows + r0 + r] = last ? acc[r] : emu_act(activation, acc[r]);
+        if (G != 1) break;
+    }
+}
+
 template <class FT>
-__global__ void __launch_bounds__(kThreads) emu_kernel(const __grid_constant__ EmuArgs<FT> a) {
+__global__ void __launch_bounds__(kThreads, 2) emu_kernel(const __grid_constant__ EmuArgs<FT> a) {
     extern __shared__ double smem[];
     double* buf0 = smem;
     double* buf1 = smem + (size_t)a.max_width * kRows;
@@ -88,24 +139,15 @@ __global__ void __launch_bounds__(kThreads) emu_kernel(const __grid_constant__ E
             const int H = a.p.width[l];
             const FT* B = W + (size_t)K * H;
             const bool last = l == a.p.n_layers - 1;
-            for (int h = threadIdx.x; h < H; h += kThreads) {
-                double acc[kRows];
-                const double b = (double)__ldg(B + h);
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) acc[r] = b;
-#pragma unroll 2
-                for (int k = 0; k < K; ++k) {
-                    const double wv = (double)__ldg(W + (size_t)k * H + h);
-                    const double2* x2 = reinterpret_cast<const double2*>(in + k * kRows);
-#pragma unroll
-                    for (int r = 0; r < kRows / 2; ++r) {
-                        const double2 v = x2[r];
-                        acc[2 * r] = fma(wv, v.x, acc[2 * r]);
-                        acc[2 * r + 1] = fma(wv, v.y, acc[2 * r + 1]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) out[h * kRows + r] = last ? acc[r] : emu_act(a.p.activation, acc[r]);
+            // narrow layers: the 32 rows are split over G = 2^g thread groups (G H <= 256), each thread keeps 32 / G accumulators
+            int G = 1;
+            while (G < kRows && 2 * G * H <= kThreads) G *= 2;
+            switch (G) {
+                case 1: dense<FT, 32>(W, B, in, out, K, H, last, a.p.activation); break;
+                case 2: dense<FT, 16>(W, B, in, out, K, H, last, a.p.activation); break;
+                case 4: dense<FT, 8>(W, B, in, out, K, H, last, a.p.activation); break;
+                case 8: dense<FT, 4>(W, B, in, out, K, H, last, a.p.activation); break;
+                default: dense<FT, 2>(W, B, in, out, K, H, last, a.p.activation); break;   // G = 16 (and 32: half the groups idle)
             }
             __syncthreads();
             W = B + H;
