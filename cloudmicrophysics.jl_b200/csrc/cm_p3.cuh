@@ -176,6 +176,7 @@ struct P3K {
     // thresholds: (6 α_va / (π ρ))^(1/(3 - β_va))
     double thr_p, thr_coef, D_th;
     double pi6, phi_coef;                 // π/6, 3 sqrt(π)
+    double log_pi4, log_gamma_a, half_log_pi, lphc_i;   // log(π/4), log γ, log(π)/2, log(3 sqrt(π) / (4 ρᵢ))
     double log_rho_i_pi6, log_alpha_va, log_mu_c, log3;
     // air
     double cbrt_Nsc, inv_nu_air, K_therm, D_vapor;
@@ -212,6 +213,8 @@ __host__ inline P3K make_p3_k(const cumicro_params_p3_f64& p, bool method_is_f32
     k.log_rho_i_pi6 = std::log(s.rho_i * pi / 6.0); k.log_alpha_va = std::log(s.alpha_va);
     k.log_mu_c = std::log(p.warm.sb.pdf_c.mu_c); k.log3 = std::log(3.0);
     k.phi_coef = 3.0 * std::sqrt(pi);
+    k.log_pi4 = std::log(pi / 4.0); k.log_gamma_a = std::log(s.gamma); k.half_log_pi = 0.5 * std::log(pi);
+    k.lphc_i = std::log(k.phi_coef / (4.0 * s.rho_i));
     const auto& aps = p.warm.aps;
     k.cbrt_Nsc = std::cbrt(aps.nu_air / aps.D_vapor);
     k.inv_nu_air = 1.0 / aps.nu_air; k.K_therm = aps.K_therm; k.D_vapor = aps.D_vapor;
@@ -299,7 +302,7 @@ struct P3Point {
     // inputs
     double rho, T, L_ice, N_ice, F_rim, rho_rim;
     // P3State thresholds                                        P3_particle_properties.jl:43-56
-    double rho_g, D_gr, D_cr;
+    double rho_g, D_gr, D_cr, lphc_g;   // lphc_g = log(3 sqrt(π) / (4 ρ_g))
     // mass regime coefficients: a D^b as exp(la + b log D)
     double la_small, la_unr, la_grp, la_part;
     // PSD
@@ -316,33 +319,37 @@ struct P3Point {
     // One code path for all regimes and both velocity curves (coefficients are selected, not branched on): the body
     // stays within the ~6 KB L0 instruction cache of an SM sub-partition, which is what bounds this kernel.
     struct Node { double mass, dmass_dD_overD, r, v, n; };   // r = sqrt(area / π)
-    template <bool NEED_V, bool NEED_MELT = false>
+    // Log-space form: log m = la + b log D and log A (analytic except in the partially rimed regime, where the area is a sum)
+    // give r = exp(log A / 2 - log π / 2) and the aspect-ratio factor ϕ^(1/3) = exp((log(3 sqrt π / 4 ρ) + log m - 3/2 log A) / 3),
+    // which is folded into the exponents of the two velocity terms: 4 exp_ + 1 log per node instead of 5 exp_ + log + sqrt + rcp +
+    // cbrt (the self-collection double integral evaluates 2048 nodes per point).  Same quantities, rounding-level differences.
+    template <bool NEED_V, bool NEED_MELT = false, bool NEED_MASS = false>
     CM_DEV Node node(double D, const P3K& k) const {
         Node o;
         const double lD = logp_(D);
         const int r = regime(D, k);
         const double la = (r == 0) ? la_small : ((r == 3) ? la_grp : ((r == 4) ? la_part : la_unr));
         const double b = (r == 0 || r == 3) ? 3.0 : k.beta_va;
-        o.mass = exp_(fma_(b, lD, la));
+        const double lm = fma_(b, lD, la);
+        o.mass = NEED_MASS ? exp_(lm) : 0.0;
         // ∂m/∂D / D = a b D^(b-2)
         o.dmass_dD_overD = NEED_MELT ? b * exp_(fma_(b - 2.0, lD, la)) : 0.0;
-        const double sph = D * D * (num<double>::pi() / 4.0);
-        const double non = k.gamma_a * exp_(k.sigma_a * lD);
-        const double area = (r == 0 || r == 3) ? sph : ((r == 4) ? F_rim * sph + (1.0 - F_rim) * non : non);
-        const double sa = sqrt_(area);
-        o.r = sa * 0.5641895835477563;   // 1/sqrt(π)
+        const bool sphere = (r == 0 || r == 3);
+        double larea = sphere ? fma_(2.0, lD, k.log_pi4) : fma_(k.sigma_a, lD, k.log_gamma_a);
+        if (r == 4) {   // F_rim sphere + (1 - F_rim) non-spherical                    P3_particle_properties.jl:407-420
+            const double sph = D * D * (num<double>::pi() / 4.0);
+            const double non = exp_(larea);
+            larea = logp_(F_rim * sph + (1.0 - F_rim) * non);
+        }
+        o.r = exp_(fma_(0.5, larea, -k.half_log_pi));
         o.n = exp_(fmax_(logN0 + mu * lD - lam * D, -700.0));
         if (NEED_V) {
             const bool small_ = D <= k.cutoff;
             const double A0 = small_ ? sa0 : ga0, B0 = small_ ? sb : gb0, A1 = small_ ? sa1 : ga1, B1 = small_ ? sb : gb1,
                          C1 = small_ ? sc1 : gc1;
-            double v = A0 * exp_(B0 * lD) + A1 * exp_(fmax_(fma_(B1, lD, -C1 * D), -700.0));
-            if (k.aspect_oblate) {
-                const double rho_m = (r == 3) ? rho_g : k.rho_i;
-                const double phi = k.phi_coef * o.mass * rcp_(4.0 * rho_m * area * sa);
-                v *= cbrtp_(phi);
-            }
-            o.v = v;
+            // ϕ = 3 sqrt(π) m / (4 ρ A^(3/2)), v *= ϕ^(1/3)                         P3_terminal_velocity.jl:32-60
+            const double lp3 = k.aspect_oblate ? (((r == 3) ? lphc_g : k.lphc_i) + lm - 1.5 * larea) * (1.0 / 3.0) : 0.0;
+            o.v = A0 * exp_(fma_(B0, lD, lp3)) + A1 * exp_(fmax_(fma_(B1, lD, -C1 * D), -700.0) + lp3);
         } else {
             o.v = 0.0;
         }
@@ -404,6 +411,7 @@ CM_DEV void p3_point_init(P3Point& s, const cumicro_params_p3_f64& p, const P3K&
     s.la_small = k.log_rho_i_pi6;
     s.la_unr = k.log_alpha_va;
     s.la_grp = unrimed ? 0.0 : logp_nl_(s.rho_g * pi / 6.0);
+    s.lphc_g = unrimed ? 0.0 : logp_nl_(k.phi_coef / (4.0 * s.rho_g));
     s.la_part = logp_nl_(k.alpha_va / Fu);
     // get_μ, get_logN₀                                               P3_size_distribution.jl:171-237
     p3_mu_lam(k, logl, s.mu, s.lam);
@@ -578,7 +586,7 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
         for (int t = lane; t < sn.count(); t += 32) {
             double D, w;
             sn.get(t, qx, qw, D, w);
-            const P3Point::Node nd = s.node<true, true>(D, k);
+            const P3Point::Node nd = s.node<true, true, true>(D, k);
             const double nv = nd.n * nd.v;
             a_n += nv * w;
             a_m += nv * nd.mass * w;
