@@ -135,6 +135,146 @@ pointwise_kernel_pipelined(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, 
     }
 }
 
+// ---- tile variant: the launch shape of the headline kernel (cm_tile2m.cuh) for any functor ---------------------------------
+// Block-uniform tile loop (tile = BLOCK consecutive points, dealt round-robin to the persistent blocks).  The NIN input tiles are
+// fetched by 1-D bulk asynchronous copies (cp.async.bulk global -> shared, completion on an mbarrier, two tiles in flight) issued
+// by one elected lane of up to NIN warps: no per-thread address arithmetic or load instruction, and the block barrier + the
+// asynchronous copies inside the loop keep ptxas from hoisting the functor's constants into (spilled) uniform registers.
+// Columns must be 16-byte aligned for the bulk copies; otherwise, and for a partial last tile, the same kernel uses guarded
+// scalar loads (identical results).
+namespace tile {
+CM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+CM_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+CM_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CM_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+CM_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one lane of a converged warp (the canonical leader election: ptxas keeps the guarded code on the uniform datapath)
+CM_DEV bool elect_one() {
+    unsigned p;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
+}
+}  // namespace tile
+
+template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB, bool ALL_OUT>
+__global__ void __launch_bounds__(BLOCK, MINB) pointwise_kernel_tiled(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a, int bulk_ok) {
+    constexpr int NWARP = BLOCK / 32;
+    extern __shared__ __align__(128) unsigned char tiled_dyn_smem[];
+    FT (*stage)[NIN][BLOCK] = reinterpret_cast<FT (*)[NIN][BLOCK]>(tiled_dyn_smem);   // [2][NIN][BLOCK]
+    __shared__ __align__(8) unsigned long long full[2];
+    math_tables_init_for<BLOCK, F>();
+    const int tid = threadIdx.x;
+    const unsigned n_tiles = (unsigned)((a.n + BLOCK - 1) / BLOCK);
+    const unsigned n_full = bulk_ok ? (unsigned)(a.n / BLOCK) : 0u;
+    constexpr unsigned kTileBytes = BLOCK * sizeof(FT);
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction
+    const bool issuer = warp < NIN;
+    constexpr int kIssuers = NWARP < NIN ? NWARP : NIN;
+    if (tid == 0) {
+        tile::mbar_init(&full[0], kIssuers);
+        tile::mbar_init(&full[1], kIssuers);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](unsigned t, int buf) {
+        if (t < n_full && tile::elect_one()) {
+            const int ncol = (NIN - warp + NWARP - 1) / NWARP;
+            tile::mbar_expect_tx(&full[buf], ncol * kTileBytes);
+#pragma unroll 1
+            for (int c = warp; c < NIN; c += NWARP) tile::bulk_g2s(&stage[buf][c][0], a.in[c] + (size_t)t * BLOCK, kTileBytes, &full[buf]);
+        }
+    };
+    unsigned t = blockIdx.x;
+    if (issuer) {
+        issue(t, 0);
+        if (t + gridDim.x < n_tiles) issue(t + gridDim.x, 1);
+    }
+    unsigned j = 0;
+    for (; t < n_tiles; t += gridDim.x, ++j) {
+        const int buf = j & 1;
+        const int64_t it = (int64_t)t * BLOCK + tid;
+        double x[NIN];
+        if (t < n_full) {
+            tile::mbar_wait(&full[buf], (j >> 1) & 1);
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) x[c] = (double)stage[buf][c][tid];
+        } else {
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) x[c] = (double)__ldg(a.in[c] + (it < a.n ? it : a.n - 1));
+        }
+        __syncthreads();   // every thread has read stage[buf]: it may be refilled
+        if (issuer) {
+            const unsigned t2 = t + 2 * gridDim.x;
+            if (t2 < n_tiles) issue(t2, buf);
+        }
+        if (it < a.n) {   // (a functor may count domain errors: a padding thread must not run it)
+            double y[NOUT];
+            a.f(x, y);
+#pragma unroll
+            for (int c = 0; c < NOUT; ++c)
+                if (ALL_OUT || a.out[c]) __stcs(a.out[c] + it, (FT)y[c]);
+        }
+    }
+}
+
+template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB>
+int launch_pointwise_tiled(const F& f, int64_t n, const FT* const (&in)[NIN], FT* const (&out)[NOUT], cudaStream_t stream, const char* what,
+                           int waves = 8) {
+    if (n == 0) return CUMICRO_OK;
+    PointwiseArgs<FT, NIN, NOUT, F> a;
+    a.f = f;
+    a.n = n;
+    int bulk_ok = 1;
+    bool all_out = true;
+    for (int c = 0; c < NIN; ++c) { a.in[c] = in[c]; if (!cmh::aligned16(in[c])) bulk_ok = 0; }
+    for (int c = 0; c < NOUT; ++c) { a.out[c] = out[c]; all_out = all_out && out[c] != nullptr; }
+    auto kern = all_out ? pointwise_kernel_tiled<FT, NIN, NOUT, F, BLOCK, MINB, true> : pointwise_kernel_tiled<FT, NIN, NOUT, F, BLOCK, MINB, false>;
+    constexpr size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[all_out]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (smem > 40 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cmh::cuda_status(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        }
+        attr_set[all_out] = true;
+    }
+#ifdef CUMICRO_TUNING
+    { const char* wv0 = getenv("CUMICRO_WAVES"); if (wv0) waves = atoi(wv0); }
+#endif
+    const int64_t n_tiles = (n + BLOCK - 1) / BLOCK;
+    const int blocks = (int)std::min<int64_t>(n_tiles, (int64_t)cmh::num_sms() * MINB * waves);
+    kern<<<blocks, BLOCK, smem, stream>>>(a, bulk_ok);
+    cmh::count_launch();
+    return cmh::cuda_status(cudaGetLastError(), what);
+}
+
 // Enqueue F over n points on `stream`.  BLOCK x MINB fixes the register budget
 // (65536 / (BLOCK*MINB) per thread).  USE_VEC = false launches the one-point-per-thread
 // variant even for aligned columns: for the FP64-pipe-bound families (2M, 1M) the

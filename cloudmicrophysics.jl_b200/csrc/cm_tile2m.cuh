@@ -34,45 +34,6 @@ template <class FT, int NIN> struct Tile2MArgs {
     int bulk_ok;   // every input column is 16-byte aligned: full tiles arrive by bulk copies (otherwise by guarded scalar loads, same bits)
 };
 
-namespace tile {
-CM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-CM_DEV void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-CM_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-CM_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-CM_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// one lane of a converged warp (the canonical leader election: ptxas keeps the guarded code on the uniform datapath)
-CM_DEV bool elect_one() {
-    unsigned p;
-    asm volatile(
-        "{\n"
-        ".reg .pred P;\n"
-        "elect.sync _|P, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, P;\n"
-        "}\n"
-        : "=r"(p));
-    return p != 0;
-}
-}  // namespace tile
 
 // PPT points per thread: the PPT bodies of one thread are independent and share every constant load.
 template <class FT, int NIN, int LIM, int BLOCK, int MINB, bool ALL_OUT, int PPT, bool TAB>

@@ -24,7 +24,17 @@
 #define CUMICRO_1MV_MINB 8   /* verbose: 4 -> 1.75 ms, 6 -> 1.34, 8 -> 1.22; linavg: 3.07, 3.01, 2.94 */
 #endif
 #ifndef CUMICRO_1M_MINB
-#define CUMICRO_1M_MINB 8   /* sweep at 2^24 points: 5 -> 1.224 ms, 6 -> 1.118, 8 -> 1.043; later: 7 -> 0.937, 8 -> 0.916 */
+#define CUMICRO_1M_MINB 7   /* sweep at 2^24 points: 5 -> 1.224 ms, 6 -> 1.118, 8 -> 1.043; later: 7 -> 0.937, 8 -> 0.916; tile shape: 6 -> 0.839, 7 -> 0.832, 8 -> 0.929 */
+#endif
+// tile shape (cm_launch.cuh, pointwise_kernel_tiled: bulk-copied input tiles, block-uniform loop) or the grid-stride register-loading shape
+#ifndef CUMICRO_1M_TILED
+#define CUMICRO_1M_TILED 1    /* Instantaneous 2^24 points: 0.892 (grid-stride, 128x8) -> 0.832 ms (tiles, 128x7) */
+#endif
+#ifndef CUMICRO_1MV_TILED
+#define CUMICRO_1MV_TILED 1   /* InstantaneousVerbose (22 columns out): 1.157 -> 0.902 ms (128x8; 128x7 0.906) */
+#endif
+#ifndef CUMICRO_1ML_TILED
+#define CUMICRO_1ML_TILED 0   /* LinearizedAverage nsub = 1: 1.266 ms as it is (1024x1, grid-stride); tiles: 1024x1 1.457, 512x2 1.400, 128x7 1.320 */
 #endif
 namespace {
 
@@ -101,14 +111,23 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
     if ((st = require_outputs<FT, 4>(n, o4, mode == 1 ? 0 : 4))) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == 0) {
+#if CUMICRO_1M_TILED
+        return launch_pointwise_tiled<FT, 7, 4, OneMInst, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
+#else
         return launch_pointwise<FT, 7, 4, OneMInst, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
+#endif
     } else if (mode == 1) {
         if (src18 == nullptr) return cmh::fail(CUMICRO_E_NULL, "source-term pointer table is NULL");
         FT* o22[4 + S1M_NSRC];
         for (int i = 0; i < 4; ++i) o22[i] = o4[i];
         for (int i = 0; i < S1M_NSRC; ++i) o22[4 + i] = src18[i];
+#if CUMICRO_1MV_TILED
+        return launch_pointwise_tiled<FT, 7, 4 + S1M_NSRC, OneMVerbose, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
+                                                                                  "bmt1m_verbose launch");
+#else
         return launch_pointwise<FT, 7, 4 + S1M_NSRC, OneMVerbose, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB, false>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
                                                                                    "bmt1m_verbose launch");
+#endif
     } else {
         if (!(dt > FT(0))) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: dt must be > 0");
         if (nsub < 1) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: nsub = %d must be >= 1", nsub);
@@ -117,7 +136,11 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
         f.nsub = nsub;
         f.Lv_over_cp = f.p.tps.LH_v0 / f.p.tps.cp_d;
         f.Ls_over_cp = f.p.tps.LH_s0 / f.p.tps.cp_d;
+#if CUMICRO_1ML_TILED
+        return launch_pointwise_tiled<FT, 7, 4, OneMLinAvg, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB>(f, n, in, o4, s, "bmt1m_linavg launch");
+#else
         return launch_pointwise<FT, 7, 4, OneMLinAvg, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
+#endif
     }
 }
 

@@ -7,7 +7,10 @@
 #include "cm_launch.cuh"
 
 #ifndef CUMICRO_ARG_MINB
-#define CUMICRO_ARG_MINB 6   /* sweep, config 3: 4 -> 3.50 ms, 6 -> 3.09, 8 -> 3.10 */
+#define CUMICRO_ARG_MINB 6   /* sweep, config 3: 4 -> 3.50 ms, 6 -> 3.09, 8 -> 3.10; tile shape: 5 -> 1.945, 6 -> 1.840, 7 -> 1.894 */
+#endif
+#ifndef CUMICRO_ARG_TILED
+#define CUMICRO_ARG_TILED 1   /* config 3: 1.983 (grid-stride register-loading shape) -> 1.840 ms (bulk-copied tiles, cm_launch.cuh) */
 #endif
 namespace {
 
@@ -208,11 +211,19 @@ int arg_icenuc_launch(const typename PI<FT>::params* p, int64_t n, const FT* con
     out[1 + 2 * MODES + 1] = J_abifm;
     out[1 + 2 * MODES + 2] = J_hom;
     out[1 + 2 * MODES + 3] = da_w;
+#if CUMICRO_ARG_TILED
+    if (want_m)
+        return launch_pointwise_tiled<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, CUMICRO_ARG_MINB>(
+            make_icenuc<FT, ArgIceNuc<MODES, true>>(p, counter), n, in, out, s, "arg_icenuc launch");
+    return launch_pointwise_tiled<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, CUMICRO_ARG_MINB>(
+        make_icenuc<FT, ArgIceNuc<MODES, false>>(p, counter), n, in, out, s, "arg_icenuc launch");
+#else
     if (want_m)
         return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, CUMICRO_ARG_MINB, false>(
             make_icenuc<FT, ArgIceNuc<MODES, true>>(p, counter), n, in, out, s, "arg_icenuc launch");
     return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, CUMICRO_ARG_MINB, false>(
         make_icenuc<FT, ArgIceNuc<MODES, false>>(p, counter), n, in, out, s, "arg_icenuc launch");
+#endif
 }
 
 template <class FT>

@@ -61,6 +61,7 @@ mp1 = CMP.Microphysics1MParams(np.float64)
 o = [torch.empty_like(c[0]) for _ in range(4)]
 m1 = BMT.Microphysics1Moment()
 report("1M Instantaneous f64 2^24", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), m1, mp1, tps, *c, out=o)), 88)
+report("1M InstantaneousVerbose (4 + 18 columns) f64", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.InstantaneousVerbose(), m1, mp1, tps, *c), reps=10), 56 + 8 * 22)
 report("1M LinearizedAverage nsub=1 f64", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.LinearizedAverage(), m1, mp1, tps, *c, Δt=60.0, nsub=1, out=o)), 88)
 report("1M LinearizedAverage nsub=3 f64", n, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.LinearizedAverage(), m1, mp1, tps, *c, Δt=60.0, nsub=3, out=o), reps=10), 88)
 n1 = 64 ** 3
