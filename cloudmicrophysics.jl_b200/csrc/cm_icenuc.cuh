@@ -19,6 +19,9 @@ template <class FT> struct ArgK {
     FT sm_coef[kMaxModes]; // 2/sqrt(hygro) (A_coef/3/r_dry)^(3/2) -> S_m = sm_coef T^(-3/2)   AA:107-118
     FT f[kMaxModes], g[kMaxModes];                  // f1 exp(f2 ln²σ), g1 + g2 ln σ     AA:175-176
     FT inv_eta_coef[kMaxModes];                     // 2π ρ_w N_i
+    FT eta_coef[kMaxModes];                         // 1 / (2π ρ_w N_i)                  (Inf for an empty mode, like the reference's division)
+    FT t1_coef[kMaxModes];                          // (2π ρ_w N_i)^p1: (ζ/η_i)^p1 = (ζ γ / sq³)^p1 * t1_coef_i — ONE exponential per point for all modes
+    FT inv_sm2_coef[kMaxModes];                     // 1 / sm_coef²: 1 / S_m,i² = inv_sm2_coef_i T³
     FT log_sm_coef[kMaxModes], log_inv_eta_coef[kMaxModes];   // their logarithms (host): one log per mode per point instead of three
     FT log_T_triple;
     FT u_coef[kMaxModes];                           // 2 / (3 √2 ln σ_i)                AA:256
@@ -41,6 +44,9 @@ template <class FT> __host__ inline ArgK<FT> make_arg_k(const cumicro_params_ice
         k.inv_eta_coef[i] = 2 * pi * p.arg.rho_w * m.N;
         k.log_sm_coef[i] = std::log(k.sm_coef[i]);
         k.log_inv_eta_coef[i] = std::log(k.inv_eta_coef[i]);   // -Inf for an empty mode: η = Inf, both powers vanish
+        k.eta_coef[i] = FT(1) / k.inv_eta_coef[i];
+        k.t1_coef[i] = std::exp(FT(p.arg.p1) * k.log_inv_eta_coef[i]);
+        k.inv_sm2_coef[i] = FT(1) / (k.sm_coef[i] * k.sm_coef[i]);
         k.u_coef[i] = FT(2) / (FT(3) * std::sqrt(FT(2)) * ls);
         k.m_fac[i] = FT(3) * ls * std::sqrt(FT(2)) / 2;
     }
@@ -114,7 +120,6 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT zeta = FT(2.0 / 3.0) * A * sq;
     const FT sq3 = sq * sq * sq;
     const FT inv_gamma = rcp_(gamma);
-    const FT Tm32 = ts.inv_T * sqrtg_(ts.inv_T);
     const FT l_zeta = logp_(zeta);
     // logarithms: log S_m,i = log(sm_coef_i) - 3/2 log T and log η_i = log(sq³/γ) - log(2π ρ_w N_i) come from host-side
     // logarithms of the parameters plus two per-point ones; per mode only log(η_i + 3ζ) remains
@@ -122,25 +127,26 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT l_T32 = FT(-1.5) * (ts.log_Tr + k.log_T_triple);
     const FT eta_common = sq3 * inv_gamma;
     const FT l_eta_common = log_g(eta_common);
-    FT Sm[kMaxModes], l_Sm[kMaxModes];
+    FT l_Sm[kMaxModes];
     FT tmp = FT(0);
+    // (ζ/η_i)^p1 = E0 (2π ρ_w N_i)^p1 with E0 = (ζ γ / sq³)^p1: one exponential for all modes (an empty mode has t1_coef = 0)
+    const FT E0 = exp_full_(ap.p1 * (l_zeta - l_eta_common));
+    const FT T3 = T * T * T;
 #pragma unroll
     for (int i = 0; i < kMaxModes; ++i) {
         if (i >= p.n_modes) break;
-        Sm[i] = k.sm_coef[i] * Tm32;
         l_Sm[i] = k.log_sm_coef[i] + l_T32;
-        const FT Sm2 = Sm[i] * Sm[i];
-        const FT eta = eta_common * rcp_(k.inv_eta_coef[i]);
+        const FT eta = eta_common * k.eta_coef[i];
         // (ζ/η)^p1 and (S_m²/(η+3ζ))^p2
-        const FT t1 = exp_full_(ap.p1 * (l_zeta - (l_eta_common - k.log_inv_eta_coef[i])));
+        const FT t1 = (k.t1_coef[i] == FT(0)) ? FT(0) : E0 * k.t1_coef[i];
         const FT t2 = exp_full_(ap.p2 * (FT(2) * l_Sm[i] - log_g(fma_(FT(3), zeta, eta))));
-        tmp += rcp_(Sm2) * fma_(k.f[i], t1, k.g[i] * t2);
+        tmp += (k.inv_sm2_coef[i] * T3) * fma_(k.f[i], t1, k.g[i] * t2);
     }
-    const FT S_max_ARG = FT(1) / sqrtg_(tmp);
-    const FT r_liq = (N_liq < tk.eps) ? FT(0) : cbrt_full_(rho_air * q_liq / N_liq / k.c43pi_rho_w);
+    const FT S_max_ARG = rsqrtg_(tmp);
+    const FT r_liq = (N_liq < tk.eps) ? FT(0) : cbrtg_(rho_air * q_liq * rcp_(N_liq * k.c43pi_rho_w));
     const FT K_liq = k.four_pi * ap.rho_w * N_liq * r_liq * G * gamma;
     const FT gamma_i = fma_(common_g, Ls, R_v * T * inv_pvs);
-    const FT r_ice = (N_ice < tk.eps) ? FT(0) : cbrt_full_(rho_air * q_ice / N_ice / k.c43pi_rho_i);
+    const FT r_ice = (N_ice < tk.eps) ? FT(0) : cbrtg_(rho_air * q_ice * rcp_(N_ice * k.c43pi_rho_i));
     const FT rhoGi = G_func(tk, k.inv_K_safe, k.inv_D_safe, Ls, inv_pvs_i, ts);
     const FT xi = p_vs * inv_pvs_i;
     const FT K_ice = k.four_pi * N_ice * r_ice * rhoGi * gamma_i;

@@ -245,6 +245,32 @@ CM_HD float sqrtp_(float x) { return sqrtf(x); }
 // guarded form: the faithful 7-instruction sqrtp_ for positive normal arguments, IEEE sqrt (0, subnormal, Inf, NaN, negative) otherwise
 CM_HD double sqrtg_(double x) { return (x > 2.3e-308 && x < 1.7e308) ? sqrtp_(x) : sqrt(x); }
 CM_HD float sqrtg_(float x) { return sqrtf(x); }
+// 1 / sqrt(x): the same coupled iteration read out on its other variable (9 FP64 instructions, < 1.5 ulp) for positive normal
+// arguments, IEEE 1 / sqrt(x) otherwise
+CM_HD double rsqrtg_(double x) {
+    if (!(x > 2.3e-308 && x < 1.7e308)) return 1.0 / sqrt(x);
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+    double r = mk64(hi32(1.0 / std::sqrt(x)), 0);
+#endif
+    double g = x * r;
+    double h = 0.5 * r;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    h = fma(h, e, h);
+    return h + h;
+}
+// x^(1/3) for x >= 0: the 12-instruction cbrtp_ for positive normal arguments, the CUDA libm's otherwise (0, subnormal, Inf, NaN)
+CM_HD double cbrt_pair_(double x, double& rc);
+CM_HD double cbrtg_(double x) {
+    if (!(x > 2.3e-308 && x < 1.7e308)) return cbrt(x);
+    double rc;
+    return cbrt_pair_(x, rc);
+}
 CM_HD float rcp_(float x) { return 1.0f / x; }
 
 // ---- exp: |x| <= 708 (callers' arguments are bounded; see exp_full_ otherwise) ---------------
