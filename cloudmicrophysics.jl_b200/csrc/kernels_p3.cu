@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
     // compacted into a list in shared memory and dealt to the W warps round-robin, one point per warp per iteration, every
     // iteration starting with a block barrier (the SM's warps walk the same loops together: see the launch-shape note).
     // Inputs travel owner -> evaluating warp and the rates travel back through a 14-double slot per point.
-    double* slots = smem + 2 * nq + W * P3Scratch::doubles(nq);                      // [BLOCK][kSlot]
+    // the warp-uniform P3Point of the point a warp is evaluating lives in shared memory, ONE copy per warp: as a local it was 32
+    // identical 280-byte copies per warp in local memory (72 registers cannot hold it), whose write-backs reached DRAM
+    constexpr int kPointDoubles = (sizeof(P3Point) + 7) / 8;
+    double* points = smem + 2 * nq + W * P3Scratch::doubles(nq);                     // [W][kPointDoubles]
+    double* slots = points + W * kPointDoubles;                                      // [BLOCK][kSlot]
     unsigned short* idx = reinterpret_cast<unsigned short*>(slots + BLOCK * kSlot);   // [BLOCK] owners of the listed points
     unsigned char* wantv = reinterpret_cast<unsigned char*>(idx + BLOCK);             // [BLOCK]
     __shared__ int warp_cnt[W];
@@ -278,8 +282,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
                 double pre = 0.0;
                 if (lane < NQ) pre = sl[11 + lane];
                 __syncwarp();
-                P3Point s;
-                p3_point_init(s, a.p, a.k, rho, T, L_ice, N_ice, L_rim, B_rim, logl);
+                P3Point& s = *reinterpret_cast<P3Point*>(points + warp * kPointDoubles);
+                p3_point_init(s, a.p, a.k, rho, T, L_ice, N_ice, L_rim, B_rim, logl);   // every lane stores the same values
+                __syncwarp();
                 P3Rates r;
                 p3_point_rates(s, a.p, a.k, a.tk, a.sk, qx, qw, sc, w_o, L_lcl, N_lcl, L_rai, N_rai, r, true, pre);
                 if (lane == 0) {
@@ -453,7 +458,7 @@ int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, i
     const int nq = a.k.n;
     size_t shmem = sizeof(double) * (size_t)(2 * nq + (BLOCK / 32) * P3Scratch::doubles(nq));
 #if CUMICRO_P3_SYNC
-    shmem += sizeof(double) * BLOCK * kSlot + BLOCK * 3 + 16;
+    shmem += sizeof(double) * BLOCK * kSlot + BLOCK * 3 + 16 + (BLOCK / 32) * ((sizeof(P3Point) + 7) / 8) * sizeof(double);
 #endif
     const int64_t tiles = (n + 31) / 32;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BLOCK / 32 - 1) / (BLOCK / 32), (int64_t)cmh::num_sms() * MINB));
