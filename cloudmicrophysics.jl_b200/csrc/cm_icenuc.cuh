@@ -89,7 +89,8 @@ struct ArgOut {
 };
 
 // AA.max_supersaturation + N_activated_per_mode + M_activated_per_mode          AA:138-324
-template <bool WANT_M>
+// FAST_ERF: erf_fast_ (cm_math.cuh) instead of the CUDA libm's erf for the activated fractions
+template <bool WANT_M, bool FAST_ERF = false>
 CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>& tk, const ArgK<double>& k, double T, double pr,
                       double w, double q_tot, double q_liq, double q_ice, double N_liq, double N_ice) {
     using FT = double;
@@ -158,7 +159,7 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     for (int i = 0; i < kMaxModes; ++i) {
         if (i >= p.n_modes) break;
         const FT lr = l_Sm[i] - l_smax;   // log(S_m / S_max)
-        o.N_act[i] = p.modes[i].N * FT(0.5) * (FT(1) - erf_(k.u_coef[i] * lr));
+        o.N_act[i] = p.modes[i].N * FT(0.5) * (FT(1) - (FAST_ERF ? erf_fast_(k.u_coef[i] * lr) : erf_(k.u_coef[i] * lr)));
         if (WANT_M) o.M_act[i] = p.modes[i].molar_mass_mix * FT(0.5) * erfc_(lr / k.m_fac[i] - k.m_fac[i]);
     }
     return o;

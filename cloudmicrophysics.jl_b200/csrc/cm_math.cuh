@@ -452,14 +452,39 @@ CM_HD double tgamma_(double x) { return tgamma(x); }
 CM_HD float tgamma_(float x) { return tgammaf(x); }
 CM_HD double lgamma_(double x) { return lgamma(x); }
 CM_HD float lgamma_(float x) { return lgammaf(x); }
-// erf: CUDA libm.  A table-driven replacement (x P(x²) below 0.875, 1 - exp_(-x²) R_i(x) on three intervals, degree-14
-// polynomials in shared memory, < 2 units of 2^-53) was built and measured: 60 instructions instead of ~90, but SLOWER in the
-// ARG2000 kernel (config 3: 2.01 -> 2.08 ms; lanes of a warp sit in different pieces and the 15 dependent LDS+DFMA pairs do not
-// overlap the way the libm's register-resident polynomial does), so it was dropped.  Round 2 tried the other direction — ONE
-// branch-free piece, erf(|x|) = 1 - exp_(-|x| Q(|x|)), Q = -log(erfc x)/x as a degree-20 polynomial from the constant bank
-// (2.4e-16 absolute, 35 FP64 + ~35 other instructions) — against the libm's, which on sm_100a is itself ONE branch-free piece
-// (41 FP64 + a MUFU.EX2 + 68 UMOVs that ptxas hoists out of the grid-stride loop): config 3 2.01 -> 1.99 ms, config 5
-// 2.36 -> 2.42 ms.  Not kept: libm's erf is not where these kernels lose time.
+// erf_ is the CUDA libm's — on sm_100a itself ONE branch-free piece (41 FP64 + a MUFU.EX2 + 68 UMOVs that ptxas hoists out of a
+// grid-stride loop).  Replacements were measured three times: round 1, a table-driven one with its polynomials in shared memory
+// (config 3 2.01 -> 2.08 ms: lanes of a warp sit in different pieces, 15 dependent LDS + DFMA pairs): dropped; round 2, erf_fast_
+// below in the grid-stride ARG2000 kernel (2.01 -> 1.99 ms) and in the fused kernel (2.36 -> 2.42 ms): no gain, because the
+// libm's constant moves sat outside those loops; then in the TILE-shaped ARG2000 kernel, whose loop does not hoist them:
+// 1.68 -> 1.57 ms — kept there (arg2000<WANT_M, FAST_ERF = true>), while the fused kernel stays on the libm's (2.22 vs 2.31 ms).
+// erf_fast_: ONE branch-free piece, erf(|x|) = 1 - exp_(-|x| Q(t)), t = |x|/4 - 3/4, |x| clamped to 6 (erfc(6) = 2e-17: the result
+// is 1.0), Q = -log(erfc(x)) / x as a degree-20 polynomial whose coefficients come from the constant bank two per uniform load
+// (tools/gen_math_tables.py: weighted fit of the ABSOLUTE error of erf).  |error| <= 2.5 units of 2^-53 ABSOLUTE — not relative
+// for |x| -> 0, which its use, N (1 - erf(u)) / 2 (AA:256), does not need.  35 FP64 + ~35 other instructions, all inside the
+// loop; the libm's 68 UMOVs are only free where ptxas can hoist them (a grid-stride loop), not in the tile loop: the ARG2000
+// kernel (tile shape) runs this one (config 3: 1.68 -> 1.57 ms), the fused kernel keeps the libm's (2.22 vs 2.31 ms with this).
+#ifdef __CUDACC__
+static __constant__ __align__(16) double cm_erf_q[CM_ERF_DEG + 1 + ((CM_ERF_DEG + 1) & 1)] = CM_ERF_Q_INIT;
+#endif
+static const double cm_erf_q_host[CM_ERF_DEG + 1] = CM_ERF_Q_INIT;
+CM_HD double exp_(double x);
+CM_HD double erf_fast_(double x) {
+#ifdef __CUDA_ARCH__
+    const double* c = cm_erf_q;
+#else
+    const double* c = cm_erf_q_host;
+#endif
+    const double a0 = fabs(x);
+    const double a = (a0 > 6.0) ? 6.0 : a0;   // NaN stays
+    const double t = fma(a, 0.25, -0.75);
+    double q = c[CM_ERF_DEG];
+#pragma unroll
+    for (int i = CM_ERF_DEG - 1; i >= 0; --i) q = fma(q, t, c[i]);
+    const double r = 1.0 - exp_(-(a * q));     // a q in [0, 38.4]
+    const double y = copysign(r, x);
+    return (x != x) ? x : y;
+}
 CM_HD double erf_(double x) { return erf(x); }
 CM_HD float erf_(float x) { return erff(x); }
 CM_HD double erfc_(double x) { return erfc(x); }

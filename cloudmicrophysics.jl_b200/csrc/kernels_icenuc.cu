@@ -9,6 +9,9 @@
 #ifndef CUMICRO_ARG_MINB
 #define CUMICRO_ARG_MINB 6   /* sweep, config 3: 4 -> 3.50 ms, 6 -> 3.09, 8 -> 3.10; tile shape: 5 -> 1.945, 6 -> 1.840, 7 -> 1.894 */
 #endif
+#ifndef CUMICRO_ARG_BLOCK
+#define CUMICRO_ARG_BLOCK 128
+#endif
 #ifndef CUMICRO_ARG_TILED
 #define CUMICRO_ARG_TILED 1   /* config 3: 1.983 (grid-stride register-loading shape) -> 1.840 ms (bulk-copied tiles, cm_launch.cuh) */
 #endif
@@ -133,7 +136,7 @@ struct IceNucRates : IceNucBase {
 //   out: S_max, N_act[MODES], M_act[MODES], J_dep, J_ABIFM, J_hom, Δa_w   (NULL columns skipped)
 template <int MODES, bool WANT_M> struct ArgIceNuc : IceNucBase {
     __device__ __forceinline__ void operator()(const D (&x)[8], D (&y)[1 + 2 * MODES + 4]) const {
-        const ArgOut o = arg2000<WANT_M>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+        const ArgOut o = arg2000<WANT_M, true>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         y[0] = o.S_max;
 #pragma unroll
         for (int i = 0; i < MODES; ++i) {
@@ -213,9 +216,9 @@ int arg_icenuc_launch(const typename PI<FT>::params* p, int64_t n, const FT* con
     out[1 + 2 * MODES + 3] = da_w;
 #if CUMICRO_ARG_TILED
     if (want_m)
-        return launch_pointwise_tiled<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, CUMICRO_ARG_MINB>(
+        return launch_pointwise_tiled<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, CUMICRO_ARG_BLOCK, CUMICRO_ARG_MINB>(
             make_icenuc<FT, ArgIceNuc<MODES, true>>(p, counter), n, in, out, s, "arg_icenuc launch");
-    return launch_pointwise_tiled<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, CUMICRO_ARG_MINB>(
+    return launch_pointwise_tiled<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, CUMICRO_ARG_BLOCK, CUMICRO_ARG_MINB>(
         make_icenuc<FT, ArgIceNuc<MODES, false>>(p, counter), n, in, out, s, "arg_icenuc launch");
 #else
     if (want_m)

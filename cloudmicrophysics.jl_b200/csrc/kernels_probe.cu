@@ -41,6 +41,7 @@ struct MathProbe {
             case 8: y[0] = cm::log1p_pos_(x[0]); break;
             case 9: y[0] = cm::rcbrtp_(x[0]); break;
             case 10: y[0] = cm::divr_(x[0], x[1], cm::rcp_cr_(x[1])); break;
+            case 11: y[0] = cm::erf_fast_(x[0]); break;
             default: y[0] = 0.0;
         }
     }
@@ -56,7 +57,7 @@ int cumicro_probe_math_f64(int fn, int64_t n, const double* x, const double* y, 
     int st = cm::validate_columns<double, 2>(&fn, n, in);
     if (st) return st;
     if ((st = cm::require_outputs<double, 1>(n, o, 1))) return st;
-    if (fn < 0 || fn > 10) return cmh::fail(CUMICRO_E_ARG, "probe_math: unknown function id %d", fn);
+    if (fn < 0 || fn > 11) return cmh::fail(CUMICRO_E_ARG, "probe_math: unknown function id %d", fn);
     return cm::launch_pointwise<double, 2, 1, MathProbe, 256, 2>(MathProbe{fn}, n, in, o, (cudaStream_t)stream,
                                                                  "math probe launch");
 }

@@ -13,5 +13,6 @@ void cmt_sqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i)
 void cmt_divr(const double* x, const double* d, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::divr_(x[i], d[i], cm::rcp_cr_(d[i])); }
 void cmt_log1p_pos(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::log1p_pos_(x[i]); }
 void cmt_rcbrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::rcbrtp_(x[i]); }
+void cmt_erf_fast(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::erf_fast_(x[i]); }
 void cmt_pow(const double* x, const double* p, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = cm::powp_(x[i], p[i]); }
 }

@@ -105,3 +105,17 @@ def test_log1p_of_a_positive_argument(lib):
     y = np.concatenate([np.exp(rng.uniform(-36.7, 18.02, 4000)), 10 ** rng.uniform(-17, -14, 300), [1e-300, 1.0, 2.0 ** -53, 2.0 ** -52]])
     assert _max_ulp(_run(lib, "cmt_log1p_pos", y), y, mp.log1p) < 4.5
 
+
+
+def test_erf_fast_absolute_error(lib):
+    """erf_fast_ = 1 - exp_(-|x| Q): ONE branch-free piece, |error| < 2.5 units of 2^-53 ABSOLUTE (its use, N (1 - erf u) / 2, needs
+    no more: AA:256), odd, saturating at +-1 beyond 6, NaN kept."""
+    mp.mp.dps = 40
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-6.5, 6.5, 4000), rng.uniform(-1, 1, 2000), 10.0 ** rng.uniform(-300, 0, 500), np.linspace(0, 6, 1201)])
+    y = _run(lib, "cmt_erf_fast", x)
+    worst = max(float(abs(mp.mpf(float(b)) - mp.erf(mp.mpf(float(a)))) / mp.mpf(2) ** -53) for a, b in zip(x, y))
+    assert worst < 2.5, worst
+    assert np.array_equal(_run(lib, "cmt_erf_fast", -x), -y)
+    s = _run(lib, "cmt_erf_fast", np.array([0.0, 7.0, -7.0, np.inf, -np.inf, np.nan, 1e300, -0.0]))
+    assert s[0] == 0 and s[1] == 1 and s[2] == -1 and s[3] == 1 and s[4] == -1 and np.isnan(s[5]) and s[6] == 1 and s[7] == 0

@@ -66,6 +66,12 @@ def test_device_erf_log1p_rcbrt_division(built, cuda):
     assert worst < 2.0, worst
     s = _probe(built, cuda, 7, np.array([0.0, 7.0, -7.0, np.inf, -np.inf, np.nan]))
     assert s[0] == 0 and s[1] == 1 and s[2] == -1 and s[3] == 1 and s[4] == -1 and np.isnan(s[5])
+    # erf_fast_ (the ARG2000 kernel's): absolute error, printed so that a failure shows the value
+    yf = _probe(built, cuda, 11, x)
+    worst_f = max(float(abs(mp.mpf(float(b)) - mp.erf(mp.mpf(float(a)))) / mp.mpf(2) ** -53) for a, b in zip(x, yf))
+    assert worst_f < 3.0, worst_f
+    sf = _probe(built, cuda, 11, np.array([0.0, 7.0, -7.0, np.inf, -np.inf, np.nan]))
+    assert sf[0] == 0 and sf[1] == 1 and sf[2] == -1 and sf[3] == 1 and sf[4] == -1 and np.isnan(sf[5])
     v = np.exp(rng.uniform(-36.7, 18.02, 3000))
     assert _max_ulp(_probe(built, cuda, 8, v), v, mp.log1p) < 4.5
     w = 10 ** rng.uniform(-300, 300, 2000)

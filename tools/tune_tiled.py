@@ -12,11 +12,7 @@ sys.path.insert(0, ROOT)
 VAR = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build", "variants")
 VARIANTS = {
     "base": "",
-    "v_tiled8": "-DCUMICRO_1MV_TILED=1",
-    "v_tiled7": "-DCUMICRO_1MV_TILED=1 -DCUMICRO_1MV_MINB=7",
-    "l_tiled1024": "-DCUMICRO_1ML_TILED=1",
-    "l_tiled128x7": "-DCUMICRO_1ML_TILED=1 -DCUMICRO_1ML_BLOCK=128 -DCUMICRO_1ML_MINB=7",
-    "l_tiled512x2": "-DCUMICRO_1ML_TILED=1 -DCUMICRO_1ML_BLOCK=512 -DCUMICRO_1ML_MINB=2",
+    "erf_fast": "-DCM_ERF_FAST=1",
 }
 FILES = ("kernels_1m.cu", "kernels_icenuc.cu", "kernels_fused.cu")
 if len(sys.argv) > 2:
