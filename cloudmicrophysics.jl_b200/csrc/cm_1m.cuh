@@ -160,7 +160,8 @@ template <class FT> CM_DEV void lambda_inverse(const MPSpeciesK<FT>& sk, FT log_
 
 template <class FT>
 CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k,
-                                              FT rho, FT T, FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno) {
+                                              FT rho, FT T, FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno,
+                                              const ThermoShared<FT>* shared = nullptr) {
     const FT e = tk.eps_n;
     const auto& o = p.processes;
     const auto& pp = p.pp;
@@ -175,11 +176,9 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     const FT T_freeze = tk.T_freeze;
 
     // ---- thermodynamic state (shared)
-    const TempState<FT> ts = temp_state(tk, T);
-    const FT p_vs_l = p_sat_liq(tk, ts);
-    const FT p_vs_i = p_sat_ice(tk, ts);
-    const FT inv_pvs_l = rcp_(fmax_(p_vs_l, e));
-    const FT inv_pvs_i = rcp_(fmax_(p_vs_i, e));
+    const ThermoShared<FT> th = shared ? *shared : thermo_shared(tk, T);   // (e = tk.eps_n)
+    const TempState<FT>& ts = th.ts;
+    const FT p_vs_l = th.p_vs_l, p_vs_i = th.p_vs_i, inv_pvs_l = th.inv_pvs_l, inv_pvs_i = th.inv_pvs_i;
     const FT Lv = latent_heat_vapor(tk, T);
     const FT Ls = latent_heat_sublim(tk, T);
     const FT Lf = latent_heat_fusion(tk, T);

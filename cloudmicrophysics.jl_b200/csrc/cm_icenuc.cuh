@@ -92,15 +92,14 @@ struct ArgOut {
 // FAST_ERF: erf_fast_ (cm_math.cuh) instead of the CUDA libm's erf for the activated fractions
 template <bool WANT_M, bool FAST_ERF = false>
 CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>& tk, const ArgK<double>& k, double T, double pr,
-                      double w, double q_tot, double q_liq, double q_ice, double N_liq, double N_ice) {
+                      double w, double q_tot, double q_liq, double q_ice, double N_liq, double N_ice,
+                      const ThermoShared<double>* shared = nullptr) {
     using FT = double;
     ArgOut o;
     const auto& ap = p.arg;
-    const TempState<FT> ts = temp_state(tk, T);
-    const FT p_vs = p_sat_liq(tk, ts);
-    const FT p_vs_i = p_sat_ice(tk, ts);
-    const FT inv_pvs = rcp_(fmax_(p_vs, tk.eps_n));
-    const FT inv_pvs_i = rcp_(fmax_(p_vs_i, tk.eps_n));
+    const ThermoShared<FT> th = shared ? *shared : thermo_shared(tk, T);
+    const TempState<FT>& ts = th.ts;
+    const FT p_vs = th.p_vs_l, p_vs_i = th.p_vs_i, inv_pvs = th.inv_pvs_l, inv_pvs_i = th.inv_pvs_i;
     const FT R_v = tk.R_v;
     const FT R_m = p.tps.R_d * (FT(1) + (k.Rv_over_Rd - FT(1)) * q_tot - k.Rv_over_Rd * (q_liq + q_ice));   // TDI.Rₘ
     const FT cpm = cp_m(tk, q_tot, q_liq, q_ice);

@@ -62,6 +62,22 @@ template <class FT> CM_DEV FT p_sat_liq(const ThermoK<FT>& k, const TempState<FT
 template <class FT> CM_DEV FT p_sat_ice(const ThermoK<FT>& k, const TempState<FT>& s) {
     return k.press_triple * exp_(fma_(k.a_ice, s.log_Tr, k.b_ice * s.dinvT));
 }
+// The temperature-only part of the thermodynamic state that the 1-moment and the ARG2000 / ice-nucleation bodies both start
+// from: computed once per point by the fused kernel (kernels_fused.cu) and handed to both.
+template <class FT> struct ThermoShared {
+    TempState<FT> ts;
+    FT p_vs_l, p_vs_i, inv_pvs_l, inv_pvs_i;   // saturation vapour pressures and 1 / max(p_vs, eps_n)
+};
+template <class FT> CM_DEV ThermoShared<FT> thermo_shared(const ThermoK<FT>& k, FT T) {
+    ThermoShared<FT> s;
+    s.ts = temp_state(k, T);
+    s.p_vs_l = p_sat_liq(k, s.ts);
+    s.p_vs_i = p_sat_ice(k, s.ts);
+    s.inv_pvs_l = rcp_(fmax_(s.p_vs_l, k.eps_n));
+    s.inv_pvs_i = rcp_(fmax_(s.p_vs_i, k.eps_n));
+    return s;
+}
+
 template <class FT> CM_DEV FT latent_heat_vapor(const ThermoK<FT>& k, FT T) { return fma_(k.dcp_vl, T - k.T_0, k.LH_v0); }
 template <class FT> CM_DEV FT latent_heat_sublim(const ThermoK<FT>& k, FT T) { return fma_(k.dcp_vi, T - k.T_0, k.LH_s0); }
 template <class FT> CM_DEV FT latent_heat_fusion(const ThermoK<FT>& k, FT T) { return fma_(k.dcp_li, T - k.T_0, k.LH_f0); }

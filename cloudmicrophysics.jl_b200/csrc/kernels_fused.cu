@@ -102,13 +102,53 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
         auto in = [&](int c) { return (double)stage[buf][c][tid]; };   // rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai
         auto put = [&](int c, double v) { if (a.out[c]) __stcs(a.out[c] + i, (FT)v); };
         // 1-moment tendencies                                         BMT:505-514
+        // the temperature-only thermodynamic state, ONCE for the 1-moment and the ice-nucleation / ARG2000 families, which run
+        // back to back (the 2-moment body has its own log-space form and runs last, so nothing is held across it)
+        ThermoShared<D> th;
+        if (active) th = thermo_shared<D>(f.tk, in(1));
         if (active) {
-            const Src1M<D> r = microphysics_source_terms_1m<D>(f.p1, f.tk, f.k1, in(0), in(1), in(4), in(5), in(6), in(7), in(8));
+            const Src1M<D> r = microphysics_source_terms_1m<D>(f.p1, f.tk, f.k1, in(0), in(1), in(4), in(5), in(6), in(7), in(8), &th);
             double t[4];
             aggregate_tendencies_1m<D>(r, t);
 #pragma unroll
             for (int k = 0; k < 4; ++k) put(k, t[k]);
             diag[0] += in(0) * (t[2] + t[3]);   // 1M precipitation production  Σ ρ (dq_rai + dq_sno)   [kg m^-3 s^-1]
+        }
+        if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
+        // ice-nucleation rates (+ ARG2000 activated number)              IN:92-134, 557-584; AA:138-273
+        if (active) {
+            const double rho = in(0), T = in(1), pr = in(2), w = in(3), q_tot = in(4), q_lcl = in(5), q_icl = in(6), q_rai = in(7),
+                         q_sno = in(8), n_lcl = in(9);
+            double n_act = 0.0;
+            double da_w;
+            if (f.with_activation) {
+                const ArgOut o = arg2000<false>(f.p3, f.tk, f.k3, T, pr, w, q_tot, q_lcl + q_rai, q_icl + q_sno, rho * n_lcl, 0.0, &th);
+                da_w = o.da_w;
+                // Activation needs an updraft: AA.max_supersaturation takes sqrt(alpha w / G) (AA:170-176), a DomainError in the
+                // reference for w < 0 and S_max = 0 for w = 0.  A model slab has downdraft cells: they activate nothing, and they
+                // must not poison the domain sum (NaN from one cell would make the all-reduced diagnostic NaN everywhere).
+                const bool updraft = w > 0.0;
+#pragma unroll
+                for (int m = 0; m < kMaxModes; ++m)
+                    if (m < f.p3.n_modes) {
+                        const double na = o.N_act[m];
+                        n_act += (updraft && na == na && na < 1.7e308) ? na : 0.0;
+                    }
+            } else {
+                const D pl = th.p_vs_l;
+                const D Rm = f.p3.tps.R_d * (1.0 + (f.k3.Rv_over_Rd - 1.0) * q_tot - f.k3.Rv_over_Rd * (q_lcl + q_rai + q_icl + q_sno));
+                const D p_v = (q_tot - (q_lcl + q_rai) - (q_icl + q_sno)) * (pr / (Rm * T)) * f.tk.R_v * T;
+                da_w = p_v / pl - th.p_vs_i / pl;
+            }
+            bool err = false;
+            put(8, deposition_J<D>(f.p3.dust, da_w, f.k3.ln10));
+            put(9, ABIFM_J<D>(f.p3.dust, da_w, f.k3.ln10));
+            double jh = f.p3.hom_linear ? homogeneous_J_linear<D>(f.p3.koop, da_w, f.k3.ln10)
+                                        : homogeneous_J_cubic<D>(f.p3.koop, da_w, f.k3.ln10, err);
+            if (err) jh = __longlong_as_double(0x7ff8000000000000LL);
+            put(10, jh);
+            diag[2] += n_act;                   // activated aerosol number     Σ N_act                  [m^-3]
+            diag[3] += 1.0;                     // points
         }
         if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         // 2-moment warm rain (cloud ice seen by the thermodynamics = q_icl + q_sno)   BMT:820-854
@@ -128,43 +168,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
                 put(7, o.dn_rai_dt);
                 diag[1] += in(0) * o.dq_rai_dt;
             }
-        }
-        if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
-        // ice-nucleation rates (+ ARG2000 activated number)              IN:92-134, 557-584; AA:138-273
-        if (active) {
-            const double rho = in(0), T = in(1), pr = in(2), w = in(3), q_tot = in(4), q_lcl = in(5), q_icl = in(6), q_rai = in(7),
-                         q_sno = in(8), n_lcl = in(9);
-            double n_act = 0.0;
-            double da_w;
-            if (f.with_activation) {
-                const ArgOut o = arg2000<false>(f.p3, f.tk, f.k3, T, pr, w, q_tot, q_lcl + q_rai, q_icl + q_sno, rho * n_lcl, 0.0);
-                da_w = o.da_w;
-                // Activation needs an updraft: AA.max_supersaturation takes sqrt(alpha w / G) (AA:170-176), a DomainError in the
-                // reference for w < 0 and S_max = 0 for w = 0.  A model slab has downdraft cells: they activate nothing, and they
-                // must not poison the domain sum (NaN from one cell would make the all-reduced diagnostic NaN everywhere).
-                const bool updraft = w > 0.0;
-#pragma unroll
-                for (int m = 0; m < kMaxModes; ++m)
-                    if (m < f.p3.n_modes) {
-                        const double na = o.N_act[m];
-                        n_act += (updraft && na == na && na < 1.7e308) ? na : 0.0;
-                    }
-            } else {
-                const TempState<D> ts = temp_state(f.tk, T);
-                const D pl = p_sat_liq(f.tk, ts);
-                const D Rm = f.p3.tps.R_d * (1.0 + (f.k3.Rv_over_Rd - 1.0) * q_tot - f.k3.Rv_over_Rd * (q_lcl + q_rai + q_icl + q_sno));
-                const D p_v = (q_tot - (q_lcl + q_rai) - (q_icl + q_sno)) * (pr / (Rm * T)) * f.tk.R_v * T;
-                da_w = p_v / pl - p_sat_ice(f.tk, ts) / pl;
-            }
-            bool err = false;
-            put(8, deposition_J<D>(f.p3.dust, da_w, f.k3.ln10));
-            put(9, ABIFM_J<D>(f.p3.dust, da_w, f.k3.ln10));
-            double jh = f.p3.hom_linear ? homogeneous_J_linear<D>(f.p3.koop, da_w, f.k3.ln10)
-                                        : homogeneous_J_cubic<D>(f.p3.koop, da_w, f.k3.ln10, err);
-            if (err) jh = __longlong_as_double(0x7ff8000000000000LL);
-            put(10, jh);
-            diag[2] += n_act;                   // activated aerosol number     Σ N_act                  [m^-3]
-            diag[3] += 1.0;                     // points
         }
         if (SYNC) __syncthreads(); else asm volatile("" ::: "memory");
         buf ^= 1;
