@@ -244,3 +244,32 @@ def test_noneq_leaf_methods(built, orc, cuda):
     assert_parity("conv_q_vap_to_q_lcl", got, ref["S_phase_change_vap_lcl"], bound=bound["S_phase_change_vap_lcl"])
     with pytest.raises(TypeError):
         NEQ.conv_q_vap_to_q_icl(CMP.CloudLiquidFormation(), mp, tps, micro, thermo)
+
+
+def test_tile_shape_ragged_sizes_and_misaligned_columns(built, cuda):
+    """The tile launch shape (cm_launch.cuh, pointwise_kernel_tiled): full tiles arrive by bulk copies, the partial last tile and
+    columns that are not 16-byte aligned by guarded scalar loads — a point's bits do not depend on which way it was loaded, on
+    its position in a tile, or on the size of the call."""
+    import torch
+    from cumicro.testing import synthetic_states_1m
+    CMP, BMT = built.CMP, built.BMT
+    mp, tps = CMP.Microphysics1MParams(np.float64), CMP.ThermodynamicsParameters(np.float64)
+    n_big = 128 * 37 + 5
+    st = synthetic_states_1m(n_big + 1, seed=77)
+    full = _dev({k: v[:n_big].copy() for k, v in st.items()}, cuda)
+    for mode in (BMT.Instantaneous(), BMT.InstantaneousVerbose()):
+        ref = _call(built, mode, mp, tps, full)
+        keys = list(ref.keys()) if hasattr(ref, "keys") else ["dq_lcl_dt", "dq_icl_dt", "dq_rai_dt", "dq_sno_dt"]
+        for n in (1, 127, 128, 129, 1000, n_big):
+            sub = _dev({k: v[:n].copy() for k, v in st.items()}, cuda)
+            got = _call(built, mode, mp, tps, sub)
+            for k in keys:
+                assert torch.equal(got[k], ref[k][:n]), (type(mode).__name__, n, k)
+        # one element into a 16-byte aligned allocation: 8-byte aligned only
+        holders = _dev(st, cuda)
+        off = [h[1:] for h in holders]
+        assert all(c.data_ptr() % 16 == 8 for c in off)
+        ref1 = _call(built, mode, mp, tps, _dev({k: v[1:].copy() for k, v in st.items()}, cuda))
+        got1 = _call(built, mode, mp, tps, off)
+        for k in keys:
+            assert torch.equal(got1[k], ref1[k]), (type(mode).__name__, "misaligned", k)

@@ -227,3 +227,41 @@ def test_multi_argument_rates_parity(built, orc, cuda):
     g = G["mohler_rate"]
     got = IN.MohlerDepositionRate(CMP.DustType("DesertDust"), CMP.Mohler2006(np.float64), tps, two(g["Si"]), two(g["T"]), two(g["dSi_dt"]), two(g["N_aer"]))
     assert abs(float(got[0]) / g["DesertDust"] - 1) < 1e-9
+
+
+def test_tile_shape_ragged_sizes_misaligned_columns_and_domain_error_count(built, orc, cuda):
+    """ARG2000 + nucleation rates in the tile launch shape: ragged sizes and 4-byte-aligned Float32 / 8-byte-aligned Float64 columns
+    give the same bits as the aligned full-tile path, and the DomainError counter (Koop's cubic outside its range) counts every point
+    of a partial tile exactly once."""
+    import torch
+    from cumicro.testing import synthetic_states_activation, arg_test_distribution
+    CMP, AA = built.CMP, built.AA
+    for F in (np.float64, np.float32):
+        tps = CMP.ThermodynamicsParameters(F)
+        ap, aip, ad = CMP.AerosolActivationParameters(F), CMP.AirProperties(F), arg_test_distribution("kappa")
+        dust, koop = CMP.DustType("Kaolinite", F) if F is np.float32 else CMP.DustType("Kaolinite"), CMP.Koop2000(F)
+        n_big = 128 * 21 + 77
+        st = synthetic_states_activation(n_big + 1, seed=3, dtype=F)
+        dev = lambda lo, hi: [torch.from_numpy(st[k][lo:hi].copy()).to(cuda) for k in KEYS]
+        ref = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *dev(0, n_big), hom_linear=False)
+        names = ("S_max", "J_dep", "J_ABIFM", "J_hom", "da_w")
+        for n in (1, 127, 129, 1000, n_big):
+            got = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *dev(0, n), hom_linear=False)
+            for k in names:
+                assert torch.equal(torch.nan_to_num(got[k], nan=-7.0), torch.nan_to_num(ref[k][:n], nan=-7.0)), (F.__name__, n, k)
+            for m in range(3):
+                assert torch.equal(got["N_act"][m], ref["N_act"][m][:n]), (F.__name__, n, m)
+            assert int(got["n_domain_errors"].item()) == int(torch.isnan(ref["J_hom"][:n]).sum().item()), (F.__name__, n)
+        if F is np.float64:
+            blk = CMP.pack_icenuc(tps, aps=aip, ap=ap, ad=ad, dust=dust, koop=koop, hom_linear=False)
+            o = orc.arg_icenuc(blk, *[st[k][:1000] for k in KEYS])
+            got = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *dev(0, 1000), hom_linear=False)
+            assert int(got["n_domain_errors"].item()) == o["n_domain_errors"] > 0
+        holders = [torch.from_numpy(st[k]).to(cuda) for k in KEYS]
+        off = [h[1:] for h in holders]
+        assert all(c.data_ptr() % 16 != 0 for c in off)
+        ref1 = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *dev(1, n_big + 1), hom_linear=False)
+        got1 = AA.activation_and_ice_nucleation(ap, ad, aip, tps, dust, koop, *off, hom_linear=False)
+        for k in names:
+            assert torch.equal(torch.nan_to_num(got1[k], nan=-7.0), torch.nan_to_num(ref1[k], nan=-7.0)), (F.__name__, "misaligned", k)
+        assert int(got1["n_domain_errors"].item()) == int(ref1["n_domain_errors"].item())

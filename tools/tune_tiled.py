@@ -12,7 +12,10 @@ sys.path.insert(0, ROOT)
 VAR = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build", "variants")
 VARIANTS = {
     "base": "",
-    "erf_fast": "-DCM_ERF_FAST=1",
+    "f1024": "-DCUMICRO_FUSED_BLOCK=1024",
+    "f768": "-DCUMICRO_FUSED_BLOCK=768",
+    "f640": "-DCUMICRO_FUSED_BLOCK=640",
+    "f960": "-DCUMICRO_FUSED_BLOCK=960",
 }
 FILES = ("kernels_1m.cu", "kernels_icenuc.cu", "kernels_fused.cu")
 if len(sys.argv) > 2:
