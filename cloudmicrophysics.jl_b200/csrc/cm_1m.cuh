@@ -54,6 +54,10 @@ template <class FT> struct OneMK {
     FT frost_c, frost_r0;    // 4 π D_vapor; FT(1e-6)
     // IEEE reciprocals of uniform divisors whose numerators are exact zeros at gated-off points (divr_, cm_math.cuh)
     FT rain_inv_k, snow_inv_k, rain_inv_tau, snow_inv_tau;
+    // default exponent structure (onem_std_exponents): every power of λ⁻¹ the body needs is an integer power of
+    // u_r = (λ_r/r0)^(1/4) resp. u_s = (λ_s/r0)^(1/8) — r0 and the powers of it that go with them
+    FT r0_rai, r0_rai4, sqrt_r0_rai, r0_sno, r0_sno3, sqrt_r0_sno;
+    int std_exponents;
 };
 
 template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::params_1m& p, bool method_is_f32 = false) {
@@ -119,6 +123,13 @@ template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::pa
     k.prescribed_nd_inv = FT(1) / (p.pp.rain_acnv_tau * std::pow(p.pp.rain_acnv_Nc / FT(100000000), p.pp.rain_acnv_alpha));
     k.ice_med = p.cloud_ice.mass.me + p.cloud_ice.mass.dm;
     k.frost_c = 4 * pi * p.aps.D_vapor;
+    k.r0_rai = p.rain.mass.r0; k.r0_rai4 = (k.r0_rai * k.r0_rai) * (k.r0_rai * k.r0_rai); k.sqrt_r0_rai = std::sqrt(k.r0_rai);
+    k.r0_sno = p.snow.mass.r0; k.r0_sno3 = k.r0_sno * k.r0_sno * k.r0_sno; k.sqrt_r0_sno = std::sqrt(k.r0_sno);
+    // rain: me+Δm = 3, ae+ve+Δ = 2.5, ve+Δv = 0.5; snow: me+Δm = 2, ae+ve+Δ = 2.25, ve+Δv = 0.25 (the reference's default 1-moment
+    // parameters): quarter resp. eighth powers only
+    k.std_exponents = (k.accr_rai_x == FT(2.5) && k.sink_x == FT(5.5) && k.vt_rai_x == FT(0.5) && k.rs_rai_delta == FT(3) &&
+                       k.vent_rai_x == FT(0.25) && k.accr_sno_x == FT(2.25) && k.vt_sno_x == FT(0.25) && k.rs_sno_delta == FT(2) &&
+                       k.vent_sno_x == FT(0.125)) ? 1 : 0;
     k.rain_inv_k = FT(1) / p.pp.rain_acnv_k; k.snow_inv_k = FT(1) / p.pp.snow_acnv_k;
     k.rain_inv_tau = FT(1) / p.pp.rain_acnv_tau; k.snow_inv_tau = FT(1) / p.pp.snow_acnv_tau;
     return k;
@@ -150,6 +161,11 @@ template <class FT> CM_DEV FT logistic_function_integral(FT e, FT x, FT x_0, FT 
 
 template <class FT> struct Src1M { FT s[S1M_NSRC]; };
 
+// log λ⁻¹ alone (floored like λ⁻¹ itself)
+template <class FT> CM_DEV void lambda_inverse_log(const MPSpeciesK<FT>& sk, FT log_rho_q, FT log_n0, FT& loglam) {
+    const FT ll = (log_rho_q + sk.log_coef - log_n0) * sk.inv_exp;
+    loglam = !(ll > sk.log_lam_floor) ? sk.log_lam_floor : ll;
+}
 // λ⁻¹ of one species and its logarithm                              CM1:126-152
 template <class FT> CM_DEV void lambda_inverse(const MPSpeciesK<FT>& sk, FT log_rho_q, FT log_n0, FT& lam, FT& loglam) {
     const FT ll = (log_rho_q + sk.log_coef - log_n0) * sk.inv_exp;
@@ -158,7 +174,11 @@ template <class FT> CM_DEV void lambda_inverse(const MPSpeciesK<FT>& sk, FT log_
     lam = floored ? sk.lam_floor : exp_(ll);
 }
 
-template <class FT>
+// STD: the block has the default exponent structure (OneMK::std_exponents, decided on the host): the ~11 real powers of λ_r⁻¹ and
+// λ_s⁻¹ (accretion, sink, fall speeds, collision arms, ventilation) are integer powers of ONE exponential per species,
+// u_r = (λ_r/r0)^(1/4) and u_s = (λ_s/r0)^(1/8), formed by ~16 multiplications instead of 9 further exp_ calls (~24 instructions
+// each).  Same quantities to rounding (a product of <= 26 factors of u: <= 3e-15 relative).
+template <class FT, bool STD = false>
 CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k,
                                               FT rho, FT T, FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno,
                                               const ThermoShared<FT>* shared = nullptr) {
@@ -197,13 +217,30 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
 
     // ---- CM1.size_distr_parameters                                   CM1:375-388
     FT lam_r, ll_r, lam_s, ll_s, lam_i, ll_i;
-    lambda_inverse(k.rai, logp_(rho * q_rai), k.log_n0_rai, lam_r, ll_r);
     lambda_inverse(k.icl, logp_(rho * q_icl), k.log_n0_icl, lam_i, ll_i);
     const FT L_sno = logp_(rho * q_sno);
     const bool has_sno = q_sno > e;
     const FT log_n0_s = has_sno ? fma_(p.snow.nu, L_sno, k.log_mu_sno) : k.log_eps_numerics;
     const FT n0_s = has_sno ? exp_(log_n0_s) : FT(0);                  // CM1.get_n0 (snow)
-    lambda_inverse(k.sno, L_sno, log_n0_s, lam_s, ll_s);
+    // powers of u_r = (λ_r/r0)^(1/4), u_s = (λ_s/r0)^(1/8) (STD only)
+    FT ur2 = 0, ur3 = 0, ur10 = 0, ur16 = 0, ur22 = 0, us2 = 0, us5 = 0, us18 = 0, us24 = 0;
+    if constexpr (STD) {
+        lambda_inverse_log(k.rai, logp_(rho * q_rai), k.log_n0_rai, ll_r);
+        lambda_inverse_log(k.sno, L_sno, log_n0_s, ll_s);
+        const FT ur = exp_(FT(0.25) * (ll_r - k.rai.log_r0));
+        ur2 = ur * ur; ur3 = ur2 * ur;
+        const FT ur4 = ur2 * ur2, ur8 = ur4 * ur4;
+        ur10 = ur8 * ur2; ur16 = ur8 * ur8; ur22 = ur16 * (ur4 * ur2);
+        lam_r = k.r0_rai * ur4;
+        const FT us = exp_(FT(0.125) * (ll_s - k.sno.log_r0));
+        us2 = us * us;
+        const FT us4 = us2 * us2, us8 = us4 * us4, us16 = us8 * us8;
+        us5 = us4 * us; us18 = us16 * us2; us24 = us16 * us8;
+        lam_s = k.r0_sno * us8;
+    } else {
+        lambda_inverse(k.rai, logp_(rho * q_rai), k.log_n0_rai, lam_r, ll_r);
+        lambda_inverse(k.sno, L_sno, log_n0_s, lam_s, ll_s);
+    }
     const FT v0_r = sqrtg_(k.v0_rai_pref * fmax_(p.vel_rain.rho_w * inv_rho - FT(1), FT(0)));   // CM1.get_v0 (rain)
     const FT dl_r = ll_r - k.rai.log_r0, dl_s = ll_s - k.sno.log_r0;   // log(λ⁻¹/r0)
 
@@ -263,8 +300,8 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
     // ---- accretion of cloud condensate by rain / snow                 CM1:491-514, 707-810
     {
         // n0 a0 v0 χa χv λ⁻¹ Γaccr / (r0/λ⁻¹)^x  (without q_clo E)
-        const FT base_r = k.accr_rai_pref * v0_r * lam_r * exp_(k.accr_rai_x * dl_r);
-        const FT base_s = k.accr_sno_pref * n0_s * lam_s * exp_(k.accr_sno_x * dl_s);
+        const FT base_r = k.accr_rai_pref * v0_r * lam_r * (STD ? ur10 : exp_(k.accr_rai_x * dl_r));
+        const FT base_s = k.accr_sno_pref * n0_s * lam_s * (STD ? us18 : exp_(k.accr_sno_x * dl_s));
         const bool rai_on = q_rai > e, sno_on = q_sno > e, lcl_on = q_lcl > e, icl_on = q_icl > e;
         r.s[S1M_ACCR_LCL_RAI] = (o.cloud_liquid_rain_accretion && lcl_on && rai_on) ? q_lcl * pp.e_lcl_rai * base_r : FT(0);
         const FT S_ls = (o.cloud_liquid_snow_accretion && lcl_on && sno_on) ? q_lcl * pp.e_lcl_sno * base_s : FT(0);
@@ -274,21 +311,21 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
         r.s[S1M_ACCR_ICL_RAI] = (o.cloud_ice_rain_accretion && icl_on && rai_on) ? q_icl * pp.e_icl_rai * base_r : FT(0);
         r.s[S1M_ACCR_ICL_SNO] = (o.cloud_ice_snow_accretion && icl_on && sno_on) ? q_icl * pp.e_icl_sno * base_s : FT(0);
         // CM1.accretion_rain_sink                                        CM1:535-561
-        const FT sink = k.sink_pref * inv_rho * v0_r * lam_i * lam_r * exp_(k.sink_x * dl_r);
+        const FT sink = k.sink_pref * inv_rho * v0_r * lam_i * lam_r * (STD ? ur22 : exp_(k.sink_x * dl_r));
         r.s[S1M_ACCR_FREEZE_ICL_RAI] = (o.cloud_ice_rain_accretion && icl_on && rai_on) ? sink : FT(0);
     }
 
     // ---- rain-snow collisions                                          CM1:604-644, 812-867
     if (o.rain_snow_accretion) {
-        const FT v_r = (q_rai > e) ? k.vt_rai_pref * v0_r * exp_(k.vt_rai_x * dl_r) : FT(0);   // CM1.terminal_velocity (Blk1M)
-        const FT v_s = (q_sno > e) ? k.vt_sno_pref * exp_(k.vt_sno_x * dl_s) : FT(0);
+        const FT v_r = (q_rai > e) ? k.vt_rai_pref * v0_r * (STD ? ur2 : exp_(k.vt_rai_x * dl_r)) : FT(0);   // CM1.terminal_velocity (Blk1M)
+        const FT v_s = (q_sno > e) ? k.vt_sno_pref * (STD ? us2 : exp_(k.vt_sno_x * dl_s)) : FT(0);
         const FT dv = v_s - v_r;                                        // IEEE, reference order (cancellation)
         const FT dv_eff = sqrtg_(dv * dv + k.coeff_disp * (v_s * v_s + v_r * v_r));
         const FT common = inv_rho * n0_s * p.rain.n0 * dv_eff;
         // arm (i, j) = (snow, rain):  λ_i³λ_j^(δ+1) ... with δ = rain me+Δm
         const FT dr = k.rs_rai_delta, ds = k.rs_sno_delta;
-        const FT pj_r = exp_((dr + FT(1)) * ll_r);                      // λ_r^(δr+1)
-        const FT pj_s = exp_((ds + FT(1)) * ll_s);                      // λ_s^(δs+1)
+        const FT pj_r = STD ? k.r0_rai4 * ur16 : exp_((dr + FT(1)) * ll_r);   // λ_r^(δr+1)
+        const FT pj_s = STD ? k.r0_sno3 * us24 : exp_((ds + FT(1)) * ll_s);   // λ_s^(δs+1)
         const FT S_rai_sno = common * k.rs_rai_pref * (lam_s * pj_r) *
                              (FT(2) * (lam_s * lam_s) + FT(2) * (dr + FT(1)) * (lam_s * lam_r) + (dr + FT(2)) * (dr + FT(1)) * (lam_r * lam_r));
         const FT S_sno_rai = common * k.rs_sno_pref * (lam_r * pj_s) *
@@ -305,9 +342,9 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
 
     // ---- ventilated diffusional growth / melt                           CM1:915-1139
     // a + b cbrt(Sc) Γvent sqrt(2 v0 χv/ν λ⁻¹) (λ⁻¹/r0)^((ve+Δv)/2)
-    const FT vent_s = fma_(k.vent_sno_b, exp_(fma_(k.vent_sno_x, dl_s, FT(0.5) * ll_s)), k.vent_sno_a);
+    const FT vent_s = fma_(k.vent_sno_b, STD ? k.sqrt_r0_sno * us5 : exp_(fma_(k.vent_sno_x, dl_s, FT(0.5) * ll_s)), k.vent_sno_a);
     if (o.rain_condensation_evaporation) {
-        const FT vent_r = fma_(k.vent_rai_b * sqrtg_(v0_r), exp_(fma_(k.vent_rai_x, dl_r, FT(0.5) * ll_r)), k.vent_rai_a);
+        const FT vent_r = fma_(k.vent_rai_b * sqrtg_(v0_r), STD ? k.sqrt_r0_rai * ur3 : exp_(fma_(k.vent_rai_x, dl_r, FT(0.5) * ll_r)), k.vent_rai_a);
         const FT rate = k.four_pi * p.rain.n0 * inv_rho * S_liq * G_liq * (lam_r * lam_r) * vent_r;
         r.s[S1M_PHASE_VAP_RAI] = cap0_((q_rai > e && S_liq < FT(0)) ? rate : FT(0));
     } else
@@ -340,10 +377,10 @@ template <class FT> CM_DEV void aggregate_tendencies_1m(const Src1M<FT>& r, FT (
 // BMT._linearize + _linearized_implicit_step                               BMT:269-465
 // (IEEE divisions and the reference's operation order throughout: the 2x2 solves
 // subtract nearly equal products.)
-template <class FT>
+template <class FT, bool STD = false>
 CM_DEV void linearized_implicit_step_1m(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k, FT rho, FT T,
                                         FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, FT inv_dt, FT (&out)[4]) {
-    const Src1M<FT> r = microphysics_source_terms_1m<FT>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno);
+    const Src1M<FT> r = microphysics_source_terms_1m<FT, STD>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno);
     const FT* s = r.s;
     const FT q_min = tk.q_min;
     const FT d_lcl = fmax_(q_min, q_lcl), d_icl = fmax_(q_min, q_icl), d_rai = fmax_(q_min, q_rai), d_sno = fmax_(q_min, q_sno);
@@ -417,7 +454,7 @@ template <class FT> __host__ inline LinAvgK<FT> make_linavg_k(FT dt, int nsub) {
 }
 
 // BMT.bulk_microphysics_tendencies(::LinearizedAverage, ...)                 BMT:572-632
-template <class FT>
+template <class FT, bool STD = false>
 CM_DEV void bmt1m_linearized_average(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k, FT rho, FT T,
                                      FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, const LinAvgK<FT>& lk, int nsub, FT Lv_over_cp,
                                      FT Ls_over_cp, FT (&out)[4]) {
@@ -425,7 +462,7 @@ CM_DEV void bmt1m_linearized_average(const typename P<FT>::params_1m& p, const T
     const FT dt_sub = lk.dt_sub;
     for (int it = 0; it < nsub; ++it) {
         FT rt[4];
-        linearized_implicit_step_1m<FT>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, lk.inv_dt_sub, rt);
+        linearized_implicit_step_1m<FT, STD>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, lk.inv_dt_sub, rt);
         q_lcl += rt[0] * dt_sub;
         q_icl += rt[1] * dt_sub;
         q_rai += rt[2] * dt_sub;

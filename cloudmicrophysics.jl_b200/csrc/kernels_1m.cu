@@ -50,16 +50,17 @@ struct OneMBase {
 };
 
 // BMT:505-514 — 7 columns in, 4 tendencies out
-struct OneMInst : OneMBase {
+// STD: the default exponent structure (cm_1m.cuh, OneMK::std_exponents): powers of λ⁻¹ by multiplication
+template <bool STD> struct OneMInst : OneMBase {
     __device__ __forceinline__ void operator()(const D (&x)[7], D (&y)[4]) const {
-        const Src1M<D> r = microphysics_source_terms_1m<D>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6]);
+        const Src1M<D> r = microphysics_source_terms_1m<D, STD>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6]);
         aggregate_tendencies_1m<D>(r, y);
     }
 };
 // BMT:533-543 — 4 tendencies + the 18 source terms
-struct OneMVerbose : OneMBase {
+template <bool STD> struct OneMVerbose : OneMBase {
     __device__ __forceinline__ void operator()(const D (&x)[7], D (&y)[4 + S1M_NSRC]) const {
-        const Src1M<D> r = microphysics_source_terms_1m<D>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6]);
+        const Src1M<D> r = microphysics_source_terms_1m<D, STD>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6]);
         D t[4];
         aggregate_tendencies_1m<D>(r, t);
 #pragma unroll
@@ -69,12 +70,12 @@ struct OneMVerbose : OneMBase {
     }
 };
 // BMT:572-632 — nsub linearised implicit substeps
-struct OneMLinAvg : OneMBase {
+template <bool STD> struct OneMLinAvg : OneMBase {
     LinAvgK<D> lk;
     D Lv_over_cp, Ls_over_cp;
     int nsub;
     __device__ __forceinline__ void operator()(const D (&x)[7], D (&y)[4]) const {
-        bmt1m_linearized_average<D>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], lk, nsub, Lv_over_cp, Ls_over_cp, y);
+        bmt1m_linearized_average<D, STD>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], lk, nsub, Lv_over_cp, Ls_over_cp, y);
     }
 };
 
@@ -98,6 +99,42 @@ template <class FT, class F> F make_1m(const typename P<FT>::params_1m* p) {
     return f;
 }
 
+// one mode with the body variant STD (default exponent structure or not) decided on the host
+template <class FT, bool STD>
+int bmt1m_launch(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT* const (&in)[7], FT dt, int nsub, FT* const (&o4)[4],
+                 FT* const* src18, cudaStream_t s) {
+    if (mode == 0) {
+        using F = OneMInst<STD>;
+#if CUMICRO_1M_TILED
+        return launch_pointwise_tiled<FT, 7, 4, F, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB>(make_1m<FT, F>(p), n, in, o4, s, "bmt1m_inst launch");
+#else
+        return launch_pointwise<FT, 7, 4, F, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB, false>(make_1m<FT, F>(p), n, in, o4, s, "bmt1m_inst launch");
+#endif
+    } else if (mode == 1) {
+        using F = OneMVerbose<STD>;
+        FT* o22[4 + S1M_NSRC];
+        for (int i = 0; i < 4; ++i) o22[i] = o4[i];
+        for (int i = 0; i < S1M_NSRC; ++i) o22[4 + i] = src18[i];
+#if CUMICRO_1MV_TILED
+        return launch_pointwise_tiled<FT, 7, 4 + S1M_NSRC, F, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB>(make_1m<FT, F>(p), n, in, o22, s, "bmt1m_verbose launch");
+#else
+        return launch_pointwise<FT, 7, 4 + S1M_NSRC, F, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB, false>(make_1m<FT, F>(p), n, in, o22, s, "bmt1m_verbose launch");
+#endif
+    } else {
+        using F = OneMLinAvg<STD>;
+        F f = make_1m<FT, F>(p);
+        f.lk = make_linavg_k<D>((D)dt, nsub);
+        f.nsub = nsub;
+        f.Lv_over_cp = f.p.tps.LH_v0 / f.p.tps.cp_d;
+        f.Ls_over_cp = f.p.tps.LH_s0 / f.p.tps.cp_d;
+#if CUMICRO_1ML_TILED
+        return launch_pointwise_tiled<FT, 7, 4, F, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB>(f, n, in, o4, s, "bmt1m_linavg launch");
+#else
+        return launch_pointwise<FT, 7, 4, F, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
+#endif
+    }
+}
+
 template <class FT>
 int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT* const (&in)[7], FT dt, int nsub, FT* const* out4,
                FT* const* src18, void* stream) {
@@ -109,39 +146,21 @@ int bmt1m_impl(int mode, const typename P<FT>::params_1m* p, int64_t n, const FT
     // Verbose: any subset of the 4 + 18 columns (NULL = not wanted) — the stand-alone leaf methods of CM1 / MicrophysicsNonEq
     // (NEQ:110-224, CM1:352-1139) are single source-term columns of this kernel
     if ((st = require_outputs<FT, 4>(n, o4, mode == 1 ? 0 : 4))) return st;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (mode == 0) {
-#if CUMICRO_1M_TILED
-        return launch_pointwise_tiled<FT, 7, 4, OneMInst, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
-#else
-        return launch_pointwise<FT, 7, 4, OneMInst, CUMICRO_1M_BLOCK, CUMICRO_1M_MINB, false>(make_1m<FT, OneMInst>(p), n, in, o4, s, "bmt1m_inst launch");
-#endif
-    } else if (mode == 1) {
-        if (src18 == nullptr) return cmh::fail(CUMICRO_E_NULL, "source-term pointer table is NULL");
-        FT* o22[4 + S1M_NSRC];
-        for (int i = 0; i < 4; ++i) o22[i] = o4[i];
-        for (int i = 0; i < S1M_NSRC; ++i) o22[4 + i] = src18[i];
-#if CUMICRO_1MV_TILED
-        return launch_pointwise_tiled<FT, 7, 4 + S1M_NSRC, OneMVerbose, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
-                                                                                  "bmt1m_verbose launch");
-#else
-        return launch_pointwise<FT, 7, 4 + S1M_NSRC, OneMVerbose, CUMICRO_1M_BLOCK, CUMICRO_1MV_MINB, false>(make_1m<FT, OneMVerbose>(p), n, in, o22, s,
-                                                                                   "bmt1m_verbose launch");
-#endif
-    } else {
+    if (mode == 1 && src18 == nullptr) return cmh::fail(CUMICRO_E_NULL, "source-term pointer table is NULL");
+    if (mode == 2) {
         if (!(dt > FT(0))) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: dt must be > 0");
         if (nsub < 1) return cmh::fail(CUMICRO_E_ARG, "LinearizedAverage: nsub = %d must be >= 1", nsub);
-        OneMLinAvg f = make_1m<FT, OneMLinAvg>(p);
-        f.lk = make_linavg_k<D>((D)dt, nsub);
-        f.nsub = nsub;
-        f.Lv_over_cp = f.p.tps.LH_v0 / f.p.tps.cp_d;
-        f.Ls_over_cp = f.p.tps.LH_s0 / f.p.tps.cp_d;
-#if CUMICRO_1ML_TILED
-        return launch_pointwise_tiled<FT, 7, 4, OneMLinAvg, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB>(f, n, in, o4, s, "bmt1m_linavg launch");
-#else
-        return launch_pointwise<FT, 7, 4, OneMLinAvg, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
-#endif
     }
+    cudaStream_t s = (cudaStream_t)stream;
+    // the default exponent structure (quarter / eighth powers of λ⁻¹ only) runs the body that forms them by multiplication
+    P<D>::params_1m wide;
+    widen(*p, wide);
+    bool std_exponents = make_1m_k<D>(wide, is_f32<FT>()).std_exponents != 0;
+#ifdef CUMICRO_TUNING
+    { static const char* g = getenv("CUMICRO_1M_GENERIC"); if (g && g[0] == '1') std_exponents = false; }
+#endif
+    return std_exponents ? bmt1m_launch<FT, true>(mode, p, n, in, dt, nsub, o4, src18, s)
+                         : bmt1m_launch<FT, false>(mode, p, n, in, dt, nsub, o4, src18, s);
 }
 
 // ---- terminal velocities: (rho, q) -> v -------------------------------------------------------

@@ -65,7 +65,8 @@ template <class FT> struct FusedArgs {
 // copies, double-buffered: the next item streams in while this one is computed) and every family stores its tendencies and
 // accumulates its diagnostic as soon as it is done, so the live register set is that of ONE family at a time and the kernel
 // keeps the occupancy of the single-family kernels.
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB>
+// S1M: the 1-moment block has the default exponent structure (cm_1m.cuh, OneMK::std_exponents): powers of λ⁻¹ by multiplication
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB, bool S1M>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     __shared__ __align__(16) double tab_s[TAB ? kTabDoubles : 2];
     if (TAB) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
         ThermoShared<D> th;
         if (active) th = thermo_shared<D>(f.tk, in(1));
         if (active) {
-            const Src1M<D> r = microphysics_source_terms_1m<D>(f.p1, f.tk, f.k1, in(0), in(1), in(4), in(5), in(6), in(7), in(8), &th);
+            const Src1M<D> r = microphysics_source_terms_1m<D, S1M>(f.p1, f.tk, f.k1, in(0), in(1), in(4), in(5), in(6), in(7), in(8), &th);
             double t[4];
             aggregate_tendencies_1m<D>(r, t);
 #pragma unroll
@@ -212,7 +213,7 @@ template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
     // the block partials: scratch of this (device, stream) — calls in flight on different streams never share it, and work on ONE
     // stream is ordered (the finish kernel of call k has read the partials before the main kernel of call k + 1 writes them)
@@ -221,7 +222,7 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false> 
     if (st) return st;
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
-    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB>;
+    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB, S1M>;
     static bool attr_set = false;   // per instantiation; the attribute is per function and device-wide idempotent
     if (!attr_set || smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -269,6 +270,7 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     a.tab = (spec == 1) ? cmh::w2_table(a.f.p2, a.f.w2k) : nullptr;
     int st;
     if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
+    else if (spec == 1 && a.tab && a.f.k1.std_exponents) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true>(a, n, s, diag);
     else if (spec == 1 && a.tab) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true>(a, n, s, diag);
     else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag);
     else if (spec == 0) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 0>(a, n, s, diag);
