@@ -273,3 +273,37 @@ def test_tile_shape_ragged_sizes_and_misaligned_columns(built, cuda):
         got1 = _call(built, mode, mp, tps, off)
         for k in keys:
             assert torch.equal(got1[k], ref1[k]), (type(mode).__name__, "misaligned", k)
+
+
+def test_non_default_exponent_structure_runs_the_generic_body(built, orc, cuda):
+    """The default 1-moment exponents (quarter / eighth powers of λ⁻¹) run the body that forms every power by multiplication
+    (cm_1m.cuh, STD); any other exponent set runs the generic exp-based body.  Both against the oracle, on the same states, and a
+    block whose only non-default entry is a Δ of 0 must reproduce the default bits (it IS the default structure)."""
+    from cumicro.testing import synthetic_states_1m, assert_parity
+    CMP, BMT = built.CMP, built.BMT
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    n = 1 << 15
+    st = synthetic_states_1m(n, seed=4321)
+    cols = _dev(st, cuda)
+    sets = [{"rain_cross_section_size_relation_coefficient_dela": 0.07, "snow_terminal_velocity_size_relation_coefficient_delv": -0.03},
+            {"rain_mass_size_relation_coefficient_delm": 0.11, "snow_mass_size_relation_coefficient_delm": -0.2,
+             "rain_terminal_velocity_size_relation_coefficient_delv": 0.05}]
+    for ov in sets:
+        mp = CMP.Microphysics1MParams(np.float64, overrides=ov)
+        blk = CMP.pack_1m(mp, tps)
+        out = _call(built, BMT.InstantaneousVerbose(), mp, tps, cols)
+        ref = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="verbose")
+        bnd = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="verbose", bound=True)
+        for k in orc.OUT_1M + orc.SRC_1M:
+            rep = assert_parity(k, out[k].cpu().numpy(), ref[k], bound=bnd[k])
+            assert rep["max_rel"] <= 1e-12, (ov, k, rep)
+        la = _call(built, BMT.LinearizedAverage(), mp, tps, cols, Δt=60.0, nsub=2)
+        rl = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="linearized_average", dt=60.0, nsub=2)
+        bl = orc.bmt1m(blk, *[st[k] for k in KEYS], mode="linearized_average", dt=60.0, nsub=2, bound=True)
+        for k in orc.OUT_1M:
+            rep = assert_parity("linavg " + k, la[k].cpu().numpy(), rl[k], bound=bl[k])
+            assert rep["max_rel"] <= 1e-12, (ov, k, rep)
+    base = _call(built, BMT.Instantaneous(), CMP.Microphysics1MParams(np.float64), tps, cols)
+    same = _call(built, BMT.Instantaneous(), CMP.Microphysics1MParams(np.float64, overrides={"rain_mass_size_relation_coefficient_delm": 0.0}), tps, cols)
+    for k in orc.OUT_1M:
+        assert np.array_equal(base[k].cpu().numpy(), same[k].cpu().numpy())
