@@ -57,6 +57,7 @@ template <class FT> struct OneMK {
     // default exponent structure (onem_std_exponents): every power of λ⁻¹ the body needs is an integer power of
     // u_r = (λ_r/r0)^(1/4) resp. u_s = (λ_s/r0)^(1/8) — r0 and the powers of it that go with them
     FT r0_rai, r0_rai4, sqrt_r0_rai, r0_sno, r0_sno3, sqrt_r0_sno;
+    FT inv_cloud_ice_tau;    // 1 / τ_relax of cloud ice
     int std_exponents;
 };
 
@@ -123,6 +124,7 @@ template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::pa
     k.prescribed_nd_inv = FT(1) / (p.pp.rain_acnv_tau * std::pow(p.pp.rain_acnv_Nc / FT(100000000), p.pp.rain_acnv_alpha));
     k.ice_med = p.cloud_ice.mass.me + p.cloud_ice.mass.dm;
     k.frost_c = 4 * pi * p.aps.D_vapor;
+    k.inv_cloud_ice_tau = FT(1) / p.pp.cloud_ice_tau_relax;
     k.r0_rai = p.rain.mass.r0; k.r0_rai4 = (k.r0_rai * k.r0_rai) * (k.r0_rai * k.r0_rai); k.sqrt_r0_rai = std::sqrt(k.r0_rai);
     k.r0_sno = p.snow.mass.r0; k.r0_sno3 = k.r0_sno * k.r0_sno * k.r0_sno; k.sqrt_r0_sno = std::sqrt(k.r0_sno);
     // rain: me+Δm = 3, ae+ve+Δ = 2.5, ve+Δv = 0.5; snow: me+Δm = 2, ae+ve+Δ = 2.25, ve+Δv = 0.25 (the reference's default 1-moment
@@ -256,7 +258,7 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
         const FT dqs = qv_sat_i * fma_(Ls * tk.inv_R_v * ts.inv_T, ts.inv_T, -ts.inv_T);
         const FT inv_gam = cp_air * rcp_(fma_(Ls, dqs, cp_air));      // 1/Γᵢ
         const FT se = qv - qv_sat_i;
-        FT inv_tau_dep = rcp_(pp.cloud_ice_tau_relax);
+        FT inv_tau_dep = k.inv_cloud_ice_tau;
         const FT inv_tau_sub = inv_tau_dep;
         if (o.cloud_ice_formation == CUMICRO_1M_CLOUD_ICE_TEMPERATURE_DEPENDENT) {
             // NEQ.τ_relax (Frostenberg 2023 INP number, monodisperse radius)   NEQ:32-50, IN:250-253

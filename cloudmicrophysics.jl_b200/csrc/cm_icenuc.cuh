@@ -105,12 +105,13 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT cpm = cp_m(tk, q_tot, q_liq, q_ice);
     const FT Lv = latent_heat_vapor(tk, T);
     const FT Ls = latent_heat_sublim(tk, T);
-    const FT rho_air = pr * rcp_(R_m * T);                                   // TDI.air_density
+    const FT inv_Rm = rcp_(R_m);
+    const FT rho_air = pr * (inv_Rm * ts.inv_T);                             // TDI.air_density = p / (R_m T)
     const FT p_v = (q_tot - q_liq - q_ice) * rho_air * R_v * T;
     const FT pv_over_pvs = p_v * inv_pvs;
     o.da_w = pv_over_pvs - p_vs_i * inv_pvs;                                  // CO.a_w_eT - CO.a_w_ice
     const FT G = G_func(tk, k.inv_K_safe, k.inv_D_safe, Lv, inv_pvs, ts) / ap.rho_w;
-    const FT inv_cpm = rcp_(cpm), inv_Rm = rcp_(R_m), inv_p = rcp_(pr);
+    const FT inv_cpm = rcp_(cpm), inv_p = rcp_(pr);
     const FT alpha = pv_over_pvs * (Lv * ap.g * tk.inv_R_v * inv_cpm * ts.inv_T * ts.inv_T - ap.g * inv_Rm * ts.inv_T);
     const FT common_g = pv_over_pvs * R_m * Lv * tk.inv_R_v * inv_cpm * ts.inv_T * inv_p;
     const FT gamma = fma_(common_g, Lv, R_v * T * inv_pvs);
@@ -151,7 +152,7 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT xi = p_vs * inv_pvs_i;
     const FT K_ice = k.four_pi * N_ice * r_ice * rhoGi * gamma_i;
     const FT aw = alpha * w;
-    const FT S_max = S_max_ARG * (aw - K_ice * (xi - FT(1))) / fma_(K_liq + K_ice * xi, S_max_ARG, aw);
+    const FT S_max = S_max_ARG * (aw - K_ice * (xi - FT(1))) * rcp_(fma_(K_liq + K_ice * xi, S_max_ARG, aw));
     o.S_max = clamp0_(S_max);
     const FT l_smax = log_g(o.S_max);   // -Inf when S_max = 0 (libm path): erf(+Inf) = 1 -> N_act = 0   (AA:256)
 #pragma unroll
