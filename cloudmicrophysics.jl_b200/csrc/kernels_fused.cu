@@ -66,7 +66,8 @@ template <class FT> struct FusedArgs {
 // accumulates its diagnostic as soon as it is done, so the live register set is that of ONE family at a time and the kernel
 // keeps the occupancy of the single-family kernels.
 // S1M: the 1-moment block has the default exponent structure (cm_1m.cuh, OneMK::std_exponents): powers of λ⁻¹ by multiplication
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB, bool S1M>
+// ALL_OUT: every output column is wanted (decided at launch): no per-column NULL test in the store sequence
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB, bool S1M, bool ALL_OUT>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     __shared__ __align__(16) double tab_s[TAB ? kTabDoubles : 2];
     if (TAB) {
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
         cp_async_commit();
         cp_async_wait<1>();
         auto in = [&](int c) { return (double)stage[buf][c][tid]; };   // rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai
-        auto put = [&](int c, double v) { if (a.out[c]) __stcs(a.out[c] + i, (FT)v); };
+        auto put = [&](int c, double v) { if (ALL_OUT || a.out[c]) __stcs(a.out[c] + i, (FT)v); };
         // 1-moment tendencies                                         BMT:505-514
         // the temperature-only thermodynamic state, ONCE for the 1-moment and the ice-nucleation / ARG2000 families, which run
         // back to back (the 2-moment body has its own log-space form and runs last, so nothing is held across it)
@@ -213,7 +214,7 @@ template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false, bool ALL_OUT = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
     // the block partials: scratch of this (device, stream) — calls in flight on different streams never share it, and work on ONE
     // stream is ordered (the finish kernel of call k has read the partials before the main kernel of call k + 1 writes them)
@@ -222,7 +223,7 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, 
     if (st) return st;
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
-    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB, S1M>;
+    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB, S1M, ALL_OUT>;
     static bool attr_set = false;   // per instantiation; the attribute is per function and device-wide idempotent
     if (!attr_set || smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -268,8 +269,11 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     if (const char* e = std::getenv("CUMICRO_FUSED_SHAPE")) small_blocks = std::string(e).rfind("128", 0) == 0;
     const int spec = w2k_supported(a.f.p2) ? (a.f.p2.sb.pdf_r.limited ? 1 : 0) : -1;
     a.tab = (spec == 1) ? cmh::w2_table(a.f.p2, a.f.w2k) : nullptr;
+    bool all_out = true;
+    for (int c = 0; c < NOUT; ++c) all_out = all_out && out[c] != nullptr;
     int st;
     if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
+    else if (spec == 1 && a.tab && a.f.k1.std_exponents && all_out) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true>(a, n, s, diag);
     else if (spec == 1 && a.tab && a.f.k1.std_exponents) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true>(a, n, s, diag);
     else if (spec == 1 && a.tab) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true>(a, n, s, diag);
     else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag);

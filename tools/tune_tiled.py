@@ -14,8 +14,9 @@ VARIANTS = {
     "base": "",
     "f1024": "-DCUMICRO_FUSED_BLOCK=1024",
     "f768": "-DCUMICRO_FUSED_BLOCK=768",
-    "f640": "-DCUMICRO_FUSED_BLOCK=640",
-    "f960": "-DCUMICRO_FUSED_BLOCK=960",
+    "f832": "-DCUMICRO_FUSED_BLOCK=832",
+    "1m8": "-DCUMICRO_1M_MINB=8",
+    "1m6": "-DCUMICRO_1M_MINB=6",
 }
 FILES = ("kernels_1m.cu", "kernels_icenuc.cu", "kernels_fused.cu")
 if len(sys.argv) > 2:
