@@ -57,8 +57,8 @@ get_distribution_loglambda_from_prognostic = get_distribution_logλ_from_prognos
 
 
 def _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, want_n, want_m):
-    cols = [ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ]
-    suf, n, dev = check_columns(cols, ["ρₐ", "ρq_ice", "ρn_ice", "ρq_rim", "ρb_rim", "logλ"])
+    cols = [ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ]     # logλ = None: solved in the kernel
+    suf, n, dev = check_columns(cols[:5] + ([logλ] if logλ is not None else []), ["ρₐ", "ρq_ice", "ρn_ice", "ρq_rim", "ρb_rim", "logλ"])
     blk = _block(mp, tps, suf, quad)
     v_n = torch.empty_like(ρₐ) if want_n else None
     v_m = torch.empty_like(ρₐ) if want_m else None
@@ -77,15 +77,17 @@ def ice_terminal_velocity_mass_weighted_from_prognostic(mp, tps, ρₐ, ρq_ice,
     return _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, False, True)[1]
 
 
-def ice_terminal_velocities_from_prognostic(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, *, quad=None):
+def ice_terminal_velocities_from_prognostic(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ=None, *, quad=None):
     """Both weighted velocities from one pass over the quadrature nodes."""
     return _termvel(mp, tps, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, quad, True, True)
 
 
-def process_rates(mp, tps, ρ, T, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ, *, quad=None, which=None):
-    """Stand-alone P3 integrals (BASELINE config 4) -> Tendencies with RATE_NAMES (``which`` selects a subset)."""
+def process_rates(mp, tps, ρ, T, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ=None, *, quad=None, which=None):
+    """Stand-alone P3 integrals (BASELINE config 4) -> Tendencies with RATE_NAMES (``which`` selects a subset).
+    ``logλ=None``: the kernel solves ``get_distribution_logλ_from_prognostic`` itself, one point per thread, before the integrals."""
     cols = [ρ, T, ρ, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ]   # slot 2 (q_tot) is not read
-    suf, n, dev = check_columns(cols, ["ρ", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim", "logλ"])
+    suf, n, dev = check_columns(cols[:11] + ([logλ] if logλ is not None else []),
+                                ["ρ", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim", "logλ"])
     blk = _block(mp, tps, suf, quad)
     names = RATE_NAMES if which is None else tuple(which)
     outs = {k: torch.empty_like(ρ) for k in names}

@@ -15,11 +15,12 @@ OUT = ("dq_lcl_dt", "dn_lcl_dt", "dq_rai_dt", "dn_rai_dt", "dq_ice_dt", "dn_ice_
 
 def bmt_2m_p3(mp, tps, rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ, inpc_log_shift=None, w=None,
               p=None, *, out=None, quad=None):
-    """``w`` and ``p`` only feed the aerosol activation that the reference leaves at zero (BMT:729, 1077-1078)."""
+    """``w`` and ``p`` only feed the aerosol activation that the reference leaves at zero (BMT:729, 1077-1078).
+    ``logλ=None``: the kernel solves ``P3.get_distribution_logλ_from_prognostic`` itself (same bits as the stand-alone solve)."""
     names = ["rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim", "logλ"]
     cols = [rho, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ]
-    allc = cols + ([inpc_log_shift] if inpc_log_shift is not None else [])
-    suf, n, dev = check_columns(allc, names + ["inpc_log_shift"])
+    given = [(c, nm) for c, nm in zip(cols + [inpc_log_shift], names + ["inpc_log_shift"]) if c is not None]
+    suf, n, dev = check_columns([c for c, _ in given], [nm for _, nm in given])
     blk = CMP3.pack_p3(mp, tps, quad=quad)
     if not type(blk).__name__.endswith(suf):
         raise TypeError(f"parameter float type does not match the columns ({suf})")

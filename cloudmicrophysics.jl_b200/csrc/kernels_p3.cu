@@ -50,7 +50,11 @@ template <class FT> struct P3Args {
     FT* out[NOUT_MAX];
     int64_t n;
     int want;
+    int solve_logl;   // the logλ column is NULL: solve it in the kernel, one listed point per thread, before the quantile phase
 };
+
+// P3.get_distribution_logλ_from_prognostic of one point (defined below, with cumicro_p3_logl_*: the same code, the same bits)
+__device__ double p3_solve_logl(const P3K& k, double L_ice, double N_ice, double L_rim, double B_rim, int iters);
 
 // ---- pointwise parts of BMT:898-1083 -------------------------------------------------------------
 // IN.INP_concentration_mean                                                        IN:250-253
@@ -261,6 +265,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
         // ---- the quantile solves of the round's listed points, ONE PER THREAD (a Halley iteration is serial: solved inside the
         // point's pass it kept 6 — velocities: 2 — lanes of the evaluating warp busy and the others waiting)
         __syncthreads();
+        if (a.solve_logl) {   // §8(f)-1: the logλ solve fused into the P3 call (a 10-step Brent search over 72 gamma_inc per step)
+            for (int j = threadIdx.x; j < total; j += BLOCK) {
+                double* sl = slots + idx[j] * kSlot;
+                sl[6] = p3_solve_logl(a.k, sl[2], sl[3], sl[4], sl[5], a.k.brent_iters);
+            }
+            __syncthreads();
+        }
         constexpr int NQ = (MODE == MODE_VEL) ? 2 : 6;
         for (int task = threadIdx.x; task < total * NQ; task += BLOCK) {
             const int j = task / NQ, which = task - j * NQ;
@@ -443,8 +454,9 @@ int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, i
     if (st) return st;
     if (n < 0) return cmh::fail(CUMICRO_E_SIZE, "n = %lld is negative", (long long)n);
     if (!in || !out) return cmh::fail(CUMICRO_E_NULL, "%s: column pointer table is NULL", what);
+    const int logl_col = (MODE == MODE_VEL) ? 5 : 11;   // may be NULL: the kernel then solves logλ itself
     for (int c = 0; c < nin_required; ++c)
-        if (n > 0 && in[c] == nullptr) return cmh::fail(CUMICRO_E_NULL, "%s: input column %d is NULL", what, c);
+        if (n > 0 && in[c] == nullptr && c != logl_col) return cmh::fail(CUMICRO_E_NULL, "%s: input column %d is NULL", what, c);
     if (n == 0) return CUMICRO_OK;
     P3Args<FT> a{};
     widen(*p, a.p);
@@ -455,6 +467,7 @@ int p3_launch(const typename PP3<FT>::type* p, int64_t n, const FT* const* in, i
     for (int c = 0; c < NOUT_MAX; ++c) a.out[c] = (c < nout) ? out[c] : nullptr;
     a.n = n;
     a.want = want;
+    a.solve_logl = (in[logl_col] == nullptr) ? 1 : 0;
     const int nq = a.k.n;
     size_t shmem = sizeof(double) * (size_t)(2 * nq + (BLOCK / 32) * P3Scratch::doubles(nq));
 #if CUMICRO_P3_SYNC
@@ -590,24 +603,24 @@ __device__ inline double p3_logmass_moment(const P3K& k, const P3Thresholds& t, 
 struct P3LogLambda {
     P3K k;
     int iters;   // Brent iterations (reference: 10 / 8)
-    __device__ __forceinline__ void operator()(const double (&x)[4], double (&y)[1]) const {
-        const double L_ice = x[0], N_ice = x[1], L_rim = x[2], B_rim = x[3];
-        const P3Thresholds t = p3_thresholds(k, L_ice, L_rim, B_rim);
-        if (N_ice < k.eps || L_ice < k.eps) { y[0] = -num<double>::inf(); return; }
-        const double target = log_full_(L_ice) - log_full_(N_ice);
-        // shape_problem(logλ) = logLdivN(state, logλ) - target                        P3_size_distribution.jl:211-216, 292
-        auto f = [&](double l) {
-            double mu;
-            const double lse = p3_logmass_moment(k, t, l, 0.0, mu);
-            const double z0 = 0.0 + mu + 1.0;
-            return (lse - (-z0 * l + lgamma_pos_(z0) + 0.0)) - target;
-        };
-        const double lo = 2.0, hi = 17.0;
-        const double f_lo = f(lo), f_hi = f(hi);
-        if (!isfinite(f_lo) || !isfinite(f_hi) || f_lo * f_hi > 0.0) { y[0] = (fabs(f_lo) <= fabs(f_hi)) ? lo : hi; return; }
-        y[0] = brent_fixed(f, lo, hi, f_lo, f_hi, iters);
-    }
+    __device__ __forceinline__ void operator()(const double (&x)[4], double (&y)[1]) const { y[0] = p3_solve_logl(k, x[0], x[1], x[2], x[3], iters); }
 };
+__device__ __noinline__ double p3_solve_logl(const P3K& k, double L_ice, double N_ice, double L_rim, double B_rim, int iters) {
+    const P3Thresholds t = p3_thresholds(k, L_ice, L_rim, B_rim);
+    if (N_ice < k.eps || L_ice < k.eps) return -num<double>::inf();
+    const double target = log_full_(L_ice) - log_full_(N_ice);
+    // shape_problem(logλ) = logLdivN(state, logλ) - target                        P3_size_distribution.jl:211-216, 292
+    auto f = [&](double l) {
+        double mu;
+        const double lse = p3_logmass_moment(k, t, l, 0.0, mu);
+        const double z0 = 0.0 + mu + 1.0;
+        return (lse - (-z0 * l + lgamma_pos_(z0) + 0.0)) - target;
+    };
+    const double lo = 2.0, hi = 17.0;
+    const double f_lo = f(lo), f_hi = f(hi);
+    if (!isfinite(f_lo) || !isfinite(f_hi) || f_lo * f_hi > 0.0) return (fabs(f_lo) <= fabs(f_hi)) ? lo : hi;
+    return brent_fixed(f, lo, hi, f_lo, f_hi, iters);
+}
 
 // P3State thresholds and the mass-weighted mean diameter D_m of (state, logλ)     P3_integral_properties.jl:56-61
 struct P3StateDiag {

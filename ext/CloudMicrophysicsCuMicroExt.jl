@@ -870,7 +870,7 @@ end
 function BMT.bulk_microphysics_tendencies(
     ::BMT.Microphysics2Moment, mp::CMP.Microphysics2MParams{WR, ICE}, tps,
     ρ::Col{FT}, T::Col{FT}, q_tot::Col{FT}, q_lcl::Col{FT}, n_lcl::Col{FT}, q_rai::Col{FT}, n_rai::Col{FT},
-    q_ice::Col{FT}, n_ice::Col{FT}, q_rim::Col{FT}, b_rim::Col{FT}, logλ::Col{FT},
+    q_ice::Col{FT}, n_ice::Col{FT}, q_rim::Col{FT}, b_rim::Col{FT}, logλ::Union{Col{FT}, Nothing},   # nothing: logλ is solved in the kernel (§8(f)-1)
     inpc_log_shift::Union{Col{FT}, Nothing} = nothing,
 ) where {WR, ICE <: CMP.P3IceParams, FT <: FTs}
     ins = (ρ, T, q_tot, q_lcl, n_lcl, q_rai, n_rai, q_ice, n_ice, q_rim, b_rim, logλ)
@@ -1336,6 +1336,7 @@ function P3.get_distribution_logλ_from_prognostic(mp::CMP.Microphysics2MParams{
     return out
 end
 
+# logλ === nothing: the kernel solves get_distribution_logλ_from_prognostic itself (same bits as the stand-alone solve)
 function p3_velocities(mp, tps, ρₐ::Col{FT}, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ; quad = mp.ice.quad) where {FT}
     n = same_length(ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ)
     v_n, v_m = similar(ρₐ), similar(ρₐ)
@@ -1343,7 +1344,7 @@ function p3_velocities(mp, tps, ρₐ::Col{FT}, ρq_ice, ρn_ice, ρq_rim, ρb_r
     GC.@preserve blk begin
         st = ccall((sym(:cumicro_termvel_p3, FT), libcumicro), Cint,
             (Ptr{Cvoid}, Int64, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, Ptr{Cvoid}),
-            blk, n, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, logλ, v_n, v_m, cur_stream())
+            blk, n, ρₐ, ρq_ice, ρn_ice, ρq_rim, ρb_rim, dev(FT, logλ), v_n, v_m, cur_stream())
     end
     check(st)
     return (v_n, v_m)
@@ -1363,7 +1364,7 @@ The stand-alone P3 integrals of one state in one launch (BASELINE config 4): bul
 `ice_melt` (P3_processes.jl:64-94), `ice_self_collection` (:676-712), `bulk_liquid_ice_collision_sources` (:606-655).
 `@assert ρw == psd_r.ρw` of :616 is checked on the host (CUMICRO_E_OPTION -> ArgumentError).
 """
-function p3_process_rates(mp::MP3, tps, cols::Vararg{Col{FT}, 12}; quad = mp.ice.quad) where {FT <: FTs}
+function p3_process_rates(mp::MP3, tps, cols::Vararg{Union{Col{FT}, Nothing}, 12}; quad = mp.ice.quad) where {FT <: FTs}   # cols[12] = logλ may be nothing
     n = same_length(cols...)
     out = ntuple(_ -> similar(cols[1]), 12)
     blk = Ref(pack(FT, mp, tps; quad))

@@ -376,6 +376,9 @@ int cumicro_fused_1m2m_icenuc_f32(const cumicro_params_1m_f32* p1, const cumicro
  * cumicro_termvel_p3_*: ice_terminal_velocity_{number,mass}_weighted_from_prognostic(vel, ρₐ, params, ρq_ice,
  *   ρn_ice, ρq_rim, ρb_rim, logλ; p = 1e-6, quad)                            P3_terminal_velocity.jl:135-173
  *
+ * The logλ column of cumicro_p3_rates_* / cumicro_bmt2m_p3_* (in12[11]) and of cumicro_termvel_p3_* may be NULL: the kernel
+ * then solves get_distribution_logλ_from_prognostic for every ice-bearing point itself (one point per thread, before the
+ * integrals; the same code and bits as cumicro_p3_logl_* with brent_iters = 0) — SURVEY §8(f)-1.
  * cumicro_p3_logl_*: get_distribution_logλ_from_prognostic(params, ρq_ice, ρn_ice, ρq_rim, ρb_rim)
  *   P3_size_distribution.jl:284-334.  brent_iters <= 0 selects the reference's fixed 10 (Float64) / 8 (Float32)
  *   Brent iterations; -Inf for empty ice (:289).

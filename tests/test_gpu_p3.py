@@ -365,3 +365,32 @@ def test_p3_state_and_shared_numerics(built, orc, cuda):
     q_rim = q_ice * rng.uniform(0, 1.2, 20000)
     assert_parity("rime_mass_fraction", P3.rime_mass_fraction(t(q_rim), t(q_ice)).cpu().numpy(), orc.p3_leaf("rime_mass_fraction", q_rim, q_ice), rtol=1e-11)
     assert_parity("rime_density", P3.rime_density(t(q_rim), t(q_ice)).cpu().numpy(), orc.p3_leaf("rime_density", q_rim, q_ice), rtol=1e-11)
+
+
+def test_log_lambda_solved_inside_the_call(built, cuda):
+    """§8(f)-1: with the logλ column NULL the P3 kernels solve get_distribution_logλ_from_prognostic themselves (one listed point per
+    thread, before the quantile phase).  Float64: bit-identical to passing the stand-alone solve's column; Float32: the in-kernel
+    value is not rounded to Float32 on the way, so the results agree to Float32 rounding of logλ's effect."""
+    import torch
+    from cumicro import BMT, CMP, P3
+    from cumicro.testing import synthetic_states_p3
+    n = 5000
+    st = synthetic_states_p3(n, seed=11)
+    mp3, tps = CMP.Microphysics2MParams(np.float64, with_ice=True), CMP.ThermodynamicsParameters(np.float64)
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in st.items()}
+    vol = [d[k] * d["rho"] for k in ("q_ice", "n_ice", "q_rim", "b_rim")]
+    logl = P3.get_distribution_logλ_from_prognostic(mp3, tps, *vol)
+    KP = ("rho", "T", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim")
+    a = P3.process_rates(mp3, tps, *[d[k] for k in KP], logl)
+    b = P3.process_rates(mp3, tps, *[d[k] for k in KP], None)
+    for k in a.keys():
+        assert torch.equal(torch.nan_to_num(a[k], nan=-1.0), torch.nan_to_num(b[k], nan=-1.0)), k
+    va = P3.ice_terminal_velocities_from_prognostic(mp3, tps, d["rho"], *vol, logl)
+    vb = P3.ice_terminal_velocities_from_prognostic(mp3, tps, d["rho"], *vol, None)
+    assert torch.equal(va[0], vb[0]) and torch.equal(va[1], vb[1])
+    cols = [d[k] for k in ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice", "q_rim", "b_rim")]
+    ta = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp3, tps, *cols, logl)
+    tb = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp3, tps, *cols, None)
+    for k in ("dq_ice_dt", "dn_ice_dt", "dq_rim_dt", "db_rim_dt", "dq_rai_dt", "dq_lcl_dt"):
+        assert torch.equal(torch.nan_to_num(ta[k], nan=-1.0), torch.nan_to_num(tb[k], nan=-1.0)), k
+    assert float(a["v_n"].abs().max()) > 0

@@ -128,6 +128,8 @@ ms = timeit(lambda: P3.ice_terminal_velocities_from_prognostic(mp3, tps, d["rho"
 report("P3 ice terminal velocities (number + mass weighted) f64", n4, ms, 64)
 ms = timeit(lambda: P3.process_rates(mp3, tps, *[d[k] for k in KP], logl), reps=2, warm=1)
 report(f"P3 process rates GL(16) f64 2^{int(np.log2(n4))} (config 4; {ice_frac:.2f} of the points ice-bearing)", n4, ms, 192)
+ms = timeit(lambda: P3.process_rates(mp3, tps, *[d[k] for k in KP], None), reps=2, warm=1)
+report("P3 process rates with the logλ solve inside the call (logλ column NULL)", n4, ms, 184)
 # CPU port of the same integrals on a bounded sample (all host cores), for the GPU/CPU ratio quoted in DESIGN.md
 from oracle import oracle as orc  # noqa: E402
 orc.set_num_threads(os.cpu_count() or 1)
