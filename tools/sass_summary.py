@@ -14,10 +14,13 @@ KERNELS = [  # (object, regex on the mangled name, label)
     # the launch bmt2m_warm_impl makes for a default-structure limited-PSD block with all four outputs: BLOCK 128, MINB 6, ALL_OUT, PPT 1, TAB
     ("kernels_2m.o", r"warm2m_tile_kernelIdLi7ELi1ELi128ELi6ELb1ELi1ELb1E", "2m_warm_f64"),
     ("kernels_2m.o", r"warm2m_tile_kernelIfLi7ELi1ELi128ELi6ELb1ELi1ELb1E", "2m_warm_f32"),
-    ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMInstELb0", "1m_inst_f64"),
-    ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMLinAvgELb0", "1m_linavg_f64"),
-    ("kernels_icenuc.o", r"pointwise_kernelIfLi8ELi11E.*ArgIceNucILi3ELb0EEELb0", "arg_icenuc_f32"),
-    ("kernels_fused.o", r"fused_kernelIdLi896ELi1ELb0ELi1ELb1E", "fused_f64"),
+    # 1M Instantaneous: tile shape, default exponent structure (STD), 128x7, ALL_OUT
+    ("kernels_1m.o", r"pointwise_kernel_tiledIdLi7ELi4E.*OneMInstILb1EEELi128ELi7ELb1E", "1m_inst_f64"),
+    ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMLinAvgILb1EEELb0", "1m_linavg_f64"),
+    # config 3: tile shape, 3 modes, no M_act, 128x6, ALL_OUT
+    ("kernels_icenuc.o", r"pointwise_kernel_tiledIfLi8ELi11E.*ArgIceNucILi3ELb0EEELi128ELi6ELb1E", "arg_icenuc_f32"),
+    # config 5: 896x1, SPEC 1, TAB, S1M, ALL_OUT
+    ("kernels_fused.o", r"fused_kernelIdLi896ELi1ELb0ELi1ELb1ELb1ELb1E", "fused_f64"),
     ("kernels_p3.o", r"p3_tile_kernelIdLi0", "p3_rates_f64"),
 ]
 FP64 = ("DFMA", "DMUL", "DADD")
