@@ -460,7 +460,8 @@ def main():
         agg_bound_s = max(h2d_bytes * world / agg_h2d, d2h_bytes * world / agg_d2h)
         frac_of_link = (agg_bound_s * args.e2e_steps) / e2e_s
         link_note = ("frac_of_link = time the longer copy leg of ALL ranks needs at the SUM of the ranks' pinned-copy rates, measured while every rank "
-                     "copies in both directions at once / measured e2e time (max over ranks); per-rank rates in `ranks`")
+                     "copies in both directions at once / measured e2e time (max over ranks); per-rank rates in `ranks`; above 1 when the chunked copies of "
+                     "desynchronised ranks contend less for the host memory system than the barrier-aligned microbenchmark does")
     hbm_peak, peak_src = _peaks()
     ri = _roofline_inputs()
     achieved_gbs = BYTES_PER_POINT * n / (kernel_ms * 1e-3) / 1e9
