@@ -21,6 +21,19 @@
 
 namespace cmh {
 // Ventilation tables: one per (device, parameter-block content), built and verified on the host, uploaded once.
+// launch shapes of the generic (non-default structure) 2-moment body and of the 15-column leaves kernel: tile shape or grid-stride
+#ifndef CUMICRO_2MG_TILED
+#define CUMICRO_2MG_TILED 0   /* generic body, 2^24 points: 0.627 ms pipelined grid-stride, 0.622-0.626 tiles: no difference */
+#endif
+#ifndef CUMICRO_2MG_MINB
+#define CUMICRO_2MG_MINB 6
+#endif
+#ifndef CUMICRO_2ML_TILED
+#define CUMICRO_2ML_TILED 1   /* 15 leaf columns, 2^24 points: 1.111 ms grid-stride (128x4) -> 0.622 ms tiles (128x5; x4 0.632, x6 0.627) */
+#endif
+#ifndef CUMICRO_2ML_MINB
+#define CUMICRO_2ML_MINB 5
+#endif
 namespace {
 struct TabEntry {
     int device;
@@ -222,7 +235,11 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
         const double* tab = lim ? w2_table_for<FT>(p, k) : nullptr;
         return lim ? launch_warm2m_tile<FT, 7, 1>(k, tab, n, in, out, s, w) : launch_warm2m_tile<FT, 7, 0>(k, nullptr, n, in, out, s, w);
     }
+#if CUMICRO_2MG_TILED
+    return launch_pointwise_tiled<FT, 7, 4, Warm2MFused<7>, 128, CUMICRO_2MG_MINB>(make_2m<FT, Warm2MFused<7>>(p), n, in, out, s, w);
+#else
     return launch_pointwise<FT, 7, 4, Warm2MFused<7>, 128, 7, false, true>(make_2m<FT, Warm2MFused<7>>(p), n, in, out, s, w);
+#endif
 }
 
 template <class FT>
@@ -236,6 +253,10 @@ int sb2006_leaves_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const
     if (out_tbl == nullptr) return cmh::fail(CUMICRO_E_NULL, "leaf pointer table is NULL");
     FT* out[CUMICRO_SB2006_NLEAF];
     for (int k = 0; k < CUMICRO_SB2006_NLEAF; ++k) out[k] = out_tbl[k];
+#if CUMICRO_2ML_TILED
+    return launch_pointwise_tiled<FT, 7, CUMICRO_SB2006_NLEAF, Warm2MLeaves, 128, CUMICRO_2ML_MINB>(make_2m<FT, Warm2MLeaves>(p), n, in, out,
+                                                                                                  (cudaStream_t)stream, "sb2006_leaves launch");
+#endif
     return launch_pointwise<FT, 7, CUMICRO_SB2006_NLEAF, Warm2MLeaves, 128, 4, false>(make_2m<FT, Warm2MLeaves>(p), n, in, out,
                                                                                      (cudaStream_t)stream, "sb2006_leaves kernel launch");
 }

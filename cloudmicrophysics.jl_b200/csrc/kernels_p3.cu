@@ -35,6 +35,10 @@ using namespace cm;
 #ifndef CUMICRO_P3_SYNC_EVERY
 #define CUMICRO_P3_SYNC_EVERY 1
 #endif
+#ifndef CUMICRO_P3L_BLOCK
+#define CUMICRO_P3L_BLOCK 896   /* the stand-alone logλ solve, 2^22 points: 128x3 19.9 ms, 128x6 17.9, 512x2 15.2, 640x1 16.0, 768x1 15.0, 896x1 14.7, 1024x1 14.8 */
+#define CUMICRO_P3L_MINB 1     /* (one block per SM: the warps walk the ~70 KB solve together, like the main kernel) */
+#endif
 constexpr int BLOCK = CUMICRO_P3_BLOCK;
 constexpr int MINB = CUMICRO_P3_MINB;
 enum { MODE_RATES = 0, MODE_BMT = 1, MODE_VEL = 2 };
@@ -668,7 +672,7 @@ int p3_logl_impl(const typename PP3<FT>::type* p, int64_t n, const FT* L_ice, co
     P3LogLambda f{};
     f.k = make_p3_k(wide, is_f32<FT>());
     f.iters = iters > 0 ? iters : f.k.brent_iters;
-    return launch_pointwise<FT, 4, 1, P3LogLambda, 128, 3, false>(f, n, in, out, (cudaStream_t)stream, "p3_logl kernel launch");
+    return launch_pointwise<FT, 4, 1, P3LogLambda, CUMICRO_P3L_BLOCK, CUMICRO_P3L_MINB, false>(f, n, in, out, (cudaStream_t)stream, "p3_logl kernel launch");
 }
 
 template <class FT>
