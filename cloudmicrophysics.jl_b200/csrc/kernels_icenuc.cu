@@ -6,11 +6,13 @@
 #include "cm_icenuc.cuh"
 #include "cm_launch.cuh"
 
+// config 3 sweeps: grid-stride 128x4 3.50 ms, x6 3.09, x8 3.10 (round 1); tile shape 128x5 1.945, x6 1.840, x7 1.894; with the
+// final body 128x6 1.547, 384x2 1.537, 768x1 1.542, 896x1 1.513 (one block per SM: the 58 KB body overflows the instruction cache)
 #ifndef CUMICRO_ARG_MINB
-#define CUMICRO_ARG_MINB 6   /* sweep, config 3: 4 -> 3.50 ms, 6 -> 3.09, 8 -> 3.10; tile shape: 5 -> 1.945, 6 -> 1.840, 7 -> 1.894 */
+#define CUMICRO_ARG_MINB 1
 #endif
 #ifndef CUMICRO_ARG_BLOCK
-#define CUMICRO_ARG_BLOCK 128
+#define CUMICRO_ARG_BLOCK 896
 #endif
 #ifndef CUMICRO_ARG_TILED
 #define CUMICRO_ARG_TILED 1   /* config 3: 1.983 (grid-stride register-loading shape) -> 1.840 ms (bulk-copied tiles, cm_launch.cuh) */
@@ -222,9 +224,9 @@ int arg_icenuc_launch(const typename PI<FT>::params* p, int64_t n, const FT* con
         make_icenuc<FT, ArgIceNuc<MODES, false>>(p, counter), n, in, out, s, "arg_icenuc launch");
 #else
     if (want_m)
-        return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, CUMICRO_ARG_MINB, false>(
+        return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, true>, 128, 6, false>(
             make_icenuc<FT, ArgIceNuc<MODES, true>>(p, counter), n, in, out, s, "arg_icenuc launch");
-    return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, CUMICRO_ARG_MINB, false>(
+    return launch_pointwise<FT, 8, 1 + 2 * MODES + 4, ArgIceNuc<MODES, false>, 128, 6, false>(
         make_icenuc<FT, ArgIceNuc<MODES, false>>(p, counter), n, in, out, s, "arg_icenuc launch");
 #endif
 }

@@ -12,11 +12,10 @@ sys.path.insert(0, ROOT)
 VAR = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build", "variants")
 VARIANTS = {
     "base": "",
-    "f1024": "-DCUMICRO_FUSED_BLOCK=1024",
-    "f768": "-DCUMICRO_FUSED_BLOCK=768",
-    "f832": "-DCUMICRO_FUSED_BLOCK=832",
-    "1m8": "-DCUMICRO_1M_MINB=8",
-    "1m6": "-DCUMICRO_1M_MINB=6",
+    "arg768x1": "-DCUMICRO_ARG_BLOCK=768 -DCUMICRO_ARG_MINB=1",
+    "arg896x1": "-DCUMICRO_ARG_BLOCK=896 -DCUMICRO_ARG_MINB=1",
+    "arg384x2": "-DCUMICRO_ARG_BLOCK=384 -DCUMICRO_ARG_MINB=2",
+    "1m896x1": "-DCUMICRO_1M_BLOCK=896 -DCUMICRO_1M_MINB=1 -DCUMICRO_1MV_MINB=1",
 }
 FILES = ("kernels_1m.cu", "kernels_icenuc.cu", "kernels_fused.cu")
 if len(sys.argv) > 2:
