@@ -85,11 +85,12 @@ __host__ __device__ __noinline__ inline double pow_pos_(double x, double y) {
 #endif
 constexpr int kP3CfUnroll = P3_CF_UNROLL;
 struct PQ { double P, Q; };
-__host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double lga, int iters) {
+// lx = log x (logp_nl_(x)): a caller that evaluates several orders a at one x passes the logarithm it already has (same bits)
+__host__ __device__ __noinline__ inline PQ gamma_inc_lx_(double a, double x, double lx, double lga, int iters) {
     PQ r;
     if (x <= 0.0) { r.P = 0.0; r.Q = 1.0; return r; }
     if (x == num<double>::inf()) { r.P = 1.0; r.Q = 0.0; return r; }
-    const double factor = exp_nl_(a * logp_nl_(x) - x - lga);
+    const double factor = exp_nl_(a * lx - x - lga);
     if (x < a + 1.0) {
         // Σ_k x^k / (a (a+1) ... (a+k)) = S_K / P_K with S_k = S_{k-1} (a+k) + x^k, P_k = P_{k-1} (a+k): the reference's term
         // recurrence (term *= x / (a+k); sum += term) without its division per term — same sum, rounding-level difference.
@@ -130,6 +131,9 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_(double a, double x, double
         r.P = 1.0 - r.Q;
     }
     return r;
+}
+__host__ __device__ inline PQ gamma_inc_(double a, double x, double lga, int iters) {
+    return gamma_inc_lx_(a, x, (x > 0.0 && x < num<double>::inf()) ? logp_nl_(x) : 0.0, lga, iters);
 }
 
 // ---- UT.gamma_inc_inv: Halley, <= 15 steps with the reference's exits                UT:205-252
@@ -788,12 +792,13 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                 for (int j = 0; j < 4; ++j) {
                     const double alpha = sc.tA[j];
                     const double xs = alpha * Dstar, x1 = alpha * rb1;
+                    const double lxs = (xs > 0.0 && xs < num<double>::inf()) ? logp_nl_(xs) : 0.0;   // one logarithm for the six orders z
                     double a_lo0 = 0.0, a_hi0 = 0.0, a_lo3 = 0.0, a_hi3 = 0.0;
 #pragma unroll 1
                     for (int pi_ = 0; pi_ < 6; ++pi_) {
                         const int g = j * 6 + pi_;
                         const double z = sc.gz[g];
-                        const PQ q = gamma_inc_(z, xs, sc.glg[g], k.gamma_iters);
+                        const PQ q = gamma_inc_lx_(z, xs, lxs, sc.glg[g], k.gamma_iters);
                         // gamma_inc_moment(D_min, Dstar) and (Dstar, D_max)                P3_size_distribution.jl:121-133
                         double m_lo = 0.0, m_hi = 0.0;
                         if (Dstar > rb0) m_lo = sc.gG[g] * fmax_((xs < z + 1.0) ? q.P - sc.gP0[g] : sc.gQ0[g] - q.Q, 0.0);
