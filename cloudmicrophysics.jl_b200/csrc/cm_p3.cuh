@@ -85,12 +85,14 @@ __host__ __device__ __noinline__ inline double pow_pos_(double x, double y) {
 #endif
 constexpr int kP3CfUnroll = P3_CF_UNROLL;
 struct PQ { double P, Q; };
-// lx = log x (logp_nl_(x)): a caller that evaluates several orders a at one x passes the logarithm it already has (same bits)
-__host__ __device__ __noinline__ inline PQ gamma_inc_lx_(double a, double x, double lx, double lga, int iters) {
+// gamma_inc_core_: the series / continued fraction with the prefactor x^a e^-x / Γ(a) given.  A caller that evaluates the orders
+// a, a + 1, a + 2, ... at one x (the closed-form rain integrals: six consecutive orders per velocity term) forms the first
+// prefactor with one exponential (from a logarithm of x it already has: gamma_inc_factor_) and the next ones by
+// factor(a + 1) = factor(a) x / a — Γ(a + 1) = a Γ(a) — instead of five more exponentials; rounding-level differences.
+__host__ __device__ __noinline__ inline PQ gamma_inc_core_(double a, double x, double factor, int iters) {
     PQ r;
     if (x <= 0.0) { r.P = 0.0; r.Q = 1.0; return r; }
     if (x == num<double>::inf()) { r.P = 1.0; r.Q = 0.0; return r; }
-    const double factor = exp_nl_(a * lx - x - lga);
     if (x < a + 1.0) {
         // Σ_k x^k / (a (a+1) ... (a+k)) = S_K / P_K with S_k = S_{k-1} (a+k) + x^k, P_k = P_{k-1} (a+k): the reference's term
         // recurrence (term *= x / (a+k); sum += term) without its division per term — same sum, rounding-level difference.
@@ -132,8 +134,10 @@ __host__ __device__ __noinline__ inline PQ gamma_inc_lx_(double a, double x, dou
     }
     return r;
 }
+__host__ __device__ inline double gamma_inc_factor_(double a, double x, double lx, double lga) { return exp_nl_(a * lx - x - lga); }
 __host__ __device__ inline PQ gamma_inc_(double a, double x, double lga, int iters) {
-    return gamma_inc_lx_(a, x, (x > 0.0 && x < num<double>::inf()) ? logp_nl_(x) : 0.0, lga, iters);
+    const bool ok = x > 0.0 && x < num<double>::inf();
+    return gamma_inc_core_(a, x, ok ? gamma_inc_factor_(a, x, logp_nl_(x), lga) : 0.0, iters);
 }
 
 // ---- UT.gamma_inc_inv: Halley, <= 15 steps with the reference's exits                UT:205-252
@@ -794,11 +798,14 @@ CM_DEV void p3_point_rates(const P3Point& s, const cumicro_params_p3_f64& p, con
                     const double xs = alpha * Dstar, x1 = alpha * rb1;
                     const double lxs = (xs > 0.0 && xs < num<double>::inf()) ? logp_nl_(xs) : 0.0;   // one logarithm for the six orders z
                     double a_lo0 = 0.0, a_hi0 = 0.0, a_lo3 = 0.0, a_hi3 = 0.0;
+                    double fac = 0.0, z_prev = 1.0;
 #pragma unroll 1
                     for (int pi_ = 0; pi_ < 6; ++pi_) {
                         const int g = j * 6 + pi_;
-                        const double z = sc.gz[g];
-                        const PQ q = gamma_inc_lx_(z, xs, lxs, sc.glg[g], k.gamma_iters);
+                        const double z = sc.gz[g];                    // six consecutive orders: z_0, z_0 + 1, ..., z_0 + 5
+                        fac = (pi_ == 0) ? gamma_inc_factor_(z, xs, lxs, sc.glg[g]) : fac * (xs * rcp_(z_prev));
+                        z_prev = z;
+                        const PQ q = gamma_inc_core_(z, xs, fac, k.gamma_iters);
                         // gamma_inc_moment(D_min, Dstar) and (Dstar, D_max)                P3_size_distribution.jl:121-133
                         double m_lo = 0.0, m_hi = 0.0;
                         if (Dstar > rb0) m_lo = sc.gG[g] * fmax_((xs < z + 1.0) ? q.P - sc.gP0[g] : sc.gQ0[g] - q.Q, 0.0);
