@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
     double* slots = points + W * kPointDoubles;                                      // [BLOCK][kSlot]
     unsigned short* idx = reinterpret_cast<unsigned short*>(slots + BLOCK * kSlot);   // [BLOCK] owners of the listed points
     unsigned char* wantv = reinterpret_cast<unsigned char*>(idx + BLOCK);             // [BLOCK]
-    __shared__ int warp_cnt[W];
+    constexpr int kCats = 4;
+    __shared__ int warp_cnt[kCats * W];
     for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < a.n; base += (int64_t)gridDim.x * BLOCK) {
         const int64_t i = base + threadIdx.x;
         const bool valid = i < a.n;
@@ -253,14 +254,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) p3_tile_kernel(const __grid_const
             if (ice_on) want |= P3_WANT_AGG | P3_WANT_COLL | ((x.T > a.tk.T_freeze) ? P3_WANT_MELT : 0);
             want &= a.want;
         }
-        const unsigned mb = __ballot_sync(0xffffffffu, want != 0);
-        if (lane == 0) warp_cnt[warp] = __popc(mb);
+        // The list is ordered by the LENGTH of a point's pass: an unrimed point has 2 non-empty mass-regime segments instead of 4
+        // (half the outer quadrature nodes of every integral), a point without rain skips the closed-form rain integrals and
+        // their root search.  An iteration lasts as long as its slowest warp (the barrier), so iterations made of short points
+        // only are short; mixed in, the short points just wait.
+        const int cat = ((x.L_rim > e && x.B_rim > e) ? 0 : 1) + ((x.L_rai > e && x.N_rai > e) ? 0 : 2);
+        unsigned mbc[kCats];
+#pragma unroll
+        for (int c = 0; c < kCats; ++c) mbc[c] = __ballot_sync(0xffffffffu, want != 0 && cat == c);
+        if (lane < kCats) warp_cnt[lane * W + warp] = __popc(mbc[lane]);
         __syncthreads();   // also: the previous round's slot reads are done
         int offset = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) { const int c = warp_cnt[w]; offset += (w < warp) ? c : 0; total += c; }
+        for (int c = 0; c < kCats; ++c)
+            for (int w = 0; w < W; ++w) {
+                const int cnt = warp_cnt[c * W + w];
+                offset += (c < cat || (c == cat && w < warp)) ? cnt : 0;
+                total += cnt;
+            }
         if (want) {
-            idx[offset + __popc(mb & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
+            idx[offset + __popc(mbc[cat] & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
             wantv[threadIdx.x] = (unsigned char)want;
             double* sl = slots + threadIdx.x * kSlot;
             sl[0] = x.rho; sl[1] = x.T; sl[2] = x.L_ice; sl[3] = x.N_ice; sl[4] = x.L_rim; sl[5] = x.B_rim; sl[6] = x.logl;
