@@ -62,8 +62,8 @@ for s, _ in sorted(merged, key=lambda m: -sum(inst[a][1] for a in m[0])):
 # ---- the largest body by address chunks: where in the kernel the issue slots and the stall samples go
 if len(sys.argv) > 2:
     chunk = int(sys.argv[2])
-    body = max(merged, key=lambda m: len(m[0]))[0]
-    print(f"\nlargest body in chunks of {chunk} SASS instructions: share of all executed instructions | of all stall samples | cm_p3.cuh / kernels line span")
+    body = max(merged, key=lambda m: sum(inst[a][1] for a in m[0]))[0]   # the body that executes the most (the kernel itself)
+    print(f"\nthe busiest body in chunks of {chunk} SASS instructions: share of all executed instructions | of all stall samples | cm_p3.cuh / kernels line span")
     for i in range(0, len(body), chunk):
         s = body[i:i + chunk]
         e = sum(inst[a][1] for a in s)
