@@ -3,13 +3,9 @@
 //
 // A ROW is one (grid point, mode i) pair: the reference builds the feature row with modes 1 and i swapped and asks the machine
 // for the activated fraction of "mode 1".  A block owns the rows of floor(32 / n_modes) consecutive points.  The rows'
-// activations live in shared memory as
-// [unit][row] (a warp reads one unit of 32 rows conflict-free; all threads of a layer read the same [unit][*] line, a broadcast),
-// a thread owns one output unit of a layer and keeps its row accumulators in registers — all 32 rows for a layer at least 129
-// units wide, 32 / G rows when G = 2, 4, 8, 16 groups of threads fit a narrower layer into the block — and the weights stream
-// through L1/L2 as [in][out], out fastest: consecutive threads read consecutive words.  Per input unit a thread issues 1 global
-// load, R / 2 shared 128-bit loads and R DFMAs; the sums run in input order (the order of a plain
-// dot product), in Float64 for both float types.
+// activations live in shared memory as [unit][row]; every dense layer is a small GEMM, Out[32][H] = In[32][K] W[K][H], and runs
+// on the FP64 tensor cores (dense_mma below) — the one GEMM-shaped operation of this library.  Float64 accumulation for both
+// float types; the sums run in the tensor core's order (rounding-level differences from a plain dot product).
 #include <algorithm>
 
 #include "cm_launch.cuh"
@@ -33,7 +29,7 @@ template <class FT> struct EmuArgs {
     FT* N_act[8];
     FT* N_tot;
     int64_t n;        // grid points
-    int max_width;    // widest layer input or output: the activation buffers are [max_width][kRows] each
+    int width_a, width_b;   // the two activation buffers, [width][kRS] each: A holds the features and the outputs of layers 1, 3 (0-based), B those of layers 0, 2
 };
 
 __device__ __forceinline__ double emu_act(int kind, double x) {
@@ -45,52 +41,79 @@ __device__ __forceinline__ double emu_act(int kind, double x) {
     }
 }
 
-// One dense layer of a tile: thread t owns output unit h = t mod H' of the R = 32 / G rows [g R, g R + R), g = t / H' (H' = H for
-// G > 1; for G = 1 a thread walks h = t, t + 256, ...).  W as [K][H], H fastest; activations [unit][32 rows].
-template <class FT, int R>
-__device__ __forceinline__ void dense(const FT* __restrict__ W, const FT* __restrict__ B, const double* __restrict__ in, double* __restrict__ out,
-                                      int K, int H, bool last, int activation) {
-    constexpr int G = kRows / R;
-    const int g = (G == 1) ? 0 : threadIdx.x / H;
-    const int h0 = (G == 1) ? threadIdx.x : threadIdx.x - g * H;
-    if (g >= G) return;
-    const int r0 = g * R;
-    for (int h = h0; h < H; h += (G == 1 ? kThreads : H)) {
-        double acc[R];
-        const double b = (double)__ldg(B + h);
+// One dense layer of a tile on the FP64 tensor cores: Out[32 rows][H] = In[32 rows][K] W[K][H] + b as 8x8x4 warp-level
+// matrix multiply-accumulates (mma.sync.aligned.m8n8k4 f64: the only FP64 tensor-core shape; tcgen05 has no FP64 kind).
+// Fragment coordinates of lane T: A[row = T/4][k = T%4], B[k = T%4][unit = T/4], C[row = T/4][unit = 2 (T%4) + {0, 1}].
+// A warp owns two 8-unit groups per pass (ug, ug + 8) for all four 8-row groups: per step of four input units it loads
+// 4 A fragments (shared memory, [unit][kRS] with kRS = 40: the four k-lanes of an 8-byte fragment load fall into disjoint bank
+// halves) and 2 B fragments (the weights, 64-byte runs through L1/L2, fetched four steps ahead) for 8 MMAs = 2048
+// multiply-adds.  Inputs / units beyond K / H enter as zeros.  The bias seeds the accumulators; hidden layers apply the activation on the way out.
+constexpr int kRS = 40;
+__device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+template <class FT>
+__device__ __forceinline__ void dense_mma(const FT* __restrict__ W, const FT* __restrict__ B, const double* __restrict__ in,
+                                          double* __restrict__ out, int K, int H, bool last, int activation) {
+    constexpr int NW = kThreads / 32, UG = 2, PF = 4;   // unit groups per warp and pass; steps of weights fetched ahead
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int n_ug = (H + 7) >> 3;
+    for (int ug0 = warp; ug0 < n_ug; ug0 += NW * UG) {      // this warp's groups of the pass: ug0, ug0 + NW
+        double acc[UG][4][2];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = b;
-        // weights of U input units are fetched ahead of their multiply-adds (an L1/L2 hit is ~10x the 2 R issue cycles of a unit)
-        constexpr int U = (R >= 32) ? 4 : 8;
-        int k = 0;
-        for (; k + U <= K; k += U) {
-            double wv[U];
+        for (int q = 0; q < UG; ++q) {
+            const int u0 = (ug0 + NW * q) * 8 + 2 * lk;
+            const double b0 = (u0 < H) ? (double)__ldg(B + u0) : 0.0, b1 = (u0 + 1 < H) ? (double)__ldg(B + u0 + 1) : 0.0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) wv[u] = (double)__ldg(W + (size_t)(k + u) * H + h);
+            for (int rg = 0; rg < 4; ++rg) { acc[q][rg][0] = b0; acc[q][rg][1] = b1; }
+        }
+        const bool two = ug0 + NW < n_ug;                    // warp-uniform: the second group exists
+        for (int k0 = 0; k0 < K; k0 += 4 * PF) {
+            // the weights of PF steps first (L1 / L2 latency is ~10 steps of MMAs), then step by step: A fragments + MMAs
+            double bfr[PF][UG];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double2* x2 = reinterpret_cast<const double2*>(in + (k + u) * kRows + r0);
+            for (int st = 0; st < PF; ++st) {
+                const int kk = k0 + 4 * st + lk;
 #pragma unroll
-                for (int r = 0; r < R / 2; ++r) {
-                    const double2 v = x2[r];
-                    acc[2 * r] = fma(wv[u], v.x, acc[2 * r]);
-                    acc[2 * r + 1] = fma(wv[u], v.y, acc[2 * r + 1]);
+                for (int q = 0; q < UG; ++q) {
+                    const int unit = (ug0 + NW * q) * 8 + lr;
+                    bfr[st][q] = (kk < K && unit < H) ? (double)__ldg(W + (size_t)kk * H + unit) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int st = 0; st < PF; ++st) {
+                const int kk = k0 + 4 * st + lk;
+                if (k0 + 4 * st < K) {                       // warp-uniform
+                    double afr[4];
+#pragma unroll
+                    for (int rg = 0; rg < 4; ++rg) afr[rg] = (kk < K) ? in[kk * kRS + rg * 8 + lr] : 0.0;
+#pragma unroll
+                    for (int rg = 0; rg < 4; ++rg) dmma8x8x4(acc[0][rg], afr[rg], bfr[st][0]);
+                    if (two) {
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) dmma8x8x4(acc[1][rg], afr[rg], bfr[st][1]);
+                    }
                 }
             }
         }
-        for (; k < K; ++k) {
-            const double wv = (double)__ldg(W + (size_t)k * H + h);
-            const double2* x2 = reinterpret_cast<const double2*>(in + k * kRows + r0);
 #pragma unroll
-            for (int r = 0; r < R / 2; ++r) {
-                const double2 v = x2[r];
-                acc[2 * r] = fma(wv, v.x, acc[2 * r]);
-                acc[2 * r + 1] = fma(wv, v.y, acc[2 * r + 1]);
+        for (int q = 0; q < UG; ++q) {
+            const int ug = ug0 + NW * q;
+            if (ug < n_ug) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int u = ug * 8 + 2 * lk + e;
+                    if (u < H) {
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) {
+                            const double v = acc[q][rg][e];
+                            out[u * kRS + rg * 8 + lr] = last ? v : emu_act(activation, v);
+                        }
+                    }
+                }
             }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) out[h * kRows + r0 + r] = last ? acc[r] : emu_act(activation, acc[r]);
-        if (G != 1) break;
     }
 }
 
@@ -98,7 +121,7 @@ template <class FT>
 __global__ void __launch_bounds__(kThreads, 2) emu_kernel(const __grid_constant__ EmuArgs<FT> a) {
     extern __shared__ double smem[];
     double* buf0 = smem;
-    double* buf1 = smem + (size_t)a.max_width * kRows;
+    double* buf1 = smem + (size_t)a.width_a * kRS;
     const int nm = a.p.n_modes;
     const int nfeat = 4 * nm + 3;
     const int ppt = kRows / nm;                       // whole points per tile: rows [0, ppt nm) are used, the rest idle
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 2) emu_kernel(const __grid_constant_
                 if (a.p.log_features && logged) x = log(x);
                 x = (x - a.p.feat_mean[f]) * a.p.feat_inv_scale[f];
             }
-            buf0[f * kRows + r] = x;
+            buf0[f * kRS + r] = x;
         }
         __syncthreads();
         // ---- dense layers
@@ -139,16 +162,7 @@ __global__ void __launch_bounds__(kThreads, 2) emu_kernel(const __grid_constant_
             const int H = a.p.width[l];
             const FT* B = W + (size_t)K * H;
             const bool last = l == a.p.n_layers - 1;
-            // narrow layers: the 32 rows are split over G = 2^g thread groups (G H <= 256), each thread keeps 32 / G accumulators
-            int G = 1;
-            while (G < kRows && 2 * G * H <= kThreads) G *= 2;
-            switch (G) {
-                case 1: dense<FT, 32>(W, B, in, out, K, H, last, a.p.activation); break;
-                case 2: dense<FT, 16>(W, B, in, out, K, H, last, a.p.activation); break;
-                case 4: dense<FT, 8>(W, B, in, out, K, H, last, a.p.activation); break;
-                case 8: dense<FT, 4>(W, B, in, out, K, H, last, a.p.activation); break;
-                default: dense<FT, 2>(W, B, in, out, K, H, last, a.p.activation); break;   // G = 16 (and 32: half the groups idle)
-            }
+            dense_mma<FT>(W, B, in, out, K, H, last, a.p.activation);
             __syncthreads();
             W = B + H;
             K = H;
@@ -219,10 +233,14 @@ int emu_launch(const typename PEmu<FT>::type* p, const FT* weights, int64_t n, c
     widen(*p, a.p);
     a.weights = weights; a.T = T; a.p_air = p_air; a.w = w; a.N_tot = N_tot; a.n = n;
     for (int i = 0; i < 8; ++i) a.N_act[i] = (N_act && i < p->n_modes) ? N_act[i] : nullptr;
-    int mw = 4 * p->n_modes + 3;
-    for (int l = 0; l < p->n_layers; ++l) mw = std::max(mw, (int)p->width[l]);
-    a.max_width = mw;
-    const size_t shmem = sizeof(double) * 2 * (size_t)mw * kRows;
+    int wa = 4 * p->n_modes + 3, wb = 1;
+    for (int l = 0; l < p->n_layers; ++l) {
+        if (l & 1) wa = std::max(wa, (int)p->width[l]);
+        else wb = std::max(wb, (int)p->width[l]);
+    }
+    a.width_a = wa;
+    a.width_b = wb;
+    const size_t shmem = sizeof(double) * (size_t)(wa + wb) * kRS;
     auto kern = emu_kernel<FT>;
     if (shmem > 48 * 1024) {
         st = cmh::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem), "cudaFuncSetAttribute");

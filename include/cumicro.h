@@ -317,9 +317,9 @@ int cumicro_arg_icenuc_f32(const cumicro_params_icenuc_f32* p, int64_t n, const 
  * AA.total_N_activated(machine, ...) of ext/EmulatorModelsExt.jl:32-103 for a multilayer-perceptron machine
  * (cumicro_params_emulator_*, cumicro_params.inc): N_act[i][k] = clamp(predict(row_i(k)), 0, 1) * mode_N[i].  The reference's
  * method ignores qₜ, qₗ, qᵢ as well.  `weights`: device buffer of cumicro_emulator_weight_count() values; N_act: HOST array of
- * n_modes device column pointers (any may be NULL); N_tot (may be NULL): their sum in mode order.  Dense layers run as a tiled
- * FP64 matrix product on the CUDA cores (32 rows per block, one output unit per thread); Float32 weights and columns are widened
- * exactly and the result is rounded once. */
+ * n_modes device column pointers (any may be NULL); N_tot (may be NULL): their sum in mode order.  Dense layers run as 8x8x4
+ * FP64 tensor-core matrix multiply-accumulates (32 rows per block); Float32 weights and columns are widened exactly and the
+ * result is rounded once. */
 int64_t cumicro_emulator_weight_count_f64(const cumicro_params_emulator_f64* p);
 int64_t cumicro_emulator_weight_count_f32(const cumicro_params_emulator_f32* p);
 int cumicro_aa_emulated_f64(const cumicro_params_emulator_f64* p, const double* weights, int64_t n, const double* T,

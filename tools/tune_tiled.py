@@ -12,10 +12,11 @@ sys.path.insert(0, ROOT)
 VAR = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build", "variants")
 VARIANTS = {
     "base": "",
-    "arg768x1": "-DCUMICRO_ARG_BLOCK=768 -DCUMICRO_ARG_MINB=1",
-    "arg896x1": "-DCUMICRO_ARG_BLOCK=896 -DCUMICRO_ARG_MINB=1",
-    "arg384x2": "-DCUMICRO_ARG_BLOCK=384 -DCUMICRO_ARG_MINB=2",
-    "1m896x1": "-DCUMICRO_1M_BLOCK=896 -DCUMICRO_1M_MINB=1 -DCUMICRO_1MV_MINB=1",
+    "l896": "-DCUMICRO_1ML_BLOCK=896 -DCUMICRO_1ML_MINB=1",
+    "l768": "-DCUMICRO_1ML_BLOCK=768 -DCUMICRO_1ML_MINB=1",
+    "l640": "-DCUMICRO_1ML_BLOCK=640 -DCUMICRO_1ML_MINB=1",
+    "l512x2": "-DCUMICRO_1ML_BLOCK=512 -DCUMICRO_1ML_MINB=2",
+    "lt896": "-DCUMICRO_1ML_TILED=1 -DCUMICRO_1ML_BLOCK=896 -DCUMICRO_1ML_MINB=1",
 }
 FILES = ("kernels_1m.cu", "kernels_icenuc.cu", "kernels_fused.cu")
 if len(sys.argv) > 2:
