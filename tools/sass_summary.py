@@ -17,11 +17,12 @@ KERNELS = [  # (object, regex on the mangled name, label)
     # 1M Instantaneous: tile shape, default exponent structure (STD), 128x7, ALL_OUT
     ("kernels_1m.o", r"pointwise_kernel_tiledIdLi7ELi4E.*OneMInstILb1EEELi128ELi7ELb1E", "1m_inst_f64"),
     ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMLinAvgILb1EEELb0", "1m_linavg_f64"),
-    # config 3: tile shape, 3 modes, no M_act, 128x6, ALL_OUT
-    ("kernels_icenuc.o", r"pointwise_kernel_tiledIfLi8ELi11E.*ArgIceNucILi3ELb0EEELi128ELi6ELb1E", "arg_icenuc_f32"),
+    # config 3: tile shape, 3 modes, no M_act, 896x1, ALL_OUT
+    ("kernels_icenuc.o", r"pointwise_kernel_tiledIfLi8ELi11E.*ArgIceNucILi3ELb0EEELi896ELi1ELb1E", "arg_icenuc_f32"),
     # config 5: 896x1, SPEC 1, TAB, S1M, ALL_OUT
     ("kernels_fused.o", r"fused_kernelIdLi896ELi1ELb0ELi1ELb1ELb1ELb1E", "fused_f64"),
     ("kernels_p3.o", r"p3_tile_kernelIdLi0", "p3_rates_f64"),
+    ("kernels_emulator.o", r"emu_kernelId", "emulator_f64"),
 ]
 FP64 = ("DFMA", "DMUL", "DADD")
 
@@ -51,7 +52,9 @@ def opcodes(lines):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     summary = ["static SASS opcode counts of the hot kernels (sm_100a, nvcc 12.9, -fmad=false); dynamic counts are in the ncu summaries",
-               "tensor-core / TMA mnemonics (UTCMMA, UTMALDG, ...) are absent by design: nothing on this path is a contraction", ""]
+               "the tile kernels fetch their input tiles with bulk asynchronous copies (UBLKCP.S.G + SYNCS mbarrier waits, one ELECT-ed lane per",
+               "issuer warp); the emulator's dense layers are DMMA.8x8x4 (FP64 tensor cores); tcgen05 / tensor-map TMA mnemonics are absent by",
+               "design: the tendency kernels are pointwise, not contractions, and their tiles are 1-D runs of a column", ""]
     cache = {}
     for obj, pat, label in KERNELS:
         fns = cache.setdefault(obj, functions(obj))
@@ -66,7 +69,7 @@ def main():
         fp64 = sum(h[k] for k in FP64)
         summary.append(f"{label}: {total} instructions, {fp64} FP64 arithmetic (DFMA {h['DFMA']}, DMUL {h['DMUL']}, DADD {h['DADD']}), "
                        f"DSETP {h['DSETP']}, MUFU {h['MUFU']}, LDS {h['LDS']}, LDG {h['LDG']}, LDGSTS {h['LDGSTS']}, STG {h['STG']}, "
-                       f"LDL {h['LDL']}, STL {h['STL']}, BRA {h['BRA']}, CALL {h['CALL']}")
+                       f"LDL {h['LDL']}, STL {h['STL']}, BRA {h['BRA']}, CALL {h['CALL']}, UBLKCP {h['UBLKCP']}, DMMA {h['DMMA']}")
         summary.append("    " + "  ".join(f"{k} {v}" for k, v in h.most_common(24)))
         summary.append(f"    {names[0][:150]}")
         if label == "2m_warm_f64":
