@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE streaming family a few times so that `ncu -k regex:<kernel> -c 1 -s 2` can capture it:
-    python tools/profile_driver.py fused|arg|linavg|inst1m|warm2m [log2n]"""
+    python tools/profile_driver.py fused|arg|linavg|inst1m|warm2m|emu [log2n]"""
 import os
 import sys
 
@@ -25,6 +25,17 @@ if fam == "fused":
     blk3 = CMP.pack_icenuc(tps, ad=arg_test_distribution("kappa"), dust=CMP.DustType("Kaolinite"), hom_linear=True)
     o = [torch.empty_like(c[0]) for _ in fused.OUT_NAMES]
     run = lambda: fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *c, out=o)
+elif fam == "emu":   # the trained-emulator methods: the reference docs' 15-250-50-5-1 network, random weights
+    from cumicro.EmulatorModels import EmulatorMLP
+    c = dc(synthetic_states_activation(n), ("T", "p", "w"))
+    rng = np.random.default_rng(0)
+    k, layers = 15, []
+    for h in (250, 50, 5, 1):
+        layers.append((rng.normal(size=(k, h)) / np.sqrt(k), rng.normal(size=h) * 0.1))
+        k = h
+    mach = EmulatorMLP(layers, activation="relu", target_transform=True)
+    ap, ad = CMP.AerosolActivationParameters(np.float64), arg_test_distribution("kappa")
+    run = lambda: AA.N_activated_per_mode(mach, ap, ad, None, tps, *c, None, None, None)
 elif fam == "arg":
     F = np.float32
     c = dc(synthetic_states_activation(n, dtype=F), ("T", "p", "w", "q_tot", "q_liq", "q_ice", "N_liq", "N_ice"))
