@@ -256,14 +256,16 @@ int launch_pointwise_tiled(const F& f, int64_t n, const FT* const (&in)[NIN], FT
     for (int c = 0; c < NOUT; ++c) { a.out[c] = out[c]; all_out = all_out && out[c] != nullptr; }
     auto kern = all_out ? pointwise_kernel_tiled<FT, NIN, NOUT, F, BLOCK, MINB, true> : pointwise_kernel_tiled<FT, NIN, NOUT, F, BLOCK, MINB, false>;
     constexpr size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[all_out]) {
+    // function attributes are per device: a process that drives several GPUs must not rely on a process-wide "already set" flag
+    // for the one that decides whether the launch is legal (the carve-out is a hint and is set once)
+    static bool hint_set[2] = {false, false};
+    if (!hint_set[all_out]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (smem > 40 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return cmh::cuda_status(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-        }
-        attr_set[all_out] = true;
+        hint_set[all_out] = true;
+    }
+    if (smem > 48 * 1024 - 8 * 1024) {   // dynamic + the static math tables (up to 8 KB) against the 48 KB default
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cmh::cuda_status(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     }
 #ifdef CUMICRO_TUNING
     { const char* wv0 = getenv("CUMICRO_WAVES"); if (wv0) waves = atoi(wv0); }

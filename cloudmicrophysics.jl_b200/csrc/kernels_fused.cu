@@ -224,11 +224,9 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, 
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
     auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB, S1M, ALL_OUT>;
-    static bool attr_set = false;   // per instantiation; the attribute is per function and device-wide idempotent
-    if (!attr_set || smem > 48 * 1024) {
+    {   // every launch: function attributes are per device, and the call costs about a microsecond against a millisecond kernel
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cmh::cuda_status(e, "fused: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-        attr_set = true;
     }
     kern<<<blocks, BLOCK, smem, s>>>(a);
     cmh::count_launch();
