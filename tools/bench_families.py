@@ -68,6 +68,21 @@ n1 = 64 ** 3
 c1 = [x[:n1].contiguous() for x in c]
 o1 = [torch.empty_like(c1[0]) for _ in range(4)]
 report("1M Instantaneous f64 64^3 (config 1)", n1, timeit(lambda: BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), m1, mp1, tps, *c1, out=o1), reps=50), 88)
+# the same 50 launches captured in a CUDA graph: at 64^3 points the eager figure is the host's call rate (ctypes + launch), not the kernel
+try:
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), m1, mp1, tps, *c1, out=o1)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(50):
+                BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), m1, mp1, tps, *c1, out=o1)
+    torch.cuda.current_stream().wait_stream(side)
+    report("1M Instantaneous f64 64^3 (config 1), 50 launches replayed from a CUDA graph", n1, timeit(g.replay, reps=20) / 50, 88)
+except Exception as e:  # noqa
+    print(json.dumps({"family": "1M Instantaneous 64^3 CUDA graph", "error": repr(e)[:200]}))
 del c, o
 
 n3 = 1 << 25
