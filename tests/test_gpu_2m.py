@@ -515,3 +515,39 @@ def test_generic_body_with_non_default_structure(built, orc, cuda, limited):
         ref, bound = _oracle_with_bound(orc, CMP.pack_2m_warm(mp, tps), sub)
         for k in OUTS:
             assert_parity(f"generic({b},{c},{d}):{k}", out[k].cpu().numpy(), ref[k], bound=bound[k])
+
+
+def test_entry_points_are_capturable_in_a_cuda_graph(built, cuda):
+    """The C-ABI enqueues on the caller's stream and never synchronises: a host model can capture its microphysics step in a CUDA
+    graph.  (The ventilation table of a parameter block is built and uploaded at the FIRST call for that block, which must be
+    outside the capture; during a capture of a never-seen block the library runs the closed form instead.)"""
+    import torch
+    from cumicro.testing import synthetic_states_2m, synthetic_states_1m
+    CMP, BMT = built.CMP, built.BMT
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    mp2, mp1 = CMP.Microphysics2MParams(np.float64), CMP.Microphysics1MParams(np.float64)
+    n = 100_000
+    s2, s1 = synthetic_states_2m(n, seed=8), synthetic_states_1m(n, seed=9)
+    c2 = [torch.from_numpy(s2[k]).to(cuda) for k in ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai")]
+    c1 = [torch.from_numpy(s1[k]).to(cuda) for k in ("rho", "T", "q_tot", "q_lcl", "q_icl", "q_rai", "q_sno")]
+    o2 = [torch.empty_like(c2[0]) for _ in range(4)]
+    o1 = [torch.empty_like(c1[0]) for _ in range(4)]
+    e2 = BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp2, tps, *c2)          # eager (also: the table is now cached)
+    e1 = BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), BMT.Microphysics1Moment(), mp1, tps, *c1)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            BMT.bulk_microphysics_tendencies(BMT.Microphysics2Moment(), mp2, tps, *c2, out=o2)
+            BMT.bulk_microphysics_tendencies(BMT.Instantaneous(), BMT.Microphysics1Moment(), mp1, tps, *c1, out=o1)
+    torch.cuda.current_stream().wait_stream(side)
+    for o in o1 + o2:
+        o.fill_(float("nan"))
+    g.replay()
+    torch.cuda.synchronize()
+    for k, o in zip(("dq_lcl_dt", "dn_lcl_dt", "dq_rai_dt", "dn_rai_dt"), o2):
+        assert torch.equal(o, e2[k]), k
+    for k, o in zip(("dq_lcl_dt", "dq_icl_dt", "dq_rai_dt", "dq_sno_dt"), o1):
+        assert torch.equal(o, e1[k]), k
