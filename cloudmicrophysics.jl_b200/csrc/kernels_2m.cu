@@ -296,8 +296,13 @@ int rain_evaporation_impl(const typename P<FT>::params_2m_warm* p, int64_t n, co
     int st = validate_columns<FT, 8>(p, n, in);
     if (st) return st;
     if ((st = check_2m_options<FT>(p))) return st;
+#if CUMICRO_2ML_TILED
+    return launch_pointwise_tiled<FT, 8, 4, RainEvap2M, 128, CUMICRO_2ML_MINB>(make_2m<FT, RainEvap2M>(p), n, in, out, (cudaStream_t)stream,
+                                                                 "rain_evaporation_2m kernel launch");
+#else
     return launch_pointwise<FT, 8, 4, RainEvap2M, 128, 4, false>(make_2m<FT, RainEvap2M>(p), n, in, out, (cudaStream_t)stream,
                                                                  "rain_evaporation_2m kernel launch");
+#endif
 }
 
 // ---- terminal velocities: (q, rho, N) -> (vt0, vt1) ---------------------------------------

@@ -542,13 +542,13 @@ int icenuc_f23_impl(const typename PP3<FT>::type* p, int64_t n, const FT* const*
         in[9] = shift;
         F23Functor<true> f{};
         fill(f);
-        return launch_pointwise<FT, 10, 7, F23Functor<true>, 128, 4, false>(f, n, in, out, s, "icenuc_f23 launch");
+        return launch_pointwise_tiled<FT, 10, 7, F23Functor<true>, 128, 5>(f, n, in, out, s, "icenuc_f23 launch");
     }
     const FT* in9c[9];
     for (int c = 0; c < 9; ++c) in9c[c] = in[c];
     F23Functor<false> f{};
     fill(f);
-    return launch_pointwise<FT, 9, 7, F23Functor<false>, 128, 4, false>(f, n, in9c, out, s, "icenuc_f23 launch");
+    return launch_pointwise_tiled<FT, 9, 7, F23Functor<false>, 128, 5>(f, n, in9c, out, s, "icenuc_f23 launch");
 }
 
 // ---- P3.get_distribution_logλ_from_prognostic: one point per thread ------------------------------

@@ -43,10 +43,15 @@ except Exception as e:  # noqa
     res["2M generic body"] = repr(e)[:200]
 mp2 = CMP.Microphysics2MParams(np.float64)
 res["SB2006 leaves (15 columns) 2^24"] = timeit(lambda: CM2.sb2006_process_rates(mp2, tps, *c), reps=5)
+z = torch.zeros_like(c[0])
+res["CM2.rain_evaporation leaf 2^24"] = timeit(lambda: CM2.rain_evaporation(mp2, tps, c[2], c[3], z, c[5], z, c[0], c[0] * c[6], c[1]), reps=5)
 n4 = 1 << 22
 sp = synthetic_states_p3(n4)
 d = {k: torch.from_numpy(v).to(dev) for k, v in sp.items()}
 mp3 = CMP.Microphysics2MParams(np.float64, with_ice=True)
 vol = [d[k] * d["rho"] for k in ("q_ice", "n_ice", "q_rim", "b_rim")]
+from cumicro import IN  # noqa: E402
+KF = ("rho", "T", "q_tot", "q_lcl", "n_lcl", "q_rai", "n_rai", "q_ice", "n_ice")
+res["F23 + Bigg nucleation rates (7 columns) 2^22"] = timeit(lambda: IN.f23_and_bigg_rates(mp3, tps, *[d[k] for k in KF]), reps=5)
 res["P3 logλ solve 2^22"] = timeit(lambda: P3.get_distribution_logλ_from_prognostic(mp3, tps, *vol), reps=5, warm=1)
 print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in res.items()}))
