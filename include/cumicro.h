@@ -22,6 +22,8 @@
  *  - Output pointers documented as "optional" may be NULL (column skipped).
  *  - Return value: 0 ok; <0 API misuse (CUMICRO_E_*); >0 a cudaError_t value.
  *    cumicro_last_error() returns a thread-local message for the last failure.
+ *  - Input domain: finite columns with rho > 0 and T > 0; contents / numbers of any sign (clamped like the reference), zeros and
+ *    sub-eps values anywhere.  A non-finite value or rho = 0 makes THAT cell's outputs unspecified ("Input domain").
  *  - Per-point domain violations (the reference throws DomainError /
  *    AssertionError, IN:558-562, IN:47,73) cannot throw from a kernel: the
  *    output is NaN and a device counter is incremented (see *_status args).
