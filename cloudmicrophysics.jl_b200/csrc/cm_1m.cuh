@@ -58,6 +58,7 @@ template <class FT> struct OneMK {
     // u_r = (λ_r/r0)^(1/4) resp. u_s = (λ_s/r0)^(1/8) — r0 and the powers of it that go with them
     FT r0_rai, r0_rai4, sqrt_r0_rai, r0_sno, r0_sno3, sqrt_r0_sno;
     FT inv_cloud_ice_tau;    // 1 / τ_relax of cloud ice
+    FT rs_r_c1, rs_r_c2, rs_s_c1, rs_s_c2;   // 2 (δ + 1) and (δ + 2)(δ + 1) of the two collision arms (the per-point expressions, hoisted: same bits)
     int std_exponents;
 };
 
@@ -125,6 +126,8 @@ template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::pa
     k.ice_med = p.cloud_ice.mass.me + p.cloud_ice.mass.dm;
     k.frost_c = 4 * pi * p.aps.D_vapor;
     k.inv_cloud_ice_tau = FT(1) / p.pp.cloud_ice_tau_relax;
+    k.rs_r_c1 = FT(2) * (k.rs_rai_delta + FT(1)); k.rs_r_c2 = (k.rs_rai_delta + FT(2)) * (k.rs_rai_delta + FT(1));
+    k.rs_s_c1 = FT(2) * (k.rs_sno_delta + FT(1)); k.rs_s_c2 = (k.rs_sno_delta + FT(2)) * (k.rs_sno_delta + FT(1));
     k.r0_rai = p.rain.mass.r0; k.r0_rai4 = (k.r0_rai * k.r0_rai) * (k.r0_rai * k.r0_rai); k.sqrt_r0_rai = std::sqrt(k.r0_rai);
     k.r0_sno = p.snow.mass.r0; k.r0_sno3 = k.r0_sno * k.r0_sno * k.r0_sno; k.sqrt_r0_sno = std::sqrt(k.r0_sno);
     // rain: me+Δm = 3, ae+ve+Δ = 2.5, ve+Δv = 0.5; snow: me+Δm = 2, ae+ve+Δ = 2.25, ve+Δv = 0.25 (the reference's default 1-moment
@@ -329,9 +332,9 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
         const FT pj_r = STD ? k.r0_rai4 * ur16 : exp_((dr + FT(1)) * ll_r);   // λ_r^(δr+1)
         const FT pj_s = STD ? k.r0_sno3 * us24 : exp_((ds + FT(1)) * ll_s);   // λ_s^(δs+1)
         const FT S_rai_sno = common * k.rs_rai_pref * (lam_s * pj_r) *
-                             (FT(2) * (lam_s * lam_s) + FT(2) * (dr + FT(1)) * (lam_s * lam_r) + (dr + FT(2)) * (dr + FT(1)) * (lam_r * lam_r));
+                             (FT(2) * (lam_s * lam_s) + k.rs_r_c1 * (lam_s * lam_r) + k.rs_r_c2 * (lam_r * lam_r));
         const FT S_sno_rai = common * k.rs_sno_pref * (lam_r * pj_s) *
-                             (FT(2) * (lam_r * lam_r) + FT(2) * (ds + FT(1)) * (lam_r * lam_s) + (ds + FT(2)) * (ds + FT(1)) * (lam_s * lam_s));
+                             (FT(2) * (lam_r * lam_r) + k.rs_s_c1 * (lam_r * lam_s) + k.rs_s_c2 * (lam_s * lam_s));
         const bool both = (q_rai > e) && (q_sno > e);
         const FT a = both ? S_rai_sno : FT(0);
         const FT b = both ? S_sno_rai : FT(0);
