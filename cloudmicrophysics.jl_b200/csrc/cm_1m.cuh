@@ -385,7 +385,9 @@ template <class FT> CM_DEV void aggregate_tendencies_1m(const Src1M<FT>& r, FT (
 template <class FT, bool STD = false>
 CM_DEV void linearized_implicit_step_1m(const typename P<FT>::params_1m& p, const ThermoK<FT>& tk, const OneMK<FT>& k, FT rho, FT T,
                                         FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno, FT inv_dt, FT (&out)[4]) {
-    const Src1M<FT> r = microphysics_source_terms_1m<FT, STD>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno);
+    // the temperature-only thermodynamic state once for the source terms and for q_sat below (same functions: same bits)
+    const ThermoShared<FT> th = thermo_shared(tk, T);
+    const Src1M<FT> r = microphysics_source_terms_1m<FT, STD>(p, tk, k, rho, T, q_tot, q_lcl, q_icl, q_rai, q_sno, &th);
     const FT* s = r.s;
     const FT q_min = tk.q_min;
     const FT d_lcl = fmax_(q_min, q_lcl), d_icl = fmax_(q_min, q_icl), d_rai = fmax_(q_min, q_rai), d_sno = fmax_(q_min, q_sno);
@@ -421,9 +423,9 @@ CM_DEV void linearized_implicit_step_1m(const typename P<FT>::params_1m& p, cons
 
     // inv_dt = RN(1/dt), from the host (uniform)
     // q_sat over liquid / ice at the (unclamped) state                       BMT:409-412
-    const TempState<FT> ts = temp_state(tk, T);
     const FT rRT = rho * tk.R_v * T;
-    const FT q_sat_min = fmin_(div_(p_sat_liq(tk, ts), rRT), div_(p_sat_ice(tk, ts), rRT));
+    const FT r_rRT = rcp_cr_(rRT);   // one correctly rounded reciprocal, two IEEE quotients (divr_, cm_math.cuh)
+    const FT q_sat_min = fmin_(divr_(th.p_vs_l, rRT, r_rRT), divr_(th.p_vs_i, rRT, r_rRT));
     const FT q_v = q_tot - q_lcl - q_icl - q_rai - q_sno;
     const FT e_sum = fmax_(e1 + e2 + e4, tk.eps);   // >= eps > 0; the numerator is an exact zero wherever the air is subsaturated
     const FT alpha = fmin_(FT(1), divr_(clamp0_(q_v - q_sat_min) * inv_dt, e_sum, rcp_cr_(e_sum)));
