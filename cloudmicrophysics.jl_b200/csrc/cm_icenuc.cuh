@@ -28,6 +28,7 @@ template <class FT> struct ArgK {
     FT m_fac[kMaxModes];                            // 3 ln σ_i √2 / 2                   AA:320
     FT inv_K_safe, inv_D_safe, ln10, c43pi_rho_w, c43pi_rho_i, four_pi;
     FT Rv_over_Rd;
+    FT rho_w_rcp;          // correctly rounded 1 / ρ_w: G / ρ_w as an IEEE quotient through divr_ (cm_math.cuh)
 };
 
 template <class FT> __host__ inline ArgK<FT> make_arg_k(const cumicro_params_icenuc_f64& p, bool method_is_f32) {
@@ -57,6 +58,7 @@ template <class FT> __host__ inline ArgK<FT> make_arg_k(const cumicro_params_ice
     k.c43pi_rho_i = FT(4.0 / 3) * pi * p.arg.rho_i;
     k.four_pi = 4 * pi;
     k.Rv_over_Rd = p.tps.R_v / p.tps.R_d;
+    k.rho_w_rcp = rcp_cr_((double)p.arg.rho_w);
     k.log_T_triple = std::log(FT(p.tps.T_triple));
     return k;
 }
@@ -110,7 +112,7 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT p_v = (q_tot - q_liq - q_ice) * rho_air * R_v * T;
     const FT pv_over_pvs = p_v * inv_pvs;
     o.da_w = pv_over_pvs - p_vs_i * inv_pvs;                                  // CO.a_w_eT - CO.a_w_ice
-    const FT G = G_func(tk, k.inv_K_safe, k.inv_D_safe, Lv, inv_pvs, ts) / ap.rho_w;
+    const FT G = divr_(G_func(tk, k.inv_K_safe, k.inv_D_safe, Lv, inv_pvs, ts), ap.rho_w, k.rho_w_rcp);
     const FT inv_cpm = rcp_(cpm), inv_p = rcp_(pr);
     const FT alpha = pv_over_pvs * (Lv * ap.g * tk.inv_R_v * inv_cpm * ts.inv_T * ts.inv_T - ap.g * inv_Rm * ts.inv_T);
     const FT common_g = pv_over_pvs * R_m * Lv * tk.inv_R_v * inv_cpm * ts.inv_T * inv_p;
