@@ -62,6 +62,28 @@ template <class FT> struct OneMK {
     int std_exponents;
 };
 
+// The reference's default process options (Microphysics1MOptions.jl: every process on, snow deposition AND sublimation): with STD
+// they are compile-time constants — no option loads, no option branches.
+struct DefaultProcesses1M {
+    static constexpr int cloud_liquid_formation = 1, cloud_ice_formation = 1, cloud_ice_melt = 1, rain_autoconversion = 1,
+                         snow_autoconversion = 1, rain_condensation_evaporation = 1, snow_deposition_sublimation = 2, snow_melt = 1,
+                         cloud_liquid_rain_accretion = 1, cloud_liquid_snow_accretion = 1, cloud_ice_rain_accretion = 1,
+                         cloud_ice_snow_accretion = 1, rain_snow_accretion = 1;
+};
+template <class O> __host__ inline bool processes_are_default(const O& o) {
+    using D = DefaultProcesses1M;
+    return o.cloud_liquid_formation == D::cloud_liquid_formation && o.cloud_ice_formation == D::cloud_ice_formation &&
+           o.cloud_ice_melt == D::cloud_ice_melt && o.rain_autoconversion == D::rain_autoconversion &&
+           o.snow_autoconversion == D::snow_autoconversion && o.rain_condensation_evaporation == D::rain_condensation_evaporation &&
+           o.snow_deposition_sublimation == D::snow_deposition_sublimation && o.snow_melt == D::snow_melt &&
+           o.cloud_liquid_rain_accretion == D::cloud_liquid_rain_accretion && o.cloud_liquid_snow_accretion == D::cloud_liquid_snow_accretion &&
+           o.cloud_ice_rain_accretion == D::cloud_ice_rain_accretion && o.cloud_ice_snow_accretion == D::cloud_ice_snow_accretion &&
+           o.rain_snow_accretion == D::rain_snow_accretion;
+}
+template <bool STD, class PARAMS> CM_DEV auto processes_of(const PARAMS& p) {
+    if constexpr (STD) return DefaultProcesses1M{};
+    else return p.processes;
+}
 template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::params_1m& p, bool method_is_f32 = false) {
     OneMK<FT> k{};
     const FT pi = FT(3.141592653589793238462643383279502884L);
@@ -134,7 +156,7 @@ template <class FT> __host__ inline OneMK<FT> make_1m_k(const typename P<FT>::pa
     // parameters): quarter resp. eighth powers only
     k.std_exponents = (k.accr_rai_x == FT(2.5) && k.sink_x == FT(5.5) && k.vt_rai_x == FT(0.5) && k.rs_rai_delta == FT(3) &&
                        k.vent_rai_x == FT(0.25) && k.accr_sno_x == FT(2.25) && k.vt_sno_x == FT(0.25) && k.rs_sno_delta == FT(2) &&
-                       k.vent_sno_x == FT(0.125)) ? 1 : 0;
+                       k.vent_sno_x == FT(0.125) && processes_are_default(p.processes)) ? 1 : 0;
     k.rain_inv_k = FT(1) / p.pp.rain_acnv_k; k.snow_inv_k = FT(1) / p.pp.snow_acnv_k;
     k.rain_inv_tau = FT(1) / p.pp.rain_acnv_tau; k.snow_inv_tau = FT(1) / p.pp.snow_acnv_tau;
     return k;
@@ -179,7 +201,7 @@ template <class FT> CM_DEV void lambda_inverse(const MPSpeciesK<FT>& sk, FT log_
     lam = floored ? sk.lam_floor : exp_(ll);
 }
 
-// STD: the block has the default exponent structure (OneMK::std_exponents, decided on the host): the ~11 real powers of λ_r⁻¹ and
+// STD: the block has the default STRUCTURE (OneMK::std_exponents, decided on the host: default exponents AND default process options): the ~11 real powers of λ_r⁻¹ and
 // λ_s⁻¹ (accretion, sink, fall speeds, collision arms, ventilation) are integer powers of ONE exponential per species,
 // u_r = (λ_r/r0)^(1/4) and u_s = (λ_s/r0)^(1/8), formed by ~16 multiplications instead of 9 further exp_ calls (~24 instructions
 // each).  Same quantities to rounding (a product of <= 26 factors of u: <= 3e-15 relative).
@@ -188,7 +210,7 @@ CM_DEV Src1M<FT> microphysics_source_terms_1m(const typename P<FT>::params_1m& p
                                               FT rho, FT T, FT q_tot, FT q_lcl, FT q_icl, FT q_rai, FT q_sno,
                                               const ThermoShared<FT>* shared = nullptr) {
     const FT e = tk.eps_n;
-    const auto& o = p.processes;
+    const auto o = processes_of<STD>(p);      // STD: the default process options as compile-time constants
     const auto& pp = p.pp;
     Src1M<FT> r;
     rho = clamp0_(rho);                                           // BMT:146-151
