@@ -91,8 +91,10 @@ struct ArgOut {
 };
 
 // AA.max_supersaturation + N_activated_per_mode + M_activated_per_mode          AA:138-324
-// FAST_ERF: erf_fast_ (cm_math.cuh) instead of the CUDA libm's erf for the activated fractions
-template <bool WANT_M, bool FAST_ERF = false>
+// FAST_ERF: erf_fast_ (cm_math.cuh) instead of the CUDA libm's erf for the activated fractions.
+// NM >= 0: the number of modes is known at compile time (= p.n_modes, checked by the caller): the mode loops unroll to exactly NM
+// bodies with no trip tests — an unrolled run-time loop keeps all kMaxModes guarded copies in the instruction stream.
+template <bool WANT_M, bool FAST_ERF = false, int NM = -1>
 CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>& tk, const ArgK<double>& k, double T, double pr,
                       double w, double q_tot, double q_liq, double q_ice, double N_liq, double N_ice,
                       const ThermoShared<double>* shared = nullptr) {
@@ -136,8 +138,8 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     const FT E0 = exp_full_(ap.p1 * (l_zeta - l_eta_common));
     const FT T3 = T * T * T;
 #pragma unroll
-    for (int i = 0; i < kMaxModes; ++i) {
-        if (i >= p.n_modes) break;
+    for (int i = 0; i < (NM >= 0 ? NM : kMaxModes); ++i) {
+        if (NM < 0 && i >= p.n_modes) break;
         l_Sm[i] = k.log_sm_coef[i] + l_T32;
         const FT eta = eta_common * k.eta_coef[i];
         // (ζ/η)^p1 and (S_m²/(η+3ζ))^p2
@@ -158,8 +160,8 @@ CM_DEV ArgOut arg2000(const cumicro_params_icenuc_f64& p, const ThermoK<double>&
     o.S_max = clamp0_(S_max);
     const FT l_smax = log_g(o.S_max);   // -Inf when S_max = 0 (libm path): erf(+Inf) = 1 -> N_act = 0   (AA:256)
 #pragma unroll
-    for (int i = 0; i < kMaxModes; ++i) {
-        if (i >= p.n_modes) break;
+    for (int i = 0; i < (NM >= 0 ? NM : kMaxModes); ++i) {
+        if (NM < 0 && i >= p.n_modes) break;
         const FT lr = l_Sm[i] - l_smax;   // log(S_m / S_max)
         o.N_act[i] = p.modes[i].N * FT(0.5) * (FT(1) - (FAST_ERF ? erf_fast_(k.u_coef[i] * lr) : erf_(k.u_coef[i] * lr)));
         if (WANT_M) o.M_act[i] = p.modes[i].molar_mass_mix * FT(0.5) * erfc_(lr / k.m_fac[i] - k.m_fac[i]);

@@ -138,7 +138,8 @@ struct IceNucRates : IceNucBase {
 //   out: S_max, N_act[MODES], M_act[MODES], J_dep, J_ABIFM, J_hom, Δa_w   (NULL columns skipped)
 template <int MODES, bool WANT_M> struct ArgIceNuc : IceNucBase {
     __device__ __forceinline__ void operator()(const D (&x)[8], D (&y)[1 + 2 * MODES + 4]) const {
-        const ArgOut o = arg2000<WANT_M, true>(p, tk, k, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+        const ArgOut o = arg2000<WANT_M, true, (MODES <= 4 ? MODES : -1)>(p, tk, k, x[0],   // MODES = 8 serves n_modes 5..8: run-time bound
+             x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         y[0] = o.S_max;
 #pragma unroll
         for (int i = 0; i < MODES; ++i) {
