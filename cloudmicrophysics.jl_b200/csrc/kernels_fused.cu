@@ -67,7 +67,8 @@ template <class FT> struct FusedArgs {
 // keeps the occupancy of the single-family kernels.
 // S1M: the 1-moment block has the default exponent structure (cm_1m.cuh, OneMK::std_exponents): powers of λ⁻¹ by multiplication
 // ALL_OUT: every output column is wanted (decided at launch): no per-column NULL test in the store sequence
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB, bool S1M, bool ALL_OUT>
+// NM3: the aerosol distribution has exactly three modes (compile-time trip count of the ARG2000 mode loops)
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB, bool S1M, bool ALL_OUT, bool NM3>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constant__ FusedArgs<FT> a) {
     __shared__ __align__(16) double tab_s[TAB ? kTabDoubles : 2];
     if (TAB) {
@@ -124,15 +125,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
             double n_act = 0.0;
             double da_w;
             if (f.with_activation) {
-                const ArgOut o = arg2000<false>(f.p3, f.tk, f.k3, T, pr, w, q_tot, q_lcl + q_rai, q_icl + q_sno, rho * n_lcl, 0.0, &th);
+                const ArgOut o = arg2000<false, false, (NM3 ? 3 : -1)>(f.p3, f.tk, f.k3, T, pr, w, q_tot, q_lcl + q_rai, q_icl + q_sno, rho * n_lcl, 0.0, &th);
                 da_w = o.da_w;
                 // Activation needs an updraft: AA.max_supersaturation takes sqrt(alpha w / G) (AA:170-176), a DomainError in the
                 // reference for w < 0 and S_max = 0 for w = 0.  A model slab has downdraft cells: they activate nothing, and they
                 // must not poison the domain sum (NaN from one cell would make the all-reduced diagnostic NaN everywhere).
                 const bool updraft = w > 0.0;
 #pragma unroll
-                for (int m = 0; m < kMaxModes; ++m)
-                    if (m < f.p3.n_modes) {
+                for (int m = 0; m < (NM3 ? 3 : kMaxModes); ++m)
+                    if (NM3 || m < f.p3.n_modes) {
                         const double na = o.N_act[m];
                         n_act += (updraft && na == na && na < 1.7e308) ? na : 0.0;
                     }
@@ -214,7 +215,7 @@ template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false, bool ALL_OUT = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false, bool ALL_OUT = false, bool NM3 = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
     // the block partials: scratch of this (device, stream) — calls in flight on different streams never share it, and work on ONE
     // stream is ordered (the finish kernel of call k has read the partials before the main kernel of call k + 1 writes them)
@@ -223,7 +224,7 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, 
     if (st) return st;
     a.partials = static_cast<double*>(ws);
     const size_t smem = sizeof(FT) * 2 * NIN * BLOCK;
-    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB, S1M, ALL_OUT>;
+    auto kern = fused_kernel<FT, BLOCK, MINB, SYNC, SPEC, TAB, S1M, ALL_OUT, NM3>;
     {   // every launch: function attributes are per device, and the call costs about a microsecond against a millisecond kernel
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cmh::cuda_status(e, "fused: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
@@ -271,6 +272,8 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     for (int c = 0; c < NOUT; ++c) all_out = all_out && out[c] != nullptr;
     int st;
     if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
+    else if (spec == 1 && a.tab && a.f.k1.std_exponents && all_out && a.f.p3.n_modes == 3)
+        st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true, true>(a, n, s, diag);
     else if (spec == 1 && a.tab && a.f.k1.std_exponents && all_out) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true>(a, n, s, diag);
     else if (spec == 1 && a.tab && a.f.k1.std_exponents) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true>(a, n, s, diag);
     else if (spec == 1 && a.tab) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true>(a, n, s, diag);

@@ -19,8 +19,8 @@ KERNELS = [  # (object, regex on the mangled name, label)
     ("kernels_1m.o", r"pointwise_kernelIdLi7ELi4E.*OneMLinAvgILb1EEELb0", "1m_linavg_f64"),
     # config 3: tile shape, 3 modes, no M_act, 896x1, ALL_OUT
     ("kernels_icenuc.o", r"pointwise_kernel_tiledIfLi8ELi11E.*ArgIceNucILi3ELb0EEELi896ELi1ELb1E", "arg_icenuc_f32"),
-    # config 5: 896x1, SPEC 1, TAB, S1M, ALL_OUT
-    ("kernels_fused.o", r"fused_kernelIdLi896ELi1ELb0ELi1ELb1ELb1ELb1E", "fused_f64"),
+    # config 5: 896x1, SPEC 1, TAB, S1M, ALL_OUT, NM3
+    ("kernels_fused.o", r"fused_kernelIdLi896ELi1ELb0ELi1ELb1ELb1ELb1ELb1E", "fused_f64"),
     ("kernels_p3.o", r"p3_tile_kernelIdLi0", "p3_rates_f64"),
     ("kernels_emulator.o", r"emu_kernelId", "emulator_f64"),
 ]
