@@ -12,11 +12,10 @@ sys.path.insert(0, ROOT)
 VAR = os.path.join(ROOT, "cloudmicrophysics.jl_b200", "build", "variants")
 VARIANTS = {
     "base": "",
-    "l896": "-DCUMICRO_1ML_BLOCK=896 -DCUMICRO_1ML_MINB=1",
-    "l768": "-DCUMICRO_1ML_BLOCK=768 -DCUMICRO_1ML_MINB=1",
-    "l640": "-DCUMICRO_1ML_BLOCK=640 -DCUMICRO_1ML_MINB=1",
-    "l512x2": "-DCUMICRO_1ML_BLOCK=512 -DCUMICRO_1ML_MINB=2",
-    "lt896": "-DCUMICRO_1ML_TILED=1 -DCUMICRO_1ML_BLOCK=896 -DCUMICRO_1ML_MINB=1",
+    "1m8_arg128x6": "-DCUMICRO_1M_MINB=8 -DCUMICRO_ARG_BLOCK=128 -DCUMICRO_ARG_MINB=6",
+    "1m6_arg128x7": "-DCUMICRO_1M_MINB=6 -DCUMICRO_ARG_BLOCK=128 -DCUMICRO_ARG_MINB=7",
+    "1m256x4_arg256x3": "-DCUMICRO_1M_BLOCK=256 -DCUMICRO_1M_MINB=4 -DCUMICRO_1MV_MINB=4 -DCUMICRO_ARG_BLOCK=256 -DCUMICRO_ARG_MINB=3",
+    "arg1024x1": "-DCUMICRO_ARG_BLOCK=1024 -DCUMICRO_ARG_MINB=1",
 }
 FILES = ("kernels_1m.cu", "kernels_icenuc.cu", "kernels_fused.cu")
 if len(sys.argv) > 2:
