@@ -15,7 +15,8 @@ Legs of the cumicro arm (all on the device's current stream, CUDA-event timed):
               H2D + kernel + D2H inside the timed region; beside it the measured pinned H2D / D2H link rates
   config5     (N > 1, or --config5) BASELINE config 5: the fused 1M + 2M + ice-nucleation kernel on this rank's column slab with
               the in-kernel domain diagnostics and their NCCL all-reduce (the only collective of the path, through the C-ABI
-              cumicro_nccl_allreduce_f64) inside the timed region
+              cumicro_nccl_allreduce_f64) inside the timed region; sub-record `p2p`: the same step with the exchange done by
+              peer-memory stores over NVLink inside the fused call's own finish kernel (cumicro_fused_1m2m_icenuc_p2p_f64)
   cpu_baseline (N = 1) the CPU restatement of the reference on the box's host cores, bounded sample
 """
 from __future__ import annotations
@@ -261,7 +262,7 @@ def _config5(torch, dist, dev, lib, args, rank, world):
             assert st_ == 0, lib.cumicro_last_error()
         return r
 
-    def timed(reduce, k):
+    def timed(reduce, k, step=step):
         for _ in range(3):
             step(reduce)
         if dist is not None:
@@ -284,13 +285,43 @@ def _config5(torch, dist, dev, lib, args, rank, world):
     diag = r["diag"].cpu().numpy().tolist()
     if world > 1:
         lib.cumicro_nccl_comm_destroy(comm)
+
+    # ---- the same step with the exchange inside the fused call's finish kernel (peer-memory stores over NVLink, csrc/cm_p2p.cuh)
+    p2p = None
+    if world > 1:
+        from cumicro import collective
+        win, err = None, ""
+        try:
+            win = collective.P2PWindow(rank, world).set_timeout(2.0).connect_with_torch_distributed()
+        except Exception as e:  # noqa  (no peer access / IPC in this container: reported, the NCCL leg stands)
+            err = repr(e)[:200]
+        ok = torch.tensor([1.0 if (win is not None and not err) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)           # every rank connected, or nobody runs the leg
+        if float(ok.item()) == 1.0:
+            def step_p2p(_reduce):
+                return fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *cols, out=outs, diagnostics=True, p2p_window=win)
+            ms_p2p, r2 = timed(True, k, step_p2p)
+            calls, bad = win.status()
+            d2 = r2["diag"].cpu().numpy()
+            ref = np.asarray(diag)
+            p2p = {"ms_per_step": ms_p2p, "value": n * world / (ms_p2p * 1e-3), "unit": UNIT,
+                   "exchange_us": max(0.0, (ms_p2p - ms_loc) * 1e3), "calls": calls, "timed_out_call": bad,
+                   "max_rel_diff_vs_nccl": float(np.max(np.abs(d2 - ref) / np.maximum(np.abs(ref), 1e-300))),
+                   "collective": "peer-memory stores + rank-ordered sum inside the fused call's finish kernel "
+                                 "(cumicro_fused_1m2m_icenuc_p2p_f64): no second launch, no library call"}
+        else:
+            p2p = {"unavailable": err or "a peer rank could not map the windows"}
+        dist.barrier()
+        torch.cuda.synchronize()
+        if win is not None:
+            win.destroy()
     return {"workload": "fused 1M + 2M + ice nucleation (+ARG2000, 3 modes) Float64, column slabs of 2^24 points per GPU, "
                         "in-kernel domain diagnostics + NCCL all-reduce of 4 doubles per step (cumicro_nccl_allreduce_f64)",
             "points_per_gpu": n, "global_points": n * world, "steps": k, "ms_per_step": ms_red,
             "value": n * world / (ms_red * 1e-3), "unit": UNIT,
             "ms_per_step_without_allreduce": ms_loc, "allreduce_us": max(0.0, (ms_red - ms_loc) * 1e3),
             "collective": "ncclAllReduce(sum, 4 x f64) per step" if world > 1 else "none (single GPU)",
-            "diag_global": dict(zip(fused.DIAG_NAMES, diag))}
+            "diag_global": dict(zip(fused.DIAG_NAMES, diag)), "p2p": p2p}
 
 
 def main():

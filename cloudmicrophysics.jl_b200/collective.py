@@ -2,7 +2,10 @@
 
 ``reduce_diagnostics`` sums weighted device columns of ONE slab (fixed order, bit-reproducible);
 ``NcclComm`` wraps the C-ABI communicator helpers (``cumicro_nccl_*``) a host without an NCCL
-binding of its own would use, and ``all_reduce`` the in-place sum over its ranks."""
+binding of its own would use, and ``all_reduce`` the in-place sum over its ranks;
+``P2PWindow`` is the same sum as peer-memory stores over NVLink inside one kernel
+(``cumicro_p2p_*``, csrc/cm_p2p.cuh) — the fused config-5 entry point takes it and reduces in
+its own finish kernel."""
 from __future__ import annotations
 
 import ctypes as C
@@ -61,3 +64,64 @@ class NcclComm:
         if self.handle:
             _abi.load().cumicro_nccl_comm_destroy(self.handle)
             self.handle = C.c_void_p(0)
+
+
+class P2PWindow:
+    """Peer-memory exchange window of this rank (one process per GPU of one NVLink node).
+
+    ``P2PWindow(rank, nranks)`` allocates the local window on the current device; ``handle()`` is
+    the 64-byte inter-process handle the host ships to the other ranks; ``connect(handles)`` maps
+    the peers' windows (``handles`` in rank order).  ``connect_with_torch_distributed`` does the
+    exchange through an initialised ``torch.distributed`` group."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, rank: int, nranks: int):
+        self.rank, self.nranks = rank, nranks
+        self.handle_ = C.c_void_p(0)
+        lib = _abi.load()
+        _abi.check(lib.cumicro_p2p_window_create(C.c_int(rank), C.c_int(nranks), C.byref(self.handle_)), "cumicro_p2p_window_create")
+
+    def handle(self) -> bytes:
+        raw = (C.c_char * self.HANDLE_BYTES)()
+        _abi.check(_abi.load().cumicro_p2p_window_handle(self.handle_, raw), "cumicro_p2p_window_handle")
+        return bytes(raw.raw)
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        if len(blob) != self.HANDLE_BYTES * self.nranks:
+            raise ValueError(f"expected {self.nranks} handles of {self.HANDLE_BYTES} bytes")
+        raw = (C.c_char * len(blob)).from_buffer_copy(blob)
+        _abi.check(_abi.load().cumicro_p2p_window_connect(self.handle_, raw), "cumicro_p2p_window_connect")
+        return self
+
+    def connect_with_torch_distributed(self, group=None):
+        import torch.distributed as dist
+        if self.nranks == 1:
+            return self
+        box = [None] * self.nranks
+        dist.all_gather_object(box, self.handle(), group=group)
+        return self.connect(box)
+
+    def set_timeout(self, seconds: float):
+        _abi.check(_abi.load().cumicro_p2p_window_set_timeout(self.handle_, C.c_double(seconds)), "cumicro_p2p_window_set_timeout")
+        return self
+
+    def status(self):
+        """(calls made, call number whose wait timed out or 0)"""
+        calls, bad = C.c_int64(0), C.c_int64(0)
+        _abi.check(_abi.load().cumicro_p2p_window_status(self.handle_, C.byref(calls), C.byref(bad)), "cumicro_p2p_window_status")
+        return calls.value, bad.value
+
+    def all_reduce(self, buf: torch.Tensor):
+        """In-place sum of a Float64 device tensor (<= 16 elements) over the ranks, on the current stream."""
+        assert buf.is_cuda and buf.dtype == torch.float64 and buf.is_contiguous()
+        st = _abi.load().cumicro_p2p_allreduce_f64(self.handle_, ptr(buf), C.c_int(buf.numel()), stream_handle(buf.device))
+        _abi.check(st, "cumicro_p2p_allreduce_f64")
+        return buf
+
+    def destroy(self):
+        """After the last call's work has completed on every rank (synchronise + barrier first)."""
+        if self.handle_:
+            _abi.load().cumicro_p2p_window_destroy(self.handle_)
+            self.handle_ = C.c_void_p(0)

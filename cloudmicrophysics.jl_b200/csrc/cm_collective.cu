@@ -5,6 +5,8 @@
 //                                 that were computed by the non-fused entry points (the fused config-5 kernel reduces in-kernel).
 //   cumicro_nccl_allreduce_f64    sum of `count` doubles over the ranks of the caller's ncclComm_t, in place, on the caller's stream.
 //   cumicro_nccl_{unique_id,comm_init_rank,comm_destroy}   for hosts without an NCCL binding of their own.
+//   cumicro_p2p_window_* / cumicro_p2p_allreduce_f64   the same sum as peer-memory stores in ONE kernel (cm_p2p.cuh): no library, no
+//                                 second launch; the fused config-5 entry point takes the window and reduces in its finish kernel.
 // libcumicro.so has no link-time dependency on NCCL: the symbols are resolved at first use from the NCCL already loaded in the process
 // (torch / NCCL.jl / MPI stack) or from libnccl.so.2 on the loader path.
 #include <dlfcn.h>
@@ -13,6 +15,7 @@
 #include <mutex>
 
 #include "cm_hostpipe.cuh"
+#include "cm_p2p.cuh"
 
 namespace {
 
@@ -88,6 +91,40 @@ int reduce_impl(int64_t n, const FT* w, const FT* const* cols, int ncols, double
     cmh::count_launch();
     return cmh::cuda_status(cudaGetLastError(), "reduce_diagnostics launch");
 }
+
+// ---- peer-memory window (cm_p2p.cuh) --------------------------------------------------------------------------------------
+struct P2PWindow {
+    int rank = 0, nranks = 1, device = 0;
+    cm::P2PWindowMem* local = nullptr;
+    cm::P2PWindowMem* peer[cm::kP2PMaxRanks] = {};
+    bool opened[cm::kP2PMaxRanks] = {};
+    bool connected = false;
+    unsigned long long timeout_ns = 10ull * 1000000000ull;
+};
+
+__global__ void __launch_bounds__(32) p2p_allreduce_kernel(const __grid_constant__ cm::P2PDev d, double* buf, int count) {
+    cm::p2p_allreduce_block(d, buf, count);
+}
+
+}  // namespace
+
+namespace cmh {
+int p2p_dev(void* win, cm::P2PDev* out) {
+    auto* w = static_cast<P2PWindow*>(win);
+    if (w == nullptr || out == nullptr) return fail(CUMICRO_E_NULL, "p2p window is NULL");
+    if (!w->connected) return fail(CUMICRO_E_ARG, "p2p window of rank %d is not connected (cumicro_p2p_window_connect)", w->rank);
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != w->device) return fail(CUMICRO_E_ARG, "p2p window belongs to device %d, the current device is %d", w->device, dev);
+    for (int r = 0; r < cm::kP2PMaxRanks; ++r) out->win[r] = r < w->nranks ? w->peer[r] : nullptr;
+    out->rank = w->rank;
+    out->nranks = w->nranks;
+    out->timeout_ns = w->timeout_ns;
+    return CUMICRO_OK;
+}
+}  // namespace cmh
+
+namespace {
 
 // ---- NCCL through dlsym -------------------------------------------------------------------------------------------------
 struct NcclId { char internal[128]; };
@@ -173,6 +210,98 @@ int cumicro_nccl_comm_destroy(void* comm) {
     int st = need_nccl();
     if (st) return st;
     return nccl_status(nccl().destroy(comm), "ncclCommDestroy");
+}
+
+int cumicro_p2p_window_create(int rank, int nranks, void** win) {
+    if (win == nullptr) return cmh::fail(CUMICRO_E_NULL, "win is NULL");
+    *win = nullptr;
+    if (nranks < 1 || nranks > cm::kP2PMaxRanks || rank < 0 || rank >= nranks)
+        return cmh::fail(CUMICRO_E_ARG, "rank %d of %d (1 <= nranks <= %d)", rank, nranks, cm::kP2PMaxRanks);
+    auto* w = new P2PWindow();
+    w->rank = rank;
+    w->nranks = nranks;
+    int st = cmh::cuda_status(cudaGetDevice(&w->device), "cudaGetDevice");
+    // cudaMalloc (not a stream-ordered pool): only such allocations can be exported with cudaIpcGetMemHandle
+    if (!st) st = cmh::cuda_status(cudaMalloc(reinterpret_cast<void**>(&w->local), sizeof(cm::P2PWindowMem)), "cudaMalloc (p2p window)");
+    if (!st) st = cmh::cuda_status(cudaMemset(w->local, 0, sizeof(cm::P2PWindowMem)), "cudaMemset (p2p window)");
+    if (!st) st = cmh::cuda_status(cudaDeviceSynchronize(), "p2p window create");   // zero before any peer can hold the handle
+    if (st) {
+        if (w->local) cudaFree(w->local);
+        delete w;
+        return st;
+    }
+    w->peer[rank] = w->local;
+    w->connected = nranks == 1;
+    *win = w;
+    return CUMICRO_OK;
+}
+int cumicro_p2p_window_handle(void* win, void* handle64) {
+    auto* w = static_cast<P2PWindow*>(win);
+    if (w == nullptr || handle64 == nullptr) return cmh::fail(CUMICRO_E_NULL, "win / handle64 is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CUMICRO_P2P_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    int st = cmh::cuda_status(cudaIpcGetMemHandle(&h, w->local), "cudaIpcGetMemHandle");
+    if (st) return st;
+    memcpy(handle64, &h, sizeof(h));
+    return CUMICRO_OK;
+}
+int cumicro_p2p_window_connect(void* win, const void* handles) {
+    auto* w = static_cast<P2PWindow*>(win);
+    if (w == nullptr) return cmh::fail(CUMICRO_E_NULL, "win is NULL");
+    if (w->connected) return CUMICRO_OK;
+    if (handles == nullptr) return cmh::fail(CUMICRO_E_NULL, "handles is NULL");
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != w->device) return cmh::fail(CUMICRO_E_ARG, "p2p window belongs to device %d, the current device is %d", w->device, dev);
+    for (int r = 0; r < w->nranks; ++r) {
+        if (r == w->rank || w->opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        int st = cmh::cuda_status(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer window; the ranks must be separate processes on one NVLink node)");
+        if (st) return st;
+        w->peer[r] = static_cast<cm::P2PWindowMem*>(p);
+        w->opened[r] = true;
+    }
+    w->connected = true;
+    return CUMICRO_OK;
+}
+int cumicro_p2p_window_set_timeout(void* win, double seconds) {
+    auto* w = static_cast<P2PWindow*>(win);
+    if (w == nullptr) return cmh::fail(CUMICRO_E_NULL, "win is NULL");
+    if (!(seconds > 0.0) || seconds > 3600.0) return cmh::fail(CUMICRO_E_ARG, "timeout = %g s (0 < t <= 3600)", seconds);
+    w->timeout_ns = (unsigned long long)(seconds * 1e9);
+    return CUMICRO_OK;
+}
+int cumicro_p2p_window_status(void* win, int64_t* calls, int64_t* timed_out_call) {
+    auto* w = static_cast<P2PWindow*>(win);
+    if (w == nullptr) return cmh::fail(CUMICRO_E_NULL, "win is NULL");
+    unsigned long long v[2] = {0, 0};
+    int st = cmh::cuda_status(cudaMemcpy(v, &w->local->counter, sizeof(v), cudaMemcpyDeviceToHost), "p2p window status");
+    if (st) return st;
+    if (calls) *calls = (int64_t)v[0];
+    if (timed_out_call) *timed_out_call = (int64_t)v[1];
+    return CUMICRO_OK;
+}
+int cumicro_p2p_allreduce_f64(void* win, double* buf, int count, void* stream) {
+    if (buf == nullptr) return cmh::fail(CUMICRO_E_NULL, "buf is NULL");
+    if (count < 0 || count > cm::kP2PMaxCount) return cmh::fail(CUMICRO_E_SIZE, "count = %d (0..%d)", count, cm::kP2PMaxCount);
+    cm::P2PDev d;
+    int st = cmh::p2p_dev(win, &d);
+    if (st) return st;
+    if (count == 0) return CUMICRO_OK;
+    p2p_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d, buf, count);
+    cmh::count_launch();
+    return cmh::cuda_status(cudaGetLastError(), "p2p_allreduce launch");
+}
+int cumicro_p2p_window_destroy(void* win) {
+    auto* w = static_cast<P2PWindow*>(win);
+    if (w == nullptr) return CUMICRO_OK;
+    for (int r = 0; r < w->nranks; ++r)
+        if (w->opened[r]) cudaIpcCloseMemHandle(w->peer[r]);
+    if (w->local) cudaFree(w->local);
+    delete w;
+    return CUMICRO_OK;
 }
 
 }  // extern "C"

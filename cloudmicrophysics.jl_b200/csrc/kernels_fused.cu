@@ -15,6 +15,7 @@
 #include "cm_hostpipe.cuh"
 #include "cm_icenuc.cuh"
 #include "cm_launch.cuh"
+#include "cm_p2p.cuh"
 #include "cm_sb2006.cuh"
 #include "cm_sb2006_fast.cuh"
 #include "cm_tile2m.cuh"
@@ -195,7 +196,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_kernel(const __grid_constan
 
 // fixed-order second pass: one block; thread t sums the partials of blocks t, t + 256, ... in that order, then a fixed
 // binary tree over the 256 thread sums -> bit-reproducible for a given grid size
-__global__ void fused_diag_finish(const double* partials, int n_blocks, double* diag) {
+// P2P: the cross-GPU sum is the tail of this kernel (peer-memory stores over NVLink, cm_p2p.cuh) — diag leaves it as the DOMAIN sums.
+template <bool P2P>
+__global__ void __launch_bounds__(256) fused_diag_finish(const double* partials, int n_blocks, double* diag, const __grid_constant__ cm::P2PDev p2p) {
     __shared__ double sh[256];
     for (int k = 0; k < NDIAG; ++k) {
         double v = 0.0;
@@ -209,13 +212,14 @@ __global__ void fused_diag_finish(const double* partials, int n_blocks, double* 
         if (threadIdx.x == 0) diag[k] = sh[0];
         __syncthreads();
     }
+    if (P2P) cm::p2p_allreduce_block(p2p, diag, NDIAG);
 }
 
 template <class FT> struct PF;
 template <> struct PF<double> { using p1 = cumicro_params_1m_f64; using p2 = cumicro_params_2m_warm_f64; using p3 = cumicro_params_icenuc_f64; };
 template <> struct PF<float> { using p1 = cumicro_params_1m_f32; using p2 = cumicro_params_2m_warm_f32; using p3 = cumicro_params_icenuc_f32; };
 
-template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false, bool ALL_OUT = false, bool NM3 = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag) {
+template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, bool S1M = false, bool ALL_OUT = false, bool NM3 = false> int launch_fused(FusedArgs<FT>& a, int64_t n, cudaStream_t s, double* diag, const cm::P2PDev* p2p) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)cmh::num_sms() * MINB * 16));   // 16 waves of the resident grid (cm_launch.cuh)
     // the block partials: scratch of this (device, stream) — calls in flight on different streams never share it, and work on ONE
     // stream is ordered (the finish kernel of call k has read the partials before the main kernel of call k + 1 writes them)
@@ -232,7 +236,8 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, 
     kern<<<blocks, BLOCK, smem, s>>>(a);
     cmh::count_launch();
     if (diag) {
-        fused_diag_finish<<<1, 256, 0, s>>>(a.partials, blocks, diag);
+        if (p2p) fused_diag_finish<true><<<1, 256, 0, s>>>(a.partials, blocks, diag, *p2p);
+        else fused_diag_finish<false><<<1, 256, 0, s>>>(a.partials, blocks, diag, cm::P2PDev{});
         cmh::count_launch();
     }
     return CUMICRO_OK;
@@ -240,7 +245,15 @@ template <class FT, int BLOCK, int MINB, bool SYNC, int SPEC, bool TAB = false, 
 
 template <class FT>
 int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, const typename PF<FT>::p3* p3, int64_t n,
-               const FT* const* in, FT* const* out, double* diag, void* stream) {
+               const FT* const* in, FT* const* out, double* diag, void* stream, void* win = nullptr, bool want_p2p = false) {
+    cm::P2PDev p2p_dev{};
+    const cm::P2PDev* p2p = nullptr;
+    if (want_p2p) {   // the exchange rides on the finish kernel: it needs the diagnostics vector
+        if (diag == nullptr) return cmh::fail(CUMICRO_E_NULL, "fused (p2p): diag is NULL");
+        const int stw = cmh::p2p_dev(win, &p2p_dev);
+        if (stw) return stw;
+        p2p = &p2p_dev;
+    }
     if (!p1 || !p2 || !p3) return cmh::fail(CUMICRO_E_NULL, "fused: a parameter block is NULL");
     if (!in || !out) return cmh::fail(CUMICRO_E_NULL, "fused: column pointer table is NULL");
     if (n < 0) return cmh::fail(CUMICRO_E_SIZE, "n = %lld is negative", (long long)n);
@@ -271,15 +284,15 @@ int fused_impl(const typename PF<FT>::p1* p1, const typename PF<FT>::p2* p2, con
     bool all_out = true;
     for (int c = 0; c < NOUT; ++c) all_out = all_out && out[c] != nullptr;
     int st;
-    if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag);
+    if (small_blocks) st = launch_fused<FT, 128, 6, false, -1>(a, n, s, diag, p2p);
     else if (spec == 1 && a.tab && a.f.k1.std_exponents && all_out && a.f.p3.n_modes == 3)
-        st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true, true>(a, n, s, diag);
-    else if (spec == 1 && a.tab && a.f.k1.std_exponents && all_out) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true>(a, n, s, diag);
-    else if (spec == 1 && a.tab && a.f.k1.std_exponents) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true>(a, n, s, diag);
-    else if (spec == 1 && a.tab) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true>(a, n, s, diag);
-    else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag);
-    else if (spec == 0) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 0>(a, n, s, diag);
-    else st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, -1>(a, n, s, diag);
+        st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true, true>(a, n, s, diag, p2p);
+    else if (spec == 1 && a.tab && a.f.k1.std_exponents && all_out) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true, true>(a, n, s, diag, p2p);
+    else if (spec == 1 && a.tab && a.f.k1.std_exponents) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true, true>(a, n, s, diag, p2p);
+    else if (spec == 1 && a.tab) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1, true>(a, n, s, diag, p2p);
+    else if (spec == 1) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 1>(a, n, s, diag, p2p);
+    else if (spec == 0) st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, 0>(a, n, s, diag, p2p);
+    else st = launch_fused<FT, CUMICRO_FUSED_BLOCK, 1, false, -1>(a, n, s, diag, p2p);
     if (st) return st;
     return cmh::cuda_status(cudaGetLastError(), "fused_1m2m_icenuc launch");
 }
@@ -297,6 +310,16 @@ int cumicro_fused_1m2m_icenuc_f32(const cumicro_params_1m_f32* p1, const cumicro
                                   const cumicro_params_icenuc_f32* p3, int64_t n, const float* const* in11,
                                   float* const* out11, double* diag, void* stream) {
     return fused_impl<float>(p1, p2, p3, n, in11, out11, diag, stream);
+}
+int cumicro_fused_1m2m_icenuc_p2p_f64(const cumicro_params_1m_f64* p1, const cumicro_params_2m_warm_f64* p2,
+                                      const cumicro_params_icenuc_f64* p3, int64_t n, const double* const* in11,
+                                      double* const* out11, double* diag, void* win, void* stream) {
+    return fused_impl<double>(p1, p2, p3, n, in11, out11, diag, stream, win, true);
+}
+int cumicro_fused_1m2m_icenuc_p2p_f32(const cumicro_params_1m_f32* p1, const cumicro_params_2m_warm_f32* p2,
+                                      const cumicro_params_icenuc_f32* p3, int64_t n, const float* const* in11,
+                                      float* const* out11, double* diag, void* win, void* stream) {
+    return fused_impl<float>(p1, p2, p3, n, in11, out11, diag, stream, win, true);
 }
 
 }  // extern "C"

@@ -43,11 +43,14 @@ def all_reduce_diagnostics(diag: torch.Tensor, group=None, async_op=False):
 
 
 def fused_1m2m_icenuc(mp1, mp2, tps, icenuc_block, rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai, *,
-                      out=None, diagnostics=True, reduce_group=None, reduce=True):
+                      out=None, diagnostics=True, reduce_group=None, reduce=True, p2p_window=None):
     """One fused kernel over this rank's slab.  Returns a ``Tendencies`` of the 11 output columns
     plus ``diag`` (Float64 device tensor of NDIAG sums, all-reduced over ``torch.distributed``
     ranks when a process group is initialised; ``reduce=False`` leaves the slab's own sums, e.g. for a
-    host that reduces through ``cumicro_nccl_allreduce_f64`` with its own communicator)."""
+    host that reduces through ``cumicro_nccl_allreduce_f64`` with its own communicator).
+    ``p2p_window`` (a connected ``collective.P2PWindow``): the cross-GPU sum happens inside the call's own finish
+    kernel by peer-memory stores over NVLink (``cumicro_fused_1m2m_icenuc_p2p_*``); ``diag`` then holds the domain sums
+    and no library collective is issued."""
     cols = [rho, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai]
     suf, n, dev = check_columns(cols, list(IN_NAMES))
     b1, b2 = CMP.pack_1m(mp1, tps), CMP.pack_2m_warm(mp2, tps)
@@ -55,12 +58,19 @@ def fused_1m2m_icenuc(mp1, mp2, tps, icenuc_block, rho, T, p, w, q_tot, q_lcl, q
         raise TypeError(f"parameter float type does not match the columns ({suf})")
     outs = list(out) if out is not None else [torch.empty_like(rho) for _ in OUT_NAMES]
     diag = torch.zeros(NDIAG, dtype=torch.float64, device=dev) if diagnostics else None
-    fn = getattr(_abi.load(), f"cumicro_fused_1m2m_icenuc_{suf}")
+    if p2p_window is not None and diag is None:
+        raise ValueError("p2p_window needs diagnostics=True")
     with torch.cuda.device(dev):
-        st = fn(C.byref(b1), C.byref(b2), C.byref(icenuc_block), C.c_int64(n), ptr_table(cols), ptr_table(outs),
-                C.c_void_p(diag.data_ptr()) if diag is not None else None, stream_handle(dev))
+        if p2p_window is not None:
+            fn = getattr(_abi.load(), f"cumicro_fused_1m2m_icenuc_p2p_{suf}")
+            st = fn(C.byref(b1), C.byref(b2), C.byref(icenuc_block), C.c_int64(n), ptr_table(cols), ptr_table(outs),
+                    C.c_void_p(diag.data_ptr()), p2p_window.handle_, stream_handle(dev))
+        else:
+            fn = getattr(_abi.load(), f"cumicro_fused_1m2m_icenuc_{suf}")
+            st = fn(C.byref(b1), C.byref(b2), C.byref(icenuc_block), C.c_int64(n), ptr_table(cols), ptr_table(outs),
+                    C.c_void_p(diag.data_ptr()) if diag is not None else None, stream_handle(dev))
     _abi.check(st, "cumicro_fused_1m2m_icenuc")
-    if diag is not None and reduce:
+    if diag is not None and reduce and p2p_window is None:
         all_reduce_diagnostics(diag, reduce_group)
     res = Tendencies(zip(OUT_NAMES, outs))
     res["diag"] = diag

@@ -495,6 +495,39 @@ int cumicro_nccl_unique_id(void* id128);
 int cumicro_nccl_comm_init_rank(void** comm, int nranks, const void* id128, int rank);
 int cumicro_nccl_comm_destroy(void* comm);
 
+/* ---------------------------------------------------------------------------
+ * The same exchange step without a library: peer-memory stores over NVLink / NVSwitch inside ONE kernel (csrc/cm_p2p.cuh).
+ * Every rank (one process per GPU of one node) owns a window in its device memory; a rank writes its doubles into its slot of
+ * every peer's window, waits for the peers' slots of its own window and adds them in rank order (bit-identical on all ranks).
+ *   cumicro_p2p_window_create:  allocates and zeroes the local window on the current device (nranks <= 16); nranks = 1 needs no
+ *                               connect step.
+ *   cumicro_p2p_window_handle:  the CUMICRO_P2P_HANDLE_BYTES-byte inter-process handle of the local window (cudaIpcMemHandle_t);
+ *                               the host ships it to the other ranks by its own means (MPI, torch.distributed, a file).
+ *   cumicro_p2p_window_connect: `handles` = nranks x CUMICRO_P2P_HANDLE_BYTES bytes in rank order (the own entry is ignored);
+ *                               maps the peers' windows.  The ranks must be separate processes with peer access between the GPUs.
+ *   cumicro_p2p_allreduce_f64:  in-place sum of `count` (<= 16) doubles at device pointer `buf` over the ranks, one single-block
+ *                               kernel on `stream`.  Every rank must make the same sequence of calls on its window.
+ *   cumicro_fused_1m2m_icenuc_p2p_*: the config-5 entry point with the exchange inside its finish kernel: `diag` holds the
+ *                               DOMAIN sums (all ranks) when the call's work completes — no second launch, no library call.
+ *   cumicro_p2p_window_status:  calls made so far and the call number whose wait timed out (0 = none; a peer that never calls
+ *                               makes the waiting ranks give up after the timeout, default 10 s, and return NaN sums).
+ *   cumicro_p2p_window_destroy: after the last call's work has completed on EVERY rank (synchronise + barrier first).
+ * ------------------------------------------------------------------------- */
+#define CUMICRO_P2P_HANDLE_BYTES 64
+int cumicro_p2p_window_create(int rank, int nranks, void** win);
+int cumicro_p2p_window_handle(void* win, void* handle64);
+int cumicro_p2p_window_connect(void* win, const void* handles);
+int cumicro_p2p_window_set_timeout(void* win, double seconds);
+int cumicro_p2p_window_status(void* win, int64_t* calls, int64_t* timed_out_call);
+int cumicro_p2p_allreduce_f64(void* win, double* buf, int count, void* stream);
+int cumicro_p2p_window_destroy(void* win);
+int cumicro_fused_1m2m_icenuc_p2p_f64(const cumicro_params_1m_f64* p1, const cumicro_params_2m_warm_f64* p2,
+                                      const cumicro_params_icenuc_f64* p3, int64_t n, const double* const* in11,
+                                      double* const* out11, double* diag, void* win, void* stream);
+int cumicro_fused_1m2m_icenuc_p2p_f32(const cumicro_params_1m_f32* p1, const cumicro_params_2m_warm_f32* p2,
+                                      const cumicro_params_icenuc_f32* p3, int64_t n, const float* const* in11,
+                                      float* const* out11, double* diag, void* win, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

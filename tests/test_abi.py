@@ -61,6 +61,14 @@ def test_api_misuse_is_reported_without_a_gpu(built):
     blk.sb.pdf_r.limited = 1
     st = lib.cumicro_bmt2m_warm_f64(C.byref(blk), C.c_int64(0), *([null] * 8), *([null] * 4), None, None)
     assert st == 0
+    # peer-memory window: rank / size and NULL checks come before any CUDA call
+    win = C.c_void_p(0)
+    assert lib.cumicro_p2p_window_create(C.c_int(2), C.c_int(2), C.byref(win)) < 0 and not win.value
+    assert lib.cumicro_p2p_window_create(C.c_int(0), C.c_int(17), C.byref(win)) < 0
+    assert lib.cumicro_p2p_window_create(C.c_int(0), C.c_int(1), None) == -1
+    assert lib.cumicro_p2p_allreduce_f64(None, fake, C.c_int(4), None) == -1 and b"window" in lib.cumicro_last_error()
+    assert lib.cumicro_p2p_allreduce_f64(None, fake, C.c_int(17), None) < 0
+    assert lib.cumicro_p2p_window_destroy(None) == 0
 
 
 def test_device_methods_refuse_cpu_arrays(built):

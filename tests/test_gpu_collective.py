@@ -119,3 +119,95 @@ def test_nccl_allreduce_through_the_c_abi_two_ranks(built, cuda):
         assert p.exitcode == 0
     for _, v in got:
         assert v == [3.0, 30.0, 1.0, 1.0]
+
+
+def _fused_args(built, cuda, n, seed):
+    import torch
+    from cumicro import fused
+    from cumicro.testing import arg_test_distribution, synthetic_states_fused
+    CMP = built.CMP if hasattr(built, "CMP") else built
+    st = synthetic_states_fused(n, seed=seed)
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in st.items()}
+    tps = CMP.ThermodynamicsParameters(np.float64)
+    blk3 = CMP.pack_icenuc(tps, ad=arg_test_distribution("kappa"), dust=CMP.DustType("Kaolinite"), hom_linear=True)
+    return (CMP.Microphysics1MParams(np.float64), CMP.Microphysics2MParams(np.float64), tps, blk3), [d[k] for k in fused.IN_NAMES]
+
+
+def test_p2p_window_single_rank_is_the_identity_and_the_fused_call_accepts_it(built, cuda):
+    """nranks = 1 runs the same exchange code against the rank's own window: sums unchanged, call counter advances, no timeout."""
+    import torch
+    from cumicro import collective, fused
+    win = collective.P2PWindow(0, 1)
+    buf = torch.tensor([1.5, -2.0, 3.25, 1e300], dtype=torch.float64, device=cuda)
+    for _ in range(5):                                  # both parities, repeatedly
+        win.all_reduce(buf)
+    torch.cuda.synchronize()
+    assert buf.cpu().tolist() == [1.5, -2.0, 3.25, 1e300]
+    params, cols = _fused_args(built, cuda, (1 << 16) + 3, seed=4)
+    a = fused.fused_1m2m_icenuc(*params, *cols)["diag"].cpu().numpy()
+    b = fused.fused_1m2m_icenuc(*params, *cols, p2p_window=win)["diag"].cpu().numpy()
+    assert np.array_equal(a, b)
+    assert win.status() == (6, 0)
+    with pytest.raises(ValueError):
+        fused.fused_1m2m_icenuc(*params, *cols, diagnostics=False, p2p_window=win)
+    win.destroy()
+
+
+def _p2p_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import cumicro
+    from cumicro import collective, fused
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # only to ship the 64-byte handles
+    win = collective.P2PWindow(rank, world).set_timeout(20.0).connect_with_torch_distributed()
+    res = []
+    for it in range(7):                                                # both parities; a fast rank may run ahead by one call
+        buf = torch.tensor([1.0 + rank + it, 10.0 * (rank + 1), 0.5, float(rank) * it], dtype=torch.float64, device=dev)
+        win.all_reduce(buf)
+        res.append(buf.cpu().numpy().tolist())
+    # the fused config-5 call with the exchange in its finish kernel == the slab sums added in rank order
+    n_global = (1 << 17) + 5
+    lo, hi = fused.slab_bounds(n_global, world, rank)
+    params, cols = _fused_args(cumicro.CMP, dev, n_global, seed=11)
+    cols = [c[lo:hi].contiguous() for c in cols]
+    own = fused.fused_1m2m_icenuc(*params, *cols, reduce=False)["diag"].cpu().numpy()
+    dom = fused.fused_1m2m_icenuc(*params, *cols, p2p_window=win)["diag"].cpu().numpy()
+    torch.cuda.synchronize()
+    box = [None] * world
+    dist.all_gather_object(box, own.tolist())
+    q.put((rank, res, dom.tolist(), box, win.status()))
+    dist.barrier()
+    win.destroy()
+    dist.destroy_process_group()
+
+
+def test_p2p_allreduce_and_fused_exchange_two_ranks(built, cuda):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, res, dom, box, status in got:
+        for it, v in enumerate(res):
+            assert v == [3.0 + 2 * it, 30.0, 1.0, float(it)]
+        expect = [box[0][k] + box[1][k] for k in range(4)]            # rank order, one addition: exact
+        assert dom == expect
+        assert status == (8, 0)
+    assert got[0][2] == got[1][2]                                     # bit-identical on both ranks
