@@ -1302,18 +1302,25 @@ function fused_tendencies(mp1::CMP.Microphysics1MParams, mp2::CMP.Microphysics2M
                           ρ::Col{FT}, T::Col{FT}, p::Col{FT}, w::Col{FT}, q_tot::Col{FT}, q_lcl::Col{FT}, q_icl::Col{FT},
                           q_rai::Col{FT}, q_sno::Col{FT}, n_lcl::Col{FT}, n_rai::Col{FT};
                           aps = mp2.warm_rain.air_properties, ap = nothing, ad = nothing, dust = nothing, koop = nothing,
-                          hom_linear = false, diagnostics = true) where {WR, FT <: FTs}
+                          hom_linear = false, diagnostics = true, window = nothing) where {WR, FT <: FTs}
     ins = (ρ, T, p, w, q_tot, q_lcl, q_icl, q_rai, q_sno, n_lcl, n_rai)
     n = same_length(ins...)
     out = ntuple(_ -> similar(ρ), 11)
+    window === nothing || diagnostics || throw(ArgumentError("window needs diagnostics = true"))
     diag = diagnostics ? CUDA.zeros(Float64, 4) : nothing
     b1, b2 = Ref(pack(FT, mp1, tps)), Ref(pack(FT, mp2, tps))
     b3 = Ref(pack_icenuc(FT, tps; aps, ap, ad, dust, koop, hom_linear))
     itab, otab = ptr_table(FT, ins), ptr_table(FT, out)
     GC.@preserve b1 b2 b3 itab otab begin
-        st = ccall((sym(:cumicro_fused_1m2m_icenuc, FT), libcumicro), Cint,
-            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{CuPtr{FT}}, Ptr{CuPtr{FT}}, CuPtr{Float64}, Ptr{Cvoid}),
-            b1, b2, b3, n, itab, otab, dev(Float64, diag), cur_stream())
+        if window === nothing
+            st = ccall((sym(:cumicro_fused_1m2m_icenuc, FT), libcumicro), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{CuPtr{FT}}, Ptr{CuPtr{FT}}, CuPtr{Float64}, Ptr{Cvoid}),
+                b1, b2, b3, n, itab, otab, dev(Float64, diag), cur_stream())
+        else   # diag = the DOMAIN sums: the exchange is the tail of the call's finish kernel (peer-memory stores over NVLink)
+            st = ccall((sym(:cumicro_fused_1m2m_icenuc_p2p, FT), libcumicro), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{CuPtr{FT}}, Ptr{CuPtr{FT}}, CuPtr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}),
+                b1, b2, b3, n, itab, otab, diag, window.handle, cur_stream())
+        end
     end
     check(st)
     names = (:dq_lcl_dt_1m, :dq_icl_dt_1m, :dq_rai_dt_1m, :dq_sno_dt_1m, :dq_lcl_dt_2m, :dn_lcl_dt_2m, :dq_rai_dt_2m,
@@ -1476,6 +1483,48 @@ function reduce_diagnostics!(diag::CuVector{Float64}; comm::Union{Ptr{Cvoid}, No
         comm, diag, length(diag), cur_stream())
     check(st)
     return diag
+end
+
+"""
+    P2PWindow(rank, nranks)            # rank is 0-based; allocates this rank's window on the current device
+    handle(win)::Vector{UInt8}         # 64 bytes to ship to the other ranks (MPI.Allgather, ...)
+    connect!(win, handles)             # handles: nranks x 64 bytes in rank order
+    reduce_diagnostics!(diag, win)     # in-place sum over the ranks, one single-block kernel, bit-identical on all ranks
+    destroy!(win)                      # after the last call has completed on every rank
+
+The same exchange as `reduce_diagnostics!(diag; comm)` without a library: peer-memory stores over NVLink / NVSwitch.
+`fused_tendencies(...; window = win)` does it inside its own finish kernel (no second launch).
+"""
+mutable struct P2PWindow
+    handle::Ptr{Cvoid}
+    rank::Int
+    nranks::Int
+    function P2PWindow(rank::Integer, nranks::Integer)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:cumicro_p2p_window_create, libcumicro), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}), rank, nranks, h))
+        return new(h[], rank, nranks)
+    end
+end
+function handle(win::P2PWindow)
+    raw = Vector{UInt8}(undef, 64)
+    check(ccall((:cumicro_p2p_window_handle, libcumicro), Cint, (Ptr{Cvoid}, Ptr{UInt8}), win.handle, raw))
+    return raw
+end
+function connect!(win::P2PWindow, handles::AbstractVector{UInt8})
+    length(handles) == 64 * win.nranks || throw(ArgumentError("expected $(win.nranks) handles of 64 bytes"))
+    raw = Vector{UInt8}(handles)
+    check(ccall((:cumicro_p2p_window_connect, libcumicro), Cint, (Ptr{Cvoid}, Ptr{UInt8}), win.handle, raw))
+    return win
+end
+function reduce_diagnostics!(diag::CuVector{Float64}, win::P2PWindow)
+    check(ccall((:cumicro_p2p_allreduce_f64, libcumicro), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Cint, Ptr{Cvoid}),
+        win.handle, diag, length(diag), cur_stream()))
+    return diag
+end
+function destroy!(win::P2PWindow)
+    win.handle == C_NULL || ccall((:cumicro_p2p_window_destroy, libcumicro), Cint, (Ptr{Cvoid},), win.handle)
+    win.handle = C_NULL
+    return nothing
 end
 
 end # module
