@@ -17,7 +17,9 @@
 #define CUMICRO_1M_BLOCK 128
 #endif
 #ifndef CUMICRO_1ML_BLOCK
-#define CUMICRO_1ML_BLOCK 1024
+#define CUMICRO_1ML_BLOCK 896   /* final body, 2^24 points, nsub 1: 1024x1 (64 registers, 456 B spilled) 1.037 ms, 896x1 (72, 248 B) 1.008, 768x1 (85, 208 B) 1.010, 640x1 (102, 100 B) 1.047 */
+#endif
+#ifndef CUMICRO_1ML_MINB
 #define CUMICRO_1ML_MINB 1
 #endif
 #ifndef CUMICRO_1MV_MINB
