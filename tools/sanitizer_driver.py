@@ -48,6 +48,12 @@ st = synthetic_states_fused(2003)
 cf = dc(st, fused.IN_NAMES)
 blk3 = CMP.pack_icenuc(tps, ad=arg_test_distribution("kappa"), dust=CMP.DustType("Kaolinite"), hom_linear=True)
 fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *cf); done.append("fused config-5 kernel + diagnostics finish")
+from cumicro import collective  # noqa: E402
+win = collective.P2PWindow(0, 1)           # single rank: the same exchange code against the rank's own window
+buf = torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64, device=dev)
+win.all_reduce(buf); win.all_reduce(buf)
+fused.fused_1m2m_icenuc(mp1, mp2, tps, blk3, *cf, p2p_window=win); done.append("peer-memory exchange window (stand-alone kernel + fused finish kernel, 1 rank)")
+torch.cuda.synchronize(); win.destroy()
 
 sp = synthetic_states_p3(700)
 d = {k: torch.from_numpy(v).to(dev) for k, v in sp.items()}
