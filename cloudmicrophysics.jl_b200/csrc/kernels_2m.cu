@@ -224,6 +224,15 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
             case 24: return launch_warm2m_tile<FT, 7, 1, 128, 5, 1>(kv, tabv, n, in, out, s, w);
             case 25: return launch_warm2m_tile<FT, 7, 1, 64, 12, 1>(kv, tabv, n, in, out, s, w);
             case 26: return launch_warm2m_tile<FT, 7, 1, 192, 4, 1>(kv, tabv, n, in, out, s, w);
+            // two points per thread share every constant load and the tile bookkeeping (1456 SASS instructions for two points against
+            // 864 for one, no spills at 96 registers) and are still slower — the body is not bound by instruction issue alone
+            // (tools/tune_2m_ab.py, round-robin, ms per 2^24 points): 128x6 PPT 1 0.398 | PPT 2: 128x3 0.452, 128x4 0.428, 128x5 0.414, 96x6 0.439
+            case 40: return launch_warm2m_tile<FT, 7, 1, 128, 3, 2>(kv, tabv, n, in, out, s, w);
+            case 41: return launch_warm2m_tile<FT, 7, 1, 128, 4, 2>(kv, tabv, n, in, out, s, w);
+            case 42: return launch_warm2m_tile<FT, 7, 1, 64, 6, 2>(kv, tabv, n, in, out, s, w);
+            case 43: return launch_warm2m_tile<FT, 7, 1, 64, 8, 2>(kv, tabv, n, in, out, s, w);
+            case 44: return launch_warm2m_tile<FT, 7, 1, 128, 5, 2>(kv, tabv, n, in, out, s, w);
+            case 47: return launch_warm2m_tile<FT, 7, 1, 96, 6, 2>(kv, tabv, n, in, out, s, w);
             default: break;
         }
     }
