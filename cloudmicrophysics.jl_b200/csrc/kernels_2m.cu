@@ -233,6 +233,12 @@ int bmt2m_warm_impl(const typename P<FT>::params_2m_warm* p, int64_t n, const FT
             case 43: return launch_warm2m_tile<FT, 7, 1, 64, 8, 2>(kv, tabv, n, in, out, s, w);
             case 44: return launch_warm2m_tile<FT, 7, 1, 128, 5, 2>(kv, tabv, n, in, out, s, w);
             case 47: return launch_warm2m_tile<FT, 7, 1, 96, 6, 2>(kv, tabv, n, in, out, s, w);
+            // other block sizes at one point per thread (same tool): 128x6 0.398 | 128x7 0.402, 128x8 0.411, 96x8 0.416, 96x9 0.419, 160x5 0.432, 224x4 0.436, 160x4 0.439
+            case 50: return launch_warm2m_tile<FT, 7, 1, 96, 8, 1>(kv, tabv, n, in, out, s, w);
+            case 51: return launch_warm2m_tile<FT, 7, 1, 160, 5, 1>(kv, tabv, n, in, out, s, w);
+            case 52: return launch_warm2m_tile<FT, 7, 1, 224, 4, 1>(kv, tabv, n, in, out, s, w);
+            case 53: return launch_warm2m_tile<FT, 7, 1, 96, 9, 1>(kv, tabv, n, in, out, s, w);
+            case 54: return launch_warm2m_tile<FT, 7, 1, 160, 4, 1>(kv, tabv, n, in, out, s, w);
             default: break;
         }
     }
