@@ -101,11 +101,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ALL_OUT: every output column is wanted (decided at launch): no per-column NULL test in the store sequence
+constexpr size_t kPipelinedStaticLimit = 40 * 1024;
+template <class FT, int NIN, int BLOCK> constexpr size_t pipelined_stage_bytes() { return sizeof(FT) * 2 * NIN * BLOCK; }
 template <class FT, int NIN, int NOUT, class F, int BLOCK, int MINB, bool ALL_OUT = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 pointwise_kernel_pipelined(const __grid_constant__ PointwiseArgs<FT, NIN, NOUT, F> a) {
     math_tables_init_for<BLOCK, F>();
-    __shared__ FT stage[2][NIN][BLOCK];
+    // the staging area: static up to 40 KB, dynamic above (one large block per SM, e.g. 896 x 7 doubles x 2 = 100 KB)
+    constexpr bool DYN = pipelined_stage_bytes<FT, NIN, BLOCK>() > kPipelinedStaticLimit;
+    extern __shared__ __align__(16) unsigned char pipelined_dyn_smem[];
+    __shared__ FT stage_static[DYN ? 1 : 2][DYN ? 1 : NIN][DYN ? 1 : BLOCK];
+    FT (*stage)[NIN][BLOCK] = DYN ? reinterpret_cast<FT (*)[NIN][BLOCK]>(pipelined_dyn_smem) : reinterpret_cast<FT (*)[NIN][BLOCK]>(&stage_static[0][0][0]);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * BLOCK;
     int64_t it = (int64_t)blockIdx.x * BLOCK + tid;
@@ -320,7 +326,13 @@ int launch_pointwise(const F& f, int64_t n, const FT* const (&in)[NIN], FT* cons
                 carveout_set[all_out] = true;
             }
             const int blocks = (int)std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)max_blocks);
-            kern<<<blocks, BLOCK, 0, stream>>>(a);
+            constexpr size_t stage_bytes = pipelined_stage_bytes<FT, NIN, BLOCK>();
+            constexpr size_t dyn = stage_bytes > kPipelinedStaticLimit ? stage_bytes : 0;
+            if (dyn) {   // every launch: function attributes are per device
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                if (e != cudaSuccess) return cmh::cuda_status(e, "pipelined: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+            }
+            kern<<<blocks, BLOCK, dyn, stream>>>(a);
             cmh::count_launch();
             return cmh::cuda_status(cudaGetLastError(), what);
         }

@@ -22,6 +22,9 @@
 #ifndef CUMICRO_1ML_MINB
 #define CUMICRO_1ML_MINB 1
 #endif
+#ifndef CUMICRO_1ML_PIPE
+#define CUMICRO_1ML_PIPE 0   /* inputs of the next grid-stride item fetched by cp.async while the current one is computed: 896x1 1.055 ms, 1024x1 1.149, 768x1 1.009 against 1.008 without (the exposed load latency is not what bounds it) */
+#endif
 #ifndef CUMICRO_1MV_MINB
 #define CUMICRO_1MV_MINB 8   /* verbose: 4 -> 1.75 ms, 6 -> 1.34, 8 -> 1.22; linavg: 3.07, 3.01, 2.94 */
 #endif
@@ -132,7 +135,7 @@ int bmt1m_launch(int mode, const typename P<FT>::params_1m* p, int64_t n, const 
 #if CUMICRO_1ML_TILED
         return launch_pointwise_tiled<FT, 7, 4, F, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB>(f, n, in, o4, s, "bmt1m_linavg launch");
 #else
-        return launch_pointwise<FT, 7, 4, F, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB, false>(f, n, in, o4, s, "bmt1m_linavg launch");
+        return launch_pointwise<FT, 7, 4, F, CUMICRO_1ML_BLOCK, CUMICRO_1ML_MINB, false, CUMICRO_1ML_PIPE != 0>(f, n, in, o4, s, "bmt1m_linavg launch");
 #endif
     }
 }
