@@ -23,6 +23,8 @@ VARIANTS = {
     "b512x2_s2": "-DCUMICRO_P3_BLOCK=512 -DCUMICRO_P3_MINB=2 -DCUMICRO_P3_SYNC=2",
     "b768x1_e1": "-DCUMICRO_P3_BLOCK=768 -DCUMICRO_P3_MINB=1 -DCUMICRO_P3_SYNC_EVERY=1",
     "b896x1_e1": "-DCUMICRO_P3_BLOCK=896 -DCUMICRO_P3_MINB=1 -DCUMICRO_P3_SYNC_EVERY=1",
+    "series4": "-DP3_SERIES_TEST_EVERY=4",
+    "base": "",
 }
 if len(sys.argv) > 2:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[2:]}
