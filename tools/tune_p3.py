@@ -24,6 +24,7 @@ VARIANTS = {
     "b768x1_e1": "-DCUMICRO_P3_BLOCK=768 -DCUMICRO_P3_MINB=1 -DCUMICRO_P3_SYNC_EVERY=1",
     "b896x1_e1": "-DCUMICRO_P3_BLOCK=896 -DCUMICRO_P3_MINB=1 -DCUMICRO_P3_SYNC_EVERY=1",
     "series4": "-DP3_SERIES_TEST_EVERY=4",
+    "divm": "-DP3_DIV_MARKSTEIN=1",
     "base": "",
 }
 if len(sys.argv) > 2:
