@@ -276,6 +276,12 @@ CM_HD float rcp_(float x) { return 1.0f / x; }
 // ---- exp: |x| <= 708 (callers' arguments are bounded; see exp_full_ otherwise) ---------------
 // x = (256 e + j) ln2/256 + r, |r| <= ln2/512;  exp(x) = 2^e * T[j] * (1 + expm1(r)).
 // 9 FP64 instructions, 1 LDS, ~5 integer: ln2/256 = L1 (21 bits, immediate, kf L1 exact) + L2F (full double, constant bank).
+#ifndef CM_EXP_ROT
+#define CM_EXP_ROT 1   /* 2M headline 0.3915 -> 0.3905 ms, P3 48.35 -> 48.18 ms per 2^20 points; same bits */
+#endif
+#ifndef CM_EXP_LEA
+#define CM_EXP_LEA 1   /* 2M headline 0.3994 -> 0.3920 ms, config 3 1.454 -> 1.442 ms, config 5 1.845 -> 1.839 ms; same bits */
+#endif
 CM_HD double exp_(double x) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
     // an FP64 instruction takes ONE non-register operand: the second constant of a two-constant fma comes from the
@@ -294,9 +300,24 @@ CM_HD double exp_(double x) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r;  // expm1(r)
+#if defined(__CUDA_ARCH__) && CM_EXP_ROT
+    unsigned off;   // byte offset of T[ki & 255]: a funnel shift (rotate by 3) + mask stay on the ALU pipe; `<< 3` becomes IMAD.SHL
+    asm("{.reg .b32 t; shf.l.wrap.b32 t, %1, %1, 3; and.b32 %0, t, 0x7f8;}" : "=r"(off) : "r"(ki));
+    const double T = bits2d(*reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(cm_sh_exp) + off));
+#else
     const double T = exp_tab(ki & 255);
+#endif
     const double y = fma(T, p, T);
+#if defined(__CUDA_ARCH__) && CM_EXP_LEA
+    // 2^(ki >> 8) onto the high word as an arithmetic shift, a shift and an add written in PTX: ptxas keeps them on the ALU pipe
+    // (SHF), while it turns the C expression below into IMAD.SHL + LOP3 + IMAD.IADD — and IMAD shares its issue path with the
+    // FP64 instructions this body is made of (the same integer result; measured, see CM_EXP_LEA)
+    int hi2;
+    asm("{.reg .s32 t; shr.s32 t, %1, 8; shl.b32 t, t, 20; add.s32 %0, t, %2;}" : "=r"(hi2) : "r"(ki), "r"(hi32(y)));
+    return mk64(hi2, lo32(y));
+#else
     return mk64(hi32(y) + (ki & ~255) * 4096, lo32(y));   // 2^(ki >> 8): one mask + one multiply-add on the high word
+#endif
 }
 // exp with the IEEE limits: gradual underflow into the subnormals, 0 below them, +Inf
 // above the range, NaN propagated.
