@@ -398,21 +398,22 @@ def main():
         step()
     barrier()
     # ---- timed region: EXACTLY K steps, CUDA events on the launching (current) stream -------------
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # Two events bracket the K launches; the timed region holds nothing but the K kernels, so the kernel's average launch duration is
+    # total / K.  (An event between every two launches — the earlier form — costs ~7 us per step: tools/launch_probe2.py.)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     launches0 = lib.cumicro_launch_count()
     with ClockSampler(local) as clocks:
         barrier()
         ev[0].record()
         for i in range(args.steps):
             step()
-            ev[i + 1].record()
+        ev[1].record()
         barrier()
     launches = lib.cumicro_launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[1])
     total_ms_max = max_over_ranks(total_ms)
     value = n * world * args.steps / (total_ms_max * 1e-3)
-    kernel_ms = float(np.mean(per_launch_ms))
+    kernel_ms = total_ms / args.steps
 
     # ---- FP64 pipe peak measured in place (same power / clock state as the leg it is compared with) -------------
     def fp64_probe():
