@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """What the measurement itself costs in bench.py's timed region: K = 20 back-to-back steps timed with (a) two events only,
-(b) an event between every two launches, (c) the in-process NVML sampler thread at 2 ms / 10 ms, (d) both."""
+(b) an event between every two launches, (c) the in-process NVML sampler thread (2 ms period), (d) both.
+B200, final tree: 0.395-0.400 | 0.402-0.403 | 0.397-0.400 | 0.399-0.403 ms per step: an event per launch costs ~7 us per step."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,15 +16,13 @@ cols = [torch.from_numpy(st[k]).to(dev) for k in B.KEYS]
 outs = [torch.empty_like(cols[0]) for _ in range(4)]
 mp = CMP.Microphysics2MParams(np.float64); tps = CMP.ThermodynamicsParameters(np.float64); scheme = BMT.Microphysics2Moment()
 step = lambda: BMT.bulk_microphysics_tendencies(scheme, mp, tps, *cols, out=outs)
-def run(k, per_step_events, sampler, period=0.002):
+def run(k, per_step_events, sampler):
     for _ in range(5): step()
     torch.cuda.synchronize()
     time.sleep(0.3)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
     ctx = B.ClockSampler(0) if sampler else None
-    if ctx:
-        ctx.period = period
-        ctx.__enter__()
+    if ctx: ctx.__enter__()
     ev[0].record()
     for i in range(k):
         step()
